@@ -1,0 +1,140 @@
+/*
+ * seald_b200.h — C-ABI of libseald_b200.so: the sm_100a implementation of SealD-NeRF's
+ * dynamic-scene render/train hot path.
+ *
+ * Every entry point replaces one pybind11 function (or fused group of them) of the reference's
+ * native extensions; the reference interface it stands in for is cited per function
+ * (paths relative to the reference checkout).
+ *
+ * Conventions (all functions):
+ *   - extern "C", plain pointers + sizes, no torch types.  All pointers are DEVICE pointers owned by
+ *     the caller ("caller allocates", like the reference: raymarching.py:205-208, grid.py:47-52).
+ *   - never allocate, never synchronise; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 = ok, negative = argument error (SEALD_E_*), positive = cudaError_t of the launch.
+ *   - dtype enum: SEALD_F32 = 0, SEALD_F16 = 1 (the reference dispatches on at::ScalarType).
+ */
+#ifndef SEALD_B200_H_
+#define SEALD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEALD_F32 0
+#define SEALD_F16 1
+
+#define SEALD_E_BADARG (-1)   /* null pointer / zero size where not allowed            */
+#define SEALD_E_UNSUPPORTED (-2) /* D / C / width / degree outside the supported set      */
+#define SEALD_E_ALIGN (-3)    /* pointer not aligned for the vector width the kernel uses */
+
+typedef void* seald_stream_t; /* cudaStream_t */
+
+/* Library/ABI version and the SM architecture the kernels were built for (100). */
+int seald_version(void);
+int seald_sm_arch(void);
+/* Human readable text for a negative status code (positive codes: cudaGetErrorString). */
+const char* seald_strerror(int status);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multiresolution hash / tiled grid encoder.
+ * Replaces grid_encode_forward / grid_encode_backward (gridencoder/src/gridencoder.h:12-13,
+ * kernels gridencoder/src/gridencoder.cu:88,249,344).
+ *   x01      [B, D] fp32, already mapped to [0,1]
+ *   table    [offsets[L], C]  dtype (fp16 or fp32)
+ *   offsets  [L+1] int32
+ *   out      [B, L*C] dtype — written directly in the layout GridEncoder.forward returns
+ *            (the reference writes [L,B,C] and permutes, grid.py:47,57)
+ *   dy_dx    [B, L, D, C] dtype or NULL
+ *   gridtype 0 = hash, 1 = tiled; interp 0 = linear, 1 = smoothstep
+ * ------------------------------------------------------------------------------------------------ */
+int seald_grid_encode_forward(const float* x01, const void* table, const int32_t* offsets, void* out, void* dy_dx,
+                              uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                              uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                              seald_stream_t stream);
+
+/* grad_out [B, L*C] dtype.  grad_table [offsets[L], C] of grad_table_dtype (fp16: half2 atomics like
+ * gridencoder.cu:325-331; fp32: float atomics) is ACCUMULATED into (caller pre-zeroes, grid.py:77).
+ * grad_x [B, D] fp32 or NULL.  If grad_x != NULL: uses dy_dx when given (gridencoder.cu:344-369), else
+ * recomputes the corner differences from `table` (fp32 accumulation). */
+int seald_grid_encode_backward(const void* grad_out, const float* x01, const void* table, const int32_t* offsets,
+                               void* grad_table, const void* dy_dx, float* grad_x,
+                               uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                               uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                               int grad_table_dtype, seald_stream_t stream);
+
+/* Debug/parity op: emits the uint32 table row index (before *C) of every (point, level, corner)
+ * [B, L, 2^D] and the per-level (scale, resolution) the device computed [L] each. */
+int seald_grid_debug_indices(const float* x01, const int32_t* offsets, uint32_t* indices, float* scales,
+                             uint32_t* resolutions, uint32_t B, uint32_t D, uint32_t L, float S, uint32_t H,
+                             uint32_t gridtype, int align_corners, seald_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray marching utilities.  Replace raymarching/src/raymarching.h:7-11.
+ * ------------------------------------------------------------------------------------------------ */
+int seald_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb6, uint32_t N,
+                             float min_near, float* nears, float* fars, seald_stream_t stream);
+int seald_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                       seald_stream_t stream);
+int seald_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, seald_stream_t stream);
+int seald_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, seald_stream_t stream);
+/* grid [n_bytes*8] fp32 -> bitfield [n_bytes]; bit i of byte n = grid[8n+i] > thresh. */
+int seald_packbits(const float* grid, uint32_t n_bytes, float thresh, uint8_t* bitfield, seald_stream_t stream);
+
+/* Training march.  Replaces march_rays_train (raymarching.h:13, raymarching.cu:312-490).
+ * Same contract: xyzs/dirs [M,3], deltas [M,2] (caller pre-zeroes), rays [N,3] = (ray id, offset, count),
+ * counter[2] += (samples, rays).  nears/fars may be NULL: then aabb6 must be given and the slab test of
+ * near_far_from_aabb (raymarching.cu:92-145) is fused in (optionally also written to nears_out/fars_out).
+ * Offsets are reserved with one atomic per CTA after a block prefix sum, so rays of one CTA are packed in
+ * ray order (the reference uses one atomic per ray, raymarching.cu:405-406). */
+int seald_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound,
+                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                           const float* nears, const float* fars, const float* aabb6, float min_near,
+                           float* nears_out, float* fars_out,
+                           float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                           const float* noises, seald_stream_t stream);
+
+/* Replaces composite_rays_train_forward/backward (raymarching.h:14-15, raymarching.cu:501-693). */
+int seald_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                       const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                       float* weights_sum, float* depth, float* image, seald_stream_t stream);
+int seald_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                        const float* rgbs, const float* deltas, const int32_t* rays,
+                                        const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                        float T_thresh, float* grad_sigmas, float* grad_rgbs, seald_stream_t stream);
+
+/* Inference march / composite.  Replace march_rays / composite_rays (raymarching.h:17-18,
+ * raymarching.cu:701-914).  n_alive_dev (optional, may be NULL): device int32 holding the live count;
+ * when given it overrides the host n_alive bound inside the kernel (threads >= *n_alive_dev exit), which
+ * lets run_cuda loop without the host-synced boolean-mask compaction (dnerf/renderer.py:372). */
+int seald_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                     const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                     uint32_t C, uint32_t H, const uint8_t* bitfield, const float* nears, const float* fars,
+                     float* xyzs, float* dirs, float* deltas, const float* noises, const int32_t* n_alive_dev,
+                     seald_stream_t stream);
+int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                         const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                         float* depth, float* image, const int32_t* n_alive_dev, seald_stream_t stream);
+/* Order-preserving compaction of rays_alive (entries >= 0 kept): out[0..*n_out) ; replaces
+ * `rays_alive = rays_alive[rays_alive >= 0]` (dnerf/renderer.py:372).  scratch: >= ceil(n/1024)+1 int32. */
+int seald_compact_alive(const int32_t* rays_alive, uint32_t n_alive, const int32_t* n_alive_dev, int32_t* out,
+                        int32_t* n_out_dev, int32_t* scratch, seald_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small encoders.  Replace freq_encode_forward/backward (freqencoder/src/freqencoder.h:7-10) and
+ * sh_encode_forward/backward (shencoder/src/shencoder.h:7-8); SH degree 1..4 (the D-NeRF setting).
+ * ------------------------------------------------------------------------------------------------ */
+int seald_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C, float* outputs,
+                              seald_stream_t stream);
+int seald_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t deg,
+                               uint32_t C, float* grad_inputs, seald_stream_t stream);
+int seald_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t degree,
+                            float* dy_dx, seald_stream_t stream);
+int seald_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree,
+                             const float* dy_dx, float* grad_inputs, seald_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEALD_B200_H_ */

@@ -1,0 +1,32 @@
+"""seald_nerf_b200 — B200-native (sm_100a) implementation of SealD-NeRF's dynamic-scene render/train hot path.
+
+The Python surface mirrors the reference's own packages (same names, arguments, error behaviour):
+
+    seald_nerf_b200.gridencoder.GridEncoder        <- gridencoder/grid.py
+    seald_nerf_b200.raymarching.*                  <- raymarching/raymarching.py
+    seald_nerf_b200.freqencoder.FreqEncoder        <- freqencoder/freq.py
+    seald_nerf_b200.shencoder.SHEncoder            <- shencoder/sphere_harmonics.py
+    seald_nerf_b200.ffmlp.FFMLP                    <- ffmlp/ffmlp.py
+    seald_nerf_b200.encoding.get_encoder           <- encoding.py
+    seald_nerf_b200.activation.trunc_exp           <- activation.py
+    seald_nerf_b200.dnerf.{renderer,network}       <- dnerf/renderer.py, dnerf/network.py
+    seald_nerf_b200.SealDNeRF.{renderer,network}   <- SealDNeRF/renderer.py, SealDNeRF/network.py
+    seald_nerf_b200.seal                           <- SealNeRF/seal_utils.py runtime mapping
+
+`install_aliases()` registers them under the reference's top-level import names (`import raymarching`,
+`from gridencoder import GridEncoder`, ...) so reference host code runs unchanged on top of this package.
+All compute goes through libseald_b200.so (include/seald_b200.h); there is no CPU fallback.
+"""
+import importlib
+import sys
+
+__version__ = "0.1.0"
+
+_ALIASES = ["gridencoder", "raymarching", "freqencoder", "shencoder", "ffmlp", "encoding", "activation"]
+
+
+def install_aliases():
+    """Make `import raymarching`, `from gridencoder import GridEncoder`, `from encoding import get_encoder` ...
+    resolve to this package (the drop-in seam of SURVEY.md §8b)."""
+    for name in _ALIASES:
+        sys.modules[name] = importlib.import_module("seald_nerf_b200." + name)

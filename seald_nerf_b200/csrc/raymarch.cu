@@ -1,0 +1,744 @@
+// raymarch.cu — occupancy-bitfield ray marching and alpha compositing for sm_100a.
+//
+// Integer/index results (Morton codes, bitfield bytes, per-ray sample counts) are bit-exact with the
+// reference's raymarching extension, and so are the fp32 sample positions: every floating-point expression
+// below keeps the operand order and literal types of the reference (raymarching/src/raymarching.cu:42-81
+// helpers, :108-144 slab test, :335-479 training march, :730-804 inference march, :516-576 / :620-681 /
+// :833-904 compositing) so that nvcc forms the same FMA contractions; the file must NOT be built with
+// --use_fast_math.  What differs is the parallel structure:
+//   * march_rays_train fuses the AABB slab test, and reserves output ranges with ONE atomic per warp after a
+//     warp prefix sum (ray-ordered packing inside a warp) instead of two atomics per ray;
+//   * rays[] rows are written in ray order (row n describes ray n), which makes the layout deterministic;
+//   * the inference kernels can take the live-ray count from device memory so the render loop needs no host
+//     synchronisation, and seald_compact_alive replaces the boolean-mask compaction.
+#include <limits>
+
+#include "common.cuh"
+
+namespace seald {
+
+__device__ __forceinline__ constexpr float SQRT3() { return 1.7320508075688772f; }
+__device__ __forceinline__ constexpr float RPI() { return 0.3183098861837907f; }
+
+__device__ __forceinline__ float signf(const float x) { return copysignf(1.0, x); }
+__device__ __forceinline__ void swapf(float& a, float& b) { float c = a; a = b; b = c; }
+
+// raymarching.cu:42-54
+__device__ __forceinline__ int mip_from_pos(const float x, const float y, const float z, const float max_cascade) {
+    const float mx = fmaxf(fabsf(x), fmaxf(fabs(y), fabs(z)));
+    int exponent;
+    frexpf(mx, &exponent);
+    return fminf(max_cascade - 1, fmaxf(0, exponent));
+}
+__device__ __forceinline__ int mip_from_dt(const float dt, const float H, const float max_cascade) {
+    const float mx = dt * H * 0.5;
+    int exponent;
+    frexpf(mx, &exponent);
+    return fminf(max_cascade - 1, fmaxf(0, exponent));
+}
+
+// raymarching.cu:56-81
+__host__ __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton3D_enc(uint32_t x, uint32_t y, uint32_t z) {
+    return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t morton3D_dec(uint32_t x) {
+    x = x & 0x49249249;
+    x = (x | (x >> 2)) & 0xc30c30c3;
+    x = (x | (x >> 4)) & 0x0f00f00f;
+    x = (x | (x >> 8)) & 0xff0000ff;
+    x = (x | (x >> 16)) & 0x0000ffff;
+    return x;
+}
+
+// raymarching.cu:108-144
+__device__ __forceinline__ void slab_test(const float ox, const float oy, const float oz, const float dx, const float dy,
+                                          const float dz, const float* __restrict__ aabb, const float min_near, float& near_o,
+                                          float& far_o) {
+    const float rdx = 1 / dx, rdy = 1 / dy, rdz = 1 / dz;
+    float near = (aabb[0] - ox) * rdx;
+    float far = (aabb[3] - ox) * rdx;
+    if (near > far) swapf(near, far);
+    float near_y = (aabb[1] - oy) * rdy;
+    float far_y = (aabb[4] - oy) * rdy;
+    if (near_y > far_y) swapf(near_y, far_y);
+    if (near > far_y || near_y > far) {
+        near_o = far_o = std::numeric_limits<float>::max();
+        return;
+    }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = (aabb[2] - oz) * rdz;
+    float far_z = (aabb[5] - oz) * rdz;
+    if (near_z > far_z) swapf(near_z, far_z);
+    if (near > far_z || near_z > far) {
+        near_o = far_o = std::numeric_limits<float>::max();
+        return;
+    }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    near_o = near;
+    far_o = far;
+}
+
+__global__ void k_near_far(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ aabb,
+                           const uint32_t N, const float min_near, float* nears, float* fars) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float* o = rays_o + (size_t)n * 3;
+    const float* d = rays_d + (size_t)n * 3;
+    float near, far;
+    slab_test(o[0], o[1], o[2], d[0], d[1], d[2], aabb, min_near, near, far);
+    nears[n] = near;
+    fars[n] = far;
+}
+
+// raymarching.cu:163-198
+__global__ void k_sph_from_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float radius, const uint32_t N,
+                               float* coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    rays_o += (size_t)n * 3;
+    rays_d += (size_t)n * 3;
+    coords += (size_t)n * 2;
+    const float ox = rays_o[0], oy = rays_o[1], oz = rays_o[2];
+    const float dx = rays_d[0], dy = rays_d[1], dz = rays_d[2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float B = ox * dx + oy * dy + oz * dz;
+    const float C = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-B + sqrtf(B * B - A * C)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2(sqrtf(x * x + z * z), y);
+    const float phi = atan2(z, x);
+    coords[0] = 2 * theta * RPI() - 1;
+    coords[1] = phi * RPI();
+}
+
+__global__ void k_morton3D(const int* __restrict__ coords, const uint32_t N, int* indices) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    coords += (size_t)n * 3;
+    indices[n] = morton3D_enc(coords[0], coords[1], coords[2]);
+}
+
+__global__ void k_morton3D_invert(const int* __restrict__ indices, const uint32_t N, int* coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    coords += (size_t)n * 3;
+    const int ind = indices[n];
+    coords[0] = morton3D_dec(ind >> 0);
+    coords[1] = morton3D_dec(ind >> 1);
+    coords[2] = morton3D_dec(ind >> 2);
+}
+
+// One thread packs 32 cells -> 4 bytes (one 128-byte coalesced read per 4 lanes), raymarching.cu:281-288.
+__global__ void k_packbits(const float* __restrict__ grid, const uint32_t n_bytes, const float thresh, uint8_t* __restrict__ bitfield) {
+    const uint32_t w = threadIdx.x + blockIdx.x * blockDim.x;  // 32-bit word of the bitfield
+    const uint32_t n_words = n_bytes / 4;
+    if (w < n_words) {
+        const float4* g = reinterpret_cast<const float4*>(grid) + (size_t)w * 8;
+        uint32_t bits = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) {
+            const float4 v = __ldg(g + i);
+            bits |= (v.x > thresh ? 1u : 0u) << (4 * i);
+            bits |= (v.y > thresh ? 1u : 0u) << (4 * i + 1);
+            bits |= (v.z > thresh ? 1u : 0u) << (4 * i + 2);
+            bits |= (v.w > thresh ? 1u : 0u) << (4 * i + 3);
+        }
+        reinterpret_cast<uint32_t*>(bitfield)[w] = bits;
+    } else {
+        // tail bytes (n_bytes % 4)
+        const uint32_t n = n_words * 4 + (w - n_words);
+        if (n >= n_bytes) return;
+        uint8_t bits = 0;
+        for (uint32_t i = 0; i < 8; i++) bits |= (grid[(size_t)n * 8 + i] > thresh) ? ((uint8_t)1 << i) : 0;
+        bitfield[n] = bits;
+    }
+}
+
+__global__ void k_packbits_bytes(const float* __restrict__ grid, const uint32_t N, const float thresh, uint8_t* bitfield) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    grid += (size_t)n * 8;
+    uint8_t bits = 0;
+#pragma unroll
+    for (uint8_t i = 0; i < 8; i++) bits |= (grid[i] > thresh) ? ((uint8_t)1 << i) : 0;
+    bitfield[n] = bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The per-ray state of the march (raymarching.cu:335-351)
+// ------------------------------------------------------------------------------------------------
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+};
+
+struct MarchConst {
+    float bound, dt_gamma, dt_min, dt_max, rH, H3;
+    uint32_t C, H;
+};
+
+__device__ __forceinline__ MarchConst make_march_const(const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t C,
+                                                        const uint32_t H) {
+    MarchConst mc;
+    mc.bound = bound;
+    mc.dt_gamma = dt_gamma;
+    mc.rH = 1 / (float)H;
+    mc.H3 = H * H * H;
+    mc.dt_min = 2 * SQRT3() / max_steps;
+    mc.dt_max = 2 * SQRT3() * (1 << (C - 1)) / H;
+    mc.C = C;
+    mc.H = H;
+    return mc;
+}
+
+// One probe of the occupancy grid at parameter t (raymarching.cu:360-379).  Returns occupancy; outputs the
+// clamped position, dt, and what the empty-space skip needs.
+struct Probe {
+    float x, y, z, dt, mip_bound;
+    int nx, ny, nz;
+};
+
+__device__ __forceinline__ bool probe_grid(const Ray& r, const MarchConst& mc, const uint8_t* __restrict__ grid, const float t, Probe& p) {
+    const float x = clampf(r.ox + t * r.dx, -mc.bound, mc.bound);
+    const float y = clampf(r.oy + t * r.dy, -mc.bound, mc.bound);
+    const float z = clampf(r.oz + t * r.dz, -mc.bound, mc.bound);
+
+    const float dt = clampf(t * mc.dt_gamma, mc.dt_min, mc.dt_max);
+
+    const int level = max(mip_from_pos(x, y, z, mc.C), mip_from_dt(dt, mc.H, mc.C));
+
+    const float mip_bound = fminf(scalbnf(1.0f, level), mc.bound);
+    const float mip_rbound = 1 / mip_bound;
+
+    const uint32_t H = mc.H;
+    const int nx = clampf(0.5 * (x * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+    const int ny = clampf(0.5 * (y * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+    const int nz = clampf(0.5 * (z * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+
+    const uint32_t index = level * mc.H3 + morton3D_enc(nx, ny, nz);
+    const bool occ = grid[index / 8] & (1 << (index % 8));
+    p.x = x; p.y = y; p.z = z; p.dt = dt; p.mip_bound = mip_bound;
+    p.nx = nx; p.ny = ny; p.nz = nz;
+    return occ;
+}
+
+// Skip to the next voxel (raymarching.cu:388-399).
+__device__ __forceinline__ float skip_voxel(const Ray& r, const MarchConst& mc, const Probe& p, float t) {
+    const float rH = mc.rH;
+    const float tx = (((p.nx + 0.5f + 0.5f * signf(r.dx)) * rH * 2 - 1) * p.mip_bound - p.x) * r.rdx;
+    const float ty = (((p.ny + 0.5f + 0.5f * signf(r.dy)) * rH * 2 - 1) * p.mip_bound - p.y) * r.rdy;
+    const float tz = (((p.nz + 0.5f + 0.5f * signf(r.dz)) * rH * 2 - 1) * p.mip_bound - p.z) * r.rdz;
+    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    do {
+        t += clampf(t * mc.dt_gamma, mc.dt_min, mc.dt_max);
+    } while (t < tt);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training march
+// ------------------------------------------------------------------------------------------------
+__global__ void k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+                                   const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t N, const uint32_t C,
+                                   const uint32_t H, const uint32_t M, const float* __restrict__ nears, const float* __restrict__ fars,
+                                   const float* __restrict__ aabb, const float min_near, float* __restrict__ nears_out,
+                                   float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                   float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter,
+                                   const float* __restrict__ noises) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool active = n < N;
+
+    Ray r;
+    float near = 0.f, far = 0.f, noise = 0.f;
+    if (active) {
+        const float* o = rays_o + (size_t)n * 3;
+        const float* d = rays_d + (size_t)n * 3;
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+        r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+        if (nears) {
+            near = nears[n];
+            far = fars[n];
+        } else {
+            slab_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, aabb, min_near, near, far);
+            if (nears_out) { nears_out[n] = near; fars_out[n] = far; }
+        }
+        noise = noises[n];
+    }
+    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+
+    float t0 = near;
+    t0 += clampf(t0 * dt_gamma, mc.dt_min, mc.dt_max) * noise;
+
+    // pass 1: count
+    float t = t0;
+    uint32_t num_steps = 0;
+    if (active) {
+        Probe p;
+        while (t < far && num_steps < max_steps) {
+            if (probe_grid(r, mc, grid, t, p)) {
+                num_steps++;
+                t += p.dt;
+            } else {
+                t = skip_voxel(r, mc, p, t);
+            }
+        }
+    }
+
+    // reserve the output range: warp prefix sum + one atomic per warp (raymarching.cu:405-406 does two per ray)
+    const uint32_t incl = warp_inclusive_scan(num_steps, lane);
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t warp_rays = __popc(__ballot_sync(0xffffffffu, active));
+    uint32_t base = 0;
+    if (lane == 0) {
+        base = atomicAdd(counter, warp_total);
+        atomicAdd(counter + 1, warp_rays);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!active) return;
+    const uint32_t point_index = base + incl - num_steps;
+
+    rays[n * 3] = n;
+    rays[n * 3 + 1] = point_index;
+    rays[n * 3 + 2] = num_steps;
+
+    if (num_steps == 0) return;
+    if (point_index + num_steps > M) return;
+
+    xyzs += (size_t)point_index * 3;
+    dirs += (size_t)point_index * 3;
+    deltas += (size_t)point_index * 2;
+
+    // pass 2: write
+    t = t0;
+    uint32_t step = 0;
+    float last_t = t;
+    Probe p;
+    while (t < far && step < num_steps) {
+        if (probe_grid(r, mc, grid, t, p)) {
+            xyzs[0] = p.x; xyzs[1] = p.y; xyzs[2] = p.z;
+            dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+            t += p.dt;
+            deltas[0] = p.dt;
+            deltas[1] = t - last_t;
+            last_t = t;
+            xyzs += 3; dirs += 3; deltas += 2;
+            step++;
+        } else {
+            t = skip_voxel(r, mc, p, t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compositing (training)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                      const int* __restrict__ rays, const uint32_t M, const uint32_t N, const float T_thresh,
+                                      float* weights_sum, float* depth, float* image) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    uint32_t index = rays[n * 3];
+    uint32_t offset = rays[n * 3 + 1];
+    uint32_t num_steps = rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) {
+        weights_sum[index] = 0;
+        depth[index] = 0;
+        image[index * 3] = 0;
+        image[index * 3 + 1] = 0;
+        image[index * 3 + 2] = 0;
+        return;
+    }
+    sigmas += offset;
+    rgbs += (size_t)offset * 3;
+    deltas += (size_t)offset * 2;
+
+    uint32_t step = 0;
+    float T = 1.0f;
+    float r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+    while (step < num_steps) {
+        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
+        const float weight = alpha * T;
+        r += weight * rgbs[0];
+        g += weight * rgbs[1];
+        b += weight * rgbs[2];
+        t += deltas[1];
+        d += weight * t;
+        ws += weight;
+        T *= 1.0f - alpha;
+        if (T < T_thresh) break;
+        sigmas++;
+        rgbs += 3;
+        deltas += 2;
+        step++;
+    }
+    weights_sum[index] = ws;
+    depth[index] = d;
+    image[index * 3] = r;
+    image[index * 3 + 1] = g;
+    image[index * 3 + 2] = b;
+}
+
+__global__ void k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
+                                      const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                      const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ image,
+                                      const uint32_t M, const uint32_t N, const float T_thresh, float* grad_sigmas, float* grad_rgbs) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    uint32_t index = rays[n * 3];
+    uint32_t offset = rays[n * 3 + 1];
+    uint32_t num_steps = rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;
+
+    grad_weights_sum += index;
+    grad_image += (size_t)index * 3;
+    weights_sum += index;
+    image += (size_t)index * 3;
+    sigmas += offset;
+    rgbs += (size_t)offset * 3;
+    deltas += (size_t)offset * 2;
+    grad_sigmas += offset;
+    grad_rgbs += (size_t)offset * 3;
+
+    uint32_t step = 0;
+    float T = 1.0f;
+    const float r_final = image[0], g_final = image[1], b_final = image[2], ws_final = weights_sum[0];
+    float r = 0, g = 0, b = 0, ws = 0;
+    while (step < num_steps) {
+        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
+        const float weight = alpha * T;
+        r += weight * rgbs[0];
+        g += weight * rgbs[1];
+        b += weight * rgbs[2];
+        ws += weight;
+        T *= 1.0f - alpha;
+        grad_rgbs[0] = grad_image[0] * weight;
+        grad_rgbs[1] = grad_image[1] * weight;
+        grad_rgbs[2] = grad_image[2] * weight;
+        grad_sigmas[0] = deltas[0] * (
+            grad_image[0] * (T * rgbs[0] - (r_final - r)) +
+            grad_image[1] * (T * rgbs[1] - (g_final - g)) +
+            grad_image[2] * (T * rgbs[2] - (b_final - b)) +
+            grad_weights_sum[0] * (1 - ws_final)
+        );
+        if (T < T_thresh) break;
+        sigmas++;
+        rgbs += 3;
+        deltas += 2;
+        grad_sigmas++;
+        grad_rgbs += 3;
+        step++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// inference march / composite
+// ------------------------------------------------------------------------------------------------
+__global__ void k_march_rays(uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
+                             const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float bound, const float dt_gamma,
+                             const uint32_t max_steps, const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid,
+                             const float* __restrict__ nears, const float* __restrict__ fars, float* xyzs, float* dirs, float* deltas,
+                             const float* __restrict__ noises, const int* __restrict__ n_alive_dev) {
+    if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+
+    const int index = rays_alive[n];
+    const float noise = noises ? noises[n] : 0.0f;
+
+    rays_o += (size_t)index * 3;
+    rays_d += (size_t)index * 3;
+    xyzs += (size_t)n * n_step * 3;
+    dirs += (size_t)n * n_step * 3;
+    deltas += (size_t)n * n_step * 2;
+
+    Ray r;
+    r.ox = rays_o[0]; r.oy = rays_o[1]; r.oz = rays_o[2];
+    r.dx = rays_d[0]; r.dy = rays_d[1]; r.dz = rays_d[2];
+    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+
+    float t = rays_t[index];
+    const float far = fars[index];
+
+    uint32_t step = 0;
+    t += clampf(t * dt_gamma, mc.dt_min, mc.dt_max) * noise;
+    float last_t = t;
+    Probe p;
+    while (t < far && step < n_step) {
+        if (probe_grid(r, mc, grid, t, p)) {
+            xyzs[0] = p.x; xyzs[1] = p.y; xyzs[2] = p.z;
+            dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+            t += p.dt;
+            deltas[0] = p.dt;
+            deltas[1] = t - last_t;
+            last_t = t;
+            xyzs += 3; dirs += 3; deltas += 2;
+            step++;
+        } else {
+            t = skip_voxel(r, mc, p, t);
+        }
+    }
+}
+
+__global__ void k_composite_rays(uint32_t n_alive, const uint32_t n_step, const float T_thresh, int* rays_alive, float* rays_t,
+                                 const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                 float* weights_sum, float* depth, float* image, const int* __restrict__ n_alive_dev) {
+    if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+
+    const int index = rays_alive[n];
+    sigmas += (size_t)n * n_step;
+    rgbs += (size_t)n * n_step * 3;
+    deltas += (size_t)n * n_step * 2;
+    rays_t += index;
+    weights_sum += index;
+    depth += index;
+    image += (size_t)index * 3;
+
+    float t = rays_t[0];
+    float weight_sum = weights_sum[0];
+    float d = depth[0];
+    float r = image[0];
+    float g = image[1];
+    float b = image[2];
+
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (deltas[0] == 0) break;
+        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
+        const float T = 1 - weight_sum;
+        const float weight = alpha * T;
+        weight_sum += weight;
+        t += deltas[1];
+        d += weight * t;
+        r += weight * rgbs[0];
+        g += weight * rgbs[1];
+        b += weight * rgbs[2];
+        if (T < T_thresh) break;
+        sigmas++;
+        rgbs += 3;
+        deltas += 2;
+        step++;
+    }
+    if (step < n_step) {
+        rays_alive[n] = -1;
+    } else {
+        rays_t[0] = t;
+    }
+    weights_sum[0] = weight_sum;
+    depth[0] = d;
+    image[0] = r;
+    image[1] = g;
+    image[2] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// order-preserving compaction of the alive list: three tiny kernels (count per tile, scan of tile totals,
+// scatter).  Tiles of 1024 entries.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kTile = 1024;
+
+__global__ void k_compact_count(const int* __restrict__ rays_alive, uint32_t n_alive, const int* __restrict__ n_alive_dev, int* __restrict__ tile_counts) {
+    if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
+    __shared__ uint32_t s_warp[32];
+    const uint32_t i = blockIdx.x * kTile + threadIdx.x;
+    const bool keep = i < n_alive && rays_alive[i] >= 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = s_warp[threadIdx.x];
+        v = warp_inclusive_scan(v, threadIdx.x);
+        if (threadIdx.x == 31) tile_counts[blockIdx.x] = v;
+    }
+}
+
+// single CTA: exclusive scan of tile counts in place; writes the total to n_out_dev
+__global__ void k_compact_scan(int* __restrict__ tile_counts, const uint32_t n_tiles, int* __restrict__ n_out_dev) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_tiles ? (uint32_t)tile_counts[i] : 0u;
+        const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+        uint32_t incl = warp_inclusive_scan(v, lane);
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t s = s_warp[lane];
+            s = warp_inclusive_scan(s, lane);
+            s_warp[lane] = s;
+        }
+        __syncthreads();
+        const uint32_t prefix = (w ? s_warp[w - 1] : 0u) + s_carry;
+        if (i < n_tiles) tile_counts[i] = (int)(prefix + incl - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = prefix + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out_dev = (int)s_carry;
+}
+
+__global__ void k_compact_scatter(const int* __restrict__ rays_alive, uint32_t n_alive, const int* __restrict__ n_alive_dev,
+                                  const int* __restrict__ tile_offsets, int* __restrict__ out) {
+    if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
+    __shared__ uint32_t s_warp[32];
+    const uint32_t i = blockIdx.x * kTile + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const int v = i < n_alive ? rays_alive[i] : -1;
+    const bool keep = v >= 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = s_warp[lane];
+        s = warp_inclusive_scan(s, lane);
+        s_warp[lane] = s;
+    }
+    __syncthreads();
+    if (keep) {
+        const uint32_t pos = (uint32_t)tile_offsets[blockIdx.x] + (w ? s_warp[w - 1] : 0u) + __popc(bal & ((1u << lane) - 1u));
+        out[pos] = v;
+    }
+}
+
+}  // namespace seald
+
+using namespace seald;
+
+extern "C" int seald_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb6, uint32_t N, float min_near,
+                                        float* nears, float* fars, seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays_o || !rays_d || !aabb6 || !nears || !fars) return SEALD_E_BADARG;
+    k_near_far<<<div_up(N, 128u), 128, 0, to_stream(stream)>>>(rays_o, rays_d, aabb6, N, min_near, nears, fars);
+    return launch_status();
+}
+
+extern "C" int seald_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays_o || !rays_d || !coords) return SEALD_E_BADARG;
+    k_sph_from_ray<<<div_up(N, 128u), 128, 0, to_stream(stream)>>>(rays_o, rays_d, radius, N, coords);
+    return launch_status();
+}
+
+extern "C" int seald_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!coords || !indices) return SEALD_E_BADARG;
+    k_morton3D<<<div_up(N, 256u), 256, 0, to_stream(stream)>>>(coords, N, indices);
+    return launch_status();
+}
+
+extern "C" int seald_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!coords || !indices) return SEALD_E_BADARG;
+    k_morton3D_invert<<<div_up(N, 256u), 256, 0, to_stream(stream)>>>(indices, N, coords);
+    return launch_status();
+}
+
+extern "C" int seald_packbits(const float* grid, uint32_t n_bytes, float thresh, uint8_t* bitfield, seald_stream_t stream) {
+    if (n_bytes == 0) return 0;
+    if (!grid || !bitfield) return SEALD_E_BADARG;
+    if (((uintptr_t)grid % 16 == 0) && ((uintptr_t)bitfield % 4 == 0)) {
+        const uint32_t n_thr = n_bytes / 4 + (n_bytes % 4);
+        k_packbits<<<div_up(n_thr, 256u), 256, 0, to_stream(stream)>>>(grid, n_bytes, thresh, bitfield);
+    } else {
+        k_packbits_bytes<<<div_up(n_bytes, 128u), 128, 0, to_stream(stream)>>>(grid, n_bytes, thresh, bitfield);
+    }
+    return launch_status();
+}
+
+extern "C" int seald_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound, float dt_gamma,
+                                      uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                      const float* fars, const float* aabb6, float min_near, float* nears_out, float* fars_out,
+                                      float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                                      seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays_o || !rays_d || !bitfield || !xyzs || !dirs || !deltas || !rays || !counter || !noises) return SEALD_E_BADARG;
+    if ((nears == nullptr) != (fars == nullptr)) return SEALD_E_BADARG;
+    if (!nears && !aabb6) return SEALD_E_BADARG;
+    if ((nears_out == nullptr) != (fars_out == nullptr)) return SEALD_E_BADARG;
+    if (C == 0 || H == 0 || max_steps == 0) return SEALD_E_BADARG;
+    // one warp per CTA while the ray count is small (spreads the latency-bound walks over all SMs)
+    const uint32_t threads = (N >= 4u * SEALD_NUM_SMS * 128u) ? 128u : 32u;
+    k_march_rays_train<<<div_up(N, threads), threads, 0, to_stream(stream)>>>(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M,
+                                                                              nears, fars, aabb6, min_near, nears_out, fars_out, xyzs, dirs,
+                                                                              deltas, rays, counter, noises);
+    return launch_status();
+}
+
+extern "C" int seald_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M,
+                                                  uint32_t N, float T_thresh, float* weights_sum, float* depth, float* image,
+                                                  seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays || !weights_sum || !depth || !image) return SEALD_E_BADARG;
+    if (M > 0 && (!sigmas || !rgbs || !deltas)) return SEALD_E_BADARG;
+    const uint32_t threads = (N >= 4u * SEALD_NUM_SMS * 128u) ? 128u : 32u;
+    k_composite_train_fwd<<<div_up(N, threads), threads, 0, to_stream(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    return launch_status();
+}
+
+extern "C" int seald_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                                   const float* rgbs, const float* deltas, const int32_t* rays, const float* weights_sum,
+                                                   const float* image, uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                                   float* grad_rgbs, seald_stream_t stream) {
+    if (N == 0 || M == 0) return 0;
+    if (!grad_weights_sum || !grad_image || !sigmas || !rgbs || !deltas || !rays || !weights_sum || !image || !grad_sigmas || !grad_rgbs)
+        return SEALD_E_BADARG;
+    const uint32_t threads = (N >= 4u * SEALD_NUM_SMS * 128u) ? 128u : 32u;
+    k_composite_train_bwd<<<div_up(N, threads), threads, 0, to_stream(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
+                                                                                 weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+    return launch_status();
+}
+
+extern "C" int seald_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                                const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                                const uint8_t* bitfield, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                const float* noises, const int32_t* n_alive_dev, seald_stream_t stream) {
+    if (n_alive == 0 || n_step == 0) return 0;
+    if (!rays_alive || !rays_t || !rays_o || !rays_d || !bitfield || !fars || !xyzs || !dirs || !deltas) return SEALD_E_BADARG;
+    (void)nears;
+    k_march_rays<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
+                                                                       max_steps, C, H, bitfield, nears, fars, xyzs, dirs, deltas, noises,
+                                                                       n_alive_dev);
+    return launch_status();
+}
+
+extern "C" int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t, const float* sigmas,
+                                    const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
+                                    const int32_t* n_alive_dev, seald_stream_t stream) {
+    if (n_alive == 0) return 0;
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return SEALD_E_BADARG;
+    k_composite_rays<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
+                                                                           weights_sum, depth, image, n_alive_dev);
+    return launch_status();
+}
+
+extern "C" int seald_compact_alive(const int32_t* rays_alive, uint32_t n_alive, const int32_t* n_alive_dev, int32_t* out, int32_t* n_out_dev,
+                                   int32_t* scratch, seald_stream_t stream) {
+    if (!n_out_dev) return SEALD_E_BADARG;
+    cudaStream_t st = to_stream(stream);
+    if (n_alive == 0) {
+        cudaError_t e = cudaMemsetAsync(n_out_dev, 0, sizeof(int32_t), st);
+        return (int)e;
+    }
+    if (!rays_alive || !out || !scratch) return SEALD_E_BADARG;
+    const uint32_t n_tiles = div_up(n_alive, kTile);
+    k_compact_count<<<n_tiles, kTile, 0, st>>>(rays_alive, n_alive, n_alive_dev, scratch);
+    k_compact_scan<<<1, 1024, 0, st>>>(scratch, n_tiles, n_out_dev);
+    k_compact_scatter<<<n_tiles, kTile, 0, st>>>(rays_alive, n_alive, n_alive_dev, scratch, out);
+    return launch_status();
+}

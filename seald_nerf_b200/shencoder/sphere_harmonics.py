@@ -1,0 +1,62 @@
+"""Drop-in `shencoder` package (reference: shencoder/sphere_harmonics.py:14-86) on libseald_b200.so.
+Degrees 1..4 (D-NeRF uses 4); higher degrees are outside the hot-path scope and raise."""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.amp import custom_bwd, custom_fwd
+
+from .. import _lib
+from .._lib import ptr
+
+
+class _sh_encoder(Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, inputs, degree, calc_grad_inputs=False):
+        inputs = inputs.contiguous()
+        B, input_dim = inputs.shape
+        output_dim = degree ** 2
+        outputs = torch.empty(B, output_dim, dtype=inputs.dtype, device=inputs.device)
+        dy_dx = torch.empty(B, input_dim * output_dim, dtype=inputs.dtype, device=inputs.device) if calc_grad_inputs else None
+        _lib.call("seald_sh_encode_forward", ptr(inputs), ptr(outputs), B, input_dim, int(degree), ptr(dy_dx), _lib.stream())
+        ctx.save_for_backward(inputs, dy_dx)
+        ctx.dims = [B, input_dim, degree]
+        return outputs
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad):
+        inputs, dy_dx = ctx.saved_tensors
+        if dy_dx is None:
+            return None, None, None
+        grad = grad.contiguous()
+        B, input_dim, degree = ctx.dims
+        grad_inputs = torch.empty_like(inputs)
+        _lib.call("seald_sh_encode_backward", ptr(grad), ptr(inputs), B, input_dim, int(degree), ptr(dy_dx), ptr(grad_inputs),
+                  _lib.stream())
+        return grad_inputs, None, None
+
+
+sh_encode = _sh_encoder.apply
+
+
+class SHEncoder(nn.Module):
+    def __init__(self, input_dim=3, degree=4):
+        super().__init__()
+        self.input_dim = input_dim
+        self.degree = degree
+        self.output_dim = degree ** 2
+        assert self.input_dim == 3, "SH encoder only support input dim == 3"
+        assert self.degree > 0 and self.degree <= 8, "SH encoder only supports degree in [1, 8]"
+        if self.degree > 4:
+            raise NotImplementedError("seald_b200 SHEncoder implements degree <= 4 (the D-NeRF/SealD setting)")
+
+    def __repr__(self):
+        return f"SHEncoder: input_dim={self.input_dim} degree={self.degree}"
+
+    def forward(self, inputs, size=1):
+        inputs = inputs / size
+        prefix_shape = list(inputs.shape[:-1])
+        inputs = inputs.reshape(-1, self.input_dim)
+        outputs = sh_encode(inputs, self.degree, inputs.requires_grad)
+        return outputs.reshape(prefix_shape + [self.output_dim])
