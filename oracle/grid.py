@@ -27,14 +27,22 @@ def make_offsets(input_dim=3, num_levels=16, level_dim=2, per_level_scale=2.0, b
     return np.array(offsets, dtype=np.int32), per_level_scale
 
 
-def level_params(L, S, H):
-    """gridencoder.cu:138-139 in fp32: scale = fma(exp2f(level*S), H, -1); resolution = ceil(scale)+1."""
+def level_params(L, S, H, scales=None):
+    """gridencoder.cu:138-139 in fp32: scale = fma(exp2f(level*S), H, -1); resolution = ceil(scale)+1.
+
+    On the GPU exp2f is the hardware ex2.approx (<= 2 ulp from libm), so for non-integer level*S the device value
+    of `scale` can differ from this libm-based one in the last bit.  Callers that need bit-exact indices pass the
+    per-level scales the device computed (seald_grid_debug_indices / tests/golden/grid_scales.npz) as `scales`.
+    """
     S = np.float32(S)
-    scales = np.empty(L, np.float32)
     res = np.empty(L, np.uint32)
+    if scales is None:
+        scales = np.empty(L, np.float32)
+        for l in range(L):
+            e = np.exp2(np.float32(np.float32(l) * S)).astype(np.float32)
+            scales[l] = np.float32(np.float64(e) * np.float64(H) - 1.0)
+    scales = np.asarray(scales, np.float32)
     for l in range(L):
-        e = np.exp2(np.float32(np.float32(l) * S)).astype(np.float32)
-        scales[l] = np.float32(np.float64(e) * np.float64(H) - 1.0)
         res[l] = np.uint32(np.ceil(scales[l])) + np.uint32(1)
     return scales, res
 
@@ -83,14 +91,14 @@ def _corner_weight(frac, idx, skip=None, start=1.0):
 
 
 def grid_encode_forward(x01, table, offsets, S, H, gridtype=0, align_corners=False, interp=0, want_dy_dx=False,
-                        want_indices=False):
+                        want_indices=False, scales=None):
     """x01 [B,D] fp32 in [0,1]; table [rows,C] (any float dtype) -> out [B, L*C] float64 (+ dy_dx [B,L,D,C], indices)."""
     x01 = np.ascontiguousarray(x01, np.float32)
     tab = np.asarray(table).astype(np.float64)
     B, D = x01.shape
     L = offsets.shape[0] - 1
     C = tab.shape[1]
-    scales, ress = level_params(L, S, H)
+    scales, ress = level_params(L, S, H, scales)
     oob = ((x01 < 0) | (x01 > 1)).any(1)
     out = np.zeros((B, L, C))
     dy_dx = np.zeros((B, L, D, C)) if want_dy_dx else None
@@ -129,14 +137,15 @@ def grid_encode_forward(x01, table, offsets, S, H, gridtype=0, align_corners=Fal
     return res[0] if len(res) == 1 else tuple(res)
 
 
-def grid_encode_backward(grad_out, x01, table, offsets, S, H, gridtype=0, align_corners=False, interp=0, want_grad_x=False):
+def grid_encode_backward(grad_out, x01, table, offsets, S, H, gridtype=0, align_corners=False, interp=0, want_grad_x=False,
+                         scales=None):
     """grad_out [B, L*C] -> grad_table [rows, C] float64 (gridencoder.cu:249-340), grad_x [B,D] (gridencoder.cu:344-369)."""
     x01 = np.ascontiguousarray(x01, np.float32)
     B, D = x01.shape
     L = offsets.shape[0] - 1
     C = np.asarray(table).shape[1]
     g = np.asarray(grad_out).astype(np.float64).reshape(B, L, C)
-    scales, ress = level_params(L, S, H)
+    scales, ress = level_params(L, S, H, scales)
     inb = ~((x01 < 0) | (x01 > 1)).any(1)
     grad_table = np.zeros((int(offsets[-1]), C))
     for l in range(L):
@@ -152,6 +161,6 @@ def grid_encode_backward(grad_out, x01, table, offsets, S, H, gridtype=0, align_
             np.add.at(grad_table, (rows[inb].astype(np.int64) + int(offsets[l])), (w[:, None] * g[:, l, :])[inb])
     if not want_grad_x:
         return grad_table
-    _, dy_dx = grid_encode_forward(x01, table, offsets, S, H, gridtype, align_corners, interp, want_dy_dx=True)
+    _, dy_dx = grid_encode_forward(x01, table, offsets, S, H, gridtype, align_corners, interp, want_dy_dx=True, scales=scales)
     grad_x = np.einsum("blc,bldc->bd", g, dy_dx)
     return grad_table, grad_x

@@ -111,7 +111,7 @@ def test_march_train_bit_exact(cuda_dev, cascade, bound, dt_gamma, perturb):
     noises = np.random.default_rng(5).random(N, dtype=np.float32) if perturb else np.zeros(N, np.float32)
     xo, do_, deo, rays_o_, cnt_o = orc.march_rays_train(ro, rd, bound, bits, cascade, H, nears, fars, noises, dt_gamma, max_steps)
     total = int(cnt_o[0])
-    assert total > 20000, "scene should produce a realistic number of samples"
+    assert total > 10000, "scene should produce a realistic number of samples"
     M = total + 128
 
     d = cuda_dev
@@ -126,7 +126,7 @@ def test_march_train_bit_exact(cuda_dev, cascade, bound, dt_gamma, perturb):
     # per-ray sample counts bit-exact, ray ids in order, ranges form an exact disjoint packing of [0, total)
     assert np.array_equal(rays_c[:, 0], np.arange(N))
     assert np.array_equal(rays_c[:, 2], rays_o_[:, 2])
-    order = np.argsort(rays_c[:, 1], kind="stable")
+    order = np.lexsort((rays_c[:, 2], rays_c[:, 1]))  # by offset, empty rays first among ties
     offs, cnts = rays_c[order, 1], rays_c[order, 2]
     assert offs[0] == 0 and np.array_equal(offs[1:], np.cumsum(cnts)[:-1]) and offs[-1] + cnts[-1] == total
     # samples bit-exact per ray
