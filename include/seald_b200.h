@@ -49,10 +49,11 @@ const char* seald_strerror(int status);
  *   dy_dx    [B, L, D, C] dtype or NULL
  *   gridtype 0 = hash, 1 = tiled; interp 0 = linear, 1 = smoothstep
  * ------------------------------------------------------------------------------------------------ */
+/*   b_dev    optional device int32: live row count; rows >= *b_dev are neither read nor written */
 int seald_grid_encode_forward(const float* x01, const void* table, const int32_t* offsets, void* out, void* dy_dx,
                               uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
                               uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
-                              seald_stream_t stream);
+                              const int32_t* b_dev, seald_stream_t stream);
 
 /* grad_out [B, L*C] dtype.  grad_table [offsets[L], C] of grad_table_dtype (fp16: half2 atomics like
  * gridencoder.cu:325-331; fp32: float atomics) is ACCUMULATED into (caller pre-zeroes, grid.py:77).
@@ -62,7 +63,7 @@ int seald_grid_encode_backward(const void* grad_out, const float* x01, const voi
                                void* grad_table, const void* dy_dx, float* grad_x,
                                uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
                                uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
-                               int grad_table_dtype, seald_stream_t stream);
+                               int grad_table_dtype, const int32_t* b_dev, seald_stream_t stream);
 
 /* Debug/parity op: emits the uint32 table row index (before *C) of every (point, level, corner)
  * [B, L, 2^D] and the per-level (scale, resolution) the device computed [L] each. */
@@ -133,6 +134,73 @@ int seald_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uin
                             float* dy_dx, seald_stream_t stream);
 int seald_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree,
                              const float* dy_dx, float* grad_inputs, seald_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused D-NeRF field (tensor-core MLPs, fp16 operands / fp32 accumulation).
+ * Replaces the per-layer cuBLAS path of NeRFNetwork.forward / .density (dnerf/network.py:123-208;
+ * SealDNeRF/network.py:125-212) and the freq / SH encoder launches feeding it.
+ * Weights are passed as HOST arrays of device pointers to fp16 nn.Linear.weight matrices [out][in]
+ * (row-major, 16-byte aligned): deform layer 0 zero-padded to [128][80], hidden [128][128], last [3][128];
+ * sigma {[64][32], [16][64]}; colour {[64][32] (column 31 zero), [64][64], [3][64]}.
+ * m_dev (optional): device int32 with the live sample count; rows >= *m_dev are skipped (they are zero padding
+ * whose outputs no ray reads, raymarching.py:205-207).
+ * ------------------------------------------------------------------------------------------------ */
+int seald_field_deform_forward(const float* xyz, const float* time_dev, const void* const* weights, int n_layers, uint32_t M,
+                               const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf /*[M,80] f16 or NULL*/,
+                               void* fwd_buf /*[n_layers-1,M,128] f16 or NULL*/, seald_stream_t stream);
+int seald_field_deform_backward(const float* grad_x01, const void* const* weights, int n_layers, uint32_t M, const int32_t* m_dev,
+                                float bound, const void* fwd_buf, void* bwd_buf /*[n_layers-1,M,128] f16*/, void* gout_buf /*[M,16] f16*/,
+                                seald_stream_t stream);
+int seald_field_heads_forward(const void* feat /*[M,32] f16*/, const float* dirs, const void* const* w_sigma, int n_sigma,
+                              const void* const* w_color, int n_color, uint32_t M, const int32_t* m_dev, float density_scale, float* sigma,
+                              float* rgb, void* hs /*[M,16] f16 or NULL*/, void* cin /*[M,32] f16*/, void* fwd_s /*[n_sigma-1,M,64]*/,
+                              void* fwd_c /*[n_color-1,M,64]*/, seald_stream_t stream);
+int seald_field_sigma_forward(const void* feat, const void* const* w_sigma, int n_sigma, uint32_t M, float density_scale, float* sigma,
+                              void* geo /*[M,15] f16 or NULL*/, seald_stream_t stream);
+int seald_field_heads_backward(const float* grad_sigma, const float* grad_rgb, const float* rgb, const void* hs, const void* const* w_sigma,
+                               int n_sigma, const void* const* w_color, int n_color, uint32_t M, const int32_t* m_dev, float density_scale,
+                               const void* fwd_s, const void* fwd_c, void* bwd_s, void* bwd_c, void* gout_s /*[M,16]*/, void* gout_c /*[M,16]*/,
+                               void* dfeat /*[M,32] f16*/, seald_stream_t stream);
+
+/* Weight gradients dW[N][K] += G[M][N]^T A[M][K] (fp16 in, fp32 atomics out); replaces the CUTLASS split-K GEMMs of
+ * ffmlp_backward (ffmlp/src/ffmlp.cu:801-877).  Up to 16 jobs per launch. */
+typedef struct {
+    const void* G; /* [M][ldg] f16 */
+    const void* A; /* [M][lda] f16 */
+    float* dW;     /* [n_real][ldw] f32, accumulated into */
+    int N, K;      /* GEMM dims padded to multiples of 16 (<= 128) */
+    int ldg, lda, ldw;
+    int n_real, k_real; /* rows / columns of dW actually written */
+} seald_wgrad_job;
+int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream);
+
+/* FFMLP-compatible fused MLP.  Replace ffmlp_forward / ffmlp_inference / ffmlp_backward (ffmlp/src/ffmlp.h:8-11).
+ * inputs [B,input_dim] f16 (input_dim % 16 == 0, <= 128), weights: flat f16 buffer (ffmlp.cu:632 layout),
+ * outputs [B,16] f16, fwd_buf [num_layers,B,hidden] f16 (NULL = inference), hidden in {16,32,64,128},
+ * activation 0 (relu) / output_activation 6 (none) as in ffmlp.py:89-96.  Backward accumulates fp32 weight gradients
+ * (layout of `weights`) into grad_weights and optionally writes grad_inputs [B,input_dim] f16. */
+int seald_ffmlp_forward(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
+                        uint32_t num_layers, uint32_t activation, uint32_t output_activation, void* fwd_buf, void* outputs,
+                        seald_stream_t stream);
+int seald_ffmlp_backward(const void* grad, const void* inputs, const void* weights, const void* fwd_buf, uint32_t B, uint32_t input_dim,
+                         uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                         void* bwd_buf, void* grad_inputs, float* grad_weights, seald_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training-step glue (replaces the torch element-wise kernels around the hot path: dnerf/utils.py:74-85 loss,
+ * torch.cuda.amp.GradScaler + torch.optim.Adam as configured in main_dnerf.py:129,136).
+ * ------------------------------------------------------------------------------------------------ */
+/* pred = image + (1 - ws) * bg (bg NULL = white); loss_sum += mean squared error (inv_count = 1/(3N) or 1/(3N*world));
+ * grad_image / grad_ws = d(loss_scale * mse)/d(image, ws). */
+int seald_mse_loss_bg(const float* image, const float* weights_sum, const float* bg, const float* gt, uint32_t N, float inv_count,
+                      const float* loss_scale, float* pred, float* loss_sum, float* grad_image, float* grad_ws, seald_stream_t stream);
+/* dst[rows][ld] f16 = src[rows][cols] f32, zero padded columns. */
+int seald_cast_pad_f16(const float* src, void* dst, uint32_t rows, uint32_t cols, uint32_t ld, seald_stream_t stream);
+int seald_grad_finite_check(const float* g, uint64_t n, int32_t* found_inf, seald_stream_t stream);
+int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
+                    const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad, seald_stream_t stream);
+int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff, int interval,
+                            seald_stream_t stream);
 
 #ifdef __cplusplus
 }

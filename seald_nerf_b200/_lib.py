@@ -17,8 +17,8 @@ _vp, _u32, _i32, _f32 = C.c_void_p, C.c_uint32, C.c_int, C.c_float
 
 # name -> argtypes (restype is always int except where noted)
 _SIGS = {
-    "seald_grid_encode_forward": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp],
-    "seald_grid_encode_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32, _vp],
+    "seald_grid_encode_forward": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp, _vp],
+    "seald_grid_encode_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32, _vp, _vp],
     "seald_grid_debug_indices": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _vp],
     "seald_near_far_from_aabb": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp],
     "seald_sph_from_ray": [_vp, _vp, _f32, _u32, _vp, _vp],
@@ -35,7 +35,34 @@ _SIGS = {
     "seald_freq_encode_backward": [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp],
     "seald_sh_encode_forward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp],
     "seald_sh_encode_backward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp],
+    "seald_field_deform_forward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "seald_field_deform_backward": [_vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
+    "seald_field_heads_forward": [_vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_field_sigma_forward": [_vp, _vp, _i32, _u32, _f32, _vp, _vp, _vp],
+    "seald_field_heads_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_mlp_wgrad": [_vp, _i32, _u32, _vp, _vp],
+    "seald_ffmlp_forward": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
+    "seald_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp],
+    "seald_mse_loss_bg": [_vp, _vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_cast_pad_f16": [_vp, _vp, _u32, _u32, _u32, _vp],
+    "seald_grad_finite_check": [_vp, C.c_uint64, _vp, _vp],
+    "seald_adam_step": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _i32, _vp],
+    "seald_loss_scale_update": [_vp, _vp, _vp, _f32, _f32, _i32, _vp],
 }
+
+
+class WgradJob(C.Structure):
+    """seald_wgrad_job of include/seald_b200.h."""
+    _fields_ = [("G", C.c_void_p), ("A", C.c_void_p), ("dW", C.c_void_p), ("N", C.c_int), ("K", C.c_int), ("ldg", C.c_int),
+                ("lda", C.c_int), ("ldw", C.c_int), ("n_real", C.c_int), ("k_real", C.c_int)]
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (const void* const*)."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
 
 _lib = None
 

@@ -1,0 +1,584 @@
+// field.cu — the D-NeRF field as fused tensor-core kernels (reference: dnerf/network.py:123-169 forward, :171-208
+// density; SealDNeRF/network.py:125-212 is the same computation).
+//
+//   deform   : freq(x) (63) || freq(t) (13)  ->  8 x Linear(128, bias=False) + ReLU  ->  dx (3);  x' = x + dx
+//   canonical: GridEncoder(x')  (grid_encoder.cu, separate launch: it is a gather, not a contraction)
+//   sigma    : 32 -> 64 -> 16 ; sigma = exp(h0) (fp32), geo = h[1:16]
+//   colour   : SH4(d) (16) || geo (15) -> 64 -> 64 -> 3 -> sigmoid
+//
+// The frequency / SH encodings are computed in the MLP input stage (they never exist in HBM unless saved for the
+// weight-gradient GEMMs), hidden activations stay in registers (mlp.cuh), trunc_exp / sigmoid are epilogues.
+// Numerics follow the reference under autocast: fp16 operands and layer outputs, fp32 accumulation (cuBLAS),
+// exp in fp32 on the fp16-rounded pre-activation (activation.py:5-17), sigmoid on the fp16 output.
+#include "encoders.cuh"
+#include "mlp.cuh"
+
+namespace seald {
+
+constexpr int kDeformW = 128, kDeformK0 = 80;  // 63 + 13 = 76 real inputs, padded to 80
+constexpr int kHeadW = 64, kHeadK0 = 32;       // sigma: 32 grid features; colour: 16 SH + 15 geo + 1 pad
+
+using DeformSmem = MlpSmem<kDeformW, kDeformK0>;
+using HeadSmem = MlpSmem<kHeadW, kHeadK0>;
+
+__device__ __forceinline__ float half_round(const float v) { return __half2float(__float2half_rn(v)); }
+
+// ---------------------------------------------------------------------------------------------------
+// deformation network forward
+//   xyz [M,3] fp32, time: device pointer to one float
+//   t0_mode: what happens when *time == 0 — 1: forward() semantics (dx := 0, network.py:140-141),
+//            2: density() semantics (x' = x but dx is still reported, network.py:188-190)
+//   outputs: deform [M,3] fp32 (fp16-rounded values), x01 [M,3] fp32 = (x' + bound) / (2 bound)  (grid.py:149)
+//   in_buf [M,80] fp16 (optional, training): the encoded input, for the first layer's weight gradient
+// ---------------------------------------------------------------------------------------------------
+template <bool SAVE>
+__global__ void __launch_bounds__(kMlpThreads, 2) k_deform_forward(const float* __restrict__ xyz, const float* __restrict__ time,
+                                                                   const MlpWeights mw, const int M, const int* __restrict__ m_dev,
+                                                                   const float bound, const int t0_mode, float* __restrict__ deform,
+                                                                   float* __restrict__ x01, __half* __restrict__ in_buf,
+                                                                   __half* __restrict__ fwd_buf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* s_in = reinterpret_cast<__half*>(smem_raw);
+    __half* s_w = s_in + DeformSmem::IN_HALVES;
+    float* s_out = reinterpret_cast<float*>(s_w + 2 * DeformSmem::W_HALVES);
+
+    const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;  // rows beyond the live sample count are skipped
+    const float tval = *time;
+    const bool t_is_zero = (tval == 0.0f);
+    const int n_tiles = (m_used + kTileRows - 1) / kTileRows;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileRows;
+        // ---- input stage: 80 columns per row, 128 rows -> each thread fills 40 entries
+        for (int i = threadIdx.x; i < kTileRows * kDeformK0; i += kMlpThreads) {
+            const int r = i / kDeformK0, c = i - r * kDeformK0;
+            const int row = row0 + r;
+            float v = 0.0f;
+            if (row < m_used) {
+                if (c < 63) {
+                    const float* x = xyz + (size_t)row * 3;
+                    const float xv[3] = {x[0], x[1], x[2]};
+                    v = freq_channel(xv, 3, c);
+                } else if (c < 76) {
+                    v = freq_channel(&tval, 1, c - 63);
+                }
+            }
+            const __half h = __float2half_rn(v);
+            s_in[r * DeformSmem::IN_STRIDE + c] = h;
+            if (SAVE && row < m_used) in_buf[(size_t)row * kDeformK0 + c] = h;
+        }
+        mlp_forward_tile<kDeformW, kDeformK0, SAVE>(mw, s_in, s_w, s_out, fwd_buf, M, row0);
+        // ---- epilogue: dx = fp16(z[0:3]); x' = x + dx; x01 = (x' + bound) / (2 bound)
+        if (threadIdx.x < kTileRows) {
+            const int row = row0 + threadIdx.x;
+            if (row < m_used) {
+                const float* z = s_out + threadIdx.x * kOutStride;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    float dx = half_round(z[d]);
+                    const float x = xyz[(size_t)row * 3 + d];
+                    float xp;
+                    if (t_is_zero) {
+                        xp = x;
+                        if (t0_mode == 1) dx = 0.0f;
+                    } else {
+                        xp = x + dx;
+                    }
+                    deform[(size_t)row * 3 + d] = dx;
+                    x01[(size_t)row * 3 + d] = (xp + bound) / (2 * bound);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// deformation network backward: g_out = grad_x01 / (2 bound) (fp16), no input gradient (xyz / t are leaves without grad)
+__global__ void __launch_bounds__(kMlpThreads, 2) k_deform_backward(const float* __restrict__ grad_x01, const MlpWeights mw, const int M,
+                                                                    const int* __restrict__ m_dev, const float bound,
+                                                                    const __half* __restrict__ fwd_buf, __half* __restrict__ bwd_buf,
+                                                                    __half* __restrict__ gout_buf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* s_g = reinterpret_cast<__half*>(smem_raw);  // [128][24]
+    __half* s_w = s_g + DeformSmem::IN_HALVES;           // keep the forward layout (s_in region is large enough)
+    const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
+    const int n_tiles = (m_used + kTileRows - 1) / kTileRows;
+    const float inv = 1.0f / (2 * bound);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileRows;
+        for (int i = threadIdx.x; i < kTileRows * 16; i += kMlpThreads) {
+            const int r = i >> 4, c = i & 15;
+            const int row = row0 + r;
+            float v = 0.0f;
+            if (row < m_used && c < 3) v = grad_x01[(size_t)row * 3 + c] * inv;
+            const __half h = __float2half_rn(v);
+            s_g[r * kGStride + c] = h;
+            if (row < m_used) gout_buf[(size_t)row * 16 + c] = h;
+        }
+        mlp_backward_tile<kDeformW, kDeformK0>(mw, s_g, s_w, fwd_buf, bwd_buf, nullptr, 0, 0, M, m_used, row0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sigma + colour heads forward
+//   feat [M,32] fp16 (grid features), dirs [M,3] fp32
+//   outputs: sigma [M] fp32 (= density_scale * exp(fp16(h0))), rgb [M,3] fp32 (fp16-rounded sigmoid)
+//   training buffers: hs [M,16] fp16 (sigma-net output), cin [M,32] fp16 (colour-net input),
+//                     fwd_s [1][M][64], fwd_c [2][M][64]
+// ---------------------------------------------------------------------------------------------------
+template <bool SAVE>
+__global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward(const __half* __restrict__ feat, const float* __restrict__ dirs,
+                                                                  const MlpWeights mw_s, const MlpWeights mw_c, const int M,
+                                                                  const int* __restrict__ m_dev, const float density_scale,
+                                                                  float* __restrict__ sigma, float* __restrict__ rgb,
+                                                                  __half* __restrict__ hs, __half* __restrict__ cin,
+                                                                  __half* __restrict__ fwd_s, __half* __restrict__ fwd_c) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* s_in = reinterpret_cast<__half*>(smem_raw);
+    __half* s_w = s_in + HeadSmem::IN_HALVES;
+    float* s_out = reinterpret_cast<float*>(s_w + 2 * HeadSmem::W_HALVES);
+    const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
+    const int n_tiles = (m_used + kTileRows - 1) / kTileRows;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileRows;
+        // ---- stage the grid features: 128 rows x 64 bytes
+        for (int i = threadIdx.x; i < kTileRows * 4; i += kMlpThreads) {
+            const int r = i >> 2, c = i & 3;
+            const int row = row0 + r;
+            __half* dst = s_in + r * HeadSmem::IN_STRIDE + c * 8;
+            if (row < m_used) cp_async16(dst, feat + (size_t)row * 32 + c * 8);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        cp_async_commit();
+        mlp_forward_tile<kHeadW, kHeadK0, SAVE>(mw_s, s_in, s_w, s_out, fwd_s, M, row0);
+        // ---- sigma epilogue + colour input stage (one thread per row)
+        if (threadIdx.x < kTileRows) {
+            const int r = threadIdx.x, row = row0 + r;
+            const float* z = s_out + r * kOutStride;
+            __half* ci = s_in + r * HeadSmem::IN_STRIDE;
+            if (row < m_used) {
+                __align__(16) __half hrow[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) hrow[c] = __float2half_rn(z[c]);
+                sigma[row] = density_scale * expf(__half2float(hrow[0]));
+                float sh[16];
+                const float* d = dirs + (size_t)row * 3;
+                sh_eval<4>(d[0], d[1], d[2], sh);
+#pragma unroll
+                for (int c = 0; c < 16; c++) ci[c] = __float2half_rn(sh[c]);
+#pragma unroll
+                for (int c = 1; c < 16; c++) ci[15 + c] = hrow[c];
+                ci[31] = __float2half_rn(0.0f);
+                if (SAVE) {
+                    *reinterpret_cast<uint4*>(hs + (size_t)row * 16) = *reinterpret_cast<const uint4*>(hrow);
+                    *reinterpret_cast<uint4*>(hs + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(hrow + 8);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        *reinterpret_cast<uint4*>(cin + (size_t)row * 32 + 8 * c) = *reinterpret_cast<const uint4*>(ci + 8 * c);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(ci + 8 * c) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        mlp_forward_tile<kHeadW, kHeadK0, SAVE>(mw_c, s_in, s_w, s_out, fwd_c, M, row0);
+        if (threadIdx.x < kTileRows) {
+            const int row = row0 + threadIdx.x;
+            if (row < m_used) {
+                const float* z = s_out + threadIdx.x * kOutStride;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float zh = half_round(z[c]);
+                    rgb[(size_t)row * 3 + c] = half_round(1.0f / (1.0f + expf(-zh)));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Density-only variant (NeRFNetwork.density, dnerf/network.py:193-206): sigma MLP only.
+__global__ void __launch_bounds__(kMlpThreads, 2) k_sigma_forward(const __half* __restrict__ feat, const MlpWeights mw_s, const int M,
+                                                                  const float density_scale, float* __restrict__ sigma,
+                                                                  __half* __restrict__ geo) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* s_in = reinterpret_cast<__half*>(smem_raw);
+    __half* s_w = s_in + HeadSmem::IN_HALVES;
+    float* s_out = reinterpret_cast<float*>(s_w + 2 * HeadSmem::W_HALVES);
+    const int n_tiles = (M + kTileRows - 1) / kTileRows;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileRows;
+        for (int i = threadIdx.x; i < kTileRows * 4; i += kMlpThreads) {
+            const int r = i >> 2, c = i & 3;
+            const int row = row0 + r;
+            __half* dst = s_in + r * HeadSmem::IN_STRIDE + c * 8;
+            if (row < M) cp_async16(dst, feat + (size_t)row * 32 + c * 8);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        cp_async_commit();
+        mlp_forward_tile<kHeadW, kHeadK0, false>(mw_s, s_in, s_w, s_out, nullptr, M, row0);
+        if (threadIdx.x < kTileRows) {
+            const int row = row0 + threadIdx.x;
+            if (row < M) {
+                const float* z = s_out + threadIdx.x * kOutStride;
+                sigma[row] = density_scale * expf(half_round(z[0]));
+                if (geo) {
+#pragma unroll
+                    for (int c = 1; c < 16; c++) geo[(size_t)row * 15 + c - 1] = __float2half_rn(z[c]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sigma + colour heads backward
+//   grad_sigma [M] fp32, grad_rgb [M,3] fp32 (already multiplied by the loss scale)
+//   outputs: dfeat [M,32] fp16, and for the weight-gradient GEMMs: gout_c [M,16], gout_s [M,16], bwd_c [2][M][64], bwd_s [1][M][64]
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMlpThreads, 2) k_heads_backward(const float* __restrict__ grad_sigma, const float* __restrict__ grad_rgb,
+                                                                   const float* __restrict__ rgb, const __half* __restrict__ hs,
+                                                                   const MlpWeights mw_s, const MlpWeights mw_c, const int M,
+                                                                   const int* __restrict__ m_dev, const float density_scale,
+                                                                   const __half* __restrict__ fwd_s, const __half* __restrict__ fwd_c,
+                                                                   __half* __restrict__ bwd_s, __half* __restrict__ bwd_c,
+                                                                   __half* __restrict__ gout_s, __half* __restrict__ gout_c,
+                                                                   __half* __restrict__ dfeat) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* s_in = reinterpret_cast<__half*>(smem_raw);  // colour dinput tile [128][40] / g_out tile [128][24]
+    __half* s_w = s_in + HeadSmem::IN_HALVES;
+    __half* s_g = reinterpret_cast<__half*>(s_w + 2 * HeadSmem::W_HALVES);  // [128][24] halves (fits in the s_out region)
+    const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
+    const int n_tiles = (m_used + kTileRows - 1) / kTileRows;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileRows;
+        // ---- colour g_out: d sigmoid
+        if (threadIdx.x < kTileRows) {
+            const int r = threadIdx.x, row = row0 + r;
+            __align__(16) __half g16[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) g16[c] = __float2half_rn(0.0f);
+            if (row < m_used) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float y = rgb[(size_t)row * 3 + c];
+                    g16[c] = __float2half_rn(grad_rgb[(size_t)row * 3 + c] * y * (1.0f - y));
+                }
+                *reinterpret_cast<uint4*>(gout_c + (size_t)row * 16) = *reinterpret_cast<const uint4*>(g16);
+                *reinterpret_cast<uint4*>(gout_c + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
+            }
+            *reinterpret_cast<uint4*>(s_g + r * kGStride) = *reinterpret_cast<const uint4*>(g16);
+            *reinterpret_cast<uint4*>(s_g + r * kGStride + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
+        }
+        // colour backward; dL/d(colour input) lands in the s_in tile
+        mlp_backward_tile<kHeadW, kHeadK0>(mw_c, s_g, s_w, fwd_c, bwd_c, s_in, HeadSmem::IN_STRIDE, 0, M, m_used, row0);
+        // ---- sigma g_out: trunc_exp backward on column 0, d geo on columns 1..15
+        if (threadIdx.x < kTileRows) {
+            const int r = threadIdx.x, row = row0 + r;
+            __align__(16) __half g16[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) g16[c] = __float2half_rn(0.0f);
+            if (row < m_used) {
+                const float h0 = __half2float(hs[(size_t)row * 16]);
+                g16[0] = __float2half_rn(grad_sigma[row] * density_scale * expf(fminf(fmaxf(h0, -15.0f), 15.0f)));
+#pragma unroll
+                for (int c = 1; c < 16; c++) g16[c] = s_in[r * HeadSmem::IN_STRIDE + 15 + c];
+                *reinterpret_cast<uint4*>(gout_s + (size_t)row * 16) = *reinterpret_cast<const uint4*>(g16);
+                *reinterpret_cast<uint4*>(gout_s + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
+            }
+            *reinterpret_cast<uint4*>(s_g + r * kGStride) = *reinterpret_cast<const uint4*>(g16);
+            *reinterpret_cast<uint4*>(s_g + r * kGStride + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
+        }
+        mlp_backward_tile<kHeadW, kHeadK0>(mw_s, s_g, s_w, fwd_s, bwd_s, dfeat, 32, row0, M, m_used, row0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradients: dW[N][K] (+)= sum_m G[m][N]^T * A[m][K]   (reference: CUTLASS split-K GEMMs, ffmlp.cu:801-877)
+// One CTA reduces a chunk of rows with mma.sync (fp32 accumulate) and adds its partial with fp32 atomics.
+//   G [M][ldg] fp16 (N columns used), A [M][lda] fp16 (K columns used); dW [n_real][ldw] fp32, rows >= n_real dropped,
+//   columns >= k_real dropped.  blockIdx.y selects the job.
+// ---------------------------------------------------------------------------------------------------
+struct WgradJob {
+    const __half* G;
+    const __half* A;
+    float* dW;
+    int N, K;        // padded GEMM dims (multiples of 16)
+    int ldg, lda, ldw;
+    int n_real, k_real;
+};
+constexpr int kMaxWgradJobs = 16;
+struct WgradJobs {
+    WgradJob j[kMaxWgradJobs];
+    int n_jobs;
+};
+
+constexpr int kWgChunk = 64;  // rows staged per step
+
+__global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M, const int* __restrict__ m_dev, const int rows_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const WgradJob jb = jobs.j[blockIdx.y];
+    const int N = jb.N, K = jb.K;
+    const int gs = N + kPad, as = K + kPad;  // smem strides
+    __half* s_gt[2];
+    __half* s_at[2];
+    s_gt[0] = reinterpret_cast<__half*>(smem_raw);
+    s_at[0] = s_gt[0] + kWgChunk * gs;
+    s_gt[1] = s_at[0] + kWgChunk * as;
+    s_at[1] = s_gt[1] + kWgChunk * gs;
+
+    const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
+    const int m_begin = blockIdx.x * rows_per_cta;
+    const int m_end = min(m_used, m_begin + rows_per_cta);
+    if (m_begin >= m_end) return;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    // output tiles: (N/16) x (K/8) of 16x8; warp w takes m-tile (w % MT) and every (8/ MT ... ) see below
+    const int MT = N / 16, NT = K / 8;
+    // distribute: tile id = mt * NT + nt ; warp handles ids with (id % 8 == warp) when MT < 8, else its own m-tile
+    // To keep registers bounded: each warp owns up to 16 n-tiles of one m-tile.
+    const int total = MT * NT;
+    const int per_warp = (total + 7) / 8;  // <= 16 for 128x128
+    float acc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+    const int first = warp * per_warp;  // contiguous range of tile ids: share an m-tile whenever per_warp divides NT
+
+    auto stage = [&](int buf, int m0) {
+        const int gchunks = N / 8, achunks = K / 8;
+        for (int i = threadIdx.x; i < kWgChunk * (gchunks + achunks); i += blockDim.x) {
+            const int r = i / (gchunks + achunks), c = i - r * (gchunks + achunks);
+            const int row = m0 + r;
+            if (c < gchunks) {
+                __half* dst = s_gt[buf] + r * gs + c * 8;
+                if (row < m_end) cp_async16(dst, jb.G + (size_t)row * jb.ldg + c * 8);
+                else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+            } else {
+                const int ca = c - gchunks;
+                __half* dst = s_at[buf] + r * as + ca * 8;
+                if (row < m_end) cp_async16(dst, jb.A + (size_t)row * jb.lda + ca * 8);
+                else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int n_steps = (m_end - m_begin + kWgChunk - 1) / kWgChunk;
+    stage(0, m_begin);
+    for (int s = 0; s < n_steps; s++) {
+        const int buf = s & 1;
+        cp_async_wait<0>();
+        __syncthreads();
+        if (s + 1 < n_steps) stage(buf ^ 1, m_begin + (s + 1) * kWgChunk);
+        const __half* gt = s_gt[buf];
+        const __half* at = s_at[buf];
+#pragma unroll
+        for (int kk = 0; kk < kWgChunk / 16; kk++) {  // k dimension = rows (samples)
+            int cur_mt = -1;
+            uint32_t a[4];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int id = first + i;
+                if (i < per_warp && id < total) {
+                    const int mt = id / NT, nt = id - mt * NT;
+                    if (mt != cur_mt) {
+                        // A operand = G^T: element (m = n_idx, k = sample) -> transposed load from [sample][n_idx]
+                        // matrices: m0 (rows n 0-7, k 0-7), m1 (rows n 8-15, k 0-7), m2 (n 0-7, k 8-15), m3 (n 8-15, k 8-15)
+                        ldmatrix_x4_trans(a, gt + (16 * kk + (lane & 7) + 8 * (lane >> 4)) * gs + 16 * mt + 8 * ((lane >> 3) & 1));
+                        cur_mt = mt;
+                    }
+                    // B operand: (k = sample, n = K idx): transposed load from [sample][k_idx]
+                    uint32_t b[2];
+                    {
+                        uint32_t r4[4];
+                        // x4 would fetch two n-tiles; fetch one n-tile (two matrices) via the x2 form encoded as x4 with duplicates
+                        ldmatrix_x4_trans(r4, at + (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * as + 8 * nt);
+                        b[0] = r4[0];
+                        b[1] = r4[1];
+                    }
+                    mma_16816(acc[i], a, b[0], b[1]);
+                }
+            }
+        }
+    }
+    // flush partial sums
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int id = first + i;
+        if (i < per_warp && id < total) {
+            const int mt = id / NT, nt = id - mt * NT;
+            const int r0 = 16 * mt + g, r1 = r0 + 8;
+            const int c0 = 8 * nt + 2 * t;
+            if (r0 < jb.n_real) {
+                if (c0 < jb.k_real) atomicAdd(jb.dW + (size_t)r0 * jb.ldw + c0, acc[i][0]);
+                if (c0 + 1 < jb.k_real) atomicAdd(jb.dW + (size_t)r0 * jb.ldw + c0 + 1, acc[i][1]);
+            }
+            if (r1 < jb.n_real) {
+                if (c0 < jb.k_real) atomicAdd(jb.dW + (size_t)r1 * jb.ldw + c0, acc[i][2]);
+                if (c0 + 1 < jb.k_real) atomicAdd(jb.dW + (size_t)r1 * jb.ldw + c0 + 1, acc[i][3]);
+            }
+        }
+    }
+}
+
+}  // namespace seald
+
+// ===================================================================================================
+// C-ABI
+// ===================================================================================================
+using namespace seald;
+
+namespace {
+
+int make_weights(MlpWeights& mw, const void* const* w, int n_layers, int k0, int k0_ld, int n_out) {
+    if (!w || n_layers < 2 || n_layers > kMaxLayers) return SEALD_E_BADARG;
+    for (int i = 0; i < n_layers; i++) {
+        if (!w[i] || ((uintptr_t)w[i] % 16) != 0) return w[i] ? SEALD_E_ALIGN : SEALD_E_BADARG;
+        mw.w[i] = reinterpret_cast<const __half*>(w[i]);
+    }
+    mw.n_layers = n_layers;
+    mw.k0 = k0;
+    mw.k0_ld = k0_ld;
+    mw.n_out = n_out;
+    return 0;
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+inline int tiles_grid(uint32_t M, int ctas_per_sm) {
+    const int n_tiles = (int)((M + kTileRows - 1) / kTileRows);
+    const int cap = SEALD_NUM_SMS * ctas_per_sm;
+    return n_tiles < cap ? (n_tiles > 0 ? n_tiles : 1) : cap;
+}
+
+}  // namespace
+
+extern "C" int seald_field_deform_forward(const float* xyz, const float* time_dev, const void* const* weights, int n_layers, uint32_t M,
+                                          const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf,
+                                          void* fwd_buf, seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!xyz || !time_dev || !deform || !x01) return SEALD_E_BADARG;
+    if ((in_buf == nullptr) != (fwd_buf == nullptr)) return SEALD_E_BADARG;
+    MlpWeights mw;
+    int rc = make_weights(mw, weights, n_layers, kDeformK0, kDeformK0, 3);
+    if (rc) return rc;
+    const size_t smem = DeformSmem::BYTES;
+    cudaStream_t st = to_stream(stream);
+    if (fwd_buf) {
+        if ((rc = set_smem(k_deform_forward<true>, smem))) return rc;
+        k_deform_forward<true><<<tiles_grid(M, 2), kMlpThreads, smem, st>>>(xyz, time_dev, mw, (int)M, m_dev, bound, t0_mode, deform, x01,
+                                                                           (__half*)in_buf, (__half*)fwd_buf);
+    } else {
+        if ((rc = set_smem(k_deform_forward<false>, smem))) return rc;
+        k_deform_forward<false><<<tiles_grid(M, 2), kMlpThreads, smem, st>>>(xyz, time_dev, mw, (int)M, m_dev, bound, t0_mode, deform, x01,
+                                                                            nullptr, nullptr);
+    }
+    return launch_status();
+}
+
+extern "C" int seald_field_deform_backward(const float* grad_x01, const void* const* weights, int n_layers, uint32_t M, const int32_t* m_dev,
+                                           float bound, const void* fwd_buf, void* bwd_buf, void* gout_buf, seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!grad_x01 || !fwd_buf || !bwd_buf || !gout_buf) return SEALD_E_BADARG;
+    MlpWeights mw;
+    int rc = make_weights(mw, weights, n_layers, kDeformK0, kDeformK0, 3);
+    if (rc) return rc;
+    const size_t smem = DeformSmem::BYTES;
+    if ((rc = set_smem(k_deform_backward, smem))) return rc;
+    k_deform_backward<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>(grad_x01, mw, (int)M, m_dev, bound, (const __half*)fwd_buf,
+                                                                                 (__half*)bwd_buf, (__half*)gout_buf);
+    return launch_status();
+}
+
+extern "C" int seald_field_heads_forward(const void* feat, const float* dirs, const void* const* w_sigma, int n_sigma, const void* const* w_color,
+                                         int n_color, uint32_t M, const int32_t* m_dev, float density_scale, float* sigma, float* rgb, void* hs,
+                                         void* cin, void* fwd_s, void* fwd_c, seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!feat || !dirs || !sigma || !rgb) return SEALD_E_BADARG;
+    const bool save = hs != nullptr;
+    if (save && (!cin || !fwd_s || !fwd_c)) return SEALD_E_BADARG;
+    MlpWeights ms, mc;
+    int rc = make_weights(ms, w_sigma, n_sigma, kHeadK0, kHeadK0, 16);
+    if (rc) return rc;
+    if ((rc = make_weights(mc, w_color, n_color, kHeadK0, kHeadK0, 3))) return rc;
+    const size_t smem = HeadSmem::BYTES;
+    cudaStream_t st = to_stream(stream);
+    if (save) {
+        if ((rc = set_smem(k_heads_forward<true>, smem))) return rc;
+        k_heads_forward<true><<<tiles_grid(M, 2), kMlpThreads, smem, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev, density_scale, sigma, rgb,
+                                                                          (__half*)hs, (__half*)cin, (__half*)fwd_s, (__half*)fwd_c);
+    } else {
+        if ((rc = set_smem(k_heads_forward<false>, smem))) return rc;
+        k_heads_forward<false><<<tiles_grid(M, 2), kMlpThreads, smem, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev, density_scale, sigma, rgb,
+                                                                           nullptr, nullptr, nullptr, nullptr);
+    }
+    return launch_status();
+}
+
+extern "C" int seald_field_sigma_forward(const void* feat, const void* const* w_sigma, int n_sigma, uint32_t M, float density_scale, float* sigma,
+                                         void* geo, seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!feat || !sigma) return SEALD_E_BADARG;
+    MlpWeights ms;
+    int rc = make_weights(ms, w_sigma, n_sigma, kHeadK0, kHeadK0, 16);
+    if (rc) return rc;
+    const size_t smem = HeadSmem::BYTES;
+    if ((rc = set_smem(k_sigma_forward, smem))) return rc;
+    k_sigma_forward<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>((const __half*)feat, ms, (int)M, density_scale, sigma, (__half*)geo);
+    return launch_status();
+}
+
+extern "C" int seald_field_heads_backward(const float* grad_sigma, const float* grad_rgb, const float* rgb, const void* hs,
+                                          const void* const* w_sigma, int n_sigma, const void* const* w_color, int n_color, uint32_t M,
+                                          const int32_t* m_dev, float density_scale, const void* fwd_s, const void* fwd_c, void* bwd_s, void* bwd_c,
+                                          void* gout_s, void* gout_c, void* dfeat, seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!grad_sigma || !grad_rgb || !rgb || !hs || !fwd_s || !fwd_c || !bwd_s || !bwd_c || !gout_s || !gout_c || !dfeat) return SEALD_E_BADARG;
+    MlpWeights ms, mc;
+    int rc = make_weights(ms, w_sigma, n_sigma, kHeadK0, kHeadK0, 16);
+    if (rc) return rc;
+    if ((rc = make_weights(mc, w_color, n_color, kHeadK0, kHeadK0, 3))) return rc;
+    const size_t smem = HeadSmem::BYTES;
+    if ((rc = set_smem(k_heads_backward, smem))) return rc;
+    k_heads_backward<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>(grad_sigma, grad_rgb, rgb, (const __half*)hs, ms, mc, (int)M, m_dev,
+                                                                                density_scale, (const __half*)fwd_s, (const __half*)fwd_c,
+                                                                                (__half*)bwd_s, (__half*)bwd_c, (__half*)gout_s, (__half*)gout_c,
+                                                                                (__half*)dfeat);
+    return launch_status();
+}
+
+extern "C" int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream) {
+    if (M == 0 || n_jobs == 0) return 0;
+    if (!jobs || n_jobs < 0 || n_jobs > kMaxWgradJobs) return SEALD_E_BADARG;
+    WgradJobs js;
+    js.n_jobs = n_jobs;
+    int maxNK = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        const seald_wgrad_job& a = jobs[i];
+        if (!a.G || !a.A || !a.dW) return SEALD_E_BADARG;
+        if (a.N % 16 || a.K % 16 || a.N <= 0 || a.K <= 0 || a.N > 128 || a.K > 128 || a.ldg % 8 || a.lda % 8) return SEALD_E_UNSUPPORTED;
+        if (((uintptr_t)a.G % 16) || ((uintptr_t)a.A % 16)) return SEALD_E_ALIGN;
+        WgradJob& j = js.j[i];
+        j.G = (const __half*)a.G; j.A = (const __half*)a.A; j.dW = a.dW;
+        j.N = a.N; j.K = a.K; j.ldg = a.ldg; j.lda = a.lda; j.ldw = a.ldw; j.n_real = a.n_real; j.k_real = a.k_real;
+        if (a.N + a.K > maxNK) maxNK = a.N + a.K;
+    }
+    const size_t smem = (size_t)2 * kWgChunk * (maxNK + 2 * kPad) * sizeof(__half);
+    int rc = set_smem(k_wgrad, smem);
+    if (rc) return rc;
+    // rows per CTA: ~4 waves over all jobs, at least 512 rows so the atomic flush is amortised
+    uint32_t ctas_x = (4u * SEALD_NUM_SMS + n_jobs - 1) / n_jobs;
+    uint32_t rows = div_up(M, ctas_x);
+    rows = div_up(rows < 512u ? 512u : rows, (uint32_t)kWgChunk) * kWgChunk;
+    dim3 grid(div_up(M, rows), n_jobs);
+    k_wgrad<<<grid, 256, smem, to_stream(stream)>>>(js, (int)M, m_dev, (int)rows);
+    return launch_status();
+}

@@ -139,13 +139,14 @@ __global__ void __launch_bounds__(256) k_grid_forward(const float* __restrict__ 
                                                       const int* __restrict__ offsets, T* __restrict__ outputs,
                                                       T* __restrict__ dy_dx, const uint32_t B, const uint32_t L,
                                                       const float S, const uint32_t H, const uint32_t gridtype,
-                                                      const bool align_corners, const uint32_t interp) {
+                                                      const bool align_corners, const uint32_t interp, const int* __restrict__ b_dev) {
     __shared__ LevelParams s_lp[kMaxLevels];
     if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H);
     __syncthreads();
+    const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;  // live rows
 
     constexpr uint32_t NC = 1u << D;
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < Bn; b += gridDim.x * blockDim.x) {
         float x[D];
         bool oob = false;
 #pragma unroll
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) k_grid_backward(const T* __restrict__ gra
                                                        const uint32_t B, const uint32_t L, const float S, const uint32_t H,
                                                        const uint32_t gridtype, const bool align_corners,
                                                        const uint32_t interp, const uint32_t smem_rows_max,
-                                                       const uint32_t points_per_cta) {
+                                                       const uint32_t points_per_cta, const int* __restrict__ b_dev) {
     extern __shared__ float s_acc[];  // [hashmap_size * C] when the level is privatised
     const uint32_t level = blockIdx.y;
     const LevelParams lp = make_level(offsets, level, S, H);
@@ -315,8 +316,10 @@ __global__ void __launch_bounds__(256) k_grid_backward(const T* __restrict__ gra
     }
     TG* gl = grad_table + (size_t)lp.offset * C;
 
+    const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;  // live rows
     const uint32_t b_begin = blockIdx.x * points_per_cta;
-    const uint32_t b_end = min(B, b_begin + points_per_cta);
+    const uint32_t b_end = min(Bn, b_begin + points_per_cta);
+    if (b_begin >= b_end) return;
     // all lanes of a warp iterate together (warp_aggregate needs the full warp)
     for (uint32_t b0 = b_begin + (threadIdx.x & ~31u); b0 < b_end; b0 += blockDim.x) {
         const uint32_t b = b0 + lane;
@@ -380,12 +383,14 @@ __global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* 
                                                                        const T* __restrict__ table, const int* __restrict__ offsets,
                                                                        float* __restrict__ grad_x, const uint32_t B, const uint32_t L,
                                                                        const float S, const uint32_t H, const uint32_t gridtype,
-                                                                       const bool align_corners, const uint32_t interp) {
+                                                                       const bool align_corners, const uint32_t interp,
+                                                                       const int* __restrict__ b_dev) {
     __shared__ LevelParams s_lp[kMaxLevels];
     if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H);
     __syncthreads();
+    const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;
     constexpr uint32_t NC = 1u << D;
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < Bn; b += gridDim.x * blockDim.x) {
         float x[D];
         bool oob = false;
 #pragma unroll
@@ -440,9 +445,10 @@ __global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* 
 // gridencoder.cu:344-369 with fp32 accumulation and the [B, L*C] grad layout.
 template <typename T, uint32_t D, uint32_t C>
 __global__ void k_grid_input_backward_dydx(const T* __restrict__ grad, const T* __restrict__ dy_dx, float* __restrict__ grad_x,
-                                           const uint32_t B, const uint32_t L) {
+                                           const uint32_t B, const uint32_t L, const int* __restrict__ b_dev) {
     const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
-    if (t >= B * D) return;
+    const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;
+    if (t >= Bn * D) return;
     const uint32_t b = t / D;
     const uint32_t d = t - b * D;
     const T* dy = dy_dx + (size_t)b * L * D * C;
@@ -486,7 +492,7 @@ __global__ void k_grid_debug_indices(const float* __restrict__ inputs, const int
 // ---- host dispatch ------------------------------------------------------------------------------
 template <typename T, uint32_t D, uint32_t C>
 int launch_forward(const float* x, const void* table, const int* offsets, void* out, void* dy_dx, uint32_t B, uint32_t L, float S,
-                   uint32_t H, uint32_t gridtype, bool align, uint32_t interp, cudaStream_t st) {
+                   uint32_t H, uint32_t gridtype, bool align, uint32_t interp, const int* b_dev, cudaStream_t st) {
     constexpr uint32_t G16 = 16 / (C * sizeof(T));  // levels per 16-byte output store
     constexpr uint32_t G = (D <= 3 && G16 >= 2 && G16 <= 4) ? G16 : 1;
     const uint32_t threads = 256;
@@ -494,36 +500,36 @@ int launch_forward(const float* x, const void* table, const int* offsets, void* 
     if constexpr (G > 1) {
         const bool vec_ok = (L % G) == 0 && ((L * C * sizeof(T)) % 16 == 0) && ((uintptr_t)out % 16 == 0);
         if (vec_ok) {
-            if (dy_dx) k_grid_forward<T, D, C, G, true><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp);
-            else k_grid_forward<T, D, C, G, false><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp);
+            if (dy_dx) k_grid_forward<T, D, C, G, true><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp, b_dev);
+            else k_grid_forward<T, D, C, G, false><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp, b_dev);
             return launch_status();
         }
     }
-    if (dy_dx) k_grid_forward<T, D, C, 1, true><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp);
-    else k_grid_forward<T, D, C, 1, false><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp);
+    if (dy_dx) k_grid_forward<T, D, C, 1, true><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp, b_dev);
+    else k_grid_forward<T, D, C, 1, false><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp, b_dev);
     return launch_status();
 }
 
 template <typename T, uint32_t D>
 int dispatch_forward_C(uint32_t C, const float* x, const void* table, const int* offsets, void* out, void* dy_dx, uint32_t B, uint32_t L,
-                       float S, uint32_t H, uint32_t gridtype, bool align, uint32_t interp, cudaStream_t st) {
+                       float S, uint32_t H, uint32_t gridtype, bool align, uint32_t interp, const int* b_dev, cudaStream_t st) {
     switch (C) {
-        case 1: return launch_forward<T, D, 1>(x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, st);
-        case 2: return launch_forward<T, D, 2>(x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, st);
-        case 4: return launch_forward<T, D, 4>(x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, st);
-        case 8: return launch_forward<T, D, 8>(x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, st);
+        case 1: return launch_forward<T, D, 1>(x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 2: return launch_forward<T, D, 2>(x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 4: return launch_forward<T, D, 4>(x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 8: return launch_forward<T, D, 8>(x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, b_dev, st);
         default: return SEALD_E_UNSUPPORTED;
     }
 }
 
 template <typename T>
 int dispatch_forward_D(uint32_t D, uint32_t C, const float* x, const void* table, const int* offsets, void* out, void* dy_dx, uint32_t B,
-                       uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align, uint32_t interp, cudaStream_t st) {
+                       uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align, uint32_t interp, const int* b_dev, cudaStream_t st) {
     switch (D) {
-        case 2: return dispatch_forward_C<T, 2>(C, x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, st);
-        case 3: return dispatch_forward_C<T, 3>(C, x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, st);
-        case 4: return dispatch_forward_C<T, 4>(C, x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, st);
-        case 5: return dispatch_forward_C<T, 5>(C, x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, st);
+        case 2: return dispatch_forward_C<T, 2>(C, x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 3: return dispatch_forward_C<T, 3>(C, x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 4: return dispatch_forward_C<T, 4>(C, x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 5: return dispatch_forward_C<T, 5>(C, x, table, offsets, out, dy_dx, B, L, S, H, gridtype, align, interp, b_dev, st);
         default: return SEALD_E_UNSUPPORTED;
     }
 }
@@ -533,7 +539,7 @@ constexpr uint32_t kBwdSmemBytes = 160 * 1024;  // privatised accumulator budget
 template <typename T, typename TG, uint32_t D, uint32_t C>
 int launch_backward(const void* grad, const float* x, const void* table, const int* offsets, void* grad_table, const void* dy_dx,
                     float* grad_x, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align, uint32_t interp,
-                    cudaStream_t st) {
+                    const int* b_dev, cudaStream_t st) {
     auto kern = k_grid_backward<T, TG, D, C, true>;
     auto kern_direct = k_grid_backward<T, TG, D, C, false>;
     static bool attr_set = false;
@@ -549,20 +555,20 @@ int launch_backward(const void* grad, const float* x, const void* table, const i
     chunks = div_up(B, ppc);
     const uint32_t smem_rows_max = kBwdSmemBytes / (C * sizeof(float));
     dim3 grid(chunks, L);
-    kern<<<grid, 256, kBwdSmemBytes, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, smem_rows_max, ppc);
+    kern<<<grid, 256, kBwdSmemBytes, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, smem_rows_max, ppc, b_dev);
     int rc = launch_status();
     if (rc) return rc;
     // direct (warp-aggregated atomics) levels: small chunks, no shared memory, full occupancy
     const uint32_t ppc_d = 1024;
     dim3 grid_d(div_up(B, ppc_d), L);
-    kern_direct<<<grid_d, 256, 0, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, smem_rows_max, ppc_d);
+    kern_direct<<<grid_d, 256, 0, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, smem_rows_max, ppc_d, b_dev);
     rc = launch_status();
     if (rc) return rc;
     if (grad_x) {
         if (dy_dx) {
-            k_grid_input_backward_dydx<T, D, C><<<div_up(B * D, 256u), 256, 0, st>>>((const T*)grad, (const T*)dy_dx, grad_x, B, L);
+            k_grid_input_backward_dydx<T, D, C><<<div_up(B * D, 256u), 256, 0, st>>>((const T*)grad, (const T*)dy_dx, grad_x, B, L, b_dev);
         } else {
-            k_grid_input_backward_recompute<T, D, C><<<div_up(B, 256u), 256, 0, st>>>((const T*)grad, x, (const T*)table, offsets, grad_x, B, L, S, H, gridtype, align, interp);
+            k_grid_input_backward_recompute<T, D, C><<<div_up(B, 256u), 256, 0, st>>>((const T*)grad, x, (const T*)table, offsets, grad_x, B, L, S, H, gridtype, align, interp, b_dev);
         }
         rc = launch_status();
     }
@@ -572,12 +578,12 @@ int launch_backward(const void* grad, const float* x, const void* table, const i
 template <typename T, typename TG, uint32_t D>
 int dispatch_backward_C(uint32_t C, const void* grad, const float* x, const void* table, const int* offsets, void* grad_table,
                         const void* dy_dx, float* grad_x, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align,
-                        uint32_t interp, cudaStream_t st) {
+                        uint32_t interp, const int* b_dev, cudaStream_t st) {
     switch (C) {
-        case 1: return launch_backward<T, TG, D, 1>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, st);
-        case 2: return launch_backward<T, TG, D, 2>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, st);
-        case 4: return launch_backward<T, TG, D, 4>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, st);
-        case 8: return launch_backward<T, TG, D, 8>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, st);
+        case 1: return launch_backward<T, TG, D, 1>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 2: return launch_backward<T, TG, D, 2>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 4: return launch_backward<T, TG, D, 4>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 8: return launch_backward<T, TG, D, 8>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
         default: return SEALD_E_UNSUPPORTED;
     }
 }
@@ -585,12 +591,12 @@ int dispatch_backward_C(uint32_t C, const void* grad, const float* x, const void
 template <typename T, typename TG>
 int dispatch_backward_D(uint32_t D, uint32_t C, const void* grad, const float* x, const void* table, const int* offsets, void* grad_table,
                         const void* dy_dx, float* grad_x, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align,
-                        uint32_t interp, cudaStream_t st) {
+                        uint32_t interp, const int* b_dev, cudaStream_t st) {
     switch (D) {
-        case 2: return dispatch_backward_C<T, TG, 2>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, st);
-        case 3: return dispatch_backward_C<T, TG, 3>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, st);
-        case 4: return dispatch_backward_C<T, TG, 4>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, st);
-        case 5: return dispatch_backward_C<T, TG, 5>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, st);
+        case 2: return dispatch_backward_C<T, TG, 2>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 3: return dispatch_backward_C<T, TG, 3>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 4: return dispatch_backward_C<T, TG, 4>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 5: return dispatch_backward_C<T, TG, 5>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
         default: return SEALD_E_UNSUPPORTED;
     }
 }
@@ -601,20 +607,20 @@ using namespace seald;
 
 extern "C" int seald_grid_encode_forward(const float* x01, const void* table, const int32_t* offsets, void* out, void* dy_dx, uint32_t B,
                                          uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
-                                         uint32_t interp, int dtype, seald_stream_t stream) {
+                                         uint32_t interp, int dtype, const int32_t* b_dev, seald_stream_t stream) {
     if (B == 0) return 0;
     if (!x01 || !table || !offsets || !out) return SEALD_E_BADARG;
     if (L == 0 || L > kMaxLevels || gridtype > 1 || interp > 1) return SEALD_E_UNSUPPORTED;
     cudaStream_t st = to_stream(stream);
-    if (dtype == SEALD_F16) return dispatch_forward_D<__half>(D, C, x01, table, offsets, out, dy_dx, B, L, S, H, gridtype, align_corners != 0, interp, st);
-    if (dtype == SEALD_F32) return dispatch_forward_D<float>(D, C, x01, table, offsets, out, dy_dx, B, L, S, H, gridtype, align_corners != 0, interp, st);
+    if (dtype == SEALD_F16) return dispatch_forward_D<__half>(D, C, x01, table, offsets, out, dy_dx, B, L, S, H, gridtype, align_corners != 0, interp, b_dev, st);
+    if (dtype == SEALD_F32) return dispatch_forward_D<float>(D, C, x01, table, offsets, out, dy_dx, B, L, S, H, gridtype, align_corners != 0, interp, b_dev, st);
     return SEALD_E_UNSUPPORTED;
 }
 
 extern "C" int seald_grid_encode_backward(const void* grad_out, const float* x01, const void* table, const int32_t* offsets,
                                           void* grad_table, const void* dy_dx, float* grad_x, uint32_t B, uint32_t D, uint32_t C,
                                           uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp,
-                                          int dtype, int grad_table_dtype, seald_stream_t stream) {
+                                          int dtype, int grad_table_dtype, const int32_t* b_dev, seald_stream_t stream) {
     if (B == 0) return 0;
     if (!grad_out || !x01 || !offsets || !grad_table) return SEALD_E_BADARG;
     if (grad_x && !dy_dx && !table) return SEALD_E_BADARG;
@@ -622,11 +628,11 @@ extern "C" int seald_grid_encode_backward(const void* grad_out, const float* x01
     cudaStream_t st = to_stream(stream);
     const bool al = align_corners != 0;
     if (dtype == SEALD_F16 && grad_table_dtype == SEALD_F16)
-        return dispatch_backward_D<__half, __half>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, st);
+        return dispatch_backward_D<__half, __half>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, st);
     if (dtype == SEALD_F16 && grad_table_dtype == SEALD_F32)
-        return dispatch_backward_D<__half, float>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, st);
+        return dispatch_backward_D<__half, float>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, st);
     if (dtype == SEALD_F32 && grad_table_dtype == SEALD_F32)
-        return dispatch_backward_D<float, float>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, st);
+        return dispatch_backward_D<float, float>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, st);
     return SEALD_E_UNSUPPORTED;
 }
 

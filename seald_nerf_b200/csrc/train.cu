@@ -1,0 +1,159 @@
+// train.cu — the element-wise glue of a training step as fused kernels: background blend + MSE loss + its gradient
+// (dnerf/utils.py:74-85, dnerf/renderer.py:325-326), fp32 -> fp16 weight staging, gradient finiteness check, dynamic
+// loss scaling (torch.cuda.amp.GradScaler semantics, nerf/utils.py:884-886) and Adam (main_dnerf.py:129).
+#include "common.cuh"
+
+namespace seald {
+
+// pred = image + (1 - ws) * bg ; loss_sum += sum (pred - gt)^2 ; grads of  loss_scale * mean((pred-gt)^2)
+__global__ void k_mse_loss_bg(const float* __restrict__ image, const float* __restrict__ weights_sum, const float* __restrict__ bg,
+                              const float* __restrict__ gt, const uint32_t N, const float inv_count, const float* __restrict__ loss_scale,
+                              float* __restrict__ pred, float* __restrict__ loss_sum, float* __restrict__ grad_image,
+                              float* __restrict__ grad_ws) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    float local = 0.0f;
+    if (n < N) {
+        const float scale = loss_scale ? *loss_scale : 1.0f;
+        const float ws = weights_sum[n];
+        float gws = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float b = bg ? bg[(size_t)n * 3 + c] : 1.0f;
+            const float p = image[(size_t)n * 3 + c] + (1 - ws) * b;
+            const float diff = p - gt[(size_t)n * 3 + c];
+            local += diff * diff;
+            const float gi = 2.0f * diff * inv_count * scale;
+            if (pred) pred[(size_t)n * 3 + c] = p;
+            grad_image[(size_t)n * 3 + c] = gi;
+            gws -= b * gi;
+        }
+        grad_ws[n] = gws;
+    }
+    // block reduction of the loss
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ float s_part[32];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(loss_sum, v * inv_count);
+    }
+}
+
+__global__ void k_cast_pad_f16(const float* __restrict__ src, __half* __restrict__ dst, const uint32_t rows, const uint32_t cols,
+                               const uint32_t ld) {
+    const size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x;
+    if (i >= (size_t)rows * ld) return;
+    const uint32_t r = i / ld, c = i - (size_t)r * ld;
+    dst[i] = __float2half_rn(c < cols ? src[(size_t)r * cols + c] : 0.0f);
+}
+
+// found_inf[0] = 1 if any gradient is inf/nan
+__global__ void k_grad_finite_check(const float* __restrict__ g, const size_t n, int* __restrict__ found_inf) {
+    bool bad = false;
+    const size_t n4 = n / 4;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = g4[i];
+        bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+    }
+    for (size_t i = n4 * 4 + threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n; i += (size_t)gridDim.x * blockDim.x) bad |= !isfinite(g[i]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(found_inf, 1);
+}
+
+// torch.optim.Adam (no amsgrad / weight decay) on a flat fp32 slab, gradients un-scaled by 1 / *loss_scale, the whole
+// update skipped when *found_inf != 0 (GradScaler.step).  Optionally refreshes an fp16 copy and zeroes the gradient.
+__global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const size_t n,
+                       const float lr, const float beta1, const float beta2, const float eps, const float bc1, const float bc2_sqrt,
+                       const float* __restrict__ loss_scale, const int* __restrict__ found_inf, __half* __restrict__ p16,
+                       const int zero_grad) {
+    const bool skip = found_inf && *found_inf != 0;
+    const float inv_scale = loss_scale ? 1.0f / *loss_scale : 1.0f;
+    for (size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!skip) {
+            const float gi = g[i] * inv_scale;
+            const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+            const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+            m[i] = mi;
+            v[i] = vi;
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            const float pi = p[i] - (lr / bc1) * (mi / denom);
+            p[i] = pi;
+            if (p16) p16[i] = __float2half_rn(pi);
+        }
+        if (zero_grad) g[i] = 0.0f;
+    }
+}
+
+// GradScaler.update(): found_inf -> scale *= backoff, tracker = 0; else tracker++ and scale *= growth every `interval`.
+__global__ void k_loss_scale_update(float* loss_scale, int* found_inf, int* growth_tracker, const float growth, const float backoff,
+                                    const int interval) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (*found_inf) {
+            *loss_scale *= backoff;
+            *growth_tracker = 0;
+        } else {
+            const int t = *growth_tracker + 1;
+            if (t >= interval) {
+                *loss_scale *= growth;
+                *growth_tracker = 0;
+            } else {
+                *growth_tracker = t;
+            }
+        }
+        *found_inf = 0;
+    }
+}
+
+}  // namespace seald
+
+using namespace seald;
+
+extern "C" int seald_mse_loss_bg(const float* image, const float* weights_sum, const float* bg, const float* gt, uint32_t N, float inv_count,
+                                 const float* loss_scale, float* pred, float* loss_sum, float* grad_image, float* grad_ws,
+                                 seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!image || !weights_sum || !gt || !loss_sum || !grad_image || !grad_ws) return SEALD_E_BADARG;
+    k_mse_loss_bg<<<div_up(N, 256u), 256, 0, to_stream(stream)>>>(image, weights_sum, bg, gt, N, inv_count, loss_scale, pred, loss_sum, grad_image,
+                                                                 grad_ws);
+    return launch_status();
+}
+
+extern "C" int seald_cast_pad_f16(const float* src, void* dst, uint32_t rows, uint32_t cols, uint32_t ld, seald_stream_t stream) {
+    if (rows == 0 || ld == 0) return 0;
+    if (!src || !dst || ld < cols) return SEALD_E_BADARG;
+    const size_t n = (size_t)rows * ld;
+    k_cast_pad_f16<<<(uint32_t)div_up(n, (size_t)256), 256, 0, to_stream(stream)>>>(src, (__half*)dst, rows, cols, ld);
+    return launch_status();
+}
+
+extern "C" int seald_grad_finite_check(const float* g, uint64_t n, int32_t* found_inf, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!g || !found_inf) return SEALD_E_BADARG;
+    if ((uintptr_t)g % 16) return SEALD_E_ALIGN;
+    const uint32_t blocks = (uint32_t)(n / 4 / 256 + 1 < 4u * SEALD_NUM_SMS ? n / 4 / 256 + 1 : 4u * SEALD_NUM_SMS);
+    k_grad_finite_check<<<blocks, 256, 0, to_stream(stream)>>>(g, (size_t)n, found_inf);
+    return launch_status();
+}
+
+extern "C" int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
+                               const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!p || !g || !m || !v || step == 0) return SEALD_E_BADARG;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const uint32_t blocks = (uint32_t)(n / 256 + 1 < 8u * SEALD_NUM_SMS ? n / 256 + 1 : 8u * SEALD_NUM_SMS);
+    k_adam<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), loss_scale, found_inf,
+                                                  (__half*)p16, zero_grad);
+    return launch_status();
+}
+
+extern "C" int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff,
+                                       int interval, seald_stream_t stream) {
+    if (!loss_scale || !found_inf || !growth_tracker) return SEALD_E_BADARG;
+    k_loss_scale_update<<<1, 32, 0, to_stream(stream)>>>(loss_scale, found_inf, growth_tracker, growth, backoff, interval);
+    return launch_status();
+}

@@ -1,0 +1,173 @@
+"""Low-level driver of the fused D-NeRF field kernels (csrc/field.cu + grid_encoder.cu).
+
+`FieldWorkspace` owns every intermediate buffer of one forward/backward pass for up to `M` samples; `field_forward`
+/ `field_backward` enqueue the kernel sequence
+
+    deform MLP (freq-encode in the input stage)  ->  grid encoder  ->  sigma + colour heads (SH in the input stage)
+
+and its reverse (heads bwd -> grid scatter + input grad -> deform bwd -> weight-gradient GEMMs).  Both the autograd
+wrapper used by the drop-in `NeRFNetwork` and the graph-captured `FusedTrainer` call these two functions.
+Reference: dnerf/network.py:123-169.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr, F16, F32
+
+DEFORM_W, DEFORM_K0, DEFORM_IN = 128, 80, 76
+HEAD_W, HEAD_K0 = 64, 32
+
+
+class FieldConfig:
+    """Static description of the field (D-NeRF defaults, dnerf/network.py:11-26)."""
+
+    def __init__(self, n_deform=8, n_sigma=2, n_color=3, bound=1.0, density_scale=1.0, grid_levels=16, grid_dim=2, grid_base=16,
+                 grid_S=None, gridtype=0, align_corners=False, interp=0):
+        self.n_deform, self.n_sigma, self.n_color = n_deform, n_sigma, n_color
+        self.bound, self.density_scale = float(bound), float(density_scale)
+        self.grid_levels, self.grid_dim, self.grid_base = grid_levels, grid_dim, grid_base
+        self.grid_S = float(grid_S)
+        self.gridtype, self.align_corners, self.interp = int(gridtype), bool(align_corners), int(interp)
+        if grid_levels * grid_dim != HEAD_K0:
+            raise NotImplementedError("fused heads expect 32 grid features (16 levels x 2)")
+
+
+def half_weight_shapes(cfg):
+    """(rows, cols, ld) of the fp16 staging copy of every nn.Linear weight, in the order deform, sigma, colour."""
+    shapes = [(DEFORM_W, DEFORM_IN, DEFORM_K0)] + [(DEFORM_W, DEFORM_W, DEFORM_W)] * (cfg.n_deform - 2) + [(3, DEFORM_W, DEFORM_W)]
+    shapes += [(HEAD_W, HEAD_K0, HEAD_K0)] + [(HEAD_W, HEAD_W, HEAD_W)] * (cfg.n_sigma - 2) + [(16, HEAD_W, HEAD_W)]
+    shapes += [(HEAD_W, 31, HEAD_K0)] + [(HEAD_W, HEAD_W, HEAD_W)] * (cfg.n_color - 2) + [(3, HEAD_W, HEAD_W)]
+    return shapes
+
+
+class HalfWeights:
+    """fp16, row-padded staging copies of the MLP weights (one flat buffer, 16-byte aligned slices)."""
+
+    def __init__(self, cfg, device):
+        self.cfg = cfg
+        self.shapes = half_weight_shapes(cfg)
+        sizes = [(r * ld + 7) // 8 * 8 for r, c, ld in self.shapes]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float16, device=device)
+        self.views, o = [], 0
+        for (r, c, ld), n in zip(self.shapes, sizes):
+            self.views.append(self.flat[o:o + r * ld].view(r, ld))
+            o += n
+        nd, ns = cfg.n_deform, cfg.n_sigma
+        self.deform, self.sigma, self.color = self.views[:nd], self.views[nd:nd + ns], self.views[nd + ns:]
+        self.p_deform, self.p_sigma, self.p_color = _lib.ptr_array(self.deform), _lib.ptr_array(self.sigma), _lib.ptr_array(self.color)
+
+    def refresh(self, weights32):
+        """weights32: list of fp32 [out,in] tensors in the same order."""
+        st = _lib.stream()
+        for w, v, (r, c, ld) in zip(weights32, self.views, self.shapes):
+            assert tuple(w.shape) == (r, c), (tuple(w.shape), (r, c))
+            _lib.call("seald_cast_pad_f16", ptr(w.contiguous()), ptr(v), r, c, ld, st)
+
+
+class FieldWorkspace:
+    def __init__(self, cfg, M, device, training=True):
+        self.cfg, self.M, self.training = cfg, int(M), training
+        f16 = dict(dtype=torch.float16, device=device)
+        f32 = dict(dtype=torch.float32, device=device)
+        M = self.M
+        self.deform = torch.empty(M, 3, **f32)
+        self.x01 = torch.empty(M, 3, **f32)
+        self.feat = torch.empty(M, HEAD_K0, **f16)
+        self.sigma = torch.empty(M, **f32)
+        self.rgb = torch.empty(M, 3, **f32)
+        if training:
+            self.in_buf = torch.empty(M, DEFORM_K0, **f16)
+            self.fwd_d = torch.empty(cfg.n_deform - 1, M, DEFORM_W, **f16)
+            self.bwd_d = torch.empty(cfg.n_deform - 1, M, DEFORM_W, **f16)
+            self.gout_d = torch.empty(M, 16, **f16)
+            self.hs = torch.empty(M, 16, **f16)
+            self.cin = torch.empty(M, HEAD_K0, **f16)
+            self.fwd_s = torch.empty(cfg.n_sigma - 1, M, HEAD_W, **f16)
+            self.fwd_c = torch.empty(cfg.n_color - 1, M, HEAD_W, **f16)
+            self.bwd_s = torch.empty(cfg.n_sigma - 1, M, HEAD_W, **f16)
+            self.bwd_c = torch.empty(cfg.n_color - 1, M, HEAD_W, **f16)
+            self.gout_s = torch.empty(M, 16, **f16)
+            self.gout_c = torch.empty(M, 16, **f16)
+            self.dfeat = torch.empty(M, HEAD_K0, **f16)
+            self.grad_x01 = torch.empty(M, 3, **f32)
+
+
+def field_forward(cfg, hw, ws, xyzs, dirs, time_dev, table16, offsets, m_dev=None, t0_mode=1, M=None):
+    """Enqueue the forward pass for rows [0, M) of the workspace.  Results: ws.sigma, ws.rgb, ws.deform."""
+    M = ws.M if M is None else int(M)
+    st = _lib.stream()
+    save = ws.training
+    _lib.call("seald_field_deform_forward", ptr(xyzs), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, int(t0_mode),
+              ptr(ws.deform), ptr(ws.x01), ptr(ws.in_buf) if save else None, ptr(ws.fwd_d) if save else None, st)
+    # rows >= *m_dev keep stale x01: the grid kernel clamps nothing, so feed it only well-defined rows
+    _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
+              cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, ptr(m_dev), st)
+    _lib.call("seald_field_heads_forward", ptr(ws.feat), ptr(dirs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, M, ptr(m_dev),
+              cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs) if save else None, ptr(ws.cin) if save else None,
+              ptr(ws.fwd_s) if save else None, ptr(ws.fwd_c) if save else None, st)
+
+
+def _job(G, A, dW, N, K, ldg, lda, ldw, n_real, k_real):
+    return _lib.WgradJob(G.data_ptr(), A.data_ptr(), dW.data_ptr(), N, K, ldg, lda, ldw, n_real, k_real)
+
+
+def wgrad_jobs(cfg, ws, grads32, deform=True):
+    """ctypes array of weight-gradient jobs; grads32: fp32 [out,in] gradient tensors in weight order."""
+    nd, ns, nc = cfg.n_deform, cfg.n_sigma, cfg.n_color
+    gd, gs, gc = grads32[:nd], grads32[nd:nd + ns], grads32[nd + ns:]
+    jobs = []
+    M = ws.M
+    if deform:
+        for l in range(nd):
+            last = l == nd - 1
+            G = ws.gout_d if last else ws.bwd_d[l]
+            A = ws.in_buf if l == 0 else ws.fwd_d[l - 1]
+            jobs.append(_job(G, A, gd[l], 16 if last else DEFORM_W, DEFORM_K0 if l == 0 else DEFORM_W, 16 if last else DEFORM_W,
+                             DEFORM_K0 if l == 0 else DEFORM_W, gd[l].shape[1], 3 if last else DEFORM_W, DEFORM_IN if l == 0 else DEFORM_W))
+    for l in range(ns):
+        last = l == ns - 1
+        G = ws.gout_s if last else ws.bwd_s[l]
+        A = ws.feat if l == 0 else ws.fwd_s[l - 1]
+        jobs.append(_job(G, A, gs[l], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W, 16 if last else HEAD_W,
+                         HEAD_K0 if l == 0 else HEAD_W, gs[l].shape[1], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W))
+    for l in range(nc):
+        last = l == nc - 1
+        G = ws.gout_c if last else ws.bwd_c[l]
+        A = ws.cin if l == 0 else ws.fwd_c[l - 1]
+        jobs.append(_job(G, A, gc[l], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W, 16 if last else HEAD_W,
+                         HEAD_K0 if l == 0 else HEAD_W, gc[l].shape[1], 3 if last else HEAD_W, 31 if l == 0 else HEAD_W))
+    arr = (_lib.WgradJob * len(jobs))(*jobs)
+    return arr, len(jobs)
+
+
+def field_backward(cfg, hw, ws, grad_sigma, grad_rgb, time_is_zero, table16, offsets, grad_table32, jobs, n_jobs, m_dev=None,
+                   deform_grad=True, M=None):
+    """Enqueue the backward pass.  grad_table32 (fp32 [rows, C]) and the fp32 weight gradients referenced by `jobs`
+    are ACCUMULATED into.  deform_grad=False: frozen deformation net (SealD student, SealDNeRF/utils.py:337-359)."""
+    M = ws.M if M is None else int(M)
+    st = _lib.stream()
+    _lib.call("seald_field_heads_backward", ptr(grad_sigma), ptr(grad_rgb), ptr(ws.rgb), ptr(ws.hs), hw.p_sigma, cfg.n_sigma, hw.p_color,
+              cfg.n_color, M, ptr(m_dev), cfg.density_scale, ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.bwd_s), ptr(ws.bwd_c), ptr(ws.gout_s),
+              ptr(ws.gout_c), ptr(ws.dfeat), st)
+    want_dx = deform_grad and not time_is_zero
+    _lib.call("seald_grid_encode_backward", ptr(ws.dfeat), ptr(ws.x01), ptr(table16), ptr(offsets), ptr(grad_table32), None,
+              ptr(ws.grad_x01) if want_dx else None, M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype,
+              int(cfg.align_corners), cfg.interp, F16, F32, ptr(m_dev), st)
+    if want_dx:
+        _lib.call("seald_field_deform_backward", ptr(ws.grad_x01), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, ptr(ws.fwd_d),
+                  ptr(ws.bwd_d), ptr(ws.gout_d), st)
+    _lib.call("seald_mlp_wgrad", C.cast(jobs, C.c_void_p), n_jobs, M, ptr(m_dev), st)
+
+
+def field_density(cfg, hw, ws, xyzs, time_dev, table16, offsets, M=None):
+    """Density-only query (NeRFNetwork.density, dnerf/network.py:171-208): deform -> grid -> sigma net."""
+    M = ws.M if M is None else int(M)
+    st = _lib.stream()
+    _lib.call("seald_field_deform_forward", ptr(xyzs), ptr(time_dev), hw.p_deform, cfg.n_deform, M, None, cfg.bound, 2, ptr(ws.deform),
+              ptr(ws.x01), None, None, st)
+    _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
+              cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, None, st)
+    _lib.call("seald_field_sigma_forward", ptr(ws.feat), hw.p_sigma, cfg.n_sigma, M, cfg.density_scale, ptr(ws.sigma), None, st)

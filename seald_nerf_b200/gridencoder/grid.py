@@ -52,7 +52,7 @@ class _grid_encode(Function):
 
         outputs = torch.empty(B, L * C, device=inputs.device, dtype=embeddings.dtype)
         _lib.call("seald_grid_encode_forward", ptr(inputs), ptr(embeddings), ptr(offsets), ptr(outputs), None, B, D, C, L, S, H,
-                  int(gridtype), int(bool(align_corners)), int(interpolation), _dtype_id(embeddings), _lib.stream())
+                  int(gridtype), int(bool(align_corners)), int(interpolation), _dtype_id(embeddings), None, _lib.stream())
 
         ctx.save_for_backward(inputs, embeddings, offsets)
         ctx.dims = [B, D, C, L, S, H, gridtype, interpolation]
@@ -72,8 +72,7 @@ class _grid_encode(Function):
         grad_inputs = torch.empty_like(inputs) if ctx.calc_grad_inputs else None
         dt = _dtype_id(embeddings)
         _lib.call("seald_grid_encode_backward", ptr(grad), ptr(inputs), ptr(embeddings), ptr(offsets), ptr(grad_embeddings), None,
-                  ptr(grad_inputs), B, D, C, L, S, H, int(gridtype), int(bool(ctx.align_corners)), int(interpolation), dt, dt,
-                  _lib.stream())
+                  ptr(grad_inputs), B, D, C, L, S, H, int(gridtype), int(bool(ctx.align_corners)), int(interpolation), dt, dt, None, _lib.stream())
         return grad_inputs, grad_embeddings, None, None, None, None, None, None, None
 
 

@@ -108,7 +108,7 @@ def test_forward_backward_vs_oracle_and_reference(cuda_dev, case, dtype):
     out = torch.empty(B, L * C, dtype=dtype, device=d)
     dy = torch.empty(B, L, D, C, dtype=dtype, device=d)
     _lib.call("seald_grid_encode_forward", ptr(tx), ptr(tt), ptr(to), ptr(out), ptr(dy), B, D, C, L, S, base, gridtype, int(align),
-              interp, dt, _lib.stream())
+              interp, dt, None, _lib.stream())
     sc_dev, _ = _device_scales(d, offsets, D, L, S, base, gridtype, align)
     out_o, dy_o = og.grid_encode_forward(x, table_q, offsets, S, base, gridtype, align, interp, want_dy_dx=True, scales=sc_dev)
     if dtype == torch.float32:
@@ -122,7 +122,7 @@ def test_forward_backward_vs_oracle_and_reference(cuda_dev, case, dtype):
     # without dy_dx the output is identical
     out2 = torch.empty_like(out)
     _lib.call("seald_grid_encode_forward", ptr(tx), ptr(tt), ptr(to), ptr(out2), None, B, D, C, L, S, base, gridtype, int(align),
-              interp, dt, _lib.stream())
+              interp, dt, None, _lib.stream())
     assert torch.equal(out, out2)
 
     # backward: table gradient (dtype of the table, like the reference) + recomputed input gradient
@@ -134,7 +134,7 @@ def test_forward_backward_vs_oracle_and_reference(cuda_dev, case, dtype):
         grad_table = torch.zeros(int(offsets[-1]), C, dtype=gtorch, device=d)
         grad_x = torch.empty(B, D, device=d)
         _lib.call("seald_grid_encode_backward", ptr(tg), ptr(tx), ptr(tt), ptr(to), ptr(grad_table), None, ptr(grad_x), B, D, C, L, S,
-                  base, gridtype, int(align), interp, dt, gdt, _lib.stream())
+                  base, gridtype, int(align), interp, dt, gdt, None, _lib.stream())
         tol = (1e-3 if gtorch == torch.float16 else 1e-5) * np.abs(gt_o).max()
         np.testing.assert_allclose(grad_table.float().cpu().numpy(), gt_o, rtol=1e-2 if gtorch == torch.float16 else 1e-4, atol=tol)
         np.testing.assert_allclose(grad_x.cpu().numpy(), gx_o, rtol=2e-2 if dtype == torch.float16 else 1e-3,
@@ -143,7 +143,7 @@ def test_forward_backward_vs_oracle_and_reference(cuda_dev, case, dtype):
     grad_table = torch.zeros(int(offsets[-1]), C, dtype=torch.float32, device=d)
     grad_x2 = torch.empty(B, D, device=d)
     _lib.call("seald_grid_encode_backward", ptr(tg), ptr(tx), ptr(tt), ptr(to), ptr(grad_table), ptr(dy), ptr(grad_x2), B, D, C, L, S,
-              base, gridtype, int(align), interp, dt, F32, _lib.stream())
+              base, gridtype, int(align), interp, dt, F32, None, _lib.stream())
     np.testing.assert_allclose(grad_x2.cpu().numpy(), gx_o, rtol=5e-2 if dtype == torch.float16 else 1e-3,
                                atol=(1e-2 if dtype == torch.float16 else 1e-4) * np.abs(gx_o).max())
 
@@ -164,7 +164,7 @@ def test_forward_backward_vs_oracle_and_reference(cuda_dev, case, dtype):
         ref.grid_encode_backward(gr, tx, tt, to, gt_r, B, D, C, L, S, base, dy_r, gx_r, gridtype, align, interp)
         mine = torch.zeros(int(offsets[-1]), C, dtype=dtype, device=d)
         _lib.call("seald_grid_encode_backward", ptr(tg), ptr(tx), ptr(tt), ptr(to), ptr(mine), None, None, B, D, C, L, S, base,
-                  gridtype, int(align), interp, dt, dt, _lib.stream())
+                  gridtype, int(align), interp, dt, dt, None, _lib.stream())
         scale = float(gt_r.float().abs().max())
         # the reference accumulates every contribution with an fp16 atomicAdd (order dependent, error grows with the
         # number of points per cell); ours accumulates in fp32 first, so the fp16 comparison gets a wider band
