@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — D-NeRF hashgrid training throughput (BASELINE.json configs[1]) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): one optimisation step of the D-NeRF field (hashgrid 16 levels x 2 features, T = 2^19,
+8x128 time-conditioned deformation net, 64-wide sigma / colour heads) on a 4096-ray batch per GPU of the synthetic
+jumpingjacks-shaped scene (800x800 cameras, t in [0,1]), `-O` semantics: fp16 tensor-core MLPs, cuda_ray march through
+the occupancy bitfield, perturbed samples, loss-scaled Adam.  Data parallel across GPUs: every rank draws its own
+4096-ray batch, one NCCL allreduce of the flat gradient buffer per step ("scaling": "weak").
+
+`value`  : rays/s with the step's inputs already resident in HBM (device-timed with CUDA events, max over ranks).
+`e2e`    : the same metric through the public API with HOST inputs (pinned H2D of rays/targets every step and a D2H
+           read of the loss inside the timed region).
+`roofline`: the dominant kernel of the step, timed alone with CUDA events, against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the reference's pure-PyTorch path (cuda_ray=False, torch frequency encoders,
+           BASELINE.json configs[0]) as ported in oracle/render.py, timed on the host cores (forward+render only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "D-NeRF train rays/s and 800x800 frame ms at 1/2/4/8 B200; hashgrid GB/s"
+UNIT = "rays/s"
+N_RAYS = 4096
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's CPU implementation of the path (oracle port), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import render
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    # bounded sample: each "step" renders ONE 4096-ray batch (forward+render, 128 steps/ray) ~1 s on 8 cores
+    rps, cores, dt = render.time_cpu_render(n_rays=N_RAYS, num_steps=128, steps=min(steps, 10), warmup=warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": min(steps, 10), "warmup": warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "dnerf_cpu_pure_pytorch_forward_render_4096rays_128steps (BASELINE configs[0]; the reference has no CPU training path)"},
+        "cpu_baseline": {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d batches of 4096 rays x 128 samples, forward+render, fp32, torch %d threads" % (min(steps, 10), cores)},
+        "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def build_scene(device, seed=0):
+    """Random-init D-NeRF (hashgrid) + analytic occupancy grid of the synthetic figure."""
+    import torch
+    from seald_nerf_b200 import synthetic as syn
+    from seald_nerf_b200.dnerf.network import NeRFNetwork
+    from seald_nerf_b200 import raymarching
+    torch.manual_seed(seed)
+    model = NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10).to(device)
+    model.train()
+    grid = syn.make_density_grid(model.time_size, model.grid_size, 1.0, device)
+    model.density_grid.copy_(grid)
+    model.mean_density = float(grid.clamp(min=0).mean())
+    thresh = min(model.mean_density, model.density_thresh)
+    for t in range(model.time_size):
+        raymarching.packbits(model.density_grid[t], thresh, model.density_bitfield[t])
+    return model
+
+
+def make_batches(n, device, rank, seed=0):
+    """n training batches: (rays_o, rays_d [n,4096,3], times [n], gt [n,4096,3]) drawn like dnerf/provider.py:304-352."""
+    import torch
+    from seald_nerf_b200 import synthetic as syn
+    intr = syn.intrinsics()
+    poses = syn.orbit_poses(200, device, seed=seed)
+    g = torch.Generator(device="cpu").manual_seed(1000 * rank + seed)
+    ro, rd, ts, gt = [], [], [], []
+    for i in range(n):
+        frame = int(torch.randint(0, 200, (1,), generator=g))
+        inds = torch.randint(0, 800 * 800, (N_RAYS,), generator=g).to(device)
+        o, d = syn.get_rays(poses[frame], intr, 800, 800, inds)
+        t = frame / 199.0
+        rgb, alpha = syn.render_gt(o, d, t, n_samples=192)
+        ro.append(o); rd.append(d); ts.append(t)
+        gt.append(rgb + (1 - alpha).unsqueeze(-1))  # white background
+    return torch.stack(ro), torch.stack(rd), ts, torch.stack(gt)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from seald_nerf_b200.trainer import FusedTrainer
+    from seald_nerf_b200 import _lib
+    _lib.load()  # fails loudly without the CUDA library
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    K, W = args.steps, max(args.warmup, 3)
+
+    model = build_scene(device)
+    n_batches = min(K + W, 64)  # batches are cycled; 64 distinct ones keep set-up short
+    rays_o, rays_d, times, gts = make_batches(n_batches, device, rank)
+    # size the sample buffers like the reference's mean_count estimate (+25%)
+    probe = FusedTrainer(model, num_rays=N_RAYS, max_samples=N_RAYS * 8, use_graph=False)
+    m_need = max(probe.calibrate_max_samples(rays_o[i], rays_d[i], times[i]) for i in range(min(8, n_batches)))
+    del probe
+    if world > 1:
+        mt = torch.tensor([m_need], device=device)
+        dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        m_need = int(mt.item())
+    trainer = FusedTrainer(model, num_rays=N_RAYS, max_samples=m_need, lr=1e-2, lr_net=1e-3, use_graph=not args.no_graph, world_size=world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident loop --------------------------------------------------------------------------------
+    for i in range(W):
+        b = i % n_batches
+        trainer.train_step(rays_o[b], rays_d[b], times[b], gts[b])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        b = (W + i) % n_batches
+        trainer.train_step(rays_o[b], rays_d[b], times[b], gts[b])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_end = float(trainer.loss.item())
+    launches = trainer.launches_per_step * K
+
+    # ---- end-to-end loop (host inputs, loss read back every step) ------------------------------------------------
+    h_o, h_d, h_g = rays_o.cpu(), rays_d.cpu(), gts.cpu()
+    for i in range(3):
+        trainer.train_step_host(h_o[i % n_batches], h_d[i % n_batches], times[i % n_batches], h_g[i % n_batches])
+    barrier()
+    Ke = max(10, K // 2)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(Ke):
+        b = i % n_batches
+        trainer.train_step_host(h_o[b], h_d[b], times[b], h_g[b])
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(tt[0]), float(tt[1])
+
+    # ---- per-stage timing + roofline of the dominant kernel (rank 0) ------------------------------------------------
+    line = None
+    if rank == 0:
+        hbm, tf_burst, tf_sust, which = _peaks()
+        trainer.set_inputs(rays_o[0], rays_d[0], times[0], gts[0])
+        st = trainer.stage_timings(reps=20)
+        m_live = st.pop("live_samples")
+        cfg = trainer.cfg
+        mac_deform = 76 * 128 + (cfg.n_deform - 2) * 128 * 128 + 128 * 3
+        mac_heads = 32 * 64 + 64 * 16 + 31 * 64 + (cfg.n_color - 2) * 64 * 64 + 64 * 3
+        work = {  # algorithmic work per launch (SURVEY.md §8d figures x live samples)
+            "deform_fwd": ("tensor", 2.0 * mac_deform * m_live),
+            "deform_bwd": ("tensor", 2.0 * (mac_deform - 76 * 128) * m_live),
+            "wgrad": ("tensor", 2.0 * (mac_deform + mac_heads) * m_live),
+            "heads_fwd": ("tensor", 2.0 * mac_heads * m_live),
+            "heads_bwd": ("tensor", 2.0 * mac_heads * m_live),
+            "grid_fwd": ("hbm", 588.0 * m_live),
+            "grid_bwd": ("hbm", (1100.0 + 588.0 + 12.0) * m_live),
+            "march": ("hbm", 48.0 * N_RAYS + 32.0 * m_live + 262144.0),
+            "composite_fwd": ("hbm", 24.0 * m_live + 32.0 * N_RAYS),
+            "composite_bwd": ("hbm", 40.0 * m_live + 48.0 * N_RAYS),
+            "optimizer": ("hbm", 30.0 * trainer.n_params + 4.0 * trainer.n_params),
+        }
+        dom = max((k for k in st if k in work), key=lambda k: st[k])
+        bound, amount = work[dom]
+        sec = st[dom] * 1e-3
+        if bound == "tensor":
+            achieved, peak, unit = amount / sec / 1e12, tf_burst, "TFLOP/s"
+        else:
+            achieved, peak, unit = amount / sec / 1e9, hbm, "GB/s"
+        roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
+                    "peak_source": which + (" burst" if bound == "tensor" else ""), "ms": st[dom],
+                    "stage_ms": {k: round(v, 4) for k, v in st.items()}, "live_samples": m_live}
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import render
+            rps, cores, dt = render.time_cpu_render(n_rays=N_RAYS, num_steps=128, steps=10, warmup=2)
+            cpu = {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "10 batches of 4096 rays x 128 samples, forward+render only (BASELINE configs[0]), fp32, %d torch threads" % cores}
+        total_rays = N_RAYS * world
+        ws_mb = (trainer.n_params * 18 + trainer.M * 4200) / 1e6
+        line = {
+            "metric": METRIC, "value": total_rays * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "dnerf_hashgrid_L16_T19_F2_deform8x128_train_step_4096rays_per_gpu (BASELINE configs[1])",
+                       "rays_per_gpu": N_RAYS, "max_samples": trainer.M, "live_samples": m_live, "cuda_graph": not args.no_graph,
+                       "parallelism": "dp%d" % world, "final_loss": loss_end,
+                       "l2": "no explicit flush: per-step working set (~%d MB of activations + optimiser state) exceeds the 126 MB L2" % ws_mb},
+            "e2e": {"value": total_rays * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": 4, "steps": Ke, "ms_per_step": ms_e2e / Ke},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

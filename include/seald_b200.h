@@ -148,7 +148,8 @@ int seald_sh_encode_backward(const float* grad, const float* inputs, uint32_t B,
 int seald_field_deform_forward(const float* xyz, const float* time_dev, const void* const* weights, int n_layers, uint32_t M,
                                const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf /*[M,80] f16 or NULL*/,
                                void* fwd_buf /*[n_layers-1,M,128] f16 or NULL*/, seald_stream_t stream);
-int seald_field_deform_backward(const float* grad_x01, const void* const* weights, int n_layers, uint32_t M, const int32_t* m_dev,
+int seald_field_deform_backward(const float* grad_x01, const float* time_dev /*NULL or device float: t == 0 => zero gradient*/,
+                                const void* const* weights, int n_layers, uint32_t M, const int32_t* m_dev,
                                 float bound, const void* fwd_buf, void* bwd_buf /*[n_layers-1,M,128] f16*/, void* gout_buf /*[M,16] f16*/,
                                 seald_stream_t stream);
 int seald_field_heads_forward(const void* feat /*[M,32] f16*/, const float* dirs, const void* const* w_sigma, int n_sigma,
@@ -197,8 +198,12 @@ int seald_mse_loss_bg(const float* image, const float* weights_sum, const float*
 /* dst[rows][ld] f16 = src[rows][cols] f32, zero padded columns. */
 int seald_cast_pad_f16(const float* src, void* dst, uint32_t rows, uint32_t cols, uint32_t ld, seald_stream_t stream);
 int seald_grad_finite_check(const float* g, uint64_t n, int32_t* found_inf, seald_stream_t stream);
+/* step_dev (optional device int32) overrides `step`: the step counter lives on the device so the optimiser can be replayed
+ * from a CUDA graph; seald_adam_advance increments it unless *found_inf (GradScaler skips optimizer.step() then). */
+int seald_adam_advance(int32_t* step_dev, const int32_t* found_inf, seald_stream_t stream);
 int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
-                    const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad, seald_stream_t stream);
+                    const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
+                    seald_stream_t stream);
 int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff, int interval,
                             seald_stream_t stream);
 

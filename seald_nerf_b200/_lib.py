@@ -36,7 +36,7 @@ _SIGS = {
     "seald_sh_encode_forward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp],
     "seald_sh_encode_backward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp],
     "seald_field_deform_forward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
-    "seald_field_deform_backward": [_vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
+    "seald_field_deform_backward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
     "seald_field_heads_forward": [_vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_field_sigma_forward": [_vp, _vp, _i32, _u32, _f32, _vp, _vp, _vp],
     "seald_field_heads_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -46,7 +46,8 @@ _SIGS = {
     "seald_mse_loss_bg": [_vp, _vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_cast_pad_f16": [_vp, _vp, _u32, _u32, _u32, _vp],
     "seald_grad_finite_check": [_vp, C.c_uint64, _vp, _vp],
-    "seald_adam_step": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _i32, _vp],
+    "seald_adam_advance": [_vp, _vp, _vp],
+    "seald_adam_step": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _vp],
     "seald_loss_scale_update": [_vp, _vp, _vp, _f32, _f32, _i32, _vp],
 }
 

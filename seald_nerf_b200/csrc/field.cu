@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_deform_forward(const float* 
 }
 
 // deformation network backward: g_out = grad_x01 / (2 bound) (fp16), no input gradient (xyz / t are leaves without grad)
-__global__ void __launch_bounds__(kMlpThreads, 2) k_deform_backward(const float* __restrict__ grad_x01, const MlpWeights mw, const int M,
+__global__ void __launch_bounds__(kMlpThreads, 2) k_deform_backward(const float* __restrict__ grad_x01, const float* __restrict__ time,
+                                                                    const MlpWeights mw, const int M,
                                                                     const int* __restrict__ m_dev, const float bound,
                                                                     const __half* __restrict__ fwd_buf, __half* __restrict__ bwd_buf,
                                                                     __half* __restrict__ gout_buf) {
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_deform_backward(const float*
     __half* s_w = s_g + DeformSmem::IN_HALVES;           // keep the forward layout (s_in region is large enough)
     const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
     const int n_tiles = (m_used + kTileRows - 1) / kTileRows;
-    const float inv = 1.0f / (2 * bound);
+    // at t == 0 the deformation is replaced by zeros (network.py:140-141): no gradient reaches the net
+    const float inv = (time && *time == 0.0f) ? 0.0f : 1.0f / (2 * bound);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row0 = tile * kTileRows;
         for (int i = threadIdx.x; i < kTileRows * 16; i += kMlpThreads) {
@@ -484,7 +486,7 @@ extern "C" int seald_field_deform_forward(const float* xyz, const float* time_de
     return launch_status();
 }
 
-extern "C" int seald_field_deform_backward(const float* grad_x01, const void* const* weights, int n_layers, uint32_t M, const int32_t* m_dev,
+extern "C" int seald_field_deform_backward(const float* grad_x01, const float* time_dev, const void* const* weights, int n_layers, uint32_t M, const int32_t* m_dev,
                                            float bound, const void* fwd_buf, void* bwd_buf, void* gout_buf, seald_stream_t stream) {
     if (M == 0) return 0;
     if (!grad_x01 || !fwd_buf || !bwd_buf || !gout_buf) return SEALD_E_BADARG;
@@ -493,7 +495,7 @@ extern "C" int seald_field_deform_backward(const float* grad_x01, const void* co
     if (rc) return rc;
     const size_t smem = DeformSmem::BYTES;
     if ((rc = set_smem(k_deform_backward, smem))) return rc;
-    k_deform_backward<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>(grad_x01, mw, (int)M, m_dev, bound, (const __half*)fwd_buf,
+    k_deform_backward<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>(grad_x01, time_dev, mw, (int)M, m_dev, bound, (const __half*)fwd_buf,
                                                                                  (__half*)bwd_buf, (__half*)gout_buf);
     return launch_status();
 }

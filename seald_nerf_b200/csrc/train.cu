@@ -67,10 +67,21 @@ __global__ void k_grad_finite_check(const float* __restrict__ g, const size_t n,
 // torch.optim.Adam (no amsgrad / weight decay) on a flat fp32 slab, gradients un-scaled by 1 / *loss_scale, the whole
 // update skipped when *found_inf != 0 (GradScaler.step).  Optionally refreshes an fp16 copy and zeroes the gradient.
 __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const size_t n,
-                       const float lr, const float beta1, const float beta2, const float eps, const float bc1, const float bc2_sqrt,
-                       const float* __restrict__ loss_scale, const int* __restrict__ found_inf, __half* __restrict__ p16,
-                       const int zero_grad) {
+                       const float lr, const float beta1, const float beta2, const float eps, float bc1, float bc2_sqrt,
+                       const int* __restrict__ step_dev, const float* __restrict__ loss_scale, const int* __restrict__ found_inf,
+                       __half* __restrict__ p16, const int zero_grad) {
     const bool skip = found_inf && *found_inf != 0;
+    if (step_dev) {  // step number kept on the device (graph replay): bias corrections computed here
+        __shared__ float s_bc[2];
+        if (threadIdx.x == 0) {
+            const double st = (double)max(*step_dev, 1);
+            s_bc[0] = (float)(1.0 - pow((double)beta1, st));
+            s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, st));
+        }
+        __syncthreads();
+        bc1 = s_bc[0];
+        bc2_sqrt = s_bc[1];
+    }
     const float inv_scale = loss_scale ? 1.0f / *loss_scale : 1.0f;
     for (size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         if (!skip) {
@@ -86,6 +97,11 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __re
         }
         if (zero_grad) g[i] = 0.0f;
     }
+}
+
+// optimizer.step() is skipped by GradScaler when a non-finite gradient was found: the step counter only advances otherwise
+__global__ void k_adam_advance(int* step_dev, const int* __restrict__ found_inf) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !(found_inf && *found_inf)) *step_dev += 1;
 }
 
 // GradScaler.update(): found_inf -> scale *= backoff, tracker = 0; else tracker++ and scale *= growth every `interval`.
@@ -139,14 +155,22 @@ extern "C" int seald_grad_finite_check(const float* g, uint64_t n, int32_t* foun
     return launch_status();
 }
 
+extern "C" int seald_adam_advance(int32_t* step_dev, const int32_t* found_inf, seald_stream_t stream) {
+    if (!step_dev) return SEALD_E_BADARG;
+    k_adam_advance<<<1, 32, 0, to_stream(stream)>>>(step_dev, found_inf);
+    return launch_status();
+}
+
 extern "C" int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
-                               const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad, seald_stream_t stream) {
+                               const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
+                               seald_stream_t stream) {
     if (n == 0) return 0;
-    if (!p || !g || !m || !v || step == 0) return SEALD_E_BADARG;
+    if (!p || !g || !m || !v || (step == 0 && !step_dev)) return SEALD_E_BADARG;
+    if (step == 0) step = 1;
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     const uint32_t blocks = (uint32_t)(n / 256 + 1 < 8u * SEALD_NUM_SMS ? n / 256 + 1 : 8u * SEALD_NUM_SMS);
-    k_adam<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), loss_scale, found_inf,
+    k_adam<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), step_dev, loss_scale, found_inf,
                                                   (__half*)p16, zero_grad);
     return launch_status();
 }

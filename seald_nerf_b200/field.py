@@ -144,9 +144,11 @@ def wgrad_jobs(cfg, ws, grads32, deform=True):
 
 
 def field_backward(cfg, hw, ws, grad_sigma, grad_rgb, time_is_zero, table16, offsets, grad_table32, jobs, n_jobs, m_dev=None,
-                   deform_grad=True, M=None):
+                   deform_grad=True, M=None, time_dev=None):
     """Enqueue the backward pass.  grad_table32 (fp32 [rows, C]) and the fp32 weight gradients referenced by `jobs`
-    are ACCUMULATED into.  deform_grad=False: frozen deformation net (SealD student, SealDNeRF/utils.py:337-359)."""
+    are ACCUMULATED into.  deform_grad=False: frozen deformation net (SealD student, SealDNeRF/utils.py:337-359).
+    time_is_zero: host knowledge of t == 0 (skips the deformation backward); when the host does not know (graph replay)
+    pass time_is_zero=False and time_dev: the kernel then zeroes the gradient itself if *time_dev == 0."""
     M = ws.M if M is None else int(M)
     st = _lib.stream()
     _lib.call("seald_field_heads_backward", ptr(grad_sigma), ptr(grad_rgb), ptr(ws.rgb), ptr(ws.hs), hw.p_sigma, cfg.n_sigma, hw.p_color,
@@ -157,7 +159,7 @@ def field_backward(cfg, hw, ws, grad_sigma, grad_rgb, time_is_zero, table16, off
               ptr(ws.grad_x01) if want_dx else None, M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype,
               int(cfg.align_corners), cfg.interp, F16, F32, ptr(m_dev), st)
     if want_dx:
-        _lib.call("seald_field_deform_backward", ptr(ws.grad_x01), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, ptr(ws.fwd_d),
+        _lib.call("seald_field_deform_backward", ptr(ws.grad_x01), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, ptr(ws.fwd_d),
                   ptr(ws.bwd_d), ptr(ws.gout_d), st)
     _lib.call("seald_mlp_wgrad", C.cast(jobs, C.c_void_p), n_jobs, M, ptr(m_dev), st)
 

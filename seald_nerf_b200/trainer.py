@@ -1,0 +1,362 @@
+"""FusedTrainer — the D-NeRF / SealD-student training step as one graph-captured kernel sequence.
+
+Replaces, for `cuda_ray=True` training, the reference's `Trainer.train_step` + `scaler.scale(loss).backward()` +
+`scaler.step(optimizer)` + `scaler.update()` (dnerf/utils.py:38-115, nerf/utils.py:879-886, Adam as configured in
+main_dnerf.py:129) with:
+
+    march (AABB fused, warp-compacted)  ->  deform MLP  ->  grid encoder  ->  sigma/colour heads  ->  composite
+    -> MSE + background blend  ->  composite bwd  ->  heads bwd  ->  grid scatter + input grad  ->  deform bwd
+    -> weight-gradient GEMMs  ->  [NCCL allreduce of the flat gradient buffer]  ->  finite check + Adam + fp16 refresh
+
+Every buffer is preallocated, no host synchronisation happens inside a step (the sample count stays on the device),
+and the whole step is replayed as CUDA graphs.  Parameters stay the model's own nn.Parameters (re-pointed into one flat
+fp32 buffer), so checkpoints and the drop-in `NeRFNetwork.forward` see the trained values.
+"""
+import math
+
+import torch
+
+from . import _lib
+from . import field as F
+from ._lib import ptr
+
+
+class FusedTrainer:
+    def __init__(self, model, num_rays=4096, max_samples=None, lr=1e-2, lr_net=None, betas=(0.9, 0.99), eps=1e-15, dt_gamma=0.0,
+                 max_steps=1024, T_thresh=1e-4, perturb=True, init_loss_scale=65536.0, growth_interval=2000, train_deform=True,
+                 use_graph=True, world_size=1, process_group=None, device=None):
+        self.model = model
+        self.device = device or model.encoder.embeddings.device
+        if self.device.type != "cuda":
+            raise RuntimeError("FusedTrainer needs a CUDA device (no CPU fallback)")
+        self.N = int(num_rays)
+        self.cfg = model._field_cfg
+        self.cfg.density_scale = float(model.density_scale)
+        self.M = int(max_samples) if max_samples else self.N * 64
+        self.M += (128 - self.M % 128) % 128
+        self.lr, self.lr_net = float(lr), float(lr if lr_net is None else lr_net)
+        self.betas, self.eps = betas, float(eps)
+        self.dt_gamma, self.max_steps, self.T_thresh, self.perturb = float(dt_gamma), int(max_steps), float(T_thresh), bool(perturb)
+        self.train_deform = bool(train_deform)
+        self.growth_interval = int(growth_interval)
+        self.world_size, self.pg = int(world_size), process_group
+        self.use_graph = bool(use_graph)
+        self.global_step = 0
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+
+        # ---- flat fp32 parameter / gradient / Adam state: [grid table | MLP weights] ----------------------------
+        weights = model.mlp_weights()
+        table = model.encoder.embeddings
+        self.n_table = table.numel()
+        sizes = [w.numel() for w in weights]
+        self.n_weights = sum(sizes)
+        n = self.n_table + self.n_weights
+        n_pad = (n + 3) // 4 * 4
+        self.params = torch.zeros(n_pad, **f32)
+        self.grads = torch.zeros(n_pad, **f32)
+        self.exp_avg = torch.zeros(n_pad, **f32)
+        self.exp_avg_sq = torch.zeros(n_pad, **f32)
+        self.n_params = n
+        with torch.no_grad():
+            self.params[:self.n_table].copy_(table.data.reshape(-1))
+            table.data = self.params[:self.n_table].view_as(table)
+            o = self.n_table
+            self.weight_views, self.grad_views = [], []
+            for w, k in zip(weights, sizes):
+                self.params[o:o + k].copy_(w.data.reshape(-1))
+                w.data = self.params[o:o + k].view_as(w)
+                self.weight_views.append(w.data)
+                self.grad_views.append(self.grads[o:o + k].view_as(w))
+                o += k
+        self.grad_table = self.grads[:self.n_table].view_as(table)
+        self.table16 = torch.empty(table.shape, dtype=torch.float16, device=dev)
+        self.table16.copy_(table.data)
+        self.hw = F.HalfWeights(self.cfg, dev)
+        self.hw.refresh(self.weight_views)
+
+        # ---- per-step buffers ----------------------------------------------------------------------------------
+        N, M = self.N, self.M
+        self.rays_o = torch.zeros(N, 3, **f32)
+        self.rays_d = torch.zeros(N, 3, **f32)
+        self.gt = torch.zeros(N, 3, **f32)
+        self.bg = torch.ones(N, 3, **f32)
+        self.time = torch.zeros(1, **f32)
+        self.noises = torch.zeros(N, **f32)
+        self.nears = torch.empty(N, **f32)
+        self.fars = torch.empty(N, **f32)
+        self.bitfield_frame = torch.zeros(model.density_bitfield.shape[1], dtype=torch.uint8, device=dev)
+        self.xyzs = torch.zeros(M, 3, **f32)
+        self.dirs = torch.zeros(M, 3, **f32)
+        self.deltas = torch.zeros(M, 2, **f32)
+        self.rays = torch.zeros(N, 3, **i32)
+        self.counter = torch.zeros(2, **i32)
+        self.weights_sum = torch.empty(N, **f32)
+        self.depth = torch.empty(N, **f32)
+        self.image = torch.empty(N, 3, **f32)
+        self.pred = torch.empty(N, 3, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.grad_image = torch.empty(N, 3, **f32)
+        self.grad_ws = torch.empty(N, **f32)
+        self.grad_sigma = torch.zeros(M, **f32)
+        self.grad_rgb = torch.zeros(M, 3, **f32)
+        self.ws = F.FieldWorkspace(self.cfg, M, dev, training=True)
+        self.jobs, self.n_jobs = F.wgrad_jobs(self.cfg, self.ws, self.grad_views, deform=self.train_deform)
+        self.loss_scale = torch.full((1,), float(init_loss_scale), **f32)
+        self.found_inf = torch.zeros(1, **i32)
+        self.growth_tracker = torch.zeros(1, **i32)
+        self.step_dev = torch.zeros(1, **i32)  # optimiser step counter (device side: the optimiser is graph-replayed)
+        # pinned staging for the end-to-end path
+        self.h_rays_o = torch.zeros(N, 3).pin_memory()
+        self.h_rays_d = torch.zeros(N, 3).pin_memory()
+        self.h_gt = torch.zeros(N, 3).pin_memory()
+        self.h_time = torch.zeros(1).pin_memory()
+        self.h_loss = torch.zeros(1).pin_memory()
+        self._g_fwd_bwd = None
+        self._g_opt = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def set_inputs(self, rays_o, rays_d, time, gt_rgb, bg_color=None):
+        """Device-resident inputs of the next step (copied into the static buffers the graph reads)."""
+        self.rays_o.copy_(rays_o.reshape(-1, 3), non_blocking=True)
+        self.rays_d.copy_(rays_d.reshape(-1, 3), non_blocking=True)
+        self.gt.copy_(gt_rgb.reshape(-1, 3), non_blocking=True)
+        if torch.is_tensor(time):
+            self.time.copy_(time.reshape(-1)[:1], non_blocking=True)
+        else:
+            self.time.fill_(float(time))
+        if bg_color is None:
+            self.bg.fill_(1.0)
+        elif torch.is_tensor(bg_color):
+            self.bg.copy_(bg_color.reshape(-1, 3).expand(self.N, 3), non_blocking=True)
+        else:
+            self.bg.fill_(float(bg_color))
+
+    def set_inputs_host(self, rays_o, rays_d, time, gt_rgb):
+        """Host inputs: staged through pinned memory, H2D on the current stream (counted in the e2e timing)."""
+        self.h_rays_o.copy_(rays_o.reshape(-1, 3))
+        self.h_rays_d.copy_(rays_d.reshape(-1, 3))
+        self.h_gt.copy_(gt_rgb.reshape(-1, 3))
+        self.h_time[0] = float(time)
+        self.rays_o.copy_(self.h_rays_o, non_blocking=True)
+        self.rays_d.copy_(self.h_rays_d, non_blocking=True)
+        self.gt.copy_(self.h_gt, non_blocking=True)
+        self.time.copy_(self.h_time, non_blocking=True)
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.N * 3 * 4 * 3 + 4
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _stages(self):
+        """The step as an ordered list of (name, callable, kernel launches): shared by the real step and by the per-stage timer."""
+        m, cfg = self.model, self.cfg
+        N, M = self.N, self.M
+        ws, hw = self.ws, self.hw
+        m_dev = self.counter[0:1]
+        offsets = m.encoder.offsets
+        inv_count = 1.0 / (3.0 * N * self.world_size)
+        F16, F32 = _lib.F16, _lib.F32
+
+        def select_frame():
+            # occupancy frame of this time stamp (dnerf/renderer.py:285), selected on the device
+            t_idx = torch.floor(self.time * m.time_size).clamp(min=0, max=m.time_size - 1).long()
+            torch.index_select(m.density_bitfield, 0, t_idx, out=self.bitfield_frame.view(1, -1))
+            self.counter.zero_()
+            if self.perturb:
+                self.noises.uniform_(0, 1)
+
+        def march():
+            _lib.call("seald_march_rays_train", ptr(self.rays_o), ptr(self.rays_d), ptr(self.bitfield_frame), float(m.bound), self.dt_gamma,
+                      self.max_steps, N, int(m.cascade), int(m.grid_size), M, None, None, ptr(m.aabb_train), float(m.min_near),
+                      ptr(self.nears), ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(self.rays), ptr(self.counter),
+                      ptr(self.noises), _lib.stream())
+
+        def deform_fwd():
+            _lib.call("seald_field_deform_forward", ptr(self.xyzs), ptr(self.time), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, 1,
+                      ptr(ws.deform), ptr(ws.x01), ptr(ws.in_buf), ptr(ws.fwd_d), _lib.stream())
+
+        def grid_fwd():
+            _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(self.table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim,
+                      cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, ptr(m_dev),
+                      _lib.stream())
+
+        def heads_fwd():
+            _lib.call("seald_field_heads_forward", ptr(ws.feat), ptr(self.dirs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, M,
+                      ptr(m_dev), cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs), ptr(ws.cin), ptr(ws.fwd_s), ptr(ws.fwd_c),
+                      _lib.stream())
+
+        def composite_fwd():
+            _lib.call("seald_composite_rays_train_forward", ptr(ws.sigma), ptr(ws.rgb), ptr(self.deltas), ptr(self.rays), M, N, self.T_thresh,
+                      ptr(self.weights_sum), ptr(self.depth), ptr(self.image), _lib.stream())
+
+        def loss():
+            self.loss.zero_()
+            _lib.call("seald_mse_loss_bg", ptr(self.image), ptr(self.weights_sum), ptr(self.bg), ptr(self.gt), N, inv_count,
+                      ptr(self.loss_scale), ptr(self.pred), ptr(self.loss), ptr(self.grad_image), ptr(self.grad_ws), _lib.stream())
+
+        def composite_bwd():
+            self.grad_sigma.zero_()
+            self.grad_rgb.zero_()
+            _lib.call("seald_composite_rays_train_backward", ptr(self.grad_ws), ptr(self.grad_image), ptr(ws.sigma), ptr(ws.rgb),
+                      ptr(self.deltas), ptr(self.rays), ptr(self.weights_sum), ptr(self.image), M, N, self.T_thresh, ptr(self.grad_sigma),
+                      ptr(self.grad_rgb), _lib.stream())
+
+        def heads_bwd():
+            _lib.call("seald_field_heads_backward", ptr(self.grad_sigma), ptr(self.grad_rgb), ptr(ws.rgb), ptr(ws.hs), hw.p_sigma, cfg.n_sigma,
+                      hw.p_color, cfg.n_color, M, ptr(m_dev), cfg.density_scale, ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.bwd_s), ptr(ws.bwd_c),
+                      ptr(ws.gout_s), ptr(ws.gout_c), ptr(ws.dfeat), _lib.stream())
+
+        def grid_bwd():
+            _lib.call("seald_grid_encode_backward", ptr(ws.dfeat), ptr(ws.x01), ptr(self.table16), ptr(offsets), ptr(self.grad_table), None,
+                      ptr(ws.grad_x01) if self.train_deform else None, M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base,
+                      cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, F32, ptr(m_dev), _lib.stream())
+
+        def deform_bwd():
+            _lib.call("seald_field_deform_backward", ptr(ws.grad_x01), ptr(self.time), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound,
+                      ptr(ws.fwd_d), ptr(ws.bwd_d), ptr(ws.gout_d), _lib.stream())
+
+        def wgrad():
+            import ctypes as C
+            _lib.call("seald_mlp_wgrad", C.cast(self.jobs, C.c_void_p), self.n_jobs, M, ptr(m_dev), _lib.stream())
+
+        stages = [("select_frame", select_frame, 3), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
+                  ("heads_fwd", heads_fwd, 1), ("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3),
+                  ("heads_bwd", heads_bwd, 1), ("grid_bwd", grid_bwd, 3 if self.train_deform else 2)]
+        if self.train_deform:
+            stages.append(("deform_bwd", deform_bwd, 1))
+        stages.append(("wgrad", wgrad, 1))
+        return stages
+
+    def _forward_backward(self):
+        n = 0
+        for _, fn, k in self._stages():
+            fn()
+            n += k
+        return n
+
+    def stage_timings(self, reps=20):
+        """Average device time (ms) of every stage, each timed alone with CUDA events on the current stream.
+        Uses the inputs currently staged; gradients accumulated here are discarded (the gradient buffer is re-zeroed)."""
+        out = {}
+        stages = self._stages() + [("optimizer", self._optimizer, 0)]
+        snapshot = (self.params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.loss_scale.clone(), self.growth_tracker.clone(),
+                    self.table16.clone(), self.hw.flat.clone(), self.step_dev.clone())
+        # one full pass so every stage sees valid inputs
+        for _, fn, _k in stages[:-1]:
+            fn()
+        for name, fn, _k in stages:
+            if name == "select_frame":
+                fn()
+                continue
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                if name == "march":
+                    self.counter.zero_()
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = e0.elapsed_time(e1) / reps
+        for dst, src in zip((self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16, self.hw.flat,
+                             self.step_dev), snapshot):
+            dst.copy_(src)
+        self.grads.zero_()
+        self.found_inf.zero_()
+        out["live_samples"] = int(self.counter[0].item())
+        return out
+
+    def _optimizer(self):
+        st = _lib.stream()
+        b1, b2 = self.betas
+        _lib.call("seald_grad_finite_check", ptr(self.grads), self.n_params, ptr(self.found_inf), st)
+        _lib.call("seald_adam_advance", ptr(self.step_dev), ptr(self.found_inf), st)
+        nt = self.n_table
+        _lib.call("seald_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), nt, self.lr, b1, b2, self.eps,
+                  0, ptr(self.step_dev), ptr(self.loss_scale), ptr(self.found_inf), ptr(self.table16), 1, st)
+        _lib.call("seald_adam_step", self.params.data_ptr() + 4 * nt, self.grads.data_ptr() + 4 * nt, self.exp_avg.data_ptr() + 4 * nt,
+                  self.exp_avg_sq.data_ptr() + 4 * nt, self.n_weights, self.lr_net, b1, b2, self.eps, 0, ptr(self.step_dev),
+                  ptr(self.loss_scale), ptr(self.found_inf), None, 1, st)
+        self.hw.refresh(self.weight_views)
+        _lib.call("seald_loss_scale_update", ptr(self.loss_scale), ptr(self.found_inf), ptr(self.growth_tracker), 2.0, 0.5,
+                  self.growth_interval, st)
+        return 5 + len(self.weight_views)
+
+    def _allreduce(self):
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def step(self):
+        """One optimisation step on the inputs staged by set_inputs*/().  No host synchronisation."""
+        self.global_step += 1
+        if not self.use_graph:
+            n = self._forward_backward()
+            self._allreduce()
+            n += self._optimizer()
+            self.launches_per_step = n
+            return
+        if self._g_fwd_bwd is None:
+            # warm-up on a side stream (module loading, cudaFuncSetAttribute), then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._snapshot = (self.params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.loss_scale.clone(),
+                                  self.growth_tracker.clone(), self.table16.clone(), self.hw.flat.clone(), self.step_dev.clone())
+                self._forward_backward()
+                self._optimizer()
+                # undo the warm-up update
+                for dst, src in zip((self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16,
+                                     self.hw.flat, self.step_dev), self._snapshot):
+                    dst.copy_(src)
+                self.grads.zero_()
+                self.found_inf.zero_()
+                del self._snapshot
+            torch.cuda.current_stream().wait_stream(s)
+            self._g_fwd_bwd = torch.cuda.CUDAGraph()
+            if self.world_size == 1:
+                # single GPU: the whole step (forward, backward, optimiser) is ONE graph
+                with torch.cuda.graph(self._g_fwd_bwd):
+                    self._n_fb = self._forward_backward()
+                    self._n_opt = self._optimizer()
+            else:
+                # data parallel: [forward+backward] graph -> NCCL allreduce of the flat gradient buffer -> [optimiser] graph
+                with torch.cuda.graph(self._g_fwd_bwd):
+                    self._n_fb = self._forward_backward()
+                self._g_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._g_opt):
+                    self._n_opt = self._optimizer()
+            self.launches_per_step = self._n_fb + self._n_opt
+        self._g_fwd_bwd.replay()
+        if self.world_size > 1:
+            self._allreduce()
+            self._g_opt.replay()
+
+    def train_step(self, rays_o, rays_d, time, gt_rgb, bg_color=None):
+        """Public API: one training step on device tensors; returns the (device) loss of this step."""
+        self.set_inputs(rays_o, rays_d, time, gt_rgb, bg_color)
+        self.step()
+        return self.loss
+
+    def train_step_host(self, rays_o, rays_d, time, gt_rgb):
+        """End-to-end variant: host inputs in, host loss out (one D2H read + sync per step)."""
+        self.set_inputs_host(rays_o, rays_d, time, gt_rgb)
+        self.step()
+        self.h_loss.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.h_loss[0])
+
+    def calibrate_max_samples(self, rays_o, rays_d, time, margin=1.25):
+        """Run the march once with a generous bound to size M (the reference's `mean_count` estimate, raymarching.py:200-203)."""
+        m = self.model
+        nears, fars = None, None
+        from . import raymarching
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, m.aabb_train, m.min_near)
+        t = m._frame_index(torch.as_tensor([[float(time)]], device=self.device))
+        counter = torch.zeros(2, dtype=torch.int32, device=self.device)
+        raymarching.march_rays_train(rays_o, rays_d, m.bound, m.density_bitfield[t], m.cascade, m.grid_size, nears, fars, counter, -1, False, 128,
+                                     True, self.dt_gamma, self.max_steps)
+        return int(counter[0].item() * margin)

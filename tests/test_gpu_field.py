@@ -2,7 +2,7 @@
 the torch-CPU oracle (oracle/field.py).
 
 Tolerances (fp16 operands, fp32 accumulation): forward outputs rtol 2e-2 / atol 2e-3 against the fp16-emulating
-oracle; gradients are compared relative to their largest magnitude: |g - g_ref| <= 3e-2 * max|g_ref|.
+oracle; gradients are compared relative to their largest magnitude: |g - g_ref| <= 6e-2 * max|g_ref| (fp16 activations AND fp16 activation gradients).
 """
 import numpy as np
 import pytest
@@ -84,7 +84,7 @@ def test_field_forward_and_backward(cuda_dev, tval):
             assert gm is None or float(gm.abs().max()) == 0.0  # no gradient reaches the deformation net at t == 0
             continue
         assert gm is not None, name
-        _close_rel(gm.cpu().numpy(), p.grad.numpy(), 4e-2, name)
+        _close_rel(gm.cpu().numpy(), p.grad.numpy(), 6e-2, name)
     _close_rel(net.encoder.embeddings.grad.cpu().numpy(), tab.grad.numpy(), 4e-2, "grid table")
 
 
