@@ -197,6 +197,9 @@ int seald_mse_loss_bg(const float* image, const float* weights_sum, const float*
                       const float* loss_scale, float* pred, float* loss_sum, float* grad_image, float* grad_ws, seald_stream_t stream);
 /* dst[rows][ld] f16 = src[rows][cols] f32, zero padded columns. */
 int seald_cast_pad_f16(const float* src, void* dst, uint32_t rows, uint32_t cols, uint32_t ld, seald_stream_t stream);
+/* n matrices in one launch; src/dst/rows/cols/ld are HOST arrays of length n (<= 32). */
+int seald_cast_pad_f16_batch(const void* const* src, void* const* dst, const uint32_t* rows, const uint32_t* cols, const uint32_t* ld, int n,
+                             seald_stream_t stream);
 int seald_grad_finite_check(const float* g, uint64_t n, int32_t* found_inf, seald_stream_t stream);
 /* step_dev (optional device int32) overrides `step`: the step counter lives on the device so the optimiser can be replayed
  * from a CUDA graph; seald_adam_advance increments it unless *found_inf (GradScaler skips optimizer.step() then). */

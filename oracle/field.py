@@ -112,11 +112,15 @@ def mlp(x, weights, half=True):
 
 
 def dnerf_forward(xyz, dirs, t, deform_w, sigma_w, color_w, table, offsets, S, H, bound=1.0, density_scale=1.0, half=True,
-                  t0_mode=1, scales=None, gridtype=0):
-    """dnerf/network.py:123-169 (t0_mode=1) / :171-208 density (t0_mode=2).  t: python float."""
+                  t0_mode=1, scales=None, gridtype=0, deform_values=None):
+    """dnerf/network.py:123-169 (t0_mode=1) / :171-208 density (t0_mode=2).  t: python float.
+    deform_values (optional): use these numbers for the deformation while keeping the oracle's own gradient path
+    (lets a test evaluate the grid at exactly the positions another implementation produced)."""
     tt = torch.full((xyz.shape[0], 1), float(t), dtype=xyz.dtype)
     enc = torch.cat([freq_encode(xyz, 10), freq_encode(tt, 6)], dim=1)
     deform = mlp(enc, deform_w, half)
+    if deform_values is not None:
+        deform = deform + (deform_values - deform).detach()
     if float(t) == 0.0:
         x = xyz
         if t0_mode == 1:

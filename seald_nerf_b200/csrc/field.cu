@@ -320,6 +320,8 @@ struct WgradJobs {
 
 constexpr int kWgChunk = 64;  // rows staged per step
 
+// Warp -> output tiles: the N/16 m-tiles are spread over the 8 warps (N in {16,32,64,128}); the warps sharing an m-tile
+// split the K/8 n-tiles in even-sized contiguous ranges (pairs of n-tiles share one ldmatrix.x4).
 __global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M, const int* __restrict__ m_dev, const int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const WgradJob jb = jobs.j[blockIdx.y];
@@ -339,35 +341,38 @@ __global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    // output tiles: (N/16) x (K/8) of 16x8; warp w takes m-tile (w % MT) and every (8/ MT ... ) see below
     const int MT = N / 16, NT = K / 8;
-    // distribute: tile id = mt * NT + nt ; warp handles ids with (id % 8 == warp) when MT < 8, else its own m-tile
-    // To keep registers bounded: each warp owns up to 16 n-tiles of one m-tile.
-    const int total = MT * NT;
-    const int per_warp = (total + 7) / 8;  // <= 16 for 128x128
-    float acc[16][4];
-#pragma unroll
-    for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
-    const int first = warp * per_warp;  // contiguous range of tile ids: share an m-tile whenever per_warp divides NT
+    const int wpm = 8 / MT;                        // warps per m-tile
+    const int mt = warp / wpm;
+    const int cnt = (((NT + wpm - 1) / wpm) + 1) & ~1;  // n-tiles per warp (even)
+    const int nt0 = (warp % wpm) * cnt;
+    const int n_pairs = max(0, min(cnt, NT - nt0)) / 2;  // <= 8
 
+    float acc[8][2][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) acc[i][h][0] = acc[i][h][1] = acc[i][h][2] = acc[i][h][3] = 0.0f;
+
+    const int gchunks = N / 8, achunks = K / 8, chunks = gchunks + achunks;
     auto stage = [&](int buf, int m0) {
-        const int gchunks = N / 8, achunks = K / 8;
-        for (int i = threadIdx.x; i < kWgChunk * (gchunks + achunks); i += blockDim.x) {
-            const int r = i / (gchunks + achunks), c = i - r * (gchunks + achunks);
+        for (int i = threadIdx.x; i < kWgChunk * chunks; i += 256) {
+            const int r = i / chunks, c = i - r * chunks;
             const int row = m0 + r;
-            if (c < gchunks) {
-                __half* dst = s_gt[buf] + r * gs + c * 8;
-                if (row < m_end) cp_async16(dst, jb.G + (size_t)row * jb.ldg + c * 8);
-                else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-            } else {
-                const int ca = c - gchunks;
-                __half* dst = s_at[buf] + r * as + ca * 8;
-                if (row < m_end) cp_async16(dst, jb.A + (size_t)row * jb.lda + ca * 8);
-                else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-            }
+            const bool is_g = c < gchunks;
+            const int cc = is_g ? c : c - gchunks;
+            __half* dst = is_g ? (s_gt[buf] + r * gs + cc * 8) : (s_at[buf] + r * as + cc * 8);
+            if (row < m_end) cp_async16(dst, is_g ? (jb.G + (size_t)row * jb.ldg + cc * 8) : (jb.A + (size_t)row * jb.lda + cc * 8));
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
         }
         cp_async_commit();
     };
+
+    // per-lane smem offsets of the two ldmatrix patterns (halves)
+    //  A = G^T (m = n_idx, k = sample): matrices (s 0-7, n 0-7), (s 0-7, n 8-15), (s 8-15, n 0-7), (s 8-15, n 8-15), transposed
+    const int a_off = ((lane & 7) + 8 * (lane >> 4)) * gs + 16 * mt + 8 * ((lane >> 3) & 1);
+    //  B (k = sample, n = k_idx), two n-tiles: (s 0-7, c 0-7), (s 8-15, c 0-7), (s 0-7, c 8-15), (s 8-15, c 8-15), transposed
+    const int b_off = ((lane & 7) + 8 * ((lane >> 3) & 1)) * as + 8 * nt0 + 8 * (lane >> 4);
 
     const int n_steps = (m_end - m_begin + kWgChunk - 1) / kWgChunk;
     stage(0, m_begin);
@@ -376,52 +381,46 @@ __global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M
         cp_async_wait<0>();
         __syncthreads();
         if (s + 1 < n_steps) stage(buf ^ 1, m_begin + (s + 1) * kWgChunk);
-        const __half* gt = s_gt[buf];
-        const __half* at = s_at[buf];
+        if (n_pairs > 0) {
+            const __half* gt = s_gt[buf] + a_off;
+            const __half* at = s_at[buf] + b_off;
 #pragma unroll
-        for (int kk = 0; kk < kWgChunk / 16; kk++) {  // k dimension = rows (samples)
-            int cur_mt = -1;
-            uint32_t a[4];
+            for (int kk = 0; kk < kWgChunk / 16; kk++) {
+                uint32_t a[4];
+                ldmatrix_x4_trans(a, gt + 16 * kk * gs);
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int id = first + i;
-                if (i < per_warp && id < total) {
-                    const int mt = id / NT, nt = id - mt * NT;
-                    if (mt != cur_mt) {
-                        // A operand = G^T: element (m = n_idx, k = sample) -> transposed load from [sample][n_idx]
-                        // matrices: m0 (rows n 0-7, k 0-7), m1 (rows n 8-15, k 0-7), m2 (n 0-7, k 8-15), m3 (n 8-15, k 8-15)
-                        ldmatrix_x4_trans(a, gt + (16 * kk + (lane & 7) + 8 * (lane >> 4)) * gs + 16 * mt + 8 * ((lane >> 3) & 1));
-                        cur_mt = mt;
+                for (int pr = 0; pr < 8; pr++) {
+                    if (pr < n_pairs) {
+                        uint32_t b[4];
+                        ldmatrix_x4_trans(b, at + 16 * kk * as + 16 * pr);
+                        mma_16816(acc[pr][0], a, b[0], b[1]);
+                        mma_16816(acc[pr][1], a, b[2], b[3]);
                     }
-                    // B operand: (k = sample, n = K idx): transposed load from [sample][k_idx]
-                    uint32_t b[2];
-                    {
-                        uint32_t r4[4];
-                        // x4 would fetch two n-tiles; fetch one n-tile (two matrices) via the x2 form encoded as x4 with duplicates
-                        ldmatrix_x4_trans(r4, at + (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * as + 8 * nt);
-                        b[0] = r4[0];
-                        b[1] = r4[1];
-                    }
-                    mma_16816(acc[i], a, b[0], b[1]);
                 }
             }
         }
     }
-    // flush partial sums
+    // flush partial sums with fp32 (vector) atomics
+    const bool vec_ok = (jb.ldw % 2 == 0) && (((uintptr_t)jb.dW % 8) == 0);
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int id = first + i;
-        if (i < per_warp && id < total) {
-            const int mt = id / NT, nt = id - mt * NT;
-            const int r0 = 16 * mt + g, r1 = r0 + 8;
-            const int c0 = 8 * nt + 2 * t;
-            if (r0 < jb.n_real) {
-                if (c0 < jb.k_real) atomicAdd(jb.dW + (size_t)r0 * jb.ldw + c0, acc[i][0]);
-                if (c0 + 1 < jb.k_real) atomicAdd(jb.dW + (size_t)r0 * jb.ldw + c0 + 1, acc[i][1]);
-            }
-            if (r1 < jb.n_real) {
-                if (c0 < jb.k_real) atomicAdd(jb.dW + (size_t)r1 * jb.ldw + c0, acc[i][2]);
-                if (c0 + 1 < jb.k_real) atomicAdd(jb.dW + (size_t)r1 * jb.ldw + c0 + 1, acc[i][3]);
+    for (int pr = 0; pr < 8; pr++) {
+        if (pr < n_pairs) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int c0 = 8 * (nt0 + 2 * pr + h) + 2 * t;
+#pragma unroll
+                for (int half_ = 0; half_ < 2; half_++) {
+                    const int r = 16 * mt + g + 8 * half_;
+                    if (r >= jb.n_real || c0 >= jb.k_real) continue;
+                    const float v0 = acc[pr][h][2 * half_], v1 = acc[pr][h][2 * half_ + 1];
+                    float* dst = jb.dW + (size_t)r * jb.ldw + c0;
+                    if (vec_ok && c0 + 1 < jb.k_real) {
+                        atomicAdd(reinterpret_cast<float2*>(dst), make_float2(v0, v1));
+                    } else {
+                        atomicAdd(dst, v0);
+                        if (c0 + 1 < jb.k_real) atomicAdd(dst + 1, v1);
+                    }
+                }
             }
         }
     }
@@ -566,7 +565,7 @@ extern "C" int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t
     for (int i = 0; i < n_jobs; i++) {
         const seald_wgrad_job& a = jobs[i];
         if (!a.G || !a.A || !a.dW) return SEALD_E_BADARG;
-        if (a.N % 16 || a.K % 16 || a.N <= 0 || a.K <= 0 || a.N > 128 || a.K > 128 || a.ldg % 8 || a.lda % 8) return SEALD_E_UNSUPPORTED;
+        if ((a.N != 16 && a.N != 32 && a.N != 64 && a.N != 128) || a.K % 16 || a.K <= 0 || a.K > 128 || a.ldg % 8 || a.lda % 8) return SEALD_E_UNSUPPORTED;
         if (((uintptr_t)a.G % 16) || ((uintptr_t)a.A % 16)) return SEALD_E_ALIGN;
         WgradJob& j = js.j[i];
         j.G = (const __half*)a.G; j.A = (const __half*)a.A; j.dW = a.dW;

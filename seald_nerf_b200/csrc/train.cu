@@ -51,6 +51,22 @@ __global__ void k_cast_pad_f16(const float* __restrict__ src, __half* __restrict
     dst[i] = __float2half_rn(c < cols ? src[(size_t)r * cols + c] : 0.0f);
 }
 
+// Batched variant: every MLP weight of the field in one launch (13 matrices -> one kernel instead of 13).
+struct CastSeg { const float* src; __half* dst; uint32_t rows, cols, ld, first; };  // first = running element offset
+constexpr int kMaxCastSegs = 32;
+struct CastSegs { CastSeg s[kMaxCastSegs]; int n; uint32_t total; };
+
+__global__ void k_cast_pad_f16_batch(const CastSegs segs) {
+    const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i >= segs.total) return;
+    int k = 0;
+    while (k + 1 < segs.n && i >= segs.s[k + 1].first) k++;
+    const CastSeg sg = segs.s[k];
+    const uint32_t j = i - sg.first;
+    const uint32_t r = j / sg.ld, c = j - r * sg.ld;
+    sg.dst[j] = __float2half_rn(c < sg.cols ? sg.src[(size_t)r * sg.cols + c] : 0.0f);
+}
+
 // found_inf[0] = 1 if any gradient is inf/nan
 __global__ void k_grad_finite_check(const float* __restrict__ g, const size_t n, int* __restrict__ found_inf) {
     bool bad = false;
@@ -83,7 +99,37 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __re
         bc2_sqrt = s_bc[1];
     }
     const float inv_scale = loss_scale ? 1.0f / *loss_scale : 1.0f;
-    for (size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // 128-bit path over the aligned body (n is a multiple of 4 for the slabs the trainer passes)
+    const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0) && (!p16 || ((uintptr_t)p16 & 7) == 0);
+    const size_t n4 = vec ? n / 4 : 0;
+    const float step_size = lr / bc1;
+    for (size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 g4 = reinterpret_cast<float4*>(g)[i];
+        if (!skip) {
+            float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+            float* pp = reinterpret_cast<float*>(&p4); float* gg = reinterpret_cast<float*>(&g4);
+            float* mm = reinterpret_cast<float*>(&m4); float* vv = reinterpret_cast<float*>(&v4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float gi = gg[k] * inv_scale;
+                mm[k] = beta1 * mm[k] + (1.0f - beta1) * gi;
+                vv[k] = beta2 * vv[k] + (1.0f - beta2) * gi * gi;
+                pp[k] = pp[k] - step_size * (mm[k] / (sqrtf(vv[k]) / bc2_sqrt + eps));
+            }
+            reinterpret_cast<float4*>(p)[i] = p4;
+            reinterpret_cast<float4*>(m)[i] = m4;
+            reinterpret_cast<float4*>(v)[i] = v4;
+            if (p16) {
+                const __half2 lo = __floats2half2_rn(pp[0], pp[1]), hi = __floats2half2_rn(pp[2], pp[3]);
+                uint2 u;
+                u.x = *reinterpret_cast<const uint32_t*>(&lo);
+                u.y = *reinterpret_cast<const uint32_t*>(&hi);
+                reinterpret_cast<uint2*>(p16)[i] = u;
+            }
+        }
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (size_t i = n4 * 4 + threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         if (!skip) {
             const float gi = g[i] * inv_scale;
             const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
@@ -143,6 +189,23 @@ extern "C" int seald_cast_pad_f16(const float* src, void* dst, uint32_t rows, ui
     if (!src || !dst || ld < cols) return SEALD_E_BADARG;
     const size_t n = (size_t)rows * ld;
     k_cast_pad_f16<<<(uint32_t)div_up(n, (size_t)256), 256, 0, to_stream(stream)>>>(src, (__half*)dst, rows, cols, ld);
+    return launch_status();
+}
+
+extern "C" int seald_cast_pad_f16_batch(const void* const* src, void* const* dst, const uint32_t* rows, const uint32_t* cols,
+                                        const uint32_t* ld, int n, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!src || !dst || !rows || !cols || !ld || n < 0 || n > kMaxCastSegs) return SEALD_E_BADARG;
+    CastSegs segs;
+    uint32_t total = 0;
+    for (int i = 0; i < n; i++) {
+        if (!src[i] || !dst[i] || ld[i] < cols[i]) return SEALD_E_BADARG;
+        segs.s[i] = CastSeg{(const float*)src[i], (__half*)dst[i], rows[i], cols[i], ld[i], total};
+        total += rows[i] * ld[i];
+    }
+    segs.n = n;
+    segs.total = total;
+    k_cast_pad_f16_batch<<<div_up(total, 256u), 256, 0, to_stream(stream)>>>(segs);
     return launch_status();
 }
 

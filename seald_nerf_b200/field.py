@@ -59,12 +59,20 @@ class HalfWeights:
         self.deform, self.sigma, self.color = self.views[:nd], self.views[nd:nd + ns], self.views[nd + ns:]
         self.p_deform, self.p_sigma, self.p_color = _lib.ptr_array(self.deform), _lib.ptr_array(self.sigma), _lib.ptr_array(self.color)
 
+        n = len(self.views)
+        self._dst = _lib.ptr_array(self.views)
+        self._rows = (C.c_uint32 * n)(*[r for r, c, ld in self.shapes])
+        self._cols = (C.c_uint32 * n)(*[c for r, c, ld in self.shapes])
+        self._ld = (C.c_uint32 * n)(*[ld for r, c, ld in self.shapes])
+
     def refresh(self, weights32):
-        """weights32: list of fp32 [out,in] tensors in the same order."""
-        st = _lib.stream()
-        for w, v, (r, c, ld) in zip(weights32, self.views, self.shapes):
+        """weights32: list of fp32 [out,in] tensors in the same order; one batched cast+pad launch."""
+        ws = []
+        for w, (r, c, ld) in zip(weights32, self.shapes):
             assert tuple(w.shape) == (r, c), (tuple(w.shape), (r, c))
-            _lib.call("seald_cast_pad_f16", ptr(w.contiguous()), ptr(v), r, c, ld, st)
+            ws.append(w if w.is_contiguous() else w.contiguous())
+        src = _lib.ptr_array(ws)
+        _lib.call("seald_cast_pad_f16_batch", src, self._dst, self._rows, self._cols, self._ld, len(ws), _lib.stream())
 
 
 class FieldWorkspace:

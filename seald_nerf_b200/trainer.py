@@ -283,7 +283,7 @@ class FusedTrainer:
         self.hw.refresh(self.weight_views)
         _lib.call("seald_loss_scale_update", ptr(self.loss_scale), ptr(self.found_inf), ptr(self.growth_tracker), 2.0, 0.5,
                   self.growth_interval, st)
-        return 5 + len(self.weight_views)
+        return 6
 
     def _allreduce(self):
         if self.world_size > 1:

@@ -135,8 +135,10 @@ def test_forward_backward_vs_oracle_and_reference(cuda_dev, case, dtype):
         grad_x = torch.empty(B, D, device=d)
         _lib.call("seald_grid_encode_backward", ptr(tg), ptr(tx), ptr(tt), ptr(to), ptr(grad_table), None, ptr(grad_x), B, D, C, L, S,
                   base, gridtype, int(align), interp, dt, gdt, None, _lib.stream())
-        tol = (1e-3 if gtorch == torch.float16 else 1e-5) * np.abs(gt_o).max()
-        np.testing.assert_allclose(grad_table.float().cpu().numpy(), gt_o, rtol=1e-2 if gtorch == torch.float16 else 1e-4, atol=tol)
+        # an fp16 gradient table is accumulated with half2 atomics (like the reference, gridencoder.cu:325-331): every add
+        # rounds to fp16, so cells that collect many points carry an error of a few 1e-3 of the largest entry
+        tol = (5e-3 if gtorch == torch.float16 else 1e-5) * np.abs(gt_o).max()
+        np.testing.assert_allclose(grad_table.float().cpu().numpy(), gt_o, rtol=3e-2 if gtorch == torch.float16 else 1e-4, atol=tol)
         np.testing.assert_allclose(grad_x.cpu().numpy(), gx_o, rtol=2e-2 if dtype == torch.float16 else 1e-3,
                                    atol=(2e-3 if dtype == torch.float16 else 1e-4) * np.abs(gx_o).max())
     # dy_dx-based input gradient path agrees with the recompute path
