@@ -123,6 +123,78 @@ int seald_compact_alive(const int32_t* rays_alive, uint32_t n_alive, const int32
                         int32_t* n_out_dev, int32_t* scratch, seald_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Seal editing proxy mapping (SealNeRF/seal_utils.py runtime: SealMapper.map_mask :132-153,
+ * SealBBoxMapper.map_to_origin :244-286, SealBrushMapper.map_to_origin :415-461,
+ * SealAnchorMapper.map_to_origin :522-578, SealMapper.map_color :48-81).
+ * The descriptor mirrors the tensors the reference keeps in `map_data` / `map_triangles` / `map_test_dir`;
+ * the struct itself lives in HOST memory, its pointer members are DEVICE arrays.
+ * ------------------------------------------------------------------------------------------------ */
+#define SEALD_SEAL_BBOX 0
+#define SEALD_SEAL_BRUSH 1
+#define SEALD_SEAL_ANCHOR 2
+#define SEALD_SEAL_ATT_LINEAR 0
+#define SEALD_SEAL_ATT_DRY 1
+
+typedef struct {
+    int32_t type;              /* SEALD_SEAL_*                                                        */
+    int32_t n_bounds;          /* B of map_bound [B,2,3] (min row, max row)                           */
+    int32_t n_tris;            /* F of map_triangles [F,3,3]                                          */
+    int32_t n_border;          /* brush: P of border_points [P,3]                                     */
+    const float* bounds;       /* device [B,2,3]                                                      */
+    const float* tris;         /* device [F,3,3]                                                      */
+    const float* border;       /* device [P,3] or NULL                                                */
+    float test_dir[3];         /* map_test_dir, or trimesh's magic direction (seal_utils.py:686-688)  */
+    float transform[12];       /* bbox: rows 0..2 of map_data['transform'] (inverse 4x4, row-major)   */
+    float rotation[9];         /* bbox: map_data['rotation'] (row-major)                              */
+    float scale[3];            /* bbox / anchor: map_data['scale']                                    */
+    float center[3];           /* bbox: from_center; brush: plane point                               */
+    int32_t has_map_source;    /* bbox: 'map_source' in map_data                                      */
+    float empty_bound[6];      /* bbox: map_data['empty_bound'] (min xyz, max xyz)                    */
+    float map_source[3];
+    float normal_expand[3];    /* brush                                                               */
+    float attenuation_distance;
+    int32_t attenuation_mode;  /* SEALD_SEAL_ATT_*                                                    */
+    float v_anchor[3], v_offset[3], v_h[3]; /* anchor                                                 */
+    float len_h, radius;
+} seald_seal_mapper;
+
+typedef struct {
+    int32_t has_hsv, has_rgb, has_image;
+    float hsv[3];              /* map_data['hsv']                                                     */
+    float rgb[3];              /* map_data['rgb']                                                     */
+    float rgb_light_offset;
+    int32_t img_h, img_w;
+    const float* image;        /* device [H,W,3]                                                      */
+    const float* image_mask;   /* device [H,W]                                                        */
+    float v_norm[3], v_o[3], v_w[3], v_h[3];
+} seald_seal_color;
+
+/* (points', dirs', mask) = mapper.map_to_origin(points, dirs).  points/dirs [M,3] fp32 (dirs may be NULL), outputs may
+ * alias the inputs; mask [M] bytes (0/1, torch.bool layout).  m_dev: optional live row count.  scratch: one int32
+ * (anchor only: the batch-wide `map_mask.any()` early exit, seal_utils.py:526-528). */
+int seald_seal_map_to_origin(const seald_seal_mapper* mapper, const float* points, const float* dirs, uint32_t M,
+                             const int32_t* m_dev, float* points_out, float* dirs_out, uint8_t* mask, int32_t* scratch,
+                             seald_stream_t stream);
+/* rgbs[mask] = mapper.map_color(points[mask], dirs[mask], rgbs[mask]) in place; rgbs [M,3] fp32, points = MAPPED points
+ * (only read for the image projection).  scratch: 4 floats (sums for the batch mean of V, seal_utils.py:771-773). */
+int seald_seal_map_color(const seald_seal_color* color, const float* points, const uint8_t* mask, float* rgbs, uint32_t M,
+                         const int32_t* m_dev, float* scratch, seald_stream_t stream);
+/* Inference / training march with the proxy mapping fused in: same contracts as seald_march_rays /
+ * seald_march_rays_train, but xyzs/dirs receive the MAPPED samples and mask [M] their map mask (replaces
+ * march_rays + seal_mapper.map_to_origin, SealDNeRF/renderer.py:245-253 and :150-158).  bbox and brush mappers. */
+int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                          const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                          uint32_t C, uint32_t H, const uint8_t* bitfield, const float* nears, const float* fars,
+                          float* xyzs, float* dirs, float* deltas, const float* noises, const int32_t* n_alive_dev,
+                          const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream);
+int seald_march_rays_train_seal(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound,
+                                float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                const float* nears, const float* fars, const float* aabb6, float min_near,
+                                float* nears_out, float* fars_out, float* xyzs, float* dirs, float* deltas, int32_t* rays,
+                                int32_t* counter, const float* noises, const seald_seal_mapper* mapper, uint8_t* mask,
+                                seald_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Small encoders.  Replace freq_encode_forward/backward (freqencoder/src/freqencoder.h:7-10) and
  * sh_encode_forward/backward (shencoder/src/shencoder.h:7-8); SH degree 1..4 (the D-NeRF setting).
  * ------------------------------------------------------------------------------------------------ */

@@ -11,7 +11,7 @@ The Python surface mirrors the reference's own packages (same names, arguments, 
     seald_nerf_b200.activation.trunc_exp           <- activation.py
     seald_nerf_b200.dnerf.{renderer,network}       <- dnerf/renderer.py, dnerf/network.py
     seald_nerf_b200.SealDNeRF.{renderer,network}   <- SealDNeRF/renderer.py, SealDNeRF/network.py
-    seald_nerf_b200.seal                           <- SealNeRF/seal_utils.py runtime mapping
+    seald_nerf_b200.SealNeRF.seal_utils            <- SealNeRF/seal_utils.py (runtime proxy mapping)
 
 `install_aliases()` registers them under the reference's top-level import names (`import raymarching`,
 `from gridencoder import GridEncoder`, ...) so reference host code runs unchanged on top of this package.

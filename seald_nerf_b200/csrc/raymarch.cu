@@ -14,6 +14,7 @@
 #include <limits>
 
 #include "common.cuh"
+#include "seal.cuh"
 
 namespace seald {
 
@@ -252,13 +253,15 @@ __device__ __forceinline__ float skip_voxel(const Ray& r, const MarchConst& mc, 
 // ------------------------------------------------------------------------------------------------
 // training march
 // ------------------------------------------------------------------------------------------------
+template <bool SEAL>
 __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
                                    const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t N, const uint32_t C,
                                    const uint32_t H, const uint32_t M, const float* __restrict__ nears, const float* __restrict__ fars,
                                    const float* __restrict__ aabb, const float min_near, float* __restrict__ nears_out,
                                    float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
                                    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter,
-                                   const float* __restrict__ noises) {
+                                   const float* __restrict__ noises, const __grid_constant__ seald_seal_mapper mp,
+                                   uint8_t* __restrict__ seal_mask) {
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     const bool active = n < N;
@@ -323,6 +326,7 @@ __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float
     xyzs += (size_t)point_index * 3;
     dirs += (size_t)point_index * 3;
     deltas += (size_t)point_index * 2;
+    if (SEAL) seal_mask += point_index;
 
     // pass 2: write
     t = t0;
@@ -331,8 +335,16 @@ __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float
     Probe p;
     while (t < far && step < num_steps) {
         if (probe_grid(r, mc, grid, t, p)) {
-            xyzs[0] = p.x; xyzs[1] = p.y; xyzs[2] = p.z;
-            dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+            if (SEAL) {
+                // Seal proxy mapping fused in: the edited sample is remapped before it is stored (and encoded)
+                float sx = p.x, sy = p.y, sz = p.z, sdx = r.dx, sdy = r.dy, sdz = r.dz;
+                seal_mask[step] = seal_map_sample(mp, sx, sy, sz, sdx, sdy, sdz) ? 1 : 0;
+                xyzs[0] = sx; xyzs[1] = sy; xyzs[2] = sz;
+                dirs[0] = sdx; dirs[1] = sdy; dirs[2] = sdz;
+            } else {
+                xyzs[0] = p.x; xyzs[1] = p.y; xyzs[2] = p.z;
+                dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+            }
             t += p.dt;
             deltas[0] = p.dt;
             deltas[1] = t - last_t;
@@ -359,12 +371,14 @@ __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float
 constexpr uint32_t kMarchWarps = 8;
 constexpr uint32_t kMaxStepsSmem = 1024;
 
+template <bool SEAL>
 __global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid, const float bound,
     const float dt_gamma, const uint32_t max_steps, const uint32_t N, const uint32_t C, const uint32_t H, const uint32_t M,
     const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ aabb, const float min_near,
     float* __restrict__ nears_out, float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
-    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter, const float* __restrict__ noises) {
+    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter, const float* __restrict__ noises,
+    const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask) {
     __shared__ float s_t[kMarchWarps][kMaxStepsSmem];
     __shared__ uint32_t s_cnt[kMarchWarps];
     __shared__ uint32_t s_off[kMarchWarps];
@@ -488,8 +502,15 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
         }
         const float t_new = t + dt;
         const size_t s = (size_t)point_index + j;
-        xyzs[s * 3] = x; xyzs[s * 3 + 1] = y; xyzs[s * 3 + 2] = z;
-        dirs[s * 3] = r.dx; dirs[s * 3 + 1] = r.dy; dirs[s * 3 + 2] = r.dz;
+        if (SEAL) {
+            float sx = x, sy = y, sz = z, sdx = r.dx, sdy = r.dy, sdz = r.dz;
+            seal_mask[s] = seal_map_sample(mp, sx, sy, sz, sdx, sdy, sdz) ? 1 : 0;
+            xyzs[s * 3] = sx; xyzs[s * 3 + 1] = sy; xyzs[s * 3 + 2] = sz;
+            dirs[s * 3] = sdx; dirs[s * 3 + 1] = sdy; dirs[s * 3 + 2] = sdz;
+        } else {
+            xyzs[s * 3] = x; xyzs[s * 3 + 1] = y; xyzs[s * 3 + 2] = z;
+            dirs[s * 3] = r.dx; dirs[s * 3 + 1] = r.dy; dirs[s * 3 + 2] = r.dz;
+        }
         deltas[s * 2] = dt;
         deltas[s * 2 + 1] = t_new - last_t;
     }
@@ -599,11 +620,13 @@ __global__ void k_composite_train_bwd(const float* __restrict__ grad_weights_sum
 // ------------------------------------------------------------------------------------------------
 // inference march / composite
 // ------------------------------------------------------------------------------------------------
+template <bool SEAL>
 __global__ void k_march_rays(uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
                              const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float bound, const float dt_gamma,
                              const uint32_t max_steps, const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid,
                              const float* __restrict__ nears, const float* __restrict__ fars, float* xyzs, float* dirs, float* deltas,
-                             const float* __restrict__ noises, const int* __restrict__ n_alive_dev) {
+                             const float* __restrict__ noises, const int* __restrict__ n_alive_dev,
+                             const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask) {
     if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= n_alive) return;
@@ -616,6 +639,7 @@ __global__ void k_march_rays(uint32_t n_alive, const uint32_t n_step, const int*
     xyzs += (size_t)n * n_step * 3;
     dirs += (size_t)n * n_step * 3;
     deltas += (size_t)n * n_step * 2;
+    if (SEAL) seal_mask += (size_t)n * n_step;
 
     Ray r;
     r.ox = rays_o[0]; r.oy = rays_o[1]; r.oz = rays_o[2];
@@ -632,8 +656,15 @@ __global__ void k_march_rays(uint32_t n_alive, const uint32_t n_step, const int*
     Probe p;
     while (t < far && step < n_step) {
         if (probe_grid(r, mc, grid, t, p)) {
-            xyzs[0] = p.x; xyzs[1] = p.y; xyzs[2] = p.z;
-            dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+            if (SEAL) {
+                float sx = p.x, sy = p.y, sz = p.z, sdx = r.dx, sdy = r.dy, sdz = r.dz;
+                seal_mask[step] = seal_map_sample(mp, sx, sy, sz, sdx, sdy, sdz) ? 1 : 0;
+                xyzs[0] = sx; xyzs[1] = sy; xyzs[2] = sz;
+                dirs[0] = sdx; dirs[1] = sdy; dirs[2] = sdz;
+            } else {
+                xyzs[0] = p.x; xyzs[1] = p.y; xyzs[2] = p.z;
+                dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+            }
             t += p.dt;
             deltas[0] = p.dt;
             deltas[1] = t - last_t;
@@ -816,30 +847,60 @@ extern "C" int seald_packbits(const float* grid, uint32_t n_bytes, float thresh,
     return launch_status();
 }
 
-extern "C" int seald_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound, float dt_gamma,
-                                      uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
-                                      const float* fars, const float* aabb6, float min_near, float* nears_out, float* fars_out,
-                                      float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter, const float* noises,
-                                      seald_stream_t stream) {
+static int march_train_impl(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound, float dt_gamma,
+                            uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears, const float* fars,
+                            const float* aabb6, float min_near, float* nears_out, float* fars_out, float* xyzs, float* dirs, float* deltas,
+                            int32_t* rays, int32_t* counter, const float* noises, const seald_seal_mapper* mapper, uint8_t* mask,
+                            seald_stream_t stream) {
     if (N == 0) return 0;
     if (!rays_o || !rays_d || !bitfield || !xyzs || !dirs || !deltas || !rays || !counter || !noises) return SEALD_E_BADARG;
     if ((nears == nullptr) != (fars == nullptr)) return SEALD_E_BADARG;
     if (!nears && !aabb6) return SEALD_E_BADARG;
     if ((nears_out == nullptr) != (fars_out == nullptr)) return SEALD_E_BADARG;
     if (C == 0 || H == 0 || max_steps == 0) return SEALD_E_BADARG;
+    static const seald_seal_mapper no_mapper = {};
+    const seald_seal_mapper& mp = mapper ? *mapper : no_mapper;
+    cudaStream_t st = to_stream(stream);
     // small batches (training: 4096 rays) are latency bound: one warp per ray.  Large batches (whole images) have enough
     // rays to fill the machine with one thread per ray, which does less total work.
     if (N <= 65536u && max_steps <= kMaxStepsSmem) {
-        k_march_rays_train_warp<<<div_up(N, kMarchWarps), kMarchWarps * 32, 0, to_stream(stream)>>>(
-            rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6, min_near, nears_out, fars_out, xyzs, dirs,
-            deltas, rays, counter, noises);
+        auto k = mapper ? k_march_rays_train_warp<true> : k_march_rays_train_warp<false>;
+        k<<<div_up(N, kMarchWarps), kMarchWarps * 32, 0, st>>>(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6,
+                                                              min_near, nears_out, fars_out, xyzs, dirs, deltas, rays, counter, noises, mp, mask);
         return launch_status();
     }
     const uint32_t threads = (N >= 4u * SEALD_NUM_SMS * 128u) ? 128u : 32u;
-    k_march_rays_train<<<div_up(N, threads), threads, 0, to_stream(stream)>>>(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M,
-                                                                              nears, fars, aabb6, min_near, nears_out, fars_out, xyzs, dirs,
-                                                                              deltas, rays, counter, noises);
+    auto k = mapper ? k_march_rays_train<true> : k_march_rays_train<false>;
+    k<<<div_up(N, threads), threads, 0, st>>>(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6, min_near,
+                                             nears_out, fars_out, xyzs, dirs, deltas, rays, counter, noises, mp, mask);
     return launch_status();
+}
+
+static int check_fusable_mapper(const seald_seal_mapper* mp, const uint8_t* mask) {
+    if (!mp || !mask) return SEALD_E_BADARG;
+    if (mp->type != SEALD_SEAL_BBOX && mp->type != SEALD_SEAL_BRUSH) return SEALD_E_UNSUPPORTED;  // anchor: batch-wide early exit, seal.cu
+    if (mp->n_bounds <= 0 || mp->n_tris <= 0 || !mp->bounds || !mp->tris) return SEALD_E_BADARG;
+    if (mp->type == SEALD_SEAL_BRUSH && mp->attenuation_mode == SEALD_SEAL_ATT_LINEAR && (mp->n_border <= 0 || !mp->border)) return SEALD_E_BADARG;
+    return 0;
+}
+
+extern "C" int seald_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound, float dt_gamma,
+                                      uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                      const float* fars, const float* aabb6, float min_near, float* nears_out, float* fars_out,
+                                      float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                                      seald_stream_t stream) {
+    return march_train_impl(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6, min_near, nears_out, fars_out,
+                            xyzs, dirs, deltas, rays, counter, noises, nullptr, nullptr, stream);
+}
+
+extern "C" int seald_march_rays_train_seal(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound, float dt_gamma,
+                                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                           const float* fars, const float* aabb6, float min_near, float* nears_out, float* fars_out,
+                                           float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                                           const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream) {
+    if (int rc = check_fusable_mapper(mapper, mask)) return rc;
+    return march_train_impl(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6, min_near, nears_out, fars_out,
+                            xyzs, dirs, deltas, rays, counter, noises, mapper, mask, stream);
 }
 
 extern "C" int seald_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M,
@@ -866,17 +927,36 @@ extern "C" int seald_composite_rays_train_backward(const float* grad_weights_sum
     return launch_status();
 }
 
+static int march_impl(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                      const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* bitfield,
+                      const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                      const int32_t* n_alive_dev, const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream) {
+    if (n_alive == 0 || n_step == 0) return 0;
+    if (!rays_alive || !rays_t || !rays_o || !rays_d || !bitfield || !fars || !xyzs || !dirs || !deltas) return SEALD_E_BADARG;
+    static const seald_seal_mapper no_mapper = {};
+    auto k = mapper ? k_march_rays<true> : k_march_rays<false>;
+    k<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
+                                                           bitfield, nears, fars, xyzs, dirs, deltas, noises, n_alive_dev,
+                                                           mapper ? *mapper : no_mapper, mask);
+    return launch_status();
+}
+
 extern "C" int seald_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                                 const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                                 const uint8_t* bitfield, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                                 const float* noises, const int32_t* n_alive_dev, seald_stream_t stream) {
-    if (n_alive == 0 || n_step == 0) return 0;
-    if (!rays_alive || !rays_t || !rays_o || !rays_d || !bitfield || !fars || !xyzs || !dirs || !deltas) return SEALD_E_BADARG;
-    (void)nears;
-    k_march_rays<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
-                                                                       max_steps, C, H, bitfield, nears, fars, xyzs, dirs, deltas, noises,
-                                                                       n_alive_dev);
-    return launch_status();
+    return march_impl(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, bitfield, nears, fars, xyzs, dirs,
+                      deltas, noises, n_alive_dev, nullptr, nullptr, stream);
+}
+
+extern "C" int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                                     const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                                     const uint8_t* bitfield, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                     const float* noises, const int32_t* n_alive_dev, const seald_seal_mapper* mapper, uint8_t* mask,
+                                     seald_stream_t stream) {
+    if (int rc = check_fusable_mapper(mapper, mask)) return rc;
+    return march_impl(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, bitfield, nears, fars, xyzs, dirs,
+                      deltas, noises, n_alive_dev, mapper, mask, stream);
 }
 
 extern "C" int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t, const float* sigmas,

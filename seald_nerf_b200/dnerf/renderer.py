@@ -73,12 +73,32 @@ class NeRFRenderer(nn.Module):
         raise NotImplementedError("the cuda_ray=False sampling path is the reference's CPU baseline (oracle/render.py); "
                                   "seald_b200 implements the cuda_ray=True hot path only")
 
-    # ---- hooks the SealD teacher overrides (SealDNeRF/renderer.py:156-158, 250-253, 271-272) ----------------
-    def _map_samples(self, xyzs, dirs):
-        return xyzs, dirs, None
+    # ---- Seal proxy mapping (SealDNeRF/renderer.py:156-158, 250-253, 271-272); None on a plain D-NeRF model ----------
+    seal_mapper = None
 
-    def _map_colors(self, xyzs, dirs, rgbs, mask):
-        return rgbs
+    def _march_train(self, rays_o, rays_d, t, nears, fars, counter, perturb, force_all_rays, dt_gamma, max_steps):
+        """march_rays_train (+ proxy mapping of the samples when a seal mapper is set) -> xyzs, dirs, deltas, rays, mask"""
+        mp = self.seal_mapper
+        args = (rays_o, rays_d, self.bound, self.density_bitfield[t], self.cascade, self.grid_size, nears, fars)
+        if mp is not None and mp.fusable:
+            return raymarching.march_rays_train_seal(*args, mp, counter, self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
+        xyzs, dirs, deltas, rays = raymarching.march_rays_train(*args, counter, self.mean_count, perturb, 128, force_all_rays, dt_gamma,
+                                                                max_steps)
+        mask = None
+        if mp is not None:
+            xyzs, dirs, mask = mp.map_to_origin(xyzs.view(-1, 3), dirs.view(-1, 3))
+        return xyzs, dirs, deltas, rays, mask
+
+    def _march_infer(self, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bitfield, nears, fars, perturb, dt_gamma, max_steps):
+        mp = self.seal_mapper
+        args = (n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, bitfield, self.cascade, self.grid_size, nears, fars)
+        if mp is not None and mp.fusable:
+            return raymarching.march_rays_seal(*args, mp, 128, perturb, dt_gamma, max_steps)
+        xyzs, dirs, deltas = raymarching.march_rays(*args, 128, perturb, dt_gamma, max_steps)
+        mask = None
+        if mp is not None:
+            xyzs, dirs, mask = mp.map_to_origin(xyzs.view(-1, 3), dirs.view(-1, 3))
+        return xyzs, dirs, deltas, mask
 
     def _frame_index(self, time):
         return torch.floor(time[0][0] * self.time_size).clamp(min=0, max=self.time_size - 1).long()
@@ -104,11 +124,9 @@ class NeRFRenderer(nn.Module):
             counter.zero_()
             self.local_step += 1
 
-            xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, self.density_bitfield[t], self.cascade,
-                                                                    self.grid_size, nears, fars, counter, self.mean_count, perturb, 128,
-                                                                    force_all_rays, dt_gamma, max_steps)
-            mx, md, _ = self._map_samples(xyzs, dirs)
-            sigmas, rgbs, deform = self(mx, md, time)
+            # (the reference's training branch maps the samples but leaves map_color commented out, SealDNeRF/renderer.py:180-182)
+            xyzs, dirs, deltas, rays, _ = self._march_train(rays_o, rays_d, t, nears, fars, counter, perturb, force_all_rays, dt_gamma, max_steps)
+            sigmas, rgbs, deform = self(xyzs, dirs, time)
             sigmas = self.density_scale * sigmas
 
             if T_thresh is None:
@@ -139,13 +157,13 @@ class NeRFRenderer(nn.Module):
                 if n_alive <= 0:
                     break
                 n_step = max(min(N // n_alive, 8), 1)
-                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, bitfield,
-                                                            self.cascade, self.grid_size, nears, fars, 128, perturb if step == 0 else False,
-                                                            dt_gamma, max_steps)
-                mx, md, mask = self._map_samples(xyzs, dirs)
-                sigmas, rgbs, _ = self(mx, md, time)
+                xyzs, dirs, deltas, mask = self._march_infer(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bitfield, nears, fars,
+                                                             perturb if step == 0 else False, dt_gamma, max_steps)
+                sigmas, rgbs, _ = self(xyzs, dirs, time)
                 sigmas = self.density_scale * sigmas
-                rgbs = self._map_colors(mx, md, rgbs, mask)
+                if mask is not None and self.seal_mapper.has_color_map:
+                    # rgbs[mask] = map_color(xyzs[mask], dirs[mask], rgbs[mask]) without the gathers (SealDNeRF/renderer.py:271-272)
+                    rgbs = self.seal_mapper.map_color_masked_(xyzs, mask, rgbs.float().contiguous())
                 if T_thresh is None:
                     raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image)
                 else:

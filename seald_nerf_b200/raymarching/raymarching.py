@@ -209,6 +209,62 @@ class _composite_rays(Function):
 composite_rays = _composite_rays.apply
 
 
+def march_rays_seal(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, density_bitfield, C, H, near, far, mapper, align=-1,
+                    perturb=False, dt_gamma=0, max_steps=1024):
+    """`march_rays` + `mapper.map_to_origin` in one kernel (SealDNeRF/renderer.py:245-253): returns the MAPPED xyzs / dirs,
+    deltas and the map mask (bool [M]).  bbox and brush mappers (`mapper.fusable`)."""
+    import ctypes as C_
+    rays_o = _cuda(rays_o).float().contiguous().view(-1, 3)
+    rays_d = _cuda(rays_d).float().contiguous().view(-1, 3)
+    M = n_alive * n_step
+    if align > 0:
+        M += align - (M % align)
+    dev, dt = rays_o.device, rays_o.dtype
+    xyzs = torch.zeros(M, 3, dtype=dt, device=dev)
+    dirs = torch.zeros(M, 3, dtype=dt, device=dev)
+    deltas = torch.zeros(M, 2, dtype=dt, device=dev)
+    mask = torch.zeros(M, dtype=torch.bool, device=dev)
+    noises = torch.rand(n_alive, dtype=dt, device=dev) if perturb else torch.zeros(n_alive, dtype=dt, device=dev)
+    _lib.call("seald_march_rays_seal", int(n_alive), int(n_step), ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), float(bound),
+              float(dt_gamma), int(max_steps), int(C), int(H), ptr(density_bitfield.contiguous()), ptr(near), ptr(far), ptr(xyzs),
+              ptr(dirs), ptr(deltas), ptr(noises), None, C_.byref(mapper.descriptor(dev)), ptr(mask), _lib.stream())
+    return xyzs, dirs, deltas, mask
+
+
+def march_rays_train_seal(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, mapper, step_counter=None, mean_count=-1,
+                          perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
+    """`march_rays_train` + `mapper.map_to_origin` in one kernel (SealDNeRF/renderer.py:150-158): returns the MAPPED xyzs /
+    dirs, deltas, rays and the map mask (bool [M]).  No gradient flows through the march (as in the reference)."""
+    import ctypes as C_
+    rays_o = _cuda(rays_o).float().contiguous().view(-1, 3)
+    rays_d = _cuda(rays_d).float().contiguous().view(-1, 3)
+    density_bitfield = _cuda(density_bitfield).contiguous()
+    N = rays_o.shape[0]
+    M = N * max_steps
+    if not force_all_rays and mean_count > 0:
+        if align > 0:
+            mean_count += align - mean_count % align
+        M = mean_count
+    dev, dt = rays_o.device, rays_o.dtype
+    xyzs = torch.zeros(M, 3, dtype=dt, device=dev)
+    dirs = torch.zeros(M, 3, dtype=dt, device=dev)
+    deltas = torch.zeros(M, 2, dtype=dt, device=dev)
+    mask = torch.zeros(M, dtype=torch.bool, device=dev)
+    rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+    if step_counter is None:
+        step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    noises = torch.rand(N, dtype=dt, device=dev) if perturb else torch.zeros(N, dtype=dt, device=dev)
+    _lib.call("seald_march_rays_train_seal", ptr(rays_o), ptr(rays_d), ptr(density_bitfield), float(bound), float(dt_gamma), int(max_steps), N,
+              int(C), int(H), M, ptr(nears.contiguous()), ptr(fars.contiguous()), None, 0.0, None, None, ptr(xyzs), ptr(dirs), ptr(deltas),
+              ptr(rays), ptr(step_counter), ptr(noises), C_.byref(mapper.descriptor(dev)), ptr(mask), _lib.stream())
+    if force_all_rays or mean_count <= 0:
+        m = step_counter[0].item()
+        if align > 0:
+            m += align - m % align
+        xyzs, dirs, deltas, mask = xyzs[:m], dirs[:m], deltas[:m], mask[:m]
+    return xyzs, dirs, deltas, rays, mask
+
+
 def compact_alive(rays_alive, n_alive=None, n_alive_dev=None):
     """Device-side, order-preserving replacement of `rays_alive[rays_alive >= 0]` (dnerf/renderer.py:372).
     Returns (compacted int32 [n_alive], count int32 [1] on device) without a host sync."""

@@ -31,3 +31,11 @@ def camera_rays(n, seed=0, radius=3.2, H=800, W=800, pose_seed=0, center_crop=No
         inds = torch.randint(0, H * W, (n,), generator=g)
     ro, rd = syn.get_rays(pose, syn.intrinsics(H, W), H, W, inds)
     return ro.numpy().astype(np.float32), rd.numpy().astype(np.float32)
+
+
+def seal_mapper_from_dict(mp):
+    """oracle.seal mapper dict (numpy tensors) -> seald_nerf_b200.SealNeRF.seal_utils mapper object."""
+    from seald_nerf_b200.SealNeRF import seal_utils as su
+    cls = {"bbox": su.SealBBoxMapper, "brush": su.SealBrushMapper, "anchor": su.SealAnchorMapper}[mp["type"]]
+    data = {k: v for k, v in mp.items() if k not in ("type", "map_triangles", "map_test_dir")}
+    return cls.from_tensors(data, mp["map_triangles"], mp.get("map_test_dir"))
