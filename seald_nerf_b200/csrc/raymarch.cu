@@ -675,6 +675,15 @@ __global__ void k_march_rays(uint32_t n_alive, const uint32_t n_step, const int*
             t = skip_voxel(r, mc, p, t);
         }
     }
+    // unused slots of this ray: delta == 0 is the "terminated" marker composite_rays looks for (raymarching.cu:850); the
+    // reference relies on the caller's torch.zeros for it, writing it here lets a render loop reuse its buffers
+    for (; step < n_step; step++) {
+        xyzs[0] = 0.f; xyzs[1] = 0.f; xyzs[2] = 0.f;
+        dirs[0] = 0.f; dirs[1] = 0.f; dirs[2] = 0.f;
+        deltas[0] = 0.f; deltas[1] = 0.f;
+        if (SEAL) seal_mask[step] = 0;
+        xyzs += 3; dirs += 3; deltas += 2;
+    }
 }
 
 __global__ void k_composite_rays(uint32_t n_alive, const uint32_t n_step, const float T_thresh, int* rays_alive, float* rays_t,

@@ -1,0 +1,181 @@
+"""Per-kernel roofline microbenchmarks (BASELINE.json configs[4] and the march / composite / packbits stages).
+
+Every number is device-timed with CUDA events on the launching stream after warm-up; working sets are larger than the
+126 MB L2 or an L2 flush (a 256 MiB memset) runs between timed launches, as stated per entry.  `algorithmic bytes` are the
+SURVEY.md §8(d) per-unit figures x the units one launch processes.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr, F16, F32
+
+
+def _time(fn, reps=20, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def grid_encoder(device, log2_B=22, D=3, gridtype="hash", dtype=torch.float16, coherent=False, reps=20, hbm_gbs=6537.6):
+    """GridEncoder fwd / bwd at B = 2^log2_B points, L16 / T2^19 / F2 (configs[4])."""
+    from .gridencoder import GridEncoder
+    B = 1 << log2_B
+    enc = GridEncoder(input_dim=D, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19, desired_resolution=2048,
+                      gridtype=gridtype).to(device)
+    g = torch.Generator(device=device).manual_seed(0)
+    x = torch.rand(B, D, device=device, generator=g)
+    if coherent:
+        # ray-coherent order: 128 consecutive samples lie on one short segment, like marched samples
+        seg = torch.rand(B // 128, 1, D, device=device, generator=g)
+        dirs = torch.nn.functional.normalize(torch.randn(B // 128, 1, D, device=device, generator=g), dim=-1)
+        tt = torch.arange(128, device=device).view(1, 128, 1) * (2 * 3 ** 0.5 / 1024 / 2)
+        x = (seg + dirs * tt).clamp(0, 1).reshape(B, D).contiguous()
+    table = enc.embeddings.detach().to(dtype).contiguous()
+    table.uniform_(-0.1, 0.1)
+    out = torch.empty(B, 32, device=device, dtype=dtype)
+    grad = torch.randn(B, 32, device=device).to(dtype)
+    gtab = torch.zeros(table.shape, device=device, dtype=torch.float32)
+    gtab16 = torch.zeros(table.shape, device=device, dtype=dtype)
+    gx = torch.empty(B, D, device=device)
+    S, H = float(np.log2(enc.per_level_scale)), 16
+    dt = F16 if dtype == torch.float16 else F32
+    gt = enc.gridtype_id
+    s = 2 if dtype == torch.float16 else 4
+    st = _lib.stream
+
+    def fwd():
+        _lib.call("seald_grid_encode_forward", ptr(x), ptr(table), ptr(enc.offsets), ptr(out), None, B, D, 2, 16, S, H, gt, 0, 0, dt, None, st())
+
+    def bwd32():
+        _lib.call("seald_grid_encode_backward", ptr(grad), ptr(x), ptr(table), ptr(enc.offsets), ptr(gtab), None, None, B, D, 2, 16, S, H, gt, 0,
+                  0, dt, F32, None, st())
+
+    def bwd16():
+        _lib.call("seald_grid_encode_backward", ptr(grad), ptr(x), ptr(table), ptr(enc.offsets), ptr(gtab16), None, None, B, D, 2, 16, S, H, gt,
+                  0, 0, dt, dt, None, st())
+
+    def bwd_x():
+        _lib.call("seald_grid_encode_backward", ptr(grad), ptr(x), ptr(table), ptr(enc.offsets), ptr(gtab), None, ptr(gx), B, D, 2, 16, S, H, gt,
+                  0, 0, dt, F32, None, st())
+
+    res = {}
+    nc = 1 << D
+    bytes_fwd = B * (4 * D + nc * 16 * 2 * s + 16 * 2 * s)
+    bytes_bwd = B * (4 * D + 16 * 2 * s + 2 * nc * 16 * 2 * s)
+    bytes_bwd32 = B * (4 * D + 16 * 2 * s + 2 * nc * 16 * 2 * 4)
+    for name, fn, nbytes in (("fwd", fwd, bytes_fwd), ("bwd_table_f32", bwd32, bytes_bwd32), ("bwd_table_same_dtype", bwd16, bytes_bwd),
+                             ("bwd_table_f32+input_grad", bwd_x, bytes_bwd32 + B * (4 * D + nc * 16 * 2 * s))):
+        ms = _time(fn, reps=reps)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res[name] = {"ms": round(ms, 4), "algorithmic_GB": round(nbytes / 1e9, 4), "GB/s": round(gbs, 1), "frac_of_hbm": round(gbs / hbm_gbs, 4),
+                     "Gpoints/s": round(B / (ms * 1e-3) / 1e9, 3)}
+    return {"B": B, "D": D, "gridtype": gridtype, "dtype": str(dtype).replace("torch.", ""), "order": "coherent" if coherent else "uniform",
+            "l2": "inputs+outputs (%d MB) exceed L2; the %.1f MiB table stays L2 resident by design" % ((B * (4 * D + 64)) >> 20, table.numel() * s / 2 ** 20),
+            "kernels": res}
+
+
+def march_composite(device, n_rays=640000, reps=10, hbm_gbs=6537.6):
+    """Training march + composite fwd/bwd + packbits on a whole 800x800 frame of the synthetic scene."""
+    from . import synthetic as syn
+    from . import raymarching as rm
+    H = 128
+    grid = syn.make_density_grid(64, H, 1.0, device)
+    bits = torch.empty(H ** 3 // 8, dtype=torch.uint8, device=device)
+    rm.packbits(grid[20], 10.0, bits)
+    pose = syn.orbit_poses(1, device, seed=0)[0]
+    inds = torch.arange(800 * 800, device=device)[:n_rays]
+    ro, rd = syn.get_rays(pose, syn.intrinsics(), 800, 800, inds)
+    ro, rd = ro.contiguous(), rd.contiguous()
+    N = ro.shape[0]
+    aabb = torch.tensor([-1, -1, -1, 1, 1, 1], dtype=torch.float32, device=device)
+    counter = torch.zeros(2, dtype=torch.int32, device=device)
+    nears, fars = rm.near_far_from_aabb(ro, rd, aabb, 0.2)
+    rm.march_rays_train(ro, rd, 1.0, bits, 1, H, nears, fars, counter, -1, False, 128, True, 0, 1024)
+    m_live = int(counter[0])
+    M = (m_live + 127) // 128 * 128
+    xyzs = torch.zeros(M, 3, device=device); dirs = torch.zeros(M, 3, device=device); deltas = torch.zeros(M, 2, device=device)
+    rays = torch.zeros(N, 3, dtype=torch.int32, device=device)
+    noises = torch.zeros(N, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    st = _lib.stream
+
+    def march():
+        counter.zero_()
+        _lib.call("seald_march_rays_train", ptr(ro), ptr(rd), ptr(bits), 1.0, 0.0, 1024, N, 1, H, M, None, None, ptr(aabb), 0.2, ptr(nears),
+                  ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), st())
+
+    sig = torch.rand(M, device=device) * 30
+    rgb = torch.rand(M, 3, device=device)
+    ws = torch.empty(N, device=device); depth = torch.empty(N, device=device); image = torch.empty(N, 3, device=device)
+    gws = torch.rand(N, device=device); gim = torch.rand(N, 3, device=device)
+    gs = torch.zeros(M, device=device); gc = torch.zeros(M, 3, device=device)
+
+    def comp_fwd():
+        _lib.call("seald_composite_rays_train_forward", ptr(sig), ptr(rgb), ptr(deltas), ptr(rays), M, N, 1e-4, ptr(ws), ptr(depth), ptr(image), st())
+
+    def comp_bwd():
+        _lib.call("seald_composite_rays_train_backward", ptr(gws), ptr(gim), ptr(sig), ptr(rgb), ptr(deltas), ptr(rays), ptr(ws), ptr(image), M, N,
+                  1e-4, ptr(gs), ptr(gc), st())
+
+    g1 = grid[20].contiguous()
+
+    def pack():
+        _lib.call("seald_packbits", ptr(g1), H ** 3 // 8, 10.0, ptr(bits), st())
+
+    gall = grid.reshape(-1).contiguous()
+    ball = torch.empty(64 * H ** 3 // 8, dtype=torch.uint8, device=device)
+
+    def pack_all():
+        _lib.call("seald_packbits", ptr(gall), 64 * H ** 3 // 8, 10.0, ptr(ball), st())
+
+    out = {"rays": N, "samples": m_live, "l2": "256 MiB flush between timed launches"}
+    for name, fn, nbytes in (("march_train", march, 48.0 * N + 32.0 * m_live + 262144.0),
+                             ("composite_fwd", comp_fwd, 24.0 * m_live + 32.0 * N),
+                             ("composite_bwd", comp_bwd, 40.0 * m_live + 48.0 * N),
+                             ("packbits_1frame", pack, 4.125 * H ** 3),
+                             ("packbits_64frames", pack_all, 4.125 * 64 * H ** 3)):
+        ms = _time(fn, reps=reps, flush=flush)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "algorithmic_GB": round(nbytes / 1e9, 5), "GB/s": round(gbs, 1), "frac_of_hbm": round(gbs / hbm_gbs, 4)}
+    return out
+
+
+def main():
+    dev = torch.device("cuda:0")
+    _lib.load()
+    peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    hbm = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
+    which = sys.argv[1:] or ["grid", "march"]
+    if "grid" in which:
+        for D in (3, 4):
+            for gt in ("hash", "tiled"):
+                print(json.dumps(grid_encoder(dev, 22, D, gt, torch.float16, hbm_gbs=hbm)), flush=True)
+        print(json.dumps(grid_encoder(dev, 22, 3, "hash", torch.float16, coherent=True, hbm_gbs=hbm)), flush=True)
+        print(json.dumps(grid_encoder(dev, 22, 3, "hash", torch.float32, hbm_gbs=hbm)), flush=True)
+    if "sweep" in which:
+        for lb in range(16, 25):
+            r = grid_encoder(dev, lb, 3, "hash", torch.float16, hbm_gbs=hbm)
+            print(json.dumps({"B": r["B"], "fwd": r["kernels"]["fwd"], "bwd": r["kernels"]["bwd_table_f32"]}), flush=True)
+    if "march" in which:
+        print(json.dumps(march_composite(dev, hbm_gbs=hbm)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@ import torch
 
 from . import _lib
 from . import field as F
+from . import parallel
 from ._lib import ptr
 
 
@@ -157,7 +158,7 @@ class FusedTrainer:
         ws, hw = self.ws, self.hw
         m_dev = self.counter[0:1]
         offsets = m.encoder.offsets
-        inv_count = 1.0 / (3.0 * N * self.world_size)
+        inv_count = parallel.loss_inv_count(N, self.world_size)
         F16, F32 = _lib.F16, _lib.F32
 
         def select_frame():
@@ -287,7 +288,7 @@ class FusedTrainer:
 
     def _allreduce(self):
         if self.world_size > 1:
-            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            parallel.allreduce_flat_grads(self.grads, self.pg)
 
     # ------------------------------------------------------------------------------------------------------------
     def step(self):

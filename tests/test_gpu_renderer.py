@@ -1,0 +1,67 @@
+"""FusedRenderer (preallocated full-frame inference loop) against the drop-in NeRFRenderer.run_cuda / SealD teacher
+run_cuda: same kernels and schedule, so images must agree to fp32 round-off (rtol/atol 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import camera_rays, scene_bitfield, seal_mapper_from_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cuda_dev, seald=False):
+    from seald_nerf_b200.dnerf.network import NeRFNetwork
+    from seald_nerf_b200.SealDNeRF.network import NeRFNetwork as SealNet
+    torch.manual_seed(0)
+    cls = SealNet if seald else NeRFNetwork
+    net = cls(encoding="hashgrid", bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10).to(cuda_dev)
+    net.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    bits, _ = scene_bitfield()
+    net.density_bitfield[:] = torch.from_numpy(bits).to(cuda_dev)[None]
+    net.eval()
+    return net
+
+
+@pytest.mark.parametrize("tval", [0.3, 0.0])
+def test_fused_renderer_matches_run_cuda(cuda_dev, tval):
+    from seald_nerf_b200.renderer_fused import FusedRenderer
+    net = _model(cuda_dev)
+    ro, rd = camera_rays(5000, seed=3, center_crop=260)
+    ro, rd = torch.from_numpy(ro).to(cuda_dev), torch.from_numpy(rd).to(cuda_dev)
+    time = torch.tensor([[tval]], device=cuda_dev)
+    with torch.no_grad():
+        ref = net.render(ro[None], rd[None], time, perturb=False)
+    fr = FusedRenderer(net, max_rays=6000)
+    out = fr.render(ro[None], rd[None], time)
+    assert out["image"].shape == (1, 5000, 3) and fr.iterations > 3 and fr.samples > 5000
+    torch.testing.assert_close(out["image"], ref["image"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out["depth"], ref["depth"], rtol=1e-5, atol=1e-5)
+    # float time takes the host-side frame index
+    out2 = fr.render(ro, rd, tval)
+    torch.testing.assert_close(out2["image"], ref["image"][0], rtol=1e-5, atol=1e-5)
+    # a second call reuses every buffer
+    out3 = fr.render(ro[:1234], rd[:1234], time)
+    torch.testing.assert_close(out3["image"], ref["image"][0, :1234], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["bbox", "brush", "anchor"])
+def test_fused_renderer_seald_teacher(cuda_dev, kind):
+    from oracle import seal as S
+    from seald_nerf_b200.renderer_fused import FusedRenderer
+    net = _model(cuda_dev, seald=True)
+    if kind == "bbox":
+        mp = S.make_bbox_mapper(center=(0.0, 0.1, 0.0), half=(0.2, 0.25, 0.2), translate=(0.08, 0.0, 0.03), rot_deg=30.0, hsv=(0.1, 0.0, 0.0))
+    elif kind == "brush":
+        mp = S.make_brush_mapper(mode="linear", pressure=0.05, depth=0.6, attenuation=0.03, rgb=(1.0, 0.0, 0.0))
+    else:
+        mp = S.make_anchor_mapper()
+    net.init_mapper(mapper=seal_mapper_from_dict(mp))
+    ro, rd = camera_rays(3000, seed=4, center_crop=200)
+    ro, rd = torch.from_numpy(ro).to(cuda_dev), torch.from_numpy(rd).to(cuda_dev)
+    time = torch.tensor([[0.55]], device=cuda_dev)
+    with torch.no_grad():
+        ref = net.render(ro[None], rd[None], time, perturb=False, force_all_rays=True)
+    out = FusedRenderer(net, max_rays=3000).render(ro[None], rd[None], time)
+    torch.testing.assert_close(out["image"], ref["image"], rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(out["depth"], ref["depth"], rtol=1e-5, atol=2e-5)   # raw depth (SealD does not normalise)
+    torch.testing.assert_close(out["weights_sum"], ref["weights_sum"], rtol=1e-5, atol=2e-5)
