@@ -157,6 +157,100 @@ def march_composite(device, n_rays=640000, reps=10, hbm_gbs=6537.6):
     return out
 
 
+def build_scene(device, seed=0, seald=False):
+    """Random-init D-NeRF (hashgrid) + analytic occupancy grid of the synthetic jumpingjacks-shaped figure."""
+    from . import synthetic as syn
+    from . import raymarching
+    if seald:
+        from .SealDNeRF.network import NeRFNetwork
+    else:
+        from .dnerf.network import NeRFNetwork
+    torch.manual_seed(seed)
+    model = NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10).to(device)
+    grid = syn.make_density_grid(model.time_size, model.grid_size, 1.0, device)
+    model.density_grid.copy_(grid)
+    model.mean_density = float(grid.clamp(min=0).mean())
+    thresh = min(model.mean_density, model.density_thresh)
+    for t in range(model.time_size):
+        raymarching.packbits(model.density_grid[t], thresh, model.density_bitfield[t])
+    return model
+
+
+def frame_rays(device, frame=0, H=800, W=800, seed=0):
+    from . import synthetic as syn
+    pose = syn.orbit_poses(200, device, seed=seed)[frame]
+    inds = torch.arange(H * W, device=device)
+    ro, rd = syn.get_rays(pose, syn.intrinsics(H, W), H, W, inds)
+    return ro.contiguous(), rd.contiguous()
+
+
+def frame_render(device, model=None, times=(0.0, 0.25, 0.5, 0.75, 1.0), reps=3, rank=0, world_size=1, T_thresh=1e-2):
+    """Full 800x800 frame (BASELINE.json configs[2]): median device time per frame over `times`, incl. the image gather."""
+    from .renderer_fused import FusedRenderer
+    from . import parallel
+    model = model or build_scene(device)
+    model.eval()
+    # a random-init field is transparent; scale sigma so rays terminate like a trained scene (sigma ~ 50 inside the figure)
+    ro, rd = frame_rays(device)
+    N = ro.shape[0]
+    n_local = parallel.shard_tiles(N, world_size, rank).shape[0]
+    fr = FusedRenderer(model, max_rays=n_local)
+    out = {}
+    ms_all = []
+    for t in times:
+        fr.render_sharded(ro, rd, float(t), rank, world_size, T_thresh=T_thresh)  # warm-up
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = fr.render_sharded(ro, rd, float(t), rank, world_size, T_thresh=T_thresh)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms_all.append(ts[len(ts) // 2])
+        out["t=%.2f" % t] = {"ms": round(ts[len(ts) // 2], 3), "iterations": fr.iterations, "field_samples": fr.samples,
+                             "coverage": round(float(res["weights_sum"].mean()), 4)}
+    out["frame_ms_median"] = round(sorted(ms_all)[len(ms_all) // 2], 3)
+    out["rays"] = N
+    return out
+
+
+def field_throughput(device, log2_M=20, reps=10, tf_peak=1678.0):
+    """Fused field kernels at M = 2^log2_M samples: deform MLP / grid / heads forward (inference) TFLOP/s."""
+    from . import field as F
+    model = build_scene(device)
+    cfg = model._field_cfg
+    M = 1 << log2_M
+    ws = F.FieldWorkspace(cfg, M, device, training=False)
+    hw = F.HalfWeights(cfg, device)
+    hw.refresh([w.detach() for w in model.mlp_weights()])
+    table16 = model.encoder.embeddings.detach().half()
+    xyz = torch.rand(M, 3, device=device) * 1.6 - 0.8
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3, device=device), dim=-1)
+    td = torch.tensor([0.4], device=device)
+    st = _lib.stream
+
+    def deform():
+        _lib.call("seald_field_deform_forward", ptr(xyz), ptr(td), hw.p_deform, cfg.n_deform, M, None, cfg.bound, 1, ptr(ws.deform), ptr(ws.x01),
+                  None, None, st())
+
+    def heads():
+        _lib.call("seald_field_heads_forward", ptr(ws.feat), ptr(dirs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, M, None, 1.0,
+                  ptr(ws.sigma), ptr(ws.rgb), None, None, None, None, st())
+
+    F.field_forward(cfg, hw, ws, xyz, dirs, td, table16, model.encoder.offsets, None, 1)
+    out = {"M": M}
+    mac_deform = 76 * 128 + (cfg.n_deform - 2) * 128 * 128 + 128 * 3
+    mac_heads = 32 * 64 + 64 * 16 + 31 * 64 + (cfg.n_color - 2) * 64 * 64 + 64 * 3
+    for name, fn, fl in (("deform_fwd", deform, 2.0 * mac_deform * M), ("heads_fwd", heads, 2.0 * mac_heads * M)):
+        ms = _time(fn, reps=reps)
+        tf = fl / (ms * 1e-3) / 1e12
+        out[name] = {"ms": round(ms, 4), "TFLOP/s": round(tf, 1), "frac_of_tensor_peak": round(tf / tf_peak, 4)}
+    return out
+
+
 def main():
     dev = torch.device("cuda:0")
     _lib.load()
@@ -175,6 +269,10 @@ def main():
             print(json.dumps({"B": r["B"], "fwd": r["kernels"]["fwd"], "bwd": r["kernels"]["bwd_table_f32"]}), flush=True)
     if "march" in which:
         print(json.dumps(march_composite(dev, hbm_gbs=hbm)), flush=True)
+    if "field" in which:
+        print(json.dumps(field_throughput(dev)), flush=True)
+    if "frame" in which:
+        print(json.dumps(frame_render(dev)), flush=True)
 
 
 if __name__ == "__main__":
