@@ -220,6 +220,15 @@ int seald_sh_encode_backward(const float* grad, const float* inputs, uint32_t B,
 int seald_field_deform_forward(const float* xyz, const float* time_dev, const void* const* weights, int n_layers, uint32_t M,
                                const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf /*[M,80] f16 or NULL*/,
                                void* fwd_buf /*[n_layers-1,M,128] f16 or NULL*/, seald_stream_t stream);
+/* Same operation on the Blackwell tensor cores (tcgen05.mma, accumulators in tensor memory; csrc/field_umma.cu).
+ * `packed`: the deformation weights re-laid out by seald_field_umma_pack_deform into the canonical K-major operand tiles
+ * ([K/8][N][8] fp16 per layer, seald_field_umma_deform_bytes(n_layers) bytes, 16-byte aligned) so that one bulk copy per
+ * layer brings them into shared memory.  Same outputs / optional training buffers as seald_field_deform_forward. */
+uint64_t seald_field_umma_deform_bytes(int n_layers);
+int seald_field_umma_pack_deform(const void* const* weights, int n_layers, void* packed, seald_stream_t stream);
+int seald_field_deform_forward_umma(const float* xyz, const float* time_dev, const void* packed, int n_layers, uint32_t M,
+                                    const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf,
+                                    void* fwd_buf, seald_stream_t stream);
 int seald_field_deform_backward(const float* grad_x01, const float* time_dev /*NULL or device float: t == 0 => zero gradient*/,
                                 const void* const* weights, int n_layers, uint32_t M, const int32_t* m_dev,
                                 float bound, const void* fwd_buf, void* bwd_buf /*[n_layers-1,M,128] f16*/, void* gout_buf /*[M,16] f16*/,

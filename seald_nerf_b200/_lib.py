@@ -41,6 +41,8 @@ _SIGS = {
     "seald_sh_encode_forward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp],
     "seald_sh_encode_backward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp],
     "seald_field_deform_forward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "seald_field_umma_pack_deform": [_vp, _i32, _vp, _vp],
+    "seald_field_deform_forward_umma": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "seald_field_deform_backward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
     "seald_field_heads_forward": [_vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_field_sigma_forward": [_vp, _vp, _i32, _u32, _f32, _vp, _vp, _vp],
@@ -76,7 +78,7 @@ _lib = None
 
 def exported_symbols():
     """Every entry point include/seald_b200.h declares (used by the CPU-side ABI test)."""
-    return ["seald_version", "seald_sm_arch", "seald_strerror"] + list(_SIGS)
+    return ["seald_version", "seald_sm_arch", "seald_strerror", "seald_field_umma_deform_bytes"] + list(_SIGS)
 
 
 def load():
@@ -92,6 +94,8 @@ def load():
     lib.seald_sm_arch.restype = C.c_int
     lib.seald_strerror.restype = C.c_char_p
     lib.seald_strerror.argtypes = [C.c_int]
+    lib.seald_field_umma_deform_bytes.restype = C.c_uint64
+    lib.seald_field_umma_deform_bytes.argtypes = [C.c_int]
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = sig

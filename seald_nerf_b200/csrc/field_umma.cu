@@ -1,0 +1,282 @@
+// field_umma.cu — the D-NeRF deformation MLP (76 -> 8 x Linear(128) + ReLU -> 3, dnerf/network.py:123-143) on the
+// Blackwell tensor cores: tcgen05.mma with fp32 accumulators in tensor memory.
+//
+// One persistent CTA per SM works on PAIRS of 128-sample tiles (two "groups" of 4 warps, one TMEM accumulator of 128
+// columns each) so that one group's epilogue overlaps the other group's MMAs:
+//
+//   warp 8 (one elected thread) : streams the layer weights global -> shared with cp.async.bulk (3 stages of 32 KiB,
+//                                 pre-packed in the canonical K-major layout of umma.cuh by k_pack_umma) and issues the
+//                                 tcgen05.mma's: per layer and group K/16 instructions of shape 128 x 128 x 16
+//                                 (last layer 128 x 16 x 16), tcgen05.commit -> mbarrier.
+//   warps 0-3 / 4-7 (group 0/1) : thread t owns sample row t of its tile = TMEM lane t.  Layer 0 input: frequency
+//                                 encoding of xyz (63) and t (13) written straight into the A-operand tile.  After each
+//                                 layer: tcgen05.ld the fp32 row, ReLU, pack to fp16, store as the next layer's A tile
+//                                 (and, when training, into fwd_buf for the backward pass).  Last layer: dx, x' = x + dx,
+//                                 x01 = (x' + bound) / (2 bound).
+//
+// Activations never leave the SM between layers; per 128-sample tile the tensor pipe does 8 layers x 4.2 MFLOP while the
+// only HBM traffic is 12 B in / 24 B out per sample (inference).  Numerics as the mma.sync kernels of field.cu: fp16
+// operands and layer outputs, fp32 accumulation.
+#include "encoders.cuh"
+#include "umma.cuh"
+
+namespace seald {
+
+constexpr int kUW = 128;            // hidden width
+constexpr int kUK0 = 80;            // layer-0 K (76 real inputs, zero padded)
+constexpr int kUNLast = 16;         // last layer N (3 real outputs, zero padded)
+constexpr int kUThreads = 288;      // 2 groups x 4 warps + 1 control warp
+constexpr int kUStages = 3;
+constexpr uint32_t kTileBytes = kUW * kUW * 2;  // 32 KiB: one A tile / one weight stage
+constexpr uint32_t kTmemCols = 256;
+
+struct UmmaSmem {
+    static constexpr size_t A_OFF = 0;
+    static constexpr size_t W_OFF = 2 * kTileBytes;
+    static constexpr size_t BAR_OFF = W_OFF + kUStages * kTileBytes;
+    static constexpr size_t BYTES = BAR_OFF + 128;
+};
+
+__host__ __device__ __forceinline__ uint32_t umma_layer_bytes(const int l, const int n_layers) {
+    if (l == 0) return kUK0 * kUW * 2;
+    if (l == n_layers - 1) return kUW * kUNLast * 2;
+    return kTileBytes;
+}
+__host__ __device__ __forceinline__ size_t umma_layer_offset(const int l, const int n_layers) {
+    size_t o = 0;
+    for (int i = 0; i < l; i++) o += umma_layer_bytes(i, n_layers);
+    return o;
+}
+
+// src [n_real][ld] row-major fp16 (nn.Linear.weight) -> dst [K/8][n_pad][8] (rows >= n_real zero)
+__global__ void k_pack_umma(const __half* __restrict__ src, __half* __restrict__ dst, const int n_real, const int n_pad, const int K, const int ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+    const int chunks = K / 8;
+    if (i >= chunks * n_pad) return;
+    const int c = i / n_pad, n = i - c * n_pad;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < n_real) v = *reinterpret_cast<const uint4*>(src + (size_t)n * ld + c * 8);
+    *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = v;
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(kUThreads, 1) k_deform_forward_umma(const float* __restrict__ xyz, const float* __restrict__ time,
+                                                                      const __half* __restrict__ packed, const int n_layers, const int M,
+                                                                      const int* __restrict__ m_dev, const float bound, const int t0_mode,
+                                                                      float* __restrict__ deform, float* __restrict__ x01,
+                                                                      __half* __restrict__ in_buf, __half* __restrict__ fwd_buf) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_a = smem + UmmaSmem::A_OFF;
+    unsigned char* s_w = smem + UmmaSmem::W_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + UmmaSmem::BAR_OFF);
+    uint64_t* bar_full = bars;            // [3] weights of a stage have landed
+    uint64_t* bar_aready = bars + 3;      // [2] the group's A tile is written
+    uint64_t* bar_mma = bars + 5;         // [2] the group's MMAs of the current layer have completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
+    const int n_tiles = (m_used + kUW - 1) / kUW;
+    const int n_pairs = (n_tiles + 1) / 2;
+    const int my_pairs = (n_pairs > (int)blockIdx.x) ? (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_items = my_pairs * n_layers;
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; i++) umma::mbar_init(bar_full + i, 1);
+        for (int i = 0; i < 2; i++) { umma::mbar_init(bar_aready + i, 128); umma::mbar_init(bar_mma + i, 1); }
+        umma::mbar_fence_init();
+    }
+    if (warp == 8) umma::tmem_alloc(tmem_slot, kTmemCols);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // =============================== control warp: weight streaming + MMA issue ===============================
+        if (lane == 0 && n_items > 0) {
+            const uint32_t a_addr = umma::smem_addr(s_a), w_addr = umma::smem_addr(s_w);
+            auto load_weights = [&](const int item) {
+                const int l = item % n_layers, s = item % kUStages;
+                const uint32_t bytes = umma_layer_bytes(l, n_layers);
+                umma::mbar_arrive_expect_tx(bar_full + s, bytes);
+                umma::bulk_load(s_w + (size_t)s * kTileBytes, reinterpret_cast<const unsigned char*>(packed) + umma_layer_offset(l, n_layers), bytes,
+                                bar_full + s);
+            };
+            load_weights(0);
+            if (n_items > 1) load_weights(1);
+            for (int i = 0; i < n_items; i++) {
+                const int l = i % n_layers, s = i % kUStages;
+                const bool last = (l == n_layers - 1);
+                const int ksteps = (l == 0 ? kUK0 : kUW) / 16;
+                const uint32_t n_rows = last ? kUNLast : kUW;
+                const uint32_t idesc = umma::instr_desc_f16(128, n_rows);
+                const uint32_t w_lbo = n_rows * 16;
+#pragma unroll 1
+                for (int g = 0; g < 2; g++) {
+                    umma::mbar_wait(bar_aready + g, i & 1);
+                    if (g == 0) {
+                        umma::mbar_wait(bar_full + s, (i / kUStages) & 1);
+                    } else if (i + 2 < n_items) {
+                        // every MMA of item i-1 has completed (group 1 waited for it before writing this A tile): its stage is free
+                        load_weights(i + 2);
+                    }
+                    umma::fence_after_sync();
+                    const uint32_t d = tmem_base + g * kUW;
+                    const uint32_t a0 = a_addr + g * kTileBytes, w0 = w_addr + s * kTileBytes;
+                    for (int k = 0; k < ksteps; k++) {
+                        const uint64_t da = umma::smem_desc(a0 + k * 2 * (kUW * 16), kUW * 16, 128);
+                        const uint64_t db = umma::smem_desc(w0 + k * 2 * w_lbo, w_lbo, 128);
+                        umma::mma_f16(d, da, db, idesc, k > 0 ? 1u : 0u);
+                    }
+                    umma::mma_commit(bar_mma + g);
+                }
+            }
+        }
+    } else {
+        // =============================== epilogue groups: one thread per sample row ===============================
+        const int g = tid >> 7, r = tid & 127;
+        unsigned char* a_tile = s_a + (size_t)g * kTileBytes;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(r & ~31) << 16) + g * kUW;  // this warp's 32-lane quadrant, group's columns
+        const float tval = *time;
+        const bool t_is_zero = (tval == 0.0f);
+        int row = 0;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        for (int i = 0; i < n_items; i++) {
+            const int l = i % n_layers;
+            if (l == 0) {
+                const int pair = (int)blockIdx.x + (i / n_layers) * (int)gridDim.x;
+                row = (2 * pair + g) * kUW + r;
+                const bool live = row < m_used;
+                if (live) { px = xyz[(size_t)row * 3]; py = xyz[(size_t)row * 3 + 1]; pz = xyz[(size_t)row * 3 + 2]; }
+                const float xv[3] = {px, py, pz};
+#pragma unroll
+                for (int c8 = 0; c8 < kUK0 / 8; c8++) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float v[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int c = c8 * 8 + j * 2 + e;
+                            float val = 0.0f;
+                            if (live) {
+                                if (c < 63) val = freq_channel(xv, 3, c);
+                                else if (c < 76) val = freq_channel(&tval, 1, c - 63);
+                            }
+                            v[e] = val;
+                        }
+                        const __half2 h = __floats2half2_rn(v[0], v[1]);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    const uint4 u = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(a_tile + ((size_t)c8 * kUW + r) * 16) = u;
+                    if (SAVE && live) *reinterpret_cast<uint4*>(in_buf + (size_t)row * kUK0 + c8 * 8) = u;
+                }
+                umma::fence_proxy_async();
+                umma::mbar_arrive(bar_aready + g);
+            }
+            umma::mbar_wait(bar_mma + g, i & 1);
+            umma::fence_after_sync();
+            if (l < n_layers - 1) {
+#pragma unroll 1
+                for (int q = 0; q < 4; q++) {
+                    uint32_t v[32];
+                    umma::tmem_ld32(t_lane + q * 32, v);
+                    umma::wait_ld();
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float a = fmaxf(__uint_as_float(v[c4 * 8 + j * 2]), 0.0f);
+                            const float b = fmaxf(__uint_as_float(v[c4 * 8 + j * 2 + 1]), 0.0f);
+                            const __half2 h = __floats2half2_rn(a, b);
+                            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        const uint4 u = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(a_tile + ((size_t)(q * 4 + c4) * kUW + r) * 16) = u;
+                        if (SAVE && row < m_used) *reinterpret_cast<uint4*>(fwd_buf + ((size_t)l * M + row) * kUW + (q * 4 + c4) * 8) = u;
+                    }
+                }
+                umma::fence_before_sync();
+                umma::fence_proxy_async();
+                umma::mbar_arrive(bar_aready + g);
+            } else {
+                uint32_t v[16];
+                umma::tmem_ld16(t_lane, v);
+                umma::wait_ld();
+                umma::fence_before_sync();
+                if (row < m_used) {
+                    const float xin[3] = {px, py, pz};
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        float dx = __half2float(__float2half_rn(__uint_as_float(v[d])));
+                        float xp;
+                        if (t_is_zero) {
+                            xp = xin[d];
+                            if (t0_mode == 1) dx = 0.0f;
+                        } else {
+                            xp = xin[d] + dx;
+                        }
+                        deform[(size_t)row * 3 + d] = dx;
+                        x01[(size_t)row * 3 + d] = (xp + bound) / (2 * bound);
+                    }
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) umma::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace seald
+
+using namespace seald;
+
+extern "C" uint64_t seald_field_umma_deform_bytes(int n_layers) {
+    if (n_layers < 2) return 0;
+    return (uint64_t)umma_layer_offset(n_layers, n_layers);
+}
+
+// weights: HOST array of device pointers to the fp16 staging copies (same as seald_field_deform_forward): layer 0
+// [128][80], hidden [128][128], last [3][128].  packed: device buffer of seald_field_umma_deform_bytes(n_layers) bytes.
+extern "C" int seald_field_umma_pack_deform(const void* const* weights, int n_layers, void* packed, seald_stream_t stream) {
+    if (!weights || !packed || n_layers < 2 || n_layers > 12) return SEALD_E_BADARG;
+    cudaStream_t st = to_stream(stream);
+    for (int l = 0; l < n_layers; l++) {
+        if (!weights[l]) return SEALD_E_BADARG;
+        const bool last = (l == n_layers - 1);
+        const int K = (l == 0) ? kUK0 : kUW, n_pad = last ? kUNLast : kUW, n_real = last ? 3 : kUW, ld = (l == 0) ? kUK0 : kUW;
+        const int chunks = K / 8 * n_pad;
+        __half* dst = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(packed) + umma_layer_offset(l, n_layers));
+        k_pack_umma<<<div_up(chunks, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(weights[l]), dst, n_real, n_pad, K, ld);
+    }
+    return launch_status();
+}
+
+extern "C" int seald_field_deform_forward_umma(const float* xyz, const float* time_dev, const void* packed, int n_layers, uint32_t M,
+                                               const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf,
+                                               void* fwd_buf, seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!xyz || !time_dev || !packed || !deform || !x01 || n_layers < 2 || n_layers > 12) return SEALD_E_BADARG;
+    if ((in_buf == nullptr) != (fwd_buf == nullptr)) return SEALD_E_BADARG;
+    if (((uintptr_t)packed & 15) != 0) return SEALD_E_ALIGN;
+    const uint32_t n_pairs = (div_up(M, (uint32_t)kUW) + 1) / 2;
+    const uint32_t grid = n_pairs < (uint32_t)SEALD_NUM_SMS ? n_pairs : (uint32_t)SEALD_NUM_SMS;
+    cudaStream_t st = to_stream(stream);
+    cudaError_t e;
+    if (fwd_buf) {
+        e = cudaFuncSetAttribute(k_deform_forward_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaSmem::BYTES);
+        if (e != cudaSuccess) return (int)e;
+        k_deform_forward_umma<true><<<grid, kUThreads, UmmaSmem::BYTES, st>>>(xyz, time_dev, (const __half*)packed, n_layers, (int)M, m_dev, bound,
+                                                                            t0_mode, deform, x01, (__half*)in_buf, (__half*)fwd_buf);
+    } else {
+        e = cudaFuncSetAttribute(k_deform_forward_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaSmem::BYTES);
+        if (e != cudaSuccess) return (int)e;
+        k_deform_forward_umma<false><<<grid, kUThreads, UmmaSmem::BYTES, st>>>(xyz, time_dev, (const __half*)packed, n_layers, (int)M, m_dev, bound,
+                                                                             t0_mode, deform, x01, nullptr, nullptr);
+    }
+    return launch_status();
+}

@@ -10,6 +10,7 @@ wrapper used by the drop-in `NeRFNetwork` and the graph-captured `FusedTrainer` 
 Reference: dnerf/network.py:123-169.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -59,6 +60,9 @@ class HalfWeights:
         self.deform, self.sigma, self.color = self.views[:nd], self.views[nd:nd + ns], self.views[nd + ns:]
         self.p_deform, self.p_sigma, self.p_color = _lib.ptr_array(self.deform), _lib.ptr_array(self.sigma), _lib.ptr_array(self.color)
 
+        # the deformation weights again, as canonical K-major UMMA operand tiles (tcgen05 path, csrc/field_umma.cu)
+        self.packed_deform = torch.zeros(int(_lib.load().seald_field_umma_deform_bytes(cfg.n_deform)) // 2, dtype=torch.float16, device=device)
+
         n = len(self.views)
         self._dst = _lib.ptr_array(self.views)
         self._rows = (C.c_uint32 * n)(*[r for r, c, ld in self.shapes])
@@ -73,6 +77,7 @@ class HalfWeights:
             ws.append(w if w.is_contiguous() else w.contiguous())
         src = _lib.ptr_array(ws)
         _lib.call("seald_cast_pad_f16_batch", src, self._dst, self._rows, self._cols, self._ld, len(ws), _lib.stream())
+        _lib.call("seald_field_umma_pack_deform", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform), _lib.stream())
 
 
 class FieldWorkspace:
@@ -103,13 +108,25 @@ class FieldWorkspace:
             self.grad_x01 = torch.empty(M, 3, **f32)
 
 
+DEFORM_IMPL = os.environ.get("SEALD_DEFORM_IMPL", "umma")  # "umma": tcgen05 kernel (default); "mma": the mma.sync kernel of field.cu
+
+
+def deform_forward(cfg, hw, xyzs, time_dev, M, m_dev, t0_mode, deform, x01, in_buf, fwd_buf):
+    st = _lib.stream()
+    if DEFORM_IMPL == "umma":
+        _lib.call("seald_field_deform_forward_umma", ptr(xyzs), ptr(time_dev), ptr(hw.packed_deform), cfg.n_deform, M, ptr(m_dev), cfg.bound,
+                  int(t0_mode), ptr(deform), ptr(x01), ptr(in_buf), ptr(fwd_buf), st)
+    else:
+        _lib.call("seald_field_deform_forward", ptr(xyzs), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, int(t0_mode),
+                  ptr(deform), ptr(x01), ptr(in_buf), ptr(fwd_buf), st)
+
+
 def field_forward(cfg, hw, ws, xyzs, dirs, time_dev, table16, offsets, m_dev=None, t0_mode=1, M=None):
     """Enqueue the forward pass for rows [0, M) of the workspace.  Results: ws.sigma, ws.rgb, ws.deform."""
     M = ws.M if M is None else int(M)
     st = _lib.stream()
     save = ws.training
-    _lib.call("seald_field_deform_forward", ptr(xyzs), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, int(t0_mode),
-              ptr(ws.deform), ptr(ws.x01), ptr(ws.in_buf) if save else None, ptr(ws.fwd_d) if save else None, st)
+    deform_forward(cfg, hw, xyzs, time_dev, M, m_dev, t0_mode, ws.deform, ws.x01, ws.in_buf if save else None, ws.fwd_d if save else None)
     # rows >= *m_dev keep stale x01: the grid kernel clamps nothing, so feed it only well-defined rows
     _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
               cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, ptr(m_dev), st)
@@ -176,8 +193,7 @@ def field_density(cfg, hw, ws, xyzs, time_dev, table16, offsets, M=None):
     """Density-only query (NeRFNetwork.density, dnerf/network.py:171-208): deform -> grid -> sigma net."""
     M = ws.M if M is None else int(M)
     st = _lib.stream()
-    _lib.call("seald_field_deform_forward", ptr(xyzs), ptr(time_dev), hw.p_deform, cfg.n_deform, M, None, cfg.bound, 2, ptr(ws.deform),
-              ptr(ws.x01), None, None, st)
+    deform_forward(cfg, hw, xyzs, time_dev, M, None, 2, ws.deform, ws.x01, None, None)
     _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
               cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, None, st)
     _lib.call("seald_field_sigma_forward", ptr(ws.feat), hw.p_sigma, cfg.n_sigma, M, cfg.density_scale, ptr(ws.sigma), None, st)

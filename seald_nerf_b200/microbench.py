@@ -233,6 +233,9 @@ def field_throughput(device, log2_M=20, reps=10, tf_peak=1678.0):
     st = _lib.stream
 
     def deform():
+        F.deform_forward(cfg, hw, xyz, td, M, None, 1, ws.deform, ws.x01, None, None)
+
+    def deform_mma_sync():
         _lib.call("seald_field_deform_forward", ptr(xyz), ptr(td), hw.p_deform, cfg.n_deform, M, None, cfg.bound, 1, ptr(ws.deform), ptr(ws.x01),
                   None, None, st())
 
@@ -244,7 +247,8 @@ def field_throughput(device, log2_M=20, reps=10, tf_peak=1678.0):
     out = {"M": M}
     mac_deform = 76 * 128 + (cfg.n_deform - 2) * 128 * 128 + 128 * 3
     mac_heads = 32 * 64 + 64 * 16 + 31 * 64 + (cfg.n_color - 2) * 64 * 64 + 64 * 3
-    for name, fn, fl in (("deform_fwd", deform, 2.0 * mac_deform * M), ("heads_fwd", heads, 2.0 * mac_heads * M)):
+    for name, fn, fl in (("deform_fwd_tcgen05", deform, 2.0 * mac_deform * M), ("deform_fwd_mma_sync", deform_mma_sync, 2.0 * mac_deform * M),
+                         ("heads_fwd", heads, 2.0 * mac_heads * M)):
         ms = _time(fn, reps=reps)
         tf = fl / (ms * 1e-3) / 1e12
         out[name] = {"ms": round(ms, 4), "TFLOP/s": round(tf, 1), "frac_of_tensor_peak": round(tf / tf_peak, 4)}

@@ -176,8 +176,7 @@ class FusedTrainer:
                       ptr(self.noises), _lib.stream())
 
         def deform_fwd():
-            _lib.call("seald_field_deform_forward", ptr(self.xyzs), ptr(self.time), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, 1,
-                      ptr(ws.deform), ptr(ws.x01), ptr(ws.in_buf), ptr(ws.fwd_d), _lib.stream())
+            F.deform_forward(cfg, hw, self.xyzs, self.time, M, m_dev, 1, ws.deform, ws.x01, ws.in_buf, ws.fwd_d)
 
         def grid_fwd():
             _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(self.table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim,

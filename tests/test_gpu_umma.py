@@ -1,0 +1,81 @@
+"""The tcgen05 deformation-MLP kernel (csrc/field_umma.cu) against the mma.sync kernel of csrc/field.cu on identical
+inputs and weights: same fp16 operands and fp32 accumulation, so outputs agree to one fp16 ulp of the layer outputs
+(accumulation ORDER differs between the two tensor-core paths): deform atol 2e-3 * max|dx|, saved activations identical
+up to isolated 1-ulp rounding flips (checked as <= 2^-9 relative on > 99.9% of entries)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cuda_dev, M, seed=0):
+    from seald_nerf_b200 import field as F
+    from seald_nerf_b200.dnerf.network import NeRFNetwork
+    torch.manual_seed(seed)
+    net = NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True).to(cuda_dev)
+    for l in net.deform_net:
+        l.weight.data.mul_(1.5)  # a deformation field that actually moves points
+    cfg = net._field_cfg
+    hw = F.HalfWeights(cfg, cuda_dev)
+    hw.refresh([w.detach() for w in net.mlp_weights()])
+    g = torch.Generator().manual_seed(seed + 1)
+    xyz = (torch.rand(M, 3, generator=g) * 1.8 - 0.9).to(cuda_dev)
+    return F, cfg, hw, xyz
+
+
+def _run(F, cfg, hw, xyz, tval, impl, save, m_live=None, t0_mode=1):
+    from seald_nerf_b200 import _lib
+    from seald_nerf_b200._lib import ptr
+    M = xyz.shape[0]
+    dev = xyz.device
+    deform = torch.full((M, 3), 7.0, device=dev); x01 = torch.full((M, 3), 7.0, device=dev)
+    in_buf = torch.zeros(M, 80, dtype=torch.float16, device=dev) if save else None
+    fwd = torch.zeros(cfg.n_deform - 1, M, 128, dtype=torch.float16, device=dev) if save else None
+    td = torch.tensor([tval], device=dev)
+    m_dev = None if m_live is None else torch.tensor([m_live], dtype=torch.int32, device=dev)
+    old = F.DEFORM_IMPL
+    F.DEFORM_IMPL = impl
+    try:
+        F.deform_forward(cfg, hw, xyz, td, M, m_dev, t0_mode, deform, x01, in_buf, fwd)
+    finally:
+        F.DEFORM_IMPL = old
+    torch.cuda.synchronize()
+    return deform, x01, in_buf, fwd
+
+
+@pytest.mark.parametrize("M,m_live", [(1000, None), (128 * 5 + 3, None), (128, None), (4096 * 11, 4096 * 7 + 77), (300, 0), (200000, None)])
+def test_umma_deform_matches_mma_sync(cuda_dev, M, m_live):
+    F, cfg, hw, xyz = _setup(cuda_dev, M)
+    d0, x0, i0, f0 = _run(F, cfg, hw, xyz, 0.37, "mma", True, m_live)
+    d1, x1, i1, f1 = _run(F, cfg, hw, xyz, 0.37, "umma", True, m_live)
+    n = M if m_live is None else m_live
+    if n == 0:
+        assert float((d1 - 7.0).abs().max()) == 0.0  # nothing written
+        return
+    assert torch.equal(i0[:n], i1[:n]), "encoded inputs are computed by the same expressions"
+    scale = float(d0[:n].abs().max())
+    assert scale > 1e-3
+    assert float((d0[:n] - d1[:n]).abs().max()) <= 2e-3 * scale + 1e-6
+    torch.testing.assert_close(x1[:n], x0[:n], rtol=0, atol=2e-3 * scale + 1e-6)
+    a, b = f0[:, :n].float(), f1[:, :n].float()
+    rel = (a - b).abs() / (a.abs().clamp(min=1e-3))
+    assert float((rel <= 2.0 ** -9).float().mean()) > 0.999
+    assert float((a - b).abs().max()) <= 0.02 * float(a.abs().max())
+    if m_live is not None:  # rows beyond the live count are left alone
+        assert float((d1[n:] - 7.0).abs().max()) == 0.0 and float(f1[:, n:].abs().max()) == 0.0
+
+
+def test_umma_deform_inference_and_t0_modes(cuda_dev):
+    F, cfg, hw, xyz = _setup(cuda_dev, 777, seed=3)
+    d_tr, x_tr, _, _ = _run(F, cfg, hw, xyz, 0.6, "umma", True)
+    d_inf, x_inf, _, _ = _run(F, cfg, hw, xyz, 0.6, "umma", False)
+    assert torch.equal(d_tr, d_inf) and torch.equal(x_tr, x_inf)
+    # t == 0: forward() semantics zero the deformation, density() semantics still report it (network.py:140-141,188-190)
+    d1, x1, _, _ = _run(F, cfg, hw, xyz, 0.0, "umma", False, t0_mode=1)
+    d2, x2, _, _ = _run(F, cfg, hw, xyz, 0.0, "umma", False, t0_mode=2)
+    assert float(d1.abs().max()) == 0.0 and float(d2.abs().max()) > 0.0
+    torch.testing.assert_close(x1, (xyz + 1) / 2, rtol=0, atol=1e-7)
+    assert torch.equal(x1, x2)
+    d2m, _, _, _ = _run(F, cfg, hw, xyz, 0.0, "mma", False, t0_mode=2)
+    assert float((d2 - d2m).abs().max()) <= 2e-3 * float(d2m.abs().max()) + 1e-6
