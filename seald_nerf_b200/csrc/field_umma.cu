@@ -1,21 +1,24 @@
 // field_umma.cu — the D-NeRF deformation MLP (76 -> 8 x Linear(128) + ReLU -> 3, dnerf/network.py:123-143) on the
 // Blackwell tensor cores: tcgen05.mma with fp32 accumulators in tensor memory.
 //
-// One persistent CTA per SM works on PAIRS of 128-sample tiles (two "groups" of 4 warps, one TMEM accumulator of 128
-// columns each) so that one group's epilogue overlaps the other group's MMAs:
+// One persistent CTA per SM works on G = 2 or 4 128-sample tiles at a time ("groups" of 4 warps, one TMEM accumulator of
+// 128 columns each) so that the groups' epilogues overlap each other's MMAs; G = 4 (all 512 TMEM columns, 224 KiB of
+// shared memory) keeps the tensor pipe busy when there are enough tiles, G = 2 spreads small batches over more SMs:
 //
-//   warp 8 (one elected thread) : streams the layer weights global -> shared with cp.async.bulk (3 stages of 32 KiB,
+//   control warp (one elected thread): streams the layer weights global -> shared with cp.async.bulk (3 stages of 32 KiB,
 //                                 pre-packed in the canonical K-major layout of umma.cuh by k_pack_umma) and issues the
 //                                 tcgen05.mma's: per layer and group K/16 instructions of shape 128 x 128 x 16
 //                                 (last layer 128 x 16 x 16), tcgen05.commit -> mbarrier.
-//   warps 0-3 / 4-7 (group 0/1) : thread t owns sample row t of its tile = TMEM lane t.  Layer 0 input: frequency
+//   4 warps per group           : thread t owns sample row t of its tile = TMEM lane t.  Layer 0 input: frequency
 //                                 encoding of xyz (63) and t (13) written straight into the A-operand tile.  After each
 //                                 layer: tcgen05.ld the fp32 row, ReLU, pack to fp16, store as the next layer's A tile
 //                                 (and, when training, into fwd_buf for the backward pass).  Last layer: dx, x' = x + dx,
 //                                 x01 = (x' + bound) / (2 bound).
 //
 // Activations never leave the SM between layers; per 128-sample tile the tensor pipe does 8 layers x 4.2 MFLOP while the
-// only HBM traffic is 12 B in / 24 B out per sample (inference).  Numerics as the mma.sync kernels of field.cu: fp16
+// only HBM traffic is 12 B in / 24 B out per sample (inference).  Measured bound (profiles/): shared-memory bandwidth —
+// an SS-mode 128x128x16 MMA reads 8 KiB of operands per 64 cycles (= the 128 B/cycle port), plus 32 KiB of epilogue
+// stores and the weight refills per tile-layer, ~830 cycles against the 512-cycle MMA floor.  Numerics as the mma.sync kernels of field.cu: fp16
 // operands and layer outputs, fp32 accumulation.
 #include "encoders.cuh"
 #include "umma.cuh"
@@ -25,14 +28,15 @@ namespace seald {
 constexpr int kUW = 128;            // hidden width
 constexpr int kUK0 = 80;            // layer-0 K (76 real inputs, zero padded)
 constexpr int kUNLast = 16;         // last layer N (3 real outputs, zero padded)
-constexpr int kUThreads = 288;      // 2 groups x 4 warps + 1 control warp
 constexpr int kUStages = 3;
 constexpr uint32_t kTileBytes = kUW * kUW * 2;  // 32 KiB: one A tile / one weight stage
-constexpr uint32_t kTmemCols = 256;
 
+template <int G>
 struct UmmaSmem {
+    static constexpr int THREADS = G * 128 + 32;  // G groups x 4 warps + 1 control warp
+    static constexpr uint32_t TMEM_COLS = G * kUW;
     static constexpr size_t A_OFF = 0;
-    static constexpr size_t W_OFF = 2 * kTileBytes;
+    static constexpr size_t W_OFF = G * kTileBytes;
     static constexpr size_t BAR_OFF = W_OFF + kUStages * kTileBytes;
     static constexpr size_t BYTES = BAR_OFF + 128;
 };
@@ -59,40 +63,42 @@ __global__ void k_pack_umma(const __half* __restrict__ src, __half* __restrict__
     *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = v;
 }
 
-template <bool SAVE>
-__global__ void __launch_bounds__(kUThreads, 1) k_deform_forward_umma(const float* __restrict__ xyz, const float* __restrict__ time,
+template <bool SAVE, int G>
+__global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma(const float* __restrict__ xyz, const float* __restrict__ time,
                                                                       const __half* __restrict__ packed, const int n_layers, const int M,
                                                                       const int* __restrict__ m_dev, const float bound, const int t0_mode,
                                                                       float* __restrict__ deform, float* __restrict__ x01,
                                                                       __half* __restrict__ in_buf, __half* __restrict__ fwd_buf) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* s_a = smem + UmmaSmem::A_OFF;
-    unsigned char* s_w = smem + UmmaSmem::W_OFF;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + UmmaSmem::BAR_OFF);
+    using SM = UmmaSmem<G>;
+    constexpr int CTRL = G * 4;  // index of the control warp
+    unsigned char* s_a = smem + SM::A_OFF;
+    unsigned char* s_w = smem + SM::W_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
     uint64_t* bar_full = bars;            // [3] weights of a stage have landed
-    uint64_t* bar_aready = bars + 3;      // [2] the group's A tile is written
-    uint64_t* bar_mma = bars + 5;         // [2] the group's MMAs of the current layer have completed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bar_aready = bars + 3;      // [G] the group's A tile is written
+    uint64_t* bar_mma = bars + 3 + G;     // [G] the group's MMAs of the current layer have completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * G);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
     const int n_tiles = (m_used + kUW - 1) / kUW;
-    const int n_pairs = (n_tiles + 1) / 2;
+    const int n_pairs = (n_tiles + G - 1) / G;  // work units of G tiles
     const int my_pairs = (n_pairs > (int)blockIdx.x) ? (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int n_items = my_pairs * n_layers;
 
     if (tid == 0) {
         for (int i = 0; i < 3; i++) umma::mbar_init(bar_full + i, 1);
-        for (int i = 0; i < 2; i++) { umma::mbar_init(bar_aready + i, 128); umma::mbar_init(bar_mma + i, 1); }
+        for (int i = 0; i < G; i++) { umma::mbar_init(bar_aready + i, 128); umma::mbar_init(bar_mma + i, 1); }
         umma::mbar_fence_init();
     }
-    if (warp == 8) umma::tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == CTRL) umma::tmem_alloc(tmem_slot, SM::TMEM_COLS);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == CTRL) {
         // =============================== control warp: weight streaming + MMA issue ===============================
         if (lane == 0 && n_items > 0) {
             const uint32_t a_addr = umma::smem_addr(s_a), w_addr = umma::smem_addr(s_w);
@@ -113,12 +119,11 @@ __global__ void __launch_bounds__(kUThreads, 1) k_deform_forward_umma(const floa
                 const uint32_t idesc = umma::instr_desc_f16(128, n_rows);
                 const uint32_t w_lbo = n_rows * 16;
 #pragma unroll 1
-                for (int g = 0; g < 2; g++) {
+                for (int g = 0; g < G; g++) {
                     umma::mbar_wait(bar_aready + g, i & 1);
-                    if (g == 0) {
-                        umma::mbar_wait(bar_full + s, (i / kUStages) & 1);
-                    } else if (i + 2 < n_items) {
-                        // every MMA of item i-1 has completed (group 1 waited for it before writing this A tile): its stage is free
+                    if (g == 0) umma::mbar_wait(bar_full + s, (i / kUStages) & 1);
+                    if (g == G - 1 && i + 2 < n_items) {
+                        // every MMA of item i-1 has completed (the last group waited for it before writing this A tile): its stage is free
                         load_weights(i + 2);
                     }
                     umma::fence_after_sync();
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(kUThreads, 1) k_deform_forward_umma(const floa
             const int l = i % n_layers;
             if (l == 0) {
                 const int pair = (int)blockIdx.x + (i / n_layers) * (int)gridDim.x;
-                row = (2 * pair + g) * kUW + r;
+                row = (G * pair + g) * kUW + r;
                 const bool live = row < m_used;
                 if (live) { px = xyz[(size_t)row * 3]; py = xyz[(size_t)row * 3 + 1]; pz = xyz[(size_t)row * 3 + 2]; }
                 const float xv[3] = {px, py, pz};
@@ -228,7 +233,10 @@ __global__ void __launch_bounds__(kUThreads, 1) k_deform_forward_umma(const floa
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 8) umma::tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == CTRL) {
+        __syncwarp();
+        umma::tmem_dealloc(tmem_base, SM::TMEM_COLS);
+    }
 }
 
 }  // namespace seald
@@ -263,20 +271,27 @@ extern "C" int seald_field_deform_forward_umma(const float* xyz, const float* ti
     if (!xyz || !time_dev || !packed || !deform || !x01 || n_layers < 2 || n_layers > 12) return SEALD_E_BADARG;
     if ((in_buf == nullptr) != (fwd_buf == nullptr)) return SEALD_E_BADARG;
     if (((uintptr_t)packed & 15) != 0) return SEALD_E_ALIGN;
-    const uint32_t n_pairs = (div_up(M, (uint32_t)kUW) + 1) / 2;
-    const uint32_t grid = n_pairs < (uint32_t)SEALD_NUM_SMS ? n_pairs : (uint32_t)SEALD_NUM_SMS;
+    const uint32_t n_tiles = div_up(M, (uint32_t)kUW);
     cudaStream_t st = to_stream(stream);
-    cudaError_t e;
+    auto launch = [&](auto kernel, const int G, const size_t smem, const int threads) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        const uint32_t units = div_up(n_tiles, (uint32_t)G);
+        const uint32_t grid = units < (uint32_t)SEALD_NUM_SMS ? units : (uint32_t)SEALD_NUM_SMS;
+        kernel<<<grid, threads, smem, st>>>(xyz, time_dev, (const __half*)packed, n_layers, (int)M, m_dev, bound, t0_mode, deform, x01,
+                                            (__half*)in_buf, (__half*)fwd_buf);
+        return 0;
+    };
+    // enough tiles to give every SM four at a time: G = 4 (tensor pipe saturated); otherwise spread over more SMs with G = 2
+    const bool big = n_tiles >= 4u * SEALD_NUM_SMS;
+    int rc;
     if (fwd_buf) {
-        e = cudaFuncSetAttribute(k_deform_forward_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaSmem::BYTES);
-        if (e != cudaSuccess) return (int)e;
-        k_deform_forward_umma<true><<<grid, kUThreads, UmmaSmem::BYTES, st>>>(xyz, time_dev, (const __half*)packed, n_layers, (int)M, m_dev, bound,
-                                                                            t0_mode, deform, x01, (__half*)in_buf, (__half*)fwd_buf);
+        rc = big ? launch(k_deform_forward_umma<true, 4>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
+                 : launch(k_deform_forward_umma<true, 2>, 2, UmmaSmem<2>::BYTES, UmmaSmem<2>::THREADS);
     } else {
-        e = cudaFuncSetAttribute(k_deform_forward_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaSmem::BYTES);
-        if (e != cudaSuccess) return (int)e;
-        k_deform_forward_umma<false><<<grid, kUThreads, UmmaSmem::BYTES, st>>>(xyz, time_dev, (const __half*)packed, n_layers, (int)M, m_dev, bound,
-                                                                             t0_mode, deform, x01, nullptr, nullptr);
+        rc = big ? launch(k_deform_forward_umma<false, 4>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
+                 : launch(k_deform_forward_umma<false, 2>, 2, UmmaSmem<2>::BYTES, UmmaSmem<2>::THREADS);
     }
+    if (rc) return rc;
     return launch_status();
 }
