@@ -13,6 +13,11 @@ the occupancy bitfield, perturbed samples, loss-scaled Adam.  Data parallel acro
 `e2e`    : the same metric through the public API with HOST inputs (pinned H2D of rays/targets every step and a D2H
            read of the loss inside the timed region).
 `roofline`: the dominant kernel of the step, timed alone with CUDA events, against MEASURED_PEAKS.json.
+`frame`   : full 800x800 render (BASELINE configs[2]) through FusedRenderer, rays tile-sharded over the N GPUs + image
+           all-gather, median device ms per frame (max over ranks).
+`hashgrid`: GridEncoder 2^22 points x 16 levels forward / backward, GB/s of algorithmic bytes (BASELINE configs[4]).
+`seald`   : SealD teacher->student distillation step (teacher render with the fused bbox proxy mapping + student train
+           step with the frozen deformation net, BASELINE configs[3]) in rays/s.
 `cpu_baseline` / `--impl reference`: the reference's pure-PyTorch path (cuda_ray=False, torch frequency encoders,
            BASELINE.json configs[0]) as ported in oracle/render.py, timed on the host cores (forward+render only).
 """
@@ -50,7 +55,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -104,21 +109,11 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def build_scene(device, seed=0):
+def build_scene(device, seed=0, seald=False):
     """Random-init D-NeRF (hashgrid) + analytic occupancy grid of the synthetic figure."""
-    import torch
-    from seald_nerf_b200 import synthetic as syn
-    from seald_nerf_b200.dnerf.network import NeRFNetwork
-    from seald_nerf_b200 import raymarching
-    torch.manual_seed(seed)
-    model = NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10).to(device)
+    from seald_nerf_b200 import microbench
+    model = microbench.build_scene(device, seed, seald)
     model.train()
-    grid = syn.make_density_grid(model.time_size, model.grid_size, 1.0, device)
-    model.density_grid.copy_(grid)
-    model.mean_density = float(grid.clamp(min=0).mean())
-    thresh = min(model.mean_density, model.density_thresh)
-    for t in range(model.time_size):
-        raymarching.packbits(model.density_grid[t], thresh, model.density_bitfield[t])
     return model
 
 
@@ -141,6 +136,53 @@ def make_batches(n, device, rank, seed=0):
     return torch.stack(ro), torch.stack(rd), ts, torch.stack(gt)
 
 
+def seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=20):
+    """SealD proxy-distillation step (SealDNeRF/utils.py:40-43,579-657 + the student step): the frozen teacher renders the
+    batch through its Seal mapper (eval branch of SealNeRFTeacherRenderer.run_cuda), the student trains on that image."""
+    import numpy as np
+    import torch
+    from seald_nerf_b200.trainer import FusedTrainer
+    from seald_nerf_b200.renderer_fused import FusedRenderer
+    from seald_nerf_b200.SealNeRF.seal_utils import SealBBoxMapper
+    teacher = build_scene(device, seed=0, seald=True)
+    teacher.eval()
+    # bbox tool: a 0.3^3 box on the torso, translated by +0.2 x and rotated 30 degrees about y (SURVEY.md config 4)
+    c, h = np.array([0.0, 0.15, 0.0]), 0.15
+    corners = np.array([[i, j, k] for i in (-1, 1) for j in (-1, 1) for k in (-1, 1)], np.float64) * h + c
+    a = np.deg2rad(30.0)
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+    T[:3, 3] = np.array([0.2, 0.0, 0.0]) + c - T[:3, :3] @ c
+    teacher.init_mapper(mapper=SealBBoxMapper("", {"type": "bbox", "raw": corners.tolist(), "transform": T.tolist(), "scale": [1, 1, 1],
+                                                   "boundType": "to", "hsv": [0.1, 0.0, 0.0]}))
+    student = build_scene(device, seed=1, seald=True)
+    trainer = FusedTrainer(student, num_rays=N_RAYS, max_samples=m_need, lr=1e-2, lr_net=1e-3, train_deform=False, world_size=world)
+    fr = FusedRenderer(teacher, max_rays=N_RAYS)
+    n = rays_o.shape[0]
+
+    def step(b):
+        out = fr.render(rays_o[b], rays_d[b], times[b], T_thresh=1e-4)
+        trainer.train_step(rays_o[b], rays_d[b], times[b], torch.nan_to_num(out["image"]))
+
+    for i in range(5):
+        step(i % n)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(i % n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    e0.record()
+    for i in range(K):
+        fr.render(rays_o[i % n], rays_d[i % n], times[i % n], T_thresh=1e-4)
+    e1.record()
+    torch.cuda.synchronize()
+    mask_count = int(fr.mask.sum())  # mapped samples in the sample buffer of the last march round
+    return {"ms_per_step": ms, "teacher_ms": e0.elapsed_time(e1) / K, "mapped_samples": mask_count}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -149,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the frame / seald / hashgrid workloads (train step only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,10 +269,25 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- full-frame render, ray tiles sharded over the ranks (configs[2]) ------------------------------------------------
+    from seald_nerf_b200 import microbench
+    frame = None
+    if not args.no_extras:
+        model.eval()
+        frame = microbench.frame_render(device, model=model, times=(0.0, 0.5, 1.0), reps=3, rank=rank, world_size=world)
+        model.train()
+    ms_frame = frame["frame_ms_median"] if frame else 0.0
+
+    # ---- SealD distillation step: teacher render (bbox proxy mapping fused into the march) + student step (configs[3]) ----
+    seald = None
+    if not args.no_extras:
+        seald = seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=max(20, K // 4))
+    ms_seald = seald["ms_per_step"] if seald else 0.0
+
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e], device=device)
+        tt = torch.tensor([ms, ms_e2e, ms_frame, ms_seald], device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(tt[0]), float(tt[1])
+        ms, ms_e2e, ms_frame, ms_seald = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
 
     # ---- per-stage timing + roofline of the dominant kernel (rank 0) ------------------------------------------------
     line = None
@@ -286,6 +344,21 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if frame:
+            line["frame"] = {"ms": ms_frame, "unit": "ms per 800x800 frame (max over ranks, incl. image all-gather)", "rays": frame["rays"],
+                             "per_time": {k: v for k, v in frame.items() if k.startswith("t=")}, "n_gpus": world,
+                             "sharding": "interleaved 256-ray tiles", "T_thresh": 1e-2}
+        if seald:
+            line["seald"] = {"value": N_RAYS * world / (ms_seald * 1e-3), "unit": "rays/s", "ms_per_step": ms_seald,
+                             "teacher_ms": seald["teacher_ms"], "mapped_samples": seald["mapped_samples"],
+                             "workload": "teacher eval render of the 4096-ray batch (bbox mapper 0.3^3, +0.2x, 30deg about y, fused in march) "
+                                         "+ student train step (frozen deform net)"}
+        if not args.no_extras:
+            g = microbench.grid_encoder(device, 22, 3, "hash", torch.float16, reps=10, hbm_gbs=hbm)
+            line["hashgrid"] = {"points": g["B"], "levels": 16, "table": "2^19 x 2 fp16", "fwd_GBs": g["kernels"]["fwd"]["GB/s"],
+                                "fwd_frac_of_hbm": g["kernels"]["fwd"]["frac_of_hbm"], "fwd_ms": g["kernels"]["fwd"]["ms"],
+                                "bwd_GBs": g["kernels"]["bwd_table_f32"]["GB/s"], "bwd_frac_of_hbm": g["kernels"]["bwd_table_f32"]["frac_of_hbm"],
+                                "bwd_ms": g["kernels"]["bwd_table_f32"]["ms"], "bytes_per_point": {"fwd": 588, "bwd_f32_table": 2124}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -318,7 +318,8 @@ struct WgradJobs {
     int n_jobs;
 };
 
-constexpr int kWgChunk = 64;  // rows staged per step
+constexpr int kWgChunk = 32;   // rows staged per step
+constexpr int kWgStages = 4;   // cp.async pipeline depth: three chunks in flight while one is consumed (the loop is load-latency bound)
 
 // Warp -> output tiles: the N/16 m-tiles are spread over the 8 warps (N in {16,32,64,128}); the warps sharing an m-tile
 // split the K/8 n-tiles in even-sized contiguous ranges (pairs of n-tiles share one ldmatrix.x4).
@@ -327,12 +328,10 @@ __global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M
     const WgradJob jb = jobs.j[blockIdx.y];
     const int N = jb.N, K = jb.K;
     const int gs = N + kPad, as = K + kPad;  // smem strides
-    __half* s_gt[2];
-    __half* s_at[2];
-    s_gt[0] = reinterpret_cast<__half*>(smem_raw);
-    s_at[0] = s_gt[0] + kWgChunk * gs;
-    s_gt[1] = s_at[0] + kWgChunk * as;
-    s_at[1] = s_gt[1] + kWgChunk * gs;
+    __half* const s_base = reinterpret_cast<__half*>(smem_raw);
+    const int stage_halves = kWgChunk * (gs + as);
+    auto s_gt = [&](const int i) { return s_base + i * stage_halves; };
+    auto s_at = [&](const int i) { return s_base + i * stage_halves + kWgChunk * gs; };
 
     const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
     const int m_begin = blockIdx.x * rows_per_cta;
@@ -361,7 +360,7 @@ __global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M
             const int row = m0 + r;
             const bool is_g = c < gchunks;
             const int cc = is_g ? c : c - gchunks;
-            __half* dst = is_g ? (s_gt[buf] + r * gs + cc * 8) : (s_at[buf] + r * as + cc * 8);
+            __half* dst = is_g ? (s_gt(buf) + r * gs + cc * 8) : (s_at(buf) + r * as + cc * 8);
             if (row < m_end) cp_async16(dst, is_g ? (jb.G + (size_t)row * jb.ldg + cc * 8) : (jb.A + (size_t)row * jb.lda + cc * 8));
             else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
         }
@@ -375,15 +374,20 @@ __global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M
     const int b_off = ((lane & 7) + 8 * ((lane >> 3) & 1)) * as + 8 * nt0 + 8 * (lane >> 4);
 
     const int n_steps = (m_end - m_begin + kWgChunk - 1) / kWgChunk;
-    stage(0, m_begin);
+#pragma unroll
+    for (int s = 0; s < kWgStages - 1; s++) {
+        if (s < n_steps) stage(s, m_begin + s * kWgChunk);
+        else cp_async_commit();
+    }
     for (int s = 0; s < n_steps; s++) {
-        const int buf = s & 1;
-        cp_async_wait<0>();
-        __syncthreads();
-        if (s + 1 < n_steps) stage(buf ^ 1, m_begin + (s + 1) * kWgChunk);
+        const int buf = s % kWgStages;
+        cp_async_wait<kWgStages - 2>();  // chunk s has landed (one group is committed per iteration)
+        __syncthreads();                 // ... for every thread, and everyone is done with the buffer refilled below
+        if (s + kWgStages - 1 < n_steps) stage((s + kWgStages - 1) % kWgStages, m_begin + (s + kWgStages - 1) * kWgChunk);
+        else cp_async_commit();
         if (n_pairs > 0) {
-            const __half* gt = s_gt[buf] + a_off;
-            const __half* at = s_at[buf] + b_off;
+            const __half* gt = s_gt(buf) + a_off;
+            const __half* at = s_at(buf) + b_off;
 #pragma unroll
             for (int kk = 0; kk < kWgChunk / 16; kk++) {
                 uint32_t a[4];
@@ -572,7 +576,7 @@ extern "C" int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t
         j.N = a.N; j.K = a.K; j.ldg = a.ldg; j.lda = a.lda; j.ldw = a.ldw; j.n_real = a.n_real; j.k_real = a.k_real;
         if (a.N + a.K > maxNK) maxNK = a.N + a.K;
     }
-    const size_t smem = (size_t)2 * kWgChunk * (maxNK + 2 * kPad) * sizeof(__half);
+    const size_t smem = (size_t)kWgStages * kWgChunk * (maxNK + 2 * kPad) * sizeof(__half);
     int rc = set_smem(k_wgrad, smem);
     if (rc) return rc;
     // rows per CTA: ~4 waves over all jobs, at least 512 rows so the atomic flush is amortised

@@ -52,14 +52,21 @@ __host__ __device__ __forceinline__ size_t umma_layer_offset(const int l, const 
     return o;
 }
 
-// src [n_real][ld] row-major fp16 (nn.Linear.weight) -> dst [K/8][n_pad][8] (rows >= n_real zero)
-__global__ void k_pack_umma(const __half* __restrict__ src, __half* __restrict__ dst, const int n_real, const int n_pad, const int K, const int ld) {
+// src [n_real][ld] row-major fp16 (nn.Linear.weight) -> dst [K/8][n_pad][8] (rows >= n_real zero); all layers in one launch
+struct PackJobs {
+    const __half* src[12];
+    int n_layers;
+};
+__global__ void k_pack_umma(const PackJobs jobs, __half* __restrict__ packed) {
+    const int l = blockIdx.y, n_layers = jobs.n_layers;
+    const bool last = (l == n_layers - 1);
+    const int K = (l == 0) ? kUK0 : kUW, n_pad = last ? kUNLast : kUW, n_real = last ? 3 : kUW, ld = K;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
-    const int chunks = K / 8;
-    if (i >= chunks * n_pad) return;
+    if (i >= K / 8 * n_pad) return;
     const int c = i / n_pad, n = i - c * n_pad;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (n < n_real) v = *reinterpret_cast<const uint4*>(src + (size_t)n * ld + c * 8);
+    if (n < n_real) v = *reinterpret_cast<const uint4*>(jobs.src[l] + (size_t)n * ld + c * 8);
+    __half* dst = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(packed) + umma_layer_offset(l, n_layers));
     *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = v;
 }
 
@@ -252,15 +259,14 @@ extern "C" uint64_t seald_field_umma_deform_bytes(int n_layers) {
 // [128][80], hidden [128][128], last [3][128].  packed: device buffer of seald_field_umma_deform_bytes(n_layers) bytes.
 extern "C" int seald_field_umma_pack_deform(const void* const* weights, int n_layers, void* packed, seald_stream_t stream) {
     if (!weights || !packed || n_layers < 2 || n_layers > 12) return SEALD_E_BADARG;
-    cudaStream_t st = to_stream(stream);
+    PackJobs jobs;
+    jobs.n_layers = n_layers;
     for (int l = 0; l < n_layers; l++) {
         if (!weights[l]) return SEALD_E_BADARG;
-        const bool last = (l == n_layers - 1);
-        const int K = (l == 0) ? kUK0 : kUW, n_pad = last ? kUNLast : kUW, n_real = last ? 3 : kUW, ld = (l == 0) ? kUK0 : kUW;
-        const int chunks = K / 8 * n_pad;
-        __half* dst = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(packed) + umma_layer_offset(l, n_layers));
-        k_pack_umma<<<div_up(chunks, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(weights[l]), dst, n_real, n_pad, K, ld);
+        if ((uintptr_t)weights[l] & 15) return SEALD_E_ALIGN;
+        jobs.src[l] = reinterpret_cast<const __half*>(weights[l]);
     }
+    k_pack_umma<<<dim3(div_up(kUW / 8 * kUW, 256), n_layers), 256, 0, to_stream(stream)>>>(jobs, reinterpret_cast<__half*>(packed));
     return launch_status();
 }
 

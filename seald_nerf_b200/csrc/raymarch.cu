@@ -618,6 +618,122 @@ __global__ void k_composite_train_bwd(const float* __restrict__ grad_weights_sum
 }
 
 // ------------------------------------------------------------------------------------------------
+// compositing (training), one WARP per ray.
+//
+// The reference walks a ray's samples with one thread (raymarching.cu:516-576, :620-681): a chain of dependent global
+// loads.  Here the 32 lanes load 32 consecutive samples at once (coalesced) and evaluate alpha = 1 - exp(-sigma * delta)
+// in parallel; the front-to-back recurrence itself (T, the colour / depth / weight sums, the early stop at T < T_thresh)
+// is then replayed IN ORDER over warp shuffles, every lane doing the same fp32 operations in the reference's expression
+// order - so sums, the termination sample and the zero pattern of the gradients are exactly those of the serial loop.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kCompWarps = 8;
+
+__global__ void __launch_bounds__(kCompWarps * 32) k_composite_train_fwd_warp(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                             const float* __restrict__ deltas, const int* __restrict__ rays,
+                                                                             const uint32_t M, const uint32_t N, const float T_thresh,
+                                                                             float* __restrict__ weights_sum, float* __restrict__ depth,
+                                                                             float* __restrict__ image) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t n = blockIdx.x * kCompWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+    float r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+    if (num_steps != 0 && offset + num_steps <= M) {
+        float T = 1.0f;
+        bool done = false;
+        for (uint32_t base = 0; base < num_steps && !done; base += 32) {
+            const uint32_t i = base + lane;
+            float alpha = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, d1 = 0.f;
+            if (i < num_steps) {
+                const size_t s = (size_t)offset + i;
+                const float2 dl = *reinterpret_cast<const float2*>(deltas + s * 2);
+                alpha = 1.0f - __expf(-sigmas[s] * dl.x);
+                d1 = dl.y;
+                c0 = rgbs[s * 3]; c1 = rgbs[s * 3 + 1]; c2 = rgbs[s * 3 + 2];
+            }
+            const uint32_t cnt = min(32u, num_steps - base);
+            for (uint32_t j = 0; j < cnt; j++) {
+                const float a = __shfl_sync(FULL, alpha, j);
+                const float x0 = __shfl_sync(FULL, c0, j), x1 = __shfl_sync(FULL, c1, j), x2 = __shfl_sync(FULL, c2, j);
+                const float weight = a * T;
+                r += weight * x0;
+                g += weight * x1;
+                b += weight * x2;
+                t += __shfl_sync(FULL, d1, j);
+                d += weight * t;
+                ws += weight;
+                T *= 1.0f - a;
+                if (T < T_thresh) { done = true; break; }
+            }
+        }
+    }
+    if (lane == 0) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[index * 3] = r;
+        image[index * 3 + 1] = g;
+        image[index * 3 + 2] = b;
+    }
+}
+
+__global__ void __launch_bounds__(kCompWarps * 32) k_composite_train_bwd_warp(
+    const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ sigmas,
+    const float* __restrict__ rgbs, const float* __restrict__ deltas, const int* __restrict__ rays, const float* __restrict__ weights_sum,
+    const float* __restrict__ image, const uint32_t M, const uint32_t N, const float T_thresh, float* __restrict__ grad_sigmas,
+    float* __restrict__ grad_rgbs) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t n = blockIdx.x * kCompWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;
+    const float gi0 = grad_image[(size_t)index * 3], gi1 = grad_image[(size_t)index * 3 + 1], gi2 = grad_image[(size_t)index * 3 + 2];
+    const float gws = grad_weights_sum[index];
+    const float r_final = image[(size_t)index * 3], g_final = image[(size_t)index * 3 + 1], b_final = image[(size_t)index * 3 + 2];
+    const float ws_final = weights_sum[index];
+    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0;
+    bool done = false;
+    for (uint32_t base = 0; base < num_steps && !done; base += 32) {
+        const uint32_t i = base + lane;
+        float alpha = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, d0 = 0.f;
+        const size_t s = (size_t)offset + i;
+        if (i < num_steps) {
+            d0 = deltas[s * 2];
+            alpha = 1.0f - __expf(-sigmas[s] * d0);
+            c0 = rgbs[s * 3]; c1 = rgbs[s * 3 + 1]; c2 = rgbs[s * 3 + 2];
+        }
+        const uint32_t cnt = min(32u, num_steps - base);
+        float my_w = 0.f, my_gs = 0.f;
+        uint32_t processed = 0;
+        for (uint32_t j = 0; j < cnt; j++) {
+            const float a = __shfl_sync(FULL, alpha, j);
+            const float x0 = __shfl_sync(FULL, c0, j), x1 = __shfl_sync(FULL, c1, j), x2 = __shfl_sync(FULL, c2, j);
+            const float dd = __shfl_sync(FULL, d0, j);
+            const float weight = a * T;
+            r += weight * x0;
+            g += weight * x1;
+            b += weight * x2;
+            ws += weight;
+            T *= 1.0f - a;
+            const float gsig = dd * (
+                gi0 * (T * x0 - (r_final - r)) +
+                gi1 * (T * x1 - (g_final - g)) +
+                gi2 * (T * x2 - (b_final - b)) +
+                gws * (1 - ws_final)
+            );
+            if (lane == j) { my_w = weight; my_gs = gsig; }
+            processed = j + 1;
+            if (T < T_thresh) { done = true; break; }
+        }
+        if (lane < processed) {
+            grad_rgbs[s * 3] = gi0 * my_w;
+            grad_rgbs[s * 3 + 1] = gi1 * my_w;
+            grad_rgbs[s * 3 + 2] = gi2 * my_w;
+            grad_sigmas[s] = my_gs;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // inference march / composite
 // ------------------------------------------------------------------------------------------------
 template <bool SEAL>
@@ -918,6 +1034,11 @@ extern "C" int seald_composite_rays_train_forward(const float* sigmas, const flo
     if (N == 0) return 0;
     if (!rays || !weights_sum || !depth || !image) return SEALD_E_BADARG;
     if (M > 0 && (!sigmas || !rgbs || !deltas)) return SEALD_E_BADARG;
+    if (((uintptr_t)deltas & 7) == 0) {
+        k_composite_train_fwd_warp<<<div_up(N, kCompWarps), kCompWarps * 32, 0, to_stream(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh,
+                                                                                                   weights_sum, depth, image);
+        return launch_status();
+    }
     const uint32_t threads = (N >= 4u * SEALD_NUM_SMS * 128u) ? 128u : 32u;
     k_composite_train_fwd<<<div_up(N, threads), threads, 0, to_stream(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
     return launch_status();
@@ -930,9 +1051,9 @@ extern "C" int seald_composite_rays_train_backward(const float* grad_weights_sum
     if (N == 0 || M == 0) return 0;
     if (!grad_weights_sum || !grad_image || !sigmas || !rgbs || !deltas || !rays || !weights_sum || !image || !grad_sigmas || !grad_rgbs)
         return SEALD_E_BADARG;
-    const uint32_t threads = (N >= 4u * SEALD_NUM_SMS * 128u) ? 128u : 32u;
-    k_composite_train_bwd<<<div_up(N, threads), threads, 0, to_stream(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
-                                                                                 weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+    k_composite_train_bwd_warp<<<div_up(N, kCompWarps), kCompWarps * 32, 0, to_stream(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas,
+                                                                                               rays, weights_sum, image, M, N, T_thresh,
+                                                                                               grad_sigmas, grad_rgbs);
     return launch_status();
 }
 
