@@ -106,17 +106,24 @@ int seald_composite_rays_train_backward(const float* grad_weights_sum, const flo
                                         float T_thresh, float* grad_sigmas, float* grad_rgbs, seald_stream_t stream);
 
 /* Inference march / composite.  Replace march_rays / composite_rays (raymarching.h:17-18,
- * raymarching.cu:701-914).  n_alive_dev (optional, may be NULL): device int32 holding the live count;
- * when given it overrides the host n_alive bound inside the kernel (threads >= *n_alive_dev exit), which
- * lets run_cuda loop without the host-synced boolean-mask compaction (dnerf/renderer.py:372). */
+ * raymarching.cu:701-914).  n_alive_dev / n_step_dev (optional, may be NULL): device int32 holding the live ray count and
+ * the samples per ray of this round; when given they override the host values inside the kernel (the host n_alive is then
+ * only the launch bound), which lets run_cuda loop without the host-synced boolean-mask compaction and `n_step` choice
+ * (dnerf/renderer.py:353-372).  seald_march_rays writes delta = 0 terminator slots itself (no pre-zeroing needed). */
 int seald_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
                      const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
                      uint32_t C, uint32_t H, const uint8_t* bitfield, const float* nears, const float* fars,
                      float* xyzs, float* dirs, float* deltas, const float* noises, const int32_t* n_alive_dev,
-                     seald_stream_t stream);
+                     const int32_t* n_step_dev, seald_stream_t stream);
 int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
                          const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
-                         float* depth, float* image, const int32_t* n_alive_dev, seald_stream_t stream);
+                         float* depth, float* image, const int32_t* n_alive_dev, const int32_t* n_step_dev,
+                         seald_stream_t stream);
+/* Device-side schedule of the render loop (dnerf/renderer.py:350-376).  state[8] int32 = {n_alive, n_step, n_alive*n_step,
+ * steps done, samples evaluated so far, non-empty rounds so far, -, -}: adds the finished round's n_step to the step counter, takes the compacted count *n_alive_new (0 once
+ * max_steps is reached) and derives the next round's n_step = clamp(N / n_alive, 1, max_n_step) (the reference uses 8). */
+int seald_render_schedule(int32_t* state, const int32_t* n_alive_new, uint32_t N, uint32_t max_steps, uint32_t max_n_step,
+                          seald_stream_t stream);
 /* Order-preserving compaction of rays_alive (entries >= 0 kept): out[0..*n_out) ; replaces
  * `rays_alive = rays_alive[rays_alive >= 0]` (dnerf/renderer.py:372).  scratch: >= ceil(n/1024)+1 int32. */
 int seald_compact_alive(const int32_t* rays_alive, uint32_t n_alive, const int32_t* n_alive_dev, int32_t* out,
@@ -186,7 +193,7 @@ int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays
                           const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
                           uint32_t C, uint32_t H, const uint8_t* bitfield, const float* nears, const float* fars,
                           float* xyzs, float* dirs, float* deltas, const float* noises, const int32_t* n_alive_dev,
-                          const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream);
+                          const int32_t* n_step_dev, const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream);
 int seald_march_rays_train_seal(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound,
                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                 const float* nears, const float* fars, const float* aabb6, float min_near,

@@ -737,13 +737,14 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_train_bwd_warp(
 // inference march / composite
 // ------------------------------------------------------------------------------------------------
 template <bool SEAL>
-__global__ void k_march_rays(uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
+__global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
                              const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float bound, const float dt_gamma,
                              const uint32_t max_steps, const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid,
                              const float* __restrict__ nears, const float* __restrict__ fars, float* xyzs, float* dirs, float* deltas,
-                             const float* __restrict__ noises, const int* __restrict__ n_alive_dev,
+                             const float* __restrict__ noises, const int* __restrict__ n_alive_dev, const int* __restrict__ n_step_dev,
                              const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask) {
     if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
+    if (n_step_dev) n_step = (uint32_t)max(*n_step_dev, 0);
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= n_alive) return;
 
@@ -802,10 +803,12 @@ __global__ void k_march_rays(uint32_t n_alive, const uint32_t n_step, const int*
     }
 }
 
-__global__ void k_composite_rays(uint32_t n_alive, const uint32_t n_step, const float T_thresh, int* rays_alive, float* rays_t,
+__global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, const float T_thresh, int* rays_alive, float* rays_t,
                                  const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
-                                 float* weights_sum, float* depth, float* image, const int* __restrict__ n_alive_dev) {
+                                 float* weights_sum, float* depth, float* image, const int* __restrict__ n_alive_dev,
+                                 const int* __restrict__ n_step_dev) {
     if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
+    if (n_step_dev) n_step = (uint32_t)max(*n_step_dev, 0);
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= n_alive) return;
 
@@ -925,6 +928,28 @@ __global__ void k_compact_scatter(const int* __restrict__ rays_alive, uint32_t n
         const uint32_t pos = (uint32_t)tile_offsets[blockIdx.x] + (w ? s_warp[w - 1] : 0u) + __popc(bal & ((1u << lane) - 1u));
         out[pos] = v;
     }
+}
+
+
+// Device-side schedule of the inference loop (dnerf/renderer.py:350-376): after a round has been composited and the alive
+// list compacted, advance the step counter and derive the next round's parameters without a host round trip.
+//   state[0] = n_alive (in: count after compaction; forced to 0 once `max_steps` is reached), state[1] = n_step of the NEXT
+//   round = clamp(N / n_alive, 1, 8), state[2] = n_alive * n_step (live sample rows), state[3] = steps marched so far,
+//   state[4] = live sample rows evaluated so far, state[5] = non-empty rounds so far (statistics).
+__global__ void k_render_schedule(int* __restrict__ state, const int* __restrict__ n_alive_new, const uint32_t N, const uint32_t max_steps,
+                                  const uint32_t max_n_step) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int step = state[3] + state[1];
+    state[4] += state[2];
+    state[5] += (state[0] > 0) ? 1 : 0;
+    int n_alive = *n_alive_new;
+    if ((uint32_t)step >= max_steps) n_alive = 0;
+    int n_step = 1;
+    if (n_alive > 0) n_step = max(min((int)(N / (uint32_t)n_alive), (int)max_n_step), 1);
+    state[0] = n_alive;
+    state[1] = n_step;
+    state[2] = n_alive * n_step;
+    state[3] = step;
 }
 
 }  // namespace seald
@@ -1060,13 +1085,14 @@ extern "C" int seald_composite_rays_train_backward(const float* grad_weights_sum
 static int march_impl(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                       const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* bitfield,
                       const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
-                      const int32_t* n_alive_dev, const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream) {
-    if (n_alive == 0 || n_step == 0) return 0;
+                      const int32_t* n_alive_dev, const int32_t* n_step_dev, const seald_seal_mapper* mapper, uint8_t* mask,
+                      seald_stream_t stream) {
+    if (n_alive == 0 || (n_step == 0 && !n_step_dev)) return 0;
     if (!rays_alive || !rays_t || !rays_o || !rays_d || !bitfield || !fars || !xyzs || !dirs || !deltas) return SEALD_E_BADARG;
     static const seald_seal_mapper no_mapper = {};
     auto k = mapper ? k_march_rays<true> : k_march_rays<false>;
     k<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
-                                                           bitfield, nears, fars, xyzs, dirs, deltas, noises, n_alive_dev,
+                                                           bitfield, nears, fars, xyzs, dirs, deltas, noises, n_alive_dev, n_step_dev,
                                                            mapper ? *mapper : no_mapper, mask);
     return launch_status();
 }
@@ -1074,28 +1100,35 @@ static int march_impl(uint32_t n_alive, uint32_t n_step, const int32_t* rays_ali
 extern "C" int seald_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                                 const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                                 const uint8_t* bitfield, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
-                                const float* noises, const int32_t* n_alive_dev, seald_stream_t stream) {
+                                const float* noises, const int32_t* n_alive_dev, const int32_t* n_step_dev, seald_stream_t stream) {
     return march_impl(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, bitfield, nears, fars, xyzs, dirs,
-                      deltas, noises, n_alive_dev, nullptr, nullptr, stream);
+                      deltas, noises, n_alive_dev, n_step_dev, nullptr, nullptr, stream);
 }
 
 extern "C" int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                                      const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                                      const uint8_t* bitfield, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
-                                     const float* noises, const int32_t* n_alive_dev, const seald_seal_mapper* mapper, uint8_t* mask,
-                                     seald_stream_t stream) {
+                                     const float* noises, const int32_t* n_alive_dev, const int32_t* n_step_dev,
+                                     const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream) {
     if (int rc = check_fusable_mapper(mapper, mask)) return rc;
     return march_impl(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, bitfield, nears, fars, xyzs, dirs,
-                      deltas, noises, n_alive_dev, mapper, mask, stream);
+                      deltas, noises, n_alive_dev, n_step_dev, mapper, mask, stream);
 }
 
 extern "C" int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t, const float* sigmas,
                                     const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
-                                    const int32_t* n_alive_dev, seald_stream_t stream) {
+                                    const int32_t* n_alive_dev, const int32_t* n_step_dev, seald_stream_t stream) {
     if (n_alive == 0) return 0;
     if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return SEALD_E_BADARG;
     k_composite_rays<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
-                                                                           weights_sum, depth, image, n_alive_dev);
+                                                                           weights_sum, depth, image, n_alive_dev, n_step_dev);
+    return launch_status();
+}
+
+extern "C" int seald_render_schedule(int32_t* state, const int32_t* n_alive_new, uint32_t N, uint32_t max_steps, uint32_t max_n_step,
+                                     seald_stream_t stream) {
+    if (!state || !n_alive_new || N == 0 || max_n_step == 0) return SEALD_E_BADARG;
+    k_render_schedule<<<1, 32, 0, to_stream(stream)>>>(state, n_alive_new, N, max_steps, max_n_step);
     return launch_status();
 }
 

@@ -189,7 +189,7 @@ class _march_rays(Function):
         noises = torch.rand(n_alive, dtype=dt, device=dev) if perturb else torch.zeros(n_alive, dtype=dt, device=dev)
         _lib.call("seald_march_rays", int(n_alive), int(n_step), ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), float(bound),
                   float(dt_gamma), int(max_steps), int(C), int(H), ptr(density_bitfield.contiguous()), ptr(near), ptr(far), ptr(xyzs),
-                  ptr(dirs), ptr(deltas), ptr(noises), None, _lib.stream())
+                  ptr(dirs), ptr(deltas), ptr(noises), None, None, _lib.stream())
         return xyzs, dirs, deltas
 
 
@@ -202,7 +202,7 @@ class _composite_rays(Function):
     def forward(ctx, n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
         _lib.call("seald_composite_rays", int(n_alive), int(n_step), float(T_thresh), ptr(rays_alive), ptr(rays_t),
                   ptr(sigmas.contiguous()), ptr(rgbs.contiguous()), ptr(deltas.contiguous()), ptr(weights_sum), ptr(depth), ptr(image),
-                  None, _lib.stream())
+                  None, None, _lib.stream())
         return tuple()
 
 
@@ -227,7 +227,7 @@ def march_rays_seal(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, 
     noises = torch.rand(n_alive, dtype=dt, device=dev) if perturb else torch.zeros(n_alive, dtype=dt, device=dev)
     _lib.call("seald_march_rays_seal", int(n_alive), int(n_step), ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), float(bound),
               float(dt_gamma), int(max_steps), int(C), int(H), ptr(density_bitfield.contiguous()), ptr(near), ptr(far), ptr(xyzs),
-              ptr(dirs), ptr(deltas), ptr(noises), None, C_.byref(mapper.descriptor(dev)), ptr(mask), _lib.stream())
+              ptr(dirs), ptr(deltas), ptr(noises), None, None, C_.byref(mapper.descriptor(dev)), ptr(mask), _lib.stream())
     return xyzs, dirs, deltas, mask
 
 

@@ -7,9 +7,10 @@ Replaces the loop of dnerf/renderer.py:332-381 and SealDNeRF/renderer.py:214-286
                        [-> map_color on mapped samples]  ->  composite_rays (in place)  ->  compact alive list
 
 Same schedule as the reference (n_step = clamp(N // n_alive, 1, 8), stop when no ray is alive or `max_steps` is reached),
-so images match the drop-in `NeRFRenderer.run_cuda` bit for bit; what changes is the plumbing: no per-iteration
-allocation or zero-fill (the march kernel writes the terminator slots itself), one fused field pass over exactly the
-live rows, device-side order-preserving compaction, ONE 4-byte D2H read per iteration (the live count the schedule needs).
+so images match the drop-in `NeRFRenderer.run_cuda`; what changes is the plumbing: no per-iteration allocation or
+zero-fill (the march kernel writes the terminator slots itself), one fused field pass over exactly the live rows,
+device-side order-preserving compaction, and NO host synchronisation inside the loop: n_alive / n_step live on the device
+(`seald_render_schedule`), two rounds are replayed as one CUDA graph, and the host only polls a lagging copy of n_alive.
 
 Multi-GPU: rays are independent, the model is replicated.  `render_sharded` gives every rank the rays of
 interleaved tiles (tile t -> rank t % world; background/object load balances out), renders them locally with no
@@ -26,7 +27,7 @@ from ._lib import ptr
 
 
 class FusedRenderer:
-    def __init__(self, model, max_rays, device=None):
+    def __init__(self, model, max_rays, device=None, use_graph=True, max_n_step=8):
         self.model = model
         self.device = device or model.encoder.embeddings.device
         if self.device.type != "cuda":
@@ -34,15 +35,23 @@ class FusedRenderer:
         self.cfg = model._field_cfg
         self.N = int(max_rays)
         self.cap = self.N + 128  # n_alive * n_step <= N, rounded up to the MLP tile
+        self.use_graph = bool(use_graph)
+        self.max_n_step = int(max_n_step)  # 8 = the reference's schedule (dnerf/renderer.py:360)
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         N, cap = self.N, self.cap
+        self.rays_o = torch.zeros(N, 3, **f32)
+        self.rays_d = torch.zeros(N, 3, **f32)
+        self.bitfield = torch.zeros(model.density_bitfield.shape[1], dtype=torch.uint8, device=dev)
         self.nears = torch.empty(N, **f32)
         self.fars = torch.empty(N, **f32)
         self.rays_t = torch.empty(N, **f32)
+        self.noises = torch.zeros(N, **f32)
         self.alive = [torch.empty(N, **i32), torch.empty(N, **i32)]
-        self.n_alive_dev = torch.zeros(1, **i32)
+        # device-side loop state {n_alive, n_step, n_alive * n_step, steps done} and the compaction's output count
+        self.state = torch.zeros(8, **i32)  # + [4] live samples evaluated so far, [5] non-empty rounds so far
+        self.n_new = torch.zeros(1, **i32)
         self.scratch = torch.empty((N + 1023) // 1024 + 1, **i32)
         self.xyzs = torch.zeros(cap, 3, **f32)
         self.dirs = torch.zeros(cap, 3, **f32)
@@ -53,10 +62,12 @@ class FusedRenderer:
         self.depth = torch.empty(N, **f32)
         self.image = torch.empty(N, 3, **f32)
         self.time = torch.zeros(1, **f32)
-        self.h_count = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.h_state = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self._poll = [(torch.zeros(8, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
         self.hw = F.HalfWeights(self.cfg, dev)
         self.table16 = None
         self.refresh_weights()
+        self._graphs = {}
         self.iterations = 0
         self.samples = 0
         self.launches = 0
@@ -65,17 +76,77 @@ class FusedRenderer:
         """Re-stage the fp16 copies of the model's parameters (call after the model was trained / loaded)."""
         m = self.model
         self.hw.refresh([w.detach() for w in m.mlp_weights()])
-        self.table16 = m.encoder.embeddings.detach().to(torch.float16).contiguous()
+        t16 = m.encoder.embeddings.detach().to(torch.float16).contiguous()
+        if self.table16 is None:
+            self.table16 = t16
+        else:
+            self.table16.copy_(t16)  # (captured graphs hold this pointer)
+
+    # ---- one round of the loop; every size is an upper bound, the live counts are read on the device ---------------------
+    def _round(self, N, cur, first, opts, mapper, desc):
+        m, cfg, st = self.model, self.cfg, _lib.stream()
+        alive, nxt = self.alive[cur], self.alive[1 - cur]
+        n_alive_dev, n_step_dev, m_dev = self.state[0:1], self.state[1:2], self.state[2:3]
+        n_bound = N  # launch bound; kernels stop at *n_alive_dev
+        noises = self.noises if (first and opts["perturb"]) else None
+        launches = 0
+        if mapper is not None and mapper.fusable:
+            _lib.call("seald_march_rays_seal", n_bound, 1, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
+                      opts["dt_gamma"], opts["max_steps"], int(m.cascade), int(m.grid_size), ptr(self.bitfield), ptr(self.nears),
+                      ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), ptr(n_alive_dev), ptr(n_step_dev),
+                      C.byref(desc), ptr(self.mask), st)
+        else:
+            _lib.call("seald_march_rays", n_bound, 1, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
+                      opts["dt_gamma"], opts["max_steps"], int(m.cascade), int(m.grid_size), ptr(self.bitfield), ptr(self.nears),
+                      ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), ptr(n_alive_dev), ptr(n_step_dev), st)
+            if mapper is not None:  # anchor mapper: batch-wide early exit, separate op
+                _lib.call("seald_seal_map_to_origin", C.byref(desc), ptr(self.xyzs), ptr(self.dirs), self.cap, ptr(m_dev), ptr(self.xyzs),
+                          ptr(self.dirs), ptr(self.mask), ptr(mapper._dev_cache["scratch_i"]), st)
+                launches += 3
+        F.field_forward(cfg, self.hw, self.ws, self.xyzs, self.dirs, self.time, self.table16, m.encoder.offsets, m_dev, 1, M=self.cap)
+        if mapper is not None and mapper.has_color_map:
+            _lib.call("seald_seal_map_color", C.byref(mapper._dev_cache["color"]), ptr(self.xyzs), ptr(self.mask), ptr(self.ws.rgb), self.cap,
+                      ptr(m_dev), ptr(mapper._dev_cache["scratch_f"]), st)
+            launches += 4
+        _lib.call("seald_composite_rays", n_bound, 1, opts["T_thresh"], ptr(alive), ptr(self.rays_t), ptr(self.ws.sigma), ptr(self.ws.rgb),
+                  ptr(self.deltas), ptr(self.weights_sum), ptr(self.depth), ptr(self.image), ptr(n_alive_dev), ptr(n_step_dev), st)
+        _lib.call("seald_compact_alive", ptr(alive), n_bound, ptr(n_alive_dev), ptr(nxt), ptr(self.n_new), ptr(self.scratch), st)
+        _lib.call("seald_render_schedule", ptr(self.state), ptr(self.n_new), N, opts["max_steps"], self.max_n_step, st)
+        return launches + 9
+
+    def _double_round_graph(self, N, opts, mapper, desc):
+        """Rounds 2k+1 and 2k+2 (alive buffers 1 -> 0 -> 1) as one CUDA graph; cached per ray count / options / mapper."""
+        key = (N, tuple(sorted(opts.items())), id(mapper), None if mapper is None else id(mapper._dev_cache["desc"]))
+        g = self._graphs.get(key)
+        if g is None:
+            saved = self.state.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):  # warm-up outside capture (function attributes, lazy module loads) on an empty state
+                self.state.zero_()
+                self._round(N, 1, False, opts, mapper, desc)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            self.state.zero_()
+            with torch.cuda.graph(g):
+                n = self._round(N, 1, False, opts, mapper, desc)
+                n += self._round(N, 0, False, opts, mapper, desc)
+            self.state.copy_(saved)
+            g.launches = n
+            self._graphs[key] = g
+        return g
 
     @torch.no_grad()
     def render(self, rays_o, rays_d, time, bg_color=None, perturb=False, dt_gamma=0, max_steps=1024, T_thresh=None, normalize_depth=None,
                **kwargs):
-        """rays_o, rays_d [..., 3] (<= max_rays rays); time [1,1] or float -> dict(image [...,3], depth [...], weights_sum [N])."""
-        m, cfg = self.model, self.cfg
+        """rays_o, rays_d [..., 3] (<= max_rays rays); time [1,1] or float -> dict(image [...,3], depth [...], weights_sum [N]).
+
+        The loop runs without host synchronisation: round sizes (n_alive, n_step = clamp(N // n_alive, 1, 8)) live on the
+        device (seald_render_schedule), launches use upper bounds, and the host only polls a lagging copy of n_alive to
+        know when to stop (extra rounds after the last ray died are empty launches)."""
+        m = self.model
         prefix = rays_o.shape[:-1]
-        rays_o = rays_o.contiguous().view(-1, 3).float()
-        rays_d = rays_d.contiguous().view(-1, 3).float()
-        N = rays_o.shape[0]
+        N = rays_o.numel() // 3
         if N > self.N:
             raise RuntimeError("FusedRenderer was sized for %d rays, got %d" % (self.N, N))
         mapper = getattr(m, "seal_mapper", None)
@@ -86,66 +157,56 @@ class FusedRenderer:
             normalize_depth = not seald
         if bg_color is None:
             bg_color = 1
+        opts = {"perturb": bool(perturb), "dt_gamma": float(dt_gamma), "max_steps": int(max_steps), "T_thresh": float(T_thresh)}
         st = _lib.stream()
-        td = self.time
+        self.rays_o[:N].copy_(rays_o.reshape(-1, 3), non_blocking=True)
+        self.rays_d[:N].copy_(rays_d.reshape(-1, 3), non_blocking=True)
         if torch.is_tensor(time):
-            td.copy_(time.reshape(-1)[:1])
-            t_host = None
+            self.time.copy_(time.reshape(-1)[:1])
+            t_idx = m._frame_index(self.time.view(1, 1))  # (device scalar -> index: the same host sync as the reference, renderer.py:285)
         else:
-            td.fill_(float(time))
-            t_host = float(time)
-        if t_host is None:
-            t_idx = m._frame_index(td.view(1, 1))  # (device scalar -> index: the same host sync as the reference, renderer.py:285)
-        else:
-            t_idx = min(max(int(t_host * m.time_size), 0), m.time_size - 1)
-        bitfield = m.density_bitfield[t_idx]
+            self.time.fill_(float(time))
+            t_idx = min(max(int(float(time) * m.time_size), 0), m.time_size - 1)
+        self.bitfield.copy_(m.density_bitfield[t_idx], non_blocking=True)
         aabb = m.aabb_train if m.training else m.aabb_infer
-        nears, fars, rays_t = self.nears[:N], self.fars[:N], self.rays_t[:N]
-        _lib.call("seald_near_far_from_aabb", ptr(rays_o), ptr(rays_d), ptr(aabb), N, float(m.min_near), ptr(nears), ptr(fars), st)
-        rays_t.copy_(nears)
+        nears, fars = self.nears[:N], self.fars[:N]
+        _lib.call("seald_near_far_from_aabb", ptr(self.rays_o), ptr(self.rays_d), ptr(aabb), N, float(m.min_near), ptr(nears), ptr(fars), st)
+        self.rays_t[:N].copy_(nears)
         ws_out, depth, image = self.weights_sum[:N], self.depth[:N], self.image[:N]
         ws_out.zero_(); depth.zero_(); image.zero_()
-        cur = 0
         torch.arange(N, dtype=torch.int32, device=self.device, out=self.alive[0][:N])
-        n_alive, step, launches, samples, iters = N, 0, 5, 0, 0
-        fused_map = mapper is not None and mapper.fusable
+        if perturb:
+            self.noises[:N].uniform_(0, 1)
+        self.h_state.zero_()
+        self.h_state[0] = N; self.h_state[1] = 1; self.h_state[2] = N
+        self.state.copy_(self.h_state, non_blocking=True)
         desc = mapper.descriptor(self.device) if mapper is not None else None
-        while step < max_steps and n_alive > 0:
-            n_step = max(min(N // n_alive, 8), 1)
-            n_s = n_alive * n_step
-            M = (n_s + 127) // 128 * 128
-            alive = self.alive[cur]
-            noises = torch.rand(n_alive, dtype=torch.float32, device=self.device) if (perturb and step == 0) else None
-            if fused_map:
-                _lib.call("seald_march_rays_seal", n_alive, n_step, ptr(alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), float(m.bound),
-                          float(dt_gamma), int(max_steps), int(m.cascade), int(m.grid_size), ptr(bitfield), ptr(nears), ptr(fars),
-                          ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), None, C.byref(desc), ptr(self.mask), st)
+
+        launches = 12 + self._round(N, 0, True, opts, mapper, desc)  # round 0 (perturbed start, alive 0 -> 1)
+        rounds = 1
+        graph = self._double_round_graph(N, opts, mapper, desc) if self.use_graph else None
+        k = 0
+        max_rounds = int(max_steps) + 2
+        while rounds < max_rounds:
+            if graph is not None:
+                graph.replay()
+                launches += graph.launches
             else:
-                _lib.call("seald_march_rays", n_alive, n_step, ptr(alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), float(m.bound),
-                          float(dt_gamma), int(max_steps), int(m.cascade), int(m.grid_size), ptr(bitfield), ptr(nears), ptr(fars),
-                          ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), None, st)
-                if mapper is not None:  # anchor mapper: batch-wide early exit, separate op
-                    _lib.call("seald_seal_map_to_origin", C.byref(desc), ptr(self.xyzs), ptr(self.dirs), n_s, None, ptr(self.xyzs),
-                              ptr(self.dirs), ptr(self.mask), ptr(mapper._dev_cache["scratch_i"]), st)
-                    launches += 2
-            F.field_forward(cfg, self.hw, self.ws, self.xyzs, self.dirs, td, self.table16, m.encoder.offsets, None, 1, M=M)
-            if mapper is not None and mapper.has_color_map:
-                _lib.call("seald_seal_map_color", C.byref(mapper._dev_cache["color"]), ptr(self.xyzs), ptr(self.mask), ptr(self.ws.rgb), n_s,
-                          None, ptr(mapper._dev_cache["scratch_f"]), st)
-                launches += 3
-            _lib.call("seald_composite_rays", n_alive, n_step, float(T_thresh), ptr(alive), ptr(rays_t), ptr(self.ws.sigma), ptr(self.ws.rgb),
-                      ptr(self.deltas), ptr(ws_out), ptr(depth), ptr(image), None, st)
-            nxt = self.alive[1 - cur]
-            _lib.call("seald_compact_alive", ptr(alive), n_alive, None, ptr(nxt), ptr(self.n_alive_dev), ptr(self.scratch), st)
-            self.h_count.copy_(self.n_alive_dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            launches += 8
-            samples += n_s
-            iters += 1
-            n_alive = int(self.h_count[0])
-            cur = 1 - cur
-            step += n_step
-        self.iterations, self.samples, self.launches = iters, samples, launches
+                launches += self._round(N, 1, False, opts, mapper, desc) + self._round(N, 0, False, opts, mapper, desc)
+            rounds += 2
+            # lagging poll of n_alive: read the state copied one double-round ago, never wait for the newest one
+            buf, ev = self._poll[k % 4]
+            buf.copy_(self.state, non_blocking=True)
+            ev.record()
+            if k >= 1:
+                pbuf, pev = self._poll[(k - 1) % 4]
+                pev.synchronize()
+                if int(pbuf[0]) == 0:
+                    break
+            k += 1
+        self.h_state.copy_(self.state, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.iterations, self.samples, self.launches = int(self.h_state[5]), int(self.h_state[4]), launches
         image = image + (1 - ws_out).unsqueeze(-1) * bg_color
         depth_out = torch.clamp(depth - nears, min=0) / (fars - nears) if normalize_depth else depth.clone()
         return {"image": image.view(*prefix, 3), "depth": depth_out.view(*prefix), "weights_sum": ws_out.clone()}
