@@ -94,7 +94,13 @@ int seald_march_rays_train(const float* rays_o, const float* rays_d, const uint8
                            const float* nears, const float* fars, const float* aabb6, float min_near,
                            float* nears_out, float* fars_out,
                            float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
-                           const float* noises, seald_stream_t stream);
+                           const float* noises, const float* occ_aabb6, seald_stream_t stream);
+/* World-space box of all occupied cells of `bitfield` (all cascades), grown by `guard_cells` (>= 1) cells; scratch: 6*C int32.
+ * Passing it to the march functions as occ_aabb6 (optional, NULL = off) lets rays that cannot meet an occupied cell end
+ * without walking the empty volume, and every walk stop where the ray leaves the box.  Only probes of empty cells are
+ * removed: counts, positions and deltas are unchanged.  Must be recomputed whenever the bitfield changes. */
+int seald_occupancy_aabb(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, int32_t guard_cells, int32_t* scratch,
+                         float* aabb6, seald_stream_t stream);
 
 /* Replaces composite_rays_train_forward/backward (raymarching.h:14-15, raymarching.cu:501-693). */
 int seald_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
@@ -114,7 +120,7 @@ int seald_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_aliv
                      const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
                      uint32_t C, uint32_t H, const uint8_t* bitfield, const float* nears, const float* fars,
                      float* xyzs, float* dirs, float* deltas, const float* noises, const int32_t* n_alive_dev,
-                     const int32_t* n_step_dev, seald_stream_t stream);
+                     const int32_t* n_step_dev, const float* occ_aabb6, seald_stream_t stream);
 int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
                          const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
                          float* depth, float* image, const int32_t* n_alive_dev, const int32_t* n_step_dev,
@@ -193,13 +199,14 @@ int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays
                           const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
                           uint32_t C, uint32_t H, const uint8_t* bitfield, const float* nears, const float* fars,
                           float* xyzs, float* dirs, float* deltas, const float* noises, const int32_t* n_alive_dev,
-                          const int32_t* n_step_dev, const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream);
+                          const int32_t* n_step_dev, const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6,
+                          seald_stream_t stream);
 int seald_march_rays_train_seal(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound,
                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                 const float* nears, const float* fars, const float* aabb6, float min_near,
                                 float* nears_out, float* fars_out, float* xyzs, float* dirs, float* deltas, int32_t* rays,
                                 int32_t* counter, const float* noises, const seald_seal_mapper* mapper, uint8_t* mask,
-                                seald_stream_t stream);
+                                const float* occ_aabb6, seald_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Small encoders.  Replace freq_encode_forward/backward (freqencoder/src/freqencoder.h:7-10) and

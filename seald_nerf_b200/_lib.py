@@ -25,18 +25,19 @@ _SIGS = {
     "seald_morton3D": [_vp, _u32, _vp, _vp],
     "seald_morton3D_invert": [_vp, _u32, _vp, _vp],
     "seald_packbits": [_vp, _u32, _f32, _vp, _vp],
-    "seald_march_rays_train": [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_march_rays_train": [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_occupancy_aabb": [_vp, _u32, _u32, _f32, _i32, _vp, _vp, _vp],
     "seald_composite_rays_train_forward": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp],
     "seald_composite_rays_train_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp],
-    "seald_march_rays": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_march_rays": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_composite_rays": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_render_schedule": [_vp, _vp, _u32, _u32, _u32, _vp],
     "seald_compact_alive": [_vp, _u32, _vp, _vp, _vp, _vp, _vp],
     "seald_seal_map_to_origin": [_vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_seal_map_color": [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp],
-    "seald_march_rays_seal": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_march_rays_seal": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_march_rays_train_seal": [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                    _vp, _vp, _vp, _vp],
+                                    _vp, _vp, _vp, _vp, _vp],
     "seald_freq_encode_forward": [_vp, _u32, _u32, _u32, _u32, _vp, _vp],
     "seald_freq_encode_backward": [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp],
     "seald_sh_encode_forward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp],

@@ -315,6 +315,7 @@ struct WgradJob {
 constexpr int kMaxWgradJobs = 16;
 struct WgradJobs {
     WgradJob j[kMaxWgradJobs];
+    int first_cta[kMaxWgradJobs + 1];  // job i owns CTAs [first_cta[i], first_cta[i+1]): a share proportional to its bytes per row
     int n_jobs;
 };
 
@@ -323,9 +324,13 @@ constexpr int kWgStages = 4;   // cp.async pipeline depth: three chunks in fligh
 
 // Warp -> output tiles: the N/16 m-tiles are spread over the 8 warps (N in {16,32,64,128}); the warps sharing an m-tile
 // split the K/8 n-tiles in even-sized contiguous ranges (pairs of n-tiles share one ldmatrix.x4).
-__global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M, const int* __restrict__ m_dev, const int rows_per_cta) {
+__global__ void __launch_bounds__(256) k_wgrad(const __grid_constant__ WgradJobs jobs, const int M, const int* __restrict__ m_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const WgradJob jb = jobs.j[blockIdx.y];
+    // one wave of CTAs; every job's rows are split evenly over its CTAs, so all CTAs stream about the same number of bytes
+    int job = 0;
+    while (job + 1 < jobs.n_jobs && (int)blockIdx.x >= jobs.first_cta[job + 1]) job++;
+    const WgradJob& jb = jobs.j[job];
+    const int part = (int)blockIdx.x - jobs.first_cta[job], parts = jobs.first_cta[job + 1] - jobs.first_cta[job];
     const int N = jb.N, K = jb.K;
     const int gs = N + kPad, as = K + kPad;  // smem strides
     __half* const s_base = reinterpret_cast<__half*>(smem_raw);
@@ -334,7 +339,8 @@ __global__ void __launch_bounds__(256) k_wgrad(const WgradJobs jobs, const int M
     auto s_at = [&](const int i) { return s_base + i * stage_halves + kWgChunk * gs; };
 
     const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
-    const int m_begin = blockIdx.x * rows_per_cta;
+    const int rows_per_cta = ((m_used + parts - 1) / parts + kWgChunk - 1) / kWgChunk * kWgChunk;
+    const int m_begin = part * rows_per_cta;
     const int m_end = min(m_used, m_begin + rows_per_cta);
     if (m_begin >= m_end) return;
 
@@ -579,11 +585,22 @@ extern "C" int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t
     const size_t smem = (size_t)kWgStages * kWgChunk * (maxNK + 2 * kPad) * sizeof(__half);
     int rc = set_smem(k_wgrad, smem);
     if (rc) return rc;
-    // rows per CTA: ~4 waves over all jobs, at least 512 rows so the atomic flush is amortised
-    uint32_t ctas_x = (4u * SEALD_NUM_SMS + n_jobs - 1) / n_jobs;
-    uint32_t rows = div_up(M, ctas_x);
-    rows = div_up(rows < 512u ? 512u : rows, (uint32_t)kWgChunk) * kWgChunk;
-    dim3 grid(div_up(M, rows), n_jobs);
-    k_wgrad<<<grid, 256, smem, to_stream(stream)>>>(js, (int)M, m_dev, (int)rows);
+    // ONE balanced wave: 2 resident CTAs per SM (98 registers x 256 threads), shared out over the jobs in proportion to the
+    // bytes a job streams per row (N + K halves); but never fewer than ~256 rows per CTA (the 64 KiB atomic flush must amortise)
+    int cost = 0;
+    for (int i = 0; i < n_jobs; i++) cost += js.j[i].N + js.j[i].K;
+    int budget = 2 * SEALD_NUM_SMS;
+    const int max_by_rows = (int)div_up(M, 256u) * n_jobs;
+    if (budget > max_by_rows) budget = max_by_rows;
+    if (budget < n_jobs) budget = n_jobs;
+    int total = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        int parts = (int)((long long)budget * (js.j[i].N + js.j[i].K) / cost);
+        if (parts < 1) parts = 1;
+        js.first_cta[i] = total;
+        total += parts;
+    }
+    js.first_cta[n_jobs] = total;
+    k_wgrad<<<total, 256, smem, to_stream(stream)>>>(js, (int)M, m_dev);
     return launch_status();
 }

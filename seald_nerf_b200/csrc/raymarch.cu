@@ -251,6 +251,90 @@ __device__ __forceinline__ float skip_voxel(const Ray& r, const MarchConst& mc, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Occupied-region guard.  `occ` = world-space AABB of every occupied cell of the bitfield, grown by a guard band of whole
+// cells (seald_occupancy_aabb).  A sample can only be produced where the ray is inside an occupied cell, so
+//   * a ray whose [near, far] segment misses `occ` has no samples at all (exactly what the full walk would find), and
+//   * no sample lies beyond the parameter at which the ray leaves `occ`: the walk may stop there.
+// Both only remove probes that land in empty cells; the sequence of probed chain elements up to the last sample - and with
+// it every count, position and delta - is untouched.  Returns false for a miss; otherwise lowers `far` to the exit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool clip_to_occupied(const Ray& r, const float* __restrict__ occ, const float near, float& far) {
+    float t0 = near, t1 = far;
+    const float o[3] = {r.ox, r.oy, r.oz}, rd[3] = {r.rdx, r.rdy, r.rdz}, d[3] = {r.dx, r.dy, r.dz};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float lo = __ldg(occ + a), hi = __ldg(occ + 3 + a);
+        if (d[a] == 0.0f) {
+            if (o[a] < lo || o[a] > hi) return false;
+        } else {
+            float ta = (lo - o[a]) * rd[a], tb = (hi - o[a]) * rd[a];
+            if (ta > tb) swapf(ta, tb);
+            t0 = fmaxf(t0, ta);
+            t1 = fminf(t1, tb);
+        }
+    }
+    if (!(t0 <= t1)) return false;
+    far = fminf(far, t1);
+    return true;
+}
+
+// per-cascade integer cell ranges of the occupied cells: ranges[c][0..2] = min ix,iy,iz ; [3..5] = max (Morton order grid)
+__global__ void k_occupancy_ranges(const uint8_t* __restrict__ bitfield, const uint32_t C, const uint32_t H, int* __restrict__ ranges) {
+    const uint32_t n_bytes = C * H * H * H / 8;
+    const uint32_t H3 = H * H * H;
+    int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
+    uint32_t cas = 0xffffffffu;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += gridDim.x * blockDim.x) {
+        const uint32_t bits = bitfield[i];
+        if (!bits) continue;
+        const uint32_t c = (i * 8) / H3;
+        if (c != cas) {
+            if (cas != 0xffffffffu) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) { atomicMin(ranges + cas * 6 + a, lo[a]); atomicMax(ranges + cas * 6 + 3 + a, hi[a]); }
+            }
+            cas = c;
+#pragma unroll
+            for (int a = 0; a < 3; a++) { lo[a] = 1 << 30; hi[a] = -1; }
+        }
+        for (uint32_t b = 0; b < 8; b++) {
+            if (!(bits & (1u << b))) continue;
+            const uint32_t m = (i * 8 + b) - c * H3;
+            const int ix = morton3D_dec(m), iy = morton3D_dec(m >> 1), iz = morton3D_dec(m >> 2);
+            lo[0] = min(lo[0], ix); lo[1] = min(lo[1], iy); lo[2] = min(lo[2], iz);
+            hi[0] = max(hi[0], ix); hi[1] = max(hi[1], iy); hi[2] = max(hi[2], iz);
+        }
+    }
+    if (cas != 0xffffffffu) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { atomicMin(ranges + cas * 6 + a, lo[a]); atomicMax(ranges + cas * 6 + 3 + a, hi[a]); }
+    }
+}
+
+__global__ void k_occupancy_init(int* __restrict__ ranges, const uint32_t C) {
+    const uint32_t i = threadIdx.x;
+    if (i < C * 6) ranges[i] = (i % 6 < 3) ? (1 << 30) : -1;
+}
+
+// union over the cascades of the occupied cell boxes, grown by `guard` cells of that cascade, in world coordinates
+// (cell ix of cascade c spans [(ix / H * 2 - 1) * mip_bound, ((ix + 1) / H * 2 - 1) * mip_bound], raymarching.cu:372-376)
+__global__ void k_occupancy_finalize(const int* __restrict__ ranges, const uint32_t C, const uint32_t H, const float bound, const int guard,
+                                     float* __restrict__ aabb6) {
+    if (threadIdx.x != 0) return;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (uint32_t c = 0; c < C; c++) {
+        const float mip_bound = fminf(scalbnf(1.0f, (int)c), bound);
+        for (int a = 0; a < 3; a++) {
+            const int l = ranges[c * 6 + a], h = ranges[c * 6 + 3 + a];
+            if (h < l) continue;
+            lo[a] = fminf(lo[a], ((float)(l - guard) / (float)H * 2.0f - 1.0f) * mip_bound);
+            hi[a] = fmaxf(hi[a], ((float)(h + 1 + guard) / (float)H * 2.0f - 1.0f) * mip_bound);
+        }
+    }
+    for (int a = 0; a < 3; a++) { aabb6[a] = lo[a]; aabb6[3 + a] = hi[a]; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // training march
 // ------------------------------------------------------------------------------------------------
 template <bool SEAL>
@@ -261,7 +345,7 @@ __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float
                                    float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
                                    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter,
                                    const float* __restrict__ noises, const __grid_constant__ seald_seal_mapper mp,
-                                   uint8_t* __restrict__ seal_mask) {
+                                   uint8_t* __restrict__ seal_mask, const float* __restrict__ occ) {
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     const bool active = n < N;
@@ -287,11 +371,13 @@ __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float
 
     float t0 = near;
     t0 += clampf(t0 * dt_gamma, mc.dt_min, mc.dt_max) * noise;
+    bool may_hit = active;
+    if (occ && active) may_hit = clip_to_occupied(r, occ, near, far);
 
     // pass 1: count
     float t = t0;
     uint32_t num_steps = 0;
-    if (active) {
+    if (may_hit) {
         Probe p;
         while (t < far && num_steps < max_steps) {
             if (probe_grid(r, mc, grid, t, p)) {
@@ -378,7 +464,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
     const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ aabb, const float min_near,
     float* __restrict__ nears_out, float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
     float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter, const float* __restrict__ noises,
-    const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask) {
+    const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask, const float* __restrict__ occ) {
     __shared__ float s_t[kMarchWarps][kMaxStepsSmem];
     __shared__ uint32_t s_cnt[kMarchWarps];
     __shared__ uint32_t s_off[kMarchWarps];
@@ -408,8 +494,11 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
     float t0 = near;
     t0 += clampf(t0 * dt_gamma, mc.dt_min, mc.dt_max) * noise;
 
+    bool may_hit = active;
+    if (occ && active) may_hit = clip_to_occupied(r, occ, near, far);
+
     uint32_t count = 0;
-    if (active && t0 < far) {
+    if (may_hit && t0 < far) {
         float tb = t0;         // chain value at the start of the current block of 32 (warp uniform)
         uint32_t lp = 0;       // walker position inside the block
         bool has_pend = false; // an empty-space skip is looking for its landing element
@@ -742,7 +831,7 @@ __global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __res
                              const uint32_t max_steps, const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid,
                              const float* __restrict__ nears, const float* __restrict__ fars, float* xyzs, float* dirs, float* deltas,
                              const float* __restrict__ noises, const int* __restrict__ n_alive_dev, const int* __restrict__ n_step_dev,
-                             const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask) {
+                             const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask, const float* __restrict__ occ) {
     if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
     if (n_step_dev) n_step = (uint32_t)max(*n_step_dev, 0);
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
@@ -765,11 +854,12 @@ __global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __res
     const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
 
     float t = rays_t[index];
-    const float far = fars[index];
+    float far = fars[index];
 
     uint32_t step = 0;
     t += clampf(t * dt_gamma, mc.dt_min, mc.dt_max) * noise;
     float last_t = t;
+    if (occ && !clip_to_occupied(r, occ, t, far)) far = t;  // cannot meet an occupied cell any more: no samples, ray ends
     Probe p;
     while (t < far && step < n_step) {
         if (probe_grid(r, mc, grid, t, p)) {
@@ -1001,7 +1091,7 @@ static int march_train_impl(const float* rays_o, const float* rays_d, const uint
                             uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears, const float* fars,
                             const float* aabb6, float min_near, float* nears_out, float* fars_out, float* xyzs, float* dirs, float* deltas,
                             int32_t* rays, int32_t* counter, const float* noises, const seald_seal_mapper* mapper, uint8_t* mask,
-                            seald_stream_t stream) {
+                            const float* occ, seald_stream_t stream) {
     if (N == 0) return 0;
     if (!rays_o || !rays_d || !bitfield || !xyzs || !dirs || !deltas || !rays || !counter || !noises) return SEALD_E_BADARG;
     if ((nears == nullptr) != (fars == nullptr)) return SEALD_E_BADARG;
@@ -1016,13 +1106,13 @@ static int march_train_impl(const float* rays_o, const float* rays_d, const uint
     if (N <= 65536u && max_steps <= kMaxStepsSmem) {
         auto k = mapper ? k_march_rays_train_warp<true> : k_march_rays_train_warp<false>;
         k<<<div_up(N, kMarchWarps), kMarchWarps * 32, 0, st>>>(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6,
-                                                              min_near, nears_out, fars_out, xyzs, dirs, deltas, rays, counter, noises, mp, mask);
+                                                              min_near, nears_out, fars_out, xyzs, dirs, deltas, rays, counter, noises, mp, mask, occ);
         return launch_status();
     }
     const uint32_t threads = (N >= 4u * SEALD_NUM_SMS * 128u) ? 128u : 32u;
     auto k = mapper ? k_march_rays_train<true> : k_march_rays_train<false>;
     k<<<div_up(N, threads), threads, 0, st>>>(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6, min_near,
-                                             nears_out, fars_out, xyzs, dirs, deltas, rays, counter, noises, mp, mask);
+                                             nears_out, fars_out, xyzs, dirs, deltas, rays, counter, noises, mp, mask, occ);
     return launch_status();
 }
 
@@ -1038,19 +1128,19 @@ extern "C" int seald_march_rays_train(const float* rays_o, const float* rays_d, 
                                       uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                                       const float* fars, const float* aabb6, float min_near, float* nears_out, float* fars_out,
                                       float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter, const float* noises,
-                                      seald_stream_t stream) {
+                                      const float* occ_aabb6, seald_stream_t stream) {
     return march_train_impl(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6, min_near, nears_out, fars_out,
-                            xyzs, dirs, deltas, rays, counter, noises, nullptr, nullptr, stream);
+                            xyzs, dirs, deltas, rays, counter, noises, nullptr, nullptr, occ_aabb6, stream);
 }
 
 extern "C" int seald_march_rays_train_seal(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound, float dt_gamma,
                                            uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                                            const float* fars, const float* aabb6, float min_near, float* nears_out, float* fars_out,
                                            float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter, const float* noises,
-                                           const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream) {
+                                           const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6, seald_stream_t stream) {
     if (int rc = check_fusable_mapper(mapper, mask)) return rc;
     return march_train_impl(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6, min_near, nears_out, fars_out,
-                            xyzs, dirs, deltas, rays, counter, noises, mapper, mask, stream);
+                            xyzs, dirs, deltas, rays, counter, noises, mapper, mask, occ_aabb6, stream);
 }
 
 extern "C" int seald_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M,
@@ -1086,33 +1176,34 @@ static int march_impl(uint32_t n_alive, uint32_t n_step, const int32_t* rays_ali
                       const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* bitfield,
                       const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
                       const int32_t* n_alive_dev, const int32_t* n_step_dev, const seald_seal_mapper* mapper, uint8_t* mask,
-                      seald_stream_t stream) {
+                      const float* occ, seald_stream_t stream) {
     if (n_alive == 0 || (n_step == 0 && !n_step_dev)) return 0;
     if (!rays_alive || !rays_t || !rays_o || !rays_d || !bitfield || !fars || !xyzs || !dirs || !deltas) return SEALD_E_BADARG;
     static const seald_seal_mapper no_mapper = {};
     auto k = mapper ? k_march_rays<true> : k_march_rays<false>;
     k<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
                                                            bitfield, nears, fars, xyzs, dirs, deltas, noises, n_alive_dev, n_step_dev,
-                                                           mapper ? *mapper : no_mapper, mask);
+                                                           mapper ? *mapper : no_mapper, mask, occ);
     return launch_status();
 }
 
 extern "C" int seald_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                                 const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                                 const uint8_t* bitfield, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
-                                const float* noises, const int32_t* n_alive_dev, const int32_t* n_step_dev, seald_stream_t stream) {
+                                const float* noises, const int32_t* n_alive_dev, const int32_t* n_step_dev, const float* occ_aabb6,
+                                seald_stream_t stream) {
     return march_impl(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, bitfield, nears, fars, xyzs, dirs,
-                      deltas, noises, n_alive_dev, n_step_dev, nullptr, nullptr, stream);
+                      deltas, noises, n_alive_dev, n_step_dev, nullptr, nullptr, occ_aabb6, stream);
 }
 
 extern "C" int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                                      const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                                      const uint8_t* bitfield, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                                      const float* noises, const int32_t* n_alive_dev, const int32_t* n_step_dev,
-                                     const seald_seal_mapper* mapper, uint8_t* mask, seald_stream_t stream) {
+                                     const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6, seald_stream_t stream) {
     if (int rc = check_fusable_mapper(mapper, mask)) return rc;
     return march_impl(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, bitfield, nears, fars, xyzs, dirs,
-                      deltas, noises, n_alive_dev, n_step_dev, mapper, mask, stream);
+                      deltas, noises, n_alive_dev, n_step_dev, mapper, mask, occ_aabb6, stream);
 }
 
 extern "C" int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t, const float* sigmas,
@@ -1122,6 +1213,18 @@ extern "C" int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_t
     if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return SEALD_E_BADARG;
     k_composite_rays<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
                                                                            weights_sum, depth, image, n_alive_dev, n_step_dev);
+    return launch_status();
+}
+
+extern "C" int seald_occupancy_aabb(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, int32_t guard_cells, int32_t* scratch,
+                                    float* aabb6, seald_stream_t stream) {
+    if (!bitfield || !scratch || !aabb6 || C == 0 || C > 16 || H == 0 || guard_cells < 1) return SEALD_E_BADARG;
+    cudaStream_t st = to_stream(stream);
+    k_occupancy_init<<<1, 128, 0, st>>>(scratch, C);
+    const uint32_t n_bytes = C * H * H * H / 8;
+    const uint32_t blocks = min(div_up(n_bytes, 256u), 4u * SEALD_NUM_SMS);
+    k_occupancy_ranges<<<blocks, 256, 0, st>>>(bitfield, C, H, scratch);
+    k_occupancy_finalize<<<1, 32, 0, st>>>(scratch, C, H, bound, guard_cells, aabb6);
     return launch_status();
 }
 

@@ -116,10 +116,13 @@ def march_composite(device, n_rays=640000, reps=10, hbm_gbs=6537.6):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     st = _lib.stream
 
+    occ = rm.occupancy_aabb(bits, 1, H, 1.0, 2)
+    use_occ = False
+
     def march():
         counter.zero_()
         _lib.call("seald_march_rays_train", ptr(ro), ptr(rd), ptr(bits), 1.0, 0.0, 1024, N, 1, H, M, None, None, ptr(aabb), 0.2, ptr(nears),
-                  ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), st())
+                  ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), ptr(occ) if use_occ else None, st())
 
     sig = torch.rand(M, device=device) * 30
     rgb = torch.rand(M, 3, device=device)
@@ -146,6 +149,11 @@ def march_composite(device, n_rays=640000, reps=10, hbm_gbs=6537.6):
         _lib.call("seald_packbits", ptr(gall), 64 * H ** 3 // 8, 10.0, ptr(ball), st())
 
     out = {"rays": N, "samples": m_live, "l2": "256 MiB flush between timed launches"}
+    ms0 = _time(march, reps=reps, flush=flush)
+    out["march_train_no_occupancy_guard"] = {"ms": round(ms0, 4)}
+    use_occ = True
+    march()
+    assert int(counter[0]) == m_live, "the occupied-region guard must not change the sample count"
     for name, fn, nbytes in (("march_train", march, 48.0 * N + 32.0 * m_live + 262144.0),
                              ("composite_fwd", comp_fwd, 24.0 * m_live + 32.0 * N),
                              ("composite_bwd", comp_bwd, 40.0 * m_live + 48.0 * N),

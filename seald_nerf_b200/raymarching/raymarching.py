@@ -120,7 +120,7 @@ class _march_rays_train(Function):
 
         _lib.call("seald_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(density_bitfield), float(bound), float(dt_gamma),
                   int(max_steps), N, int(C), int(H), M, ptr(nears.contiguous()), ptr(fars.contiguous()), None, 0.0, None, None,
-                  ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(step_counter), ptr(noises), _lib.stream())
+                  ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(step_counter), ptr(noises), None, _lib.stream())
 
         # first epochs only: trim to the used length (host sync, as in the reference raymarching.py:223-231)
         if force_all_rays or mean_count <= 0:
@@ -189,7 +189,7 @@ class _march_rays(Function):
         noises = torch.rand(n_alive, dtype=dt, device=dev) if perturb else torch.zeros(n_alive, dtype=dt, device=dev)
         _lib.call("seald_march_rays", int(n_alive), int(n_step), ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), float(bound),
                   float(dt_gamma), int(max_steps), int(C), int(H), ptr(density_bitfield.contiguous()), ptr(near), ptr(far), ptr(xyzs),
-                  ptr(dirs), ptr(deltas), ptr(noises), None, None, _lib.stream())
+                  ptr(dirs), ptr(deltas), ptr(noises), None, None, None, _lib.stream())
         return xyzs, dirs, deltas
 
 
@@ -227,7 +227,7 @@ def march_rays_seal(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, 
     noises = torch.rand(n_alive, dtype=dt, device=dev) if perturb else torch.zeros(n_alive, dtype=dt, device=dev)
     _lib.call("seald_march_rays_seal", int(n_alive), int(n_step), ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), float(bound),
               float(dt_gamma), int(max_steps), int(C), int(H), ptr(density_bitfield.contiguous()), ptr(near), ptr(far), ptr(xyzs),
-              ptr(dirs), ptr(deltas), ptr(noises), None, None, C_.byref(mapper.descriptor(dev)), ptr(mask), _lib.stream())
+              ptr(dirs), ptr(deltas), ptr(noises), None, None, C_.byref(mapper.descriptor(dev)), ptr(mask), None, _lib.stream())
     return xyzs, dirs, deltas, mask
 
 
@@ -256,13 +256,25 @@ def march_rays_train_seal(rays_o, rays_d, bound, density_bitfield, C, H, nears, 
     noises = torch.rand(N, dtype=dt, device=dev) if perturb else torch.zeros(N, dtype=dt, device=dev)
     _lib.call("seald_march_rays_train_seal", ptr(rays_o), ptr(rays_d), ptr(density_bitfield), float(bound), float(dt_gamma), int(max_steps), N,
               int(C), int(H), M, ptr(nears.contiguous()), ptr(fars.contiguous()), None, 0.0, None, None, ptr(xyzs), ptr(dirs), ptr(deltas),
-              ptr(rays), ptr(step_counter), ptr(noises), C_.byref(mapper.descriptor(dev)), ptr(mask), _lib.stream())
+              ptr(rays), ptr(step_counter), ptr(noises), C_.byref(mapper.descriptor(dev)), ptr(mask), None, _lib.stream())
     if force_all_rays or mean_count <= 0:
         m = step_counter[0].item()
         if align > 0:
             m += align - m % align
         xyzs, dirs, deltas, mask = xyzs[:m], dirs[:m], deltas[:m], mask[:m]
     return xyzs, dirs, deltas, rays, mask
+
+
+def occupancy_aabb(density_bitfield, C, H, bound, guard_cells=2, out=None):
+    """World-space box [6] of the occupied cells of one bitfield frame, grown by `guard_cells` cells (seald_occupancy_aabb):
+    the optional `occ_aabb6` guard of the march kernels (rays that cannot meet an occupied cell skip the walk)."""
+    dev = density_bitfield.device
+    if out is None:
+        out = torch.empty(6, dtype=torch.float32, device=dev)
+    scratch = torch.empty(6 * int(C), dtype=torch.int32, device=dev)
+    _lib.call("seald_occupancy_aabb", ptr(density_bitfield.contiguous()), int(C), int(H), float(bound), int(guard_cells), ptr(scratch), ptr(out),
+              _lib.stream())
+    return out
 
 
 def compact_alive(rays_alive, n_alive=None, n_alive_dev=None):

@@ -44,6 +44,8 @@ class FusedRenderer:
         self.rays_o = torch.zeros(N, 3, **f32)
         self.rays_d = torch.zeros(N, 3, **f32)
         self.bitfield = torch.zeros(model.density_bitfield.shape[1], dtype=torch.uint8, device=dev)
+        self.occ = torch.zeros(6, **f32)  # box of the occupied cells of the current frame (+ guard band): march early-out
+        self.occ_scratch = torch.zeros(6 * model.cascade, **i32)
         self.nears = torch.empty(N, **f32)
         self.fars = torch.empty(N, **f32)
         self.rays_t = torch.empty(N, **f32)
@@ -94,11 +96,12 @@ class FusedRenderer:
             _lib.call("seald_march_rays_seal", n_bound, 1, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
                       opts["dt_gamma"], opts["max_steps"], int(m.cascade), int(m.grid_size), ptr(self.bitfield), ptr(self.nears),
                       ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), ptr(n_alive_dev), ptr(n_step_dev),
-                      C.byref(desc), ptr(self.mask), st)
+                      C.byref(desc), ptr(self.mask), ptr(self.occ), st)
         else:
             _lib.call("seald_march_rays", n_bound, 1, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
                       opts["dt_gamma"], opts["max_steps"], int(m.cascade), int(m.grid_size), ptr(self.bitfield), ptr(self.nears),
-                      ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), ptr(n_alive_dev), ptr(n_step_dev), st)
+                      ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), ptr(n_alive_dev), ptr(n_step_dev),
+                      ptr(self.occ), st)
             if mapper is not None:  # anchor mapper: batch-wide early exit, separate op
                 _lib.call("seald_seal_map_to_origin", C.byref(desc), ptr(self.xyzs), ptr(self.dirs), self.cap, ptr(m_dev), ptr(self.xyzs),
                           ptr(self.dirs), ptr(self.mask), ptr(mapper._dev_cache["scratch_i"]), st)
@@ -168,6 +171,8 @@ class FusedRenderer:
             self.time.fill_(float(time))
             t_idx = min(max(int(float(time) * m.time_size), 0), m.time_size - 1)
         self.bitfield.copy_(m.density_bitfield[t_idx], non_blocking=True)
+        _lib.call("seald_occupancy_aabb", ptr(self.bitfield), int(m.cascade), int(m.grid_size), float(m.bound), 2, ptr(self.occ_scratch),
+                  ptr(self.occ), st)
         aabb = m.aabb_train if m.training else m.aabb_infer
         nears, fars = self.nears[:N], self.fars[:N]
         _lib.call("seald_near_far_from_aabb", ptr(self.rays_o), ptr(self.rays_d), ptr(aabb), N, float(m.min_near), ptr(nears), ptr(fars), st)

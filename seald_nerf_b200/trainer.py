@@ -88,6 +88,10 @@ class FusedTrainer:
         self.nears = torch.empty(N, **f32)
         self.fars = torch.empty(N, **f32)
         self.bitfield_frame = torch.zeros(model.density_bitfield.shape[1], dtype=torch.uint8, device=dev)
+        # box of the occupied cells per time frame (+ guard band): rays that cannot meet an occupied cell skip the walk
+        self.occ_all = torch.zeros(model.density_bitfield.shape[0], 6, **f32)
+        self.occ_frame = torch.zeros(1, 6, **f32)
+        self.refresh_occupancy()
         self.xyzs = torch.zeros(M, 3, **f32)
         self.dirs = torch.zeros(M, 3, **f32)
         self.deltas = torch.zeros(M, 2, **f32)
@@ -119,6 +123,13 @@ class FusedTrainer:
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------------------------
+    def refresh_occupancy(self):
+        """Recompute the per-frame occupied-cell boxes; call after the model's density_bitfield changed (update_extra_state)."""
+        from . import raymarching
+        m = self.model
+        for t in range(m.density_bitfield.shape[0]):
+            raymarching.occupancy_aabb(m.density_bitfield[t], m.cascade, m.grid_size, m.bound, 2, out=self.occ_all[t])
+
     def set_inputs(self, rays_o, rays_d, time, gt_rgb, bg_color=None):
         """Device-resident inputs of the next step (copied into the static buffers the graph reads)."""
         self.rays_o.copy_(rays_o.reshape(-1, 3), non_blocking=True)
@@ -165,6 +176,7 @@ class FusedTrainer:
             # occupancy frame of this time stamp (dnerf/renderer.py:285), selected on the device
             t_idx = torch.floor(self.time * m.time_size).clamp(min=0, max=m.time_size - 1).long()
             torch.index_select(m.density_bitfield, 0, t_idx, out=self.bitfield_frame.view(1, -1))
+            torch.index_select(self.occ_all, 0, t_idx, out=self.occ_frame)
             self.counter.zero_()
             if self.perturb:
                 self.noises.uniform_(0, 1)
@@ -173,7 +185,7 @@ class FusedTrainer:
             _lib.call("seald_march_rays_train", ptr(self.rays_o), ptr(self.rays_d), ptr(self.bitfield_frame), float(m.bound), self.dt_gamma,
                       self.max_steps, N, int(m.cascade), int(m.grid_size), M, None, None, ptr(m.aabb_train), float(m.min_near),
                       ptr(self.nears), ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(self.rays), ptr(self.counter),
-                      ptr(self.noises), _lib.stream())
+                      ptr(self.noises), ptr(self.occ_frame), _lib.stream())
 
         def deform_fwd():
             F.deform_forward(cfg, hw, self.xyzs, self.time, M, m_dev, 1, ws.deform, ws.x01, ws.in_buf, ws.fwd_d)
@@ -222,7 +234,7 @@ class FusedTrainer:
             import ctypes as C
             _lib.call("seald_mlp_wgrad", C.cast(self.jobs, C.c_void_p), self.n_jobs, M, ptr(m_dev), _lib.stream())
 
-        stages = [("select_frame", select_frame, 3), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
+        stages = [("select_frame", select_frame, 4), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
                   ("heads_fwd", heads_fwd, 1), ("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3),
                   ("heads_bwd", heads_bwd, 1), ("grid_bwd", grid_bwd, 3 if self.train_deform else 2)]
         if self.train_deform:

@@ -11,7 +11,7 @@ def _declared():
     for fn in os.listdir(os.path.join(ROOT, "include")):
         if fn.endswith(".h"):
             txt = open(os.path.join(ROOT, "include", fn)).read()
-            names += re.findall(r"^\s*(?:int|const char\*)\s+(seald_\w+)\s*\(", txt, flags=re.M)
+            names += re.findall(r"^\s*(?:int|uint64_t|const char\*)\s+(seald_\w+)\s*\(", txt, flags=re.M)
     return sorted(set(names))
 
 

@@ -101,6 +101,7 @@ def _per_ray(rays, xyzs, deltas):
                                                            (2, 2.0, 1 / 128, False), (2, 2.0, 0.0, True)])
 def test_march_train_bit_exact(cuda_dev, cascade, bound, dt_gamma, perturb):
     from seald_nerf_b200 import _lib
+    from seald_nerf_b200 import raymarching as rm
     from seald_nerf_b200._lib import ptr
     from oracle import raymarch as orc
     N, H, max_steps = 4096, 128, 1024
@@ -119,7 +120,7 @@ def test_march_train_bit_exact(cuda_dev, cascade, bound, dt_gamma, perturb):
     rays = torch.zeros(N, 3, dtype=torch.int32, device=d); counter = torch.zeros(2, dtype=torch.int32, device=d)
     tro, trd, tb, tn, tf, tz = _t(ro, d), _t(rd, d), _t(bits, d), _t(nears, d), _t(fars, d), _t(noises, d)
     _lib.call("seald_march_rays_train", ptr(tro), ptr(trd), ptr(tb), bound, dt_gamma, max_steps, N, cascade, H, M, ptr(tn), ptr(tf),
-              None, 0.0, None, None, ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(tz), _lib.stream())
+              None, 0.0, None, None, ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(tz), None, _lib.stream())
     torch.cuda.synchronize()
     rays_c = rays.cpu().numpy()
     assert counter.cpu().tolist() == [total, N]
@@ -148,7 +149,7 @@ def test_march_train_bit_exact(cuda_dev, cascade, bound, dt_gamma, perturb):
     taabb = _t(aabb, d)
     _lib.call("seald_march_rays_train", ptr(tro), ptr(trd), ptr(tb), bound, dt_gamma, max_steps, N, cascade, H, M, None, None,
               ptr(taabb), 0.2, ptr(n_out), ptr(f_out), ptr(xyzs2), ptr(dirs2), ptr(deltas2), ptr(rays2), ptr(counter2), ptr(tz),
-              _lib.stream())
+              ptr(rm.occupancy_aabb(tb, cascade, H, bound)), _lib.stream())  # fused slab test AND the occupied-region guard
     assert np.array_equal(n_out.cpu().numpy(), nears) and np.array_equal(f_out.cpu().numpy(), fars)
     assert torch.equal(rays2[:, 2], rays[:, 2])
     mine2 = _per_ray(rays2.cpu().numpy(), xyzs2.cpu().numpy(), deltas2.cpu().numpy())
@@ -309,3 +310,65 @@ def test_inference_loop_matches_oracle(cuda_dev, T_thresh):
     np.testing.assert_allclose(image.cpu().numpy(), image_o, rtol=RTOL, atol=2e-6)
     np.testing.assert_allclose(depth.cpu().numpy(), depth_o, rtol=RTOL, atol=2e-5)
     assert float(ws.max()) > 0.9
+
+
+@pytest.mark.parametrize("n_rays,dt_gamma,cascade", [(3000, 0.0, 1), (3000, 1.0 / 128, 2), (70000, 0.0, 1)])
+def test_occupied_region_guard_changes_nothing(cuda_dev, n_rays, dt_gamma, cascade):
+    """occ_aabb6 (seald_occupancy_aabb) lets rays skip the empty volume; counts, positions and deltas must be bit-identical
+    with and without it - for the warp-per-ray kernel, the thread-per-ray kernel (> 65536 rays) and the inference march."""
+    from seald_nerf_b200 import _lib
+    from seald_nerf_b200 import raymarching as rm
+    from seald_nerf_b200._lib import ptr
+    d = cuda_dev
+    bound = float(2 ** (cascade - 1))
+    H = 128
+    bits, _ = scene_bitfield(H=H, cascade=cascade)
+    ro, rd = camera_rays(n_rays, seed=9, radius=3.2 * bound)
+    tro, trd, tb = _t(ro, d), _t(rd, d), _t(bits, d)
+    aabb = torch.tensor([-bound] * 3 + [bound] * 3, dtype=torch.float32, device=d)
+    nears, fars = rm.near_far_from_aabb(tro, trd, aabb, 0.2)
+    occ = rm.occupancy_aabb(tb, cascade, H, bound, 2)
+    o = occ.cpu().numpy()
+    assert np.all(o[:3] < o[3:]) and np.all(o[:3] >= -bound - 0.1) and np.all(o[3:] <= bound + 0.1)
+    assert (o[3:] - o[:3]).max() < 2 * bound * 0.95, "the figure does not fill the volume: the guard must be a real restriction"
+    noises = torch.rand(n_rays, device=d)
+    res = []
+    for use in (None, occ):
+        M = n_rays * 64
+        xyzs = torch.zeros(M, 3, device=d); dirs = torch.zeros(M, 3, device=d); deltas = torch.zeros(M, 2, device=d)
+        rays = torch.zeros(n_rays, 3, dtype=torch.int32, device=d); counter = torch.zeros(2, dtype=torch.int32, device=d)
+        _lib.call("seald_march_rays_train", ptr(tro), ptr(trd), ptr(tb), bound, dt_gamma, 1024, n_rays, cascade, H, M, ptr(nears), ptr(fars),
+                  None, 0.0, None, None, ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), ptr(use), _lib.stream())
+        torch.cuda.synchronize()
+        r = rays.cpu().numpy()
+        x, de = xyzs.cpu().numpy(), deltas.cpu().numpy()
+        # CTAs race for output ranges: compare per ray
+        res.append((counter.cpu().tolist(), r[:, 2].copy(), [x[o_:o_ + k].copy() for _, o_, k in r[::13]], [de[o_:o_ + k].copy() for _, o_, k in r[::13]]))
+    assert res[0][0] == res[1][0] and res[0][0][0] > 100
+    assert np.array_equal(res[0][1], res[1][1])
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)
+    for a, b in zip(res[0][3], res[1][3]):
+        assert np.array_equal(a, b)
+
+    # inference march, three rounds of 8 steps with compositing in between (rays_t advances)
+    outs = []
+    for use in (None, occ):
+        alive = torch.arange(n_rays, dtype=torch.int32, device=d)
+        rays_t = nears.clone()
+        ws = torch.zeros(n_rays, device=d); depth = torch.zeros(n_rays, device=d); image = torch.zeros(n_rays, 3, device=d)
+        log = []
+        for _ in range(3):
+            n_alive = alive.shape[0]
+            M = n_alive * 8 + 128
+            xyzs = torch.empty(M, 3, device=d).fill_(7); dirs = torch.empty(M, 3, device=d).fill_(7); deltas = torch.empty(M, 2, device=d).fill_(7)
+            _lib.call("seald_march_rays", n_alive, 8, ptr(alive), ptr(rays_t), ptr(tro), ptr(trd), bound, dt_gamma, 1024, cascade, H, ptr(tb),
+                      ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), None, None, None, ptr(use), _lib.stream())
+            log.append((xyzs[:n_alive * 8].clone(), deltas[:n_alive * 8].clone()))
+            sig = torch.full((M,), 3.0, device=d); rgb = torch.full((M, 3), 0.5, device=d)
+            rm.composite_rays(n_alive, 8, alive, rays_t, sig, rgb, deltas, ws, depth, image, 1e-4)
+            alive = alive[alive >= 0]
+        outs.append((log, alive.clone(), rays_t.clone(), image.clone()))
+    for (xa, da), (xb, db) in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(xa, xb) and torch.equal(da, db)
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
