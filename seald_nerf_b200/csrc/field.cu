@@ -359,17 +359,34 @@ __global__ void __launch_bounds__(256) k_wgrad(const __grid_constant__ WgradJobs
 #pragma unroll
         for (int h = 0; h < 2; h++) acc[i][h][0] = acc[i][h][1] = acc[i][h][2] = acc[i][h][3] = 0.0f;
 
+    // Staging: every thread owns up to 4 fixed (row-in-chunk, 16-byte column) slots of a chunk; source pointers and
+    // shared-memory offsets are computed once, a stage is then 4 predicated cp.async per thread (the integer divisions of a
+    // per-copy index decode made the loop issue bound).
     const int gchunks = N / 8, achunks = K / 8, chunks = gchunks + achunks;
-    auto stage = [&](int buf, int m0) {
-        for (int i = threadIdx.x; i < kWgChunk * chunks; i += 256) {
-            const int r = i / chunks, c = i - r * chunks;
-            const int row = m0 + r;
-            const bool is_g = c < gchunks;
-            const int cc = is_g ? c : c - gchunks;
-            __half* dst = is_g ? (s_gt(buf) + r * gs + cc * 8) : (s_at(buf) + r * as + cc * 8);
-            if (row < m_end) cp_async16(dst, is_g ? (jb.G + (size_t)row * jb.ldg + cc * 8) : (jb.A + (size_t)row * jb.lda + cc * 8));
-            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    constexpr int kSlots = 4;  // kWgChunk * chunks / 256 <= 32 * 32 / 256
+    const __half* src[kSlots];
+    int dst[kSlots], srow[kSlots], sld[kSlots];
+#pragma unroll
+    for (int k = 0; k < kSlots; k++) {
+        const int i = threadIdx.x + 256 * k;
+        const int r = i / chunks, c = i - r * chunks;
+        const bool is_g = c < gchunks;
+        const int cc = is_g ? c : c - gchunks;
+        srow[k] = (i < kWgChunk * chunks) ? r : (1 << 28);  // inactive slots never pass the row test
+        sld[k] = kWgChunk * (is_g ? jb.ldg : jb.lda);
+        src[k] = (is_g ? jb.G + (size_t)(m_begin + r) * jb.ldg : jb.A + (size_t)(m_begin + r) * jb.lda) + cc * 8;
+        dst[k] = is_g ? (r * gs + cc * 8) : (kWgChunk * gs + r * as + cc * 8);
+    }
+    int m_next = m_begin;  // first row of the next chunk to stage (stages are issued in order)
+    auto stage = [&](int buf, int) {
+        __half* sb = s_base + buf * stage_halves;
+#pragma unroll
+        for (int k = 0; k < kSlots; k++) {
+            if (m_next + srow[k] < m_end) cp_async16(sb + dst[k], src[k]);
+            else if (srow[k] < kWgChunk) *reinterpret_cast<uint4*>(sb + dst[k]) = make_uint4(0, 0, 0, 0);
+            src[k] += sld[k];
         }
+        m_next += kWgChunk;
         cp_async_commit();
     };
 
