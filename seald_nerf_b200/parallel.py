@@ -52,13 +52,28 @@ def shard_capacity(n_rays, world_size, tile=256):
     return ((n_tiles + world_size - 1) // world_size) * tile
 
 
+_UNSHARD_CACHE = {}
+
+
+def unshard_index(n_rays, world_size, tile, device):
+    """Row of the padded, rank-major gather buffer [world * cap] that holds ray i (cached per shape and device)."""
+    key = (n_rays, world_size, tile, str(device))
+    idx = _UNSHARD_CACHE.get(key)
+    if idx is None:
+        cap = shard_capacity(n_rays, world_size, tile)
+        idx = torch.empty(n_rays, dtype=torch.int64)
+        for r in range(world_size):
+            mine = shard_tiles(n_rays, world_size, r, tile)
+            idx[mine] = r * cap + torch.arange(mine.shape[0])
+        idx = idx.to(device)
+        _UNSHARD_CACHE[key] = idx
+    return idx
+
+
 def unshard(gathered, n_rays, world_size, tile=256):
-    """gathered [world, cap, K] (rank-major, padded) -> [n_rays, K] in ray order."""
-    out = gathered.new_empty(n_rays, gathered.shape[-1])
-    for r in range(world_size):
-        idx = shard_tiles(n_rays, world_size, r, tile).to(gathered.device)
-        out[idx] = gathered[r, :idx.shape[0]]
-    return out
+    """gathered [world, cap, K] (rank-major, padded) -> [n_rays, K] in ray order (one gather)."""
+    flat = gathered.reshape(-1, gathered.shape[-1])
+    return flat.index_select(0, unshard_index(n_rays, world_size, tile, gathered.device))
 
 
 def gather_frame(local, n_rays, rank, world_size, group=None, tile=256):

@@ -27,16 +27,24 @@ from ._lib import ptr
 
 
 class FusedRenderer:
-    def __init__(self, model, max_rays, device=None, use_graph=True, max_n_step=8):
+    def __init__(self, model, max_rays, device=None, use_graph=True, max_n_step=None, min_samples=1 << 16):
         self.model = model
         self.device = device or model.encoder.embeddings.device
         if self.device.type != "cuda":
             raise RuntimeError("FusedRenderer needs a CUDA device (no CPU fallback)")
         self.cfg = model._field_cfg
         self.N = int(max_rays)
-        self.cap = self.N + 128  # n_alive * n_step <= N, rounded up to the MLP tile
+        # Sample slots per round.  The reference marches n_step = clamp(N // n_alive, 1, 8) samples per live ray, i.e. at most
+        # N slots per round (dnerf/renderer.py:360); that is kept for full frames.  Small batches (training-size teacher
+        # renders) would need ~15 nearly empty rounds that way, so the slot budget has a floor of `min_samples` and n_step may
+        # grow to 32: the per-ray compositing sequence - and therefore the image - does not depend on how a ray's samples are
+        # cut into rounds.
+        self.slots = max(self.N, int(min_samples))
+        self.cap = self.slots + 128  # rounded up to the MLP tile
         self.use_graph = bool(use_graph)
-        self.max_n_step = int(max_n_step)  # 8 = the reference's schedule (dnerf/renderer.py:360)
+        if max_n_step is None:
+            max_n_step = 8 if self.slots == self.N else 32
+        self.max_n_step = int(max_n_step)
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
@@ -114,7 +122,8 @@ class FusedRenderer:
         _lib.call("seald_composite_rays", n_bound, 1, opts["T_thresh"], ptr(alive), ptr(self.rays_t), ptr(self.ws.sigma), ptr(self.ws.rgb),
                   ptr(self.deltas), ptr(self.weights_sum), ptr(self.depth), ptr(self.image), ptr(n_alive_dev), ptr(n_step_dev), st)
         _lib.call("seald_compact_alive", ptr(alive), n_bound, ptr(n_alive_dev), ptr(nxt), ptr(self.n_new), ptr(self.scratch), st)
-        _lib.call("seald_render_schedule", ptr(self.state), ptr(self.n_new), N, opts["max_steps"], self.max_n_step, st)
+        _lib.call("seald_render_schedule", ptr(self.state), ptr(self.n_new), max(N, self.slots), opts["max_steps"],
+                  self.max_n_step, st)
         return launches + 9
 
     def _double_round_graph(self, N, opts, mapper, desc):
@@ -182,8 +191,10 @@ class FusedRenderer:
         torch.arange(N, dtype=torch.int32, device=self.device, out=self.alive[0][:N])
         if perturb:
             self.noises[:N].uniform_(0, 1)
+        budget = max(N, self.slots)
+        n_step0 = max(min(budget // N, self.max_n_step), 1)
         self.h_state.zero_()
-        self.h_state[0] = N; self.h_state[1] = 1; self.h_state[2] = N
+        self.h_state[0] = N; self.h_state[1] = n_step0; self.h_state[2] = N * n_step0
         self.state.copy_(self.h_state, non_blocking=True)
         desc = mapper.descriptor(self.device) if mapper is not None else None
 
@@ -224,8 +235,12 @@ class FusedRenderer:
         N = rays_o.shape[0]
         if world_size == 1:
             return self.render(rays_o, rays_d, time, **kwargs)
-        idx = parallel.shard_tiles(N, world_size, rank, tile).to(rays_o.device)
-        out = self.render(rays_o[idx], rays_d[idx], time, **kwargs)
+        key = (N, world_size, rank, tile)
+        if getattr(self, "_shard_key", None) != key:  # cached: building the index on the host costs more than the render
+            self._shard_idx = parallel.shard_tiles(N, world_size, rank, tile).to(rays_o.device)
+            self._shard_key = key
+        idx = self._shard_idx
+        out = self.render(rays_o.index_select(0, idx), rays_d.index_select(0, idx), time, **kwargs)
         local = torch.cat([out["image"].view(-1, 3), out["depth"].view(-1, 1), out["weights_sum"].view(-1, 1)], dim=1)
         full = parallel.gather_frame(local, N, rank, world_size, group, tile)
         return {"image": full[:, :3].contiguous(), "depth": full[:, 3].contiguous(), "weights_sum": full[:, 4].contiguous()}
