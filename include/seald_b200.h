@@ -269,6 +269,9 @@ typedef struct {
     int n_real, k_real; /* rows / columns of dW actually written */
 } seald_wgrad_job;
 int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream);
+/* Same contract on the Blackwell tensor cores (csrc/wgrad_umma.cu): tcgen05.mma over MN-major operand tiles staged with
+ * cp.async, fp32 accumulators in tensor memory, one vector-atomic flush per CTA. */
+int seald_mlp_wgrad_umma(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream);
 
 /* FFMLP-compatible fused MLP.  Replace ffmlp_forward / ffmlp_inference / ffmlp_backward (ffmlp/src/ffmlp.h:8-11).
  * inputs [B,input_dim] f16 (input_dim % 16 == 0, <= 128), weights: flat f16 buffer (ffmlp.cu:632 layout),

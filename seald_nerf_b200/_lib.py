@@ -50,6 +50,7 @@ _SIGS = {
     "seald_field_sigma_forward": [_vp, _vp, _i32, _u32, _f32, _vp, _vp, _vp],
     "seald_field_heads_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_mlp_wgrad": [_vp, _i32, _u32, _vp, _vp],
+    "seald_mlp_wgrad_umma": [_vp, _i32, _u32, _vp, _vp],
     "seald_ffmlp_forward": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "seald_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp],
     "seald_mse_loss_bg": [_vp, _vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -108,6 +108,7 @@ class FieldWorkspace:
             self.grad_x01 = torch.empty(M, 3, **f32)
 
 
+WGRAD_IMPL = os.environ.get("SEALD_WGRAD_IMPL", "umma")  # "umma": tcgen05 kernel (csrc/wgrad_umma.cu); "mma": mma.sync kernel (field.cu)
 DEFORM_IMPL = os.environ.get("SEALD_DEFORM_IMPL", "umma")  # "umma": tcgen05 kernel (default); "mma": the mma.sync kernel of field.cu
 
 
@@ -119,6 +120,11 @@ def deform_forward(cfg, hw, xyzs, time_dev, M, m_dev, t0_mode, deform, x01, in_b
     else:
         _lib.call("seald_field_deform_forward", ptr(xyzs), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, int(t0_mode),
                   ptr(deform), ptr(x01), ptr(in_buf), ptr(fwd_buf), st)
+
+
+def mlp_wgrad(jobs, n_jobs, M, m_dev):
+    name = "seald_mlp_wgrad_umma" if WGRAD_IMPL == "umma" else "seald_mlp_wgrad"
+    _lib.call(name, C.cast(jobs, C.c_void_p), n_jobs, M, ptr(m_dev), _lib.stream())
 
 
 def field_forward(cfg, hw, ws, xyzs, dirs, time_dev, table16, offsets, m_dev=None, t0_mode=1, M=None):
@@ -186,7 +192,7 @@ def field_backward(cfg, hw, ws, grad_sigma, grad_rgb, time_is_zero, table16, off
     if want_dx:
         _lib.call("seald_field_deform_backward", ptr(ws.grad_x01), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, ptr(ws.fwd_d),
                   ptr(ws.bwd_d), ptr(ws.gout_d), st)
-    _lib.call("seald_mlp_wgrad", C.cast(jobs, C.c_void_p), n_jobs, M, ptr(m_dev), st)
+    mlp_wgrad(jobs, n_jobs, M, m_dev)
 
 
 def field_density(cfg, hw, ws, xyzs, time_dev, table16, offsets, M=None):

@@ -231,8 +231,7 @@ class FusedTrainer:
                       ptr(ws.fwd_d), ptr(ws.bwd_d), ptr(ws.gout_d), _lib.stream())
 
         def wgrad():
-            import ctypes as C
-            _lib.call("seald_mlp_wgrad", C.cast(self.jobs, C.c_void_p), self.n_jobs, M, ptr(m_dev), _lib.stream())
+            F.mlp_wgrad(self.jobs, self.n_jobs, M, m_dev)
 
         stages = [("select_frame", select_frame, 4), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
                   ("heads_fwd", heads_fwd, 1), ("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3),

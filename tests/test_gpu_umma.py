@@ -79,3 +79,40 @@ def test_umma_deform_inference_and_t0_modes(cuda_dev):
     assert torch.equal(x1, x2)
     d2m, _, _, _ = _run(F, cfg, hw, xyz, 0.0, "mma", False, t0_mode=2)
     assert float((d2 - d2m).abs().max()) <= 2e-3 * float(d2m.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("M,m_live", [(1000, None), (4096 * 11, 4096 * 7 + 77), (64, None), (300, 0)])
+def test_umma_wgrad_matches_mma_sync(cuda_dev, M, m_live):
+    """tcgen05 weight-gradient kernel (MN-major operands, csrc/wgrad_umma.cu) vs the mma.sync kernel on the same job table:
+    both accumulate fp16 products in fp32; only the summation order differs -> rtol 1e-3 of the largest entry per layer."""
+    from seald_nerf_b200 import field as F
+    from seald_nerf_b200.dnerf.network import NeRFNetwork
+    torch.manual_seed(0)
+    net = NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True).to(cuda_dev)
+    cfg = net._field_cfg
+    ws = F.FieldWorkspace(cfg, M, cuda_dev, training=True)
+    g = torch.Generator(device=cuda_dev).manual_seed(1)
+    for name in ("in_buf", "fwd_d", "bwd_d", "gout_d", "hs", "cin", "fwd_s", "fwd_c", "bwd_s", "bwd_c", "gout_s", "gout_c", "feat"):
+        t = getattr(ws, name)
+        t.copy_(torch.randn(t.shape, device=cuda_dev, generator=g).to(t.dtype))
+    m_dev = None if m_live is None else torch.tensor([m_live], dtype=torch.int32, device=cuda_dev)
+    outs = []
+    for impl in ("mma", "umma"):
+        grads = [torch.zeros_like(w, dtype=torch.float32) for w in net.mlp_weights()]
+        jobs, n_jobs = F.wgrad_jobs(cfg, ws, grads, deform=True)
+        old = F.WGRAD_IMPL
+        F.WGRAD_IMPL = impl
+        try:
+            F.mlp_wgrad(jobs, n_jobs, M, m_dev)
+            F.mlp_wgrad(jobs, n_jobs, M, m_dev)  # accumulates
+        finally:
+            F.WGRAD_IMPL = old
+        torch.cuda.synchronize()
+        outs.append(grads)
+    for a, b in zip(*outs):
+        if m_live == 0:
+            assert float(b.abs().max()) == 0.0
+            continue
+        scale = float(a.abs().max())
+        assert scale > 0
+        assert float((a - b).abs().max()) <= 1e-3 * scale, (tuple(a.shape), float((a - b).abs().max()), scale)
