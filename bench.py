@@ -310,6 +310,7 @@ def main():
             "march": ("hbm", 48.0 * N_RAYS + 32.0 * m_live + 262144.0),
             "composite_fwd": ("hbm", 24.0 * m_live + 32.0 * N_RAYS),
             "composite_bwd": ("hbm", 40.0 * m_live + 48.0 * N_RAYS),
+            "composite_loss_fused": ("hbm", 64.0 * m_live + 104.0 * N_RAYS),
             "optimizer": ("hbm", 30.0 * trainer.n_params + 4.0 * trainer.n_params),
         }
         dom = max((k for k in st if k in work), key=lambda k: st[k])

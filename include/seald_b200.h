@@ -111,6 +111,15 @@ int seald_composite_rays_train_backward(const float* grad_weights_sum, const flo
                                         const float* weights_sum, const float* image, uint32_t M, uint32_t N,
                                         float T_thresh, float* grad_sigmas, float* grad_rgbs, seald_stream_t stream);
 
+/* composite forward + background blend / MSE loss + composite backward of a training step in one kernel (the arithmetic of
+ * seald_composite_rays_train_forward + seald_mse_loss_bg + seald_composite_rays_train_backward): also writes the zeros of
+ * grad_sigmas / grad_rgbs behind each ray's early stop, so the caller does not pre-zero them.  bg [N,3] or NULL (white),
+ * gt [N,3]; loss_sum += mean squared error * (3N * inv_count); gradients are those of loss_scale * that loss. */
+int seald_composite_train_loss_fused(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M,
+                                     uint32_t N, float T_thresh, const float* bg, const float* gt, float inv_count,
+                                     const float* loss_scale, float* weights_sum, float* depth, float* image, float* pred,
+                                     float* loss_sum, float* grad_sigmas, float* grad_rgbs, seald_stream_t stream);
+
 /* Inference march / composite.  Replace march_rays / composite_rays (raymarching.h:17-18,
  * raymarching.cu:701-914).  n_alive_dev / n_step_dev (optional, may be NULL): device int32 holding the live ray count and
  * the samples per ray of this round; when given they override the host values inside the kernel (the host n_alive is then

@@ -29,6 +29,7 @@ _SIGS = {
     "seald_occupancy_aabb": [_vp, _u32, _u32, _f32, _i32, _vp, _vp, _vp],
     "seald_composite_rays_train_forward": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp],
     "seald_composite_rays_train_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp],
+    "seald_composite_train_loss_fused": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_march_rays": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_composite_rays": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_render_schedule": [_vp, _vp, _u32, _u32, _u32, _vp],

@@ -823,6 +823,147 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_train_bwd_warp(
 }
 
 // ------------------------------------------------------------------------------------------------
+// Training tail in ONE kernel, one warp per ray: composite forward -> background blend + MSE loss and its gradient
+// (dnerf/utils.py:74-85, dnerf/renderer.py:325-326) -> composite backward.  Same arithmetic, in the same order, as
+// k_composite_train_fwd_warp + k_mse_loss_bg + k_composite_train_bwd_warp; what disappears are two launches, the
+// grad_image / grad_weights_sum round trip and the zero-fill of grad_sigmas / grad_rgbs (samples behind the early stop
+// get their zeros here).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCompWarps * 32) k_composite_train_loss_fused(
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas, const int* __restrict__ rays,
+    const uint32_t M, const uint32_t N, const float T_thresh, const float* __restrict__ bg, const float* __restrict__ gt,
+    const float inv_count, const float* __restrict__ loss_scale, float* __restrict__ weights_sum, float* __restrict__ depth,
+    float* __restrict__ image, float* __restrict__ pred, float* __restrict__ loss_sum, float* __restrict__ grad_sigmas,
+    float* __restrict__ grad_rgbs) {
+    // The recurrence over a block of 32 samples is replayed from shared memory (broadcast reads that do not depend on the
+    // loop-carried transmittance, so they pipeline) and WITHOUT a branch per sample: after the early stop the weights are
+    // multiplied by zero instead (x + 0 * c == x exactly), which keeps every sum identical to the serial loop.
+    __shared__ float s_loss[kCompWarps];
+    __shared__ float s_v[kCompWarps][5][32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x * kCompWarps + warp;
+    float(*sv)[32] = s_v[warp];
+    float local = 0.0f;
+    if (n < N) {
+        const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+        const bool has = num_steps != 0 && offset + num_steps <= M;
+        // ---- forward (k_composite_train_fwd_warp)
+        float r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+        if (has) {
+            float T = 1.0f;
+            bool live = true;
+            for (uint32_t base = 0; base < num_steps && live; base += 32) {
+                const uint32_t i = base + lane;
+                float alpha = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, d1 = 0.f;
+                if (i < num_steps) {
+                    const size_t s = (size_t)offset + i;
+                    const float2 dl = *reinterpret_cast<const float2*>(deltas + s * 2);
+                    alpha = 1.0f - __expf(-sigmas[s] * dl.x);
+                    d1 = dl.y;
+                    c0 = rgbs[s * 3]; c1 = rgbs[s * 3 + 1]; c2 = rgbs[s * 3 + 2];
+                }
+                __syncwarp();
+                sv[0][lane] = alpha; sv[1][lane] = c0; sv[2][lane] = c1; sv[3][lane] = c2; sv[4][lane] = d1;
+                __syncwarp();
+#pragma unroll
+                for (uint32_t j = 0; j < 32; j++) {
+                    const float a = sv[0][j];
+                    const float weight = live ? a * T : 0.0f;  // samples past the block end have a == 0
+                    r += weight * sv[1][j];
+                    g += weight * sv[2][j];
+                    b += weight * sv[3][j];
+                    t += sv[4][j];
+                    d += weight * t;
+                    ws += weight;
+                    T *= 1.0f - a;
+                    live = live && !(T < T_thresh);
+                }
+            }
+        }
+        // ---- loss and its gradient (k_mse_loss_bg)
+        const float scale = loss_scale ? *loss_scale : 1.0f;
+        const float img[3] = {r, g, b};
+        float gi[3], gws = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float bgc = bg ? bg[(size_t)index * 3 + c] : 1.0f;
+            const float p = img[c] + (1 - ws) * bgc;
+            const float diff = p - gt[(size_t)index * 3 + c];
+            local += diff * diff;
+            gi[c] = 2.0f * diff * inv_count * scale;
+            gws -= bgc * gi[c];
+            if (pred && lane == 0) pred[(size_t)index * 3 + c] = p;
+        }
+        if (lane == 0) {
+            weights_sum[index] = ws;
+            depth[index] = d;
+            image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+        } else {
+            local = 0.0f;  // every lane holds the same value: count the ray once
+        }
+        // ---- backward (k_composite_train_bwd_warp), zeros behind the early stop
+        if (has) {
+            const float r_final = r, g_final = g, b_final = b, ws_final = ws;
+            const float gws_term = gws * (1 - ws_final);
+            float T = 1.0f, ra = 0, ga = 0, ba = 0;
+            bool live = true;
+            for (uint32_t base = 0; base < num_steps; base += 32) {
+                const uint32_t i = base + lane;
+                const size_t s = (size_t)offset + i;
+                float my_w = 0.f, my_gs = 0.f;
+                bool my_live = false;
+                if (live) {
+                    float alpha = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, d0 = 0.f;
+                    if (i < num_steps) {
+                        d0 = deltas[s * 2];
+                        alpha = 1.0f - __expf(-sigmas[s] * d0);
+                        c0 = rgbs[s * 3]; c1 = rgbs[s * 3 + 1]; c2 = rgbs[s * 3 + 2];
+                    }
+                    __syncwarp();
+                    sv[0][lane] = alpha; sv[1][lane] = c0; sv[2][lane] = c1; sv[3][lane] = c2; sv[4][lane] = d0;
+                    __syncwarp();
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; j++) {
+                        const float a = sv[0][j];
+                        const float x0 = sv[1][j], x1 = sv[2][j], x2 = sv[3][j];
+                        const float weight = a * T;
+                        const bool was_live = live;
+                        if (was_live) {  // (uniform) the serial loop stops updating its running sums at the early stop
+                            ra += weight * x0;
+                            ga += weight * x1;
+                            ba += weight * x2;
+                            T *= 1.0f - a;
+                        }
+                        const float gsig = sv[4][j] * (
+                            gi[0] * (T * x0 - (r_final - ra)) +
+                            gi[1] * (T * x1 - (g_final - ga)) +
+                            gi[2] * (T * x2 - (b_final - ba)) +
+                            gws_term
+                        );
+                        if (lane == j) { my_w = weight; my_gs = gsig; my_live = was_live; }
+                        live = was_live && !(T < T_thresh);
+                    }
+                }
+                if (i < num_steps) {
+                    grad_rgbs[s * 3] = my_live ? gi[0] * my_w : 0.0f;
+                    grad_rgbs[s * 3 + 1] = my_live ? gi[1] * my_w : 0.0f;
+                    grad_rgbs[s * 3 + 2] = my_live ? gi[2] * my_w : 0.0f;
+                    grad_sigmas[s] = my_live ? my_gs : 0.0f;
+                }
+            }
+        }
+    }
+    if (lane == 0) s_loss[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.0f;
+#pragma unroll
+        for (uint32_t w = 0; w < kCompWarps; w++) v += s_loss[w];
+        atomicAdd(loss_sum, v * inv_count);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // inference march / composite
 // ------------------------------------------------------------------------------------------------
 template <bool SEAL>
@@ -1213,6 +1354,20 @@ extern "C" int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_t
     if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return SEALD_E_BADARG;
     k_composite_rays<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
                                                                            weights_sum, depth, image, n_alive_dev, n_step_dev);
+    return launch_status();
+}
+
+extern "C" int seald_composite_train_loss_fused(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M,
+                                                uint32_t N, float T_thresh, const float* bg, const float* gt, float inv_count,
+                                                const float* loss_scale, float* weights_sum, float* depth, float* image, float* pred,
+                                                float* loss_sum, float* grad_sigmas, float* grad_rgbs, seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays || !gt || !weights_sum || !depth || !image || !loss_sum || !grad_sigmas || !grad_rgbs) return SEALD_E_BADARG;
+    if (M > 0 && (!sigmas || !rgbs || !deltas)) return SEALD_E_BADARG;
+    if ((uintptr_t)deltas & 7) return SEALD_E_ALIGN;
+    k_composite_train_loss_fused<<<div_up(N, kCompWarps), kCompWarps * 32, 0, to_stream(stream)>>>(
+        sigmas, rgbs, deltas, rays, M, N, T_thresh, bg, gt, inv_count, loss_scale, weights_sum, depth, image, pred, loss_sum, grad_sigmas,
+        grad_rgbs);
     return launch_status();
 }
 

@@ -25,7 +25,7 @@ from ._lib import ptr
 class FusedTrainer:
     def __init__(self, model, num_rays=4096, max_samples=None, lr=1e-2, lr_net=None, betas=(0.9, 0.99), eps=1e-15, dt_gamma=0.0,
                  max_steps=1024, T_thresh=1e-4, perturb=True, init_loss_scale=65536.0, growth_interval=2000, train_deform=True,
-                 use_graph=True, world_size=1, process_group=None, device=None):
+                 use_graph=True, world_size=1, process_group=None, device=None, fuse_composite=True):
         self.model = model
         self.device = device or model.encoder.embeddings.device
         if self.device.type != "cuda":
@@ -42,6 +42,7 @@ class FusedTrainer:
         self.growth_interval = int(growth_interval)
         self.world_size, self.pg = int(world_size), process_group
         self.use_graph = bool(use_graph)
+        self.fuse_composite = bool(fuse_composite)
         self.global_step = 0
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -233,9 +234,19 @@ class FusedTrainer:
         def wgrad():
             F.mlp_wgrad(self.jobs, self.n_jobs, M, m_dev)
 
+        def composite_loss_fused():
+            # composite forward + loss + composite backward in one kernel (bg/gt are indexed by ray)
+            self.loss.zero_()
+            _lib.call("seald_composite_train_loss_fused", ptr(ws.sigma), ptr(ws.rgb), ptr(self.deltas), ptr(self.rays), M, N, self.T_thresh,
+                      ptr(self.bg), ptr(self.gt), inv_count, ptr(self.loss_scale), ptr(self.weights_sum), ptr(self.depth), ptr(self.image),
+                      ptr(self.pred), ptr(self.loss), ptr(self.grad_sigma), ptr(self.grad_rgb), _lib.stream())
+
+        if self.fuse_composite:
+            tail = [("composite_loss_fused", composite_loss_fused, 2)]
+        else:
+            tail = [("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3)]
         stages = [("select_frame", select_frame, 4), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
-                  ("heads_fwd", heads_fwd, 1), ("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3),
-                  ("heads_bwd", heads_bwd, 1), ("grid_bwd", grid_bwd, 3 if self.train_deform else 2)]
+                  ("heads_fwd", heads_fwd, 1)] + tail + [("heads_bwd", heads_bwd, 1), ("grid_bwd", grid_bwd, 3 if self.train_deform else 2)]
         if self.train_deform:
             stages.append(("deform_bwd", deform_bwd, 1))
         stages.append(("wgrad", wgrad, 1))

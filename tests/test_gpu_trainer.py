@@ -77,3 +77,39 @@ def test_training_reduces_loss(cuda_dev, use_graph):
     l = tr.train_step_host(o.cpu(), d.cpu(), t, gt.cpu())
     assert np.isfinite(l)
     assert tr.launches_per_step > 20
+
+
+def test_fused_composite_loss_kernel_equals_three_kernels(cuda_dev):
+    """seald_composite_train_loss_fused == composite forward + mse_loss_bg + composite backward (same arithmetic and order):
+    composited outputs bit-identical, gradients equal to fp32 round-off with the identical zero pattern behind each ray's
+    early stop; loss equal up to the order of the per-CTA atomic partial sums."""
+    from seald_nerf_b200.trainer import FusedTrainer
+    res = []
+    for fuse in (False, True):
+        model = _scene(cuda_dev)
+        model.encoder.embeddings.data.uniform_(-0.3, 0.3)
+        model.density_scale = 200.0  # opaque enough that most rays hit the T < 1e-4 early stop
+        o, d, t, gt = _batch(cuda_dev)
+        tr = FusedTrainer(model, num_rays=4096, max_samples=4096 * 48, perturb=False, init_loss_scale=128.0, use_graph=False, fuse_composite=fuse)
+        tr.grad_sigma.fill_(7.0); tr.grad_rgb.fill_(7.0)  # the fused kernel must overwrite every live sample row itself
+        bg = torch.rand(4096, 3, device=cuda_dev)
+        tr.set_inputs(o, d, t, gt, bg)
+        tr._forward_backward()
+        torch.cuda.synchronize()
+        m = int(tr.counter[0])
+        # the march hands out sample ranges to CTAs in arrival order: re-pack the per-sample gradients in ray order
+        rays = tr.rays.cpu().numpy()
+        gs, gc = tr.grad_sigma.cpu(), tr.grad_rgb.cpu()
+        gs = torch.cat([gs[o_:o_ + k] for _, o_, k in rays])
+        gc = torch.cat([gc[o_:o_ + k] for _, o_, k in rays])
+        assert gs.shape[0] == m
+        res.append((tr.image.clone(), tr.weights_sum.clone(), tr.depth.clone(), tr.pred.clone(), gs, gc, float(tr.loss), tr.grad_table.clone()))
+    for a, b in zip(res[0][:4], res[1][:4]):
+        assert torch.equal(a, b)  # image, weights_sum, depth, pred: bit-identical
+    for a, b in zip(res[0][4:6], res[1][4:6]):  # gradients: same zero pattern (early stops), values to fp32 round-off (FMA contraction)
+        assert torch.equal(a == 0, b == 0)
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-9)
+    assert abs(res[0][6] - res[1][6]) <= 1e-6 * abs(res[0][6]) + 1e-9
+    assert float((res[0][4] == 0).float().mean()) > 0.2  # many samples lie behind an early stop
+    scale = float(res[0][7].abs().max())
+    assert float((res[0][7] - res[1][7]).abs().max()) <= 1e-4 * scale  # (atomic order in the scatter)
