@@ -252,6 +252,13 @@ int seald_field_umma_pack_deform(const void* const* weights, int n_layers, void*
 int seald_field_deform_forward_umma(const float* xyz, const float* time_dev, const void* packed, int n_layers, uint32_t M,
                                     const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf,
                                     void* fwd_buf, seald_stream_t stream);
+/* Backward (dgrad chain) on tcgen05: same buffers as seald_field_deform_backward; packedT = the transposed weight tiles
+ * W_l^T of layers 1..n-1 (seald_field_umma_pack_deform_T, seald_field_umma_deform_bytes_T(n_layers) bytes). */
+uint64_t seald_field_umma_deform_bytes_T(int n_layers);
+int seald_field_umma_pack_deform_T(const void* const* weights, int n_layers, void* packedT, seald_stream_t stream);
+int seald_field_deform_backward_umma(const float* grad_x01, const float* time_dev, const void* packedT, int n_layers, uint32_t M,
+                                     const int32_t* m_dev, float bound, const void* fwd_buf, void* bwd_buf, void* gout_buf,
+                                     seald_stream_t stream);
 int seald_field_deform_backward(const float* grad_x01, const float* time_dev /*NULL or device float: t == 0 => zero gradient*/,
                                 const void* const* weights, int n_layers, uint32_t M, const int32_t* m_dev,
                                 float bound, const void* fwd_buf, void* bwd_buf /*[n_layers-1,M,128] f16*/, void* gout_buf /*[M,16] f16*/,

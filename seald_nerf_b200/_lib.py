@@ -46,6 +46,8 @@ _SIGS = {
     "seald_field_deform_forward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "seald_field_umma_pack_deform": [_vp, _i32, _vp, _vp],
     "seald_field_deform_forward_umma": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "seald_field_umma_pack_deform_T": [_vp, _i32, _vp, _vp],
+    "seald_field_deform_backward_umma": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
     "seald_field_deform_backward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
     "seald_field_heads_forward": [_vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_field_sigma_forward": [_vp, _vp, _i32, _u32, _f32, _vp, _vp, _vp],
@@ -82,7 +84,7 @@ _lib = None
 
 def exported_symbols():
     """Every entry point include/seald_b200.h declares (used by the CPU-side ABI test)."""
-    return ["seald_version", "seald_sm_arch", "seald_strerror", "seald_field_umma_deform_bytes"] + list(_SIGS)
+    return ["seald_version", "seald_sm_arch", "seald_strerror", "seald_field_umma_deform_bytes", "seald_field_umma_deform_bytes_T"] + list(_SIGS)
 
 
 def load():
@@ -100,6 +102,8 @@ def load():
     lib.seald_strerror.argtypes = [C.c_int]
     lib.seald_field_umma_deform_bytes.restype = C.c_uint64
     lib.seald_field_umma_deform_bytes.argtypes = [C.c_int]
+    lib.seald_field_umma_deform_bytes_T.restype = C.c_uint64
+    lib.seald_field_umma_deform_bytes_T.argtypes = [C.c_int]
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = sig

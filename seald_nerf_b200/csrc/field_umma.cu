@@ -246,6 +246,193 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
     }
 }
 
+
+// =====================================================================================================================
+// Deformation MLP backward (dgrad chain) on tcgen05: G_{l-1} = (G_l W_l) * ReLU'(h_l), l = n-1 .. 1, starting from
+// G_{n-1} = dL/d(dx) = grad_x01 / (2 bound) (zero at t == 0, dnerf/network.py:140-141).  Same CTA organisation as the forward
+// kernel; the B operand of step l is W_l^T in the canonical K-major layout (K = out features), pre-packed by
+// k_pack_umma_T.  The epilogue multiplies the fp32 accumulator row by the ReLU mask of the saved activation, writes G_{l-1}
+// as fp16 both to bwd_buf (the weight-gradient kernel reads it) and into the A-operand tile of the next step.
+// No input gradient: xyz and t are leaves without grad (dnerf/network.py:129-134).
+// =====================================================================================================================
+__host__ __device__ __forceinline__ uint32_t umma_layerT_bytes(const int l, const int n_layers) {
+    return (l == n_layers - 1) ? (uint32_t)(kUNLast * kUW * 2) : kTileBytes;  // layers 1 .. n-1 (layer 0 has no dgrad)
+}
+__host__ __device__ __forceinline__ size_t umma_layerT_offset(const int l, const int n_layers) {
+    size_t o = 0;
+    for (int i = 1; i < l; i++) o += umma_layerT_bytes(i, n_layers);
+    return o;
+}
+
+// dst chunk (c, n) = W_l[8c .. 8c+7][n] (rows >= n_real zero): the K-major tile of W_l^T, K = out features
+__global__ void k_pack_umma_T(const PackJobs jobs, __half* __restrict__ packedT) {
+    const int l = blockIdx.y + 1, n_layers = jobs.n_layers;
+    const bool last = (l == n_layers - 1);
+    const int K = last ? kUNLast : kUW, n_real = last ? 3 : kUW;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K / 8 * kUW) return;
+    const int c = i / kUW, n = i - c * kUW;
+    __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int k = c * 8 + e;
+        v[e] = (k < n_real) ? jobs.src[l][(size_t)k * kUW + n] : __float2half_rn(0.0f);
+    }
+    __half* dst = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(packedT) + umma_layerT_offset(l, n_layers));
+    *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
+template <int G>
+__global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umma(const float* __restrict__ grad_x01, const float* __restrict__ time,
+                                                                                  const __half* __restrict__ packedT, const int n_layers,
+                                                                                  const int M, const int* __restrict__ m_dev, const float bound,
+                                                                                  const __half* __restrict__ fwd_buf, __half* __restrict__ bwd_buf,
+                                                                                  __half* __restrict__ gout_buf) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using SM = UmmaSmem<G>;
+    constexpr int CTRL = G * 4;
+    unsigned char* s_a = smem + SM::A_OFF;
+    unsigned char* s_w = smem + SM::W_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+    uint64_t* bar_full = bars;
+    uint64_t* bar_aready = bars + 3;
+    uint64_t* bar_mma = bars + 3 + G;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * G);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
+    const int n_tiles = (m_used + kUW - 1) / kUW;
+    const int n_units = (n_tiles + G - 1) / G;
+    const int my_units = (n_units > (int)blockIdx.x) ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_steps = n_layers - 1;  // steps per unit: differentiate through matmuls n-1 .. 1
+    const int n_items = my_units * n_steps;
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; i++) umma::mbar_init(bar_full + i, 1);
+        for (int i = 0; i < G; i++) { umma::mbar_init(bar_aready + i, 128); umma::mbar_init(bar_mma + i, 1); }
+        umma::mbar_fence_init();
+    }
+    if (warp == CTRL) umma::tmem_alloc(tmem_slot, SM::TMEM_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == CTRL) {
+        if (lane == 0 && n_items > 0) {
+            const uint32_t a_addr = umma::smem_addr(s_a), w_addr = umma::smem_addr(s_w);
+            auto load_weights = [&](const int item) {
+                const int l = n_layers - 1 - (item % n_steps), st = item % kUStages;
+                const uint32_t bytes = umma_layerT_bytes(l, n_layers);
+                umma::mbar_arrive_expect_tx(bar_full + st, bytes);
+                umma::bulk_load(s_w + (size_t)st * kTileBytes, reinterpret_cast<const unsigned char*>(packedT) + umma_layerT_offset(l, n_layers), bytes,
+                                bar_full + st);
+            };
+            load_weights(0);
+            if (n_items > 1) load_weights(1);
+            const uint32_t idesc = umma::instr_desc_f16(128, kUW);
+            for (int i = 0; i < n_items; i++) {
+                const int st = i % kUStages;
+                const int ksteps = ((i % n_steps) == 0 ? kUNLast : kUW) / 16;
+#pragma unroll 1
+                for (int g = 0; g < G; g++) {
+                    umma::mbar_wait(bar_aready + g, i & 1);
+                    if (g == 0) umma::mbar_wait(bar_full + st, (i / kUStages) & 1);
+                    if (g == G - 1 && i + 2 < n_items) load_weights(i + 2);
+                    umma::fence_after_sync();
+                    const uint32_t d = tmem_base + g * kUW;
+                    const uint32_t a0 = a_addr + g * kTileBytes, w0 = w_addr + st * kTileBytes;
+                    for (int k = 0; k < ksteps; k++) {
+                        const uint64_t da = umma::smem_desc(a0 + k * 2 * (kUW * 16), kUW * 16, 128);
+                        const uint64_t db = umma::smem_desc(w0 + k * 2 * (kUW * 16), kUW * 16, 128);
+                        umma::mma_f16(d, da, db, idesc, k > 0 ? 1u : 0u);
+                    }
+                    umma::mma_commit(bar_mma + g);
+                }
+            }
+        }
+    } else {
+        const int g = tid >> 7, r = tid & 127;
+        unsigned char* a_tile = s_a + (size_t)g * kTileBytes;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(r & ~31) << 16) + g * kUW;
+        // at t == 0 the deformation is replaced by zeros (network.py:140-141): no gradient reaches the net
+        const float inv = (time && *time == 0.0f) ? 0.0f : 1.0f / (2 * bound);
+        int row = 0;
+        for (int i = 0; i < n_items; i++) {
+            const int s = i % n_steps;
+            const int l = n_layers - 1 - s;
+            if (s == 0) {
+                const int unit = (int)blockIdx.x + (i / n_steps) * (int)gridDim.x;
+                row = (G * unit + g) * kUW + r;
+                const bool live = row < m_used;
+                float gv[3] = {0.f, 0.f, 0.f};
+                if (live) { gv[0] = grad_x01[(size_t)row * 3] * inv; gv[1] = grad_x01[(size_t)row * 3 + 1] * inv; gv[2] = grad_x01[(size_t)row * 3 + 2] * inv; }
+                const __half2 h01 = __floats2half2_rn(gv[0], gv[1]), h2 = __floats2half2_rn(gv[2], 0.0f);
+                const uint4 u0 = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h2), 0u, 0u);
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(a_tile + ((size_t)0 * kUW + r) * 16) = u0;
+                *reinterpret_cast<uint4*>(a_tile + ((size_t)1 * kUW + r) * 16) = z;
+                if (live) {
+                    *reinterpret_cast<uint4*>(gout_buf + (size_t)row * 16) = u0;
+                    *reinterpret_cast<uint4*>(gout_buf + (size_t)row * 16 + 8) = z;
+                }
+                umma::fence_proxy_async();
+                umma::mbar_arrive(bar_aready + g);
+            }
+            const bool live = row < m_used;
+            const __half* hsave = fwd_buf + ((size_t)(l - 1) * M + row) * kUW;   // h_l: the activation that fed matmul l
+            __half* gsave = bwd_buf + ((size_t)(l - 1) * M + row) * kUW;         // G_{l-1}
+            uint4 hm[4];
+            auto load_mask = [&](const int q) {
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) hm[c4] = live ? __ldg(reinterpret_cast<const uint4*>(hsave + q * 32 + c4 * 8)) : make_uint4(0u, 0u, 0u, 0u);
+            };
+            load_mask(0);  // in flight while the MMAs finish
+            umma::mbar_wait(bar_mma + g, i & 1);
+            umma::fence_after_sync();
+            const bool feeds_next = (s + 1 < n_steps);
+#pragma unroll 1
+            for (int q = 0; q < 4; q++) {
+                uint32_t v[32];
+                umma::tmem_ld32(t_lane + q * 32, v);
+                umma::wait_ld();
+                uint4 out[4];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    const uint32_t hw[4] = {hm[c4].x, hm[c4].y, hm[c4].z, hm[c4].w};
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const __half2 hh = *reinterpret_cast<const __half2*>(&hw[j]);
+                        const float a = __low2float(hh) > 0.f ? __uint_as_float(v[c4 * 8 + j * 2]) : 0.f;
+                        const float b = __high2float(hh) > 0.f ? __uint_as_float(v[c4 * 8 + j * 2 + 1]) : 0.f;
+                        const __half2 p = __floats2half2_rn(a, b);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&p);
+                    }
+                    out[c4] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                if (q + 1 < 4) load_mask(q + 1);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    if (feeds_next) *reinterpret_cast<uint4*>(a_tile + ((size_t)(q * 4 + c4) * kUW + r) * 16) = out[c4];
+                    if (live) *reinterpret_cast<uint4*>(gsave + q * 32 + c4 * 8) = out[c4];
+                }
+            }
+            umma::fence_before_sync();
+            if (feeds_next) {
+                umma::fence_proxy_async();
+                umma::mbar_arrive(bar_aready + g);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == CTRL) {
+        __syncwarp();
+        umma::tmem_dealloc(tmem_base, SM::TMEM_COLS);
+    }
+}
+
 }  // namespace seald
 
 using namespace seald;
@@ -267,6 +454,48 @@ extern "C" int seald_field_umma_pack_deform(const void* const* weights, int n_la
         jobs.src[l] = reinterpret_cast<const __half*>(weights[l]);
     }
     k_pack_umma<<<dim3(div_up(kUW / 8 * kUW, 256), n_layers), 256, 0, to_stream(stream)>>>(jobs, reinterpret_cast<__half*>(packed));
+    return launch_status();
+}
+
+extern "C" uint64_t seald_field_umma_deform_bytes_T(int n_layers) {
+    if (n_layers < 2) return 0;
+    return (uint64_t)umma_layerT_offset(n_layers, n_layers);
+}
+
+// packedT: the transposed tiles W_l^T (layers 1 .. n-1) for the backward kernel, seald_field_umma_deform_bytes_T(n) bytes
+extern "C" int seald_field_umma_pack_deform_T(const void* const* weights, int n_layers, void* packedT, seald_stream_t stream) {
+    if (!weights || !packedT || n_layers < 2 || n_layers > 12) return SEALD_E_BADARG;
+    PackJobs jobs;
+    jobs.n_layers = n_layers;
+    for (int l = 0; l < n_layers; l++) {
+        if (!weights[l]) return SEALD_E_BADARG;
+        jobs.src[l] = reinterpret_cast<const __half*>(weights[l]);
+    }
+    k_pack_umma_T<<<dim3(div_up(kUW / 8 * kUW, 256), n_layers - 1), 256, 0, to_stream(stream)>>>(jobs, reinterpret_cast<__half*>(packedT));
+    return launch_status();
+}
+
+extern "C" int seald_field_deform_backward_umma(const float* grad_x01, const float* time_dev, const void* packedT, int n_layers, uint32_t M,
+                                                const int32_t* m_dev, float bound, const void* fwd_buf, void* bwd_buf, void* gout_buf,
+                                                seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!grad_x01 || !packedT || !fwd_buf || !bwd_buf || !gout_buf || n_layers < 2 || n_layers > 12) return SEALD_E_BADARG;
+    if (((uintptr_t)packedT & 15) != 0) return SEALD_E_ALIGN;
+    const uint32_t n_tiles = div_up(M, (uint32_t)kUW);
+    cudaStream_t st = to_stream(stream);
+    auto launch = [&](auto kernel, const int G, const size_t smem, const int threads) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        const uint32_t units = div_up(n_tiles, (uint32_t)G);
+        const uint32_t grid = units < (uint32_t)SEALD_NUM_SMS ? units : (uint32_t)SEALD_NUM_SMS;
+        kernel<<<grid, threads, smem, st>>>(grad_x01, time_dev, (const __half*)packedT, n_layers, (int)M, m_dev, bound, (const __half*)fwd_buf,
+                                            (__half*)bwd_buf, (__half*)gout_buf);
+        return 0;
+    };
+    const bool big = n_tiles >= 4u * SEALD_NUM_SMS;
+    const int rc = big ? launch(k_deform_backward_umma<4>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
+                       : launch(k_deform_backward_umma<2>, 2, UmmaSmem<2>::BYTES, UmmaSmem<2>::THREADS);
+    if (rc) return rc;
     return launch_status();
 }
 

@@ -62,6 +62,8 @@ class HalfWeights:
 
         # the deformation weights again, as canonical K-major UMMA operand tiles (tcgen05 path, csrc/field_umma.cu)
         self.packed_deform = torch.zeros(int(_lib.load().seald_field_umma_deform_bytes(cfg.n_deform)) // 2, dtype=torch.float16, device=device)
+        self.packed_deform_T = torch.zeros(int(_lib.load().seald_field_umma_deform_bytes_T(cfg.n_deform)) // 2, dtype=torch.float16, device=device)
+        self.pack_transposed = True  # the transposed tiles are only needed for training (deformation backward)
 
         n = len(self.views)
         self._dst = _lib.ptr_array(self.views)
@@ -78,6 +80,8 @@ class HalfWeights:
         src = _lib.ptr_array(ws)
         _lib.call("seald_cast_pad_f16_batch", src, self._dst, self._rows, self._cols, self._ld, len(ws), _lib.stream())
         _lib.call("seald_field_umma_pack_deform", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform), _lib.stream())
+        if self.pack_transposed:
+            _lib.call("seald_field_umma_pack_deform_T", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform_T), _lib.stream())
 
 
 class FieldWorkspace:
@@ -120,6 +124,16 @@ def deform_forward(cfg, hw, xyzs, time_dev, M, m_dev, t0_mode, deform, x01, in_b
     else:
         _lib.call("seald_field_deform_forward", ptr(xyzs), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, int(t0_mode),
                   ptr(deform), ptr(x01), ptr(in_buf), ptr(fwd_buf), st)
+
+
+def deform_backward(cfg, hw, grad_x01, time_dev, M, m_dev, fwd_d, bwd_d, gout_d):
+    st = _lib.stream()
+    if DEFORM_IMPL == "umma":
+        _lib.call("seald_field_deform_backward_umma", ptr(grad_x01), ptr(time_dev), ptr(hw.packed_deform_T), cfg.n_deform, M, ptr(m_dev),
+                  cfg.bound, ptr(fwd_d), ptr(bwd_d), ptr(gout_d), st)
+    else:
+        _lib.call("seald_field_deform_backward", ptr(grad_x01), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, ptr(fwd_d),
+                  ptr(bwd_d), ptr(gout_d), st)
 
 
 def mlp_wgrad(jobs, n_jobs, M, m_dev):
@@ -190,8 +204,7 @@ def field_backward(cfg, hw, ws, grad_sigma, grad_rgb, time_is_zero, table16, off
               ptr(ws.grad_x01) if want_dx else None, M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype,
               int(cfg.align_corners), cfg.interp, F16, F32, ptr(m_dev), st)
     if want_dx:
-        _lib.call("seald_field_deform_backward", ptr(ws.grad_x01), ptr(time_dev), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound, ptr(ws.fwd_d),
-                  ptr(ws.bwd_d), ptr(ws.gout_d), st)
+        deform_backward(cfg, hw, ws.grad_x01, time_dev, M, m_dev, ws.fwd_d, ws.bwd_d, ws.gout_d)
     mlp_wgrad(jobs, n_jobs, M, m_dev)
 
 

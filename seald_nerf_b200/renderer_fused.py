@@ -75,6 +75,7 @@ class FusedRenderer:
         self.h_state = torch.zeros(8, dtype=torch.int32).pin_memory()
         self._poll = [(torch.zeros(8, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
         self.hw = F.HalfWeights(self.cfg, dev)
+        self.hw.pack_transposed = False  # inference only
         self.table16 = None
         self.refresh_weights()
         self._graphs = {}

@@ -228,8 +228,7 @@ class FusedTrainer:
                       cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, F32, ptr(m_dev), _lib.stream())
 
         def deform_bwd():
-            _lib.call("seald_field_deform_backward", ptr(ws.grad_x01), ptr(self.time), hw.p_deform, cfg.n_deform, M, ptr(m_dev), cfg.bound,
-                      ptr(ws.fwd_d), ptr(ws.bwd_d), ptr(ws.gout_d), _lib.stream())
+            F.deform_backward(cfg, hw, ws.grad_x01, self.time, M, m_dev, ws.fwd_d, ws.bwd_d, ws.gout_d)
 
         def wgrad():
             F.mlp_wgrad(self.jobs, self.n_jobs, M, m_dev)
