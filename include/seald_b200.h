@@ -256,6 +256,7 @@ int seald_field_deform_forward_umma(const float* xyz, const float* time_dev, con
  * W_l^T of layers 1..n-1 (seald_field_umma_pack_deform_T, seald_field_umma_deform_bytes_T(n_layers) bytes). */
 uint64_t seald_field_umma_deform_bytes_T(int n_layers);
 int seald_field_umma_pack_deform_T(const void* const* weights, int n_layers, void* packedT, seald_stream_t stream);
+int seald_field_umma_pack_deform_both(const void* const* weights, int n_layers, void* packed, void* packedT, seald_stream_t stream);
 int seald_field_deform_backward_umma(const float* grad_x01, const float* time_dev, const void* packedT, int n_layers, uint32_t M,
                                      const int32_t* m_dev, float bound, const void* fwd_buf, void* bwd_buf, void* gout_buf,
                                      seald_stream_t stream);
@@ -305,6 +306,10 @@ int seald_ffmlp_backward(const void* grad, const void* inputs, const void* weigh
  * Training-step glue (replaces the torch element-wise kernels around the hot path: dnerf/utils.py:74-85 loss,
  * torch.cuda.amp.GradScaler + torch.optim.Adam as configured in main_dnerf.py:129,136).
  * ------------------------------------------------------------------------------------------------ */
+/* Start of a step: t_idx = clamp(floor(*time * T), 0, T-1) (dnerf/renderer.py:285); copies frame t_idx of bitfield_all
+ * [T, frame_bytes] (and row t_idx of occ_all [T,6], optional) into the step's static buffers and zeroes counter[2] (optional). */
+int seald_select_frame(const float* time_dev, uint32_t T, const uint8_t* bitfield_all, uint32_t frame_bytes, uint8_t* bitfield_out,
+                       const float* occ_all, float* occ_out, int32_t* counter, seald_stream_t stream);
 /* pred = image + (1 - ws) * bg (bg NULL = white); loss_sum += mean squared error (inv_count = 1/(3N) or 1/(3N*world));
  * grad_image / grad_ws = d(loss_scale * mse)/d(image, ws). */
 int seald_mse_loss_bg(const float* image, const float* weights_sum, const float* bg, const float* gt, uint32_t N, float inv_count,
@@ -321,8 +326,10 @@ int seald_adam_advance(int32_t* step_dev, const int32_t* found_inf, seald_stream
 int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
                     const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
                     seald_stream_t stream);
+/* step_dev (optional): completed-update counter, incremented here when no inf was found (then seald_adam_advance is not
+ * needed and seald_adam_step is called with step = 1: "this is update number *step_dev + 1"). */
 int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff, int interval,
-                            seald_stream_t stream);
+                            int32_t* step_dev, seald_stream_t stream);
 
 #ifdef __cplusplus
 }

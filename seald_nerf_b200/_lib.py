@@ -47,6 +47,7 @@ _SIGS = {
     "seald_field_umma_pack_deform": [_vp, _i32, _vp, _vp],
     "seald_field_deform_forward_umma": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "seald_field_umma_pack_deform_T": [_vp, _i32, _vp, _vp],
+    "seald_field_umma_pack_deform_both": [_vp, _i32, _vp, _vp, _vp],
     "seald_field_deform_backward_umma": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
     "seald_field_deform_backward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
     "seald_field_heads_forward": [_vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -56,13 +57,14 @@ _SIGS = {
     "seald_mlp_wgrad_umma": [_vp, _i32, _u32, _vp, _vp],
     "seald_ffmlp_forward": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "seald_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp],
+    "seald_select_frame": [_vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp],
     "seald_mse_loss_bg": [_vp, _vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_cast_pad_f16": [_vp, _vp, _u32, _u32, _u32, _vp],
     "seald_cast_pad_f16_batch": [_vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "seald_grad_finite_check": [_vp, C.c_uint64, _vp, _vp],
     "seald_adam_advance": [_vp, _vp, _vp],
     "seald_adam_step": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _vp],
-    "seald_loss_scale_update": [_vp, _vp, _vp, _f32, _f32, _i32, _vp],
+    "seald_loss_scale_update": [_vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp],
 }
 
 

@@ -57,8 +57,8 @@ struct PackJobs {
     const __half* src[12];
     int n_layers;
 };
-__global__ void k_pack_umma(const PackJobs jobs, __half* __restrict__ packed) {
-    const int l = blockIdx.y, n_layers = jobs.n_layers;
+__device__ __forceinline__ void pack_umma_body(const PackJobs& jobs, __half* __restrict__ packed, const int l) {
+    const int n_layers = jobs.n_layers;
     const bool last = (l == n_layers - 1);
     const int K = (l == 0) ? kUK0 : kUW, n_pad = last ? kUNLast : kUW, n_real = last ? 3 : kUW, ld = K;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
@@ -69,6 +69,7 @@ __global__ void k_pack_umma(const PackJobs jobs, __half* __restrict__ packed) {
     __half* dst = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(packed) + umma_layer_offset(l, n_layers));
     *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = v;
 }
+__global__ void k_pack_umma(const PackJobs jobs, __half* __restrict__ packed) { pack_umma_body(jobs, packed, blockIdx.y); }
 
 template <bool SAVE, int G>
 __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma(const float* __restrict__ xyz, const float* __restrict__ time,
@@ -265,8 +266,8 @@ __host__ __device__ __forceinline__ size_t umma_layerT_offset(const int l, const
 }
 
 // dst chunk (c, n) = W_l[8c .. 8c+7][n] (rows >= n_real zero): the K-major tile of W_l^T, K = out features
-__global__ void k_pack_umma_T(const PackJobs jobs, __half* __restrict__ packedT) {
-    const int l = blockIdx.y + 1, n_layers = jobs.n_layers;
+__device__ __forceinline__ void pack_umma_T_body(const PackJobs& jobs, __half* __restrict__ packedT, const int l) {
+    const int n_layers = jobs.n_layers;
     const bool last = (l == n_layers - 1);
     const int K = last ? kUNLast : kUW, n_real = last ? 3 : kUW;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,6 +281,11 @@ __global__ void k_pack_umma_T(const PackJobs jobs, __half* __restrict__ packedT)
     }
     __half* dst = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(packedT) + umma_layerT_offset(l, n_layers));
     *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = *reinterpret_cast<const uint4*>(v);
+}
+__global__ void k_pack_umma_T(const PackJobs jobs, __half* __restrict__ packedT) { pack_umma_T_body(jobs, packedT, blockIdx.y + 1); }
+__global__ void k_pack_umma_both(const PackJobs jobs, __half* __restrict__ packed, __half* __restrict__ packedT) {
+    if ((int)blockIdx.y < jobs.n_layers) pack_umma_body(jobs, packed, blockIdx.y);
+    else pack_umma_T_body(jobs, packedT, (int)blockIdx.y - jobs.n_layers + 1);
 }
 
 template <int G>
@@ -472,6 +478,21 @@ extern "C" int seald_field_umma_pack_deform_T(const void* const* weights, int n_
         jobs.src[l] = reinterpret_cast<const __half*>(weights[l]);
     }
     k_pack_umma_T<<<dim3(div_up(kUW / 8 * kUW, 256), n_layers - 1), 256, 0, to_stream(stream)>>>(jobs, reinterpret_cast<__half*>(packedT));
+    return launch_status();
+}
+
+// both layouts in one launch pair-free call (the optimiser refreshes them every step)
+extern "C" int seald_field_umma_pack_deform_both(const void* const* weights, int n_layers, void* packed, void* packedT, seald_stream_t stream) {
+    if (!weights || !packed || !packedT || n_layers < 2 || n_layers > 12) return SEALD_E_BADARG;
+    PackJobs jobs;
+    jobs.n_layers = n_layers;
+    for (int l = 0; l < n_layers; l++) {
+        if (!weights[l]) return SEALD_E_BADARG;
+        if ((uintptr_t)weights[l] & 15) return SEALD_E_ALIGN;
+        jobs.src[l] = reinterpret_cast<const __half*>(weights[l]);
+    }
+    k_pack_umma_both<<<dim3(div_up(kUW / 8 * kUW, 256), 2 * n_layers - 1), 256, 0, to_stream(stream)>>>(jobs, reinterpret_cast<__half*>(packed),
+                                                                                                      reinterpret_cast<__half*>(packedT));
     return launch_status();
 }
 

@@ -84,13 +84,13 @@ __global__ void k_grad_finite_check(const float* __restrict__ g, const size_t n,
 // update skipped when *found_inf != 0 (GradScaler.step).  Optionally refreshes an fp16 copy and zeroes the gradient.
 __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const size_t n,
                        const float lr, const float beta1, const float beta2, const float eps, float bc1, float bc2_sqrt,
-                       const int* __restrict__ step_dev, const float* __restrict__ loss_scale, const int* __restrict__ found_inf,
-                       __half* __restrict__ p16, const int zero_grad) {
+                       const int* __restrict__ step_dev, const int step_add, const float* __restrict__ loss_scale,
+                       const int* __restrict__ found_inf, __half* __restrict__ p16, const int zero_grad) {
     const bool skip = found_inf && *found_inf != 0;
     if (step_dev) {  // step number kept on the device (graph replay): bias corrections computed here
         __shared__ float s_bc[2];
         if (threadIdx.x == 0) {
-            const double st = (double)max(*step_dev, 1);
+            const double st = (double)max(*step_dev + step_add, 1);
             s_bc[0] = (float)(1.0 - pow((double)beta1, st));
             s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, st));
         }
@@ -152,8 +152,9 @@ __global__ void k_adam_advance(int* step_dev, const int* __restrict__ found_inf)
 
 // GradScaler.update(): found_inf -> scale *= backoff, tracker = 0; else tracker++ and scale *= growth every `interval`.
 __global__ void k_loss_scale_update(float* loss_scale, int* found_inf, int* growth_tracker, const float growth, const float backoff,
-                                    const int interval) {
+                                    const int interval, int* step_dev) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (step_dev && !*found_inf) *step_dev += 1;  // optimizer.step() ran: one more completed update
         if (*found_inf) {
             *loss_scale *= backoff;
             *growth_tracker = 0;
@@ -170,9 +171,36 @@ __global__ void k_loss_scale_update(float* loss_scale, int* found_inf, int* grow
     }
 }
 
+// Start of a training step (dnerf/renderer.py:285,291-292): pick the occupancy frame of this time stamp
+// t_idx = clamp(floor(time * T), 0, T-1), copy its bitfield and occupied-cell box into the step's static buffers and reset
+// the sample counter - one launch instead of a chain of small tensor ops.
+__global__ void k_select_frame(const float* __restrict__ time, const uint32_t T, const uint4* __restrict__ bitfield_all, const uint32_t frame_vec16,
+                               uint4* __restrict__ bitfield_out, const float* __restrict__ occ_all, float* __restrict__ occ_out,
+                               int* __restrict__ counter) {
+    int t_idx = (int)floorf(*time * (float)T);
+    t_idx = min(max(t_idx, 0), (int)T - 1);
+    const uint4* src = bitfield_all + (size_t)t_idx * frame_vec16;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < frame_vec16; i += gridDim.x * blockDim.x) bitfield_out[i] = src[i];
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 6 && occ_all && occ_out) occ_out[threadIdx.x] = occ_all[(size_t)t_idx * 6 + threadIdx.x];
+        if (threadIdx.x < 2 && counter) counter[threadIdx.x] = 0;
+    }
+}
+
 }  // namespace seald
 
 using namespace seald;
+
+extern "C" int seald_select_frame(const float* time_dev, uint32_t T, const uint8_t* bitfield_all, uint32_t frame_bytes, uint8_t* bitfield_out,
+                                  const float* occ_all, float* occ_out, int32_t* counter, seald_stream_t stream) {
+    if (!time_dev || !bitfield_all || !bitfield_out || T == 0 || frame_bytes == 0) return SEALD_E_BADARG;
+    if (frame_bytes % 16 || ((uintptr_t)bitfield_all & 15) || ((uintptr_t)bitfield_out & 15)) return SEALD_E_ALIGN;
+    const uint32_t n16 = frame_bytes / 16;
+    const uint32_t blocks = div_up(n16, 256u) < (uint32_t)SEALD_NUM_SMS ? div_up(n16, 256u) : (uint32_t)SEALD_NUM_SMS;
+    k_select_frame<<<blocks, 256, 0, to_stream(stream)>>>(time_dev, T, reinterpret_cast<const uint4*>(bitfield_all), n16,
+                                                         reinterpret_cast<uint4*>(bitfield_out), occ_all, occ_out, counter);
+    return launch_status();
+}
 
 extern "C" int seald_mse_loss_bg(const float* image, const float* weights_sum, const float* bg, const float* gt, uint32_t N, float inv_count,
                                  const float* loss_scale, float* pred, float* loss_sum, float* grad_image, float* grad_ws,
@@ -229,18 +257,21 @@ extern "C" int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t 
                                seald_stream_t stream) {
     if (n == 0) return 0;
     if (!p || !g || !m || !v || (step == 0 && !step_dev)) return SEALD_E_BADARG;
+    const uint32_t step_in = step;
     if (step == 0) step = 1;
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     const uint32_t blocks = (uint32_t)(n / 256 + 1 < 8u * SEALD_NUM_SMS ? n / 256 + 1 : 8u * SEALD_NUM_SMS);
-    k_adam<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), step_dev, loss_scale, found_inf,
-                                                  (__half*)p16, zero_grad);
+    // with step_dev: the step number of THIS update is *step_dev + step (step = 0: the counter was advanced already by
+    // seald_adam_advance; step = 1: it counts completed updates and is advanced by seald_loss_scale_update afterwards)
+    k_adam<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), step_dev,
+                                                  step_dev ? (int)step_in : 0, loss_scale, found_inf, (__half*)p16, zero_grad);
     return launch_status();
 }
 
 extern "C" int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff,
-                                       int interval, seald_stream_t stream) {
+                                       int interval, int32_t* step_dev, seald_stream_t stream) {
     if (!loss_scale || !found_inf || !growth_tracker) return SEALD_E_BADARG;
-    k_loss_scale_update<<<1, 32, 0, to_stream(stream)>>>(loss_scale, found_inf, growth_tracker, growth, backoff, interval);
+    k_loss_scale_update<<<1, 32, 0, to_stream(stream)>>>(loss_scale, found_inf, growth_tracker, growth, backoff, interval, step_dev);
     return launch_status();
 }

@@ -79,9 +79,11 @@ class HalfWeights:
             ws.append(w if w.is_contiguous() else w.contiguous())
         src = _lib.ptr_array(ws)
         _lib.call("seald_cast_pad_f16_batch", src, self._dst, self._rows, self._cols, self._ld, len(ws), _lib.stream())
-        _lib.call("seald_field_umma_pack_deform", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform), _lib.stream())
         if self.pack_transposed:
-            _lib.call("seald_field_umma_pack_deform_T", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform_T), _lib.stream())
+            _lib.call("seald_field_umma_pack_deform_both", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform), ptr(self.packed_deform_T),
+                      _lib.stream())
+        else:
+            _lib.call("seald_field_umma_pack_deform", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform), _lib.stream())
 
 
 class FieldWorkspace:

@@ -174,11 +174,9 @@ class FusedTrainer:
         F16, F32 = _lib.F16, _lib.F32
 
         def select_frame():
-            # occupancy frame of this time stamp (dnerf/renderer.py:285), selected on the device
-            t_idx = torch.floor(self.time * m.time_size).clamp(min=0, max=m.time_size - 1).long()
-            torch.index_select(m.density_bitfield, 0, t_idx, out=self.bitfield_frame.view(1, -1))
-            torch.index_select(self.occ_all, 0, t_idx, out=self.occ_frame)
-            self.counter.zero_()
+            # occupancy frame of this time stamp (dnerf/renderer.py:285) + its occupied-cell box, selected on the device; counter reset
+            _lib.call("seald_select_frame", ptr(self.time), int(m.time_size), ptr(m.density_bitfield), int(m.density_bitfield.shape[1]),
+                      ptr(self.bitfield_frame), ptr(self.occ_all), ptr(self.occ_frame), ptr(self.counter), _lib.stream())
             if self.perturb:
                 self.noises.uniform_(0, 1)
 
@@ -244,7 +242,7 @@ class FusedTrainer:
             tail = [("composite_loss_fused", composite_loss_fused, 2)]
         else:
             tail = [("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3)]
-        stages = [("select_frame", select_frame, 4), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
+        stages = [("select_frame", select_frame, 2), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
                   ("heads_fwd", heads_fwd, 1)] + tail + [("heads_bwd", heads_bwd, 1), ("grid_bwd", grid_bwd, 3 if self.train_deform else 2)]
         if self.train_deform:
             stages.append(("deform_bwd", deform_bwd, 1))
@@ -294,16 +292,15 @@ class FusedTrainer:
         st = _lib.stream()
         b1, b2 = self.betas
         _lib.call("seald_grad_finite_check", ptr(self.grads), self.n_params, ptr(self.found_inf), st)
-        _lib.call("seald_adam_advance", ptr(self.step_dev), ptr(self.found_inf), st)
         nt = self.n_table
         _lib.call("seald_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), nt, self.lr, b1, b2, self.eps,
-                  0, ptr(self.step_dev), ptr(self.loss_scale), ptr(self.found_inf), ptr(self.table16), 1, st)
+                  1, ptr(self.step_dev), ptr(self.loss_scale), ptr(self.found_inf), ptr(self.table16), 1, st)
         _lib.call("seald_adam_step", self.params.data_ptr() + 4 * nt, self.grads.data_ptr() + 4 * nt, self.exp_avg.data_ptr() + 4 * nt,
-                  self.exp_avg_sq.data_ptr() + 4 * nt, self.n_weights, self.lr_net, b1, b2, self.eps, 0, ptr(self.step_dev),
+                  self.exp_avg_sq.data_ptr() + 4 * nt, self.n_weights, self.lr_net, b1, b2, self.eps, 1, ptr(self.step_dev),
                   ptr(self.loss_scale), ptr(self.found_inf), None, 1, st)
         self.hw.refresh(self.weight_views)
         _lib.call("seald_loss_scale_update", ptr(self.loss_scale), ptr(self.found_inf), ptr(self.growth_tracker), 2.0, 0.5,
-                  self.growth_interval, st)
+                  self.growth_interval, ptr(self.step_dev), st)
         return 6
 
     def _allreduce(self):
