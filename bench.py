@@ -64,11 +64,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=10.0):
+        """nvidia-smi takes a moment to start: block until its first sample so that short timed regions are covered."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -76,7 +86,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if (t_begin is not None and ts < t_begin) or (t_end is not None and ts > t_end + 0.03):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -86,7 +98,8 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "device-timed loop + end-to-end loop"}
 
 
 def run_reference(args, rank):
@@ -241,6 +254,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+    t_clk0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -250,8 +265,10 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    loss_end = float(trainer.loss.item())
+    loss_t = trainer.loss.clone()  # each rank holds its share of the global-batch mean (its squared errors / GLOBAL element count)
+    if world > 1:
+        dist.all_reduce(loss_t)
+    loss_end = float(loss_t.item())
     launches = trainer.launches_per_step * K
 
     # ---- end-to-end loop (host inputs, loss read back every step) ------------------------------------------------
@@ -268,6 +285,7 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_clk0, sampler.mark()) if rank == 0 else None
 
     # ---- full-frame render, ray tiles sharded over the ranks (configs[2]) ------------------------------------------------
     from seald_nerf_b200 import microbench
@@ -306,7 +324,8 @@ def main():
             "heads_fwd": ("tensor", 2.0 * mac_heads * m_live),
             "heads_bwd": ("tensor", 2.0 * mac_heads * m_live),
             "grid_fwd": ("hbm", 588.0 * m_live),
-            "grid_bwd": ("hbm", (1100.0 + 588.0 + 12.0) * m_live),
+            "grid_scatter": ("hbm", 2124.0 * m_live),      # fp32 gradient table: 12 + 64 + 2 * 8 * 16 * 2 * 4
+            "grid_input_bwd": ("hbm", (588.0 + 12.0) * m_live),
             "march": ("hbm", 48.0 * N_RAYS + 32.0 * m_live + 262144.0),
             "composite_fwd": ("hbm", 24.0 * m_live + 32.0 * N_RAYS),
             "composite_bwd": ("hbm", 40.0 * m_live + 48.0 * N_RAYS),
@@ -362,8 +381,16 @@ def main():
                                 "bwd_ms": g["kernels"]["bwd_table_f32"]["ms"], "bytes_per_point": {"fwd": 588, "bwd_f32_table": 2124}}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # release the CUDA graphs that hold captured NCCL kernels before the communicator goes away; a communicator teardown
+        # that blocks must not turn a finished measurement into a hang, so it gets a bounded wait
+        del trainer
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        th.start()
+        th.join(timeout=20)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

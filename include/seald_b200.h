@@ -42,7 +42,9 @@ const char* seald_strerror(int status);
  * Replaces grid_encode_forward / grid_encode_backward (gridencoder/src/gridencoder.h:12-13,
  * kernels gridencoder/src/gridencoder.cu:88,249,344).
  *   x01      [B, D] fp32, already mapped to [0,1]
- *   table    [offsets[L], C]  dtype (fp16 or fp32)
+ *   table    [offsets[L], C]  dtype (fp16 or fp32); when 16-byte aligned, rows of 4 or 8 bytes are fetched in aligned 16-byte
+ *            groups, so the allocation must be readable up to the next 16-byte boundary past its last row (GridEncoder
+ *            rounds every level to a multiple of 8 rows, grid.py:125, which guarantees it)
  *   offsets  [L+1] int32
  *   out      [B, L*C] dtype — written directly in the layout GridEncoder.forward returns
  *            (the reference writes [L,B,C] and permutes, grid.py:47,57)
@@ -64,6 +66,19 @@ int seald_grid_encode_backward(const void* grad_out, const float* x01, const voi
                                uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
                                uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
                                int grad_table_dtype, const int32_t* b_dev, seald_stream_t stream);
+
+/* The two halves of seald_grid_encode_backward as separate launches (they are independent: the fused trainer runs the table
+ * scatter beside the deformation-net backward on a second stream).  found_inf (optional, device int32): set to a non-zero
+ * word (the bits of 1.0f) when a consumed grad_out element is inf/nan; the table gradient is non-finite exactly then, so
+ * GradScaler's overflow check (nerf/utils.py:884-886 scaler.step) need not re-read the table gradient. */
+int seald_grid_encode_backward_table(const void* grad_out, const float* x01, const int32_t* offsets, void* grad_table,
+                                     uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                     uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                                     int grad_table_dtype, const int32_t* b_dev, int32_t* found_inf, seald_stream_t stream);
+int seald_grid_encode_backward_input(const void* grad_out, const float* x01, const void* table, const int32_t* offsets,
+                                     const void* dy_dx, float* grad_x, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                                     float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                                     const int32_t* b_dev, seald_stream_t stream);
 
 /* Debug/parity op: emits the uint32 table row index (before *C) of every (point, level, corner)
  * [B, L, 2^D] and the per-level (scale, resolution) the device computed [L] each. */

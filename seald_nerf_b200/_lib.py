@@ -19,6 +19,8 @@ _vp, _u32, _i32, _f32 = C.c_void_p, C.c_uint32, C.c_int, C.c_float
 _SIGS = {
     "seald_grid_encode_forward": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp, _vp],
     "seald_grid_encode_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32, _vp, _vp],
+    "seald_grid_encode_backward_table": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32, _vp, _vp, _vp],
+    "seald_grid_encode_backward_input": [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp, _vp],
     "seald_grid_debug_indices": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _vp],
     "seald_near_far_from_aabb": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp],
     "seald_sph_from_ray": [_vp, _vp, _f32, _u32, _vp, _vp],

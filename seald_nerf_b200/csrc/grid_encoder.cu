@@ -10,6 +10,9 @@
 //               accumulated in a CTA-private fp32 copy (shared atomics) and flushed once; the others use
 //               warp-aggregated (match.any) vector atomics.  Input gradients are recomputed from the table
 //               with fp32 accumulation (or taken from dy_dx when the caller kept it).
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace seald {
@@ -237,6 +240,192 @@ __global__ void __launch_bounds__(256) k_grid_forward(const float* __restrict__ 
     }
 }
 
+
+// =================================================================================================
+// forward, paired corner loads
+// =================================================================================================
+// The two corners of a cell that differ in dimension 0 are neighbours in memory: on a dense level they are rows r and
+// r + 1, on a hashed level (prime[0] == 1) rows h ^ x and h ^ (x + 1), which differ only in the low bits x ^ (x + 1).
+// Three times out of four both lie inside one aligned 16-byte group of the table, so ONE 16-byte load fetches the pair and
+// a 4/8-byte load is issued only by the lanes whose pair straddles a group.  The gathers are L1-wavefront bound (one
+// wavefront per lane per load), so this removes ~3/8 of the wavefronts.  Rows are RB = C * sizeof(T) = 4 or 8 bytes.
+template <typename T, uint32_t C>
+struct RowPack {
+    static constexpr uint32_t RB = C * sizeof(T);
+    static constexpr uint32_t W = RB / 4;        // 32-bit words per row
+    static constexpr uint32_t R16 = 16 / RB;     // rows per 16-byte group
+    static constexpr bool ok = (RB == 4 || RB == 8);
+    static __device__ __forceinline__ void pick(const uint4& u, const uint32_t k, uint32_t (&w)[W]) {
+        if constexpr (W == 1) {
+            const uint32_t lo = (k & 1u) ? u.y : u.x;
+            const uint32_t hi = (k & 1u) ? u.w : u.z;
+            w[0] = (k & 2u) ? hi : lo;
+        } else {
+            w[0] = (k & 1u) ? u.z : u.x;
+            w[1] = (k & 1u) ? u.w : u.y;
+        }
+    }
+    static __device__ __forceinline__ void load_row(const T* p, uint32_t (&w)[W]) {
+        if constexpr (W == 1) {
+            w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+        } else {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+            w[0] = u.x; w[1] = u.y;
+        }
+    }
+    static __device__ __forceinline__ void unpack(const uint32_t (&w)[W], float (&v)[C]) {
+        if constexpr (sizeof(T) == 2) {
+#pragma unroll
+            for (uint32_t i = 0; i < W; i++) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                v[2 * i] = f.x; v[2 * i + 1] = f.y;
+            }
+        } else {
+#pragma unroll
+            for (uint32_t i = 0; i < W; i++) v[i] = __uint_as_float(w[i]);
+        }
+    }
+};
+
+// Gathers the 2^D corner rows of one cell with paired loads.  issue(): all loads in flight; resolve(): rows as floats.
+template <typename T, uint32_t D, uint32_t C>
+struct CellGather {
+    using RP = RowPack<T, C>;
+    static constexpr uint32_t NP = 1u << (D - 1);
+    uint4 u[NP];
+    uint32_t w1[NP][RP::W];
+    uint32_t code;      // per pair 4 bits: position of row 0 / row 1 inside the 16-byte group (2 + 2); NP <= 8
+    uint32_t straddle;  // bit j: pair j does not fit one group, w1[j] holds row 1
+
+    // tl = base of the whole table (16-byte aligned, readable up to the next 16-byte boundary past its last row)
+    __device__ __forceinline__ void issue(const T* __restrict__ tl, const uint32_t gridtype, const bool align_corners, const LevelParams& lp,
+                                          const uint32_t (&pos_grid)[D]) {
+        code = 0;
+        straddle = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < NP; j++) {
+            uint32_t pg[D];
+            pg[0] = pos_grid[0];
+#pragma unroll
+            for (uint32_t d = 1; d < D; d++) pg[d] = pos_grid[d] + ((j >> (d - 1)) & 1u);
+            // absolute rows: 16-byte groups are aligned relative to the table base (level offsets need not be)
+            const uint32_t r0 = lp.offset + grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+            pg[0] = pos_grid[0] + 1;
+            const uint32_t r1 = lp.offset + grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+            u[j] = __ldg(reinterpret_cast<const uint4*>(tl + (size_t)(r0 & ~(RP::R16 - 1)) * C));
+            const bool far = (r0 ^ r1) >= RP::R16;
+            if (far) RP::load_row(tl + (size_t)r1 * C, w1[j]);
+            code |= ((r0 & (RP::R16 - 1)) | ((r1 & (RP::R16 - 1)) << 2)) << (4 * j);
+            straddle |= (far ? 1u : 0u) << j;
+        }
+    }
+    // val[idx][c], idx bit d = +1 in dimension d (same corner numbering as the reference)
+    __device__ __forceinline__ void resolve(float (&val)[1u << D][C]) const {
+#pragma unroll
+        for (uint32_t j = 0; j < NP; j++) {
+            uint32_t a[RP::W], b[RP::W];
+            RP::pick(u[j], (code >> (4 * j)) & 3u, a);
+            RP::pick(u[j], (code >> (4 * j + 2)) & 3u, b);
+            if ((straddle >> j) & 1u) {
+#pragma unroll
+                for (uint32_t i = 0; i < RP::W; i++) b[i] = w1[j][i];
+            }
+            RP::unpack(a, val[2 * j]);
+            RP::unpack(b, val[2 * j + 1]);
+        }
+    }
+};
+
+template <typename T, uint32_t D, uint32_t C, uint32_t G, bool DYDX>
+__global__ void __launch_bounds__(256) k_grid_forward_pair(const float* __restrict__ inputs, const T* __restrict__ table,
+                                                           const int* __restrict__ offsets, T* __restrict__ outputs,
+                                                           T* __restrict__ dy_dx, const uint32_t B, const uint32_t L,
+                                                           const float S, const uint32_t H, const uint32_t gridtype,
+                                                           const bool align_corners, const uint32_t interp, const int* __restrict__ b_dev) {
+    __shared__ LevelParams s_lp[kMaxLevels];
+    if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H);
+    __syncthreads();
+    const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;  // live rows
+    constexpr uint32_t NC = 1u << D;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < Bn; b += gridDim.x * blockDim.x) {
+        float x[D];
+        bool oob = false;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            x[d] = inputs[(size_t)b * D + d];
+            if (x[d] < 0 || x[d] > 1) oob = true;
+        }
+        T* out_row = outputs + (size_t)b * L * C;
+        T* dy_row = DYDX ? dy_dx + (size_t)b * L * D * C : nullptr;
+        for (uint32_t l0 = 0; l0 < L; l0 += G) {
+            float res[G][C];
+            float pos[G][D], deriv[G][D];
+            CellGather<T, D, C> cg[G];
+            if (!oob) {
+#pragma unroll
+                for (uint32_t g = 0; g < G; g++) {
+                    const LevelParams lp = s_lp[l0 + g];
+                    uint32_t pos_grid[D];
+                    locate<D>(x, lp, align_corners, interp, pos[g], deriv[g], pos_grid);
+                    cg[g].issue(table, gridtype, align_corners, lp, pos_grid);
+                }
+            }
+#pragma unroll
+            for (uint32_t g = 0; g < G; g++) {
+                float gres[D][C];
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) res[g][c] = 0.0f;
+#pragma unroll
+                for (uint32_t d = 0; d < D; d++)
+#pragma unroll
+                    for (uint32_t c = 0; c < C; c++) gres[d][c] = 0.0f;
+                if (!oob) {
+                    float val[NC][C];
+                    cg[g].resolve(val);
+#pragma unroll
+                    for (uint32_t idx = 0; idx < NC; idx++) {
+                        float w = 1;
+#pragma unroll
+                        for (uint32_t d = 0; d < D; d++) w *= ((idx >> d) & 1u) ? pos[g][d] : 1 - pos[g][d];
+#pragma unroll
+                        for (uint32_t c = 0; c < C; c++) res[g][c] += w * val[idx][c];
+                    }
+                    if constexpr (DYDX) {
+                        const float scale = s_lp[l0 + g].scale;
+#pragma unroll
+                        for (uint32_t gd = 0; gd < D; gd++) {
+#pragma unroll
+                            for (uint32_t idx = 0; idx < NC; idx++) {
+                                if ((idx >> gd) & 1u) continue;
+                                float w = scale;
+#pragma unroll
+                                for (uint32_t d = 0; d < D; d++)
+                                    if (d != gd) w *= ((idx >> d) & 1u) ? pos[g][d] : 1 - pos[g][d];
+#pragma unroll
+                                for (uint32_t c = 0; c < C; c++)
+                                    gres[gd][c] += w * (val[idx | (1u << gd)][c] - val[idx][c]) * deriv[g][gd];
+                            }
+                        }
+                    }
+                }
+                if constexpr (DYDX) {
+#pragma unroll
+                    for (uint32_t d = 0; d < D; d++) Row<T, C>::store(dy_row + ((size_t)(l0 + g) * D + d) * C, gres[d]);
+                }
+            }
+            if constexpr (G * C * sizeof(T) == 16) {
+                T packed[G * C];
+#pragma unroll
+                for (uint32_t g = 0; g < G; g++) Row<T, C>::store(packed + g * C, res[g]);
+                *reinterpret_cast<uint4*>(out_row + (size_t)l0 * C) = *reinterpret_cast<const uint4*>(packed);
+            } else {
+#pragma unroll
+                for (uint32_t g = 0; g < G; g++) Row<T, C>::store(out_row + (size_t)(l0 + g) * C, res[g]);
+            }
+        }
+    }
+}
+
 // =================================================================================================
 // backward
 // =================================================================================================
@@ -294,32 +483,34 @@ __device__ __forceinline__ bool warp_aggregate(const uint32_t key, float (&v)[C]
     return lane == (uint32_t)(__ffs(peers) - 1);
 }
 
-// grid = (point chunks, L).  TG = dtype of grad_table.
-template <typename T, typename TG, uint32_t D, uint32_t C, bool PRIV>
-__global__ void __launch_bounds__(256) k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
-                                                       const int* __restrict__ offsets, TG* __restrict__ grad_table,
-                                                       const uint32_t B, const uint32_t L, const float S, const uint32_t H,
-                                                       const uint32_t gridtype, const bool align_corners,
-                                                       const uint32_t interp, const uint32_t smem_rows_max,
-                                                       const uint32_t points_per_cta, const int* __restrict__ b_dev) {
-    extern __shared__ float s_acc[];  // [hashmap_size * C] when the level is privatised
-    const uint32_t level = blockIdx.y;
-    const LevelParams lp = make_level(offsets, level, S, H);
-    const bool privatised = lp.hashmap_size <= smem_rows_max;
-    if (privatised != PRIV) return;  // the other launch handles this level
-    constexpr uint32_t NC = 1u << D;
-    const uint32_t lane = threadIdx.x & 31u;
-
-    if (privatised) {
-        for (uint32_t i = threadIdx.x; i < lp.hashmap_size * C; i += blockDim.x) s_acc[i] = 0.0f;
-        __syncthreads();
-    }
-    TG* gl = grad_table + (size_t)lp.offset * C;
-
+// Scatter of the table gradient.  One CTA = (chunk of points, level), the level varying fastest over blockIdx.x so the CTAs
+// that re-read one chunk's grad rows run together (L2 hits).  Every corner contribution is a fire-and-forget vector reduction
+// (red.global.add.v2.f32); the two corners that differ in dimension 0 go out as ONE red.global.add.v4.f32 when they are the two
+// halves of an aligned 16-byte group (rows r, r ^ 1: every dense-level cell with even r, every hashed cell with even x).
+// The `agg_levels` coarsest levels sum the lanes of a warp that hit the same row first (match.any): consecutive samples of a ray
+// share coarse cells.  found_inf (optional): set to 1.0f's bit pattern when a consumed grad element is inf/nan — the table
+// gradient is non-finite exactly when one of them is (weights are in [0,1], the sums are fp32), so the optimiser's overflow
+// check does not have to re-read the whole table gradient.
+template <typename T, typename TG, uint32_t D, uint32_t C, bool V4>
+__global__ void __launch_bounds__(256) k_grid_scatter(const T* __restrict__ grad, const float* __restrict__ inputs,
+                                                      const int* __restrict__ offsets, TG* __restrict__ grad_table,
+                                                      const uint32_t B, const uint32_t L, const float S, const uint32_t H,
+                                                      const uint32_t gridtype, const bool align_corners, const uint32_t interp,
+                                                      const uint32_t points_per_cta, const uint32_t agg_levels,
+                                                      const int* __restrict__ b_dev, int* __restrict__ found_inf) {
+    const uint32_t level = blockIdx.x % L;
+    const uint32_t chunk = blockIdx.x / L;
     const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;  // live rows
-    const uint32_t b_begin = blockIdx.x * points_per_cta;
+    const uint32_t b_begin = chunk * points_per_cta;
     const uint32_t b_end = min(Bn, b_begin + points_per_cta);
     if (b_begin >= b_end) return;
+    const LevelParams lp = make_level(offsets, level, S, H);
+    const bool agg = level < agg_levels;
+    constexpr uint32_t NP = 1u << (D - 1);
+    const uint32_t lane = threadIdx.x & 31u;
+    TG* gl = grad_table + (size_t)lp.offset * C;
+    bool bad = false;
+
     // all lanes of a warp iterate together (warp_aggregate needs the full warp)
     for (uint32_t b0 = b_begin + (threadIdx.x & ~31u); b0 < b_end; b0 += blockDim.x) {
         const uint32_t b = b0 + lane;
@@ -331,55 +522,63 @@ __global__ void __launch_bounds__(256) k_grid_backward(const T* __restrict__ gra
             if (x[d] < 0 || x[d] > 1) valid = false;  // gridencoder.cu:276-281
         }
         float g[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) g[c] = 0.0f;
         if (valid) {
             Row<T, C>::load(grad + ((size_t)b * L + level) * C, g);
-        } else {
 #pragma unroll
-            for (uint32_t c = 0; c < C; c++) g[c] = 0.0f;
+            for (uint32_t c = 0; c < C; c++) bad |= !isfinite(g[c]);
         }
         float pos[D], deriv[D];
         uint32_t pos_grid[D];
         locate<D>(x, lp, align_corners, interp, pos, deriv, pos_grid);
 #pragma unroll
-        for (uint32_t idx = 0; idx < NC; idx++) {
-            float w = 1;
+        for (uint32_t j = 0; j < NP; j++) {
             uint32_t pg[D];
+            pg[0] = pos_grid[0];
 #pragma unroll
-            for (uint32_t d = 0; d < D; d++) {
-                w *= ((idx >> d) & 1u) ? pos[d] : 1 - pos[d];
-                pg[d] = pos_grid[d] + ((idx >> d) & 1u);
+            for (uint32_t d = 1; d < D; d++) pg[d] = pos_grid[d] + ((j >> (d - 1)) & 1u);
+            const uint32_t r0 = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+            pg[0] = pos_grid[0] + 1;
+            const uint32_t r1 = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+            // same product order as the reference (w = 1 * w_0 * w_1 * ...)
+            float w0 = 1 - pos[0], w1 = pos[0];
+#pragma unroll
+            for (uint32_t d = 1; d < D; d++) {
+                const float f = ((j >> (d - 1)) & 1u) ? pos[d] : 1 - pos[d];
+                w0 *= f; w1 *= f;
             }
-            const uint32_t row = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
-            float wv[C];
+            float a0[C], a1[C];
 #pragma unroll
-            for (uint32_t c = 0; c < C; c++) wv[c] = w * g[c];
-            // lanes of a warp that hit the same row (consecutive samples of a ray share coarse cells) are summed first
-            const uint32_t key = valid ? row : (0xffffffffu - lane);
-            const bool leader = warp_aggregate<C>(key, wv, lane);
-            if (valid && leader) {
-                if (privatised) {
-#pragma unroll
-                    for (uint32_t c = 0; c < C; c++) atomicAdd(&s_acc[row * C + c], wv[c]);
+            for (uint32_t c = 0; c < C; c++) { a0[c] = w0 * g[c]; a1[c] = w1 * g[c]; }
+            if (agg) {
+                const bool lead0 = warp_aggregate<C>(valid ? r0 : (0xffffffffu - lane), a0, lane);
+                if (valid && lead0) VecAtomic<TG, C>::add(gl + (size_t)r0 * C, a0);
+                const bool lead1 = warp_aggregate<C>(valid ? r1 : (0xffffffffu - lane), a1, lane);
+                if (valid && lead1) VecAtomic<TG, C>::add(gl + (size_t)r1 * C, a1);
+            } else if (valid) {
+                if constexpr (V4) {  // TG = float, C = 2, 16-byte aligned table
+                    const uint32_t ra0 = lp.offset + r0, ra1 = lp.offset + r1;
+                    if ((ra0 ^ ra1) == 1u) {
+                        const bool odd = ra0 & 1u;
+                        const float4 v = odd ? make_float4(a1[0], a1[1], a0[0], a0[1]) : make_float4(a0[0], a0[1], a1[0], a1[1]);
+                        atomicAdd(reinterpret_cast<float4*>(grad_table + (size_t)(ra0 & ~1u) * C), v);  // red.global.add.v4.f32
+                    } else {
+                        VecAtomic<TG, C>::add(gl + (size_t)r0 * C, a0);
+                        VecAtomic<TG, C>::add(gl + (size_t)r1 * C, a1);
+                    }
                 } else {
-                    VecAtomic<TG, C>::add(gl + (size_t)row * C, wv);
+                    VecAtomic<TG, C>::add(gl + (size_t)r0 * C, a0);
+                    VecAtomic<TG, C>::add(gl + (size_t)r1 * C, a1);
                 }
             }
         }
     }
-    if (privatised) {
-        __syncthreads();
-        for (uint32_t r = threadIdx.x; r < lp.hashmap_size; r += blockDim.x) {
-            float v[C];
-            bool nz = false;
-#pragma unroll
-            for (uint32_t c = 0; c < C; c++) { v[c] = s_acc[r * C + c]; nz |= (v[c] != 0.0f); }
-            if (nz) VecAtomic<TG, C>::add(gl + (size_t)r * C, v);
-        }
-    }
+    if (found_inf && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(found_inf, 0x3f800000);
 }
 
 // grad_x[b, d] = sum_{l,c} grad[b,l,c] * d out[b,l,c] / d x[b,d]; recomputed from the table (fp32 accumulate)
-template <typename T, uint32_t D, uint32_t C>
+template <typename T, uint32_t D, uint32_t C, bool PAIR>
 __global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* __restrict__ grad, const float* __restrict__ inputs,
                                                                        const T* __restrict__ table, const int* __restrict__ offsets,
                                                                        float* __restrict__ grad_x, const uint32_t B, const uint32_t L,
@@ -409,15 +608,21 @@ __global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* 
                 float pos[D], deriv[D];
                 uint32_t pos_grid[D];
                 locate<D>(x, lp, align_corners, interp, pos, deriv, pos_grid);
-                const T* tl = table + (size_t)lp.offset * C;
                 float val[NC][C];
+                if constexpr (PAIR) {
+                    CellGather<T, D, C> cg;
+                    cg.issue(table, gridtype, align_corners, lp, pos_grid);
+                    cg.resolve(val);
+                } else {
+                    const T* tl = table + (size_t)lp.offset * C;
 #pragma unroll
-                for (uint32_t idx = 0; idx < NC; idx++) {
-                    uint32_t pg[D];
+                    for (uint32_t idx = 0; idx < NC; idx++) {
+                        uint32_t pg[D];
 #pragma unroll
-                    for (uint32_t d = 0; d < D; d++) pg[d] = pos_grid[d] + ((idx >> d) & 1u);
-                    const uint32_t row = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
-                    Row<T, C>::load(tl + (size_t)row * C, val[idx]);
+                        for (uint32_t d = 0; d < D; d++) pg[d] = pos_grid[d] + ((idx >> d) & 1u);
+                        const uint32_t row = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+                        Row<T, C>::load(tl + (size_t)row * C, val[idx]);
+                    }
                 }
                 float g[C];
                 Row<T, C>::load(grad + ((size_t)b * L + l) * C, g);
@@ -500,6 +705,13 @@ int launch_forward(const float* x, const void* table, const int* offsets, void* 
     const uint32_t blocks = div_up(B, threads);
     if constexpr (G > 1) {
         const bool vec_ok = (L % G) == 0 && ((L * C * sizeof(T)) % 16 == 0) && ((uintptr_t)out % 16 == 0);
+        if constexpr (RowPack<T, C>::ok && D >= 2 && D <= 4) {
+            if (vec_ok && ((uintptr_t)table % 16 == 0)) {
+                if (dy_dx) k_grid_forward_pair<T, D, C, G, true><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp, b_dev);
+                else k_grid_forward_pair<T, D, C, G, false><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp, b_dev);
+                return launch_status();
+            }
+        }
         if (vec_ok) {
             if (dy_dx) k_grid_forward<T, D, C, G, true><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp, b_dev);
             else k_grid_forward<T, D, C, G, false><<<blocks, threads, 0, st>>>(x, (const T*)table, offsets, (T*)out, (T*)dy_dx, B, L, S, H, gridtype, align, interp, b_dev);
@@ -535,62 +747,77 @@ int dispatch_forward_D(uint32_t D, uint32_t C, const float* x, const void* table
     }
 }
 
-constexpr uint32_t kBwdSmemBytes = 160 * 1024;  // privatised accumulator budget per CTA
+// Number of coarse levels whose contributions are summed inside the warp before the reduction goes out: levels whose cells are
+// large against the sample spacing of a marched ray (resolution <= 128: a ray at dt = 2*sqrt(3)/1024 puts >= 2 consecutive
+// samples in a cell).  Uniformly random point sets (the encoder benchmark) gain nothing from it; SEALD_GRID_AGG_LEVELS overrides.
+inline uint32_t default_agg_levels(uint32_t B, uint32_t L, float S, uint32_t H) {
+    static int env = -2;
+    if (env == -2) {
+        const char* e = getenv("SEALD_GRID_AGG_LEVELS");
+        env = e ? atoi(e) : -1;
+    }
+    if (env >= 0) return (uint32_t)env;
+    if (B >= (1u << 18)) return 0;
+    uint32_t n = 0;
+    for (uint32_t l = 0; l < L; l++)
+        if (exp2f(l * S) * H <= 128.0f) n = l + 1;
+    return n;
+}
 
+template <typename T, typename TG, uint32_t D, uint32_t C>
+int launch_scatter(const void* grad, const float* x, const int* offsets, void* grad_table, uint32_t B, uint32_t L, float S, uint32_t H,
+                   uint32_t gridtype, bool align, uint32_t interp, const int* b_dev, int* found_inf, cudaStream_t st) {
+    const uint32_t ppc = 1024;
+    const uint32_t grid = div_up(B, ppc) * L;
+    const uint32_t agg = default_agg_levels(B, L, S, H);
+    if constexpr (std::is_same<TG, float>::value && C == 2) {
+        if ((uintptr_t)grad_table % 16 == 0) {
+            k_grid_scatter<T, TG, D, C, true><<<grid, 256, 0, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, ppc, agg, b_dev, found_inf);
+            return launch_status();
+        }
+    }
+    k_grid_scatter<T, TG, D, C, false><<<grid, 256, 0, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, ppc, agg, b_dev, found_inf);
+    return launch_status();
+}
+
+template <typename T, uint32_t D, uint32_t C>
+int launch_input_backward(const void* grad, const float* x, const void* table, const int* offsets, const void* dy_dx, float* grad_x, uint32_t B,
+                          uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align, uint32_t interp, const int* b_dev, cudaStream_t st) {
+    if (dy_dx) {
+        k_grid_input_backward_dydx<T, D, C><<<div_up(B * D, 256u), 256, 0, st>>>((const T*)grad, (const T*)dy_dx, grad_x, B, L, b_dev);
+        return launch_status();
+    }
+    if constexpr (RowPack<T, C>::ok && D >= 2 && D <= 4) {
+        if ((uintptr_t)table % 16 == 0) {
+            k_grid_input_backward_recompute<T, D, C, true><<<div_up(B, 256u), 256, 0, st>>>((const T*)grad, x, (const T*)table, offsets, grad_x, B, L, S, H, gridtype, align, interp, b_dev);
+            return launch_status();
+        }
+    }
+    k_grid_input_backward_recompute<T, D, C, false><<<div_up(B, 256u), 256, 0, st>>>((const T*)grad, x, (const T*)table, offsets, grad_x, B, L, S, H, gridtype, align, interp, b_dev);
+    return launch_status();
+}
+
+// grad_table == nullptr: input gradient only; grad_x == nullptr: table gradient only
 template <typename T, typename TG, uint32_t D, uint32_t C>
 int launch_backward(const void* grad, const float* x, const void* table, const int* offsets, void* grad_table, const void* dy_dx,
                     float* grad_x, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align, uint32_t interp,
-                    const int* b_dev, cudaStream_t st) {
-    auto kern = k_grid_backward<T, TG, D, C, true>;
-    auto kern_direct = k_grid_backward<T, TG, D, C, false>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    // Shared-memory privatisation of the small (coarse) levels only pays when many points hit each cell (large batches,
-    // e.g. the 2^22-point encoder benchmark); for a training batch every level uses warp-aggregated global atomics.
-    const bool use_priv = B >= (1u << 18);
-    const uint32_t smem_rows_max = use_priv ? kBwdSmemBytes / (C * sizeof(float)) : 0u;
+                    const int* b_dev, int* found_inf, cudaStream_t st) {
     int rc = 0;
-    if (use_priv) {
-        // chunks: enough CTAs per level to fill the machine ~2x over all levels, but large enough to amortise the flush
-        uint32_t chunks = div_up(2u * SEALD_NUM_SMS, L);
-        uint32_t ppc = div_up(B, chunks);
-        ppc = div_up(ppc < 2048u ? 2048u : ppc, 256u) * 256u;
-        chunks = div_up(B, ppc);
-        dim3 grid(chunks, L);
-        kern<<<grid, 256, kBwdSmemBytes, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, smem_rows_max, ppc, b_dev);
-        rc = launch_status();
-        if (rc) return rc;
-    }
-    // direct (warp-aggregated atomics) levels: small chunks, no shared memory, full occupancy
-    const uint32_t ppc_d = 1024;
-    dim3 grid_d(div_up(B, ppc_d), L);
-    kern_direct<<<grid_d, 256, 0, st>>>((const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, smem_rows_max, ppc_d, b_dev);
-    rc = launch_status();
+    if (grad_table) rc = launch_scatter<T, TG, D, C>(grad, x, offsets, grad_table, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
     if (rc) return rc;
-    if (grad_x) {
-        if (dy_dx) {
-            k_grid_input_backward_dydx<T, D, C><<<div_up(B * D, 256u), 256, 0, st>>>((const T*)grad, (const T*)dy_dx, grad_x, B, L, b_dev);
-        } else {
-            k_grid_input_backward_recompute<T, D, C><<<div_up(B, 256u), 256, 0, st>>>((const T*)grad, x, (const T*)table, offsets, grad_x, B, L, S, H, gridtype, align, interp, b_dev);
-        }
-        rc = launch_status();
-    }
+    if (grad_x) rc = launch_input_backward<T, D, C>(grad, x, table, offsets, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
     return rc;
 }
 
 template <typename T, typename TG, uint32_t D>
 int dispatch_backward_C(uint32_t C, const void* grad, const float* x, const void* table, const int* offsets, void* grad_table,
                         const void* dy_dx, float* grad_x, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align,
-                        uint32_t interp, const int* b_dev, cudaStream_t st) {
+                        uint32_t interp, const int* b_dev, int* found_inf, cudaStream_t st) {
     switch (C) {
-        case 1: return launch_backward<T, TG, D, 1>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
-        case 2: return launch_backward<T, TG, D, 2>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
-        case 4: return launch_backward<T, TG, D, 4>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
-        case 8: return launch_backward<T, TG, D, 8>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 1: return launch_backward<T, TG, D, 1>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
+        case 2: return launch_backward<T, TG, D, 2>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
+        case 4: return launch_backward<T, TG, D, 4>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
+        case 8: return launch_backward<T, TG, D, 8>(grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
         default: return SEALD_E_UNSUPPORTED;
     }
 }
@@ -598,12 +825,12 @@ int dispatch_backward_C(uint32_t C, const void* grad, const float* x, const void
 template <typename T, typename TG>
 int dispatch_backward_D(uint32_t D, uint32_t C, const void* grad, const float* x, const void* table, const int* offsets, void* grad_table,
                         const void* dy_dx, float* grad_x, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align,
-                        uint32_t interp, const int* b_dev, cudaStream_t st) {
+                        uint32_t interp, const int* b_dev, int* found_inf, cudaStream_t st) {
     switch (D) {
-        case 2: return dispatch_backward_C<T, TG, 2>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
-        case 3: return dispatch_backward_C<T, TG, 3>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
-        case 4: return dispatch_backward_C<T, TG, 4>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
-        case 5: return dispatch_backward_C<T, TG, 5>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
+        case 2: return dispatch_backward_C<T, TG, 2>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
+        case 3: return dispatch_backward_C<T, TG, 3>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
+        case 4: return dispatch_backward_C<T, TG, 4>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
+        case 5: return dispatch_backward_C<T, TG, 5>(C, grad, x, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
         default: return SEALD_E_UNSUPPORTED;
     }
 }
@@ -624,23 +851,50 @@ extern "C" int seald_grid_encode_forward(const float* x01, const void* table, co
     return SEALD_E_UNSUPPORTED;
 }
 
-extern "C" int seald_grid_encode_backward(const void* grad_out, const float* x01, const void* table, const int32_t* offsets,
-                                          void* grad_table, const void* dy_dx, float* grad_x, uint32_t B, uint32_t D, uint32_t C,
-                                          uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp,
-                                          int dtype, int grad_table_dtype, const int32_t* b_dev, seald_stream_t stream) {
+static int grid_backward_any(const void* grad_out, const float* x01, const void* table, const int32_t* offsets, void* grad_table,
+                             const void* dy_dx, float* grad_x, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                             uint32_t gridtype, int align_corners, uint32_t interp, int dtype, int grad_table_dtype, const int32_t* b_dev,
+                             int32_t* found_inf, seald_stream_t stream) {
     if (B == 0) return 0;
-    if (!grad_out || !x01 || !offsets || !grad_table) return SEALD_E_BADARG;
+    if (!grad_out || !x01 || !offsets || (!grad_table && !grad_x)) return SEALD_E_BADARG;
     if (grad_x && !dy_dx && !table) return SEALD_E_BADARG;
     if (L == 0 || L > kMaxLevels || gridtype > 1 || interp > 1) return SEALD_E_UNSUPPORTED;
     cudaStream_t st = to_stream(stream);
     const bool al = align_corners != 0;
     if (dtype == SEALD_F16 && grad_table_dtype == SEALD_F16)
-        return dispatch_backward_D<__half, __half>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, st);
+        return dispatch_backward_D<__half, __half>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, found_inf, st);
     if (dtype == SEALD_F16 && grad_table_dtype == SEALD_F32)
-        return dispatch_backward_D<__half, float>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, st);
+        return dispatch_backward_D<__half, float>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, found_inf, st);
     if (dtype == SEALD_F32 && grad_table_dtype == SEALD_F32)
-        return dispatch_backward_D<float, float>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, st);
+        return dispatch_backward_D<float, float>(D, C, grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, L, S, H, gridtype, al, interp, b_dev, found_inf, st);
     return SEALD_E_UNSUPPORTED;
+}
+
+extern "C" int seald_grid_encode_backward(const void* grad_out, const float* x01, const void* table, const int32_t* offsets,
+                                          void* grad_table, const void* dy_dx, float* grad_x, uint32_t B, uint32_t D, uint32_t C,
+                                          uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp,
+                                          int dtype, int grad_table_dtype, const int32_t* b_dev, seald_stream_t stream) {
+    if (!grad_table) return SEALD_E_BADARG;
+    return grid_backward_any(grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, D, C, L, S, H, gridtype, align_corners, interp, dtype,
+                             grad_table_dtype, b_dev, nullptr, stream);
+}
+
+extern "C" int seald_grid_encode_backward_table(const void* grad_out, const float* x01, const int32_t* offsets, void* grad_table, uint32_t B,
+                                                uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                                uint32_t interp, int dtype, int grad_table_dtype, const int32_t* b_dev, int32_t* found_inf,
+                                                seald_stream_t stream) {
+    if (!grad_table) return SEALD_E_BADARG;
+    return grid_backward_any(grad_out, x01, nullptr, offsets, grad_table, nullptr, nullptr, B, D, C, L, S, H, gridtype, align_corners, interp,
+                             dtype, grad_table_dtype, b_dev, found_inf, stream);
+}
+
+extern "C" int seald_grid_encode_backward_input(const void* grad_out, const float* x01, const void* table, const int32_t* offsets,
+                                                const void* dy_dx, float* grad_x, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                                uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                                                const int32_t* b_dev, seald_stream_t stream) {
+    if (!grad_x) return SEALD_E_BADARG;
+    return grid_backward_any(grad_out, x01, table, offsets, nullptr, dy_dx, grad_x, B, D, C, L, S, H, gridtype, align_corners, interp, dtype,
+                             dtype == SEALD_F16 ? SEALD_F16 : SEALD_F32, b_dev, nullptr, stream);
 }
 
 extern "C" int seald_grid_debug_indices(const float* x01, const int32_t* offsets, uint32_t* indices, float* scales, uint32_t* resolutions,

@@ -67,7 +67,8 @@ __global__ void k_cast_pad_f16_batch(const CastSegs segs) {
     sg.dst[j] = __float2half_rn(c < sg.cols ? sg.src[(size_t)r * sg.cols + c] : 0.0f);
 }
 
-// found_inf[0] = 1 if any gradient is inf/nan
+// found_inf[0] |= bits of 1.0f if any gradient is inf/nan (non-zero as an int AND a positive float: the flag is summed over the
+// ranks by a float all-reduce)
 __global__ void k_grad_finite_check(const float* __restrict__ g, const size_t n, int* __restrict__ found_inf) {
     bool bad = false;
     const size_t n4 = n / 4;
@@ -77,7 +78,7 @@ __global__ void k_grad_finite_check(const float* __restrict__ g, const size_t n,
         bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
     }
     for (size_t i = n4 * 4 + threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n; i += (size_t)gridDim.x * blockDim.x) bad |= !isfinite(g[i]);
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(found_inf, 1);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(found_inf, 0x3f800000);
 }
 
 // torch.optim.Adam (no amsgrad / weight decay) on a flat fp32 slab, gradients un-scaled by 1 / *loss_scale, the whole

@@ -25,7 +25,7 @@ from ._lib import ptr
 class FusedTrainer:
     def __init__(self, model, num_rays=4096, max_samples=None, lr=1e-2, lr_net=None, betas=(0.9, 0.99), eps=1e-15, dt_gamma=0.0,
                  max_steps=1024, T_thresh=1e-4, perturb=True, init_loss_scale=65536.0, growth_interval=2000, train_deform=True,
-                 use_graph=True, world_size=1, process_group=None, device=None, fuse_composite=True):
+                 use_graph=True, world_size=1, process_group=None, device=None, fuse_composite=True, shard_optimizer=True):
         self.model = model
         self.device = device or model.encoder.embeddings.device
         if self.device.type != "cuda":
@@ -54,17 +54,28 @@ class FusedTrainer:
         self.n_table = table.numel()
         sizes = [w.numel() for w in weights]
         self.n_weights = sum(sizes)
-        n = self.n_table + self.n_weights
-        n_pad = (n + 3) // 4 * 4
+        # data parallel with a sharded optimiser ("zero1"): the table region is padded to world_size equal shards of a multiple of
+        # 8 elements; rank r owns elements [r * shard_len, (r + 1) * shard_len)
+        W = self.world_size
+        self.shard_optimizer = bool(shard_optimizer) and W > 1
+        self.rank = torch.distributed.get_rank(self.pg) if W > 1 else 0
+        self.shard_len = ((self.n_table + W - 1) // W + 7) // 8 * 8 if self.shard_optimizer else 0
+        self.n_table_pad = self.shard_len * W if self.shard_optimizer else (self.n_table + 3) // 4 * 4
+        n = self.n_table_pad + self.n_weights
+        # flat buffers: [table (padded) | MLP weights | pad | overflow flag (4 floats)].  The flag lives INSIDE the gradient buffer so the
+        # all-reduce that sums the MLP gradients also tells every rank whether any rank overflowed (GradScaler's found_inf).
+        self.n_flag = (n + 3) // 4 * 4
+        n_pad = self.n_flag + 4
         self.params = torch.zeros(n_pad, **f32)
         self.grads = torch.zeros(n_pad, **f32)
         self.exp_avg = torch.zeros(n_pad, **f32)
         self.exp_avg_sq = torch.zeros(n_pad, **f32)
         self.n_params = n
+        self.n_real_params = self.n_table + self.n_weights
         with torch.no_grad():
             self.params[:self.n_table].copy_(table.data.reshape(-1))
             table.data = self.params[:self.n_table].view_as(table)
-            o = self.n_table
+            o = self.n_table_pad
             self.weight_views, self.grad_views = [], []
             for w, k in zip(weights, sizes):
                 self.params[o:o + k].copy_(w.data.reshape(-1))
@@ -73,8 +84,14 @@ class FusedTrainer:
                 self.grad_views.append(self.grads[o:o + k].view_as(w))
                 o += k
         self.grad_table = self.grads[:self.n_table].view_as(table)
-        self.table16 = torch.empty(table.shape, dtype=torch.float16, device=dev)
+        self.table16_pad = torch.zeros(self.n_table_pad, dtype=torch.float16, device=dev)
+        self.table16 = self.table16_pad[:self.n_table].view(table.shape)
         self.table16.copy_(table.data)
+        if self.shard_optimizer:
+            self.grad_shard = torch.zeros(self.shard_len, **f32)               # this rank's slice of the summed table gradient
+            self.shard16 = torch.zeros(self.shard_len, dtype=torch.float16, device=dev)  # ... and of the refreshed fp16 table
+            self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
+        self._side = torch.cuda.Stream(device=dev)
         self.hw = F.HalfWeights(self.cfg, dev)
         self.hw.refresh(self.weight_views)
 
@@ -110,7 +127,7 @@ class FusedTrainer:
         self.ws = F.FieldWorkspace(self.cfg, M, dev, training=True)
         self.jobs, self.n_jobs = F.wgrad_jobs(self.cfg, self.ws, self.grad_views, deform=self.train_deform)
         self.loss_scale = torch.full((1,), float(init_loss_scale), **f32)
-        self.found_inf = torch.zeros(1, **i32)
+        self.found_inf = self.grads[self.n_flag:self.n_flag + 1].view(torch.int32)  # 0 or the bits of a positive float
         self.growth_tracker = torch.zeros(1, **i32)
         self.step_dev = torch.zeros(1, **i32)  # optimiser step counter (device side: the optimiser is graph-replayed)
         # pinned staging for the end-to-end path
@@ -119,8 +136,7 @@ class FusedTrainer:
         self.h_gt = torch.zeros(N, 3).pin_memory()
         self.h_time = torch.zeros(1).pin_memory()
         self.h_loss = torch.zeros(1).pin_memory()
-        self._g_fwd_bwd = None
-        self._g_opt = None
+        self._graph = None
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------------------------
@@ -220,10 +236,16 @@ class FusedTrainer:
                       hw.p_color, cfg.n_color, M, ptr(m_dev), cfg.density_scale, ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.bwd_s), ptr(ws.bwd_c),
                       ptr(ws.gout_s), ptr(ws.gout_c), ptr(ws.dfeat), _lib.stream())
 
-        def grid_bwd():
-            _lib.call("seald_grid_encode_backward", ptr(ws.dfeat), ptr(ws.x01), ptr(self.table16), ptr(offsets), ptr(self.grad_table), None,
-                      ptr(ws.grad_x01) if self.train_deform else None, M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base,
-                      cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, F32, ptr(m_dev), _lib.stream())
+        def grid_scatter():
+            # table gradient; also raises the overflow flag when dfeat holds an inf/nan (== the table gradient would)
+            _lib.call("seald_grid_encode_backward_table", ptr(ws.dfeat), ptr(ws.x01), ptr(offsets), ptr(self.grad_table), M, 3, cfg.grid_dim,
+                      cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, F32, ptr(m_dev),
+                      ptr(self.found_inf), _lib.stream())
+
+        def grid_input_bwd():
+            _lib.call("seald_grid_encode_backward_input", ptr(ws.dfeat), ptr(ws.x01), ptr(self.table16), ptr(offsets), None, ptr(ws.grad_x01),
+                      M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16,
+                      ptr(m_dev), _lib.stream())
 
         def deform_bwd():
             F.deform_backward(cfg, hw, ws.grad_x01, self.time, M, m_dev, ws.fwd_d, ws.bwd_d, ws.gout_d)
@@ -243,115 +265,171 @@ class FusedTrainer:
         else:
             tail = [("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3)]
         stages = [("select_frame", select_frame, 2), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
-                  ("heads_fwd", heads_fwd, 1)] + tail + [("heads_bwd", heads_bwd, 1), ("grid_bwd", grid_bwd, 3 if self.train_deform else 2)]
+                  ("heads_fwd", heads_fwd, 1)] + tail + [("heads_bwd", heads_bwd, 1), ("grid_scatter", grid_scatter, 1)]
         if self.train_deform:
-            stages.append(("deform_bwd", deform_bwd, 1))
+            stages += [("grid_input_bwd", grid_input_bwd, 1), ("deform_bwd", deform_bwd, 1)]
         stages.append(("wgrad", wgrad, 1))
         return stages
 
+    # ------------------------------------------------------------------------------------------------------------
+    # The step body.  ONE function describes the step for 1 GPU, data parallel with a flat all-reduce, and data parallel with a
+    # sharded optimiser; it is either run eagerly or captured — collectives included — into ONE CUDA graph.  Two streams:
+    #
+    #   main : [select frame, march, deformation forward] . grid forward .. heads backward | input grad, deform backward, wgrad, check | Adam
+    #   side : [all-gather fp16 table (sharded)]                                           | table scatter, reduce-scatter / all-reduce |
+    #
+    # The table scatter (atomic/latency bound) runs beside the tensor-core backward of the deformation net; with a sharded
+    # optimiser the reduce-scatter of the table gradient hides behind the same kernels and the all-gather of the refreshed
+    # fp16 table behind the NEXT step's march + deformation forward, which do not read the table.
+    def _step_body(self):
+        S = {name: (fn, k) for name, fn, k in self._stages()}
+        n = [0]
+
+        def run(*names):
+            for nm in names:
+                if nm in S:
+                    S[nm][0]()
+                    n[0] += S[nm][1]
+
+        dist = torch.distributed
+        W, sharded = self.world_size, self.shard_optimizer
+        main, side = torch.cuda.current_stream(), self._side
+        ntp = self.n_table_pad
+        if sharded:  # last step's refreshed table shards (a no-op exchange before the first step)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
+        run("select_frame", "march", "deform_fwd")
+        if sharded:
+            main.wait_stream(side)
+        run("grid_fwd", "heads_fwd", "composite_fwd", "loss", "composite_bwd", "composite_loss_fused", "heads_bwd")
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            run("grid_scatter")
+            if sharded:
+                dist.reduce_scatter_tensor(self.grad_shard, self.grads[:ntp], op=dist.ReduceOp.SUM, group=self.pg)
+                self.grads[:ntp].zero_()  # consumed; the Adam kernel only sees the shard
+            elif W > 1:
+                dist.all_reduce(self.grads[:ntp], op=dist.ReduceOp.SUM, group=self.pg)
+        run("grid_input_bwd", "deform_bwd", "wgrad")
+        st = _lib.stream()
+        _lib.call("seald_grad_finite_check", self.grads.data_ptr() + 4 * ntp, self.n_weights, ptr(self.found_inf), st)
+        n[0] += 1
+        main.wait_stream(side)  # (also orders the overflow flag written by the scatter before it is exchanged)
+        if W > 1:  # MLP gradients + the overflow flag (a float: > 0 on every rank if any rank overflowed)
+            dist.all_reduce(self.grads[ntp:], op=dist.ReduceOp.SUM, group=self.pg)
+        n[0] += self._optimizer()
+        return n[0]
+
     def _forward_backward(self):
+        """Every stage of the forward + backward pass in order on the current stream (no optimiser, no exchange): tests / debugging."""
         n = 0
         for _, fn, k in self._stages():
             fn()
             n += k
         return n
 
-    def stage_timings(self, reps=20):
-        """Average device time (ms) of every stage, each timed alone with CUDA events on the current stream.
-        Uses the inputs currently staged; gradients accumulated here are discarded (the gradient buffer is re-zeroed)."""
-        out = {}
-        stages = self._stages() + [("optimizer", self._optimizer, 0)]
-        snapshot = (self.params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.loss_scale.clone(), self.growth_tracker.clone(),
-                    self.table16.clone(), self.hw.flat.clone(), self.step_dev.clone())
-        # one full pass so every stage sees valid inputs
-        for _, fn, _k in stages[:-1]:
-            fn()
-        for name, fn, _k in stages:
-            if name == "select_frame":
-                fn()
-                continue
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                if name == "march":
-                    self.counter.zero_()
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            out[name] = e0.elapsed_time(e1) / reps
-        for dst, src in zip((self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16, self.hw.flat,
-                             self.step_dev), snapshot):
-            dst.copy_(src)
-        self.grads.zero_()
-        self.found_inf.zero_()
-        out["live_samples"] = int(self.counter[0].item())
-        return out
+    def _allreduce(self):
+        """Flat all-reduce of the whole gradient buffer, overflow flag included (the unsharded data-parallel exchange, in one piece)."""
+        if self.world_size > 1:
+            parallel.allreduce_flat_grads(self.grads, self.pg)
 
     def _optimizer(self):
+        """GradScaler.step + optimizer.step + GradScaler.update as device kernels (nerf/utils.py:884-886): the whole update is
+        skipped when the overflow flag is set, the loss scale backs off / grows, the fp16 copies are refreshed."""
         st = _lib.stream()
         b1, b2 = self.betas
-        _lib.call("seald_grad_finite_check", ptr(self.grads), self.n_params, ptr(self.found_inf), st)
-        nt = self.n_table
-        _lib.call("seald_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), nt, self.lr, b1, b2, self.eps,
-                  1, ptr(self.step_dev), ptr(self.loss_scale), ptr(self.found_inf), ptr(self.table16), 1, st)
-        _lib.call("seald_adam_step", self.params.data_ptr() + 4 * nt, self.grads.data_ptr() + 4 * nt, self.exp_avg.data_ptr() + 4 * nt,
-                  self.exp_avg_sq.data_ptr() + 4 * nt, self.n_weights, self.lr_net, b1, b2, self.eps, 1, ptr(self.step_dev),
+        ntp = self.n_table_pad
+        if self.shard_optimizer:
+            off = self.rank * self.shard_len
+            _lib.call("seald_adam_step", self.params.data_ptr() + 4 * off, ptr(self.grad_shard), self.exp_avg.data_ptr() + 4 * off,
+                      self.exp_avg_sq.data_ptr() + 4 * off, self.shard_len, self.lr, b1, b2, self.eps, 1, ptr(self.step_dev), ptr(self.loss_scale),
+                      ptr(self.found_inf), ptr(self.shard16), 0, st)
+        else:
+            _lib.call("seald_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ntp, self.lr, b1, b2, self.eps,
+                      1, ptr(self.step_dev), ptr(self.loss_scale), ptr(self.found_inf), ptr(self.table16_pad), 1, st)
+        _lib.call("seald_adam_step", self.params.data_ptr() + 4 * ntp, self.grads.data_ptr() + 4 * ntp, self.exp_avg.data_ptr() + 4 * ntp,
+                  self.exp_avg_sq.data_ptr() + 4 * ntp, self.n_weights, self.lr_net, b1, b2, self.eps, 1, ptr(self.step_dev),
                   ptr(self.loss_scale), ptr(self.found_inf), None, 1, st)
         self.hw.refresh(self.weight_views)
         _lib.call("seald_loss_scale_update", ptr(self.loss_scale), ptr(self.found_inf), ptr(self.growth_tracker), 2.0, 0.5,
                   self.growth_interval, ptr(self.step_dev), st)
-        return 6
+        return 5
 
-    def _allreduce(self):
-        if self.world_size > 1:
-            parallel.allreduce_flat_grads(self.grads, self.pg)
+    def _state(self):
+        return (self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16_pad, self.hw.flat, self.step_dev)
+
+    def stage_timings(self, reps=20):
+        """Average device time (ms) of every stage, each timed alone with CUDA events on the current stream.
+        Uses the inputs currently staged; the optimiser state is restored afterwards."""
+        out = {}
+        stages = [(nm, fn) for nm, fn, _k in self._stages()] + [("optimizer", self._optimizer)]
+        snapshot = [t.clone() for t in self._state()]
+        for _, fn in stages[:-1]:  # one full pass so every stage sees valid inputs
+            fn()
+        torch.cuda.synchronize()
+        out["live_samples"] = int(self.counter[0].item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for name, fn in stages:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = e0.elapsed_time(e1) / reps
+        for dst, src in zip(self._state(), snapshot):
+            dst.copy_(src)
+        self.hw.refresh(self.weight_views)
+        self.grads.zero_()
+        if self.shard_optimizer:
+            self.grad_shard.zero_()
+            self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
+        return out
+
+    def sync_params(self):
+        """Sharded optimiser: bring every rank's fp16 table and fp32 master copy up to date (before evaluation / checkpoints);
+        the per-step exchange of the fp16 table is deferred to the beginning of the next step."""
+        if not self.shard_optimizer:
+            return
+        dist = torch.distributed
+        off = self.rank * self.shard_len
+        dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
+        dist.all_gather_into_tensor(self.params[:self.n_table_pad], self.params[off:off + self.shard_len].clone(), group=self.pg)
+
+    def _warmup(self):
+        """One eager step on a side stream (module loading, NCCL communicator set-up), then the state is put back."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            snap = [t.clone() for t in self._state()]
+            self._step_body()
+            self._side.synchronize()
+            for dst, src in zip(self._state(), snap):
+                dst.copy_(src)
+            self.hw.refresh(self.weight_views)
+            self.grads.zero_()
+            if self.shard_optimizer:
+                self.grad_shard.zero_()
+                self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
 
     # ------------------------------------------------------------------------------------------------------------
     def step(self):
         """One optimisation step on the inputs staged by set_inputs*/().  No host synchronisation."""
         self.global_step += 1
         if not self.use_graph:
-            n = self._forward_backward()
-            self._allreduce()
-            n += self._optimizer()
-            self.launches_per_step = n
+            self.launches_per_step = self._step_body()
             return
-        if self._g_fwd_bwd is None:
-            # warm-up on a side stream (module loading, cudaFuncSetAttribute), then capture
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                self._snapshot = (self.params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.loss_scale.clone(),
-                                  self.growth_tracker.clone(), self.table16.clone(), self.hw.flat.clone(), self.step_dev.clone())
-                self._forward_backward()
-                self._optimizer()
-                # undo the warm-up update
-                for dst, src in zip((self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16,
-                                     self.hw.flat, self.step_dev), self._snapshot):
-                    dst.copy_(src)
-                self.grads.zero_()
-                self.found_inf.zero_()
-                del self._snapshot
-            torch.cuda.current_stream().wait_stream(s)
-            self._g_fwd_bwd = torch.cuda.CUDAGraph()
-            if self.world_size == 1:
-                # single GPU: the whole step (forward, backward, optimiser) is ONE graph
-                with torch.cuda.graph(self._g_fwd_bwd):
-                    self._n_fb = self._forward_backward()
-                    self._n_opt = self._optimizer()
-            else:
-                # data parallel: [forward+backward] graph -> NCCL allreduce of the flat gradient buffer -> [optimiser] graph
-                with torch.cuda.graph(self._g_fwd_bwd):
-                    self._n_fb = self._forward_backward()
-                self._g_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._g_opt):
-                    self._n_opt = self._optimizer()
-            self.launches_per_step = self._n_fb + self._n_opt
-        self._g_fwd_bwd.replay()
-        if self.world_size > 1:
-            self._allreduce()
-            self._g_opt.replay()
+        if self._graph is None:
+            self._warmup()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.launches_per_step = self._step_body()
+        self._graph.replay()
 
     def train_step(self, rays_o, rays_d, time, gt_rgb, bg_color=None):
         """Public API: one training step on device tensors; returns the (device) loss of this step."""
