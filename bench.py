@@ -385,10 +385,12 @@ def main():
         # that blocks must not turn a finished measurement into a hang, so it gets a bounded wait
         del trainer
         torch.cuda.synchronize()
-        dist.barrier()
-        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        def _teardown():
+            dist.barrier()
+            dist.destroy_process_group()
+        th = threading.Thread(target=_teardown, daemon=True)
         th.start()
-        th.join(timeout=20)
+        th.join(timeout=30)
         sys.stdout.flush()
         os._exit(0)
 

@@ -346,6 +346,28 @@ int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr
 int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff, int interval,
                             int32_t* step_dev, seald_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel exchange fused with the optimiser over NVLink peer memory (no counterpart in the reference, which is
+ * single-GPU: this is the "hash-table and MLP gradients summed over the GPUs" step of BASELINE.json's north_star,
+ * SURVEY.md §8e).  peer_grads[r] / peer_table16[r]: rank r's flat fp32 gradient buffer and fp16 table mapped into this
+ * process (symmetric memory); mc_*: NVSwitch multicast mappings of the same buffers, or NULL.  The calling rank owns table
+ * elements [shard_off, shard_off + shard_len).
+ *   seald_dp_reduce_shard   grad_shard[0..shard_len) = sum over the ranks of grads[shard_off ..) (peer loads, or in-switch
+ *                           reduction with multicast).
+ *   seald_dp_adam_broadcast grads[flag_off] (a float, > 0 = overflow) is summed over the ranks first: if set, nothing is
+ *                           updated (GradScaler.step) and found_inf_out says so.  Otherwise Adam runs on the local fp32
+ *                           p/m/v of the shard (gradient = grad_shard) and of the MLP region [w_off, w_off + n_weights)
+ *                           (gradient summed over the peers here), and the shard's fp16 rows go to EVERY rank's table.
+ * The caller orders the ranks with barriers (see csrc/dp_fused.cu).
+ * ------------------------------------------------------------------------------------------------ */
+int seald_dp_reduce_shard(const void* const* peer_grads, const void* mc_grads, int world, uint64_t shard_off,
+                          uint64_t shard_len, float* grad_shard, seald_stream_t stream);
+int seald_dp_adam_broadcast(const void* const* peer_grads, void* const* peer_table16, const void* mc_grads, void* mc_table16,
+                            int world, float* p, float* m, float* v, const float* grad_shard, uint64_t shard_off,
+                            uint64_t shard_len, uint64_t w_off, uint64_t n_weights, uint64_t flag_off, float lr,
+                            float lr_net, float beta1, float beta2, float eps, const int32_t* step_dev,
+                            const float* loss_scale, int32_t* found_inf_out, seald_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,6 @@
 """2-GPU check of the data-parallel trainer (run under torchrun): when every rank trains on the SAME batch, the summed
-gradient of the global-mean loss equals the single-GPU gradient, so K steps of the DP trainer (sharded optimiser, overlapped
-reduce-scatter / all-gather) must reproduce K steps of a single-GPU trainer up to fp32 atomic-order noise."""
+gradient of the global-mean loss equals the single-GPU gradient, so K steps of the DP trainer (fused peer-memory exchange, NCCL
+reduce-scatter / all-gather, NCCL all-reduce) must reproduce K steps of a single-GPU trainer up to fp32 atomic-order noise."""
 import os
 import sys
 
@@ -33,7 +33,7 @@ def run(world_size, **kw):
 # ---- 1. gradients of ONE step: sum over ranks of the per-rank gradient of (loss / world) == the single-GPU gradient ----------------
 def grads_once(world_size):
     model = bench.build_scene(dev, seed=0)
-    tr = FusedTrainer(model, num_rays=4096, max_samples=4096 * 16, perturb=False, world_size=world_size, use_graph=False, shard_optimizer=False)
+    tr = FusedTrainer(model, num_rays=4096, max_samples=4096 * 16, perturb=False, world_size=world_size, use_graph=False, dp_mode="allreduce")
     tr.set_inputs(ro[0], rd[0], ts[0], gt[0])
     tr._forward_backward()
     tr._allreduce()
@@ -52,8 +52,10 @@ if rank == 0:
 # ---- 2. K optimiser steps.  Adam normalises every entry's step, so an entry whose gradient is atomic-order noise around zero moves by
 # +-lr with a noise-chosen sign: the max over 12M entries is meaningless; compare the mean absolute difference and the loss. -----------
 results = {}
-for name, kw in (("sharded", dict(shard_optimizer=True)), ("allreduce", dict(shard_optimizer=False)),
-                 ("eager_sharded", dict(shard_optimizer=True, use_graph=False)), ("eager_allreduce", dict(shard_optimizer=False, use_graph=False))):
+for name, kw in (("fused", dict(dp_mode="fused")), ("fused_no_multicast", dict(dp_mode="fused")), ("eager_fused", dict(dp_mode="fused", use_graph=False)),
+                 ("sharded", dict(dp_mode="sharded")), ("allreduce", dict(dp_mode="allreduce")),
+                 ("eager_sharded", dict(dp_mode="sharded", use_graph=False)), ("eager_allreduce", dict(dp_mode="allreduce", use_graph=False))):
+    os.environ["SEALD_DP_MULTICAST"] = "0" if name == "fused_no_multicast" else "1"
     tr = run(world, **kw)
     results[name] = (tr.table16.float().clone(), [w.clone() for w in tr.weight_views], float(tr.loss), int(tr.step_dev),
                      tr.params[:tr.n_table].clone())

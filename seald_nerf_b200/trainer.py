@@ -14,6 +14,9 @@ fp32 buffer), so checkpoints and the drop-in `NeRFNetwork.forward` see the train
 """
 import math
 
+import ctypes as C
+import os
+
 import torch
 
 from . import _lib
@@ -25,7 +28,7 @@ from ._lib import ptr
 class FusedTrainer:
     def __init__(self, model, num_rays=4096, max_samples=None, lr=1e-2, lr_net=None, betas=(0.9, 0.99), eps=1e-15, dt_gamma=0.0,
                  max_steps=1024, T_thresh=1e-4, perturb=True, init_loss_scale=65536.0, growth_interval=2000, train_deform=True,
-                 use_graph=True, world_size=1, process_group=None, device=None, fuse_composite=True, shard_optimizer=True):
+                 use_graph=True, world_size=1, process_group=None, device=None, fuse_composite=True, shard_optimizer=True, dp_mode=None):
         self.model = model
         self.device = device or model.encoder.embeddings.device
         if self.device.type != "cuda":
@@ -56,18 +59,51 @@ class FusedTrainer:
         self.n_weights = sum(sizes)
         # data parallel with a sharded optimiser ("zero1"): the table region is padded to world_size equal shards of a multiple of
         # 8 elements; rank r owns elements [r * shard_len, (r + 1) * shard_len)
+        # data-parallel exchange (world_size > 1):
+        #   "fused"     gradient buffer + fp16 table in symmetric memory; ONE kernel per step sums this rank's shard of the table gradient
+        #               over the ranks (in the NVSwitch when a multicast mapping exists), runs Adam on it and writes the refreshed fp16
+        #               rows into every rank's table (csrc/dp_fused.cu); two cross-rank barriers per step, no NCCL call in the step
+        #   "sharded"   NCCL reduce-scatter -> Adam on the own shard -> NCCL all-gather, captured in the step graph
+        #   "allreduce" NCCL all-reduce of the whole flat buffer, every rank runs the whole optimiser
         W = self.world_size
-        self.shard_optimizer = bool(shard_optimizer) and W > 1
+        if dp_mode is None:
+            dp_mode = os.environ.get("SEALD_DP_MODE", "fused" if shard_optimizer else "allreduce")
+        self.dp_mode = dp_mode if W > 1 else "single"
+        if self.dp_mode not in ("single", "fused", "sharded", "allreduce"):
+            raise ValueError("dp_mode must be fused | sharded | allreduce")
+        self.shard_optimizer = self.dp_mode == "sharded"
         self.rank = torch.distributed.get_rank(self.pg) if W > 1 else 0
-        self.shard_len = ((self.n_table + W - 1) // W + 7) // 8 * 8 if self.shard_optimizer else 0
-        self.n_table_pad = self.shard_len * W if self.shard_optimizer else (self.n_table + 3) // 4 * 4
+        sharded_layout = self.dp_mode in ("fused", "sharded")  # table padded to W equal shards of a multiple of 8 elements
+        self.shard_len = ((self.n_table + W - 1) // W + 7) // 8 * 8 if sharded_layout else 0
+        self.n_table_pad = self.shard_len * W if sharded_layout else (self.n_table + 3) // 4 * 4
         n = self.n_table_pad + self.n_weights
         # flat buffers: [table (padded) | MLP weights | pad | overflow flag (4 floats)].  The flag lives INSIDE the gradient buffer so the
-        # all-reduce that sums the MLP gradients also tells every rank whether any rank overflowed (GradScaler's found_inf).
+        # exchange that sums the MLP gradients also tells every rank whether any rank overflowed (GradScaler's found_inf).
         self.n_flag = (n + 3) // 4 * 4
         n_pad = self.n_flag + 4
+        self._symm = None
+        if self.dp_mode == "fused":
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else torch.distributed.group.WORLD
+            self.grads = symm.empty(n_pad, dtype=torch.float32, device=dev)
+            self.grads.zero_()
+            self.table16_pad = symm.empty(self.n_table_pad, dtype=torch.float16, device=dev)
+            self.table16_pad.zero_()
+            hg, ht = symm.rendezvous(self.grads, group), symm.rendezvous(self.table16_pad, group)
+            use_mc = os.environ.get("SEALD_DP_MULTICAST", "1") != "0" and bool(hg.multicast_ptr) and bool(ht.multicast_ptr)
+            self._symm = (hg, ht)
+            self._peer_grads = (C.c_void_p * W)(*[int(x) for x in hg.buffer_ptrs])
+            self._peer_table16 = (C.c_void_p * W)(*[int(x) for x in ht.buffer_ptrs])
+            self._mc_grads = int(hg.multicast_ptr) if use_mc else None      # in-switch reduction / replication (NVLS) when mapped
+            self._mc_table16 = int(ht.multicast_ptr) if use_mc else None
+            # the shard sum: peer loads measured faster than multimem.ld_reduce on 2 GPUs (480 vs 290 GB/s inbound); switchable
+            self._mc_reduce = use_mc and os.environ.get("SEALD_DP_MULTICAST_REDUCE", "0") == "1"
+            self.found_inf_global = torch.zeros(1, **i32)
+            self.grad_shard = torch.zeros(self.shard_len, **f32)
+        else:
+            self.grads = torch.zeros(n_pad, **f32)
+            self.table16_pad = torch.zeros(self.n_table_pad, dtype=torch.float16, device=dev)
         self.params = torch.zeros(n_pad, **f32)
-        self.grads = torch.zeros(n_pad, **f32)
         self.exp_avg = torch.zeros(n_pad, **f32)
         self.exp_avg_sq = torch.zeros(n_pad, **f32)
         self.n_params = n
@@ -84,10 +120,9 @@ class FusedTrainer:
                 self.grad_views.append(self.grads[o:o + k].view_as(w))
                 o += k
         self.grad_table = self.grads[:self.n_table].view_as(table)
-        self.table16_pad = torch.zeros(self.n_table_pad, dtype=torch.float16, device=dev)
         self.table16 = self.table16_pad[:self.n_table].view(table.shape)
         self.table16.copy_(table.data)
-        if self.shard_optimizer:
+        if self.dp_mode == "sharded":
             self.grad_shard = torch.zeros(self.shard_len, **f32)               # this rank's slice of the summed table gradient
             self.shard16 = torch.zeros(self.shard_len, dtype=torch.float16, device=dev)  # ... and of the refreshed fp16 table
             self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
@@ -292,32 +327,48 @@ class FusedTrainer:
                     n[0] += S[nm][1]
 
         dist = torch.distributed
-        W, sharded = self.world_size, self.shard_optimizer
+        W, mode = self.world_size, self.dp_mode
         main, side = torch.cuda.current_stream(), self._side
         ntp = self.n_table_pad
-        if sharded:  # last step's refreshed table shards (a no-op exchange before the first step)
+        if mode in ("fused", "sharded"):
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
+                if mode == "sharded":  # last step's refreshed table shards (a no-op exchange before the first step)
+                    dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
+                else:
+                    # every rank finished last step's fused exchange: its fp16 rows are in our table, and nobody reads our gradient
+                    # buffer any more, so it can be cleared for this step
+                    self._symm[0].barrier(1)
+                    self.grads.zero_()
         run("select_frame", "march", "deform_fwd")
-        if sharded:
+        if mode in ("fused", "sharded"):
             main.wait_stream(side)
         run("grid_fwd", "heads_fwd", "composite_fwd", "loss", "composite_bwd", "composite_loss_fused", "heads_bwd")
         side.wait_stream(main)
         with torch.cuda.stream(side):
             run("grid_scatter")
-            if sharded:
+            if mode == "sharded":
                 dist.reduce_scatter_tensor(self.grad_shard, self.grads[:ntp], op=dist.ReduceOp.SUM, group=self.pg)
                 self.grads[:ntp].zero_()  # consumed; the Adam kernel only sees the shard
-            elif W > 1:
+            elif mode == "allreduce":
                 dist.all_reduce(self.grads[:ntp], op=dist.ReduceOp.SUM, group=self.pg)
+            elif mode == "fused":
+                # every rank's table gradient is complete -> pull this rank's shard of the sum over NVLink, underneath the tensor-core
+                # backward of the deformation net running on the main stream
+                self._symm[0].barrier(0)
+                _lib.call("seald_dp_reduce_shard", C.cast(self._peer_grads, C.c_void_p), self._mc_grads if self._mc_reduce else None, W,
+                          self.rank * self.shard_len, self.shard_len, ptr(self.grad_shard), _lib.stream())
+                n[0] += 2
         run("grid_input_bwd", "deform_bwd", "wgrad")
         st = _lib.stream()
         _lib.call("seald_grad_finite_check", self.grads.data_ptr() + 4 * ntp, self.n_weights, ptr(self.found_inf), st)
         n[0] += 1
         main.wait_stream(side)  # (also orders the overflow flag written by the scatter before it is exchanged)
-        if W > 1:  # MLP gradients + the overflow flag (a float: > 0 on every rank if any rank overflowed)
+        if mode in ("sharded", "allreduce"):  # MLP gradients + the overflow flag (a float: > 0 on every rank if any rank overflowed)
             dist.all_reduce(self.grads[ntp:], op=dist.ReduceOp.SUM, group=self.pg)
+        elif mode == "fused":
+            self._symm[0].barrier(2)  # every rank's MLP gradients and overflow flag are complete
+            n[0] += 1
         n[0] += self._optimizer()
         return n[0]
 
@@ -340,21 +391,33 @@ class FusedTrainer:
         st = _lib.stream()
         b1, b2 = self.betas
         ntp = self.n_table_pad
-        if self.shard_optimizer:
-            off = self.rank * self.shard_len
-            _lib.call("seald_adam_step", self.params.data_ptr() + 4 * off, ptr(self.grad_shard), self.exp_avg.data_ptr() + 4 * off,
-                      self.exp_avg_sq.data_ptr() + 4 * off, self.shard_len, self.lr, b1, b2, self.eps, 1, ptr(self.step_dev), ptr(self.loss_scale),
-                      ptr(self.found_inf), ptr(self.shard16), 0, st)
+        found = self.found_inf
+        if self.dp_mode == "fused":
+            # overflow decision + Adam on the shard (gradient summed by seald_dp_reduce_shard) and on the replicated MLP weights (summed
+            # here) + fp16 rows to every rank's table: one kernel
+            found = self.found_inf_global
+            _lib.call("seald_dp_adam_broadcast", C.cast(self._peer_grads, C.c_void_p), C.cast(self._peer_table16, C.c_void_p),
+                      self._mc_grads, self._mc_table16, self.world_size, ptr(self.params), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                      ptr(self.grad_shard), self.rank * self.shard_len, self.shard_len, ntp, self.n_weights, self.n_flag, self.lr,
+                      self.lr_net, b1, b2, self.eps, ptr(self.step_dev), ptr(self.loss_scale), ptr(found), st)
+            n = 3
         else:
-            _lib.call("seald_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ntp, self.lr, b1, b2, self.eps,
-                      1, ptr(self.step_dev), ptr(self.loss_scale), ptr(self.found_inf), ptr(self.table16_pad), 1, st)
-        _lib.call("seald_adam_step", self.params.data_ptr() + 4 * ntp, self.grads.data_ptr() + 4 * ntp, self.exp_avg.data_ptr() + 4 * ntp,
-                  self.exp_avg_sq.data_ptr() + 4 * ntp, self.n_weights, self.lr_net, b1, b2, self.eps, 1, ptr(self.step_dev),
-                  ptr(self.loss_scale), ptr(self.found_inf), None, 1, st)
+            if self.dp_mode == "sharded":
+                off = self.rank * self.shard_len
+                _lib.call("seald_adam_step", self.params.data_ptr() + 4 * off, ptr(self.grad_shard), self.exp_avg.data_ptr() + 4 * off,
+                          self.exp_avg_sq.data_ptr() + 4 * off, self.shard_len, self.lr, b1, b2, self.eps, 1, ptr(self.step_dev),
+                          ptr(self.loss_scale), ptr(found), ptr(self.shard16), 0, st)
+            else:
+                _lib.call("seald_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ntp, self.lr, b1, b2,
+                          self.eps, 1, ptr(self.step_dev), ptr(self.loss_scale), ptr(found), ptr(self.table16_pad), 1, st)
+            _lib.call("seald_adam_step", self.params.data_ptr() + 4 * ntp, self.grads.data_ptr() + 4 * ntp, self.exp_avg.data_ptr() + 4 * ntp,
+                      self.exp_avg_sq.data_ptr() + 4 * ntp, self.n_weights, self.lr_net, b1, b2, self.eps, 1, ptr(self.step_dev),
+                      ptr(self.loss_scale), ptr(found), None, 1, st)
+            n = 5
         self.hw.refresh(self.weight_views)
-        _lib.call("seald_loss_scale_update", ptr(self.loss_scale), ptr(self.found_inf), ptr(self.growth_tracker), 2.0, 0.5,
+        _lib.call("seald_loss_scale_update", ptr(self.loss_scale), ptr(found), ptr(self.growth_tracker), 2.0, 0.5,
                   self.growth_interval, ptr(self.step_dev), st)
-        return 5
+        return n
 
     def _state(self):
         return (self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16_pad, self.hw.flat, self.step_dev)
@@ -380,42 +443,51 @@ class FusedTrainer:
             e1.record()
             torch.cuda.synchronize()
             out[name] = e0.elapsed_time(e1) / reps
-        for dst, src in zip(self._state(), snapshot):
-            dst.copy_(src)
-        self.hw.refresh(self.weight_views)
-        self.grads.zero_()
-        if self.shard_optimizer:
-            self.grad_shard.zero_()
-            self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
+        torch.cuda.synchronize()
+        self._restore(snapshot)
         return out
 
     def sync_params(self):
-        """Sharded optimiser: bring every rank's fp16 table and fp32 master copy up to date (before evaluation / checkpoints);
-        the per-step exchange of the fp16 table is deferred to the beginning of the next step."""
-        if not self.shard_optimizer:
+        """Data parallel with a sharded table: bring every rank's fp16 table and fp32 master copy up to date (before evaluation /
+        checkpoints); the per-step exchange of the fp16 table completes at the beginning of the NEXT step."""
+        if self.dp_mode not in ("fused", "sharded"):
             return
         dist = torch.distributed
         off = self.rank * self.shard_len
-        dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
+        if self.dp_mode == "sharded":
+            dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
+        else:
+            torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.pg)  # every rank's fused kernel (which writes our table) has finished
         dist.all_gather_into_tensor(self.params[:self.n_table_pad], self.params[off:off + self.shard_len].clone(), group=self.pg)
 
+    def _restore(self, snap):
+        for dst, src in zip(self._state(), snap):
+            dst.copy_(src)
+        self.hw.refresh(self.weight_views)
+        self.grads.zero_()
+        if self.dp_mode == "fused":
+            self.grad_shard.zero_()
+        if self.dp_mode == "sharded":
+            self.grad_shard.zero_()
+            self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
+
+    def _rank_sync(self):
+        torch.cuda.synchronize()
+        if self.world_size > 1:
+            torch.distributed.barrier(group=self.pg)
+
     def _warmup(self):
-        """One eager step on a side stream (module loading, NCCL communicator set-up), then the state is put back."""
+        """One eager step on a side stream (module loading, communicator set-up), then the state is put back.  The ranks are
+        synchronised around the restore: in the fused mode the peers write their shard of the warm-up update into OUR table."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             snap = [t.clone() for t in self._state()]
             self._step_body()
-            self._side.synchronize()
-            for dst, src in zip(self._state(), snap):
-                dst.copy_(src)
-            self.hw.refresh(self.weight_views)
-            self.grads.zero_()
-            if self.shard_optimizer:
-                self.grad_shard.zero_()
-                self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
+        self._rank_sync()
+        self._restore(snap)
+        self._rank_sync()
 
     # ------------------------------------------------------------------------------------------------------------
     def step(self):

@@ -113,3 +113,22 @@ def test_fused_composite_loss_kernel_equals_three_kernels(cuda_dev):
     assert float((res[0][4] == 0).float().mean()) > 0.2  # many samples lie behind an early stop
     scale = float(res[0][7].abs().max())
     assert float((res[0][7] - res[1][7]).abs().max()) <= 1e-4 * scale  # (atomic order in the scatter)
+
+
+@pytest.mark.gpu
+def test_data_parallel_modes_two_gpus():
+    """World-size-2 run of scripts/dp_check.py (needs 2 GPUs): the summed per-rank gradient equals the single-GPU gradient
+    (rtol 1e-3), and 12 optimiser steps of every exchange mode — fused peer-memory kernels with and without NVSwitch multicast,
+    NCCL reduce-scatter/all-gather, NCCL all-reduce; graph-captured and eager — follow the single-GPU loss trajectory (2e-3),
+    skip no step, and leave fp16 table == half(fp32 master) on every rank."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", os.path.join(root, "scripts", "dp_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "MISMATCH" not in p.stdout and p.stdout.count(" OK") >= 8
