@@ -285,6 +285,7 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    trainer.flush()  # the table pass of the last step's optimiser is deferred into the next step: apply it before the model is rendered
     clocks = sampler.stop(t_clk0, sampler.mark()) if rank == 0 else None
 
     # ---- full-frame render, ray tiles sharded over the ranks (configs[2]) ------------------------------------------------
@@ -330,7 +331,8 @@ def main():
             "composite_fwd": ("hbm", 24.0 * m_live + 32.0 * N_RAYS),
             "composite_bwd": ("hbm", 40.0 * m_live + 48.0 * N_RAYS),
             "composite_loss_fused": ("hbm", 64.0 * m_live + 104.0 * N_RAYS),
-            "optimizer": ("hbm", 30.0 * trainer.n_params + 4.0 * trainer.n_params),
+            # Adam over the fp32 table: p, m, v read + written (24 B), gradient read + cleared (8 B), fp16 copy written (2 B) per parameter
+            "optimizer_table": ("hbm", 34.0 * (trainer.shard_len if trainer.dp_mode in ("fused", "sharded") else trainer.n_table_pad)),
         }
         dom = max((k for k in st if k in work), key=lambda k: st[k])
         bound, amount = work[dom]

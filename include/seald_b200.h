@@ -341,10 +341,19 @@ int seald_adam_advance(int32_t* step_dev, const int32_t* found_inf, seald_stream
 int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
                     const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
                     seald_stream_t stream);
+/* Same with a cap on the grid (0 = default): a pass that shares the GPU with other kernels (the trainer runs the table pass
+ * beside the next step's march) must not fill every SM, or the latency-bound kernel next to it cannot be scheduled. */
+int seald_adam_step_ex(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
+                       const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
+                       uint32_t max_blocks, seald_stream_t stream);
 /* step_dev (optional): completed-update counter, incremented here when no inf was found (then seald_adam_advance is not
  * needed and seald_adam_step is called with step = 1: "this is update number *step_dev + 1"). */
 int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff, int interval,
                             int32_t* step_dev, seald_stream_t stream);
+/* Same, and also records {found_inf, *step_dev, bits of *loss_scale} (before they change) into stash[0..2]: the values the
+ * deferred part of this step's optimiser (the hash-table pass, run beside the next step's march) must use. */
+int seald_loss_scale_update_stash(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff,
+                                  int interval, int32_t* step_dev, int32_t* stash, seald_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Data-parallel exchange fused with the optimiser over NVLink peer memory (no counterpart in the reference, which is
@@ -354,19 +363,24 @@ int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* grow
  * elements [shard_off, shard_off + shard_len).
  *   seald_dp_reduce_shard   grad_shard[0..shard_len) = sum over the ranks of grads[shard_off ..) (peer loads, or in-switch
  *                           reduction with multicast).
- *   seald_dp_adam_broadcast grads[flag_off] (a float, > 0 = overflow) is summed over the ranks first: if set, nothing is
+ *   seald_dp_adam_weights   grads[flag_off] (a float, > 0 = overflow) is summed over the ranks first: if set, nothing is
  *                           updated (GradScaler.step) and found_inf_out says so.  Otherwise Adam runs on the local fp32
- *                           p/m/v of the shard (gradient = grad_shard) and of the MLP region [w_off, w_off + n_weights)
- *                           (gradient summed over the peers here), and the shard's fp16 rows go to EVERY rank's table.
+ *                           p/m/v of the replicated MLP region [w_off, w_off + n_weights), its gradient summed over the peers.
+ *   seald_dp_adam_shard_broadcast  Adam on the local fp32 p/m/v of the shard (gradient = grad_shard, skipped when
+ *                           *found_inf != 0) and the shard's fp16 rows stored into EVERY rank's table.  step_dev / loss_scale /
+ *                           found_inf are the values stashed by seald_loss_scale_update_stash: the trainer runs this
+ *                           kernel at the beginning of the NEXT step, beside the march.
  * The caller orders the ranks with barriers (see csrc/dp_fused.cu).
  * ------------------------------------------------------------------------------------------------ */
 int seald_dp_reduce_shard(const void* const* peer_grads, const void* mc_grads, int world, uint64_t shard_off,
                           uint64_t shard_len, float* grad_shard, seald_stream_t stream);
-int seald_dp_adam_broadcast(const void* const* peer_grads, void* const* peer_table16, const void* mc_grads, void* mc_table16,
-                            int world, float* p, float* m, float* v, const float* grad_shard, uint64_t shard_off,
-                            uint64_t shard_len, uint64_t w_off, uint64_t n_weights, uint64_t flag_off, float lr,
-                            float lr_net, float beta1, float beta2, float eps, const int32_t* step_dev,
-                            const float* loss_scale, int32_t* found_inf_out, seald_stream_t stream);
+int seald_dp_adam_weights(const void* const* peer_grads, const void* mc_grads, int world, float* p, float* m, float* v,
+                          uint64_t w_off, uint64_t n_weights, uint64_t flag_off, float lr_net, float beta1, float beta2, float eps,
+                          const int32_t* step_dev, const float* loss_scale, int32_t* found_inf_out, seald_stream_t stream);
+int seald_dp_adam_shard_broadcast(void* const* peer_table16, void* mc_table16, int world, float* p, float* m, float* v,
+                                  const float* grad_shard, uint64_t shard_off, uint64_t shard_len, float lr, float beta1,
+                                  float beta2, float eps, const int32_t* step_dev, const float* loss_scale,
+                                  const int32_t* found_inf, seald_stream_t stream);
 
 #ifdef __cplusplus
 }

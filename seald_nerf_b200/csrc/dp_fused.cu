@@ -9,10 +9,11 @@
 //                          multimem.ld_reduce: the sum happens IN the switch).  Launched on the trainer's second stream as
 //                          soon as every rank finished its table scatter, so the NVLink transfer runs underneath the
 //                          tensor-core backward of the deformation net (which does not touch the table gradient).
-//   k_dp_adam_broadcast    sums the overflow flag and the small MLP region over the peers, runs Adam (torch.optim.Adam +
-//                          GradScaler semantics exactly as k_adam, train.cu) on the local fp32 p/m/v of the shard and of the
-//                          replicated MLP weights, and stores the refreshed fp16 table rows into EVERY rank's table
-//                          (multimem.st: one store, replicated by the switch; else one store per peer).
+//   k_dp_adam_weights      sums the overflow flag and the small MLP region over the peers and runs Adam (torch.optim.Adam +
+//                          GradScaler semantics exactly as k_adam, train.cu) on the replicated MLP weights.
+//   k_dp_adam_shard_broadcast  Adam on the local fp32 p/m/v of the shard, refreshed fp16 rows stored into EVERY rank's table
+//                          (multimem.st: one store, replicated by the switch; else one store per peer).  The trainer defers this
+//                          kernel into the beginning of the next step, where it runs beside the march + deformation forward.
 //
 // Ordering is the caller's (trainer.py): a cross-rank barrier before each kernel (all table gradients / all MLP gradients
 // complete) and one before the table is read or the gradient buffer is cleared again — that last one sits behind the next
@@ -112,16 +113,14 @@ __global__ void __launch_bounds__(256) k_dp_reduce_shard(const DpPeers peers, co
     }
 }
 
-// ---- phase B: overflow decision, Adam on the shard + the replicated MLP weights, fp16 rows to every rank ------------------------
+// ---- phase B1: overflow decision + Adam on the replicated MLP weights (gradient summed over the peers here: 0.5 MB) ------------
 template <bool MC>
-__global__ void __launch_bounds__(256) k_dp_adam_broadcast(const DpPeers peers, const float* __restrict__ mc_grads,
-                                                           __half* __restrict__ mc_table16, const int world, float* __restrict__ p,
-                                                           float* __restrict__ m, float* __restrict__ v,
-                                                           const float* __restrict__ grad_shard, const size_t shard_off,
-                                                           const size_t shard_len, const size_t w_off, const size_t n_weights,
-                                                           const size_t flag_off, const float lr, const float lr_net, const float beta1,
-                                                           const float beta2, const float eps, const int* __restrict__ step_dev,
-                                                           const float* __restrict__ loss_scale, int* __restrict__ found_inf_out) {
+__global__ void __launch_bounds__(256) k_dp_adam_weights(const DpPeers peers, const float* __restrict__ mc_grads, const int world,
+                                                         float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                         const size_t w_off, const size_t n_weights, const size_t flag_off,
+                                                         const float lr_net, const float beta1, const float beta2, const float eps,
+                                                         const int* __restrict__ step_dev, const float* __restrict__ loss_scale,
+                                                         int* __restrict__ found_inf_out) {
     __shared__ float s_bc[2];
     __shared__ int s_skip;
     if (threadIdx.x == 0) {
@@ -138,46 +137,60 @@ __global__ void __launch_bounds__(256) k_dp_adam_broadcast(const DpPeers peers, 
     const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
     const float inv_scale = 1.0f / *loss_scale;
     const size_t tid = threadIdx.x + (size_t)blockIdx.x * blockDim.x, nth = (size_t)gridDim.x * blockDim.x;
-
-    // ---- MLP weights first (their remote loads are latency, not bandwidth): every rank reduces the whole small region ----
-    {
-        const float step_size = lr_net / bc1;
-        const size_t n4 = n_weights / 4;
-        for (size_t j = tid; j < n4; j += nth) {
-            const size_t i = w_off + j * 4;
-            const float4 g4 = reduce_f32x4<MC>(peers, mc_grads, world, i);
-            float4 p4 = *reinterpret_cast<const float4*>(p + i), m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
-            adam4(p4, m4, v4, g4, inv_scale, beta1, beta2, eps, step_size, bc2_sqrt);
-            *reinterpret_cast<float4*>(p + i) = p4;
-            *reinterpret_cast<float4*>(m + i) = m4;
-            *reinterpret_cast<float4*>(v + i) = v4;
-        }
+    const float step_size = lr_net / bc1;
+    const size_t n4 = n_weights / 4;
+    for (size_t j = tid; j < n4; j += nth) {
+        const size_t i = w_off + j * 4;
+        const float4 g4 = reduce_f32x4<MC>(peers, mc_grads, world, i);
+        float4 p4 = *reinterpret_cast<const float4*>(p + i), m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
+        adam4(p4, m4, v4, g4, inv_scale, beta1, beta2, eps, step_size, bc2_sqrt);
+        *reinterpret_cast<float4*>(p + i) = p4;
+        *reinterpret_cast<float4*>(m + i) = m4;
+        *reinterpret_cast<float4*>(v + i) = v4;
     }
-    // ---- this rank's shard of the hash table: 8 elements per thread and iteration -------------------------------------
-    {
-        const float step_size = lr / bc1;
-        const size_t n8 = shard_len / 8;
-        for (size_t j = tid; j < n8; j += nth) {
-            const size_t i = shard_off + j * 8;
-            const float4 ga = *reinterpret_cast<const float4*>(grad_shard + j * 8), gb = *reinterpret_cast<const float4*>(grad_shard + j * 8 + 4);
-            float4 pa = *reinterpret_cast<const float4*>(p + i), pb = *reinterpret_cast<const float4*>(p + i + 4);
-            float4 ma = *reinterpret_cast<const float4*>(m + i), mb = *reinterpret_cast<const float4*>(m + i + 4);
-            float4 va = *reinterpret_cast<const float4*>(v + i), vb = *reinterpret_cast<const float4*>(v + i + 4);
-            adam4(pa, ma, va, ga, inv_scale, beta1, beta2, eps, step_size, bc2_sqrt);
-            adam4(pb, mb, vb, gb, inv_scale, beta1, beta2, eps, step_size, bc2_sqrt);
-            *reinterpret_cast<float4*>(p + i) = pa; *reinterpret_cast<float4*>(p + i + 4) = pb;
-            *reinterpret_cast<float4*>(m + i) = ma; *reinterpret_cast<float4*>(m + i + 4) = mb;
-            *reinterpret_cast<float4*>(v + i) = va; *reinterpret_cast<float4*>(v + i + 4) = vb;
-            const __half2 h0 = __floats2half2_rn(pa.x, pa.y), h1 = __floats2half2_rn(pa.z, pa.w);
-            const __half2 h2 = __floats2half2_rn(pb.x, pb.y), h3 = __floats2half2_rn(pb.z, pb.w);
-            uint4 u;
-            u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
-            u.z = *reinterpret_cast<const uint32_t*>(&h2); u.w = *reinterpret_cast<const uint32_t*>(&h3);
-            if constexpr (MC) {
-                mc_st_b128(mc_table16 + i, u);
-            } else {
-                for (int r = 0; r < world; r++) *reinterpret_cast<uint4*>(peers.table16[r] + i) = u;
-            }
+}
+
+// ---- phase B2: Adam on this rank's shard of the hash table + its fp16 rows to every rank (8 elements per thread and iteration) ----
+template <bool MC>
+__global__ void __launch_bounds__(256) k_dp_adam_shard_broadcast(const DpPeers peers, __half* __restrict__ mc_table16, const int world,
+                                                                 float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                                 const float* __restrict__ grad_shard, const size_t shard_off,
+                                                                 const size_t shard_len, const float lr, const float beta1,
+                                                                 const float beta2, const float eps, const int* __restrict__ step_dev,
+                                                                 const float* __restrict__ loss_scale, const int* __restrict__ found_inf) {
+    if (*found_inf != 0) return;
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+        const double st = (double)max(*step_dev + 1, 1);
+        s_bc[0] = (float)(1.0 - pow((double)beta1, st));
+        s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, st));
+    }
+    __syncthreads();
+    const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+    const float inv_scale = 1.0f / *loss_scale;
+    const size_t tid = threadIdx.x + (size_t)blockIdx.x * blockDim.x, nth = (size_t)gridDim.x * blockDim.x;
+    const float step_size = lr / bc1;
+    const size_t n8 = shard_len / 8;
+    for (size_t j = tid; j < n8; j += nth) {
+        const size_t i = shard_off + j * 8;
+        const float4 ga = *reinterpret_cast<const float4*>(grad_shard + j * 8), gb = *reinterpret_cast<const float4*>(grad_shard + j * 8 + 4);
+        float4 pa = *reinterpret_cast<const float4*>(p + i), pb = *reinterpret_cast<const float4*>(p + i + 4);
+        float4 ma = *reinterpret_cast<const float4*>(m + i), mb = *reinterpret_cast<const float4*>(m + i + 4);
+        float4 va = *reinterpret_cast<const float4*>(v + i), vb = *reinterpret_cast<const float4*>(v + i + 4);
+        adam4(pa, ma, va, ga, inv_scale, beta1, beta2, eps, step_size, bc2_sqrt);
+        adam4(pb, mb, vb, gb, inv_scale, beta1, beta2, eps, step_size, bc2_sqrt);
+        *reinterpret_cast<float4*>(p + i) = pa; *reinterpret_cast<float4*>(p + i + 4) = pb;
+        *reinterpret_cast<float4*>(m + i) = ma; *reinterpret_cast<float4*>(m + i + 4) = mb;
+        *reinterpret_cast<float4*>(v + i) = va; *reinterpret_cast<float4*>(v + i + 4) = vb;
+        const __half2 h0 = __floats2half2_rn(pa.x, pa.y), h1 = __floats2half2_rn(pa.z, pa.w);
+        const __half2 h2 = __floats2half2_rn(pb.x, pb.y), h3 = __floats2half2_rn(pb.z, pb.w);
+        uint4 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        u.z = *reinterpret_cast<const uint32_t*>(&h2); u.w = *reinterpret_cast<const uint32_t*>(&h3);
+        if constexpr (MC) {
+            mc_st_b128(mc_table16 + i, u);
+        } else {
+            for (int r = 0; r < world; r++) *reinterpret_cast<uint4*>(peers.table16[r] + i) = u;
         }
     }
 }
@@ -218,24 +231,44 @@ extern "C" int seald_dp_reduce_shard(const void* const* peer_grads, const void* 
     return launch_status();
 }
 
-extern "C" int seald_dp_adam_broadcast(const void* const* peer_grads, void* const* peer_table16, const void* mc_grads, void* mc_table16,
-                                       int world, float* p, float* m, float* v, const float* grad_shard, uint64_t shard_off,
-                                       uint64_t shard_len, uint64_t w_off, uint64_t n_weights, uint64_t flag_off, float lr, float lr_net,
-                                       float beta1, float beta2, float eps, const int32_t* step_dev, const float* loss_scale,
-                                       int32_t* found_inf_out, seald_stream_t stream) {
-    if (!peer_table16 || !p || !m || !v || !grad_shard || !step_dev || !loss_scale || !found_inf_out) return SEALD_E_BADARG;
-    if ((shard_off | shard_len) % 8 || (w_off | n_weights | flag_off) % 4) return SEALD_E_BADARG;  // 16-byte vectors throughout
+extern "C" int seald_dp_adam_weights(const void* const* peer_grads, const void* mc_grads, int world, float* p, float* m, float* v,
+                                     uint64_t w_off, uint64_t n_weights, uint64_t flag_off, float lr_net, float beta1, float beta2, float eps,
+                                     const int32_t* step_dev, const float* loss_scale, int32_t* found_inf_out, seald_stream_t stream) {
+    if (!p || !m || !v || !step_dev || !loss_scale || !found_inf_out) return SEALD_E_BADARG;
+    if ((w_off | n_weights | flag_off) % 4) return SEALD_E_BADARG;  // 16-byte vectors throughout
     DpPeers peers;
-    int rc = fill_peers(peers, peer_grads, peer_table16, world);
+    int rc = fill_peers(peers, peer_grads, nullptr, world);
     if (rc) return rc;
     cudaStream_t st = to_stream(stream);
-    const uint32_t blocks = 4u * SEALD_NUM_SMS;
-    if (mc_grads && mc_table16)
-        k_dp_adam_broadcast<true><<<blocks, 256, 0, st>>>(peers, (const float*)mc_grads, (__half*)mc_table16, world, p, m, v, grad_shard, shard_off,
-                                                          shard_len, w_off, n_weights, flag_off, lr, lr_net, beta1, beta2, eps, step_dev, loss_scale,
-                                                          found_inf_out);
+    const uint32_t blocks = (uint32_t)div_up<uint64_t>(n_weights / 4 + 1, 256);
+    if (mc_grads)
+        k_dp_adam_weights<true><<<blocks, 256, 0, st>>>(peers, (const float*)mc_grads, world, p, m, v, w_off, n_weights, flag_off, lr_net, beta1,
+                                                        beta2, eps, step_dev, loss_scale, found_inf_out);
     else
-        k_dp_adam_broadcast<false><<<blocks, 256, 0, st>>>(peers, nullptr, nullptr, world, p, m, v, grad_shard, shard_off, shard_len, w_off,
-                                                           n_weights, flag_off, lr, lr_net, beta1, beta2, eps, step_dev, loss_scale, found_inf_out);
+        k_dp_adam_weights<false><<<blocks, 256, 0, st>>>(peers, nullptr, world, p, m, v, w_off, n_weights, flag_off, lr_net, beta1, beta2, eps,
+                                                         step_dev, loss_scale, found_inf_out);
+    return launch_status();
+}
+
+extern "C" int seald_dp_adam_shard_broadcast(void* const* peer_table16, void* mc_table16, int world, float* p, float* m, float* v,
+                                             const float* grad_shard, uint64_t shard_off, uint64_t shard_len, float lr, float beta1,
+                                             float beta2, float eps, const int32_t* step_dev, const float* loss_scale,
+                                             const int32_t* found_inf, seald_stream_t stream) {
+    if (!peer_table16 || !p || !m || !v || !grad_shard || !step_dev || !loss_scale || !found_inf) return SEALD_E_BADARG;
+    if ((shard_off | shard_len) % 8 || world < 1 || world > kMaxRanks) return SEALD_E_BADARG;
+    DpPeers peers;
+    for (int r = 0; r < kMaxRanks; r++) {
+        peers.grads[r] = nullptr;
+        peers.table16[r] = r < world ? (__half*)peer_table16[r] : nullptr;
+        if (r < world && !peers.table16[r]) return SEALD_E_BADARG;
+    }
+    cudaStream_t st = to_stream(stream);
+    const uint32_t blocks = 4u * SEALD_NUM_SMS;
+    if (mc_table16)
+        k_dp_adam_shard_broadcast<true><<<blocks, 256, 0, st>>>(peers, (__half*)mc_table16, world, p, m, v, grad_shard, shard_off, shard_len, lr,
+                                                                beta1, beta2, eps, step_dev, loss_scale, found_inf);
+    else
+        k_dp_adam_shard_broadcast<false><<<blocks, 256, 0, st>>>(peers, nullptr, world, p, m, v, grad_shard, shard_off, shard_len, lr, beta1, beta2,
+                                                                 eps, step_dev, loss_scale, found_inf);
     return launch_status();
 }

@@ -152,9 +152,16 @@ __global__ void k_adam_advance(int* step_dev, const int* __restrict__ found_inf)
 }
 
 // GradScaler.update(): found_inf -> scale *= backoff, tracker = 0; else tracker++ and scale *= growth every `interval`.
+// stash (optional, 4 words): {found_inf, step counter, loss scale} as they were for THIS step's update, kept for the part of the
+// optimiser that the trainer defers into the next step (the hash-table Adam pass runs beside the next march).
 __global__ void k_loss_scale_update(float* loss_scale, int* found_inf, int* growth_tracker, const float growth, const float backoff,
-                                    const int interval, int* step_dev) {
+                                    const int interval, int* step_dev, int* stash) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (stash) {
+            stash[0] = *found_inf;
+            stash[1] = step_dev ? *step_dev : 0;
+            stash[2] = __float_as_int(*loss_scale);
+        }
         if (step_dev && !*found_inf) *step_dev += 1;  // optimizer.step() ran: one more completed update
         if (*found_inf) {
             *loss_scale *= backoff;
@@ -253,16 +260,17 @@ extern "C" int seald_adam_advance(int32_t* step_dev, const int32_t* found_inf, s
     return launch_status();
 }
 
-extern "C" int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
-                               const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
-                               seald_stream_t stream) {
+static int adam_launch(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
+                       const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
+                       uint32_t max_blocks, seald_stream_t stream) {
     if (n == 0) return 0;
     if (!p || !g || !m || !v || (step == 0 && !step_dev)) return SEALD_E_BADARG;
     const uint32_t step_in = step;
     if (step == 0) step = 1;
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    const uint32_t blocks = (uint32_t)(n / 256 + 1 < 8u * SEALD_NUM_SMS ? n / 256 + 1 : 8u * SEALD_NUM_SMS);
+    if (max_blocks == 0) max_blocks = 8u * SEALD_NUM_SMS;
+    const uint32_t blocks = (uint32_t)(n / 256 + 1 < max_blocks ? n / 256 + 1 : max_blocks);
     // with step_dev: the step number of THIS update is *step_dev + step (step = 0: the counter was advanced already by
     // seald_adam_advance; step = 1: it counts completed updates and is advanced by seald_loss_scale_update afterwards)
     k_adam<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), step_dev,
@@ -270,9 +278,28 @@ extern "C" int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t 
     return launch_status();
 }
 
+extern "C" int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
+                               const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
+                               seald_stream_t stream) {
+    return adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, step, step_dev, loss_scale, found_inf, p16, zero_grad, 0, stream);
+}
+
+extern "C" int seald_adam_step_ex(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps,
+                                  uint32_t step, const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16,
+                                  int zero_grad, uint32_t max_blocks, seald_stream_t stream) {
+    return adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, step, step_dev, loss_scale, found_inf, p16, zero_grad, max_blocks, stream);
+}
+
 extern "C" int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff,
                                        int interval, int32_t* step_dev, seald_stream_t stream) {
     if (!loss_scale || !found_inf || !growth_tracker) return SEALD_E_BADARG;
-    k_loss_scale_update<<<1, 32, 0, to_stream(stream)>>>(loss_scale, found_inf, growth_tracker, growth, backoff, interval, step_dev);
+    k_loss_scale_update<<<1, 32, 0, to_stream(stream)>>>(loss_scale, found_inf, growth_tracker, growth, backoff, interval, step_dev, nullptr);
+    return launch_status();
+}
+
+extern "C" int seald_loss_scale_update_stash(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff,
+                                             int interval, int32_t* step_dev, int32_t* stash, seald_stream_t stream) {
+    if (!loss_scale || !found_inf || !growth_tracker || !stash) return SEALD_E_BADARG;
+    k_loss_scale_update<<<1, 32, 0, to_stream(stream)>>>(loss_scale, found_inf, growth_tracker, growth, backoff, interval, step_dev, stash);
     return launch_status();
 }

@@ -28,7 +28,8 @@ from ._lib import ptr
 class FusedTrainer:
     def __init__(self, model, num_rays=4096, max_samples=None, lr=1e-2, lr_net=None, betas=(0.9, 0.99), eps=1e-15, dt_gamma=0.0,
                  max_steps=1024, T_thresh=1e-4, perturb=True, init_loss_scale=65536.0, growth_interval=2000, train_deform=True,
-                 use_graph=True, world_size=1, process_group=None, device=None, fuse_composite=True, shard_optimizer=True, dp_mode=None):
+                 use_graph=True, world_size=1, process_group=None, device=None, fuse_composite=True, shard_optimizer=True, dp_mode=None,
+                 defer_table_update=True):
         self.model = model
         self.device = device or model.encoder.embeddings.device
         if self.device.type != "cuda":
@@ -127,6 +128,17 @@ class FusedTrainer:
             self.shard16 = torch.zeros(self.shard_len, dtype=torch.float16, device=dev)  # ... and of the refreshed fp16 table
             self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
         self._side = torch.cuda.Stream(device=dev)
+        # the table pass of the optimiser is software-pipelined into the next step (single GPU and the fused exchange); flush() / sync_params()
+        # bring the parameters up to date.  pending = {found_inf (1 = nothing pending), step counter, loss-scale bits} of the stashed update
+        defer = os.environ.get("SEALD_DEFER", "auto")
+        if defer == "auto":
+            # measured: on one GPU the overlap buys nothing (0.403 vs 0.406 ms: the march is a chain of dependent bitfield look-ups and
+            # slows down beside a pass that saturates HBM); with the fused exchange it hides the NVLink stores (0.437 -> 0.417 ms on 2 GPUs)
+            defer = "start" if self.dp_mode == "fused" else "0"
+        self.defer_table_update = bool(defer_table_update) and self.dp_mode in ("single", "fused") and defer != "0"
+        self.defer_point = defer
+        self.pending = torch.tensor([1, 0, 0, 0], dtype=torch.int32, device=dev)
+        self.adam_blocks = int(os.environ.get("SEALD_ADAM_BLOCKS", "296"))
         self.hw = F.HalfWeights(self.cfg, dev)
         self.hw.refresh(self.weight_views)
 
@@ -330,20 +342,30 @@ class FusedTrainer:
         W, mode = self.world_size, self.dp_mode
         main, side = torch.cuda.current_stream(), self._side
         ntp = self.n_table_pad
-        if mode in ("fused", "sharded"):
+        # ---- beginning of the step: the march and the deformation forward do not read the hash table, so the table part of the
+        # PREVIOUS step's optimiser (the largest memory pass of a step) runs beside them on the second stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if self.defer_table_update and self.defer_point == "start":
+                n[0] += self._optimizer_table_deferred()
+            if mode == "sharded":  # last step's refreshed table shards (a no-op exchange before the first step)
+                dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
+            elif mode == "fused":
+                # every rank finished writing its fp16 rows into our table, and nobody reads our gradient buffer any more: clear it
+                self._symm[0].barrier(1)
+                self.grads.zero_()
+                n[0] += 2
+        run("select_frame", "march")
+        if self.defer_table_update and self.defer_point == "after_march":
+            # (the march is a chain of dependent bitfield look-ups: its latency suffers beside a pass that saturates HBM, so on one GPU the
+            # table pass only shares the GPU with the tensor-core deformation forward)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                if mode == "sharded":  # last step's refreshed table shards (a no-op exchange before the first step)
-                    dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
-                else:
-                    # every rank finished last step's fused exchange: its fp16 rows are in our table, and nobody reads our gradient
-                    # buffer any more, so it can be cleared for this step
-                    self._symm[0].barrier(1)
-                    self.grads.zero_()
-        run("select_frame", "march", "deform_fwd")
-        if mode in ("fused", "sharded"):
-            main.wait_stream(side)
+                n[0] += self._optimizer_table_deferred()
+        run("deform_fwd")
+        main.wait_stream(side)
         run("grid_fwd", "heads_fwd", "composite_fwd", "loss", "composite_bwd", "composite_loss_fused", "heads_bwd")
+        # ---- the table scatter (atomics) beside the tensor-core backward of the deformation net
         side.wait_stream(main)
         with torch.cuda.stream(side):
             run("grid_scatter")
@@ -353,8 +375,8 @@ class FusedTrainer:
             elif mode == "allreduce":
                 dist.all_reduce(self.grads[:ntp], op=dist.ReduceOp.SUM, group=self.pg)
             elif mode == "fused":
-                # every rank's table gradient is complete -> pull this rank's shard of the sum over NVLink, underneath the tensor-core
-                # backward of the deformation net running on the main stream
+                # every rank's table gradient is complete -> pull this rank's shard of the sum over NVLink, underneath the backward
+                # of the deformation net
                 self._symm[0].barrier(0)
                 _lib.call("seald_dp_reduce_shard", C.cast(self._peer_grads, C.c_void_p), self._mc_grads if self._mc_reduce else None, W,
                           self.rank * self.shard_len, self.shard_len, ptr(self.grad_shard), _lib.stream())
@@ -385,64 +407,112 @@ class FusedTrainer:
         if self.world_size > 1:
             parallel.allreduce_flat_grads(self.grads, self.pg)
 
+    def _adam_table(self, step_dev, loss_scale, found_inf, st):
+        b1, b2 = self.betas
+        if self.dp_mode == "fused":  # own shard (gradient already summed over the ranks) + fp16 rows to every rank's table
+            _lib.call("seald_dp_adam_shard_broadcast", C.cast(self._peer_table16, C.c_void_p), self._mc_table16, self.world_size,
+                      ptr(self.params), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.grad_shard), self.rank * self.shard_len,
+                      self.shard_len, self.lr, b1, b2, self.eps, step_dev, loss_scale, found_inf, st)
+        elif self.dp_mode == "sharded":
+            off = self.rank * self.shard_len
+            _lib.call("seald_adam_step", self.params.data_ptr() + 4 * off, ptr(self.grad_shard), self.exp_avg.data_ptr() + 4 * off,
+                      self.exp_avg_sq.data_ptr() + 4 * off, self.shard_len, self.lr, b1, b2, self.eps, 1, step_dev, loss_scale, found_inf,
+                      ptr(self.shard16), 0, st)
+        else:
+            # beside the march the pass must leave room on every SM (a full-occupancy grid would push the latency-bound march behind it)
+            cap = self.adam_blocks if self.defer_table_update else 0
+            _lib.call("seald_adam_step_ex", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n_table_pad,
+                      self.lr, b1, b2, self.eps, 1, step_dev, loss_scale, found_inf, ptr(self.table16_pad), 1, cap, st)
+        return 1
+
+    def _optimizer_table_deferred(self):
+        """The hash-table pass of the previous step's optimiser, with the overflow decision / step number / loss scale that step
+        stashed (the first call finds found_inf = 1: nothing pending)."""
+        p = self.pending.data_ptr()
+        return self._adam_table(p + 4, p + 8, p, _lib.stream())
+
     def _optimizer(self):
         """GradScaler.step + optimizer.step + GradScaler.update as device kernels (nerf/utils.py:884-886): the whole update is
-        skipped when the overflow flag is set, the loss scale backs off / grows, the fp16 copies are refreshed."""
+        skipped when the overflow flag is set, the loss scale backs off / grows, the fp16 copies are refreshed.  With
+        defer_table_update the hash-table pass is not launched here but at the beginning of the next step (or by flush())."""
         st = _lib.stream()
         b1, b2 = self.betas
         ntp = self.n_table_pad
         found = self.found_inf
-        if self.dp_mode == "fused":
-            # overflow decision + Adam on the shard (gradient summed by seald_dp_reduce_shard) and on the replicated MLP weights (summed
-            # here) + fp16 rows to every rank's table: one kernel
+        n = 3
+        if self.dp_mode == "fused":  # overflow decision over the ranks + Adam on the replicated MLP weights (gradient summed over the peers)
             found = self.found_inf_global
-            _lib.call("seald_dp_adam_broadcast", C.cast(self._peer_grads, C.c_void_p), C.cast(self._peer_table16, C.c_void_p),
-                      self._mc_grads, self._mc_table16, self.world_size, ptr(self.params), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                      ptr(self.grad_shard), self.rank * self.shard_len, self.shard_len, ntp, self.n_weights, self.n_flag, self.lr,
-                      self.lr_net, b1, b2, self.eps, ptr(self.step_dev), ptr(self.loss_scale), ptr(found), st)
-            n = 3
+            _lib.call("seald_dp_adam_weights", C.cast(self._peer_grads, C.c_void_p), self._mc_grads, self.world_size, ptr(self.params),
+                      ptr(self.exp_avg), ptr(self.exp_avg_sq), ntp, self.n_weights, self.n_flag, self.lr_net, b1, b2, self.eps,
+                      ptr(self.step_dev), ptr(self.loss_scale), ptr(found), st)
         else:
-            if self.dp_mode == "sharded":
-                off = self.rank * self.shard_len
-                _lib.call("seald_adam_step", self.params.data_ptr() + 4 * off, ptr(self.grad_shard), self.exp_avg.data_ptr() + 4 * off,
-                          self.exp_avg_sq.data_ptr() + 4 * off, self.shard_len, self.lr, b1, b2, self.eps, 1, ptr(self.step_dev),
-                          ptr(self.loss_scale), ptr(found), ptr(self.shard16), 0, st)
-            else:
-                _lib.call("seald_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ntp, self.lr, b1, b2,
-                          self.eps, 1, ptr(self.step_dev), ptr(self.loss_scale), ptr(found), ptr(self.table16_pad), 1, st)
             _lib.call("seald_adam_step", self.params.data_ptr() + 4 * ntp, self.grads.data_ptr() + 4 * ntp, self.exp_avg.data_ptr() + 4 * ntp,
                       self.exp_avg_sq.data_ptr() + 4 * ntp, self.n_weights, self.lr_net, b1, b2, self.eps, 1, ptr(self.step_dev),
                       ptr(self.loss_scale), ptr(found), None, 1, st)
-            n = 5
+        if not self.defer_table_update:
+            n += self._adam_table(ptr(self.step_dev), ptr(self.loss_scale), ptr(found), st)
         self.hw.refresh(self.weight_views)
-        _lib.call("seald_loss_scale_update", ptr(self.loss_scale), ptr(found), ptr(self.growth_tracker), 2.0, 0.5,
-                  self.growth_interval, ptr(self.step_dev), st)
+        _lib.call("seald_loss_scale_update_stash", ptr(self.loss_scale), ptr(found), ptr(self.growth_tracker), 2.0, 0.5,
+                  self.growth_interval, ptr(self.step_dev), ptr(self.pending), st)
         return n
 
+    def flush(self):
+        """Apply the deferred hash-table update of the last step now (parameters are about to be read: evaluation, checkpoint)."""
+        if not self.defer_table_update:
+            return
+        self._optimizer_table_deferred()
+        self.pending[0] = 1  # nothing pending any more
+        torch.cuda.current_stream().synchronize()
+        if self.dp_mode == "fused":
+            torch.distributed.barrier(group=self.pg)  # every rank's rows have arrived in our fp16 table
+
     def _state(self):
-        return (self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16_pad, self.hw.flat, self.step_dev)
+        return (self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16_pad, self.hw.flat, self.step_dev,
+                self.pending)
 
     def stage_timings(self, reps=20):
-        """Average device time (ms) of every stage, each timed alone with CUDA events on the current stream.
-        Uses the inputs currently staged; the optimiser state is restored afterwards."""
+        """Average device time (ms) of every stage, each timed alone: `reps` back-to-back launches captured in a CUDA graph and
+        replayed, so the host's launch cost is not in the number.  Uses the inputs currently staged; the optimiser state is
+        restored afterwards."""
         out = {}
         stages = [(nm, fn) for nm, fn, _k in self._stages()] + [("optimizer", self._optimizer)]
+        if self.defer_table_update:
+            stages.append(("optimizer_table", self._optimizer_table_deferred))
         snapshot = [t.clone() for t in self._state()]
-        for _, fn in stages[:-1]:  # one full pass so every stage sees valid inputs
+        for _, fn in stages[:len(self._stages())]:  # one full pass so every stage sees valid inputs
             fn()
         torch.cuda.synchronize()
         out["live_samples"] = int(self.counter[0].item())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        S = dict(stages)
+
+        def march_with_reset():  # the march appends to the sample counter: reset it per launch, like the step does
+            S["select_frame"]()
+            S["march"]()
+
         for name, fn in stages:
-            for _ in range(3):
+            if name == "march":
+                fn = march_with_reset
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
                 fn()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    fn()
+            g.replay()
             torch.cuda.synchronize()
             e0.record()
-            for _ in range(reps):
-                fn()
+            g.replay()
             e1.record()
             torch.cuda.synchronize()
             out[name] = e0.elapsed_time(e1) / reps
+            if name == "march":
+                out[name] = max(out[name] - out["select_frame"], 0.0)
+            del g
         torch.cuda.synchronize()
         self._restore(snapshot)
         return out
@@ -450,15 +520,13 @@ class FusedTrainer:
     def sync_params(self):
         """Data parallel with a sharded table: bring every rank's fp16 table and fp32 master copy up to date (before evaluation /
         checkpoints); the per-step exchange of the fp16 table completes at the beginning of the NEXT step."""
+        self.flush()
         if self.dp_mode not in ("fused", "sharded"):
             return
         dist = torch.distributed
         off = self.rank * self.shard_len
         if self.dp_mode == "sharded":
             dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
-        else:
-            torch.cuda.current_stream().synchronize()
-            dist.barrier(group=self.pg)  # every rank's fused kernel (which writes our table) has finished
         dist.all_gather_into_tensor(self.params[:self.n_table_pad], self.params[off:off + self.shard_len].clone(), group=self.pg)
 
     def _restore(self, snap):
