@@ -193,6 +193,7 @@ def seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=20):
     e1.record()
     torch.cuda.synchronize()
     mask_count = int(fr.mask.sum())  # mapped samples in the sample buffer of the last march round
+    trainer.flush()  # (data parallel: also a rank barrier — no rank frees its symmetric buffers while a peer's kernels may still read them)
     return {"ms_per_step": ms, "teacher_ms": e0.elapsed_time(e1) / K, "mapped_samples": mask_count}
 
 
@@ -383,16 +384,21 @@ def main():
                                 "bwd_ms": g["kernels"]["bwd_table_f32"]["ms"], "bytes_per_point": {"fwd": 588, "bwd_f32_table": 2124}}
         print(json.dumps(line), flush=True)
     if world > 1:
-        # release the CUDA graphs that hold captured NCCL kernels before the communicator goes away; a communicator teardown
-        # that blocks must not turn a finished measurement into a hang, so it gets a bounded wait
+        # Teardown with a bounded wait (a communicator teardown that blocks must not turn a finished measurement into a hang).
+        # Order matters: the barrier comes FIRST — rank 0 may still be timing stages whose kernels touch the peers' symmetric
+        # memory, so no rank may free its buffers before every rank got here; then the CUDA graphs holding captured exchange
+        # kernels are released, then the communicator.
+        holder = [trainer]
         del trainer
-        torch.cuda.synchronize()
+
         def _teardown():
             dist.barrier()
+            holder.clear()
+            torch.cuda.synchronize()
             dist.destroy_process_group()
         th = threading.Thread(target=_teardown, daemon=True)
         th.start()
-        th.join(timeout=30)
+        th.join(timeout=60)
         sys.stdout.flush()
         os._exit(0)
 

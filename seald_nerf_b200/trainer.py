@@ -458,13 +458,13 @@ class FusedTrainer:
 
     def flush(self):
         """Apply the deferred hash-table update of the last step now (parameters are about to be read: evaluation, checkpoint)."""
-        if not self.defer_table_update:
-            return
-        self._optimizer_table_deferred()
-        self.pending[0] = 1  # nothing pending any more
-        torch.cuda.current_stream().synchronize()
+        if self.defer_table_update:
+            self._optimizer_table_deferred()
+            self.pending[0] = 1  # nothing pending any more
         if self.dp_mode == "fused":
-            torch.distributed.barrier(group=self.pg)  # every rank's rows have arrived in our fp16 table
+            # every rank's rows have arrived in our fp16 table; also the point after which a rank may free its symmetric buffers
+            torch.cuda.current_stream().synchronize()
+            torch.distributed.barrier(group=self.pg)
 
     def _state(self):
         return (self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16_pad, self.hw.flat, self.step_dev,
