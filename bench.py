@@ -332,9 +332,12 @@ def main():
             "composite_fwd": ("hbm", 24.0 * m_live + 32.0 * N_RAYS),
             "composite_bwd": ("hbm", 40.0 * m_live + 48.0 * N_RAYS),
             "composite_loss_fused": ("hbm", 64.0 * m_live + 104.0 * N_RAYS),
+            "optimizer": ("hbm", 34.0 * trainer.n_params),   # (1 GPU: table + MLP weights in the same stage; the weights are 1% of it)
             # Adam over the fp32 table: p, m, v read + written (24 B), gradient read + cleared (8 B), fp16 copy written (2 B) per parameter
             "optimizer_table": ("hbm", 34.0 * (trainer.shard_len if trainer.dp_mode in ("fused", "sharded") else trainer.n_table_pad)),
         }
+        if trainer.defer_table_update or trainer.dp_mode != "single":
+            work.pop("optimizer")  # there it is only the MLP-weight update + fp16 repack + loss-scale kernels
         dom = max((k for k in st if k in work), key=lambda k: st[k])
         bound, amount = work[dom]
         sec = st[dom] * 1e-3
@@ -342,7 +345,17 @@ def main():
             achieved, peak, unit = amount / sec / 1e12, tf_burst, "TFLOP/s"
         else:
             achieved, peak, unit = amount / sec / 1e9, hbm, "GB/s"
-        roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of the same step (profiles/, per round)
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r1c_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            ent = tj["per_launch_dram_bytes"].get(dom)
+            if ent and world == 1:
+                traffic, traffic_src = ent["read"] + ent["write"], "%s: %s" % (tj["source"], ent["kernel"])
+        roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": traffic,
+                    "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
+                    "algorithmic_per_launch": amount,
                     "peak_source": which + (" burst" if bound == "tensor" else ""), "ms": st[dom],
                     "stage_ms": {k: round(v, 4) for k, v in st.items()}, "live_samples": m_live}
 
