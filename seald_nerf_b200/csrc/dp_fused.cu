@@ -51,11 +51,15 @@ __device__ __forceinline__ float4 reduce_f32x4(const DpPeers& peers, const float
     if constexpr (MC) {
         return mc_ld_reduce_f32x4(mc_grads + i);
     } else {
+        // all peer loads in flight before the first add (remote latency is microseconds): fixed unroll, predicated on the world size
+        float4 b[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; r++)
+            if (r < world) b[r] = *reinterpret_cast<const float4*>(peers.grads[r] + i);  // (weak load: ordered by the caller's barrier)
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < world; r++) {
-            const float4 b = *reinterpret_cast<const float4*>(peers.grads[r] + i);  // (weak load: ordered by the caller's barrier)
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; r++)
+            if (r < world) { a.x += b[r].x; a.y += b[r].y; a.z += b[r].z; a.w += b[r].w; }
         return a;
     }
 }

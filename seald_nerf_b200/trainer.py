@@ -97,8 +97,11 @@ class FusedTrainer:
             self._peer_table16 = (C.c_void_p * W)(*[int(x) for x in ht.buffer_ptrs])
             self._mc_grads = int(hg.multicast_ptr) if use_mc else None      # in-switch reduction / replication (NVLS) when mapped
             self._mc_table16 = int(ht.multicast_ptr) if use_mc else None
-            # the shard sum: peer loads measured faster than multimem.ld_reduce on 2 GPUs (480 vs 290 GB/s inbound); switchable
-            self._mc_reduce = use_mc and os.environ.get("SEALD_DP_MULTICAST_REDUCE", "0") == "1"
+            # the shard sum, measured (scripts/dp_kernel_bench.py): 2 GPUs peer loads 0.051 ms vs multimem.ld_reduce 0.085 ms; 8 GPUs peer
+            # loads 0.096 ms (43 MB inbound) vs in-switch reduction 0.072 ms (6 MB inbound) -> multicast from 4 ranks up.  The small MLP
+            # region is always summed with peer loads (8 GPUs: 0.040 vs 0.056 ms for the stage).
+            mcr = os.environ.get("SEALD_DP_MULTICAST_REDUCE", "auto")
+            self._mc_reduce = use_mc and (W >= 4 if mcr == "auto" else mcr == "1")
             self.found_inf_global = torch.zeros(1, **i32)
             self.grad_shard = torch.zeros(self.shard_len, **f32)
         else:
@@ -139,16 +142,21 @@ class FusedTrainer:
         self.defer_point = defer
         self.pending = torch.tensor([1, 0, 0, 0], dtype=torch.int32, device=dev)
         self.adam_blocks = int(os.environ.get("SEALD_ADAM_BLOCKS", "296"))
+        # one GPU: the scatter beside the deformation backward measured SLOWER than in line (0.414 vs 0.400-0.408 ms: its 2656 short CTAs
+        # delay the persistent tensor-core kernel's CTAs); the second stream is for the data-parallel exchange
+        self.fork_scatter = os.environ.get("SEALD_FORK", "0") != "0"
         self.hw = F.HalfWeights(self.cfg, dev)
         self.hw.refresh(self.weight_views)
 
         # ---- per-step buffers ----------------------------------------------------------------------------------
         N, M = self.N, self.M
-        self.rays_o = torch.zeros(N, 3, **f32)
-        self.rays_d = torch.zeros(N, 3, **f32)
-        self.gt = torch.zeros(N, 3, **f32)
+        # the step's inputs live in ONE device buffer [rays_o | rays_d | gt | time] so that host batches arrive with a single H2D copy
+        self.inputs = torch.zeros(9 * N + 4, **f32)
+        self.rays_o = self.inputs[0:3 * N].view(N, 3)
+        self.rays_d = self.inputs[3 * N:6 * N].view(N, 3)
+        self.gt = self.inputs[6 * N:9 * N].view(N, 3)
         self.bg = torch.ones(N, 3, **f32)
-        self.time = torch.zeros(1, **f32)
+        self.time = self.inputs[9 * N:9 * N + 1]
         self.noises = torch.zeros(N, **f32)
         self.nears = torch.empty(N, **f32)
         self.fars = torch.empty(N, **f32)
@@ -178,10 +186,11 @@ class FusedTrainer:
         self.growth_tracker = torch.zeros(1, **i32)
         self.step_dev = torch.zeros(1, **i32)  # optimiser step counter (device side: the optimiser is graph-replayed)
         # pinned staging for the end-to-end path
-        self.h_rays_o = torch.zeros(N, 3).pin_memory()
-        self.h_rays_d = torch.zeros(N, 3).pin_memory()
-        self.h_gt = torch.zeros(N, 3).pin_memory()
-        self.h_time = torch.zeros(1).pin_memory()
+        self.h_inputs = torch.zeros(9 * N + 4).pin_memory()
+        self.h_rays_o = self.h_inputs[0:3 * N].view(N, 3)
+        self.h_rays_d = self.h_inputs[3 * N:6 * N].view(N, 3)
+        self.h_gt = self.h_inputs[6 * N:9 * N].view(N, 3)
+        self.h_time = self.h_inputs[9 * N:9 * N + 1]
         self.h_loss = torch.zeros(1).pin_memory()
         self._graph = None
         self.launches_per_step = 0
@@ -216,14 +225,11 @@ class FusedTrainer:
         self.h_rays_d.copy_(rays_d.reshape(-1, 3))
         self.h_gt.copy_(gt_rgb.reshape(-1, 3))
         self.h_time[0] = float(time)
-        self.rays_o.copy_(self.h_rays_o, non_blocking=True)
-        self.rays_d.copy_(self.h_rays_d, non_blocking=True)
-        self.gt.copy_(self.h_gt, non_blocking=True)
-        self.time.copy_(self.h_time, non_blocking=True)
+        self.inputs.copy_(self.h_inputs, non_blocking=True)
 
     @property
     def h2d_bytes_per_step(self):
-        return self.N * 3 * 4 * 3 + 4
+        return self.inputs.numel() * 4
 
     # ------------------------------------------------------------------------------------------------------------
     def _stages(self):
@@ -366,8 +372,10 @@ class FusedTrainer:
         main.wait_stream(side)
         run("grid_fwd", "heads_fwd", "composite_fwd", "loss", "composite_bwd", "composite_loss_fused", "heads_bwd")
         # ---- the table scatter (atomics) beside the tensor-core backward of the deformation net
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
+        fork = self.fork_scatter or mode in ("fused", "sharded", "allreduce")
+        if fork:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if fork else main):
             run("grid_scatter")
             if mode == "sharded":
                 dist.reduce_scatter_tensor(self.grad_shard, self.grads[:ntp], op=dist.ReduceOp.SUM, group=self.pg)
@@ -442,7 +450,7 @@ class FusedTrainer:
         n = 3
         if self.dp_mode == "fused":  # overflow decision over the ranks + Adam on the replicated MLP weights (gradient summed over the peers)
             found = self.found_inf_global
-            _lib.call("seald_dp_adam_weights", C.cast(self._peer_grads, C.c_void_p), self._mc_grads, self.world_size, ptr(self.params),
+            _lib.call("seald_dp_adam_weights", C.cast(self._peer_grads, C.c_void_p), None, self.world_size, ptr(self.params),
                       ptr(self.exp_avg), ptr(self.exp_avg_sq), ntp, self.n_weights, self.n_flag, self.lr_net, b1, b2, self.eps,
                       ptr(self.step_dev), ptr(self.loss_scale), ptr(found), st)
         else:

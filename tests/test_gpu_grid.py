@@ -203,3 +203,51 @@ def test_grid_encoder_module_autograd(cuda_dev):
     enc.zero_grad()
     y32 = enc(x.detach(), bound=1)
     assert y32.dtype == torch.float32
+
+
+def test_split_backward_equals_combined_and_overflow_flag(cuda_dev):
+    """seald_grid_encode_backward_table + _input == seald_grid_encode_backward (same kernels, separate launches), and the
+    overflow flag of the table scatter is raised exactly when the table gradient is non-finite (GradScaler's found_inf)."""
+    from seald_nerf_b200 import _lib
+    from seald_nerf_b200._lib import ptr, F16, F32
+    D, L, C, log2_T, base, desired = 3, 16, 2, 19, 16, 2048
+    offsets, S, _ = _cfg(D, L, C, log2_T, base, desired)
+    d = cuda_dev
+    B = 5000
+    rng = np.random.default_rng(5)
+    tx = torch.from_numpy(_points(B, D, 3)).to(d)
+    to = torch.from_numpy(offsets).to(d)
+    tt = torch.from_numpy((rng.standard_normal((int(offsets[-1]), C)) * 0.1).astype(np.float32)).to(d).half()
+    tg = torch.from_numpy(rng.standard_normal((B, L * C)).astype(np.float32)).to(d).half()
+    ga, gxa = torch.zeros(int(offsets[-1]), C, device=d), torch.empty(B, D, device=d)
+    _lib.call("seald_grid_encode_backward", ptr(tg), ptr(tx), ptr(tt), ptr(to), ptr(ga), None, ptr(gxa), B, D, C, L, S, base, 0, 0, 0, F16,
+              F32, None, _lib.stream())
+    gb, gxb = torch.zeros_like(ga), torch.empty_like(gxa)
+    flag = torch.zeros(1, dtype=torch.int32, device=d)
+    _lib.call("seald_grid_encode_backward_table", ptr(tg), ptr(tx), ptr(to), ptr(gb), B, D, C, L, S, base, 0, 0, 0, F16, F32, None,
+              ptr(flag), _lib.stream())
+    _lib.call("seald_grid_encode_backward_input", ptr(tg), ptr(tx), ptr(tt), ptr(to), None, ptr(gxb), B, D, C, L, S, base, 0, 0, 0, F16,
+              None, _lib.stream())
+    assert torch.equal(gxa, gxb)
+    torch.testing.assert_close(ga, gb, rtol=1e-5, atol=1e-5 * float(ga.abs().max()))  # (atomic order)
+    assert int(flag) == 0 and bool(torch.isfinite(gb).all())
+    # live-row count: rows >= *b_dev are not consumed, an inf there must not raise the flag ...
+    tg2 = tg.clone()
+    tg2[4000, 7] = float("inf")
+    b_dev = torch.tensor([3000], dtype=torch.int32, device=d)
+    gb.zero_()
+    _lib.call("seald_grid_encode_backward_table", ptr(tg2), ptr(tx), ptr(to), ptr(gb), B, D, C, L, S, base, 0, 0, 0, F16, F32, ptr(b_dev),
+              ptr(flag), _lib.stream())
+    assert int(flag) == 0 and bool(torch.isfinite(gb).all())
+    # ... and one in a consumed row must, together with a non-finite table gradient
+    gb.zero_()
+    _lib.call("seald_grid_encode_backward_table", ptr(tg2), ptr(tx), ptr(to), ptr(gb), B, D, C, L, S, base, 0, 0, 0, F16, F32, None,
+              ptr(flag), _lib.stream())
+    assert int(flag) != 0 and not bool(torch.isfinite(gb).all())
+    # an out-of-range point contributes nothing (gridencoder.cu:276-281): its inf is not consumed either
+    tg3 = tg.clone()
+    tg3[2, 0] = float("nan")  # _points() puts row 2 just outside [0,1]
+    flag.zero_(); gb.zero_()
+    _lib.call("seald_grid_encode_backward_table", ptr(tg3), ptr(tx), ptr(to), ptr(gb), B, D, C, L, S, base, 0, 0, 0, F16, F32, None,
+              ptr(flag), _lib.stream())
+    assert int(flag) == 0 and bool(torch.isfinite(gb).all())
