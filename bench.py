@@ -304,6 +304,24 @@ def main():
         seald = seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=max(20, K // 4))
     ms_seald = seald["ms_per_step"] if seald else 0.0
 
+    # ---- occupancy-grid refresh (update_extra_state, every 100 steps in main_dnerf.py): fused device pipeline, frames sharded ----
+    occ = None
+    if not args.no_extras:
+        saved = (model.density_grid.clone(), model.density_bitfield.clone(), model.iter_density, model.mean_density)
+        occ = {}
+        for name, it in (("full_sweep_ms", 0), ("partial_ms", 16)):
+            model.iter_density = it
+            trainer.update_extra_state()  # warm (allocations)
+            model.iter_density = it
+            barrier()
+            t0 = time.perf_counter()
+            trainer.update_extra_state()
+            barrier()
+            occ[name] = (time.perf_counter() - t0) * 1e3
+        model.density_grid.copy_(saved[0]); model.density_bitfield.copy_(saved[1])
+        model.iter_density, model.mean_density = saved[2], saved[3]
+        trainer.refresh_occupancy()
+
     if world > 1:
         tt = torch.tensor([ms, ms_e2e, ms_frame, ms_seald], device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -389,6 +407,11 @@ def main():
                              "teacher_ms": seald["teacher_ms"], "mapped_samples": seald["mapped_samples"],
                              "workload": "teacher eval render of the 4096-ray batch (bbox mapper 0.3^3, +0.2x, 30deg about y, fused in march) "
                                          "+ student train step (frozen deform net)"}
+        if occ:
+            step_ms = ms / K
+            line["occupancy_update"] = dict(occ, unit="wall ms per update_extra_state (64 time frames x 128^3 cells, sharded over the ranks, incl. its host syncs)",
+                                            field_queries={"full_sweep": 64 * 128 ** 3, "partial": 64 * 128 ** 3 // 2},
+                                            amortised_rays_per_s_every_100_steps=total_rays / ((step_ms + occ["partial_ms"] / 100.0) * 1e-3))
         if not args.no_extras:
             g = microbench.grid_encoder(device, 22, 3, "hash", torch.float16, reps=10, hbm_gbs=hbm)
             line["hashgrid"] = {"points": g["B"], "levels": 16, "table": "2^19 x 2 fp16", "fwd_GBs": g["kernels"]["fwd"]["GB/s"],

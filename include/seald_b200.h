@@ -382,6 +382,19 @@ int seald_dp_adam_shard_broadcast(void* const* peer_table16, void* mc_table16, i
                                   float beta2, float eps, const int32_t* step_dev, const float* loss_scale,
                                   const int32_t* found_inf, seald_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Occupancy-grid refresh on the device (NeRFRenderer.update_extra_state, dnerf/renderer.py:453-555).
+ *   seald_occ_cell_points  sample point of cell j: (2 c / (H-1) - 1) * span + (rand * 2 - 1) * half_cell in the reference's fp32
+ *                          operation order; c = coords[j] or, when coords == NULL, the j-th cell of custom_meshgrid(X, Y, Z)
+ *                          (:477-497); indices[j] = Morton code of c (optional).
+ *   seald_occ_store        tmp[indices[j]] = sigma[j] * density_scale          (`tmp_grid[t, cas, indices] = sigmas`, :499)
+ *   seald_occ_ema_max      grid = max(grid * decay, tmp) where grid >= 0 and tmp >= 0 (:541-543); tmp is reset to -1.
+ * ------------------------------------------------------------------------------------------------ */
+int seald_occ_cell_points(const int32_t* coords, const float* rand3, uint32_t n, uint32_t H, float span, float half_cell,
+                          float* xyzs, int32_t* indices, seald_stream_t stream);
+int seald_occ_store(const float* sigma, const int32_t* indices, uint32_t n, float density_scale, float* tmp, seald_stream_t stream);
+int seald_occ_ema_max(float* grid, float* tmp, uint32_t n, float decay, seald_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,93 @@
+// occupancy.cu — device side of the occupancy-grid refresh (NeRFRenderer.update_extra_state, dnerf/renderer.py:453-555).
+//
+// The reference builds, per time frame, the cell sample points with ~10 torch kernels (meshgrid, cat, morton3D, scale, two
+// rand_like passes), queries the density field, scatters into a 512 MiB temporary and does three full-tensor passes for the
+// decayed maximum.  Here one kernel produces the jittered sample points + their Morton cell indices, the field kernels run on
+// preallocated buffers, one kernel stores the scaled densities into a per-frame temporary and one applies
+// grid = max(grid * decay, tmp) where both are >= 0 (dnerf/renderer.py:541-543) and resets the temporary.
+// Arithmetic keeps the reference's fp32 operation order (explicit _rn intrinsics: no FMA contraction), so with the same
+// uniform random numbers the points are bit-identical to the torch expressions.
+#include "common.cuh"
+
+namespace seald {
+
+__device__ __forceinline__ uint32_t occ_expand_bits(uint32_t v) {  // raymarching.cu:56-62
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+// coords == nullptr: point j is cell (x, y, z) = (j / H^2, (j / H) % H, j % H), the order of custom_meshgrid(X, Y, Z)
+// (dnerf/renderer.py:481-483); else coords[j] (the random / re-sampled cells of the partial pass, :507-518).
+__global__ void k_occ_cell_points(const int* __restrict__ coords, const float* __restrict__ rand3, const uint32_t n, const uint32_t H,
+                                  const float span, const float half_cell, float* __restrict__ xyzs, int* __restrict__ indices) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t c[3];
+    if (coords) {
+        c[0] = (uint32_t)coords[j * 3]; c[1] = (uint32_t)coords[j * 3 + 1]; c[2] = (uint32_t)coords[j * 3 + 2];
+    } else {
+        c[2] = j % H; c[1] = (j / H) % H; c[0] = j / (H * H);
+    }
+    if (indices) indices[j] = (int)(occ_expand_bits(c[0]) | (occ_expand_bits(c[1]) << 1) | (occ_expand_bits(c[2]) << 2));
+    // torch divides a CUDA tensor by a host scalar as a * (1 / b) with the reciprocal rounded to fp32 (BinaryDivTrueKernel.cu)
+    const float inv_hm1 = __fdiv_rn(1.0f, (float)(H - 1));
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        // xyzs = 2 * coords.float() / (H - 1) - 1;  cas_xyzs = xyzs * (bound - half);  cas_xyzs += (rand * 2 - 1) * half
+        const float x = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, (float)c[d]), inv_hm1), 1.0f);
+        const float jit = __fmul_rn(__fsub_rn(__fmul_rn(rand3[j * 3 + d], 2.0f), 1.0f), half_cell);
+        xyzs[j * 3 + d] = __fadd_rn(__fmul_rn(x, span), jit);
+    }
+}
+
+// tmp[indices[j]] = sigma[j] * density_scale (duplicates: one writer wins, as in `tmp_grid[t, cas, indices] = sigmas`)
+__global__ void k_occ_store(const float* __restrict__ sigma, const int* __restrict__ indices, const uint32_t n, const float density_scale,
+                            float* __restrict__ tmp) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    tmp[indices[j]] = __fmul_rn(sigma[j], density_scale);
+}
+
+// grid = max(grid * decay, tmp) where grid >= 0 and tmp >= 0; tmp reset to -1 for the next frame.  float4 over the frame.
+__global__ void k_occ_ema_max(float* __restrict__ grid, float* __restrict__ tmp, const uint32_t n4, const float decay) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 g = reinterpret_cast<float4*>(grid)[i];
+    const float4 t = reinterpret_cast<const float4*>(tmp)[i];
+    bool any = false;
+    if (g.x >= 0 && t.x >= 0) { g.x = fmaxf(__fmul_rn(g.x, decay), t.x); any = true; }
+    if (g.y >= 0 && t.y >= 0) { g.y = fmaxf(__fmul_rn(g.y, decay), t.y); any = true; }
+    if (g.z >= 0 && t.z >= 0) { g.z = fmaxf(__fmul_rn(g.z, decay), t.z); any = true; }
+    if (g.w >= 0 && t.w >= 0) { g.w = fmaxf(__fmul_rn(g.w, decay), t.w); any = true; }
+    if (any) reinterpret_cast<float4*>(grid)[i] = g;
+    if (t.x != -1.0f || t.y != -1.0f || t.z != -1.0f || t.w != -1.0f) reinterpret_cast<float4*>(tmp)[i] = make_float4(-1.f, -1.f, -1.f, -1.f);
+}
+
+}  // namespace seald
+
+using namespace seald;
+
+extern "C" int seald_occ_cell_points(const int32_t* coords, const float* rand3, uint32_t n, uint32_t H, float span, float half_cell,
+                                     float* xyzs, int32_t* indices, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!rand3 || !xyzs || H < 2 || H > 1024) return SEALD_E_BADARG;
+    k_occ_cell_points<<<div_up(n, 256u), 256, 0, to_stream(stream)>>>(coords, rand3, n, H, span, half_cell, xyzs, indices);
+    return launch_status();
+}
+
+extern "C" int seald_occ_store(const float* sigma, const int32_t* indices, uint32_t n, float density_scale, float* tmp, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!sigma || !indices || !tmp) return SEALD_E_BADARG;
+    k_occ_store<<<div_up(n, 256u), 256, 0, to_stream(stream)>>>(sigma, indices, n, density_scale, tmp);
+    return launch_status();
+}
+
+extern "C" int seald_occ_ema_max(float* grid, float* tmp, uint32_t n, float decay, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!grid || !tmp || n % 4 || ((uintptr_t)grid | (uintptr_t)tmp) % 16) return SEALD_E_BADARG;
+    k_occ_ema_max<<<div_up(n / 4, 256u), 256, 0, to_stream(stream)>>>(grid, tmp, n / 4, decay);
+    return launch_status();
+}

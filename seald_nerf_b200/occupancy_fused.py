@@ -1,0 +1,113 @@
+"""FusedOccupancy — NeRFRenderer.update_extra_state (dnerf/renderer.py:453-555) as a preallocated, sync-free device pipeline.
+
+Same schedule as the reference (full sweep of every cell of every time frame for the first 16 calls, then H^3/4 random cells +
+H^3/4 re-sampled occupied cells per frame), same random-number consumption for the full sweep (so it is bit-identical to the
+torch-composed `NeRFRenderer.update_extra_state` of this package under the same seed), but per time frame it is
+    1 kernel   jittered sample points + Morton indices          (csrc/occupancy.cu; the reference: ~10 torch kernels)
+    3 kernels  density query: tcgen05 deformation net -> hash grid -> sigma head, on buffers allocated ONCE for H^3 points
+    2 kernels  store into a per-frame temporary, decayed maximum (no 512 MiB temporaries, no boolean-mask passes)
+followed by ONE packbits launch over all time frames.  The occupied-cell re-sampling of the partial pass picks the k-th occupied
+cell through a prefix sum + binary search on the device (the reference synchronises per frame for `nonzero`).
+"""
+import torch
+
+from . import _lib
+from . import field as F
+from . import raymarching
+from ._lib import ptr
+
+
+class FusedOccupancy:
+    def __init__(self, model, hw=None, table16=None, rank=0, world_size=1, process_group=None):
+        self.model = model
+        # data parallel: the time frames are dealt to the ranks in contiguous blocks and the refreshed grids all-gathered
+        self.rank, self.world_size, self.pg = int(rank), int(world_size), process_group
+        if model.time_size % self.world_size:
+            raise ValueError("time_size must be divisible by the number of ranks")
+        m = model
+        dev = m.density_grid.device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedOccupancy needs the model on a CUDA device (no CPU fallback)")
+        self.H = int(m.grid_size)
+        self.n_full = self.H ** 3
+        self.cfg = m._field_cfg
+        self.hw, self.table16 = hw, table16  # shared with a FusedTrainer (already fp16 / packed); else refreshed per update
+        self.ws = F.FieldWorkspace(self.cfg, self.n_full, dev, training=False)
+        self.xyzs = torch.empty(self.n_full, 3, device=dev)
+        self.indices = torch.empty(self.n_full, dtype=torch.int32, device=dev)
+        self.tmp = torch.full((self.n_full,), -1.0, device=dev)
+        self.time_dev = torch.zeros(1, device=dev)
+
+    def _weights(self):
+        m = self.model
+        if self.hw is not None:
+            return self.hw, self.table16
+        hw = m._half_weights()
+        hw.refresh([w.detach() for w in m.mlp_weights()])
+        return hw, m.encoder.embeddings.detach().to(torch.float16)
+
+    def _query_and_store(self, n, t, cas, hw, table16):
+        """density at self.xyzs[:n] (time self.time_dev) -> tmp[indices] -> density_grid[t, cas] = max(grid * decay, tmp)"""
+        m, cfg = self.model, self.cfg
+        saved, cfg.density_scale = cfg.density_scale, 1.0  # like NeRFNetwork.density: the renderer applies density_scale itself
+        try:
+            F.field_density(cfg, hw, self.ws, self.xyzs, self.time_dev, table16, m.encoder.offsets, M=n)
+        finally:
+            cfg.density_scale = saved
+        st = _lib.stream()
+        _lib.call("seald_occ_store", ptr(self.ws.sigma), ptr(self.indices), n, float(m.density_scale), ptr(self.tmp), st)
+        _lib.call("seald_occ_ema_max", ptr(m.density_grid[t, cas]), ptr(self.tmp), self.n_full, self._decay, st)
+
+    @torch.no_grad()
+    def update(self, decay=0.95):
+        m = self.model
+        if not m.cuda_ray:
+            return
+        H, n_full = self.H, self.n_full
+        dev = m.density_grid.device
+        hw, table16 = self._weights()
+        self._decay = float(decay)
+        half_time = 0.5 / m.time_size
+        st = _lib.stream
+        full = m.iter_density < 16
+        if not full and m.iter_density >= 100:
+            pass  # the reference stops re-sampling after 100 refreshes (only decay-free bookkeeping below)
+        else:
+            n_rand = n_full // 4
+            per = m.time_size // self.world_size
+            for t in range(self.rank * per, (self.rank + 1) * per):
+                time = m.times[t]
+                for cas in range(m.cascade):
+                    bound = min(2 ** cas, m.bound)
+                    half_cell = bound / H
+                    if full:
+                        n = n_full
+                        rnd = torch.rand(n, 3, device=dev)          # == torch.rand_like(cas_xyzs) of the reference loop
+                        _lib.call("seald_occ_cell_points", None, ptr(rnd), n, H, float(bound - half_cell), float(half_cell), ptr(self.xyzs),
+                                  ptr(self.indices), st())
+                    else:
+                        coords = torch.randint(0, H, (n_rand, 3), device=dev, dtype=torch.int32)
+                        # k-th occupied cell of this frame, k uniform: prefix sum + binary search on the device (no nonzero / sync)
+                        csum = torch.cumsum((m.density_grid[t, cas] > 0).to(torch.int32), 0)
+                        k = (torch.rand(n_rand, device=dev) * csum[-1]).to(torch.int32)
+                        occ = torch.searchsorted(csum, k + 1).clamp_(max=n_full - 1).to(torch.int32)
+                        occ_coords = raymarching.morton3D_invert(occ)
+                        coords = torch.cat([coords, occ_coords.to(torch.int32)], 0).contiguous()
+                        n = coords.shape[0]
+                        rnd = torch.rand(n, 3, device=dev)
+                        _lib.call("seald_occ_cell_points", ptr(coords), ptr(rnd), n, H, float(bound - half_cell), float(half_cell),
+                                  ptr(self.xyzs), ptr(self.indices), st())
+                    self.time_dev.copy_((time + (torch.rand_like(time) * 2 - 1) * half_time).reshape(-1)[:1])
+                    self._query_and_store(n, t, cas, hw, table16)
+            if self.world_size > 1:
+                mine = m.density_grid[self.rank * per:(self.rank + 1) * per].clone()
+                torch.distributed.all_gather_into_tensor(m.density_grid.view(-1), mine.view(-1), group=self.pg)
+        m.mean_density = torch.mean(m.density_grid.clamp(min=0)).item()
+        m.iter_density += 1
+        density_thresh = min(m.mean_density, m.density_thresh)
+        # density_grid [T, cascade, H^3] and density_bitfield [T, cascade * H^3 / 8] are contiguous: one launch packs every frame
+        raymarching.packbits(m.density_grid.view(1, -1), density_thresh, m.density_bitfield.view(-1))
+        total_step = min(16, m.local_step)
+        if total_step > 0:
+            m.mean_count = int(m.step_counter[:total_step, 0].sum().item() / total_step)
+        m.local_step = 0

@@ -193,6 +193,7 @@ class FusedTrainer:
         self.h_time = self.h_inputs[9 * N:9 * N + 1]
         self.h_loss = torch.zeros(1).pin_memory()
         self._graph = None
+        self._occ = None
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------------------------
@@ -202,6 +203,17 @@ class FusedTrainer:
         m = self.model
         for t in range(m.density_bitfield.shape[0]):
             raymarching.occupancy_aabb(m.density_bitfield[t], m.cascade, m.grid_size, m.bound, 2, out=self.occ_all[t])
+
+    def update_extra_state(self, decay=0.95):
+        """Occupancy-grid refresh (NeRFRenderer.update_extra_state, dnerf/renderer.py:453-555) through the fused device pipeline
+        (occupancy_fused.py) on the trainer's own fp16 weights / table; time frames are sharded over the ranks."""
+        from .occupancy_fused import FusedOccupancy
+        self.flush()  # the density field must see the last update on every rank
+        if self._occ is None:
+            self._occ = FusedOccupancy(self.model, hw=self.hw, table16=self.table16, rank=self.rank, world_size=self.world_size,
+                                       process_group=self.pg)
+        self._occ.update(decay)
+        self.refresh_occupancy()
 
     def set_inputs(self, rays_o, rays_d, time, gt_rgb, bg_color=None):
         """Device-resident inputs of the next step (copied into the static buffers the graph reads)."""

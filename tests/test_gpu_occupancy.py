@@ -1,0 +1,96 @@
+"""GPU parity of the fused occupancy-grid refresh (seald_nerf_b200/occupancy_fused.py, csrc/occupancy.cu) against the
+torch-composed restatement of NeRFRenderer.update_extra_state (dnerf/renderer.py:453-555) in seald_nerf_b200/dnerf/renderer.py.
+
+Full sweep (first 16 refreshes): same seed -> same uniform numbers in the same order -> the sample points are BIT-identical
+(the kernel keeps torch's fp32 operation order), the density kernels are the same, so density_grid, mean_density and the
+bitfield must be bit-exact.  Partial pass: the occupied cells are re-sampled through a device prefix sum instead of
+`nonzero` + `randint` (different random stream), so it is checked through the invariants of the update rule."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(dev, seed=0):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    m = bench.build_scene(dev, seed)
+    m.encoder.embeddings.data.uniform_(-0.5, 0.5)  # a field with structure (random-init tables give sigma ~ exp(0))
+    return m
+
+
+def test_cell_points_bit_identical_to_torch_expressions(cuda_dev):
+    from seald_nerf_b200 import _lib, raymarching
+    from seald_nerf_b200._lib import ptr
+    d = cuda_dev
+    H = 128
+    for bound in (1.0, 2.0):
+        half = bound / H
+        torch.manual_seed(3)
+        xs = torch.arange(H, dtype=torch.int32, device=d)
+        xx, yy, zz = torch.meshgrid(xs, xs, xs, indexing="ij")
+        coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+        xyzs = 2 * coords.float() / (H - 1) - 1
+        cas = xyzs * (bound - half)
+        rnd = torch.rand_like(cas)
+        cas += (rnd * 2 - 1) * half
+        out = torch.empty(H ** 3, 3, device=d)
+        idx = torch.empty(H ** 3, dtype=torch.int32, device=d)
+        _lib.call("seald_occ_cell_points", None, ptr(rnd), H ** 3, H, float(bound - half), float(half), ptr(out), ptr(idx), _lib.stream())
+        assert torch.equal(out, cas)
+        assert torch.equal(idx, raymarching.morton3D(coords))
+        # explicit coordinates (partial pass)
+        c2 = torch.randint(0, H, (5001, 3), device=d, dtype=torch.int32)
+        r2 = torch.rand(5001, 3, device=d)
+        ref = (2 * c2.float() / (H - 1) - 1) * (bound - half)
+        ref += (r2 * 2 - 1) * half
+        out2 = torch.empty(5001, 3, device=d)
+        _lib.call("seald_occ_cell_points", ptr(c2), ptr(r2), 5001, H, float(bound - half), float(half), ptr(out2), None, _lib.stream())
+        assert torch.equal(out2, ref)
+
+
+def test_full_sweep_bit_exact_vs_torch_composed_update(cuda_dev):
+    from seald_nerf_b200.occupancy_fused import FusedOccupancy
+    a, b = _model(cuda_dev), _model(cuda_dev)
+    for m in (a, b):
+        m.time_size_used = m.time_size
+        m.iter_density = 0
+        m.local_step = 0
+    torch.manual_seed(11)
+    a.update_extra_state()
+    torch.manual_seed(11)
+    FusedOccupancy(b).update()
+    assert a.iter_density == b.iter_density == 1
+    assert torch.equal(a.density_grid, b.density_grid)
+    assert a.mean_density == b.mean_density
+    assert torch.equal(a.density_bitfield, b.density_bitfield)
+    assert 0 < int(b.density_bitfield.count_nonzero())
+
+
+def test_partial_pass_invariants(cuda_dev):
+    from seald_nerf_b200 import raymarching
+    from seald_nerf_b200.occupancy_fused import FusedOccupancy
+    m = _model(cuda_dev)
+    m.density_grid[:, :, ::97] = -1.0  # untrained cells (mark_untrained_grid) must never be touched
+    m.iter_density = 16
+    before = m.density_grid.clone()
+    torch.manual_seed(5)
+    FusedOccupancy(m).update(decay=0.95)
+    after = m.density_grid
+    assert m.iter_density == 17
+    assert torch.equal(after[before < 0], before[before < 0])
+    changed = after != before
+    frac = float(changed.float().mean())
+    # H^3/4 random cells (with replacement) + H^3/4 occupied re-samples per frame touch between ~15% and 50% of the cells
+    assert 0.10 < frac < 0.55, frac
+    assert bool((after[changed] >= before[changed] * 0.95 - 1e-6).all())  # max(grid * decay, sigma) >= grid * decay
+    # occupied cells are re-sampled more often than empty ones
+    occ = before > 0
+    assert float(changed[occ].float().mean()) > float(changed[~occ & (before >= 0)].float().mean())
+    thresh = min(m.mean_density, m.density_thresh)
+    assert abs(m.mean_density - float(after.clamp(min=0).mean())) < 1e-7
+    for t in (0, 31, 63):
+        assert torch.equal(m.density_bitfield[t], raymarching.packbits(after[t], thresh))
