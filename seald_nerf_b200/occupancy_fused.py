@@ -32,11 +32,15 @@ class FusedOccupancy:
         self.n_full = self.H ** 3
         self.cfg = m._field_cfg
         self.hw, self.table16 = hw, table16  # shared with a FusedTrainer (already fp16 / packed); else refreshed per update
-        self.ws = F.FieldWorkspace(self.cfg, self.n_full, dev, training=False)
-        self.xyzs = torch.empty(self.n_full, 3, device=dev)
-        self.indices = torch.empty(self.n_full, dtype=torch.int32, device=dev)
-        self.tmp = torch.full((self.n_full,), -1.0, device=dev)
-        self.time_dev = torch.zeros(1, device=dev)
+        # Two frame pipelines on two streams: the tensor-core deformation net of one time frame runs beside the gather-bound hash-grid
+        # pass of the previous one (different SM resources).  Random numbers are drawn on the host thread in the reference's order, so
+        # the result does not depend on how the streams interleave.
+        self.n_pipes = 2
+        self.pipes = []
+        for _ in range(self.n_pipes):
+            self.pipes.append(dict(ws=F.FieldWorkspace(self.cfg, self.n_full, dev, training=False), xyzs=torch.empty(self.n_full, 3, device=dev),
+                                   indices=torch.empty(self.n_full, dtype=torch.int32, device=dev), tmp=torch.full((self.n_full,), -1.0, device=dev),
+                                   time_dev=torch.zeros(1, device=dev), stream=torch.cuda.Stream(device=dev)))
 
     def _weights(self):
         m = self.model
@@ -46,17 +50,17 @@ class FusedOccupancy:
         hw.refresh([w.detach() for w in m.mlp_weights()])
         return hw, m.encoder.embeddings.detach().to(torch.float16)
 
-    def _query_and_store(self, n, t, cas, hw, table16):
-        """density at self.xyzs[:n] (time self.time_dev) -> tmp[indices] -> density_grid[t, cas] = max(grid * decay, tmp)"""
+    def _query_and_store(self, pp, n, t, cas, hw, table16):
+        """density at pp.xyzs[:n] (time pp.time_dev) -> tmp[indices] -> density_grid[t, cas] = max(grid * decay, tmp)"""
         m, cfg = self.model, self.cfg
         saved, cfg.density_scale = cfg.density_scale, 1.0  # like NeRFNetwork.density: the renderer applies density_scale itself
         try:
-            F.field_density(cfg, hw, self.ws, self.xyzs, self.time_dev, table16, m.encoder.offsets, M=n)
+            F.field_density(cfg, hw, pp["ws"], pp["xyzs"], pp["time_dev"], table16, m.encoder.offsets, M=n)
         finally:
             cfg.density_scale = saved
         st = _lib.stream()
-        _lib.call("seald_occ_store", ptr(self.ws.sigma), ptr(self.indices), n, float(m.density_scale), ptr(self.tmp), st)
-        _lib.call("seald_occ_ema_max", ptr(m.density_grid[t, cas]), ptr(self.tmp), self.n_full, self._decay, st)
+        _lib.call("seald_occ_store", ptr(pp["ws"].sigma), ptr(pp["indices"]), n, float(m.density_scale), ptr(pp["tmp"]), st)
+        _lib.call("seald_occ_ema_max", ptr(m.density_grid[t, cas]), ptr(pp["tmp"]), self.n_full, self._decay, st)
 
     @torch.no_grad()
     def update(self, decay=0.95):
@@ -75,30 +79,39 @@ class FusedOccupancy:
         else:
             n_rand = n_full // 4
             per = m.time_size // self.world_size
+            main = torch.cuda.current_stream()
+            for pp in self.pipes:
+                pp["stream"].wait_stream(main)
+            job = 0
             for t in range(self.rank * per, (self.rank + 1) * per):
                 time = m.times[t]
                 for cas in range(m.cascade):
                     bound = min(2 ** cas, m.bound)
                     half_cell = bound / H
-                    if full:
-                        n = n_full
-                        rnd = torch.rand(n, 3, device=dev)          # == torch.rand_like(cas_xyzs) of the reference loop
-                        _lib.call("seald_occ_cell_points", None, ptr(rnd), n, H, float(bound - half_cell), float(half_cell), ptr(self.xyzs),
-                                  ptr(self.indices), st())
-                    else:
-                        coords = torch.randint(0, H, (n_rand, 3), device=dev, dtype=torch.int32)
-                        # k-th occupied cell of this frame, k uniform: prefix sum + binary search on the device (no nonzero / sync)
-                        csum = torch.cumsum((m.density_grid[t, cas] > 0).to(torch.int32), 0)
-                        k = (torch.rand(n_rand, device=dev) * csum[-1]).to(torch.int32)
-                        occ = torch.searchsorted(csum, k + 1).clamp_(max=n_full - 1).to(torch.int32)
-                        occ_coords = raymarching.morton3D_invert(occ)
-                        coords = torch.cat([coords, occ_coords.to(torch.int32)], 0).contiguous()
-                        n = coords.shape[0]
-                        rnd = torch.rand(n, 3, device=dev)
-                        _lib.call("seald_occ_cell_points", ptr(coords), ptr(rnd), n, H, float(bound - half_cell), float(half_cell),
-                                  ptr(self.xyzs), ptr(self.indices), st())
-                    self.time_dev.copy_((time + (torch.rand_like(time) * 2 - 1) * half_time).reshape(-1)[:1])
-                    self._query_and_store(n, t, cas, hw, table16)
+                    pp = self.pipes[job % self.n_pipes]
+                    job += 1
+                    with torch.cuda.stream(pp["stream"]):
+                        if full:
+                            n = n_full
+                            rnd = torch.rand(n, 3, device=dev)          # == torch.rand_like(cas_xyzs) of the reference loop
+                            _lib.call("seald_occ_cell_points", None, ptr(rnd), n, H, float(bound - half_cell), float(half_cell), ptr(pp["xyzs"]),
+                                      ptr(pp["indices"]), st())
+                        else:
+                            coords = torch.randint(0, H, (n_rand, 3), device=dev, dtype=torch.int32)
+                            # k-th occupied cell of this frame, k uniform: prefix sum + binary search on the device (no nonzero / sync)
+                            csum = torch.cumsum((m.density_grid[t, cas] > 0).to(torch.int32), 0)
+                            k = (torch.rand(n_rand, device=dev) * csum[-1]).to(torch.int32)
+                            occ = torch.searchsorted(csum, k + 1).clamp_(max=n_full - 1).to(torch.int32)
+                            occ_coords = raymarching.morton3D_invert(occ)
+                            coords = torch.cat([coords, occ_coords.to(torch.int32)], 0).contiguous()
+                            n = coords.shape[0]
+                            rnd = torch.rand(n, 3, device=dev)
+                            _lib.call("seald_occ_cell_points", ptr(coords), ptr(rnd), n, H, float(bound - half_cell), float(half_cell),
+                                      ptr(pp["xyzs"]), ptr(pp["indices"]), st())
+                        pp["time_dev"].copy_((time + (torch.rand_like(time) * 2 - 1) * half_time).reshape(-1)[:1])
+                        self._query_and_store(pp, n, t, cas, hw, table16)
+            for pp in self.pipes:
+                main.wait_stream(pp["stream"])
             if self.world_size > 1:
                 mine = m.density_grid[self.rank * per:(self.rank + 1) * per].clone()
                 torch.distributed.all_gather_into_tensor(m.density_grid.view(-1), mine.view(-1), group=self.pg)
