@@ -700,7 +700,8 @@ template <typename T, uint32_t D, uint32_t C>
 int launch_forward(const float* x, const void* table, const int* offsets, void* out, void* dy_dx, uint32_t B, uint32_t L, float S,
                    uint32_t H, uint32_t gridtype, bool align, uint32_t interp, const int* b_dev, cudaStream_t st) {
     constexpr uint32_t G16 = 16 / (C * sizeof(T));  // levels per 16-byte output store
-    constexpr uint32_t G = (D <= 3 && G16 >= 2 && G16 <= 4) ? G16 : 1;
+    // levels per pass: all gathers of G levels are in flight before the first use; 4-D cells have 16 corners, so two levels fill the registers
+    constexpr uint32_t G = (G16 >= 2 && G16 <= 4) ? (D <= 3 ? G16 : (D == 4 ? 2u : 1u)) : 1;
     const uint32_t threads = 256;
     const uint32_t blocks = div_up(B, threads);
     if constexpr (G > 1) {

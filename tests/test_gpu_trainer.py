@@ -131,4 +131,4 @@ def test_data_parallel_modes_two_gpus():
            "--master-port", "29571", os.path.join(root, "scripts", "dp_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert "MISMATCH" not in p.stdout and p.stdout.count(" OK") >= 8
+    assert "MISMATCH" not in p.stdout and p.stdout.count(" OK") >= 9
