@@ -194,6 +194,7 @@ class FusedTrainer:
         self.h_loss = torch.zeros(1).pin_memory()
         self._graph = None
         self._occ = None
+        self._trace = None
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------------------------
@@ -355,9 +356,18 @@ class FusedTrainer:
                 if nm in S:
                     S[nm][0]()
                     n[0] += S[nm][1]
+                    mark(nm)
+
+        def mark(label):
+            # optional in-graph timeline: external event-record nodes after every stage of the main stream (step_timeline())
+            if self._trace is not None:
+                ev = torch.cuda.Event(enable_timing=True, external=True)
+                ev.record(torch.cuda.current_stream())
+                self._trace.append((label, ev))
 
         dist = torch.distributed
         W, mode = self.world_size, self.dp_mode
+        mark("begin")
         main, side = torch.cuda.current_stream(), self._side
         ntp = self.n_table_pad
         # ---- beginning of the step: the march and the deformation forward do not read the hash table, so the table part of the
@@ -411,8 +421,39 @@ class FusedTrainer:
         elif mode == "fused":
             self._symm[0].barrier(2)  # every rank's MLP gradients and overflow flag are complete
             n[0] += 1
+        mark("check+exchange")
         n[0] += self._optimizer()
+        mark("optimizer")
         return n[0]
+
+    def step_timeline(self, reps=50):
+        """Time between consecutive stage boundaries INSIDE the replayed step graph (external event-record nodes), averaged over
+        `reps` replays: what each stage costs in its real position, caches as the previous stage left them."""
+        if not self.use_graph:
+            raise RuntimeError("step_timeline() needs use_graph=True")
+        snapshot = [t.clone() for t in self._state()]
+        self._warmup()
+        self._trace = []
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body()
+        trace, self._trace = self._trace, None
+        acc = [0.0] * (len(trace) - 1)
+        for _ in range(3):
+            g.replay()
+        for _ in range(reps):
+            g.replay()
+            torch.cuda.synchronize()
+            for i in range(len(trace) - 1):
+                acc[i] += trace[i][1].elapsed_time(trace[i + 1][1])
+        out = {}
+        for i in range(len(trace) - 1):
+            out[trace[i + 1][0]] = out.get(trace[i + 1][0], 0.0) + acc[i] / reps
+        out["total"] = sum(acc) / reps
+        del g
+        torch.cuda.synchronize()
+        self._restore(snapshot)
+        return out
 
     def _forward_backward(self):
         """Every stage of the forward + backward pass in order on the current stream (no optimiser, no exchange): tests / debugging."""
