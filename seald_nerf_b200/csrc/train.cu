@@ -83,7 +83,7 @@ __global__ void k_grad_finite_check(const float* __restrict__ g, const size_t n,
 
 // torch.optim.Adam (no amsgrad / weight decay) on a flat fp32 slab, gradients un-scaled by 1 / *loss_scale, the whole
 // update skipped when *found_inf != 0 (GradScaler.step).  Optionally refreshes an fp16 copy and zeroes the gradient.
-__global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const size_t n,
+__global__ void __launch_bounds__(256, 4) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const size_t n,
                        const float lr, const float beta1, const float beta2, const float eps, float bc1, float bc2_sqrt,
                        const int* __restrict__ step_dev, const int step_add, const float* __restrict__ loss_scale,
                        const int* __restrict__ found_inf, __half* __restrict__ p16, const int zero_grad) {
