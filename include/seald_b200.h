@@ -395,6 +395,20 @@ int seald_occ_cell_points(const int32_t* coords, const float* rand3, uint32_t n,
 int seald_occ_store(const float* sigma, const int32_t* indices, uint32_t n, float density_scale, float* tmp, seald_stream_t stream);
 int seald_occ_ema_max(float* grid, float* tmp, uint32_t n, float decay, seald_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Step input generation on the device: get_rays for the sampled pixels of one camera
+ * (nerf/utils.py:54-137, N > 0, patch_size 1, no error_map: pixel centres at +0.5, normalised directions rotated by
+ * pose[:3,:3], origin pose[:3,3]) + the ground-truth gather / alpha blend of NeRFDataset.collate and Trainer.train_step
+ * (dnerf/provider.py:340-343, dnerf/utils.py:61-66).
+ *   poses [F,4,4], times [F] (or NULL), images [F,H*W,C] (C = 3 or 4; or NULL) resident tables; frame_dev: device int32
+ *   frame index (NULL = 0); inds [N] int64 flat pixel indices h*W+w; bg [N,3] or NULL (white) for C = 4;
+ *   outputs rays_o, rays_d, gt [N,3]; time_out [1] = times[frame] (optional).
+ * ------------------------------------------------------------------------------------------------ */
+int seald_get_rays_gather(const float* poses, const float* times, const float* images, const int32_t* frame_dev,
+                          const int64_t* inds, uint32_t N, uint32_t H, uint32_t W, uint32_t C, float fx, float fy, float cx,
+                          float cy, const float* bg, float* rays_o, float* rays_d, float* gt, float* time_out,
+                          seald_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -330,3 +330,65 @@ extern "C" int seald_loss_scale_update_stash(float* loss_scale, int32_t* found_i
     k_loss_scale_update<<<1, 32, 0, to_stream(stream)>>>(loss_scale, found_inf, growth_tracker, growth, backoff, interval, step_dev, stash);
     return launch_status();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Step input generation on the device: get_rays (nerf/utils.py:54-137) for the sampled pixels of ONE camera
+// + the ground-truth gather of NeRFDataset.collate (dnerf/provider.py:340-343) in one kernel.  The reference runs ~15 small
+// torch kernels per step for this (meshgrid, gather x2, stack, norm, div, bmm, expand, gather of the image); with the dataset
+// preloaded on the GPU (provider `preload`) the host then only sends a frame index per step.
+//   pixel (w, h) = (ind % W, ind / W), centre at +0.5; dir = ((i - cx) / fx, (j - cy) / fy, 1) normalised, rotated by pose[:3,:3];
+//   origin = pose[:3, 3].  The division by the scalar intrinsics is a multiplication by the fp32 reciprocal, as torch does it.
+//   gt: C = 3 copies RGB; C = 4 blends rgb * a + bg * (1 - a) (dnerf/utils.py:61-66) with bg[n] (NULL = white).
+//   frame_dev selects pose / time / image from the resident tables; time_out receives times[frame].
+// ------------------------------------------------------------------------------------------------
+namespace seald {
+__global__ void k_get_rays_gather(const float* __restrict__ poses, const float* __restrict__ times, const float* __restrict__ images,
+                                  const int* __restrict__ frame_dev, const long long* __restrict__ inds, const uint32_t N, const uint32_t H,
+                                  const uint32_t W, const uint32_t C, const float inv_fx, const float inv_fy, const float cx, const float cy,
+                                  const float* __restrict__ bg, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                                  float* __restrict__ gt, float* __restrict__ time_out) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int frame = frame_dev ? *frame_dev : 0;
+    const float* P = poses + (size_t)frame * 16;
+    if (n == 0 && time_out && times) *time_out = times[frame];
+    if (n >= N) return;
+    const long long ind = inds[n];
+    const uint32_t w = (uint32_t)(ind % W), h = (uint32_t)(ind / W);
+    const float i = __fadd_rn((float)w, 0.5f), j = __fadd_rn((float)h, 0.5f);
+    const float xs = __fmul_rn(__fsub_rn(i, cx), inv_fx), ys = __fmul_rn(__fsub_rn(j, cy), inv_fy), zs = 1.0f;
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xs, xs), __fmul_rn(ys, ys)), __fmul_rn(zs, zs)));
+    const float dx = __fdiv_rn(xs, nrm), dy = __fdiv_rn(ys, nrm), dz = __fdiv_rn(zs, nrm);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        rays_d[(size_t)n * 3 + r] = dx * P[r * 4] + dy * P[r * 4 + 1] + dz * P[r * 4 + 2];  // directions @ R^T
+        rays_o[(size_t)n * 3 + r] = P[r * 4 + 3];
+    }
+    if (gt && images) {
+        const float* px = images + ((size_t)frame * H * W + (size_t)ind) * C;
+        if (C == 4) {
+            const float a = px[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float b = bg ? bg[(size_t)n * 3 + c] : 1.0f;
+                gt[(size_t)n * 3 + c] = __fadd_rn(__fmul_rn(px[c], a), __fmul_rn(b, __fsub_rn(1.0f, a)));
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; c++) gt[(size_t)n * 3 + c] = px[c];
+        }
+    }
+}
+}  // namespace seald
+
+extern "C" int seald_get_rays_gather(const float* poses, const float* times, const float* images, const int32_t* frame_dev,
+                                     const int64_t* inds, uint32_t N, uint32_t H, uint32_t W, uint32_t C, float fx, float fy, float cx,
+                                     float cy, const float* bg, float* rays_o, float* rays_d, float* gt, float* time_out,
+                                     seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!poses || !inds || !rays_o || !rays_d || H == 0 || W == 0 || fx == 0.0f || fy == 0.0f) return SEALD_E_BADARG;
+    if (gt && images && C != 3 && C != 4) return SEALD_E_UNSUPPORTED;
+    seald::k_get_rays_gather<<<seald::div_up(N, 256u), 256, 0, seald::to_stream(stream)>>>(poses, times, images, frame_dev, (const long long*)inds, N, H, W, C,
+                                                                                          1.0f / fx, 1.0f / fy, cx, cy, bg, rays_o, rays_d, gt,
+                                                                                          time_out);
+    return seald::launch_status();
+}

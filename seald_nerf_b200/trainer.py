@@ -192,9 +192,11 @@ class FusedTrainer:
         self.h_gt = self.h_inputs[6 * N:9 * N].view(N, 3)
         self.h_time = self.h_inputs[9 * N:9 * N + 1]
         self.h_loss = torch.zeros(1).pin_memory()
-        self._graph = None
+        self._graphs = {}
         self._occ = None
         self._trace = None
+        self._ds = None
+        self._ds_active = False
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------------------------
@@ -215,6 +217,45 @@ class FusedTrainer:
                                        process_group=self.pg)
         self._occ.update(decay)
         self.refresh_occupancy()
+
+    # ---- step inputs generated on the device from a resident dataset ----------------------------------------
+    def attach_dataset(self, poses, intrinsics, H, W, images, times):
+        """Keep the training set on the GPU (the reference's `preload`, dnerf/provider.py:246-252): poses [F,4,4] cam2world, intrinsics
+        (fx, fy, cx, cy), images [F, H*W, 3|4] float32, times [F].  train_step_frame(i) then draws the pixels, builds the rays
+        (get_rays, nerf/utils.py:54-137) and gathers the targets (collate, dnerf/provider.py:340-343) INSIDE the step graph."""
+        dev = self.device
+        self._ds = dict(poses=poses.to(dev, torch.float32).contiguous(), times=times.to(dev, torch.float32).reshape(-1).contiguous(),
+                        images=images.to(dev, torch.float32).contiguous(), H=int(H), W=int(W), C=int(images.shape[-1]),
+                        intr=[float(v) for v in intrinsics])
+        if self._ds["C"] not in (3, 4) or self._ds["images"].shape[1] != H * W:
+            raise ValueError("images must be [F, H*W, 3|4]")
+        self.inds = torch.zeros(self.N, dtype=torch.int64, device=dev)
+        self.frame_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.h_frame = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._graphs.pop(True, None)
+
+    def _dataset_prologue(self):
+        ds = self._ds
+        self.inds.random_(0, ds["H"] * ds["W"])  # torch.randint(0, H*W, [N]) of get_rays (:95-97); philox state is graph-safe
+        fx, fy, cx, cy = ds["intr"]
+        _lib.call("seald_get_rays_gather", ptr(ds["poses"]), ptr(ds["times"]), ptr(ds["images"]), ptr(self.frame_dev), ptr(self.inds), self.N,
+                  ds["H"], ds["W"], ds["C"], fx, fy, cx, cy, ptr(self.bg), ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt), ptr(self.time),
+                  _lib.stream())
+        return 2
+
+    def train_step_frame(self, frame, host_loss=False):
+        """One step on N random pixels of training frame `frame` of the attached dataset: the host sends 4 bytes.  host_loss=True
+        reads the loss back (one D2H + sync), the end-to-end variant."""
+        if self._ds is None:
+            raise RuntimeError("attach_dataset() first")
+        self.h_frame[0] = int(frame)
+        self.frame_dev.copy_(self.h_frame, non_blocking=True)
+        self.step(dataset=True)
+        if not host_loss:
+            return self.loss
+        self.h_loss.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.h_loss[0])
 
     def set_inputs(self, rays_o, rays_d, time, gt_rgb, bg_color=None):
         """Device-resident inputs of the next step (copied into the static buffers the graph reads)."""
@@ -368,6 +409,9 @@ class FusedTrainer:
         dist = torch.distributed
         W, mode = self.world_size, self.dp_mode
         mark("begin")
+        if self._ds is not None and self._use_dataset:
+            n[0] += self._dataset_prologue()
+            mark("get_rays")
         main, side = torch.cuda.current_stream(), self._side
         ntp = self.n_table_pad
         # ---- beginning of the step: the march and the deformation forward do not read the hash table, so the table part of the
@@ -619,18 +663,26 @@ class FusedTrainer:
         self._rank_sync()
 
     # ------------------------------------------------------------------------------------------------------------
-    def step(self):
-        """One optimisation step on the inputs staged by set_inputs*/().  No host synchronisation."""
+    def step(self, dataset=False):
+        """One optimisation step on the inputs staged by set_inputs*/() — or, with dataset=True, on pixels drawn inside the step from
+        the attached dataset.  No host synchronisation.  One CUDA graph per input mode."""
         self.global_step += 1
+        self._ds_active = bool(dataset)
         if not self.use_graph:
             self.launches_per_step = self._step_body()
             return
-        if self._graph is None:
+        g = self._graphs.get(self._ds_active)
+        if g is None:
             self._warmup()
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
                 self.launches_per_step = self._step_body()
-        self._graph.replay()
+            self._graphs[self._ds_active] = g
+        g.replay()
+
+    @property
+    def _use_dataset(self):
+        return self._ds is not None and self._ds_active
 
     def train_step(self, rays_o, rays_d, time, gt_rgb, bg_color=None):
         """Public API: one training step on device tensors; returns the (device) loss of this step."""
