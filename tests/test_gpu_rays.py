@@ -44,7 +44,7 @@ def test_get_rays_gather_vs_reference_golden_and_oracle(cuda_dev):
             img = torch.zeros(3, H * W, 4, device=d)
             img[2] = torch.rand(1, H, W, 4, generator=gen)[0].reshape(-1, 4).to(d)
         ro, rd, gt, t_out = _call(d, poses, times, img, 2, inds, H, W, 4, c["intr"])
-        assert float(t_out) == pytest.approx(0.7, abs=0)
+        assert float(t_out) == float(np.float32(0.7))
         assert np.array_equal(ro.cpu().numpy(), c["rays_o"])
         np.testing.assert_allclose(rd.cpu().numpy(), c["rays_d"], rtol=1e-5, atol=1e-6)
         ro_o, rd_o = orr.get_rays(c["pose"], c["intr"], H, W, c["inds"])
@@ -83,11 +83,19 @@ def test_trainer_step_from_resident_dataset(cuda_dev):
             torch.manual_seed(3)
             loss = float(tr.train_step_frame(2))
             inds = tr.inds.clone()
+            assert int(inds.min()) >= 0 and int(inds.max()) < H * W and inds.unique().numel() > 3500  # 4096 draws from 40 000 pixels
+            staged = (tr.rays_o.clone(), tr.rays_d.clone(), tr.gt.clone(), float(tr.time))
         else:
             ro, rdir = syn.get_rays(poses[2], intr, H, W, inds)
             loss = float(tr.train_step(ro, rdir, 0.6, images[2][inds]))
+            # what the graph staged for itself == the explicitly computed batch of the same pixels
+            assert torch.equal(staged[0], ro) and torch.equal(staged[2], images[2][inds]) and staged[3] == float(np.float32(0.6))
+            torch.testing.assert_close(staged[1], rdir, rtol=1e-5, atol=1e-6)
         tr.flush()
         res.append((loss, tr.params[:tr.n_table].clone()))
     assert res[0][0] == pytest.approx(res[1][0], rel=1e-4)
+    # one Adam step moves every touched entry by ~lr * sign(g): entries whose gradient is round-off noise around zero may differ by
+    # 2 * lr, everything else must agree
     scale = float(res[1][1].abs().max())
-    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-3 * scale
+    differ = ((res[0][1] - res[1][1]).abs() > 1e-3 * scale).float().mean()
+    assert float(differ) < 1e-3
