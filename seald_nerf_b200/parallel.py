@@ -38,6 +38,17 @@ def loss_inv_count(n_rays_local, world_size, channels=3):
     return 1.0 / (channels * n_rays_local * world_size)
 
 
+def shard_layout(n_table, world_size):
+    """Layout of the flat table region for a sharded optimiser: (shard_len, n_table_pad).  The table is padded to `world_size` equal
+    shards whose length is a multiple of 8 elements (16-byte fp16 vectors / two float4 per thread in the exchange kernels); rank r owns
+    elements [r * shard_len, (r + 1) * shard_len).  A single rank keeps the table as it is, rounded up to a float4."""
+    n_table, world_size = int(n_table), int(world_size)
+    if world_size <= 1:
+        return n_table, (n_table + 3) // 4 * 4
+    shard_len = ((n_table + world_size - 1) // world_size + 7) // 8 * 8
+    return shard_len, shard_len * world_size
+
+
 def shard_tiles(n_rays, world_size, rank, tile=256):
     """Indices (int64, ascending) of the rays rank `rank` renders: tiles of `tile` consecutive rays dealt round-robin."""
     n_tiles = (n_rays + tile - 1) // tile

@@ -4,13 +4,18 @@ Replaces, for `cuda_ray=True` training, the reference's `Trainer.train_step` + `
 `scaler.step(optimizer)` + `scaler.update()` (dnerf/utils.py:38-115, nerf/utils.py:879-886, Adam as configured in
 main_dnerf.py:129) with:
 
-    march (AABB fused, warp-compacted)  ->  deform MLP  ->  grid encoder  ->  sigma/colour heads  ->  composite
-    -> MSE + background blend  ->  composite bwd  ->  heads bwd  ->  grid scatter + input grad  ->  deform bwd
-    -> weight-gradient GEMMs  ->  [NCCL allreduce of the flat gradient buffer]  ->  finite check + Adam + fp16 refresh
+    [pixel sampling + get_rays + target gather from a resident dataset]  ->  march (AABB fused, warp-compacted)  ->  deform MLP
+    ->  grid encoder  ->  sigma/colour heads  ->  composite + MSE/background blend + composite bwd (one kernel)  ->  heads bwd
+    ->  grid scatter + input grad  ->  deform bwd  ->  weight-gradient GEMMs  ->  [gradient exchange over the GPUs, fused with
+    the optimiser: csrc/dp_fused.cu]  ->  overflow check + Adam + fp16 refresh + loss-scale update
 
-Every buffer is preallocated, no host synchronisation happens inside a step (the sample count stays on the device),
-and the whole step is replayed as CUDA graphs.  Parameters stay the model's own nn.Parameters (re-pointed into one flat
-fp32 buffer), so checkpoints and the drop-in `NeRFNetwork.forward` see the trained values.
+Every buffer is preallocated, no host synchronisation happens inside a step (the sample count stays on the device), and the
+whole step — exchange kernels and cross-rank barriers included — is ONE CUDA graph per rank.  Parameters stay the model's own
+nn.Parameters (re-pointed into one flat fp32 buffer), so checkpoints and the drop-in `NeRFNetwork.forward` see the trained values
+(call flush() / sync_params() first when the table pass of the optimiser is deferred, i.e. in the fused data-parallel mode).
+
+Environment switches (measurement only; defaults follow the measurements recorded in DESIGN.md §3): SEALD_DP_MODE, SEALD_DP_MULTICAST,
+SEALD_DP_MULTICAST_REDUCE, SEALD_DEFER, SEALD_FORK, SEALD_ADAM_BLOCKS, SEALD_GRID_AGG_LEVELS, SEALD_GRID_SCATTER_PPC.
 """
 import math
 
@@ -75,8 +80,9 @@ class FusedTrainer:
         self.shard_optimizer = self.dp_mode == "sharded"
         self.rank = torch.distributed.get_rank(self.pg) if W > 1 else 0
         sharded_layout = self.dp_mode in ("fused", "sharded")  # table padded to W equal shards of a multiple of 8 elements
-        self.shard_len = ((self.n_table + W - 1) // W + 7) // 8 * 8 if sharded_layout else 0
-        self.n_table_pad = self.shard_len * W if sharded_layout else (self.n_table + 3) // 4 * 4
+        self.shard_len, self.n_table_pad = parallel.shard_layout(self.n_table, W if sharded_layout else 1)
+        if not sharded_layout:
+            self.shard_len = 0
         n = self.n_table_pad + self.n_weights
         # flat buffers: [table (padded) | MLP weights | pad | overflow flag (4 floats)].  The flag lives INSIDE the gradient buffer so the
         # exchange that sums the MLP gradients also tells every rank whether any rank overflowed (GradScaler's found_inf).

@@ -90,3 +90,23 @@ def test_single_process_is_a_noop():
     assert parallel.world() == (0, 1)
     x = torch.rand(10, 5)
     assert parallel.gather_frame(x, 10, 0, 1) is x
+
+
+def test_shard_layout_covers_the_table_in_equal_aligned_shards():
+    """Sharded optimiser / fused exchange: every element of the table belongs to exactly one rank, shards are equal, 8-element
+    aligned (16-byte fp16 vectors), and the padding is smaller than 8 elements per rank."""
+    from seald_nerf_b200 import parallel
+    n_table = 12239728  # L16 / T2^19 / F2 hash grid (SURVEY §8)
+    for W in (1, 2, 3, 4, 8, 16):
+        shard, padded = parallel.shard_layout(n_table, W)
+        if W == 1:
+            assert shard == n_table and padded % 4 == 0 and 0 <= padded - n_table < 4
+            continue
+        assert shard % 8 == 0 and padded == shard * W and padded >= n_table and padded - n_table < 8 * W + W
+        owners = [(r * shard, min((r + 1) * shard, n_table)) for r in range(W)]
+        assert owners[0][0] == 0 and owners[-1][1] == n_table
+        assert all(owners[r][1] == owners[r + 1][0] or owners[r + 1][0] >= n_table for r in range(W - 1))
+    for n in (1, 7, 8, 9, 1000003):
+        for W in (2, 8):
+            shard, padded = parallel.shard_layout(n, W)
+            assert shard % 8 == 0 and padded >= n and padded == shard * W
