@@ -174,7 +174,7 @@ def seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=20):
     n = rays_o.shape[0]
 
     def step(b):
-        out = fr.render(rays_o[b], rays_d[b], times[b], T_thresh=1e-4)
+        out = fr.render_one_pass(rays_o[b], rays_d[b], times[b], T_thresh=1e-4)
         trainer.train_step(rays_o[b], rays_d[b], times[b], torch.nan_to_num(out["image"]))
 
     for i in range(5):
@@ -189,12 +189,12 @@ def seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=20):
     ms = e0.elapsed_time(e1) / K
     e0.record()
     for i in range(K):
-        fr.render(rays_o[i % n], rays_d[i % n], times[i % n], T_thresh=1e-4)
+        fr.render_one_pass(rays_o[i % n], rays_d[i % n], times[i % n], T_thresh=1e-4)
     e1.record()
     torch.cuda.synchronize()
-    mask_count = int(fr.mask.sum())  # mapped samples in the sample buffer of the last march round
+    mask_count = int(fr.mask[:max(fr.samples, 1)].sum())  # mapped samples of the last teacher render
     trainer.flush()  # (data parallel: also a rank barrier — no rank frees its symmetric buffers while a peer's kernels may still read them)
-    return {"ms_per_step": ms, "teacher_ms": e0.elapsed_time(e1) / K, "mapped_samples": mask_count}
+    return {"ms_per_step": ms, "teacher_ms": e0.elapsed_time(e1) / K, "mapped_samples": mask_count, "teacher_iterations": fr.iterations}
 
 
 def main():
@@ -438,8 +438,9 @@ def main():
         if seald:
             line["seald"] = {"value": N_RAYS * world / (ms_seald * 1e-3), "unit": "rays/s", "ms_per_step": ms_seald,
                              "teacher_ms": seald["teacher_ms"], "mapped_samples": seald["mapped_samples"],
-                             "workload": "teacher eval render of the 4096-ray batch (bbox mapper 0.3^3, +0.2x, 30deg about y, fused in march) "
-                                         "+ student train step (frozen deform net)"}
+                             "teacher_iterations": seald["teacher_iterations"],
+                             "workload": "teacher eval render of the 4096-ray batch in one pass (bbox mapper 0.3^3, +0.2x, 30deg about y, fused in "
+                                         "the march; FusedRenderer.render_one_pass) + student train step (frozen deform net)"}
         if occ:
             step_ms = ms / K
             line["occupancy_update"] = dict(occ, unit="wall ms per update_extra_state (64 time frames x 128^3 cells, sharded over the ranks, incl. its host syncs)",

@@ -229,6 +229,84 @@ class FusedRenderer:
         return {"image": image.view(*prefix, 3), "depth": depth_out.view(*prefix), "weights_sum": ws_out.clone()}
 
     @torch.no_grad()
+    def render_one_pass(self, rays_o, rays_d, time, bg_color=None, dt_gamma=0, max_steps=1024, T_thresh=None, normalize_depth=None, **kwargs):
+        """Small-batch render (a training-size teacher batch of the SealD distillation step) WITHOUT the round loop: every ray is
+        marched to the end in one launch (the training march, force_all_rays semantics, with the Seal proxy mapping fused in), the
+        field is evaluated once over all samples, and one compositing kernel applies the same front-to-back recurrence with the same
+        T_thresh early stop.  5 launches instead of ~4 rounds x 9.  Against render(): identical sample positions; the stop test sits
+        after the sample here (composite_rays_train, raymarching.cu:560-566) and before the next one there (composite_rays, :880-886),
+        so a ray can take one sample fewer, whose weight is < T_thresh: image / weights_sum agree to T_thresh.  Falls back to render()
+        when the batch needs more sample slots than this renderer was sized for."""
+        m = self.model
+        prefix = rays_o.shape[:-1]
+        N = rays_o.numel() // 3
+        if N > self.N:
+            raise RuntimeError("FusedRenderer was sized for %d rays, got %d" % (self.N, N))
+        mapper = getattr(m, "seal_mapper", None)
+        seald = hasattr(m, "init_mapper")
+        if mapper is not None and not mapper.fusable:
+            return self.render(rays_o, rays_d, time, bg_color=bg_color, dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh,
+                               normalize_depth=normalize_depth, **kwargs)
+        if T_thresh is None:
+            T_thresh = 1e-4 if seald else 1e-2
+        if normalize_depth is None:
+            normalize_depth = not seald
+        if bg_color is None:
+            bg_color = 1
+        st = _lib.stream()
+        self.rays_o[:N].copy_(rays_o.reshape(-1, 3), non_blocking=True)
+        self.rays_d[:N].copy_(rays_d.reshape(-1, 3), non_blocking=True)
+        if torch.is_tensor(time):
+            self.time.copy_(time.reshape(-1)[:1])
+            t_idx = m._frame_index(self.time.view(1, 1))
+        else:
+            self.time.fill_(float(time))
+            t_idx = min(max(int(float(time) * m.time_size), 0), m.time_size - 1)
+        self.bitfield.copy_(m.density_bitfield[t_idx], non_blocking=True)
+        _lib.call("seald_occupancy_aabb", ptr(self.bitfield), int(m.cascade), int(m.grid_size), float(m.bound), 2, ptr(self.occ_scratch),
+                  ptr(self.occ), st)
+        aabb = m.aabb_train if m.training else m.aabb_infer
+        nears, fars = self.nears[:N], self.fars[:N]
+        if getattr(self, "_rays", None) is None:
+            self._rays = torch.zeros(self.N, 3, dtype=torch.int32, device=self.device)
+            self._counter = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._h_counter = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self._zero_noise = torch.zeros(self.N, dtype=torch.float32, device=self.device)
+        self._counter.zero_()
+        m_dev = self._counter[0:1]
+        M = self.cap - 128
+        args = (ptr(self.rays_o), ptr(self.rays_d), ptr(self.bitfield), float(m.bound), float(dt_gamma), int(max_steps), N, int(m.cascade),
+                int(m.grid_size), M, None, None, ptr(aabb), float(m.min_near), ptr(nears), ptr(fars), ptr(self.xyzs), ptr(self.dirs),
+                ptr(self.deltas), ptr(self._rays), ptr(self._counter), ptr(self._zero_noise))
+        if mapper is not None:
+            desc = mapper.descriptor(self.device)
+            _lib.call("seald_march_rays_train_seal", *args, C.byref(desc), ptr(self.mask), ptr(self.occ), st)
+        else:
+            _lib.call("seald_march_rays_train", *args, ptr(self.occ), st)
+        F.field_forward(self.cfg, self.hw, self.ws, self.xyzs, self.dirs, self.time, self.table16, m.encoder.offsets, m_dev, 1, M=M)
+        launches = 8
+        if mapper is not None and mapper.has_color_map:
+            _lib.call("seald_seal_map_color", C.byref(mapper._dev_cache["color"]), ptr(self.xyzs), ptr(self.mask), ptr(self.ws.rgb), M,
+                      ptr(m_dev), ptr(mapper._dev_cache["scratch_f"]), st)
+            launches += 4
+        ws_out, depth, image = self.weights_sum[:N], self.depth[:N], self.image[:N]
+        _lib.call("seald_composite_rays_train_forward", ptr(self.ws.sigma), ptr(self.ws.rgb), ptr(self.deltas), ptr(self._rays), M, N,
+                  float(T_thresh), ptr(ws_out), ptr(depth), ptr(image), st)
+        self._h_counter.copy_(self._counter, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n_samples = int(self._h_counter[0])
+        if n_samples > M:  # not every ray found room for its samples: the round loop has no such limit
+            return self.render(rays_o, rays_d, time, bg_color=bg_color, dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh,
+                               normalize_depth=normalize_depth, **kwargs)
+        self.iterations, self.samples, self.launches = 1, n_samples, launches
+        # the training compositor measures depth from the ray's first sample parameter (its t starts at 0, raymarching.cu:538); the
+        # inference compositor from the ray origin (t starts at rays_t = near, :869): add near * weights_sum
+        depth = depth + nears * ws_out
+        image = image + (1 - ws_out).unsqueeze(-1) * bg_color
+        depth_out = torch.clamp(depth - nears, min=0) / (fars - nears) if normalize_depth else depth
+        return {"image": image.view(*prefix, 3), "depth": depth_out.view(*prefix), "weights_sum": ws_out.clone()}
+
+    @torch.no_grad()
     def render_sharded(self, rays_o, rays_d, time, rank=0, world_size=1, group=None, tile=256, **kwargs):
         """Every rank passes the SAME full ray set; each renders its interleaved tiles and all ranks get the full frame."""
         rays_o = rays_o.contiguous().view(-1, 3)

@@ -65,3 +65,41 @@ def test_fused_renderer_seald_teacher(cuda_dev, kind):
     torch.testing.assert_close(out["image"], ref["image"], rtol=1e-5, atol=2e-5)
     torch.testing.assert_close(out["depth"], ref["depth"], rtol=1e-5, atol=2e-5)   # raw depth (SealD does not normalise)
     torch.testing.assert_close(out["weights_sum"], ref["weights_sum"], rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("kind", ["plain", "bbox", "brush"])
+def test_one_pass_small_batch_render_matches_round_loop(cuda_dev, kind):
+    """render_one_pass (training march + one field pass + composite_rays_train forward) against the round loop of render():
+    identical sample positions; the early-stop test sits after the sample instead of before the next one, so a ray may take one
+    sample fewer whose weight is below T_thresh.  Tolerance: image / weights_sum atol 2 * T_thresh, raw depth atol 4 * T_thresh
+    (ray parameters are <= 3.5)."""
+    from oracle import seal as S
+    from seald_nerf_b200.renderer_fused import FusedRenderer
+    seald = kind != "plain"
+    net = _model(cuda_dev, seald=seald)
+    if kind == "bbox":
+        net.init_mapper(mapper=seal_mapper_from_dict(S.make_bbox_mapper(center=(0.0, 0.1, 0.0), half=(0.2, 0.25, 0.2), translate=(0.08, 0.0, 0.03),
+                                                                        rot_deg=30.0, hsv=(0.1, 0.0, 0.0))))
+    elif kind == "brush":
+        net.init_mapper(mapper=seal_mapper_from_dict(S.make_brush_mapper(mode="linear", pressure=0.05, depth=0.6, attenuation=0.03, rgb=(1.0, 0.0, 0.0))))
+    ro, rd = camera_rays(4096, seed=5, center_crop=220)
+    ro, rd = torch.from_numpy(ro).to(cuda_dev), torch.from_numpy(rd).to(cuda_dev)
+    time = torch.tensor([[0.41]], device=cuda_dev)
+    for T_thresh in (1e-4, 1e-2):
+        fr = FusedRenderer(net, max_rays=4096, min_samples=1 << 18)
+        ref = fr.render(ro, rd, time, T_thresh=T_thresh)
+        out = fr.render_one_pass(ro, rd, time, T_thresh=T_thresh)
+        assert fr.iterations == 1 and fr.samples > 4096  # the one-pass path ran (no fallback) and marched real samples
+        torch.testing.assert_close(out["image"], ref["image"], rtol=0, atol=2 * T_thresh)
+        torch.testing.assert_close(out["weights_sum"], ref["weights_sum"], rtol=0, atol=2 * T_thresh)
+        if seald:
+            torch.testing.assert_close(out["depth"], ref["depth"], rtol=0, atol=4 * T_thresh)
+        else:
+            torch.testing.assert_close(out["depth"], ref["depth"], rtol=0, atol=4 * T_thresh)  # normalised by (far - near) ~ 3
+        assert float((out["image"] - ref["image"]).abs().mean()) < 0.1 * T_thresh  # most rays agree to round-off
+    # too few sample slots -> falls back to the round loop (same result as render())
+    small = FusedRenderer(net, max_rays=4096, min_samples=4096)
+    out_fb = small.render_one_pass(ro, rd, time, T_thresh=1e-4)
+    ref_fb = small.render(ro, rd, time, T_thresh=1e-4)
+    assert small.iterations > 1
+    torch.testing.assert_close(out_fb["image"], ref_fb["image"], rtol=1e-5, atol=1e-5)
