@@ -245,6 +245,10 @@ int seald_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uin
 int seald_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree,
                              const float* dy_dx, float* grad_inputs, seald_stream_t stream);
 
+/* trunc_exp (activation.py:5-17): y = exp(x) in fp32; grad_x = grad * exp(clamp(x, -15, 15)). */
+int seald_trunc_exp_forward(const float* x, float* y, uint64_t n, seald_stream_t stream);
+int seald_trunc_exp_backward(const float* grad, const float* x, float* grad_x, uint64_t n, seald_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused D-NeRF field (tensor-core MLPs, fp16 operands / fp32 accumulation).
  * Replaces the per-layer cuBLAS path of NeRFNetwork.forward / .density (dnerf/network.py:123-208;

@@ -71,6 +71,8 @@ _SIGS = {
     "seald_occ_store": [_vp, _vp, _u32, _f32, _vp, _vp],
     "seald_occ_ema_max": [_vp, _vp, _u32, _f32, _vp],
     "seald_get_rays_gather": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_trunc_exp_forward": [_vp, _vp, C.c_uint64, _vp],
+    "seald_trunc_exp_backward": [_vp, _vp, _vp, C.c_uint64, _vp],
     "seald_grad_finite_check": [_vp, C.c_uint64, _vp, _vp],
     "seald_adam_advance": [_vp, _vp, _vp],
     "seald_adam_step": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _vp],

@@ -119,3 +119,30 @@ extern "C" int seald_sh_encode_backward(const float* grad, const float* inputs, 
     k_sh_bwd<<<div_up(B * D, 256u), 256, 0, to_stream(stream)>>>(grad, B, D, degree * degree, dy_dx, grad_inputs);
     return launch_status();
 }
+
+// ---- trunc_exp (activation.py:5-17): y = exp(x) in fp32; dx = g * exp(clamp(x, -15, 15)) ------------------------------------
+namespace seald {
+__global__ void k_trunc_exp_fwd(const float* __restrict__ x, float* __restrict__ y, const size_t n) {
+    for (size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = expf(x[i]);
+}
+__global__ void k_trunc_exp_bwd(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ gx, const size_t n) {
+    for (size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        gx[i] = g[i] * expf(clampf(x[i], -15.0f, 15.0f));
+}
+}  // namespace seald
+
+extern "C" int seald_trunc_exp_forward(const float* x, float* y, uint64_t n, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!x || !y) return SEALD_E_BADARG;
+    const uint32_t blocks = (uint32_t)(n / 256 + 1 < 8u * SEALD_NUM_SMS ? n / 256 + 1 : 8u * SEALD_NUM_SMS);
+    seald::k_trunc_exp_fwd<<<blocks, 256, 0, seald::to_stream(stream)>>>(x, y, (size_t)n);
+    return seald::launch_status();
+}
+
+extern "C" int seald_trunc_exp_backward(const float* grad, const float* x, float* grad_x, uint64_t n, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!grad || !x || !grad_x) return SEALD_E_BADARG;
+    const uint32_t blocks = (uint32_t)(n / 256 + 1 < 8u * SEALD_NUM_SMS ? n / 256 + 1 : 8u * SEALD_NUM_SMS);
+    seald::k_trunc_exp_bwd<<<blocks, 256, 0, seald::to_stream(stream)>>>(grad, x, grad_x, (size_t)n);
+    return seald::launch_status();
+}
