@@ -179,9 +179,14 @@ class NeRFNetwork(NeRFRenderer):
         raise NotImplementedError("separate colour query belongs to the non-cuda_ray path (out of the hot-path scope)")
 
     def get_params(self, lr, lr_net):
+        # the reference's seven optimiser groups in its order (dnerf/network.py:260-272; the encoder_dir / encoder_deform / encoder_time
+        # groups are empty for the SH / frequency encoders): optimiser state dicts are interchangeable with the reference's
         return [
-            {"params": self.encoder.parameters(), "lr": lr},
-            {"params": self.sigma_net.parameters(), "lr": lr_net},
-            {"params": self.color_net.parameters(), "lr": lr_net},
-            {"params": self.deform_net.parameters(), "lr": lr_net},
+            {"params": list(self.encoder.parameters()), "lr": lr},
+            {"params": list(self.sigma_net.parameters()), "lr": lr_net},
+            {"params": list(self.encoder_dir.parameters()), "lr": lr},
+            {"params": list(self.color_net.parameters()), "lr": lr_net},
+            {"params": list(self.encoder_deform.parameters()), "lr": lr},
+            {"params": list(self.encoder_time.parameters()), "lr": lr},
+            {"params": list(self.deform_net.parameters()), "lr": lr_net},
         ]
