@@ -47,3 +47,32 @@ def test_reference_style_checkpoint_roundtrip(tmp_path):
     assert not missing and not unexpected
     for k, v in net.state_dict().items():
         assert torch.equal(v, model_sd[k]), k
+
+
+def test_optimizer_state_dict_host_logic_loads_into_torch_adam():
+    """checkpoint.optimizer_state_dict / scaler_state_dict only re-label views of the trainer's flat buffers: exercised on CPU with a
+    stand-in trainer (the real one needs a GPU; tests/test_gpu_checkpoint.py covers it end to end).  The result must load into
+    torch.optim.Adam built over the reference's seven parameter groups (dnerf/network.py:260-272) and a GradScaler."""
+    from types import SimpleNamespace
+    from seald_nerf_b200 import checkpoint as ckpt
+    net = _ours(False)
+    n_table = net.encoder.embeddings.numel()
+    weights = net.mlp_weights()
+    n = n_table + sum(w.numel() for w in weights)
+    g = torch.Generator().manual_seed(2)
+    tr = SimpleNamespace(model=net, lr=1e-2, lr_net=1e-3, betas=(0.9, 0.99), eps=1e-15, n_table=n_table, n_table_pad=n_table,
+                         exp_avg=torch.rand(n, generator=g), exp_avg_sq=torch.rand(n, generator=g), step_dev=torch.tensor([17]),
+                         loss_scale=torch.tensor([4096.0]), growth_tracker=torch.tensor([5]), growth_interval=2000)
+    sd = ckpt.optimizer_state_dict(tr)
+    assert [len(pg["params"]) for pg in sd["param_groups"]] == [1, 2, 0, 3, 0, 0, 8]
+    assert [pg["lr"] for pg in sd["param_groups"]] == [1e-2, 1e-3, 1e-2, 1e-3, 1e-2, 1e-2, 1e-3]
+    opt = torch.optim.Adam(net.get_params(1e-2, 1e-3), betas=(0.9, 0.99), eps=1e-15)
+    opt.load_state_dict(sd)
+    assert torch.equal(opt.state[net.encoder.embeddings]["exp_avg"].reshape(-1), tr.exp_avg[:n_table])
+    o = n_table
+    for w in weights:  # flat order of the trainer: deformation net, sigma net, colour net
+        assert torch.equal(opt.state[w]["exp_avg_sq"].reshape(-1), tr.exp_avg_sq[o:o + w.numel()])
+        assert float(opt.state[w]["step"]) == 17.0
+        o += w.numel()
+    sc = ckpt.scaler_state_dict(tr)
+    assert sc == {"scale": 4096.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 5}
