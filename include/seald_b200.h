@@ -391,11 +391,18 @@ int seald_dp_adam_shard_broadcast(void* const* peer_table16, void* mc_table16, i
  *   seald_occ_cell_points  sample point of cell j: (2 c / (H-1) - 1) * span + (rand * 2 - 1) * half_cell in the reference's fp32
  *                          operation order; c = coords[j] or, when coords == NULL, the j-th cell of custom_meshgrid(X, Y, Z)
  *                          (:477-497); indices[j] = Morton code of c (optional).
+ *   seald_occ_partial_points  the 2n sample points of the partial pass (:504-518): points [0, n) from the drawn cells rand_coords
+ *                          (torch.randint, int64 [n,3]); points [n, 2n) from the rand_mask[j]-th OCCUPIED cell
+ *                          (== nonzero(grid > 0)[rand_mask], :509-511), found by binary search in csum = inclusive prefix sum of
+ *                          (grid > 0) [n_cells] and decoded with morton3D_invert; indices[2n] = Morton codes; rand3 [2n,3] jitter.
  *   seald_occ_store        tmp[indices[j]] = sigma[j] * density_scale          (`tmp_grid[t, cas, indices] = sigmas`, :499)
  *   seald_occ_ema_max      grid = max(grid * decay, tmp) where grid >= 0 and tmp >= 0 (:541-543); tmp is reset to -1.
  * ------------------------------------------------------------------------------------------------ */
 int seald_occ_cell_points(const int32_t* coords, const float* rand3, uint32_t n, uint32_t H, float span, float half_cell,
                           float* xyzs, int32_t* indices, seald_stream_t stream);
+int seald_occ_partial_points(const int64_t* rand_coords, const int64_t* rand_mask, const int32_t* csum, uint32_t n_cells,
+                             const float* rand3, uint32_t n, uint32_t H, float span, float half_cell, float* xyzs, int32_t* indices,
+                             seald_stream_t stream);
 int seald_occ_store(const float* sigma, const int32_t* indices, uint32_t n, float density_scale, float* tmp, seald_stream_t stream);
 int seald_occ_ema_max(float* grid, float* tmp, uint32_t n, float decay, seald_stream_t stream);
 

@@ -70,11 +70,15 @@ def main(argv):
     if len(argv) >= 2 and argv[0] == "--one":
         build_one(argv[1])
         return 0
-    names = argv or ["gridencoder", "raymarching", "freqencoder", "shencoder"]
+    names = argv or ["gridencoder", "raymarching", "freqencoder", "shencoder", "ffmlp"]
     if not os.path.isdir(REF):
         print("reference tree absent (%s): using prebuilt oracle/_ref/*.so as-is" % REF)
         return 0
     os.makedirs(OUT, exist_ok=True)
+    # the reference's host modules, byte-compiled where they lie into oracle/_ref/py/ (sourceless .pyc; oracle/ref_runtime.py)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import ref_runtime
+    ref_runtime.stage_python()
     procs = []
     for n in names:
         if have(n):

@@ -68,6 +68,7 @@ _SIGS = {
     "seald_dp_adam_shard_broadcast": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],
     "seald_loss_scale_update_stash": [_vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp],
     "seald_occ_cell_points": [_vp, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _vp],
+    "seald_occ_partial_points": [_vp, _vp, _vp, _u32, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _vp],
     "seald_occ_store": [_vp, _vp, _u32, _f32, _vp, _vp],
     "seald_occ_ema_max": [_vp, _vp, _u32, _f32, _vp],
     "seald_get_rays_gather": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -19,6 +19,15 @@ __device__ __forceinline__ uint32_t occ_expand_bits(uint32_t v) {  // raymarchin
     return v;
 }
 
+__device__ __forceinline__ uint32_t occ_compact_bits(uint32_t x) {  // inverse of occ_expand_bits (raymarching.cu:71-80)
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xC30C30C3u;
+    x = (x | (x >> 4)) & 0x0F00F00Fu;
+    x = (x | (x >> 8)) & 0xFF0000FFu;
+    x = (x | (x >> 16)) & 0x0000FFFFu;
+    return x;
+}
+
 // coords == nullptr: point j is cell (x, y, z) = (j / H^2, (j / H) % H, j % H), the order of custom_meshgrid(X, Y, Z)
 // (dnerf/renderer.py:481-483); else coords[j] (the random / re-sampled cells of the partial pass, :507-518).
 __global__ void k_occ_cell_points(const int* __restrict__ coords, const float* __restrict__ rand3, const uint32_t n, const uint32_t H,
@@ -40,6 +49,40 @@ __global__ void k_occ_cell_points(const int* __restrict__ coords, const float* _
         const float x = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, (float)c[d]), inv_hm1), 1.0f);
         const float jit = __fmul_rn(__fsub_rn(__fmul_rn(rand3[j * 3 + d], 2.0f), 1.0f), half_cell);
         xyzs[j * 3 + d] = __fadd_rn(__fmul_rn(x, span), jit);
+    }
+}
+
+// Partial pass (dnerf/renderer.py:504-518): points [0, n) are the uniformly drawn cells `rand_coords` (torch.randint, int64), points
+// [n, 2n) re-sample OCCUPIED cells: the reference takes occ_indices = nonzero(grid > 0)[rand_mask]; here the rand_mask[j]-th occupied
+// cell is found by binary search in the inclusive prefix sum `csum` of (grid > 0) — the same cell, without materialising the index
+// list — and decoded from its Morton index (morton3D_invert).  Jitter and scaling as in k_occ_cell_points (same fp32 operation order).
+__global__ void k_occ_partial_points(const int64_t* __restrict__ rand_coords, const int64_t* __restrict__ rand_mask,
+                                     const int* __restrict__ csum, const uint32_t n_cells, const float* __restrict__ rand3, const uint32_t n,
+                                     const uint32_t H, const float span, const float half_cell, float* __restrict__ xyzs,
+                                     int* __restrict__ indices) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 2 * n) return;
+    uint32_t c[3], idx;
+    if (j < n) {
+        c[0] = (uint32_t)rand_coords[(size_t)j * 3]; c[1] = (uint32_t)rand_coords[(size_t)j * 3 + 1]; c[2] = (uint32_t)rand_coords[(size_t)j * 3 + 2];
+        idx = occ_expand_bits(c[0]) | (occ_expand_bits(c[1]) << 1) | (occ_expand_bits(c[2]) << 2);
+    } else {
+        const int want = (int)rand_mask[j - n] + 1;  // the (k+1)-th occupied cell = first position whose prefix sum reaches k + 1
+        uint32_t lo = 0, hi = n_cells - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(csum + mid) >= want) hi = mid; else lo = mid + 1;
+        }
+        idx = lo;
+        c[0] = occ_compact_bits(idx); c[1] = occ_compact_bits(idx >> 1); c[2] = occ_compact_bits(idx >> 2);
+    }
+    indices[j] = (int)idx;
+    const float inv_hm1 = __fdiv_rn(1.0f, (float)(H - 1));
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float x = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, (float)c[d]), inv_hm1), 1.0f);
+        const float jit = __fmul_rn(__fsub_rn(__fmul_rn(rand3[(size_t)j * 3 + d], 2.0f), 1.0f), half_cell);
+        xyzs[(size_t)j * 3 + d] = __fadd_rn(__fmul_rn(x, span), jit);
     }
 }
 
@@ -75,6 +118,16 @@ extern "C" int seald_occ_cell_points(const int32_t* coords, const float* rand3, 
     if (n == 0) return 0;
     if (!rand3 || !xyzs || H < 2 || H > 1024) return SEALD_E_BADARG;
     k_occ_cell_points<<<div_up(n, 256u), 256, 0, to_stream(stream)>>>(coords, rand3, n, H, span, half_cell, xyzs, indices);
+    return launch_status();
+}
+
+extern "C" int seald_occ_partial_points(const int64_t* rand_coords, const int64_t* rand_mask, const int32_t* csum, uint32_t n_cells,
+                                        const float* rand3, uint32_t n, uint32_t H, float span, float half_cell, float* xyzs,
+                                        int32_t* indices, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!rand_coords || !rand_mask || !csum || !rand3 || !xyzs || !indices || H < 2 || H > 1024 || n_cells == 0) return SEALD_E_BADARG;
+    k_occ_partial_points<<<div_up(2 * n, 256u), 256, 0, to_stream(stream)>>>(rand_coords, rand_mask, csum, n_cells, rand3, n, H, span, half_cell,
+                                                                            xyzs, indices);
     return launch_status();
 }
 

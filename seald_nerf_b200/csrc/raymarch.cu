@@ -407,7 +407,15 @@ __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float
     rays[n * 3 + 2] = num_steps;
 
     if (num_steps == 0) return;
-    if (point_index + num_steps > M) return;
+    if (point_index + num_steps > M) {  // overflow: dropped ray; its rows below M get the reference's zero fill (see the warp kernel)
+        for (size_t s = point_index; s < M; s++) {
+            xyzs[s * 3] = 0.f; xyzs[s * 3 + 1] = 0.f; xyzs[s * 3 + 2] = 0.f;
+            dirs[s * 3] = 0.f; dirs[s * 3 + 1] = 0.f; dirs[s * 3 + 2] = 0.f;
+            deltas[s * 2] = 0.f; deltas[s * 2 + 1] = 0.f;
+            if (SEAL) seal_mask[s] = 0;
+        }
+        return;
+    }
 
     xyzs += (size_t)point_index * 3;
     dirs += (size_t)point_index * 3;
@@ -576,7 +584,18 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
         rays[n * 3 + 2] = count;
     }
     if (count == 0) return;
-    if (point_index + count > M) return;
+    if (point_index + count > M) {
+        // overflow: the ray is dropped like in the reference (raymarching.cu:408), whose wrapper zero-filled the buffers
+        // (raymarching.py:205-207).  Rows [point_index, M) belong to no ray but are still evaluated by the field kernels:
+        // give them the reference's zeros instead of last step's samples.
+        for (size_t s = (size_t)point_index + lane; s < M; s += 32) {
+            xyzs[s * 3] = 0.f; xyzs[s * 3 + 1] = 0.f; xyzs[s * 3 + 2] = 0.f;
+            dirs[s * 3] = 0.f; dirs[s * 3 + 1] = 0.f; dirs[s * 3 + 2] = 0.f;
+            deltas[s * 2] = 0.f; deltas[s * 2 + 1] = 0.f;
+            if (SEAL) seal_mask[s] = 0;
+        }
+        return;
+    }
     __syncwarp();
     for (uint32_t j = lane; j < count; j += 32) {
         const float t = s_t[warp][j];
@@ -950,6 +969,14 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_train_loss_fused(
                     grad_rgbs[s * 3 + 2] = my_live ? gi[2] * my_w : 0.0f;
                     grad_sigmas[s] = my_live ? my_gs : 0.0f;
                 }
+            }
+        } else if (num_steps != 0 && offset < M) {
+            // Sample-buffer overflow: this ray's range straddles the end of the buffer, the ray is dropped (raymarching.cu:523-535)
+            // but its rows [offset, M) are still seen by the field backward (it runs over min(M, counter) rows).  The reference
+            // zero-fills the gradients before the launch (raymarching.py:283-284); nobody else writes these rows here, so do it.
+            for (size_t s = (size_t)offset + lane; s < M; s += 32) {
+                grad_rgbs[s * 3] = 0.0f; grad_rgbs[s * 3 + 1] = 0.0f; grad_rgbs[s * 3 + 2] = 0.0f;
+                grad_sigmas[s] = 0.0f;
             }
         }
     }

@@ -6,8 +6,10 @@ torch-composed `NeRFRenderer.update_extra_state` of this package under the same 
     1 kernel   jittered sample points + Morton indices          (csrc/occupancy.cu; the reference: ~10 torch kernels)
     3 kernels  density query: tcgen05 deformation net -> hash grid -> sigma head, on buffers allocated ONCE for H^3 points
     2 kernels  store into a per-frame temporary, decayed maximum (no 512 MiB temporaries, no boolean-mask passes)
-followed by ONE packbits launch over all time frames.  The occupied-cell re-sampling of the partial pass picks the k-th occupied
-cell through a prefix sum + binary search on the device (the reference synchronises per frame for `nonzero`).
+followed by ONE packbits launch over all time frames.  The partial pass draws the reference's random numbers in the reference's
+order (cells, ranks among the occupied cells, jitter), so it consumes the same generator stream and samples the SAME points; the
+rank-th occupied cell is found by a prefix sum + in-kernel binary search instead of `nonzero` (one host read of the 64 occupied-cell
+counts per refresh instead of one synchronisation per frame).
 """
 import torch
 
@@ -78,6 +80,9 @@ class FusedOccupancy:
             pass  # the reference stops re-sampling after 100 refreshes (only decay-free bookkeeping below)
         else:
             n_rand = n_full // 4
+            if not full:
+                # occupied-cell count of every frame in ONE host read (the reference synchronises per frame for `nonzero`, :509)
+                occ_counts = (m.density_grid > 0).sum(-1).cpu()
             per = m.time_size // self.world_size
             main = torch.cuda.current_stream()
             for pp in self.pipes:
@@ -97,17 +102,18 @@ class FusedOccupancy:
                             _lib.call("seald_occ_cell_points", None, ptr(rnd), n, H, float(bound - half_cell), float(half_cell), ptr(pp["xyzs"]),
                                       ptr(pp["indices"]), st())
                         else:
-                            coords = torch.randint(0, H, (n_rand, 3), device=dev, dtype=torch.int32)
-                            # k-th occupied cell of this frame, k uniform: prefix sum + binary search on the device (no nonzero / sync)
-                            csum = torch.cumsum((m.density_grid[t, cas] > 0).to(torch.int32), 0)
-                            k = (torch.rand(n_rand, device=dev) * csum[-1]).to(torch.int32)
-                            occ = torch.searchsorted(csum, k + 1).clamp_(max=n_full - 1).to(torch.int32)
-                            occ_coords = raymarching.morton3D_invert(occ)
-                            coords = torch.cat([coords, occ_coords.to(torch.int32)], 0).contiguous()
-                            n = coords.shape[0]
+                            # the reference's draws, in its order and dtypes (same generator stream): cells, then ranks among the occupied
+                            # cells of this frame, then the jitter of all 2n points (dnerf/renderer.py:507-524)
+                            coords = torch.randint(0, H, (n_rand, 3), device=dev)
+                            n_occ = int(occ_counts[t, cas])
+                            if n_occ == 0:  # (the reference's randint(0, 0) raises here; an empty frame just gets no re-sampled cells)
+                                n_occ = 1
+                            rand_mask = torch.randint(0, n_occ, [n_rand], dtype=torch.long, device=dev)
+                            csum = torch.cumsum(m.density_grid[t, cas] > 0, 0, dtype=torch.int32)
+                            n = 2 * n_rand
                             rnd = torch.rand(n, 3, device=dev)
-                            _lib.call("seald_occ_cell_points", ptr(coords), ptr(rnd), n, H, float(bound - half_cell), float(half_cell),
-                                      ptr(pp["xyzs"]), ptr(pp["indices"]), st())
+                            _lib.call("seald_occ_partial_points", ptr(coords), ptr(rand_mask), ptr(csum), n_full, ptr(rnd), n_rand, H,
+                                      float(bound - half_cell), float(half_cell), ptr(pp["xyzs"]), ptr(pp["indices"]), st())
                         pp["time_dev"].copy_((time + (torch.rand_like(time) * 2 - 1) * half_time).reshape(-1)[:1])
                         self._query_and_store(pp, n, t, cas, hw, table16)
             for pp in self.pipes:

@@ -115,6 +115,47 @@ def test_fused_composite_loss_kernel_equals_three_kernels(cuda_dev):
     assert float((res[0][7] - res[1][7]).abs().max()) <= 1e-4 * scale  # (atomic order in the scatter)
 
 
+def test_sample_buffer_overflow_leaves_no_stale_gradients(cuda_dev):
+    """max_samples below the live sample count: rays whose range does not fit are dropped (raymarching.cu:408, :523), and the rows of
+    the one range that straddles the end of the buffer must carry the reference's zero fill — not the previous step's samples and
+    gradients.  Two steps on different batches with an overflowing buffer: the table / weight gradients of the second step must equal
+    those of the same step run from clean buffers, for the fused compositing kernel and the three-kernel path alike."""
+    from seald_nerf_b200.trainer import FusedTrainer
+    grads = {}
+    for fuse in (True, False):
+        for poison in (True, False):
+            model = _scene(cuda_dev)
+            model.encoder.embeddings.data.uniform_(-0.3, 0.3)
+            o, d, t, gt = _batch(cuda_dev, n=2048, seed=0)
+            tr = FusedTrainer(model, num_rays=2048, max_samples=8192, perturb=False, init_loss_scale=128.0, use_graph=False, fuse_composite=fuse)
+            if poison:  # what an earlier overflowing step would have left behind
+                tr.xyzs.uniform_(-0.5, 0.5); tr.dirs.fill_(0.577); tr.deltas.fill_(0.01)
+                tr.grad_sigma.fill_(3.0); tr.grad_rgb.fill_(-2.0)
+            tr.set_inputs(o, d, t, gt)
+            tr._forward_backward()
+            torch.cuda.synchronize()
+            live = int(tr.counter[0])
+            assert live > tr.M, (live, tr.M)  # the batch really overflows
+            rays = tr.rays.cpu()
+            kept = (rays[:, 2] > 0) & (rays[:, 1] + rays[:, 2] <= tr.M)
+            assert 0 < int(kept.sum()) < int((rays[:, 2] > 0).sum())
+            straddle = (rays[:, 2] > 0) & (rays[:, 1] < tr.M) & (rays[:, 1] + rays[:, 2] > tr.M)
+            if bool(straddle.any()):
+                off = int(rays[straddle][0, 1])
+                for buf in (tr.xyzs, tr.dirs, tr.deltas, tr.grad_sigma, tr.grad_rgb):
+                    assert float(buf[off:tr.M].abs().max()) == 0.0
+            grads[(fuse, poison)] = (tr.grad_table.clone(), [g.clone() for g in tr.grad_views], kept)
+    for fuse in (True, False):
+        (ta, wa, ka), (tb, wb, kb) = grads[(fuse, True)], grads[(fuse, False)]
+        # (which rays fit depends on the order in which CTAs reserve their ranges: compare only when the same rays were kept)
+        if torch.equal(ka, kb):
+            scale = float(tb.abs().max())
+            assert float((ta - tb).abs().max()) <= 1e-4 * scale
+            for a, b in zip(wa, wb):
+                assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-9
+        assert bool(torch.isfinite(ta).all())
+
+
 @pytest.mark.gpu
 def test_data_parallel_modes_two_gpus():
     """World-size-2 run of scripts/dp_check.py (needs 2 GPUs): the summed per-rank gradient equals the single-GPU gradient
