@@ -6,8 +6,10 @@
 Workload (config.workload): one optimisation step of the D-NeRF field (hashgrid 16 levels x 2 features, T = 2^19,
 8x128 time-conditioned deformation net, 64-wide sigma / colour heads) on a 4096-ray batch per GPU of the synthetic
 jumpingjacks-shaped scene (800x800 cameras, t in [0,1]), `-O` semantics: fp16 tensor-core MLPs, cuda_ray march through
-the occupancy bitfield, perturbed samples, loss-scaled Adam.  Data parallel across GPUs: every rank draws its own
-4096-ray batch, one NCCL allreduce of the flat gradient buffer per step ("scaling": "weak").
+the occupancy bitfield, perturbed samples, loss-scaled Adam.  Data parallel across GPUs ("scaling": "weak"): every rank draws its own
+4096-ray batch; the table / MLP gradients are summed by the fused exchange kernels of csrc/dp_fused.cu over NVLink peer memory
+(symmetric memory + NVSwitch multicast; the reduce-scatter -> shard Adam -> fp16 broadcast is part of the step graph).  NCCL is
+the process-group plumbing and the fallback exchange (SEALD_DP_MODE=sharded|allreduce).
 
 `value`  : rays/s with the step's inputs already resident in HBM (device-timed with CUDA events, max over ranks).
 `e2e`    : the same metric through the public API with HOST inputs (pinned H2D of rays/targets every step and a D2H
@@ -18,6 +20,9 @@ the occupancy bitfield, perturbed samples, loss-scaled Adam.  Data parallel acro
 `hashgrid`: GridEncoder 2^22 points x 16 levels forward / backward, GB/s of algorithmic bytes (BASELINE configs[4]).
 `seald`   : SealD teacher->student distillation step (teacher render with the fused bbox proxy mapping + student train
            step with the frozen deformation net, BASELINE configs[3]) in rays/s.
+`ref_gpu` : the REFERENCE's own CUDA path on this GPU (its host code + its extensions recompiled for sm_100a + cuBLAS autocast,
+           oracle/ref_bench.py in a subprocess): train step, frame, occupancy refresh and per-kernel times beside ours.
+`roofline_rows`: every north-star kernel (encoder fwd/bwd, march, composite, MLPs) at benchmark and at microbenchmark size.
 `cpu_baseline` / `--impl reference`: the reference's pure-PyTorch path (cuda_ray=False, torch frequency encoders,
            BASELINE.json configs[0]) as ported in oracle/render.py, timed on the host cores (forward+render only).
 """
@@ -206,6 +211,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the frame / seald / hashgrid workloads (train step only)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU subprocess (oracle/ref_bench.py)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -315,6 +321,7 @@ def main():
         barrier()
         ms_e2e_ds = e0.elapsed_time(e1)
     trainer.flush()  # the table pass of the last step's optimiser is deferred into the next step: apply it before the model is rendered
+    steps_run = trainer.global_step
     clocks = sampler.stop(t_clk0, sampler.mark()) if rank == 0 else None
 
     # ---- full-frame render, ray tiles sharded over the ranks (configs[2]) ------------------------------------------------
@@ -365,25 +372,47 @@ def main():
         cfg = trainer.cfg
         mac_deform = 76 * 128 + (cfg.n_deform - 2) * 128 * 128 + 128 * 3
         mac_heads = 32 * 64 + 64 * 16 + 31 * 64 + (cfg.n_color - 2) * 64 * 64 + 64 * 3
-        work = {  # algorithmic work per launch (SURVEY.md §8d figures x live samples)
+        def bytes_moved_by_adam(n_elems):
+            """Bytes the table pass really moves: it reads g, m, v of every element (12 B) and, only where the gradient or a moment is
+            non-zero, reads p and writes p, m, v and the fp16 copy (+18 B); the gradient is cleared where it was non-zero (+4 B)."""
+            nt = (n_elems // 4) * 4
+            touched = int((trainer.exp_avg[:nt].view(-1, 4) != 0).any(1).sum().item()) * 4
+            return 12.0 * n_elems + 18.0 * touched + 4.0 * min(touched, 16 * 8 * m_live * cfg.grid_dim), touched
+
+        n_opt = trainer.shard_len if trainer.dp_mode in ("fused", "sharded") else trainer.n_table_pad
+        adam_moved, adam_touched = bytes_moved_by_adam(n_opt)
+        work = {  # ALGORITHMIC work per launch (SURVEY.md §8d per-unit figures x live samples)
             "deform_fwd": ("tensor", 2.0 * mac_deform * m_live),
             "deform_bwd": ("tensor", 2.0 * (mac_deform - 76 * 128) * m_live),
             "wgrad": ("tensor", 2.0 * (mac_deform + mac_heads) * m_live),
             "heads_fwd": ("tensor", 2.0 * mac_heads * m_live),
             "heads_bwd": ("tensor", 2.0 * mac_heads * m_live),
             "grid_fwd": ("hbm", 588.0 * m_live),
-            "grid_scatter": ("hbm", 2124.0 * m_live),      # fp32 gradient table: 12 + 64 + 2 * 8 * 16 * 2 * 4
+            "grid_scatter": ("hbm", 1100.0 * m_live),      # §8(d): 12 + 64 + 2 * 8 * 16 * 2 * 2 (fp16 table); the fp32 table we keep moves 2124
             "grid_input_bwd": ("hbm", (588.0 + 12.0) * m_live),
             "march": ("hbm", 48.0 * N_RAYS + 32.0 * m_live + 262144.0),
             "composite_fwd": ("hbm", 24.0 * m_live + 32.0 * N_RAYS),
             "composite_bwd": ("hbm", 40.0 * m_live + 48.0 * N_RAYS),
             "composite_loss_fused": ("hbm", 64.0 * m_live + 104.0 * N_RAYS),
-            "optimizer": ("hbm", 34.0 * trainer.n_params),   # (1 GPU: table + MLP weights in the same stage; the weights are 1% of it)
-            # Adam over the fp32 table: p, m, v read + written (24 B), gradient read + cleared (8 B), fp16 copy written (2 B) per parameter
-            "optimizer_table": ("hbm", 34.0 * (trainer.shard_len if trainer.dp_mode in ("fused", "sharded") else trainer.n_table_pad)),
+            # Adam over the fp32 table: 34 B/param if every element were updated; what the kernel really moves is computed above
+            "optimizer": ("hbm", min(34.0 * trainer.n_params, adam_moved + 34.0 * trainer.n_weights)),
+            "optimizer_table": ("hbm", min(34.0 * n_opt, adam_moved)),
         }
-        if trainer.defer_table_update or trainer.dp_mode != "single":
+        if "optimizer_table" in st:
             work.pop("optimizer")  # there it is only the MLP-weight update + fp16 repack + loss-scale kernels
+        else:
+            work.pop("optimizer_table")
+
+        def row(name, bound, amount, ms, size):
+            sec = ms * 1e-3
+            if bound == "tensor":
+                a, pk, un = amount / sec / 1e12, tf_burst, "TFLOP/s"
+            else:
+                a, pk, un = amount / sec / 1e9, hbm, "GB/s"
+            return {"kernel": name, "size": size, "bound": bound, "ms": round(ms, 5), "algorithmic": amount, "achieved": round(a, 2), "peak": pk,
+                    "unit": un, "frac": round(a / pk, 4)}
+
+        rows = [row(k, work[k][0], work[k][1], st[k], "train step: 4096 rays / %d samples" % m_live) for k in st if k in work and st[k] > 0]
         dom = max((k for k in st if k in work), key=lambda k: st[k])
         bound, amount = work[dom]
         sec = st[dom] * 1e-3
@@ -393,15 +422,18 @@ def main():
             achieved, peak, unit = amount / sec / 1e9, hbm, "GB/s"
         # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of the same step (profiles/, per round)
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r1c_traffic.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
-            ent = tj["per_launch_dram_bytes"].get(dom)
-            if ent and world == 1:
-                traffic, traffic_src = ent["read"] + ent["write"], "%s: %s" % (tj["source"], ent["kernel"])
+        for tp in ("r2_traffic.json", "r1c_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tp)
+            if os.path.exists(tp) and traffic is None:
+                tj = json.load(open(tp))
+                ent = tj["per_launch_dram_bytes"].get(dom)
+                if ent and world == 1:
+                    traffic, traffic_src = ent["read"] + ent["write"], "%s: %s" % (tj["source"], ent["kernel"])
         roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": traffic,
                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
                     "algorithmic_per_launch": amount,
+                    "bytes_note": ("optimizer: bytes the kernel really moves (12 B/element read + 22 B where a gradient or moment is non-zero; %d of %d "
+                                   "elements live), not 34 B x every element" % (adam_touched, n_opt)) if dom.startswith("optimizer") else None,
                     "peak_source": which + (" burst" if bound == "tensor" else ""), "ms": st[dom],
                     "stage_ms": {k: round(v, 4) for k, v in st.items()}, "live_samples": m_live}
 
@@ -446,12 +478,59 @@ def main():
             line["occupancy_update"] = dict(occ, unit="wall ms per update_extra_state (64 time frames x 128^3 cells, sharded over the ranks, incl. its host syncs)",
                                             field_queries={"full_sweep": 64 * 128 ** 3, "partial": 64 * 128 ** 3 // 2},
                                             amortised_rays_per_s_every_100_steps=total_rays / ((step_ms + occ["partial_ms"] / 100.0) * 1e-3))
+        line["config"]["skipped_steps"] = int(steps_run - int(trainer.step_dev.item())) if steps_run is not None else None
+        line["config"]["skipped_steps_note"] = ("optimiser steps GradScaler skipped (overflow while the loss scale settles from 65536) out of %d run "
+                                                "since the trainer was built; a skipped step does not touch Adam rows" % steps_run)
         if not args.no_extras:
             g = microbench.grid_encoder(device, 22, 3, "hash", torch.float16, reps=10, hbm_gbs=hbm)
+            g4 = microbench.grid_encoder(device, 22, 4, "hash", torch.float16, reps=5, hbm_gbs=hbm)
+            mc = microbench.march_composite(device, reps=5, hbm_gbs=hbm)
+            fl = microbench.field_throughput(device, log2_M=20, reps=5, tf_peak=tf_burst)
+            big = "2^22 uniform points"
+            k3, k4 = g["kernels"], g4["kernels"]
+            rows += [
+                row("grid_fwd", "hbm", 588.0 * g["B"], k3["fwd"]["ms"], big + ", 3-D"),
+                row("grid_fwd", "hbm", 1104.0 * g4["B"], k4["fwd"]["ms"], big + ", 4-D"),
+                row("grid_bwd_table (fp32 gradient table, the product path)", "hbm", 1100.0 * g["B"], k3["bwd_table_f32"]["ms"], big + ", 3-D, §8d bytes (1100 B/pt)"),
+                row("grid_bwd_table (fp32 gradient table, the product path)", "hbm", 2124.0 * g["B"], k3["bwd_table_f32"]["ms"], big + ", 3-D, bytes of the fp32 table (2124 B/pt)"),
+                row("grid_bwd_table (fp16 gradient table, the reference's dtype)", "hbm", 1100.0 * g["B"], k3["bwd_table_same_dtype"]["ms"], big + ", 3-D"),
+                row("march_train", "hbm", mc["march_train"]["algorithmic_GB"] * 1e9, mc["march_train"]["ms"], "%d rays / %d samples" % (mc["rays"], mc["samples"])),
+                row("composite_fwd", "hbm", mc["composite_fwd"]["algorithmic_GB"] * 1e9, mc["composite_fwd"]["ms"], "%d rays / %d samples" % (mc["rays"], mc["samples"])),
+                row("composite_bwd", "hbm", mc["composite_bwd"]["algorithmic_GB"] * 1e9, mc["composite_bwd"]["ms"], "%d rays / %d samples" % (mc["rays"], mc["samples"])),
+                row("packbits", "hbm", mc["packbits_64frames"]["algorithmic_GB"] * 1e9, mc["packbits_64frames"]["ms"], "64 frames x 128^3 cells"),
+                row("deform_fwd (tcgen05)", "tensor", 2.0 * mac_deform * fl["M"], fl["deform_fwd_tcgen05"]["ms"], "2^20 samples"),
+                row("heads_fwd", "tensor", 2.0 * mac_heads * fl["M"], fl["heads_fwd"]["ms"], "2^20 samples"),
+            ]
+            line["roofline_rows"] = rows
+            line["hashgrid_4d"] = {"points": g4["B"], "fwd_ms": k4["fwd"]["ms"], "fwd_GBs": k4["fwd"]["GB/s"], "fwd_frac_of_hbm": k4["fwd"]["frac_of_hbm"],
+                                   "bwd_ms": k4["bwd_table_f32"]["ms"], "bytes_per_point": {"fwd": 1104}}
             line["hashgrid"] = {"points": g["B"], "levels": 16, "table": "2^19 x 2 fp16", "fwd_GBs": g["kernels"]["fwd"]["GB/s"],
                                 "fwd_frac_of_hbm": g["kernels"]["fwd"]["frac_of_hbm"], "fwd_ms": g["kernels"]["fwd"]["ms"],
                                 "bwd_GBs": g["kernels"]["bwd_table_f32"]["GB/s"], "bwd_frac_of_hbm": g["kernels"]["bwd_table_f32"]["frac_of_hbm"],
-                                "bwd_ms": g["kernels"]["bwd_table_f32"]["ms"], "bytes_per_point": {"fwd": 588, "bwd_f32_table": 2124}}
+                                "bwd_ms": g["kernels"]["bwd_table_f32"]["ms"], "bytes_per_point": {"fwd": 588, "bwd_f32_table": 2124},
+                                "bwd_frac_of_hbm_on_1100B": round(1100.0 * g["B"] / (g["kernels"]["bwd_table_f32"]["ms"] * 1e-3) / 1e9 / hbm, 4)}
+        else:
+            line["roofline_rows"] = rows
+        if world == 1 and not args.no_ref_gpu and not args.no_extras:
+            # the reference's own CUDA path on this GPU, in its own process (it launches on the legacy default stream)
+            try:
+                pr = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--steps", str(min(max(K, 20), 100)),
+                                     "--warmup", "20"], capture_output=True, text=True, timeout=600)
+                rg = json.loads(pr.stdout.strip().splitlines()[-1]) if pr.returncode == 0 and pr.stdout.strip() else {
+                    "unavailable": "oracle/ref_bench.py rc %d: %s" % (pr.returncode, pr.stderr[-300:])}
+            except Exception as e:  # noqa: BLE001
+                rg = {"unavailable": repr(e)[:300]}
+            if "train" in rg:
+                rg["ours_over_ref"] = {
+                    "train_step": round(rg["train"]["ms_per_step"] / (ms / K), 2),
+                    "train_step_e2e": round(rg["train"]["e2e_ms_per_step"] / (ms_e2e / Ke), 2),
+                    "frame": round(rg["frame"]["frame_ms_median"] / ms_frame, 2) if ms_frame > 0 and "frame" in rg else None,
+                    "occupancy_full": round(rg["occupancy_update"]["full_sweep_ms"] / occ["full_sweep_ms"], 2) if occ and "occupancy_update" in rg else None,
+                    "occupancy_partial": round(rg["occupancy_update"]["partial_ms"] / occ["partial_ms"], 2) if occ and "occupancy_update" in rg else None,
+                    "grid_fwd_2p22": round(rg["kernels"]["grid_3d_fwd"]["ms"] / line["hashgrid"]["fwd_ms"], 2) if "kernels" in rg else None,
+                    "grid_bwd_2p22": round(rg["kernels"]["grid_3d_bwd_fp16_table"]["ms"] / line["hashgrid"]["bwd_ms"], 2) if "kernels" in rg else None,
+                }
+            line["ref_gpu"] = rg
         print(json.dumps(line), flush=True)
     if world > 1:
         # Teardown with a bounded wait (a communicator teardown that blocks must not turn a finished measurement into a hang).

@@ -359,6 +359,36 @@ int seald_loss_scale_update(float* loss_scale, int32_t* found_inf, int32_t* grow
 int seald_loss_scale_update_stash(float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth, float backoff,
                                   int interval, int32_t* step_dev, int32_t* stash, seald_stream_t stream);
 
+/* The learning rate as lr * *lr_scale_dev (NULL: lr): the LambdaLR factor of main_dnerf.py:134 lives on the device so a
+ * graph-captured step follows the schedule without being recaptured.  Otherwise seald_adam_step_ex. */
+int seald_adam_step_lr(float* p, float* g, float* m, float* v, uint64_t n, float lr, const float* lr_scale_dev, float beta1, float beta2,
+                       float eps, uint32_t step, const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16,
+                       int zero_grad, uint32_t max_blocks, seald_stream_t stream);
+
+/* The MLP-weight tail of a training step in ONE launch (csrc/optim_tail.cu): overflow check of the MLP gradients (ORed into
+ * *found_inf, which the table scatter may already have raised) -> grid barrier -> torch.optim.Adam on the weights
+ * (p, g, m, v point at the MLP region; skipped on overflow; gradients cleared) with the refreshed values written as fp16 into the
+ * row-padded staging copy and the tcgen05 operand tiles (seald_field_umma_pack_deform* layouts) -> GradScaler.update()
+ * (nerf/utils.py:884-886) -> lr_scheduler.step() (factor 0.1 ** min(iter / sched_iters, 1) written to *lr_scale; sched_iters <= 0
+ * or lr_scale == NULL: constant).  stash[4] receives {found_inf, step, loss-scale bits, lr-factor bits} as they applied to THIS
+ * step, for the hash-table pass (seald_adam_step_lr with the stash as step_dev / loss_scale / found_inf / lr_scale_dev).
+ * segs: the weight matrices in buffer order (first = running element offset); sync2: two zero-initialised ints. */
+typedef struct seald_tail_seg {
+    uint32_t first, rows, cols, ld;
+    void* dst16;    /* fp16 staging copy [rows][ld] */
+    void* packed;   /* K-major operand tile of a deformation layer ([cols_pad/8][n_pad][8]) or NULL */
+    uint32_t n_pad;
+    void* packedT;  /* transposed operand tile ([rows_pad/8][128][8]) or NULL */
+} seald_tail_seg;
+int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2,
+                   float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth,
+                   float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters, int32_t* sync2,
+                   seald_stream_t stream);
+
+/* torch_ema.ExponentialMovingAverage.update: shadow -= (1 - decay) * (shadow - param) (ema_decay = 0.95, main_dnerf.py:136;
+ * once per epoch, nerf/utils.py:909-910). */
+int seald_ema_update(float* shadow, const float* param, uint64_t n, float decay, seald_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Data-parallel exchange fused with the optimiser over NVLink peer memory (no counterpart in the reference, which is
  * single-GPU: this is the "hash-table and MLP gradients summed over the GPUs" step of BASELINE.json's north_star,

@@ -78,8 +78,17 @@ _SIGS = {
     "seald_adam_advance": [_vp, _vp, _vp],
     "seald_adam_step": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _vp],
     "seald_adam_step_ex": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _u32, _vp],
+    "seald_adam_step_lr": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _vp, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _u32, _vp],
+    "seald_mlp_tail": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
+    "seald_ema_update": [_vp, _vp, C.c_uint64, _f32, _vp],
     "seald_loss_scale_update": [_vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp],
 }
+
+
+class TailSeg(C.Structure):
+    """seald_tail_seg of include/seald_b200.h."""
+    _fields_ = [("first", C.c_uint32), ("rows", C.c_uint32), ("cols", C.c_uint32), ("ld", C.c_uint32), ("dst16", C.c_void_p),
+                ("packed", C.c_void_p), ("n_pad", C.c_uint32), ("packedT", C.c_void_p)]
 
 
 class WgradJob(C.Structure):

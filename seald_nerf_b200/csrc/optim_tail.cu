@@ -1,0 +1,184 @@
+// optim_tail.cu — everything a training step does after the weight-gradient GEMMs, for the MLP weights, in ONE launch:
+//
+//     GradScaler.unscale_ / found-inf check  ->  Adam on the 13 nn.Linear weights (main_dnerf.py:129)  ->  fp16 staging copies and
+//     the tcgen05 operand tiles of the refreshed weights  ->  GradScaler.update (nerf/utils.py:884-886)  ->  lr_scheduler.step()
+//     (LambdaLR 0.1 ** min(iter / iters, 1), main_dnerf.py:134)
+//
+// The reference runs this as  scaler.step(optimizer); scaler.update(); lr_scheduler.step()  = one multi-tensor Adam + ~10 tiny
+// kernels and two host synchronisations (found_inf.item()).  Round 1 of this library used five launches (finite check, Adam, fp16
+// cast, tile repack, loss-scale update); they were ~15 us of a 400 us step, all launch latency.  Here:
+//
+//   phase 0   every thread looks at its share of the MLP gradients; a CTA that sees inf/nan raises the step's overflow flag
+//             (the table scatter has already raised it for the table gradient)
+//   barrier   grid-wide (atomic arrive + spin; the grid is at most one CTA per SM, so every CTA is resident)
+//   phase 1   Adam on the same elements (skipped as a whole on overflow), gradient cleared, and the new value scattered as fp16 to
+//             the three places the forward/backward kernels read it from: row-padded staging copy, K-major UMMA tile, and the
+//             transposed UMMA tile of the deformation backward — all pure permutations of the weight matrix
+//   phase 2   the LAST CTA to finish applies GradScaler.update, advances the step / scheduler counters, computes the next
+//             learning-rate factor, stashes {found_inf, step, loss scale} for the hash-table pass that follows, resets the flags
+//
+// The hash-table Adam pass (k_adam, train.cu) runs after it (or beside the next step's march) with the stashed values.
+#include "common.cuh"
+
+namespace seald {
+
+constexpr int kTailMaxSegs = 16;
+struct TailSeg {
+    uint32_t first;      // offset of the matrix inside the MLP region of the flat buffers
+    uint32_t rows, cols; // nn.Linear.weight [rows = out][cols = in]
+    uint32_t ld;         // row pitch of the fp16 staging copy
+    __half* dst16;       // staging copy [rows][ld]
+    __half* packed;      // K-major operand tile [cols_pad / 8][n_pad][8] of this layer (deformation net only, else nullptr)
+    uint32_t n_pad;      // rows of that tile (128, or 16 for the last layer)
+    __half* packedT;     // transposed tile [rows_pad / 8][128][8] (deformation layers 1 .. n-1, else nullptr)
+};
+struct TailSegs {
+    TailSeg s[kTailMaxSegs];
+    int n;
+    uint32_t total;
+};
+
+struct TailState {
+    int* step_dev;         // completed optimiser updates
+    float* loss_scale;
+    int* found_inf;        // bits of a positive float when any gradient overflowed (summed across ranks as a float elsewhere)
+    int* growth_tracker;
+    int* stash;            // [4]: {found_inf, step, loss-scale bits, -} of THIS step, for the table pass
+    float* lr_scale;       // learning-rate factor of the CURRENT step (read), replaced by the next step's (written)
+    int* sched_step;       // lr_scheduler.last_epoch
+    int* sync;             // [2]: barrier arrivals, finished CTAs
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_mlp_tail(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                  const __grid_constant__ TailSegs segs, const TailState st, const float lr,
+                                                  const float beta1, const float beta2, const float eps, const float growth, const float backoff,
+                                                  const int interval, const int sched_iters) {
+    const uint32_t n = segs.total;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+
+    // ---- phase 0: overflow check over this thread's gradients -----------------------------------------------------------------
+    bool bad = false;
+    for (uint32_t i = i0; i < n; i += stride) bad |= !isfinite(g[i]);
+    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+    if (threadIdx.x == 0) {
+        if (any_bad) atomicOr(st.found_inf, 0x3f800000);
+        __threadfence();
+        atomicAdd(st.sync, 1);
+        while (ld_acquire(st.sync) < (int)gridDim.x) __nanosleep(32);
+    }
+    __syncthreads();
+
+    // ---- phase 1: Adam + fp16 copies ----------------------------------------------------------------------------------------------
+    const bool skip = ld_acquire(st.found_inf) != 0;
+    if (!skip) {
+        const double stp = (double)(*st.step_dev + 1);
+        const float bc1 = (float)(1.0 - pow((double)beta1, stp));
+        const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, stp));
+        const float inv_scale = 1.0f / *st.loss_scale;
+        const float step_size = (lr * (st.lr_scale ? *st.lr_scale : 1.0f)) / bc1;
+        int k = 0;
+        for (uint32_t i = i0; i < n; i += stride) {
+            while (k + 1 < segs.n && i >= segs.s[k + 1].first) k++;
+            const TailSeg& sg = segs.s[k];
+            const float gi = g[i] * inv_scale;
+            const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+            const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+            const float pi = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+            m[i] = mi; v[i] = vi; p[i] = pi; g[i] = 0.0f;
+            const uint32_t j = i - sg.first;
+            const uint32_t r = j / sg.cols, c = j - r * sg.cols;
+            const __half h = __float2half_rn(pi);
+            sg.dst16[(size_t)r * sg.ld + c] = h;
+            if (sg.packed) sg.packed[((size_t)(c >> 3) * sg.n_pad + r) * 8 + (c & 7)] = h;
+            if (sg.packedT) sg.packedT[((size_t)(r >> 3) * 128 + c) * 8 + (r & 7)] = h;
+        }
+    } else {
+        for (uint32_t i = i0; i < n; i += stride) g[i] = 0.0f;
+    }
+
+    // ---- phase 2: the last CTA closes the step ---------------------------------------------------------------------------------------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(st.sync + 1, 1) + 1;
+        if (done == (int)gridDim.x) {
+            const int found = *st.found_inf;
+            st.stash[0] = found;
+            st.stash[1] = *st.step_dev;
+            st.stash[2] = __float_as_int(*st.loss_scale);
+            st.stash[3] = __float_as_int(st.lr_scale ? *st.lr_scale : 1.0f);
+            if (found) {
+                *st.loss_scale *= backoff;
+                *st.growth_tracker = 0;
+            } else {
+                *st.step_dev += 1;
+                const int t = *st.growth_tracker + 1;
+                if (t >= interval) { *st.loss_scale *= growth; *st.growth_tracker = 0; }
+                else *st.growth_tracker = t;
+            }
+            if (st.sched_step) {  // lr_scheduler.step() runs every iteration, skipped or not (nerf/utils.py:888-889)
+                const int e = *st.sched_step + 1;
+                *st.sched_step = e;
+                if (st.lr_scale && sched_iters > 0) *st.lr_scale = (float)pow(0.1, fmin((double)e / (double)sched_iters, 1.0));
+            }
+            *st.found_inf = 0;
+            st.sync[0] = 0;
+            st.sync[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// shadow -= (1 - decay) * (shadow - param): torch_ema.ExponentialMovingAverage.update (the reference's `ema_decay=0.95`,
+// main_dnerf.py:136, updated once per epoch, nerf/utils.py:909-910)
+__global__ void k_ema_update(float* __restrict__ shadow, const float* __restrict__ param, const size_t n, const float one_minus_decay) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float s = shadow[i];
+        shadow[i] = s - one_minus_decay * (s - param[i]);
+    }
+}
+
+}  // namespace seald
+
+using namespace seald;
+
+extern "C" int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2,
+                              float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth,
+                              float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters,
+                              int32_t* sync2, seald_stream_t stream) {
+    if (!p || !g || !m || !v || !segs || n_segs <= 0 || n_segs > kTailMaxSegs) return SEALD_E_BADARG;
+    if (!step_dev || !loss_scale || !found_inf || !growth_tracker || !stash || !sync2) return SEALD_E_BADARG;
+    TailSegs ts;
+    uint32_t total = 0;
+    for (int i = 0; i < n_segs; i++) {
+        const seald_tail_seg& a = segs[i];
+        if (!a.dst16 || a.rows == 0 || a.cols == 0 || a.ld < a.cols || a.first != total) return SEALD_E_BADARG;
+        if (a.packedT && (a.cols > 128)) return SEALD_E_UNSUPPORTED;
+        ts.s[i] = TailSeg{a.first, a.rows, a.cols, a.ld, (__half*)a.dst16, (__half*)a.packed, a.n_pad, (__half*)a.packedT};
+        total += a.rows * a.cols;
+    }
+    ts.n = n_segs;
+    ts.total = total;
+    TailState st{step_dev, loss_scale, found_inf, growth_tracker, stash, lr_scale, sched_step, sync2};
+    // at most one CTA per SM: the grid barrier needs every CTA resident
+    uint32_t blocks = div_up(total, 256u * 4u);
+    if (blocks > (uint32_t)SEALD_NUM_SMS) blocks = SEALD_NUM_SMS;
+    if (blocks == 0) blocks = 1;
+    k_mlp_tail<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff, interval, sched_iters);
+    return launch_status();
+}
+
+extern "C" int seald_ema_update(float* shadow, const float* param, uint64_t n, float decay, seald_stream_t stream) {
+    if (n == 0) return 0;
+    if (!shadow || !param || !(decay >= 0.0f && decay <= 1.0f)) return SEALD_E_BADARG;
+    const uint32_t blocks = (uint32_t)(div_up<uint64_t>(n, 256) < 8ull * SEALD_NUM_SMS ? div_up<uint64_t>(n, 256) : 8ull * SEALD_NUM_SMS);
+    k_ema_update<<<blocks, 256, 0, to_stream(stream)>>>(shadow, param, (size_t)n, 1.0f - decay);
+    return launch_status();
+}

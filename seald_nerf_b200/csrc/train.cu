@@ -86,7 +86,7 @@ __global__ void k_grad_finite_check(const float* __restrict__ g, const size_t n,
 __global__ void __launch_bounds__(256, 4) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const size_t n,
                        const float lr, const float beta1, const float beta2, const float eps, float bc1, float bc2_sqrt,
                        const int* __restrict__ step_dev, const int step_add, const float* __restrict__ loss_scale,
-                       const int* __restrict__ found_inf, __half* __restrict__ p16, const int zero_grad) {
+                       const int* __restrict__ found_inf, __half* __restrict__ p16, const int zero_grad, const float* __restrict__ lr_scale) {
     const bool skip = found_inf && *found_inf != 0;
     if (step_dev) {  // step number kept on the device (graph replay): bias corrections computed here
         __shared__ float s_bc[2];
@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256, 4) k_adam(float* __restrict__ p, float* _
     // 128-bit path over the aligned body (n is a multiple of 4 for the slabs the trainer passes)
     const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0) && (!p16 || ((uintptr_t)p16 & 7) == 0);
     const size_t n4 = vec ? n / 4 : 0;
-    const float step_size = lr / bc1;
+    const float lr_eff = lr_scale ? lr * *lr_scale : lr;  // LambdaLR factor kept on the device (main_dnerf.py:134)
+    const float step_size = lr_eff / bc1;
     // Two independent float4 lanes per thread and iteration (more bytes in flight per thread); streaming loads / stores: every
     // element is touched exactly once per step.  An entry whose gradient AND both moments are exactly zero (a table row no sample
     // has reached yet: most of the coarse dense levels outside the occupied region) is left alone - its update is exactly zero
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256, 4) k_adam(float* __restrict__ p, float* _
             m[i] = mi;
             v[i] = vi;
             const float denom = sqrtf(vi) / bc2_sqrt + eps;
-            const float pi = p[i] - (lr / bc1) * (mi / denom);
+            const float pi = p[i] - step_size * (mi / denom);
             p[i] = pi;
             if (p16) p16[i] = __float2half_rn(pi);
         }
@@ -289,7 +290,7 @@ extern "C" int seald_adam_advance(int32_t* step_dev, const int32_t* found_inf, s
 
 static int adam_launch(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
                        const int32_t* step_dev, const float* loss_scale, const int32_t* found_inf, void* p16, int zero_grad,
-                       uint32_t max_blocks, seald_stream_t stream) {
+                       uint32_t max_blocks, seald_stream_t stream, const float* lr_scale = nullptr) {
     if (n == 0) return 0;
     if (!p || !g || !m || !v || (step == 0 && !step_dev)) return SEALD_E_BADARG;
     const uint32_t step_in = step;
@@ -301,8 +302,15 @@ static int adam_launch(float* p, float* g, float* m, float* v, uint64_t n, float
     // with step_dev: the step number of THIS update is *step_dev + step (step = 0: the counter was advanced already by
     // seald_adam_advance; step = 1: it counts completed updates and is advanced by seald_loss_scale_update afterwards)
     k_adam<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), step_dev,
-                                                  step_dev ? (int)step_in : 0, loss_scale, found_inf, (__half*)p16, zero_grad);
+                                                  step_dev ? (int)step_in : 0, loss_scale, found_inf, (__half*)p16, zero_grad, lr_scale);
     return launch_status();
+}
+
+extern "C" int seald_adam_step_lr(float* p, float* g, float* m, float* v, uint64_t n, float lr, const float* lr_scale_dev, float beta1,
+                                  float beta2, float eps, uint32_t step, const int32_t* step_dev, const float* loss_scale,
+                                  const int32_t* found_inf, void* p16, int zero_grad, uint32_t max_blocks, seald_stream_t stream) {
+    return adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, step, step_dev, loss_scale, found_inf, p16, zero_grad, max_blocks, stream,
+                       lr_scale_dev);
 }
 
 extern "C" int seald_adam_step(float* p, float* g, float* m, float* v, uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step,
