@@ -149,6 +149,17 @@ int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int3
                          const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
                          float* depth, float* image, const int32_t* n_alive_dev, const int32_t* n_step_dev,
                          seald_stream_t stream);
+
+/* composite_rays + the compaction `rays_alive = rays_alive[rays_alive >= 0]` + the loop bookkeeping of run_cuda
+ * (dnerf/renderer.py:349-376: n_alive, n_step = clamp(N / n_alive, 1, 8), step += n_step) in ONE launch for a device-resident render
+ * loop.  n_alive / n_step are launch bounds; the live values are state[0] / state[1].  Survivors are appended to next_alive (any
+ * order: a ray's result does not depend on its position) and the last CTA rewrites state[0..5] = {n_alive, n_step of the next round
+ * = clamp(budget / n_alive, 1, max_n_step), n_alive * n_step, steps marched, sample rows evaluated, non-empty rounds}; n_alive becomes 0
+ * once max_steps is reached.  counters2: two zero-initialised ints (left zero). */
+int seald_composite_rays_compact(uint32_t n_alive, uint32_t n_step, float T_thresh, const int32_t* rays_alive, float* rays_t,
+                                 const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                                 float* image, int32_t* next_alive, int32_t* state, int32_t* counters2, uint32_t budget, uint32_t max_steps,
+                                 uint32_t max_n_step, seald_stream_t stream);
 /* Device-side schedule of the render loop (dnerf/renderer.py:350-376).  state[8] int32 = {n_alive, n_step, n_alive*n_step,
  * steps done, samples evaluated so far, non-empty rounds so far, -, -}: adds the finished round's n_step to the step counter, takes the compacted count *n_alive_new (0 once
  * max_steps is reached) and derives the next round's n_step = clamp(N / n_alive, 1, max_n_step) (the reference uses 8). */
@@ -388,6 +399,12 @@ int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg*
 /* torch_ema.ExponentialMovingAverage.update: shadow -= (1 - decay) * (shadow - param) (ema_decay = 0.95, main_dnerf.py:136;
  * once per epoch, nerf/utils.py:909-910). */
 int seald_ema_update(float* shadow, const float* param, uint64_t n, float decay, seald_stream_t stream);
+
+
+/* Measurement kernel (csrc/umma_probe.cu): cycles one SM needs for `iters` back-to-back tcgen05.mma 128 x n_cols x 16 (fp16 -> fp32)
+ * with the operands placed as `mode` says (0 smem/smem no-swizzle, 1 smem/smem 128-byte swizzle, 2 A in tensor memory + B no-swizzle,
+ * 3 A in tensor memory + B swizzled; modes 2/3: n_cols <= 64), issued by `issuers` (1..4) warps at once, each into its own accumulator.  out_cycles[2 * sm] = issue time, [2 * sm + 1] = time until the last MMA completed. */
+int seald_umma_probe(int mode, int iters, int n_cols, int issuers, int64_t* out_cycles, seald_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Data-parallel exchange fused with the optimiser over NVLink peer memory (no counterpart in the reference, which is

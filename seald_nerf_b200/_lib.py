@@ -34,6 +34,7 @@ _SIGS = {
     "seald_composite_train_loss_fused": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_march_rays": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_composite_rays": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_composite_rays_compact": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
     "seald_render_schedule": [_vp, _vp, _u32, _u32, _u32, _vp],
     "seald_compact_alive": [_vp, _u32, _vp, _vp, _vp, _vp, _vp],
     "seald_seal_map_to_origin": [_vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -81,6 +82,7 @@ _SIGS = {
     "seald_adam_step_lr": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _vp, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _u32, _vp],
     "seald_mlp_tail": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "seald_ema_update": [_vp, _vp, C.c_uint64, _f32, _vp],
+    "seald_umma_probe": [_i32, _i32, _i32, _i32, _vp, _vp],
     "seald_loss_scale_update": [_vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp],
 }
 

@@ -1,19 +1,24 @@
 // field_umma.cu — the D-NeRF deformation MLP (76 -> 8 x Linear(128) + ReLU -> 3, dnerf/network.py:123-143) on the
 // Blackwell tensor cores: tcgen05.mma with fp32 accumulators in tensor memory.
 //
-// One persistent CTA per SM works on G = 2 or 4 128-sample tiles at a time ("groups" of 4 warps, one TMEM accumulator of
-// 128 columns each) so that the groups' epilogues overlap each other's MMAs; G = 4 (all 512 TMEM columns, 224 KiB of
-// shared memory) keeps the tensor pipe busy when there are enough tiles, G = 2 spreads small batches over more SMs:
+// One persistent CTA per SM works on G = 2 or 4 128-sample tiles at a time ("groups"); each group is an independent pipeline of
+// 4 epilogue warps + ONE ISSUER WARP, with its own TMEM accumulator (128 columns) and its own pair of mbarriers:
 //
-//   control warp (one elected thread): streams the layer weights global -> shared with cp.async.bulk (3 stages of 32 KiB,
-//                                 pre-packed in the canonical K-major layout of umma.cuh by k_pack_umma) and issues the
-//                                 tcgen05.mma's: per layer and group K/16 instructions of shape 128 x 128 x 16
-//                                 (last layer 128 x 16 x 16), tcgen05.commit -> mbarrier.
+//   issuer warp g (one elected thread): waits for the group's A tile and for the layer's weights, issues the tcgen05.mma's of that
+//                                 tile-layer (K/16 instructions of shape 128 x 128 x 16, last layer 128 x 16 x 16) and commits them to
+//                                 the group's mbarrier (and to the weight stage's "free" barrier).
+//   loader warp (one thread)    : streams the layer weights global -> shared with cp.async.bulk (3 stages of 32 KiB, pre-packed in
+//                                 the canonical K-major layout of umma.cuh), refilling a stage once every group's MMAs on it are done.
 //   4 warps per group           : thread t owns sample row t of its tile = TMEM lane t.  Layer 0 input: frequency
 //                                 encoding of xyz (63) and t (13) written straight into the A-operand tile.  After each
 //                                 layer: tcgen05.ld the fp32 row, ReLU, pack to fp16, store as the next layer's A tile
 //                                 (and, when training, into fwd_buf for the backward pass).  Last layer: dx, x' = x + dx,
 //                                 x01 = (x' + bound) / (2 bound).
+//
+// Why one issuer per group (profiles/r2_umma_probe.md): a single thread gets one 128 x 128 x 16 MMA accepted every ~165 cycles
+// whatever the operand placement (shared memory with or without swizzle, A in tensor memory), 2.5x the 64-cycle floor of the tensor
+// pipe; four threads issuing into four accumulators reach one MMA per 77 cycles.  Round 1's single control thread also served the
+// groups one after the other (~180 cycles per mbarrier wait with the pipe idle), which put the kernel at 36% of the tensor peak.
 //
 // Activations never leave the SM between layers; per 128-sample tile the tensor pipe does 8 layers x 4.2 MFLOP while the
 // only HBM traffic is 12 B in / 24 B out per sample (inference).  Measured bound (profiles/): shared-memory bandwidth —
@@ -33,7 +38,7 @@ constexpr uint32_t kTileBytes = kUW * kUW * 2;  // 32 KiB: one A tile / one weig
 
 template <int G>
 struct UmmaSmem {
-    static constexpr int THREADS = G * 128 + 32;  // G groups x 4 warps + 1 control warp
+    static constexpr int THREADS = G * 128 + (G + 1) * 32;  // G groups x 4 epilogue warps + G issuer warps + 1 loader warp
     static constexpr uint32_t TMEM_COLS = G * kUW;
     static constexpr size_t A_OFF = 0;
     static constexpr size_t W_OFF = G * kTileBytes;
@@ -79,14 +84,16 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                                                                       __half* __restrict__ in_buf, __half* __restrict__ fwd_buf) {
     extern __shared__ __align__(128) unsigned char smem[];
     using SM = UmmaSmem<G>;
-    constexpr int CTRL = G * 4;  // index of the control warp
+    constexpr int ISSUE0 = G * 4;      // warps ISSUE0 .. ISSUE0 + G - 1 issue the MMAs of group 0 .. G - 1
+    constexpr int LOADER = G * 4 + G;  // streams the weights
     unsigned char* s_a = smem + SM::A_OFF;
     unsigned char* s_w = smem + SM::W_OFF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
     uint64_t* bar_full = bars;            // [3] weights of a stage have landed
-    uint64_t* bar_aready = bars + 3;      // [G] the group's A tile is written
-    uint64_t* bar_mma = bars + 3 + G;     // [G] the group's MMAs of the current layer have completed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * G);
+    uint64_t* bar_wfree = bars + 3;       // [3] every group's MMAs on a stage have completed (count G)
+    uint64_t* bar_aready = bars + 6;      // [G] the group's A tile is written
+    uint64_t* bar_mma = bars + 6 + G;     // [G] the group's MMAs of the current layer have completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * G);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
@@ -96,29 +103,34 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
     const int n_items = my_pairs * n_layers;
 
     if (tid == 0) {
-        for (int i = 0; i < 3; i++) umma::mbar_init(bar_full + i, 1);
+        for (int i = 0; i < 3; i++) { umma::mbar_init(bar_full + i, 1); umma::mbar_init(bar_wfree + i, G); }
         for (int i = 0; i < G; i++) { umma::mbar_init(bar_aready + i, 128); umma::mbar_init(bar_mma + i, 1); }
         umma::mbar_fence_init();
     }
-    if (warp == CTRL) umma::tmem_alloc(tmem_slot, SM::TMEM_COLS);
+    if (warp == LOADER) umma::tmem_alloc(tmem_slot, SM::TMEM_COLS);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == CTRL) {
-        // =============================== control warp: weight streaming + MMA issue ===============================
-        if (lane == 0 && n_items > 0) {
-            const uint32_t a_addr = umma::smem_addr(s_a), w_addr = umma::smem_addr(s_w);
-            auto load_weights = [&](const int item) {
-                const int l = item % n_layers, s = item % kUStages;
+    if (warp == LOADER) {
+        // =============================== loader: weights of item i into stage i % 3, two items ahead of the MMAs ===============================
+        if (lane == 0) {
+            for (int i = 0; i < n_items; i++) {
+                const int l = i % n_layers, s = i % kUStages;
+                if (i >= kUStages) umma::mbar_wait(bar_wfree + s, ((i / kUStages) - 1) & 1);  // every group is done with item i - 3
                 const uint32_t bytes = umma_layer_bytes(l, n_layers);
                 umma::mbar_arrive_expect_tx(bar_full + s, bytes);
                 umma::bulk_load(s_w + (size_t)s * kTileBytes, reinterpret_cast<const unsigned char*>(packed) + umma_layer_offset(l, n_layers), bytes,
                                 bar_full + s);
-            };
-            load_weights(0);
-            if (n_items > 1) load_weights(1);
+            }
+        }
+    } else if (warp >= ISSUE0) {
+        // =============================== issuer of group g: its tile's MMAs, layer after layer ===============================
+        const int g = warp - ISSUE0;
+        if (lane == 0) {
+            const uint32_t a0 = umma::smem_addr(s_a) + g * kTileBytes, w_addr = umma::smem_addr(s_w);
+            const uint32_t d = tmem_base + g * kUW;
             for (int i = 0; i < n_items; i++) {
                 const int l = i % n_layers, s = i % kUStages;
                 const bool last = (l == n_layers - 1);
@@ -126,24 +138,17 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                 const uint32_t n_rows = last ? kUNLast : kUW;
                 const uint32_t idesc = umma::instr_desc_f16(128, n_rows);
                 const uint32_t w_lbo = n_rows * 16;
-#pragma unroll 1
-                for (int g = 0; g < G; g++) {
-                    umma::mbar_wait(bar_aready + g, i & 1);
-                    if (g == 0) umma::mbar_wait(bar_full + s, (i / kUStages) & 1);
-                    if (g == G - 1 && i + 2 < n_items) {
-                        // every MMA of item i-1 has completed (the last group waited for it before writing this A tile): its stage is free
-                        load_weights(i + 2);
-                    }
-                    umma::fence_after_sync();
-                    const uint32_t d = tmem_base + g * kUW;
-                    const uint32_t a0 = a_addr + g * kTileBytes, w0 = w_addr + s * kTileBytes;
-                    for (int k = 0; k < ksteps; k++) {
-                        const uint64_t da = umma::smem_desc(a0 + k * 2 * (kUW * 16), kUW * 16, 128);
-                        const uint64_t db = umma::smem_desc(w0 + k * 2 * w_lbo, w_lbo, 128);
-                        umma::mma_f16(d, da, db, idesc, k > 0 ? 1u : 0u);
-                    }
-                    umma::mma_commit(bar_mma + g);
+                umma::mbar_wait(bar_full + s, (i / kUStages) & 1);
+                umma::mbar_wait(bar_aready + g, i & 1);
+                umma::fence_after_sync();
+                const uint32_t w0 = w_addr + s * kTileBytes;
+                for (int k = 0; k < ksteps; k++) {
+                    const uint64_t da = umma::smem_desc(a0 + k * 2 * (kUW * 16), kUW * 16, 128);
+                    const uint64_t db = umma::smem_desc(w0 + k * 2 * w_lbo, w_lbo, 128);
+                    umma::mma_f16(d, da, db, idesc, k > 0 ? 1u : 0u);
                 }
+                umma::mma_commit(bar_mma + g);    // -> the group's epilogue warps
+                umma::mma_commit(bar_wfree + s);  // -> the loader (stage s may be refilled once all G groups arrived)
             }
         }
     } else {
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == CTRL) {
+    if (warp == LOADER) {
         __syncwarp();
         umma::tmem_dealloc(tmem_base, SM::TMEM_COLS);
     }
@@ -296,14 +301,15 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
                                                                                   __half* __restrict__ gout_buf) {
     extern __shared__ __align__(128) unsigned char smem[];
     using SM = UmmaSmem<G>;
-    constexpr int CTRL = G * 4;
+    constexpr int ISSUE0 = G * 4, LOADER = G * 4 + G;  // same warp roles as the forward kernel
     unsigned char* s_a = smem + SM::A_OFF;
     unsigned char* s_w = smem + SM::W_OFF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
     uint64_t* bar_full = bars;
-    uint64_t* bar_aready = bars + 3;
-    uint64_t* bar_mma = bars + 3 + G;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * G);
+    uint64_t* bar_wfree = bars + 3;
+    uint64_t* bar_aready = bars + 6;
+    uint64_t* bar_mma = bars + 6 + G;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * G);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
@@ -314,47 +320,47 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
     const int n_items = my_units * n_steps;
 
     if (tid == 0) {
-        for (int i = 0; i < 3; i++) umma::mbar_init(bar_full + i, 1);
+        for (int i = 0; i < 3; i++) { umma::mbar_init(bar_full + i, 1); umma::mbar_init(bar_wfree + i, G); }
         for (int i = 0; i < G; i++) { umma::mbar_init(bar_aready + i, 128); umma::mbar_init(bar_mma + i, 1); }
         umma::mbar_fence_init();
     }
-    if (warp == CTRL) umma::tmem_alloc(tmem_slot, SM::TMEM_COLS);
+    if (warp == LOADER) umma::tmem_alloc(tmem_slot, SM::TMEM_COLS);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == CTRL) {
-        if (lane == 0 && n_items > 0) {
-            const uint32_t a_addr = umma::smem_addr(s_a), w_addr = umma::smem_addr(s_w);
-            auto load_weights = [&](const int item) {
-                const int l = n_layers - 1 - (item % n_steps), st = item % kUStages;
+    if (warp == LOADER) {
+        if (lane == 0) {
+            for (int i = 0; i < n_items; i++) {
+                const int l = n_layers - 1 - (i % n_steps), st = i % kUStages;
+                if (i >= kUStages) umma::mbar_wait(bar_wfree + st, ((i / kUStages) - 1) & 1);
                 const uint32_t bytes = umma_layerT_bytes(l, n_layers);
                 umma::mbar_arrive_expect_tx(bar_full + st, bytes);
                 umma::bulk_load(s_w + (size_t)st * kTileBytes, reinterpret_cast<const unsigned char*>(packedT) + umma_layerT_offset(l, n_layers), bytes,
                                 bar_full + st);
-            };
-            load_weights(0);
-            if (n_items > 1) load_weights(1);
+            }
+        }
+    } else if (warp >= ISSUE0) {
+        const int g = warp - ISSUE0;
+        if (lane == 0) {
+            const uint32_t a0 = umma::smem_addr(s_a) + g * kTileBytes, w_addr = umma::smem_addr(s_w);
+            const uint32_t d = tmem_base + g * kUW;
             const uint32_t idesc = umma::instr_desc_f16(128, kUW);
             for (int i = 0; i < n_items; i++) {
                 const int st = i % kUStages;
                 const int ksteps = ((i % n_steps) == 0 ? kUNLast : kUW) / 16;
-#pragma unroll 1
-                for (int g = 0; g < G; g++) {
-                    umma::mbar_wait(bar_aready + g, i & 1);
-                    if (g == 0) umma::mbar_wait(bar_full + st, (i / kUStages) & 1);
-                    if (g == G - 1 && i + 2 < n_items) load_weights(i + 2);
-                    umma::fence_after_sync();
-                    const uint32_t d = tmem_base + g * kUW;
-                    const uint32_t a0 = a_addr + g * kTileBytes, w0 = w_addr + st * kTileBytes;
-                    for (int k = 0; k < ksteps; k++) {
-                        const uint64_t da = umma::smem_desc(a0 + k * 2 * (kUW * 16), kUW * 16, 128);
-                        const uint64_t db = umma::smem_desc(w0 + k * 2 * (kUW * 16), kUW * 16, 128);
-                        umma::mma_f16(d, da, db, idesc, k > 0 ? 1u : 0u);
-                    }
-                    umma::mma_commit(bar_mma + g);
+                umma::mbar_wait(bar_full + st, (i / kUStages) & 1);
+                umma::mbar_wait(bar_aready + g, i & 1);
+                umma::fence_after_sync();
+                const uint32_t w0 = w_addr + st * kTileBytes;
+                for (int k = 0; k < ksteps; k++) {
+                    const uint64_t da = umma::smem_desc(a0 + k * 2 * (kUW * 16), kUW * 16, 128);
+                    const uint64_t db = umma::smem_desc(w0 + k * 2 * (kUW * 16), kUW * 16, 128);
+                    umma::mma_f16(d, da, db, idesc, k > 0 ? 1u : 0u);
                 }
+                umma::mma_commit(bar_mma + g);
+                umma::mma_commit(bar_wfree + st);
             }
         }
     } else {
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == CTRL) {
+    if (warp == LOADER) {
         __syncwarp();
         umma::tmem_dealloc(tmem_base, SM::TMEM_COLS);
     }

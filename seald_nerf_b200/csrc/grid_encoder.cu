@@ -6,10 +6,10 @@
 //   * forward : one thread per point, looping over levels, all 2^D corner gathers of a level group issued
 //               before use (memory-level parallelism), row-vector loads (half2 / uint2 / uint4), fp32
 //               accumulation, output written straight into [B, L*C] with 16-byte stores (no [L,B,C] + permute).
-//   * backward: grid = (point chunks, levels).  Levels whose table slice fits in shared memory are
-//               accumulated in a CTA-private fp32 copy (shared atomics) and flushed once; the others use
-//               warp-aggregated (match.any) vector atomics.  Input gradients are recomputed from the table
-//               with fp32 accumulation (or taken from dy_dx when the caller kept it).
+//   * backward: grid = (point chunks, levels), level fastest.  Every corner contribution is a fire-and-forget vector reduction
+//               (red.global.add.v2/.v4.f32) into the fp32 gradient table; on the coarse levels the lanes of a warp that hit the
+//               same row are summed first (match.any) so contended rows see one reduction per warp.  Input gradients are
+//               recomputed from the table with fp32 accumulation (or taken from dy_dx when the caller kept it).
 #include <cstdlib>
 #include <type_traits>
 

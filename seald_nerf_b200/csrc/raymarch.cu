@@ -991,129 +991,208 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_train_loss_fused(
 }
 
 // ------------------------------------------------------------------------------------------------
-// inference march / composite
+// inference round (run_cuda eval branch, dnerf/renderer.py:349-376): march n_step samples per live ray, [field], composite.
+//
+// The contract of the sample buffers is the reference's (row n * n_step + s belongs to the n-th entry of the alive list; unused
+// slots are zero, delta == 0 being the "ray ended" marker, raymarching.cu:850), and so is every number a ray produces; the kernels
+// are organised for the memory system instead of one strided 12-byte store / load per thread and sample:
+//
+//   k_march_round      a CTA of 128 rays walks the bitfield (thread per ray: after the first round the live rays sit inside the
+//                      occupied region and find their n_step samples within a few probes) and collects the samples in shared memory;
+//                      the CTA's slice of xyzs / dirs / deltas is contiguous in the output, so it is written with coalesced 128-bit
+//                      stores, terminator slots included (no zero-fill pass over the buffers).  Live count and n_step are read on
+//                      the device, so the host never synchronises inside the loop.
+//   k_composite_round  the CTA's slice of sigmas / rgbs / deltas is staged with coalesced loads, each thread then runs the
+//                      front-to-back recurrence of its ray from shared memory.  COMPACT: the survivors are appended to the next
+//                      round's alive list (warp-aggregated, one atomic per warp) and the last CTA to finish derives the next round's
+//                      schedule (n_alive, n_step = clamp(N / n_alive, 1, 8), steps marched) — composite + boolean-mask compaction +
+//                      host-side bookkeeping of the reference in one launch.  Otherwise (drop-in op): dead rays are marked -1 in
+//                      place, as composite_rays does.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kRoundThreads = 128;
+
 template <bool SEAL>
-__global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
-                             const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float bound, const float dt_gamma,
-                             const uint32_t max_steps, const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid,
-                             const float* __restrict__ nears, const float* __restrict__ fars, float* xyzs, float* dirs, float* deltas,
-                             const float* __restrict__ noises, const int* __restrict__ n_alive_dev, const int* __restrict__ n_step_dev,
-                             const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask, const float* __restrict__ occ) {
+__global__ void __launch_bounds__(kRoundThreads) k_march_round(
+    uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+    const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H,
+    const uint8_t* __restrict__ grid, const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
+    float* __restrict__ deltas, const float* __restrict__ noises, const int* __restrict__ n_alive_dev, const int* __restrict__ n_step_dev,
+    const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask, const float* __restrict__ occ, const uint32_t smem_rows) {
+    extern __shared__ __align__(16) float s_round[];
     if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
     if (n_step_dev) n_step = (uint32_t)max(*n_step_dev, 0);
-    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
-    if (n >= n_alive) return;
-
-    const int index = rays_alive[n];
-    const float noise = noises ? noises[n] : 0.0f;
-
-    rays_o += (size_t)index * 3;
-    rays_d += (size_t)index * 3;
-    xyzs += (size_t)n * n_step * 3;
-    dirs += (size_t)n * n_step * 3;
-    deltas += (size_t)n * n_step * 2;
-    if (SEAL) seal_mask += (size_t)n * n_step;
-
-    Ray r;
-    r.ox = rays_o[0]; r.oy = rays_o[1]; r.oz = rays_o[2];
-    r.dx = rays_d[0]; r.dy = rays_d[1]; r.dz = rays_d[2];
-    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
-    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
-
-    float t = rays_t[index];
-    float far = fars[index];
-
-    uint32_t step = 0;
-    t += clampf(t * dt_gamma, mc.dt_min, mc.dt_max) * noise;
-    float last_t = t;
-    if (occ && !clip_to_occupied(r, occ, t, far)) far = t;  // cannot meet an occupied cell any more: no samples, ray ends
-    Probe p;
-    while (t < far && step < n_step) {
-        if (probe_grid(r, mc, grid, t, p)) {
-            if (SEAL) {
+    const uint32_t first = blockIdx.x * blockDim.x;  // first alive-list entry of this CTA
+    if (first >= n_alive || n_step == 0) return;
+    const uint32_t n_rays = min((uint32_t)blockDim.x, n_alive - first);
+    const uint32_t rows = n_rays * n_step;            // sample rows this CTA owns: [first * n_step, first * n_step + rows)
+    const bool staged = rows <= smem_rows;
+    float* s_xyz = s_round;                           // [rows][3]
+    float* s_dir = s_round + (size_t)smem_rows * 3;   // [rows][3]
+    float* s_del = s_round + (size_t)smem_rows * 6;   // [rows][2]
+    if (staged) {
+        for (uint32_t i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+            if (i < rows * 3) s_xyz[i] = 0.f;
+            else if (i < rows * 6) s_dir[i - rows * 3] = 0.f;
+            else s_del[i - rows * 6] = 0.f;
+        }
+        __syncthreads();
+    }
+    const uint32_t n = first + threadIdx.x;
+    if (threadIdx.x < n_rays) {
+        const int index = rays_alive[n];
+        const float noise = noises ? noises[n] : 0.0f;
+        Ray r;
+        const float* o = rays_o + (size_t)index * 3;
+        const float* d = rays_d + (size_t)index * 3;
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+        r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+        const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+        float t = rays_t[index];
+        float far = fars[index];
+        t += clampf(t * dt_gamma, mc.dt_min, mc.dt_max) * noise;
+        float last_t = t;
+        if (occ && !clip_to_occupied(r, occ, t, far)) far = t;  // cannot meet an occupied cell any more: no samples, the ray ends
+        const uint32_t row0 = staged ? threadIdx.x * n_step : n * n_step;
+        float* oxyz = staged ? s_xyz : xyzs;
+        float* odir = staged ? s_dir : dirs;
+        float* odel = staged ? s_del : deltas;
+        uint32_t step = 0;
+        Probe p;
+        while (t < far && step < n_step) {
+            if (probe_grid(r, mc, grid, t, p)) {
                 float sx = p.x, sy = p.y, sz = p.z, sdx = r.dx, sdy = r.dy, sdz = r.dz;
-                seal_mask[step] = seal_map_sample(mp, sx, sy, sz, sdx, sdy, sdz) ? 1 : 0;
-                xyzs[0] = sx; xyzs[1] = sy; xyzs[2] = sz;
-                dirs[0] = sdx; dirs[1] = sdy; dirs[2] = sdz;
+                if (SEAL) seal_mask[(size_t)n * n_step + step] = seal_map_sample(mp, sx, sy, sz, sdx, sdy, sdz) ? 1 : 0;
+                const size_t row = row0 + step;
+                oxyz[row * 3] = sx; oxyz[row * 3 + 1] = sy; oxyz[row * 3 + 2] = sz;
+                odir[row * 3] = sdx; odir[row * 3 + 1] = sdy; odir[row * 3 + 2] = sdz;
+                t += p.dt;
+                odel[row * 2] = p.dt;
+                odel[row * 2 + 1] = t - last_t;
+                last_t = t;
+                step++;
             } else {
-                xyzs[0] = p.x; xyzs[1] = p.y; xyzs[2] = p.z;
-                dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+                t = skip_voxel(r, mc, p, t);
             }
-            t += p.dt;
-            deltas[0] = p.dt;
-            deltas[1] = t - last_t;
-            last_t = t;
-            xyzs += 3; dirs += 3; deltas += 2;
-            step++;
-        } else {
-            t = skip_voxel(r, mc, p, t);
+        }
+        for (; step < n_step; step++) {  // terminator slots
+            if (SEAL) seal_mask[(size_t)n * n_step + step] = 0;
+            if (!staged) {
+                const size_t row = row0 + step;
+                oxyz[row * 3] = 0.f; oxyz[row * 3 + 1] = 0.f; oxyz[row * 3 + 2] = 0.f;
+                odir[row * 3] = 0.f; odir[row * 3 + 1] = 0.f; odir[row * 3 + 2] = 0.f;
+                odel[row * 2] = 0.f; odel[row * 2 + 1] = 0.f;
+            }
         }
     }
-    // unused slots of this ray: delta == 0 is the "terminated" marker composite_rays looks for (raymarching.cu:850); the
-    // reference relies on the caller's torch.zeros for it, writing it here lets a render loop reuse its buffers
-    for (; step < n_step; step++) {
-        xyzs[0] = 0.f; xyzs[1] = 0.f; xyzs[2] = 0.f;
-        dirs[0] = 0.f; dirs[1] = 0.f; dirs[2] = 0.f;
-        deltas[0] = 0.f; deltas[1] = 0.f;
-        if (SEAL) seal_mask[step] = 0;
-        xyzs += 3; dirs += 3; deltas += 2;
-    }
+    if (!staged) return;
+    __syncthreads();
+    // coalesced copy-out: the CTA's rows are contiguous in each output array (row base is a multiple of 4 floats when n_step * 128 is)
+    const size_t base = (size_t)first * n_step;
+    auto copy_out = [&](const float* __restrict__ src, float* __restrict__ dst, const uint32_t count) {
+        if ((((uintptr_t)dst) & 15) == 0 && (count & 3) == 0) {
+            for (uint32_t i = threadIdx.x; i < count / 4; i += blockDim.x) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        } else {
+            for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+        }
+    };
+    copy_out(s_xyz, xyzs + base * 3, rows * 3);
+    copy_out(s_dir, dirs + base * 3, rows * 3);
+    copy_out(s_del, deltas + base * 2, rows * 2);
 }
 
-__global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, const float T_thresh, int* rays_alive, float* rays_t,
-                                 const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
-                                 float* weights_sum, float* depth, float* image, const int* __restrict__ n_alive_dev,
-                                 const int* __restrict__ n_step_dev) {
+template <bool COMPACT>
+__global__ void __launch_bounds__(kRoundThreads) k_composite_round(
+    uint32_t n_alive, uint32_t n_step, const float T_thresh, int* __restrict__ rays_alive, float* __restrict__ rays_t,
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas, float* __restrict__ weights_sum,
+    float* __restrict__ depth, float* __restrict__ image, const int* __restrict__ n_alive_dev, const int* __restrict__ n_step_dev,
+    int* __restrict__ next_alive, int* __restrict__ state, int* __restrict__ counters, const uint32_t budget, const uint32_t max_steps,
+    const uint32_t max_n_step, const uint32_t smem_rows) {
+    extern __shared__ __align__(16) float s_round[];
     if (n_alive_dev) n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
     if (n_step_dev) n_step = (uint32_t)max(*n_step_dev, 0);
-    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
-    if (n >= n_alive) return;
-
-    const int index = rays_alive[n];
-    sigmas += (size_t)n * n_step;
-    rgbs += (size_t)n * n_step * 3;
-    deltas += (size_t)n * n_step * 2;
-    rays_t += index;
-    weights_sum += index;
-    depth += index;
-    image += (size_t)index * 3;
-
-    float t = rays_t[0];
-    float weight_sum = weights_sum[0];
-    float d = depth[0];
-    float r = image[0];
-    float g = image[1];
-    float b = image[2];
-
-    uint32_t step = 0;
-    while (step < n_step) {
-        if (deltas[0] == 0) break;
-        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
-        const float T = 1 - weight_sum;
-        const float weight = alpha * T;
-        weight_sum += weight;
-        t += deltas[1];
-        d += weight * t;
-        r += weight * rgbs[0];
-        g += weight * rgbs[1];
-        b += weight * rgbs[2];
-        if (T < T_thresh) break;
-        sigmas++;
-        rgbs += 3;
-        deltas += 2;
-        step++;
+    const uint32_t first = blockIdx.x * blockDim.x;
+    const bool cta_live = first < n_alive && n_step > 0;
+    bool survive = false;
+    int index = -1;
+    if (cta_live) {
+        const uint32_t n_rays = min((uint32_t)blockDim.x, n_alive - first);
+        const uint32_t rows = n_rays * n_step;
+        const bool staged = rows <= smem_rows;
+        float* s_sig = s_round;                           // [rows]
+        float* s_rgb = s_round + smem_rows;               // [rows][3]
+        float* s_del = s_round + (size_t)smem_rows * 4;   // [rows][2]
+        const size_t base = (size_t)first * n_step;
+        if (staged) {
+            for (uint32_t i = threadIdx.x; i < rows; i += blockDim.x) s_sig[i] = sigmas[base + i];
+            for (uint32_t i = threadIdx.x; i < rows * 3; i += blockDim.x) s_rgb[i] = rgbs[base * 3 + i];
+            for (uint32_t i = threadIdx.x; i < rows * 2; i += blockDim.x) s_del[i] = deltas[base * 2 + i];
+            __syncthreads();
+        }
+        if (threadIdx.x < n_rays) {
+            const uint32_t n = first + threadIdx.x;
+            index = rays_alive[n];
+            const float* sg = staged ? s_sig + threadIdx.x * n_step : sigmas + (size_t)n * n_step;
+            const float* cl = staged ? s_rgb + (size_t)threadIdx.x * n_step * 3 : rgbs + (size_t)n * n_step * 3;
+            const float* dl = staged ? s_del + (size_t)threadIdx.x * n_step * 2 : deltas + (size_t)n * n_step * 2;
+            float t = rays_t[index];
+            float ws = weights_sum[index], d = depth[index];
+            float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
+            uint32_t step = 0;
+            for (; step < n_step; step++) {
+                const float d0 = dl[step * 2];
+                if (d0 == 0) break;                         // terminator slot: the march found no further sample
+                const float alpha = 1.0f - __expf(-sg[step] * d0);
+                const float T = 1 - ws;
+                const float weight = alpha * T;
+                ws += weight;
+                t += dl[step * 2 + 1];
+                d += weight * t;
+                r += weight * cl[step * 3];
+                g += weight * cl[step * 3 + 1];
+                b += weight * cl[step * 3 + 2];
+                if (T < T_thresh) break;                    // (tested on the transmittance BEFORE this sample, raymarching.cu:880-886)
+            }
+            survive = step == n_step;
+            if (survive) rays_t[index] = t;
+            else if (!COMPACT) rays_alive[n] = -1;
+            weights_sum[index] = ws;
+            depth[index] = d;
+            image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+        }
     }
-    if (step < n_step) {
-        rays_alive[n] = -1;
-    } else {
-        rays_t[0] = t;
+    if (!COMPACT) return;
+    // ---- survivors -> next alive list (one atomic per warp), then the last CTA computes the next round's schedule
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, survive);
+    if (bal) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(bal) - 1)) base = (uint32_t)atomicAdd(counters, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        if (survive) next_alive[base + __popc(bal & ((1u << lane) - 1u))] = index;
     }
-    weights_sum[0] = weight_sum;
-    depth[0] = d;
-    image[0] = r;
-    image[1] = g;
-    image[2] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(counters + 1, 1) + 1;
+        if (done == (int)gridDim.x) {
+            __threadfence();
+            int n_new = atomicAdd(counters, 0);
+            const int step = state[3] + state[1];
+            state[4] += state[2];
+            state[5] += (state[0] > 0) ? 1 : 0;
+            if ((uint32_t)step >= max_steps) n_new = 0;
+            int ns = 1;
+            if (n_new > 0) ns = max(min((int)(budget / (uint32_t)n_new), (int)max_n_step), 1);
+            state[0] = n_new;
+            state[1] = ns;
+            state[2] = n_new * ns;
+            state[3] = step;
+            counters[0] = 0;
+            counters[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1340,18 +1419,34 @@ extern "C" int seald_composite_rays_train_backward(const float* grad_weights_sum
     return launch_status();
 }
 
+static uint32_t round_smem_rows(uint32_t n_step_max) {
+    // rows of shared-memory staging per CTA: 128 rays x n_step (32 B per row), capped at 64 KiB; beyond that the kernels fall back to
+    // direct (strided) access
+    const uint32_t rows = kRoundThreads * (n_step_max ? n_step_max : 1u);
+    return rows <= 2048u ? rows : 0u;
+}
+
 static int march_impl(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                       const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* bitfield,
                       const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
-                      const int32_t* n_alive_dev, const int32_t* n_step_dev, const seald_seal_mapper* mapper, uint8_t* mask,
-                      const float* occ, seald_stream_t stream) {
-    if (n_alive == 0 || (n_step == 0 && !n_step_dev)) return 0;
+                      const int32_t* n_alive_dev, const int32_t* n_step_dev, const seald_seal_mapper* mapper, uint8_t* mask, const float* occ,
+                      seald_stream_t stream) {
+    (void)nears;
+    if (n_alive == 0 || n_step == 0) return 0;
     if (!rays_alive || !rays_t || !rays_o || !rays_d || !bitfield || !fars || !xyzs || !dirs || !deltas) return SEALD_E_BADARG;
+    if (C == 0 || H == 0 || max_steps == 0) return SEALD_E_BADARG;
     static const seald_seal_mapper no_mapper = {};
-    auto k = mapper ? k_march_rays<true> : k_march_rays<false>;
-    k<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
-                                                           bitfield, nears, fars, xyzs, dirs, deltas, noises, n_alive_dev, n_step_dev,
-                                                           mapper ? *mapper : no_mapper, mask, occ);
+    const seald_seal_mapper& mp = mapper ? *mapper : no_mapper;
+    const uint32_t smem_rows = round_smem_rows(n_step);   // n_step is the launch's upper bound when the live value is on the device
+    const size_t smem = (size_t)smem_rows * 8 * sizeof(float);
+    auto k = mapper ? k_march_round<true> : k_march_round<false>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    k<<<div_up(n_alive, kRoundThreads), kRoundThreads, smem, to_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound,
+                                                                                 dt_gamma, max_steps, C, H, bitfield, fars, xyzs, dirs, deltas,
+                                                                                 noises, n_alive_dev, n_step_dev, mp, mask, occ, smem_rows);
     return launch_status();
 }
 
@@ -1377,10 +1472,38 @@ extern "C" int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const in
 extern "C" int seald_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t, const float* sigmas,
                                     const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
                                     const int32_t* n_alive_dev, const int32_t* n_step_dev, seald_stream_t stream) {
-    if (n_alive == 0) return 0;
+    if (n_alive == 0 || n_step == 0) return 0;
     if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return SEALD_E_BADARG;
-    k_composite_rays<<<div_up(n_alive, 128u), 128, 0, to_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
-                                                                           weights_sum, depth, image, n_alive_dev, n_step_dev);
+    const uint32_t smem_rows = round_smem_rows(n_step);
+    const size_t smem = (size_t)smem_rows * 6 * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_composite_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    k_composite_round<false><<<div_up(n_alive, kRoundThreads), kRoundThreads, smem, to_stream(stream)>>>(
+        n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, n_alive_dev, n_step_dev, nullptr, nullptr,
+        nullptr, 0, 0, 0, smem_rows);
+    return launch_status();
+}
+
+extern "C" int seald_composite_rays_compact(uint32_t n_alive, uint32_t n_step, float T_thresh, const int32_t* rays_alive, float* rays_t,
+                                            const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                                            float* image, int32_t* next_alive, int32_t* state, int32_t* counters2, uint32_t budget,
+                                            uint32_t max_steps, uint32_t max_n_step, seald_stream_t stream) {
+    if (n_alive == 0 || n_step == 0) return 0;
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image || !next_alive || !state || !counters2)
+        return SEALD_E_BADARG;
+    if (budget == 0 || max_n_step == 0 || rays_alive == next_alive) return SEALD_E_BADARG;
+    const uint32_t smem_rows = round_smem_rows(n_step);
+    const size_t smem = (size_t)smem_rows * 6 * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_composite_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    // n_alive / n_step are launch bounds; the live values are state[0] / state[1]
+    k_composite_round<true><<<div_up(n_alive, kRoundThreads), kRoundThreads, smem, to_stream(stream)>>>(
+        n_alive, n_step, T_thresh, const_cast<int32_t*>(rays_alive), rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, state, state + 1,
+        next_alive, state, counters2, budget, max_steps, max_n_step, smem_rows);
     return launch_status();
 }
 

@@ -61,6 +61,7 @@ class FusedRenderer:
         self.alive = [torch.empty(N, **i32), torch.empty(N, **i32)]
         # device-side loop state {n_alive, n_step, n_alive * n_step, steps done} and the compaction's output count
         self.state = torch.zeros(8, **i32)  # + [4] live samples evaluated so far, [5] non-empty rounds so far
+        self.counters = torch.zeros(2, **i32)  # survivors appended so far / CTAs finished (seald_composite_rays_compact; left zero)
         self.n_new = torch.zeros(1, **i32)
         self.scratch = torch.empty((N + 1023) // 1024 + 1, **i32)
         self.xyzs = torch.zeros(cap, 3, **f32)
@@ -102,12 +103,12 @@ class FusedRenderer:
         noises = self.noises if (first and opts["perturb"]) else None
         launches = 0
         if mapper is not None and mapper.fusable:
-            _lib.call("seald_march_rays_seal", n_bound, 1, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
+            _lib.call("seald_march_rays_seal", n_bound, self.max_n_step, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
                       opts["dt_gamma"], opts["max_steps"], int(m.cascade), int(m.grid_size), ptr(self.bitfield), ptr(self.nears),
                       ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), ptr(n_alive_dev), ptr(n_step_dev),
                       C.byref(desc), ptr(self.mask), ptr(self.occ), st)
         else:
-            _lib.call("seald_march_rays", n_bound, 1, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
+            _lib.call("seald_march_rays", n_bound, self.max_n_step, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
                       opts["dt_gamma"], opts["max_steps"], int(m.cascade), int(m.grid_size), ptr(self.bitfield), ptr(self.nears),
                       ptr(self.fars), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), ptr(n_alive_dev), ptr(n_step_dev),
                       ptr(self.occ), st)
@@ -120,12 +121,12 @@ class FusedRenderer:
             _lib.call("seald_seal_map_color", C.byref(mapper._dev_cache["color"]), ptr(self.xyzs), ptr(self.mask), ptr(self.ws.rgb), self.cap,
                       ptr(m_dev), ptr(mapper._dev_cache["scratch_f"]), st)
             launches += 4
-        _lib.call("seald_composite_rays", n_bound, 1, opts["T_thresh"], ptr(alive), ptr(self.rays_t), ptr(self.ws.sigma), ptr(self.ws.rgb),
-                  ptr(self.deltas), ptr(self.weights_sum), ptr(self.depth), ptr(self.image), ptr(n_alive_dev), ptr(n_step_dev), st)
-        _lib.call("seald_compact_alive", ptr(alive), n_bound, ptr(n_alive_dev), ptr(nxt), ptr(self.n_new), ptr(self.scratch), st)
-        _lib.call("seald_render_schedule", ptr(self.state), ptr(self.n_new), max(N, self.slots), opts["max_steps"],
-                  self.max_n_step, st)
-        return launches + 9
+        # composite + survivor compaction + next round's schedule in one launch (the reference: composite_rays, a boolean-mask gather
+        # with a host synchronisation, and Python bookkeeping)
+        _lib.call("seald_composite_rays_compact", n_bound, self.max_n_step, opts["T_thresh"], ptr(alive), ptr(self.rays_t), ptr(self.ws.sigma),
+                  ptr(self.ws.rgb), ptr(self.deltas), ptr(self.weights_sum), ptr(self.depth), ptr(self.image), ptr(nxt), ptr(self.state),
+                  ptr(self.counters), max(N, self.slots), opts["max_steps"], self.max_n_step, st)
+        return launches + 5
 
     def _double_round_graph(self, N, opts, mapper, desc):
         """Rounds 2k+1 and 2k+2 (alive buffers 1 -> 0 -> 1) as one CUDA graph; cached per ray count / options / mapper."""

@@ -34,7 +34,7 @@ class FusedTrainer:
     def __init__(self, model, num_rays=4096, max_samples=None, lr=1e-2, lr_net=None, betas=(0.9, 0.99), eps=1e-15, dt_gamma=0.0,
                  max_steps=1024, T_thresh=1e-4, perturb=True, init_loss_scale=65536.0, growth_interval=2000, train_deform=True,
                  use_graph=True, world_size=1, process_group=None, device=None, fuse_composite=True, shard_optimizer=True, dp_mode=None,
-                 defer_table_update=True):
+                 defer_table_update=True, lr_decay_iters=None, ema_decay=None):
         self.model = model
         self.device = device or model.encoder.embeddings.device
         if self.device.type != "cuda":
@@ -49,6 +49,10 @@ class FusedTrainer:
         self.dt_gamma, self.max_steps, self.T_thresh, self.perturb = float(dt_gamma), int(max_steps), float(T_thresh), bool(perturb)
         self.train_deform = bool(train_deform)
         self.growth_interval = int(growth_interval)
+        # LambdaLR(0.1 ** min(iter / iters, 1)) of main_dnerf.py:134, stepped every iteration: the factor lives on the device
+        # (self.lr_scale), is advanced by the optimiser-tail kernel and read by both Adam passes, so the captured step follows it
+        self.lr_decay_iters = int(lr_decay_iters) if lr_decay_iters else 0
+        self.ema_decay = float(ema_decay) if ema_decay else None
         self.world_size, self.pg = int(world_size), process_group
         self.use_graph = bool(use_graph)
         self.fuse_composite = bool(fuse_composite)
@@ -153,6 +157,16 @@ class FusedTrainer:
         self.fork_scatter = os.environ.get("SEALD_FORK", "0") != "0"
         self.hw = F.HalfWeights(self.cfg, dev)
         self.hw.refresh(self.weight_views)
+        self.lr_scale = torch.ones(1, **f32)
+        self.sched_step = torch.zeros(1, **i32)
+        self._tail_sync = torch.zeros(2, **i32)
+        self._tail_segs = self._build_tail_segs(sizes)
+        # the fused MLP tail (csrc/optim_tail.cu): single GPU; the data-parallel modes keep their exchange-fused optimiser kernels
+        self.fused_tail = self.dp_mode == "single" and os.environ.get("SEALD_FUSED_TAIL", "1") != "0"
+        # torch_ema.ExponentialMovingAverage over every parameter (ema_decay = 0.95 in main_dnerf.py:136): a shadow of the flat buffer
+        self.ema_shadow = self.params.clone() if self.ema_decay else None
+        self.ema_num_updates = 0
+        self._ema_backup = None
 
         # ---- per-step buffers ----------------------------------------------------------------------------------
         N, M = self.N, self.M
@@ -206,6 +220,75 @@ class FusedTrainer:
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------------------------
+    def _build_tail_segs(self, sizes):
+        """seald_tail_seg table of the MLP weights in flat-buffer order: where the fp16 copies of every matrix live (row-padded staging
+        copy; K-major tcgen05 operand tile and its transpose for the deformation layers — the layouts of csrc/field_umma.cu)."""
+        cfg, hw = self.cfg, self.hw
+        nd = cfg.n_deform
+
+        def fwd_bytes(l):
+            return F.DEFORM_K0 * 128 * 2 if l == 0 else (128 * 16 * 2 if l == nd - 1 else 128 * 128 * 2)
+
+        def bwd_bytes(l):
+            return 16 * 128 * 2 if l == nd - 1 else 128 * 128 * 2
+
+        segs, first = [], 0
+        for k, ((rows, cols, ld), n) in enumerate(zip(hw.shapes, sizes)):
+            assert rows * cols == n
+            packed = packedT = None
+            n_pad = 0
+            if k < nd:
+                packed = hw.packed_deform.data_ptr() + sum(fwd_bytes(i) for i in range(k))
+                n_pad = 16 if k == nd - 1 else 128
+                if k >= 1:
+                    packedT = hw.packed_deform_T.data_ptr() + sum(bwd_bytes(i) for i in range(1, k))
+            segs.append(_lib.TailSeg(first, rows, cols, ld, hw.views[k].data_ptr(), packed, n_pad, packedT))
+            first += n
+        return (_lib.TailSeg * len(segs))(*segs)
+
+    # ---- exponential moving average of the parameters (torch_ema semantics; the reference updates it once per epoch) -----------
+    def ema_update(self):
+        """ExponentialMovingAverage.update(): decay = min(ema_decay, (1 + n) / (10 + n)); shadow -= (1 - decay) * (shadow - param)."""
+        if self.ema_shadow is None:
+            raise RuntimeError("FusedTrainer was built without ema_decay")
+        self.sync_params()
+        self.ema_num_updates += 1
+        decay = min(self.ema_decay, (1 + self.ema_num_updates) / (10 + self.ema_num_updates))
+        _lib.call("seald_ema_update", ptr(self.ema_shadow), ptr(self.params), self.n_params, float(decay), _lib.stream())
+
+    def _restage(self):
+        self.table16.copy_(self.model.encoder.embeddings.data)
+        if self.dp_mode == "sharded":
+            self.shard16.copy_(self.table16_pad[self.rank * self.shard_len:(self.rank + 1) * self.shard_len])
+        self.hw.refresh(self.weight_views)
+
+    def ema_copy_to(self):
+        """ema.store(); ema.copy_to(): evaluate / export with the averaged parameters (nerf/utils.py:939-941, 1071-1073)."""
+        self.sync_params()
+        self._ema_backup = self.params.clone()
+        self.params.copy_(self.ema_shadow)
+        self._restage()
+
+    def ema_restore(self):
+        """ema.restore(): back to the raw parameters."""
+        if self._ema_backup is None:
+            return
+        self.params.copy_(self._ema_backup)
+        self._ema_backup = None
+        self._restage()
+
+    def set_lr_scale(self, factor, sched_step=None):
+        """Overwrite the learning-rate factor (e.g. when resuming: LambdaLR's last_epoch)."""
+        self.lr_scale.fill_(float(factor))
+        if sched_step is not None:
+            self.sched_step.fill_(int(sched_step))
+
+    @property
+    def current_lr(self):
+        f = float(self.lr_scale)
+        return self.lr * f, self.lr_net * f
+
+    # ------------------------------------------------------------------------------------------------------------
     def refresh_occupancy(self):
         """Recompute the per-frame occupied-cell boxes; call after the model's density_bitfield changed (update_extra_state)."""
         from . import raymarching
@@ -217,7 +300,7 @@ class FusedTrainer:
         """Occupancy-grid refresh (NeRFRenderer.update_extra_state, dnerf/renderer.py:453-555) through the fused device pipeline
         (occupancy_fused.py) on the trainer's own fp16 weights / table; time frames are sharded over the ranks."""
         from .occupancy_fused import FusedOccupancy
-        self.flush()  # the density field must see the last update on every rank
+        self.sync_params()  # the density field must see the last update on every rank (sharded modes: fp16 rows exchanged now)
         if self._occ is None:
             self._occ = FusedOccupancy(self.model, hw=self.hw, table16=self.table16, rank=self.rank, world_size=self.world_size,
                                        process_group=self.pg)
@@ -462,9 +545,9 @@ class FusedTrainer:
                           self.rank * self.shard_len, self.shard_len, ptr(self.grad_shard), _lib.stream())
                 n[0] += 2
         run("grid_input_bwd", "deform_bwd", "wgrad")
-        st = _lib.stream()
-        _lib.call("seald_grad_finite_check", self.grads.data_ptr() + 4 * ntp, self.n_weights, ptr(self.found_inf), st)
-        n[0] += 1
+        if not self.fused_tail:
+            _lib.call("seald_grad_finite_check", self.grads.data_ptr() + 4 * ntp, self.n_weights, ptr(self.found_inf), _lib.stream())
+            n[0] += 1
         main.wait_stream(side)  # (also orders the overflow flag written by the scatter before it is exchanged)
         if mode in ("sharded", "allreduce"):  # MLP gradients + the overflow flag (a float: > 0 on every rank if any rank overflowed)
             dist.all_reduce(self.grads[ntp:], op=dist.ReduceOp.SUM, group=self.pg)
@@ -518,8 +601,10 @@ class FusedTrainer:
         if self.world_size > 1:
             parallel.allreduce_flat_grads(self.grads, self.pg)
 
-    def _adam_table(self, step_dev, loss_scale, found_inf, st):
+    def _adam_table(self, step_dev, loss_scale, found_inf, st, lr_scale=None):
         b1, b2 = self.betas
+        if lr_scale is None:
+            lr_scale = ptr(self.lr_scale)
         if self.dp_mode == "fused":  # own shard (gradient already summed over the ranks) + fp16 rows to every rank's table
             _lib.call("seald_dp_adam_shard_broadcast", C.cast(self._peer_table16, C.c_void_p), self._mc_table16, self.world_size,
                       ptr(self.params), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.grad_shard), self.rank * self.shard_len,
@@ -532,15 +617,15 @@ class FusedTrainer:
         else:
             # beside the march the pass must leave room on every SM (a full-occupancy grid would push the latency-bound march behind it)
             cap = self.adam_blocks if self.defer_table_update else 0
-            _lib.call("seald_adam_step_ex", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n_table_pad,
-                      self.lr, b1, b2, self.eps, 1, step_dev, loss_scale, found_inf, ptr(self.table16_pad), 1, cap, st)
+            _lib.call("seald_adam_step_lr", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n_table_pad,
+                      self.lr, lr_scale, b1, b2, self.eps, 1, step_dev, loss_scale, found_inf, ptr(self.table16_pad), 1, cap, st)
         return 1
 
     def _optimizer_table_deferred(self):
         """The hash-table pass of the previous step's optimiser, with the overflow decision / step number / loss scale that step
         stashed (the first call finds found_inf = 1: nothing pending)."""
         p = self.pending.data_ptr()
-        return self._adam_table(p + 4, p + 8, p, _lib.stream())
+        return self._adam_table(p + 4, p + 8, p, _lib.stream(), p + 12 if self.fused_tail else None)
 
     def _optimizer(self):
         """GradScaler.step + optimizer.step + GradScaler.update as device kernels (nerf/utils.py:884-886): the whole update is
@@ -550,6 +635,18 @@ class FusedTrainer:
         b1, b2 = self.betas
         ntp = self.n_table_pad
         found = self.found_inf
+        if self.fused_tail:
+            # ONE launch: overflow check of the MLP gradients, Adam on the weights, fp16 copies + tcgen05 tiles, GradScaler.update,
+            # lr_scheduler.step; it stashes {found_inf, step, loss scale, lr factor} of this step for the table pass
+            o = 4 * ntp
+            _lib.call("seald_mlp_tail", self.params.data_ptr() + o, self.grads.data_ptr() + o, self.exp_avg.data_ptr() + o,
+                      self.exp_avg_sq.data_ptr() + o, C.cast(self._tail_segs, C.c_void_p), len(self._tail_segs), self.lr_net, b1, b2, self.eps,
+                      ptr(self.step_dev), ptr(self.loss_scale), ptr(found), ptr(self.growth_tracker), 2.0, 0.5, self.growth_interval,
+                      ptr(self.pending), ptr(self.lr_scale), ptr(self.sched_step), self.lr_decay_iters, ptr(self._tail_sync), st)
+            n = 1
+            if not self.defer_table_update:
+                n += self._optimizer_table_deferred()
+            return n
         n = 3
         if self.dp_mode == "fused":  # overflow decision over the ranks + Adam on the replicated MLP weights (gradient summed over the peers)
             found = self.found_inf_global
@@ -579,7 +676,7 @@ class FusedTrainer:
 
     def _state(self):
         return (self.params, self.exp_avg, self.exp_avg_sq, self.loss_scale, self.growth_tracker, self.table16_pad, self.hw.flat, self.step_dev,
-                self.pending)
+                self.pending, self.lr_scale, self.sched_step)
 
     def stage_timings(self, reps=20):
         """Average device time (ms) of every stage, each timed alone: `reps` back-to-back launches captured in a CUDA graph and
@@ -628,9 +725,10 @@ class FusedTrainer:
         self._restore(snapshot)
         return out
 
-    def sync_params(self):
+    def sync_params(self, moments=False):
         """Data parallel with a sharded table: bring every rank's fp16 table and fp32 master copy up to date (before evaluation /
-        checkpoints); the per-step exchange of the fp16 table completes at the beginning of the NEXT step."""
+        checkpoints); the per-step exchange of the fp16 table completes at the beginning of the NEXT step.  moments=True also gathers
+        the Adam moments of the shards the other ranks own (a checkpoint must hold all of them)."""
         self.flush()
         if self.dp_mode not in ("fused", "sharded"):
             return
@@ -638,7 +736,9 @@ class FusedTrainer:
         off = self.rank * self.shard_len
         if self.dp_mode == "sharded":
             dist.all_gather_into_tensor(self.table16_pad, self.shard16, group=self.pg)
-        dist.all_gather_into_tensor(self.params[:self.n_table_pad], self.params[off:off + self.shard_len].clone(), group=self.pg)
+        bufs = [self.params] + ([self.exp_avg, self.exp_avg_sq] if moments else [])
+        for b in bufs:
+            dist.all_gather_into_tensor(b[:self.n_table_pad], b[off:off + self.shard_len].clone(), group=self.pg)
 
     def _restore(self, snap):
         for dst, src in zip(self._state(), snap):

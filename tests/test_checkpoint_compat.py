@@ -62,7 +62,8 @@ def test_optimizer_state_dict_host_logic_loads_into_torch_adam():
     g = torch.Generator().manual_seed(2)
     tr = SimpleNamespace(model=net, lr=1e-2, lr_net=1e-3, betas=(0.9, 0.99), eps=1e-15, n_table=n_table, n_table_pad=n_table,
                          exp_avg=torch.rand(n, generator=g), exp_avg_sq=torch.rand(n, generator=g), step_dev=torch.tensor([17]),
-                         loss_scale=torch.tensor([4096.0]), growth_tracker=torch.tensor([5]), growth_interval=2000)
+                         loss_scale=torch.tensor([4096.0]), growth_tracker=torch.tensor([5]), growth_interval=2000,
+                         lr_scale=torch.tensor([1.0]), sched_step=torch.tensor([17]))
     sd = ckpt.optimizer_state_dict(tr)
     assert [len(pg["params"]) for pg in sd["param_groups"]] == [1, 2, 0, 3, 0, 0, 8]
     assert [pg["lr"] for pg in sd["param_groups"]] == [1e-2, 1e-3, 1e-2, 1e-3, 1e-2, 1e-2, 1e-3]
@@ -74,5 +75,12 @@ def test_optimizer_state_dict_host_logic_loads_into_torch_adam():
         assert torch.equal(opt.state[w]["exp_avg_sq"].reshape(-1), tr.exp_avg_sq[o:o + w.numel()])
         assert float(opt.state[w]["step"]) == 17.0
         o += w.numel()
+    # LambdaLR state: loads into torch's scheduler (main_dnerf.py:134) and reports the device-side factor
+    tr.lr_scale = torch.tensor([0.5])
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** min(it / 100, 1))
+    sched.load_state_dict(ckpt.lr_scheduler_state_dict(tr))
+    assert sched.last_epoch == 17 and sched.get_last_lr() == [0.5 * g["lr"] for g in net.get_params(1e-2, 1e-3)]
+    assert ckpt.optimizer_state_dict(tr)["param_groups"][0]["lr"] == 0.5e-2
+    assert set(ckpt.default_stats()) == {"loss", "valid_loss", "results", "checkpoints", "best_result"}
     sc = ckpt.scaler_state_dict(tr)
     assert sc == {"scale": 4096.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 5}

@@ -18,13 +18,24 @@ def test_save_load_resume_and_torch_optimizer_compat(cuda_dev, tmp_path):
     d = cuda_dev
     ro, rd, ts, gt = bench.make_batches(2, d, 0)
     a = bench.build_scene(d, seed=0)
-    ta = FusedTrainer(a, num_rays=4096, max_samples=4096 * 16, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=1024.0)
+    ta = FusedTrainer(a, num_rays=4096, max_samples=4096 * 16, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=1024.0, lr_decay_iters=30,
+                      ema_decay=0.95)
     for i in range(6):
         ta.train_step(ro[i % 2], rd[i % 2], ts[i % 2], gt[i % 2])
+    ta.ema_update()
     path = os.path.join(tmp_path, "ngp_ep0001.pth")
     state = ckpt.save_checkpoint(path, ta, epoch=1)
-    assert set(state) >= {"epoch", "global_step", "stats", "mean_count", "mean_density", "model", "optimizer", "scaler"}
+    assert set(state) >= {"epoch", "global_step", "stats", "mean_count", "mean_density", "model", "optimizer", "scaler", "lr_scheduler", "ema"}
     assert state["global_step"] == 6
+    # the keys the reference's Trainer indexes after `self.stats = checkpoint_dict['stats']` (nerf/utils.py:1049,1060,1117)
+    assert set(state["stats"]) >= {"loss", "valid_loss", "results", "checkpoints", "best_result"}
+    # lr_scheduler: loads into torch's LambdaLR built like main_dnerf.py:134 and reports the learning rate this trainer had reached
+    sopt = torch.optim.Adam(bench.build_scene(d, seed=9).get_params(1e-2, 1e-3), betas=(0.9, 0.99), eps=1e-15)
+    sched = torch.optim.lr_scheduler.LambdaLR(sopt, lambda it: 0.1 ** min(it / 30, 1))
+    sched.load_state_dict(state["lr_scheduler"])
+    assert sched.last_epoch == 6 and sched.get_last_lr()[0] == pytest.approx(1e-2 * 0.1 ** (6 / 30), rel=1e-6)
+    assert state["optimizer"]["param_groups"][0]["lr"] == pytest.approx(1e-2 * 0.1 ** (6 / 30), rel=1e-6)
+    assert state["ema"]["num_updates"] == 1 and len(state["ema"]["shadow_params"]) == len(list(a.parameters()))
 
     # the reference builds torch.optim.Adam(model.get_params(lr, lr_net), betas=(0.9, 0.99), eps=1e-15) and a GradScaler: both accept the entries
     ref_model = bench.build_scene(d, seed=3)
@@ -42,8 +53,11 @@ def test_save_load_resume_and_torch_optimizer_compat(cuda_dev, tmp_path):
 
     # resume in a fresh trainer: the next step is the same step
     b = bench.build_scene(d, seed=5)
-    tb = FusedTrainer(b, num_rays=4096, max_samples=4096 * 16, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=7.0)
+    tb = FusedTrainer(b, num_rays=4096, max_samples=4096 * 16, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=7.0, lr_decay_iters=30,
+                      ema_decay=0.95)
     info = ckpt.load_checkpoint(path, tb)
+    assert int(tb.sched_step) == 6 and float(tb.lr_scale) == pytest.approx(float(ta.lr_scale), rel=1e-6)
+    assert torch.equal(tb.ema_shadow[:tb.n_params], ta.ema_shadow[:ta.n_params]) and tb.ema_num_updates == 1
     assert not info["missing_keys"] and not info["unexpected_keys"] and info["epoch"] == 1
     assert tb.global_step == 6 and int(tb.step_dev) == int(ta.step_dev) and float(tb.loss_scale) == float(ta.loss_scale)
     assert torch.equal(tb.params[:tb.n_params], ta.params[:ta.n_params]) and torch.equal(tb.exp_avg_sq[:tb.n_params], ta.exp_avg_sq[:ta.n_params])

@@ -173,3 +173,95 @@ def test_data_parallel_modes_two_gpus():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "MISMATCH" not in p.stdout and p.stdout.count(" OK") >= 9
+
+
+def test_fused_optimizer_tail_equals_five_kernel_tail_and_follows_lambda_lr(cuda_dev, monkeypatch):
+    """The one-launch MLP tail (csrc/optim_tail.cu: overflow check -> Adam -> fp16 copies + tcgen05 tiles -> GradScaler.update ->
+    lr_scheduler.step) against the round-1 sequence of five kernels on the SAME gradients and optimiser state: parameters, moments,
+    fp16 staging copies and both packed operand layouts, step counter, loss scale and growth tracker agree — for a normal step, a
+    step whose MLP gradient holds an inf (skipped, scale halved) and a step that reaches the growth interval; with lr_decay_iters
+    the learning rate follows torch's LambdaLR(0.1 ** min(iter / iters, 1)) stepped every iteration."""
+    import seald_nerf_b200._lib as L
+    from seald_nerf_b200.trainer import FusedTrainer
+    o, d, t, gt = _batch(cuda_dev, n=2048, seed=4)
+    model = _scene(cuda_dev, seed=2)
+    tr = FusedTrainer(model, num_rays=2048, max_samples=2048 * 48, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=1024.0, growth_interval=3,
+                      use_graph=False, defer_table_update=False)
+    assert tr.fused_tail
+    for _ in range(3):  # some history in the moments
+        tr.train_step(o, d, t, gt)
+    ntp, nw = tr.n_table_pad, tr.n_weights
+    for case in ("normal", "overflow", "growth"):
+        tr.set_inputs(o, d, t, gt)
+        tr.grads.zero_()
+        tr._forward_backward()
+        if case == "overflow":
+            tr.grads[ntp + 12345] = float("inf")
+        if case == "growth":
+            tr.growth_tracker.fill_(2)
+        state = [x.clone() for x in tr._state()] + [tr.grads.clone()]
+        res = {}
+        for fused in (True, False):
+            for dst, src in zip(list(tr._state()) + [tr.grads], state):
+                dst.copy_(src)
+            tr.hw.refresh(tr.weight_views)
+            tr.fused_tail = fused
+            if not fused:
+                L.call("seald_grad_finite_check", tr.grads.data_ptr() + 4 * ntp, nw, L.ptr(tr.found_inf), L.stream())
+            tr._optimizer()
+            torch.cuda.synchronize()
+            res[fused] = (tr.params.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone(), tr.hw.flat.clone(), tr.hw.packed_deform.clone(),
+                          tr.hw.packed_deform_T.clone(), tr.table16.clone(), int(tr.step_dev), float(tr.loss_scale), int(tr.growth_tracker),
+                          float(tr.grads.abs().max()))
+        tr.fused_tail = True
+        a, b = res[False], res[True]
+        assert a[7:] == b[7:], (case, a[7:], b[7:])                         # step counter, loss scale, growth tracker, cleared gradients
+        if case == "overflow":
+            assert b[7] == int(state[7]) and b[8] == 0.5 * float(state[3]) and torch.equal(b[0], state[0])   # skipped: nothing moved, scale halved
+        if case == "growth":
+            assert b[8] == 2.0 * float(state[3]) and b[9] == 0
+        for x, y in zip(a[:3], b[:3]):                                      # fp32 parameters / moments (table and MLP regions)
+            torch.testing.assert_close(x, y, rtol=5e-5, atol=1e-9)      # (FMA contraction differs between the two kernels)
+        for x, y in zip(a[3:7], b[3:7]):                                    # fp16 copies: casts of (almost) the same fp32 values
+            assert float((x.float() - y.float()).abs().max()) <= 1e-3 * float(x.float().abs().max()) + 1e-8
+            assert torch.equal(x == 0, y == 0)                              # same zero padding in every layout
+        # the tiles the tail scattered == a fresh cast + pack of the fp32 weights it produced
+        tr.hw.refresh(tr.weight_views)
+        assert torch.equal(tr.hw.flat, b[3]) and torch.equal(tr.hw.packed_deform, b[4]) and torch.equal(tr.hw.packed_deform_T, b[5])
+
+    # ---- learning-rate schedule on the device vs torch's LambdaLR
+    monkeypatch.setenv("SEALD_FUSED_TAIL", "1")
+    model = _scene(cuda_dev, seed=2)
+    iters = 20
+    tr = FusedTrainer(model, num_rays=2048, max_samples=2048 * 48, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=1024.0, lr_decay_iters=iters)
+    ref_opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1, device=cuda_dev))], lr=1e-2)
+    sched = torch.optim.lr_scheduler.LambdaLR(ref_opt, lambda it: 0.1 ** min(it / iters, 1))
+    for i in range(25):
+        assert tr.current_lr[0] == pytest.approx(sched.get_last_lr()[0], rel=1e-6)
+        tr.train_step(o, d, t, gt)
+        ref_opt.step()
+        sched.step()
+    torch.cuda.synchronize()
+    assert int(tr.sched_step) == 25 and tr.current_lr[0] == pytest.approx(1e-3, rel=1e-6)
+
+
+def test_ema_matches_torch_ema_rule(cuda_dev):
+    """ema_update(): decay = min(0.95, (1 + n) / (10 + n)); shadow -= (1 - decay) * (shadow - param) (torch_ema, once per epoch)."""
+    from seald_nerf_b200.trainer import FusedTrainer
+    model = _scene(cuda_dev, seed=3)
+    o, d, t, gt = _batch(cuda_dev, n=1024, seed=1)
+    tr = FusedTrainer(model, num_rays=1024, max_samples=1024 * 48, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=1024.0, ema_decay=0.95)
+    shadow = tr.params.clone()
+    for epoch in range(3):
+        for _ in range(4):
+            tr.train_step(o, d, t, gt)
+        tr.ema_update()
+        decay = min(0.95, (1 + epoch + 1) / (10 + epoch + 1))
+        tmp = (shadow - tr.params) * (1.0 - decay)
+        shadow = shadow - tmp
+    torch.testing.assert_close(tr.ema_shadow, shadow, rtol=1e-4, atol=1e-8)  # (the kernel contracts s - omd * (s - p) into an FMA)
+    raw = tr.params.clone()
+    tr.ema_copy_to()
+    assert torch.equal(tr.params, tr.ema_shadow) and torch.equal(tr.table16, model.encoder.embeddings.data.half())
+    tr.ema_restore()
+    assert torch.equal(tr.params, raw)
