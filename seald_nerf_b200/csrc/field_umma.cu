@@ -25,6 +25,8 @@
 // an SS-mode 128x128x16 MMA reads 8 KiB of operands per 64 cycles (= the 128 B/cycle port), plus 32 KiB of epilogue
 // stores and the weight refills per tile-layer, ~830 cycles against the 512-cycle MMA floor.  Numerics as the mma.sync kernels of field.cu: fp16
 // operands and layer outputs, fp32 accumulation.
+#include <cstdlib>
+
 #include "encoders.cuh"
 #include "umma.cuh"
 
@@ -519,7 +521,8 @@ extern "C" int seald_field_deform_backward_umma(const float* grad_x01, const flo
                                             (__half*)bwd_buf, (__half*)gout_buf);
         return 0;
     };
-    const bool big = n_tiles >= 4u * SEALD_NUM_SMS;
+    static const int forced_g = getenv("SEALD_UMMA_G") ? atoi(getenv("SEALD_UMMA_G")) : 0;  // measurement switch
+    const bool big = forced_g ? forced_g == 4 : n_tiles >= 4u * SEALD_NUM_SMS;
     const int rc = big ? launch(k_deform_backward_umma<4>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
                        : launch(k_deform_backward_umma<2>, 2, UmmaSmem<2>::BYTES, UmmaSmem<2>::THREADS);
     if (rc) return rc;
@@ -545,7 +548,8 @@ extern "C" int seald_field_deform_forward_umma(const float* xyz, const float* ti
         return 0;
     };
     // enough tiles to give every SM four at a time: G = 4 (tensor pipe saturated); otherwise spread over more SMs with G = 2
-    const bool big = n_tiles >= 4u * SEALD_NUM_SMS;
+    static const int forced_g = getenv("SEALD_UMMA_G") ? atoi(getenv("SEALD_UMMA_G")) : 0;  // measurement switch
+    const bool big = forced_g ? forced_g == 4 : n_tiles >= 4u * SEALD_NUM_SMS;
     int rc;
     if (fwd_buf) {
         rc = big ? launch(k_deform_forward_umma<true, 4>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
