@@ -11,6 +11,7 @@
 //   * rays[] rows are written in ray order (row n describes ray n), which makes the layout deterministic;
 //   * the inference kernels can take the live-ray count from device memory so the render loop needs no host
 //     synchronisation, and seald_compact_alive replaces the boolean-mask compaction.
+#include <cstdlib>
 #include <limits>
 
 #include "common.cuh"
@@ -465,48 +466,13 @@ __global__ void k_march_rays_train(const float* __restrict__ rays_o, const float
 constexpr uint32_t kMarchWarps = 8;
 constexpr uint32_t kMaxStepsSmem = 1024;
 
-template <bool SEAL>
-__global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
-    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid, const float bound,
-    const float dt_gamma, const uint32_t max_steps, const uint32_t N, const uint32_t C, const uint32_t H, const uint32_t M,
-    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ aabb, const float min_near,
-    float* __restrict__ nears_out, float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
-    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter, const float* __restrict__ noises,
-    const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask, const float* __restrict__ occ) {
-    __shared__ float s_t[kMarchWarps][kMaxStepsSmem];
-    __shared__ uint32_t s_cnt[kMarchWarps];
-    __shared__ uint32_t s_off[kMarchWarps];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t n = blockIdx.x * kMarchWarps + warp;
-    const bool active = n < N;
+// The sequential-chain walk of one ray by one warp (see k_march_rays_train_warp): returns the sample count, sample parameters in s_t.
+__device__ __forceinline__ uint32_t walk_sequential(const Ray& r, const MarchConst& mc, const uint8_t* __restrict__ grid, const float t0,
+                                                    const float far, const float dt_gamma, const uint32_t max_steps, const uint32_t lane,
+                                                    float* __restrict__ s_t) {
     constexpr uint32_t FULL = 0xffffffffu;
-
-    Ray r;
-    float near = 0.f, far = 0.f, noise = 0.f;
-    if (active) {
-        const float* o = rays_o + (size_t)n * 3;
-        const float* d = rays_d + (size_t)n * 3;
-        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
-        r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
-        r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
-        if (nears) {
-            near = nears[n];
-            far = fars[n];
-        } else {
-            slab_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, aabb, min_near, near, far);
-            if (nears_out && lane == 0) { nears_out[n] = near; fars_out[n] = far; }
-        }
-        noise = noises[n];
-    }
-    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
-    float t0 = near;
-    t0 += clampf(t0 * dt_gamma, mc.dt_min, mc.dt_max) * noise;
-
-    bool may_hit = active;
-    if (occ && active) may_hit = clip_to_occupied(r, occ, near, far);
-
     uint32_t count = 0;
-    if (may_hit && t0 < far) {
+    {
         float tb = t0;         // chain value at the start of the current block of 32 (warp uniform)
         uint32_t lp = 0;       // walker position inside the block
         bool has_pend = false; // an empty-space skip is looking for its landing element
@@ -551,7 +517,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
                     const uint32_t inv = ~(occ_mask >> lp);
                     uint32_t n_run = inv ? (uint32_t)(__ffs(inv) - 1) : 32u;
                     n_run = min(n_run, max_steps - count);
-                    if (lane >= lp && lane < lp + n_run) s_t[warp][count + lane - lp] = mine;
+                    if (lane >= lp && lane < lp + n_run) s_t[count + lane - lp] = mine;
                     count += n_run;
                     lp += n_run;
                     if (count >= max_steps) { done = true; break; }
@@ -565,6 +531,52 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
             if (!(tb < far)) done = true;  // every later element is beyond far
         }
     }
+    return count;
+}
+
+
+template <bool SEAL>
+__global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid, const float bound,
+    const float dt_gamma, const uint32_t max_steps, const uint32_t N, const uint32_t C, const uint32_t H, const uint32_t M,
+    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ aabb, const float min_near,
+    float* __restrict__ nears_out, float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
+    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter, const float* __restrict__ noises,
+    const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask, const float* __restrict__ occ) {
+    __shared__ float s_t[kMarchWarps][kMaxStepsSmem];
+    __shared__ uint32_t s_cnt[kMarchWarps];
+    __shared__ uint32_t s_off[kMarchWarps];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x * kMarchWarps + warp;
+    const bool active = n < N;
+    constexpr uint32_t FULL = 0xffffffffu;
+
+    Ray r;
+    float near = 0.f, far = 0.f, noise = 0.f;
+    if (active) {
+        const float* o = rays_o + (size_t)n * 3;
+        const float* d = rays_d + (size_t)n * 3;
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+        r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+        if (nears) {
+            near = nears[n];
+            far = fars[n];
+        } else {
+            slab_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, aabb, min_near, near, far);
+            if (nears_out && lane == 0) { nears_out[n] = near; fars_out[n] = far; }
+        }
+        noise = noises[n];
+    }
+    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+    float t0 = near;
+    t0 += clampf(t0 * dt_gamma, mc.dt_min, mc.dt_max) * noise;
+
+    bool may_hit = active;
+    if (occ && active) may_hit = clip_to_occupied(r, occ, near, far);
+
+    uint32_t count = 0;
+    if (may_hit && t0 < far) count = walk_sequential(r, mc, grid, t0, far, dt_gamma, max_steps, lane, s_t[warp]);
     if (lane == 0) s_cnt[warp] = active ? count : 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -620,6 +632,354 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_rays_train_warp(
             dirs[s * 3] = r.dx; dirs[s * 3 + 1] = r.dy; dirs[s * 3 + 2] = r.dz;
         }
         deltas[s * 2] = dt;
+        deltas[s * 2 + 1] = t_new - last_t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// training march with a constant step (dt_gamma == 0, the D-NeRF default), one warp per ray, NO sequential adds.
+//
+// The chain t_{k+1} = fl(t_k + dt) is piecewise linear in k: inside one binade every t_k is a multiple of ulp(t) and
+// fl(t + dt) = t + I * ulp with I = dt / ulp rounded to nearest (a constant unless dt sits exactly half-way between two
+// multiples).  So the chain is described by <= kChainSegs segments {k0, t(k0), I * ulp}; the element that crosses into the next
+// binade is produced by ONE real fp32 add.  t_k = fma(k - k0, inc, t(k0)) is then exact, i.e. bit-identical to the
+// reference's running sum (checked against sequential adds for every case the tests march).  With that:
+//   phase A  every chain element of the ray is probed in parallel (no dependency between blocks of 32, the bitfield loads
+//            pipeline); an empty element computes by itself WHERE its empty-space skip lands: the first element with
+//            !(t_j < tt), found from the closed form and verified with exact comparisons.  succ[k] = occupied flag | landing;
+//   phase B  the reference's control flow is a pointer chase through succ[] in shared memory (~1 LDS per visited element);
+//   write    samples are recomputed from their chain indices and stored cooperatively (coalesced).
+// Rays whose chain has a tie / leaves the supported exponent range fall back to the sequential walk of the legacy kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChainSegs = 6;
+constexpr uint32_t kChainChunk = 1024;   // chain elements resolved per phase A/B pass
+constexpr int kChainMaxIndex = 32767;    // succ[] stores absolute indices in 15 bits
+
+struct Chain {
+    int k[kChainSegs];
+    float t[kChainSegs];
+    float inc[kChainSegs];
+    int k_end;  // first chain index with !(t < far)
+    bool ok;
+};
+
+__device__ __forceinline__ float chain_at(const Chain& c, const int j) {
+    float ts = c.t[0], inc = c.inc[0];
+    int ks = 0;
+#pragma unroll
+    for (int i = 1; i < kChainSegs; i++)
+        if (j >= c.k[i]) { ts = c.t[i]; inc = c.inc[i]; ks = c.k[i]; }
+    return __fmaf_rn((float)(j - ks), inc, ts);
+}
+
+__device__ __forceinline__ void chain_build(Chain& c, const float t0, const float dt, const float far) {
+#pragma unroll
+    for (int i = 0; i < kChainSegs; i++) { c.k[i] = 0x7fffffff; c.t[i] = 0.f; c.inc[i] = 0.f; }
+    c.ok = true;
+    c.k_end = 0;
+    const uint32_t bd = __float_as_uint(dt);
+    const int ed = (int)(bd >> 23);
+    const uint32_t D = (bd & 0x7fffffu) | 0x800000u;
+    if (ed == 0 || ed >= 255) { c.ok = false; return; }
+    float t = t0;
+    int k = 0;
+    bool open = true;
+#pragma unroll
+    for (int s = 0; s < kChainSegs; s++) {
+        if (open) {
+            if (!(t < far)) {
+                c.k_end = k;
+                open = false;
+            } else {
+                const uint32_t bt = __float_as_uint(t);
+                const int et = (int)(bt >> 23);
+                const int shift = et - ed;
+                if (et < 24 || et >= 255 || shift < 1 || shift > 23) { c.ok = false; return; }
+                const uint32_t Mt = (bt & 0x7fffffu) | 0x800000u;
+                const uint32_t q = D >> shift, rem = D & ((1u << shift) - 1u), half = 1u << (shift - 1);
+                if (rem == half) { c.ok = false; return; }  // tie: the increment alternates with the parity of the sum
+                const uint32_t I = q + (rem > half ? 1u : 0u);
+                const uint32_t n_safe = (0xffffffu - Mt) / I;  // elements k .. k + n_safe stay inside the binade
+                const float inc = __uint_as_float((uint32_t)(et - 23) << 23) * (float)I;
+                c.k[s] = k; c.t[s] = t; c.inc[s] = inc;
+                const float tl = __fmaf_rn((float)n_safe, inc, t);
+                if (!(tl < far)) {
+                    int j = __float2int_ru((far - t) / inc);
+                    j = max(0, min(j, (int)n_safe));
+                    while (j > 0 && !(__fmaf_rn((float)(j - 1), inc, t) < far)) j--;
+                    while (__fmaf_rn((float)j, inc, t) < far) j++;
+                    c.k_end = k + j;
+                    open = false;
+                } else {
+                    t = tl + dt;  // the one real add that crosses into the next binade
+                    k += (int)n_safe + 1;
+                }
+            }
+        }
+    }
+    if (open) {
+        if (t < far) c.ok = false; else c.k_end = k;
+    }
+    if (c.k_end > kChainMaxIndex) c.ok = false;
+}
+
+// probe_grid with the cascade selection short-cut for a single cascade and the cell index in fp32: 0.5 * v is exact and
+// v * 0.5 * H has one rounding in fp32 exactly like the double product rounded to float, so the integers are the same
+__device__ __forceinline__ bool probe_grid_fast(const Ray& r, const MarchConst& mc, const uint8_t* __restrict__ grid, const float t, Probe& p) {
+    const float x = clampf(r.ox + t * r.dx, -mc.bound, mc.bound);
+    const float y = clampf(r.oy + t * r.dy, -mc.bound, mc.bound);
+    const float z = clampf(r.oz + t * r.dz, -mc.bound, mc.bound);
+    const float dt = clampf(t * mc.dt_gamma, mc.dt_min, mc.dt_max);
+    int level = 0;
+    if (mc.C > 1) level = max(mip_from_pos(x, y, z, mc.C), mip_from_dt(dt, mc.H, mc.C));
+    const float mip_bound = fminf(scalbnf(1.0f, level), mc.bound);
+    const float mip_rbound = 1 / mip_bound;
+    const float fH = (float)mc.H, top = (float)(mc.H - 1);
+    const int nx = clampf((0.5f * (x * mip_rbound + 1)) * fH, 0.0f, top);
+    const int ny = clampf((0.5f * (y * mip_rbound + 1)) * fH, 0.0f, top);
+    const int nz = clampf((0.5f * (z * mip_rbound + 1)) * fH, 0.0f, top);
+    const uint32_t index = level * mc.H3 + morton3D_enc(nx, ny, nz);
+    const bool occ = __ldg(grid + index / 8) & (1 << (index % 8));
+    p.x = x; p.y = y; p.z = z; p.dt = dt; p.mip_bound = mip_bound;
+    p.nx = nx; p.ny = ny; p.nz = nz;
+    return occ;
+}
+
+// per-ray record shared by the CTA: phase A is pooled over all warps (a ray that misses costs nothing, a long ray is
+// probed by the whole CTA), so the kernel's duration follows the CTA's mean ray, not the longest ray of the batch
+struct ChainRay {
+    Ray r;
+    int seg_k[kChainSegs + 1];
+    float seg_t[kChainSegs];
+    float seg_inc[kChainSegs];
+    int k_end;
+};
+
+__device__ __forceinline__ float chain_at(const ChainRay& c, const int j) {
+    float ts = c.seg_t[0], inc = c.seg_inc[0];
+    int ks = 0;
+#pragma unroll
+    for (int i = 1; i < kChainSegs; i++)
+        if (j >= c.seg_k[i]) { ts = c.seg_t[i]; inc = c.seg_inc[i]; ks = c.seg_k[i]; }
+    return __fmaf_rn((float)(j - ks), inc, ts);
+}
+
+template <bool SEAL>
+__global__ void __launch_bounds__(kMarchWarps * 32, 4) k_march_rays_train_chain(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid, const float bound,
+    const uint32_t max_steps, const uint32_t N, const uint32_t C, const uint32_t H, const uint32_t M,
+    const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ aabb, const float min_near,
+    float* __restrict__ nears_out, float* __restrict__ fars_out, float* __restrict__ xyzs, float* __restrict__ dirs,
+    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter, const float* __restrict__ noises,
+    const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask, const float* __restrict__ occ) {
+    // per ray: succ[kChainChunk] + sample indices[kMaxStepsSmem] (uint16), or - fallback rays - kMaxStepsSmem sample parameters (fp32)
+    __shared__ __align__(16) uint16_t s_buf[kMarchWarps][kChainChunk + kMaxStepsSmem];
+    __shared__ ChainRay s_ray[kMarchWarps];
+    __shared__ uint32_t s_cnt[kMarchWarps];
+    __shared__ uint32_t s_off[kMarchWarps];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x * kMarchWarps + warp;
+    const bool active = n < N;
+    uint16_t* s_samp = s_buf[warp] + kChainChunk;
+    float* s_t = reinterpret_cast<float*>(s_buf[warp]);
+
+    Ray r;
+    float near = 0.f, far = 0.f, noise = 0.f;
+    if (active) {
+        const float* o = rays_o + (size_t)n * 3;
+        const float* d = rays_d + (size_t)n * 3;
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+        r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+        if (nears) {
+            near = nears[n];
+            far = fars[n];
+        } else {
+            slab_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, aabb, min_near, near, far);
+            if (nears_out && lane == 0) { nears_out[n] = near; fars_out[n] = far; }
+        }
+        noise = noises[n];
+    }
+    const MarchConst mc = make_march_const(bound, 0.0f, max_steps, C, H);
+    const float dt_c = clampf(0.0f, mc.dt_min, mc.dt_max);
+    float t0 = near;
+    t0 += dt_c * noise;
+
+    bool may_hit = active;
+    if (occ && active) may_hit = clip_to_occupied(r, occ, near, far);
+
+    uint32_t count = 0;
+    bool use_chain = true;
+    int my_k_end = 0;
+    {
+        Chain ch;
+        ch.k_end = 0;
+        if (may_hit && t0 < far) {
+            chain_build(ch, t0, dt_c, far);
+            use_chain = ch.ok;
+            if (!use_chain) count = walk_sequential(r, mc, grid, t0, far, 0.0f, max_steps, lane, s_t);
+        }
+        my_k_end = use_chain ? ch.k_end : 0;
+        if (lane == 0) {
+            ChainRay& cr = s_ray[warp];
+            cr.r = r;
+#pragma unroll
+            for (int i = 0; i < kChainSegs; i++) { cr.seg_k[i] = ch.k[i]; cr.seg_t[i] = ch.t[i]; cr.seg_inc[i] = ch.inc[i]; }
+            cr.seg_k[0] = 0;
+            cr.seg_k[kChainSegs] = 0x7fffffff;
+            cr.k_end = my_k_end;
+        }
+    }
+    __syncthreads();
+    int k_max = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kMarchWarps; w++) k_max = max(k_max, s_ray[w].k_end);
+
+    int kw = 0;  // this warp's walker on its own ray
+    bool done = false;
+    for (int c0 = 0; c0 < k_max; c0 += (int)kChainChunk) {
+        // ---- phase A, pooled: blocks of 32 chain elements of every ray of the CTA are dealt round-robin to the warps
+        uint32_t rot = 0;
+        for (uint32_t w = 0; w < kMarchWarps; w++) {
+            const ChainRay& cr = s_ray[w];
+            const int k_end = cr.k_end;
+            const int ke = min(k_end, c0 + (int)kChainChunk);
+            if (ke <= c0) continue;
+            const uint32_t nb = (uint32_t)(ke - c0 + 31) / 32u;
+            const Ray rr = cr.r;
+            for (uint32_t blk = (warp - rot) & (kMarchWarps - 1); blk < nb; blk += kMarchWarps) {
+                const int kb = c0 + (int)blk * 32;
+                const int k = kb + (int)lane;
+                // segment of the block's first element (warp uniform); elements past its end take the general path
+                int si = 0;
+#pragma unroll
+                for (int i = 1; i < kChainSegs; i++) si += (kb >= cr.seg_k[i]) ? 1 : 0;
+                const int ks = cr.seg_k[si], kn = cr.seg_k[si + 1];
+                const float ts = cr.seg_t[si], inc = cr.seg_inc[si];
+                auto T = [&](const int q) {
+                    if (q < kn) return __fmaf_rn((float)(q - ks), inc, ts);
+                    float t2 = ts, i2 = inc;
+                    int k2 = ks;
+                    for (int i = si + 1; i < kChainSegs; i++)
+                        if (q >= cr.seg_k[i]) { t2 = cr.seg_t[i]; i2 = cr.seg_inc[i]; k2 = cr.seg_k[i]; }
+                    return __fmaf_rn((float)(q - k2), i2, t2);
+                };
+                bool is_occ = false;
+                uint32_t v = 0;
+                if (k < k_end) {
+                    const float t = T(k);
+                    Probe p;
+                    is_occ = probe_grid_fast(rr, mc, grid, t, p);
+                    if (!is_occ) {
+                        const float tt = voxel_exit(rr, mc, p, t);
+                        int j = ks + min(__float2int_ru(__fdividef(tt - ts, inc)), 1 << 20);
+                        j = min(max(j, k + 1), k_end);
+                        while (j < k_end && T(j) < tt) j++;
+                        while (j > k + 1 && !(T(j - 1) < tt)) j--;
+                        v = (uint32_t)j;
+                    }
+                }
+                // an occupied element stores the length of the run of occupied elements it starts inside this block
+                const uint32_t occ_mask = __ballot_sync(0xffffffffu, is_occ);
+                if (is_occ) {
+                    const uint32_t inv = ~(occ_mask >> lane);
+                    v = 0x8000u | (inv ? (uint32_t)(__ffs(inv) - 1) : 32u);
+                }
+                if (k < k_end) s_buf[w][k - c0] = (uint16_t)v;
+            }
+            rot += nb;
+        }
+        __syncthreads();
+        // ---- pointer jumping through runs of empty elements (in place: every value an element can read is a later element of
+        // its own path that is reached through empties only, so the walk below visits the same occupied elements in the same order)
+#pragma unroll 1
+        for (int round = 0; round < 3; round++) {
+            for (uint32_t w = 0; w < kMarchWarps; w++) {
+                const int nk = min(s_ray[w].k_end, c0 + (int)kChainChunk) - c0;
+                uint16_t* sw = s_buf[w];
+                for (int e = (int)threadIdx.x; e < nk; e += (int)(kMarchWarps * 32)) {
+                    const uint32_t v = sw[e];
+                    const int ve = (int)v - c0;
+                    if (!(v & 0x8000u) && ve < nk) {
+                        const uint32_t u = sw[ve];
+                        if (!(u & 0x8000u)) sw[e] = (uint16_t)u;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- phase B: the reference's loop as a pointer chase through this warp's own ray (warp uniform)
+        if (use_chain && !done) {
+            const int c1 = min(my_k_end, c0 + (int)kChainChunk);
+            const uint16_t* s_succ = s_buf[warp];
+            while (kw < c1) {
+                const uint32_t v = s_succ[kw - c0];
+                if (v & 0x8000u) {
+                    const uint32_t n_run = min(v & 0xffu, max_steps - count);
+                    if (lane < n_run) s_samp[count + lane] = (uint16_t)(kw + (int)lane);
+                    count += n_run;
+                    kw += (int)n_run;
+                    if (count >= max_steps) { done = true; break; }
+                } else {
+                    kw = (int)v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (lane == 0) s_cnt[warp] = active ? count : 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < kMarchWarps; w++) { s_off[w] = total; total += s_cnt[w]; }
+        const uint32_t n_rays = min(kMarchWarps, N - blockIdx.x * kMarchWarps);
+        const uint32_t base = atomicAdd(counter, total);
+        atomicAdd(counter + 1, n_rays);
+        for (uint32_t w = 0; w < kMarchWarps; w++) s_off[w] += base;
+    }
+    __syncthreads();
+    if (!active) return;
+    const uint32_t point_index = s_off[warp];
+    if (lane == 0) {
+        rays[n * 3] = n;
+        rays[n * 3 + 1] = point_index;
+        rays[n * 3 + 2] = count;
+    }
+    if (count == 0) return;
+    if (point_index + count > M) {  // overflow: dropped ray, zero fill of the unowned rows (see k_march_rays_train_warp)
+        for (size_t s = (size_t)point_index + lane; s < M; s += 32) {
+            xyzs[s * 3] = 0.f; xyzs[s * 3 + 1] = 0.f; xyzs[s * 3 + 2] = 0.f;
+            dirs[s * 3] = 0.f; dirs[s * 3 + 1] = 0.f; dirs[s * 3 + 2] = 0.f;
+            deltas[s * 2] = 0.f; deltas[s * 2 + 1] = 0.f;
+            if (SEAL) seal_mask[s] = 0;
+        }
+        return;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < count; j += 32) {
+        float t, last_t = t0;
+        if (use_chain) {
+            t = chain_at(s_ray[warp], (int)s_samp[j]);
+            if (j > 0) last_t = chain_at(s_ray[warp], (int)s_samp[j - 1]) + dt_c;
+        } else {
+            t = s_t[j];
+            if (j > 0) last_t = s_t[j - 1] + dt_c;
+        }
+        const float x = clampf(r.ox + t * r.dx, -bound, bound);
+        const float y = clampf(r.oy + t * r.dy, -bound, bound);
+        const float z = clampf(r.oz + t * r.dz, -bound, bound);
+        const float t_new = t + dt_c;
+        const size_t s = (size_t)point_index + j;
+        if (SEAL) {
+            float sx = x, sy = y, sz = z, sdx = r.dx, sdy = r.dy, sdz = r.dz;
+            seal_mask[s] = seal_map_sample(mp, sx, sy, sz, sdx, sdy, sdz) ? 1 : 0;
+            xyzs[s * 3] = sx; xyzs[s * 3 + 1] = sy; xyzs[s * 3 + 2] = sz;
+            dirs[s * 3] = sdx; dirs[s * 3 + 1] = sdy; dirs[s * 3 + 2] = sdz;
+        } else {
+            xyzs[s * 3] = x; xyzs[s * 3 + 1] = y; xyzs[s * 3 + 2] = z;
+            dirs[s * 3] = r.dx; dirs[s * 3 + 1] = r.dy; dirs[s * 3 + 2] = r.dz;
+        }
+        deltas[s * 2] = dt_c;
         deltas[s * 2 + 1] = t_new - last_t;
     }
 }
@@ -1350,6 +1710,14 @@ static int march_train_impl(const float* rays_o, const float* rays_d, const uint
     cudaStream_t st = to_stream(stream);
     // small batches (training: 4096 rays) are latency bound: one warp per ray.  Large batches (whole images) have enough
     // rays to fill the machine with one thread per ray, which does less total work.
+    static const bool no_chain = getenv("SEALD_MARCH_CHAIN") && atoi(getenv("SEALD_MARCH_CHAIN")) == 0;  // measurement switch
+    if (N <= 65536u && max_steps <= kMaxStepsSmem && dt_gamma == 0.0f && !no_chain) {
+        // constant step: closed-form chain, every element probed in parallel + pointer chase
+        auto k = mapper ? k_march_rays_train_chain<true> : k_march_rays_train_chain<false>;
+        k<<<div_up(N, kMarchWarps), kMarchWarps * 32, 0, st>>>(rays_o, rays_d, bitfield, bound, max_steps, N, C, H, M, nears, fars, aabb6, min_near,
+                                                              nears_out, fars_out, xyzs, dirs, deltas, rays, counter, noises, mp, mask, occ);
+        return launch_status();
+    }
     if (N <= 65536u && max_steps <= kMaxStepsSmem) {
         auto k = mapper ? k_march_rays_train_warp<true> : k_march_rays_train_warp<false>;
         k<<<div_up(N, kMarchWarps), kMarchWarps * 32, 0, st>>>(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb6,
