@@ -276,14 +276,17 @@ int seald_field_deform_forward(const float* xyz, const float* time_dev, const vo
 /* Same operation on the Blackwell tensor cores (tcgen05.mma, accumulators in tensor memory; csrc/field_umma.cu).
  * `packed`: the deformation weights re-laid out by seald_field_umma_pack_deform into the canonical K-major operand tiles
  * ([K/8][N][8] fp16 per layer, seald_field_umma_deform_bytes(n_layers) bytes, 16-byte aligned) so that one bulk copy per
- * layer brings them into shared memory.  Same outputs / optional training buffers as seald_field_deform_forward. */
+ * layer brings them into shared memory.  Same outputs as seald_field_deform_forward; the optional training buffers hold whole
+ * 128-row TILE IMAGES (the shared-memory A tile as it is: [tile][width/8][128][8] fp16, dead rows of a live tile zero):
+ * in_buf ceil128(M) x 80, fwd_buf [n_layers-1] x ceil128(M) x 128 halves — the layout seald_mlp_wgrad_umma reads with ld = 0. */
 uint64_t seald_field_umma_deform_bytes(int n_layers);
 int seald_field_umma_pack_deform(const void* const* weights, int n_layers, void* packed, seald_stream_t stream);
 int seald_field_deform_forward_umma(const float* xyz, const float* time_dev, const void* packed, int n_layers, uint32_t M,
                                     const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf,
                                     void* fwd_buf, seald_stream_t stream);
-/* Backward (dgrad chain) on tcgen05: same buffers as seald_field_deform_backward; packedT = the transposed weight tiles
- * W_l^T of layers 1..n-1 (seald_field_umma_pack_deform_T, seald_field_umma_deform_bytes_T(n_layers) bytes). */
+/* Backward (dgrad chain) on tcgen05: the buffers of seald_field_deform_backward as tile images (fwd_buf as written by
+ * seald_field_deform_forward_umma; bwd_buf [n_layers-1] x ceil128(M) x 128, gout_buf ceil128(M) x 16 halves); packedT = the transposed
+ * weight tiles W_l^T of layers 1..n-1 (seald_field_umma_pack_deform_T, seald_field_umma_deform_bytes_T(n_layers) bytes). */
 uint64_t seald_field_umma_deform_bytes_T(int n_layers);
 int seald_field_umma_pack_deform_T(const void* const* weights, int n_layers, void* packedT, seald_stream_t stream);
 int seald_field_umma_pack_deform_both(const void* const* weights, int n_layers, void* packed, void* packedT, seald_stream_t stream);
@@ -316,8 +319,10 @@ typedef struct {
     int n_real, k_real; /* rows / columns of dW actually written */
 } seald_wgrad_job;
 int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream);
-/* Same contract on the Blackwell tensor cores (csrc/wgrad_umma.cu): tcgen05.mma over MN-major operand tiles staged with
- * cp.async, fp32 accumulators in tensor memory, one vector-atomic flush per CTA. */
+/* Same contract on the Blackwell tensor cores (csrc/wgrad_umma.cu): tcgen05.mma over MN-major operand tiles, fp32 accumulators in
+ * tensor memory, one vector-atomic flush per CTA.  Row-major operands are staged with cp.async.  ldg == lda == 0 declares TILE-IMAGE
+ * operands as the tcgen05 deformation kernels save them: [tile][width/8][128 rows][8 halves] per 128-row tile (dead rows of a live
+ * tile zero); such a tile is fetched with one cp.async.bulk per operand. */
 int seald_mlp_wgrad_umma(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream);
 
 /* FFMLP-compatible fused MLP.  Replace ffmlp_forward / ffmlp_inference / ffmlp_backward (ffmlp/src/ffmlp.h:8-11).

@@ -592,7 +592,7 @@ extern "C" int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t
     for (int i = 0; i < n_jobs; i++) {
         const seald_wgrad_job& a = jobs[i];
         if (!a.G || !a.A || !a.dW) return SEALD_E_BADARG;
-        if ((a.N != 16 && a.N != 32 && a.N != 64 && a.N != 128) || a.K % 16 || a.K <= 0 || a.K > 128 || a.ldg % 8 || a.lda % 8) return SEALD_E_UNSUPPORTED;
+        if ((a.N != 16 && a.N != 32 && a.N != 64 && a.N != 128) || a.K % 16 || a.K <= 0 || a.K > 128 || a.ldg % 8 || a.lda % 8 || a.ldg == 0 || a.lda == 0) return SEALD_E_UNSUPPORTED;  // (ld 0 = tile images: wgrad_umma.cu only)
         if (((uintptr_t)a.G % 16) || ((uintptr_t)a.A % 16)) return SEALD_E_ALIGN;
         WgradJob& j = js.j[i];
         j.G = (const __half*)a.G; j.A = (const __half*)a.A; j.dW = a.dW;

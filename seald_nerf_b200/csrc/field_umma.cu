@@ -160,13 +160,17 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
         const uint32_t t_lane = tmem_base + ((uint32_t)(r & ~31) << 16) + g * kUW;  // this warp's 32-lane quadrant, group's columns
         const float tval = *time;
         const bool t_is_zero = (tval == 0.0f);
-        int row = 0;
+        int row = 0, tile = 0;
+        bool save_tile = false;
+        const size_t tiles_cap = (size_t)(M + kUW - 1) / kUW;  // tiles the saved-activation buffers hold per layer
         float px = 0.f, py = 0.f, pz = 0.f;
         for (int i = 0; i < n_items; i++) {
             const int l = i % n_layers;
             if (l == 0) {
                 const int pair = (int)blockIdx.x + (i / n_layers) * (int)gridDim.x;
-                row = (G * pair + g) * kUW + r;
+                tile = G * pair + g;
+                row = tile * kUW + r;
+                save_tile = SAVE && tile < n_tiles;
                 const bool live = row < m_used;
                 if (live) { px = xyz[(size_t)row * 3]; py = xyz[(size_t)row * 3 + 1]; pz = xyz[(size_t)row * 3 + 2]; }
                 const float xv[3] = {px, py, pz};
@@ -191,7 +195,9 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                     }
                     const uint4 u = make_uint4(w[0], w[1], w[2], w[3]);
                     *reinterpret_cast<uint4*>(a_tile + ((size_t)c8 * kUW + r) * 16) = u;
-                    if (SAVE && live) *reinterpret_cast<uint4*>(in_buf + (size_t)row * kUK0 + c8 * 8) = u;
+                    // saved in the tile-image layout (umma.cuh): the shared-memory tile as it is, 512 contiguous bytes per warp store;
+                    // dead rows of a live tile are zeros (their values never reach a weight gradient)
+                    if (save_tile) *reinterpret_cast<uint4*>(in_buf + (((size_t)tile * (kUK0 / 8) + c8) * kUW + r) * 8) = u;
                 }
                 umma::fence_proxy_async();
                 umma::mbar_arrive(bar_aready + g);
@@ -216,7 +222,9 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                         }
                         const uint4 u = make_uint4(w[0], w[1], w[2], w[3]);
                         *reinterpret_cast<uint4*>(a_tile + ((size_t)(q * 4 + c4) * kUW + r) * 16) = u;
-                        if (SAVE && row < m_used) *reinterpret_cast<uint4*>(fwd_buf + ((size_t)l * M + row) * kUW + (q * 4 + c4) * 8) = u;
+                        if (save_tile)
+                            *reinterpret_cast<uint4*>(fwd_buf + ((((size_t)l * tiles_cap + tile) * (kUW / 8) + (q * 4 + c4)) * kUW + r) * 8) =
+                                (row < m_used) ? u : make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
                 umma::fence_before_sync();
@@ -371,13 +379,17 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
         const uint32_t t_lane = tmem_base + ((uint32_t)(r & ~31) << 16) + g * kUW;
         // at t == 0 the deformation is replaced by zeros (network.py:140-141): no gradient reaches the net
         const float inv = (time && *time == 0.0f) ? 0.0f : 1.0f / (2 * bound);
-        int row = 0;
+        int row = 0, tile = 0;
+        bool live_tile = false;
+        const size_t tiles_cap = (size_t)(M + kUW - 1) / kUW;
         for (int i = 0; i < n_items; i++) {
             const int s = i % n_steps;
             const int l = n_layers - 1 - s;
             if (s == 0) {
                 const int unit = (int)blockIdx.x + (i / n_steps) * (int)gridDim.x;
-                row = (G * unit + g) * kUW + r;
+                tile = G * unit + g;
+                row = tile * kUW + r;
+                live_tile = tile < n_tiles;
                 const bool live = row < m_used;
                 float gv[3] = {0.f, 0.f, 0.f};
                 if (live) { gv[0] = grad_x01[(size_t)row * 3] * inv; gv[1] = grad_x01[(size_t)row * 3 + 1] * inv; gv[2] = grad_x01[(size_t)row * 3 + 2] * inv; }
@@ -386,20 +398,22 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                 *reinterpret_cast<uint4*>(a_tile + ((size_t)0 * kUW + r) * 16) = u0;
                 *reinterpret_cast<uint4*>(a_tile + ((size_t)1 * kUW + r) * 16) = z;
-                if (live) {
-                    *reinterpret_cast<uint4*>(gout_buf + (size_t)row * 16) = u0;
-                    *reinterpret_cast<uint4*>(gout_buf + (size_t)row * 16 + 8) = z;
+                if (live_tile) {  // tile-image layout, dead rows zero (u0 is zero for them)
+                    *reinterpret_cast<uint4*>(gout_buf + (((size_t)tile * 2 + 0) * kUW + r) * 8) = u0;
+                    *reinterpret_cast<uint4*>(gout_buf + (((size_t)tile * 2 + 1) * kUW + r) * 8) = z;
                 }
                 umma::fence_proxy_async();
                 umma::mbar_arrive(bar_aready + g);
             }
             const bool live = row < m_used;
-            const __half* hsave = fwd_buf + ((size_t)(l - 1) * M + row) * kUW;   // h_l: the activation that fed matmul l
-            __half* gsave = bwd_buf + ((size_t)(l - 1) * M + row) * kUW;         // G_{l-1}
+            // tile images (umma.cuh): chunk (column group c, row r) of tile t of layer j at (((j * tiles_cap + t) * 16 + c) * 128 + r) * 8
+            const __half* hsave = fwd_buf + ((((size_t)(l - 1) * tiles_cap + tile) * (kUW / 8)) * kUW + r) * 8;  // h_l: the activation that fed matmul l
+            __half* gsave = bwd_buf + ((((size_t)(l - 1) * tiles_cap + tile) * (kUW / 8)) * kUW + r) * 8;        // G_{l-1}
             uint4 hm[4];
             auto load_mask = [&](const int q) {
 #pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) hm[c4] = live ? __ldg(reinterpret_cast<const uint4*>(hsave + q * 32 + c4 * 8)) : make_uint4(0u, 0u, 0u, 0u);
+                for (int c4 = 0; c4 < 4; c4++)
+                    hm[c4] = live ? __ldg(reinterpret_cast<const uint4*>(hsave + (size_t)(q * 4 + c4) * kUW * 8)) : make_uint4(0u, 0u, 0u, 0u);
             };
             load_mask(0);  // in flight while the MMAs finish
             umma::mbar_wait(bar_mma + g, i & 1);
@@ -429,7 +443,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++) {
                     if (feeds_next) *reinterpret_cast<uint4*>(a_tile + ((size_t)(q * 4 + c4) * kUW + r) * 16) = out[c4];
-                    if (live) *reinterpret_cast<uint4*>(gsave + q * 32 + c4 * 8) = out[c4];
+                    if (live_tile) *reinterpret_cast<uint4*>(gsave + (size_t)(q * 4 + c4) * kUW * 8) = out[c4];  // (dead rows: mask 0 -> zeros)
                 }
             }
             umma::fence_before_sync();

@@ -86,22 +86,47 @@ class HalfWeights:
             _lib.call("seald_field_umma_pack_deform", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform), _lib.stream())
 
 
+WGRAD_IMPL = os.environ.get("SEALD_WGRAD_IMPL", "umma")  # "umma": tcgen05 kernel (csrc/wgrad_umma.cu); "mma": mma.sync kernel (field.cu)
+DEFORM_IMPL = os.environ.get("SEALD_DEFORM_IMPL", "umma")  # "umma": tcgen05 kernel (default); "mma": the mma.sync kernel of field.cu
+TILE_ROWS = 128
+
+
+def tile_image(x):
+    """[M, w] row-major fp16 -> the 128-row TILE-IMAGE layout the tcgen05 deformation kernels save their activations in
+    (csrc/field_umma.cu, csrc/wgrad_umma.cu): [tile][w / 8][128 rows][8 halves], returned as [ceil128(M), w] (rows beyond M zero)."""
+    M, w = x.shape
+    T = (M + TILE_ROWS - 1) // TILE_ROWS
+    xp = x.new_zeros(T * TILE_ROWS, w)
+    xp[:M] = x
+    return xp.view(T, TILE_ROWS, w // 8, 8).permute(0, 2, 1, 3).contiguous().view(T * TILE_ROWS, w)
+
+
+def from_tile_image(img, M=None):
+    """Inverse of tile_image: [ceil128(M), w] tile images -> [M, w] row-major."""
+    Mp, w = img.shape
+    out = img.view(Mp // TILE_ROWS, w // 8, TILE_ROWS, 8).permute(0, 2, 1, 3).contiguous().view(Mp, w)
+    return out if M is None else out[:M]
+
+
 class FieldWorkspace:
     def __init__(self, cfg, M, device, training=True):
         self.cfg, self.M, self.training = cfg, int(M), training
         f16 = dict(dtype=torch.float16, device=device)
         f32 = dict(dtype=torch.float32, device=device)
         M = self.M
+        # tcgen05 path: the deformation net's saved tensors hold whole 128-row tiles; the mma.sync kernels index [layer][M][width]
+        Mp = (M + TILE_ROWS - 1) // TILE_ROWS * TILE_ROWS if DEFORM_IMPL == "umma" else M
         self.deform = torch.empty(M, 3, **f32)
         self.x01 = torch.empty(M, 3, **f32)
         self.feat = torch.empty(M, HEAD_K0, **f16)
         self.sigma = torch.empty(M, **f32)
         self.rgb = torch.empty(M, 3, **f32)
         if training:
-            self.in_buf = torch.empty(M, DEFORM_K0, **f16)
-            self.fwd_d = torch.empty(cfg.n_deform - 1, M, DEFORM_W, **f16)
-            self.bwd_d = torch.empty(cfg.n_deform - 1, M, DEFORM_W, **f16)
-            self.gout_d = torch.empty(M, 16, **f16)
+            # tcgen05 path (DEFORM_IMPL "umma"): tile images (tile_image()); mma.sync path: row-major, first M rows
+            self.in_buf = torch.empty(Mp, DEFORM_K0, **f16)
+            self.fwd_d = torch.empty(cfg.n_deform - 1, Mp, DEFORM_W, **f16)
+            self.bwd_d = torch.empty(cfg.n_deform - 1, Mp, DEFORM_W, **f16)
+            self.gout_d = torch.empty(Mp, 16, **f16)
             self.hs = torch.empty(M, 16, **f16)
             self.cin = torch.empty(M, HEAD_K0, **f16)
             self.fwd_s = torch.empty(cfg.n_sigma - 1, M, HEAD_W, **f16)
@@ -112,10 +137,6 @@ class FieldWorkspace:
             self.gout_c = torch.empty(M, 16, **f16)
             self.dfeat = torch.empty(M, HEAD_K0, **f16)
             self.grad_x01 = torch.empty(M, 3, **f32)
-
-
-WGRAD_IMPL = os.environ.get("SEALD_WGRAD_IMPL", "umma")  # "umma": tcgen05 kernel (csrc/wgrad_umma.cu); "mma": mma.sync kernel (field.cu)
-DEFORM_IMPL = os.environ.get("SEALD_DEFORM_IMPL", "umma")  # "umma": tcgen05 kernel (default); "mma": the mma.sync kernel of field.cu
 
 
 def deform_forward(cfg, hw, xyzs, time_dev, M, m_dev, t0_mode, deform, x01, in_buf, fwd_buf):
@@ -168,12 +189,17 @@ def wgrad_jobs(cfg, ws, grads32, deform=True):
     jobs = []
     M = ws.M
     if deform:
+        # the tcgen05 deformation kernels save tile images: leading dimensions 0 tell the weight-gradient kernel (bulk-copy path)
+        tiled = DEFORM_IMPL == "umma"
+        if tiled and WGRAD_IMPL != "umma":
+            raise RuntimeError("SEALD_WGRAD_IMPL=mma reads row-major activations: use it with SEALD_DEFORM_IMPL=mma")
         for l in range(nd):
             last = l == nd - 1
             G = ws.gout_d if last else ws.bwd_d[l]
             A = ws.in_buf if l == 0 else ws.fwd_d[l - 1]
-            jobs.append(_job(G, A, gd[l], 16 if last else DEFORM_W, DEFORM_K0 if l == 0 else DEFORM_W, 16 if last else DEFORM_W,
-                             DEFORM_K0 if l == 0 else DEFORM_W, gd[l].shape[1], 3 if last else DEFORM_W, DEFORM_IN if l == 0 else DEFORM_W))
+            jobs.append(_job(G, A, gd[l], 16 if last else DEFORM_W, DEFORM_K0 if l == 0 else DEFORM_W, 0 if tiled else (16 if last else DEFORM_W),
+                             0 if tiled else (DEFORM_K0 if l == 0 else DEFORM_W), gd[l].shape[1], 3 if last else DEFORM_W,
+                             DEFORM_IN if l == 0 else DEFORM_W))
     for l in range(ns):
         last = l == ns - 1
         G = ws.gout_s if last else ws.bwd_s[l]

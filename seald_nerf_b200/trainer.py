@@ -326,11 +326,17 @@ class FusedTrainer:
     def _dataset_prologue(self):
         ds = self._ds
         self.inds.random_(0, ds["H"] * ds["W"])  # torch.randint(0, H*W, [N]) of get_rays (:95-97); philox state is graph-safe
+        n_launch = 2
+        if ds["C"] == 4:
+            # RGBA frames train against a fresh random background every step (dnerf/utils.py:68-73: bg_color = rand_like(rgb)); the
+            # gather kernel blends the target with bg[n] and the compositing kernel blends the prediction with the same row
+            self.bg.uniform_(0, 1)
+            n_launch = 3
         fx, fy, cx, cy = ds["intr"]
         _lib.call("seald_get_rays_gather", ptr(ds["poses"]), ptr(ds["times"]), ptr(ds["images"]), ptr(self.frame_dev), ptr(self.inds), self.N,
                   ds["H"], ds["W"], ds["C"], fx, fy, cx, cy, ptr(self.bg), ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt), ptr(self.time),
                   _lib.stream())
-        return 2
+        return n_launch
 
     def train_step_frame(self, frame, host_loss=False):
         """One step on N random pixels of training frame `frame` of the attached dataset: the host sends 4 bytes.  host_loss=True

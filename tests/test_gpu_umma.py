@@ -30,8 +30,9 @@ def _run(F, cfg, hw, xyz, tval, impl, save, m_live=None, t0_mode=1):
     M = xyz.shape[0]
     dev = xyz.device
     deform = torch.full((M, 3), 7.0, device=dev); x01 = torch.full((M, 3), 7.0, device=dev)
-    in_buf = torch.zeros(M, 80, dtype=torch.float16, device=dev) if save else None
-    fwd = torch.zeros(cfg.n_deform - 1, M, 128, dtype=torch.float16, device=dev) if save else None
+    Mp = (M + 127) // 128 * 128 if impl == "umma" else M  # the tcgen05 kernels save whole 128-row tile images (field.tile_image)
+    in_buf = torch.zeros(Mp, 80, dtype=torch.float16, device=dev) if save else None
+    fwd = torch.zeros(cfg.n_deform - 1, Mp, 128, dtype=torch.float16, device=dev) if save else None
     td = torch.tensor([tval], device=dev)
     m_dev = None if m_live is None else torch.tensor([m_live], dtype=torch.int32, device=dev)
     old = F.DEFORM_IMPL
@@ -41,6 +42,9 @@ def _run(F, cfg, hw, xyz, tval, impl, save, m_live=None, t0_mode=1):
     finally:
         F.DEFORM_IMPL = old
     torch.cuda.synchronize()
+    if save and impl == "umma":  # back to row-major for the comparisons
+        in_buf = F.from_tile_image(in_buf)
+        fwd = torch.stack([F.from_tile_image(f) for f in fwd])
     return deform, x01, in_buf, fwd
 
 
@@ -92,21 +96,34 @@ def test_umma_wgrad_matches_mma_sync(cuda_dev, M, m_live):
     cfg = net._field_cfg
     ws = F.FieldWorkspace(cfg, M, cuda_dev, training=True)
     g = torch.Generator(device=cuda_dev).manual_seed(1)
-    for name in ("in_buf", "fwd_d", "bwd_d", "gout_d", "hs", "cin", "fwd_s", "fwd_c", "bwd_s", "bwd_c", "gout_s", "gout_c", "feat"):
+    n_live = M if m_live is None else m_live
+    deform_bufs = ("in_buf", "fwd_d", "bwd_d", "gout_d")
+    rowmajor = {}
+    for name in deform_bufs + ("hs", "cin", "fwd_s", "fwd_c", "bwd_s", "bwd_c", "gout_s", "gout_c", "feat"):
         t = getattr(ws, name)
         t.copy_(torch.randn(t.shape, device=cuda_dev, generator=g).to(t.dtype))
+        if name in deform_bufs:  # rows beyond the live count are zero in the saved tile images
+            t[..., n_live:, :] = 0
+            rowmajor[name] = t.clone()
     m_dev = None if m_live is None else torch.tensor([m_live], dtype=torch.int32, device=cuda_dev)
     outs = []
     for impl in ("mma", "umma"):
+        # mma.sync kernel: row-major operands; tcgen05 kernel: the deformation net's operands as tile images (bulk-copy path)
+        for name in deform_bufs:
+            t, src = getattr(ws, name), rowmajor[name]
+            if impl == "umma":
+                t.copy_(F.tile_image(src) if src.dim() == 2 else torch.stack([F.tile_image(x) for x in src]))
+            else:
+                t.copy_(src)
         grads = [torch.zeros_like(w, dtype=torch.float32) for w in net.mlp_weights()]
-        jobs, n_jobs = F.wgrad_jobs(cfg, ws, grads, deform=True)
-        old = F.WGRAD_IMPL
-        F.WGRAD_IMPL = impl
+        old = F.WGRAD_IMPL, F.DEFORM_IMPL
+        F.WGRAD_IMPL = F.DEFORM_IMPL = impl
         try:
+            jobs, n_jobs = F.wgrad_jobs(cfg, ws, grads, deform=True)
             F.mlp_wgrad(jobs, n_jobs, M, m_dev)
             F.mlp_wgrad(jobs, n_jobs, M, m_dev)  # accumulates
         finally:
-            F.WGRAD_IMPL = old
+            F.WGRAD_IMPL, F.DEFORM_IMPL = old
         torch.cuda.synchronize()
         outs.append(grads)
     for a, b in zip(*outs):
@@ -124,22 +141,27 @@ def test_umma_deform_backward_matches_mma_sync(cuda_dev, M, m_live, tval):
     agree to fp16 round-off of each layer's output (accumulation order differs): <= 2^-8 relative on > 99.5% of entries
     and <= 2% of the layer maximum everywhere; dL/d(dx) (gout) bit-identical; zero at t == 0."""
     F, cfg, hw, xyz = _setup(cuda_dev, M)
-    _, _, in_buf, fwd = _run(F, cfg, hw, xyz, tval, "umma", True, m_live)
+    _, _, in_buf, fwd = _run(F, cfg, hw, xyz, tval, "umma", True, m_live)  # (row-major view of the saved tile images)
+    Mp = (M + 127) // 128 * 128
     g = torch.Generator(device=cuda_dev).manual_seed(5)
     grad_x01 = torch.randn(M, 3, device=cuda_dev, generator=g) * 64.0
     td = torch.tensor([tval], device=cuda_dev)
     m_dev = None if m_live is None else torch.tensor([m_live], dtype=torch.int32, device=cuda_dev)
     outs = []
     for impl in ("mma", "umma"):
-        bwd = torch.zeros(cfg.n_deform - 1, M, 128, dtype=torch.float16, device=cuda_dev)
-        gout = torch.zeros(M, 16, dtype=torch.float16, device=cuda_dev)
+        rows = Mp if impl == "umma" else M
+        bwd = torch.zeros(cfg.n_deform - 1, rows, 128, dtype=torch.float16, device=cuda_dev)
+        gout = torch.zeros(rows, 16, dtype=torch.float16, device=cuda_dev)
+        fwd_in = torch.stack([F.tile_image(f[:M]) for f in fwd]) if impl == "umma" else fwd[:, :M].contiguous()
         old = F.DEFORM_IMPL
         F.DEFORM_IMPL = impl
         try:
-            F.deform_backward(cfg, hw, grad_x01, td, M, m_dev, fwd, bwd, gout)
+            F.deform_backward(cfg, hw, grad_x01, td, M, m_dev, fwd_in, bwd, gout)
         finally:
             F.DEFORM_IMPL = old
         torch.cuda.synchronize()
+        if impl == "umma":
+            bwd, gout = torch.stack([F.from_tile_image(b) for b in bwd]), F.from_tile_image(gout)
         outs.append((bwd, gout))
     n = M if m_live is None else m_live
     assert torch.equal(outs[0][1][:n], outs[1][1][:n])
