@@ -322,6 +322,20 @@ def main():
         ms_e2e_ds = e0.elapsed_time(e1)
     trainer.flush()  # the table pass of the last step's optimiser is deferred into the next step: apply it before the model is rendered
     steps_run = trainer.global_step
+    # ---- replicas after all those steps: every rank must hold the same fp16 table and the same MLP weights (the fused exchange writes
+    # each shard's refreshed rows into every rank's table; a lost or torn broadcast would show here) -------------------------------------
+    dp_consistent = None
+    if world > 1:
+        trainer.sync_params()
+        torch.cuda.synchronize()
+        sums = torch.stack([trainer.table16.view(torch.int16).to(torch.int64).sum(), (trainer.table16.view(torch.int16).to(torch.int64)
+                            * (torch.arange(trainer.table16.numel(), device=device) % 65521).view_as(trainer.table16)).sum(),
+                            trainer.hw.flat.view(torch.int16).to(torch.int64).sum()])
+        allsums = [torch.zeros_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        dp_consistent = {"ok": bool(all(torch.equal(a, allsums[0]) for a in allsums)),
+                         "checksums_rank0": [int(v) for v in allsums[0].tolist()],
+                         "what": "position-weighted integer checksums of the fp16 hash table and of the fp16 MLP weights after all steps, equal on every rank"}
     clocks = sampler.stop(t_clk0, sampler.mark()) if rank == 0 else None
 
     # ---- full-frame render, ray tiles sharded over the ranks (configs[2]) ------------------------------------------------
@@ -446,6 +460,7 @@ def main():
         total_rays = N_RAYS * world
         ws_mb = (trainer.n_params * 18 + trainer.M * 4200) / 1e6
         line = {
+            "dp_consistent": dp_consistent,
             "metric": METRIC, "value": total_rays * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "dnerf_hashgrid_L16_T19_F2_deform8x128_train_step_4096rays_per_gpu (BASELINE configs[1])",

@@ -49,6 +49,55 @@ grad_ok = gt_err < 1e-3 and gw_err < 1e-3
 if rank == 0:
     print("one-step gradient: table max rel err %.2e, MLP weights %.2e  %s" % (gt_err, gw_err, "OK" if grad_ok else "MISMATCH"), flush=True)
 
+# ---- 1b. the FUSED exchange itself (k_dp_reduce_shard / k_dp_adam_shard_broadcast over peer memory), element by element: after one
+# step on the same batch this rank's `grad_shard` must be the single-GPU gradient slice, and after the shard's Adam the fp32 master copy
+# must equal single-GPU Adam wherever the gradient is above atomic-order noise (Adam's first step is lr * g / (|g| + eps): only the sign
+# of g matters, and the sign is noise where |g| is) ---------------------------------------------------------------------------------
+def one_step(world_size, **kw):
+    model = bench.build_scene(dev, seed=0)
+    tr = FusedTrainer(model, num_rays=4096, max_samples=4096 * 16, lr=1e-2, lr_net=1e-3, perturb=False, world_size=world_size, use_graph=False, **kw)
+    p0 = tr.params[:tr.n_table_pad].clone()
+    tr.train_step(ro[0], rd[0], ts[0], gt[0])
+    torch.cuda.synchronize()
+    return tr, p0
+
+
+fused_ok = True
+for variant, mc_reduce in (("peer loads", "0"), ("multimem.ld_reduce", "1")):
+    os.environ["SEALD_DP_MULTICAST_REDUCE"] = mc_reduce
+    tr_f, p0 = one_step(world, dp_mode="fused")
+    off, n_sh = tr_f.rank * tr_f.shard_len, tr_f.shard_len
+    g_ref = g_1[:ntp][off:off + n_sh]
+    gmax = float(g_1[:ntp].abs().max())
+    gshard = tr_f.grad_shard.clone()
+    shard_err = float((gshard - g_ref).abs().max()) / gmax
+    tr_f.sync_params()
+    torch.cuda.synchronize()
+    tr_s, _ = one_step(1)
+    tr_s.flush()
+    torch.cuda.synchronize()
+    pf, ps = tr_f.params[:ntp], tr_s.params[:ntp]
+    solid = g_1[:ntp].abs() > 1e-3 * gmax           # gradient entries far above the ~1e-5 * max atomic-order noise
+    untouched = g_1[:ntp] == 0
+    adam_err = float((pf - ps)[solid].abs().max()) / tr_f.lr
+    moved = float((pf - p0)[solid].abs().min()) / tr_f.lr
+    # (an entry whose single-GPU gradient cancels to exactly 0 can carry ~1e-8 of round-off in the two-rank sum: noise class, like above;
+    # "untouched" is judged on what this rank's own reduction delivered)
+    zero_own = gshard == 0
+    still = bool((pf[off:off + n_sh][zero_own] == p0[off:off + n_sh][zero_own]).all())
+    n_noise = int((untouched[off:off + n_sh] & ~zero_own).sum())
+    t16_ok = bool((tr_f.table16.reshape(-1)[:tr_f.n_table].float() == pf[:tr_f.n_table].half().float()).all())
+    good = shard_err < 5e-5 and adam_err < 1e-3 and moved > 0.5 and still and t16_ok
+    fused_ok &= good
+    if rank == 0:
+        print("fused exchange (%s): grad_shard vs single-GPU slice max err %.2e * max|g|; post-Adam fp32 master on %d solid entries: max diff %.2e * lr "
+              "(each moved >= %.2f * lr); zero-gradient entries untouched %s (%d entries exactly 0 on one GPU carry round-off here); fp16 table == half(master) on every row %s  %s"
+              % (variant, shard_err, int(solid.sum()), adam_err, moved, still, n_noise, t16_ok, "OK" if good else "MISMATCH"), flush=True)
+    del tr_f, tr_s
+    dist.barrier()
+os.environ["SEALD_DP_MULTICAST_REDUCE"] = "auto"
+grad_ok = grad_ok and fused_ok
+
 # ---- 2. K optimiser steps.  Adam normalises every entry's step, so an entry whose gradient is atomic-order noise around zero moves by
 # +-lr with a noise-chosen sign: the max over 12M entries is meaningless; compare the mean absolute difference and the loss. -----------
 results = {}
