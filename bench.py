@@ -154,16 +154,10 @@ def make_batches(n, device, rank, seed=0):
     return torch.stack(ro), torch.stack(rd), ts, torch.stack(gt)
 
 
-def seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=20):
-    """SealD proxy-distillation step (SealDNeRF/utils.py:40-43,579-657 + the student step): the frozen teacher renders the
-    batch through its Seal mapper (eval branch of SealNeRFTeacherRenderer.run_cuda), the student trains on that image."""
+def seald_mappers():
+    """The three edits of BASELINE configs[3], built from GUI-style configs by the package's own mapper construction."""
     import numpy as np
-    import torch
-    from seald_nerf_b200.trainer import FusedTrainer
-    from seald_nerf_b200.renderer_fused import FusedRenderer
-    from seald_nerf_b200.SealNeRF.seal_utils import SealBBoxMapper
-    teacher = build_scene(device, seed=0, seald=True)
-    teacher.eval()
+    from seald_nerf_b200.SealNeRF.seal_utils import get_seal_mapper
     # bbox tool: a 0.3^3 box on the torso, translated by +0.2 x and rotated 30 degrees about y (SURVEY.md config 4)
     c, h = np.array([0.0, 0.15, 0.0]), 0.15
     corners = np.array([[i, j, k] for i in (-1, 1) for j in (-1, 1) for k in (-1, 1)], np.float64) * h + c
@@ -171,35 +165,65 @@ def seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=20):
     T = np.eye(4)
     T[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
     T[:3, 3] = np.array([0.2, 0.0, 0.0]) + c - T[:3, :3] @ c
-    teacher.init_mapper(mapper=SealBBoxMapper("", {"type": "bbox", "raw": corners.tolist(), "transform": T.tolist(), "scale": [1, 1, 1],
-                                                   "boundType": "to", "hsv": [0.1, 0.0, 0.0]}))
+    out = {"bbox": get_seal_mapper("", {"type": "bbox", "raw": corners.tolist(), "transform": T.tolist(), "scale": [1, 1, 1], "boundType": "to",
+                                        "hsv": [0.1, 0.0, 0.0]})}
+    # brush tool: two line strokes on the figure's front (plane x = 0.12), raised by 0.02 along +x, affecting 0.6 pressures of depth
+    strokes = []
+    for k in range(2):
+        cc = np.array([0.12, 0.25 - 0.35 * k, 0.02 + 0.05 * k])
+        u = np.linspace(-1, 1, 12)
+        pts = [[0, p * 0.12, q * 0.05] for p in u for q in (-1, 1)] + [[0, q * 0.12, p * 0.05] for p in u for q in (-1, 1)] + \
+              [[0, p * 0.06, q * 0.02] for p in (-1, 0, 1) for q in (-1, 1)]
+        strokes.append((cc + np.array(pts)).tolist())
+    for mode, extra in (("dry", {"rgb": [1.0, 0.0, 0.0]}), ("linear", {})):
+        out["brush_" + mode] = get_seal_mapper("", dict({"type": "brush", "raw": strokes, "normal": [1, 0, 0], "brushType": "line", "brushDepth": 0.6,
+                                                         "brushPressure": 0.02, "attenuationDistance": 0.02, "attenuationMode": mode}, **extra))
+    return out
+
+
+def seald_step_bench(device, rank, world, rays_o, rays_d, times, m_need, K=20):
+    """SealD proxy-distillation step (SealDNeRF/utils.py:40-43,579-657 + the student step): the frozen teacher renders the
+    batch through its Seal mapper (eval branch of SealNeRFTeacherRenderer.run_cuda), the student trains on that image.  One
+    result per mapper of BASELINE configs[3]: bbox (headline), brush 'dry', brush 'linear'."""
+    import torch
+    from seald_nerf_b200.trainer import FusedTrainer
+    from seald_nerf_b200.renderer_fused import FusedRenderer
+    teacher = build_scene(device, seed=0, seald=True)
+    teacher.eval()
     student = build_scene(device, seed=1, seald=True)
     trainer = FusedTrainer(student, num_rays=N_RAYS, max_samples=m_need, lr=1e-2, lr_net=1e-3, train_deform=False, world_size=world)
-    fr = FusedRenderer(teacher, max_rays=N_RAYS)
     n = rays_o.shape[0]
+    res = {}
+    for kind, mapper in seald_mappers().items():
+        teacher.init_mapper(mapper=mapper)
+        fr = FusedRenderer(teacher, max_rays=N_RAYS)
 
-    def step(b):
-        out = fr.render_one_pass(rays_o[b], rays_d[b], times[b], T_thresh=1e-4)
-        trainer.train_step(rays_o[b], rays_d[b], times[b], torch.nan_to_num(out["image"]))
+        def step(b):
+            out = fr.render_one_pass(rays_o[b], rays_d[b], times[b], T_thresh=1e-4)
+            trainer.train_step(rays_o[b], rays_d[b], times[b], torch.nan_to_num(out["image"]))
 
-    for i in range(5):
-        step(i % n)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        step(i % n)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / K
-    e0.record()
-    for i in range(K):
-        fr.render_one_pass(rays_o[i % n], rays_d[i % n], times[i % n], T_thresh=1e-4)
-    e1.record()
-    torch.cuda.synchronize()
-    mask_count = int(fr.mask[:max(fr.samples, 1)].sum())  # mapped samples of the last teacher render
+        for i in range(5):
+            step(i % n)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            step(i % n)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        e0.record()
+        for i in range(K):
+            fr.render_one_pass(rays_o[i % n], rays_d[i % n], times[i % n], T_thresh=1e-4)
+        e1.record()
+        torch.cuda.synchronize()
+        mask_count = int(fr.mask[:max(fr.samples, 1)].sum())  # mapped samples of the last teacher render
+        res[kind] = {"ms_per_step": ms, "teacher_ms": e0.elapsed_time(e1) / K, "mapped_samples": mask_count, "teacher_iterations": fr.iterations}
+        del fr
     trainer.flush()  # (data parallel: also a rank barrier — no rank frees its symmetric buffers while a peer's kernels may still read them)
-    return {"ms_per_step": ms, "teacher_ms": e0.elapsed_time(e1) / K, "mapped_samples": mask_count, "teacher_iterations": fr.iterations}
+    out = dict(res["bbox"])
+    out["brush"] = {k[6:]: v for k, v in res.items() if k.startswith("brush_")}
+    return out
 
 
 def main():
@@ -487,7 +511,11 @@ def main():
                              "teacher_ms": seald["teacher_ms"], "mapped_samples": seald["mapped_samples"],
                              "teacher_iterations": seald["teacher_iterations"],
                              "workload": "teacher eval render of the 4096-ray batch in one pass (bbox mapper 0.3^3, +0.2x, 30deg about y, fused in "
-                                         "the march; FusedRenderer.render_one_pass) + student train step (frozen deform net)"}
+                                         "the march; FusedRenderer.render_one_pass) + student train step (frozen deform net)",
+                             "brush": {k: dict(v, value=N_RAYS * world / (v["ms_per_step"] * 1e-3), unit="rays/s (this rank's step time)")
+                                       for k, v in seald.get("brush", {}).items()},
+                             "brush_workload": "the same step with the brush tool (two line strokes, pressure 0.02, depth 0.6): 'dry' recolours, "
+                                               "'linear' pushes samples along the normal with border attenuation"}
         if occ:
             step_ms = ms / K
             line["occupancy_update"] = dict(occ, unit="wall ms per update_extra_state (64 time frames x 128^3 cells, sharded over the ranks, incl. its host syncs)",

@@ -349,6 +349,10 @@ int seald_select_frame(const float* time_dev, uint32_t T, const uint8_t* bitfiel
  * grad_image / grad_ws = d(loss_scale * mse)/d(image, ws). */
 int seald_mse_loss_bg(const float* image, const float* weights_sum, const float* bg, const float* gt, uint32_t N, float inv_count,
                       const float* loss_scale, float* pred, float* loss_sum, float* grad_image, float* grad_ws, seald_stream_t stream);
+/* Seal local pre-training loss (SealNeRF/trainer.py:448-462, pretrain_step): loss_sum += L1Loss(sigma, gt_sigma) +
+ * L1Loss(rgb, gt_rgb) ('mean' over M resp. 3M elements); grad_sigma [M] / grad_rgb [M,3] = d(loss_scale * loss)/d(sigma, rgb). */
+int seald_l1_pretrain_loss(const float* sigma, const float* rgb, const float* gt_sigma, const float* gt_rgb, uint32_t M,
+                           const float* loss_scale, float* loss_sum, float* grad_sigma, float* grad_rgb, seald_stream_t stream);
 /* dst[rows][ld] f16 = src[rows][cols] f32, zero padded columns. */
 int seald_cast_pad_f16(const float* src, void* dst, uint32_t rows, uint32_t cols, uint32_t ld, seald_stream_t stream);
 /* n matrices in one launch; src/dst/rows/cols/ld are HOST arrays of length n (<= 32). */

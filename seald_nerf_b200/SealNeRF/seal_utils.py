@@ -6,10 +6,12 @@ config_dict, config_file)` and the `map_data` / `map_triangles` / `map_test_dir`
 (SealDNeRF/renderer.py:52,157,252,272) — evaluated by the sm_100a kernels of csrc/seal.cu (stand-alone) and
 csrc/raymarch.cu (fused into the march, `march_rays_seal`).
 
-Scope: the per-sample runtime.  Mapper CONSTRUCTION from a GUI config needs trimesh's oriented
-bounding boxes / scikit-spatial planes / open3d simplification in the reference (seal_utils.py:168-242, 304-413,
-475-520); here a mapper is built either from the finished tensors (`from_tensors`, what the tests and benchmarks use)
-or — bbox tool only — from a config whose `raw` points are the 8 corners of a box, which needs no third-party code.
+Scope: the per-sample runtime and mapper CONSTRUCTION from a GUI edit config (§8 f4; seal_utils.py:168-242,
+304-413, 475-520).  The reference builds its boxes / planes / stroke meshes with trimesh, scikit-spatial, pytorch3d and open3d; here
+the same geometry comes from `mapper_build.py` (numpy / scipy: minimum-volume oriented box, least-squares plane, k-NN stroke mesh
+with vertex clustering), so `get_seal_mapper(config)` works for the bbox, brush ('line' and 'curve') and anchor tools without them.
+`from_tensors` builds a mapper from finished tensors (tests, benchmarks).  Nothing is written to `config_path` (the reference
+exports from.obj / to.obj there for its GUI).
 """
 import ctypes as C
 import json
@@ -20,6 +22,7 @@ import torch
 
 from .. import _lib
 from .._lib import ptr
+from . import mapper_build as mb
 
 _DEFAULT_TEST_DIR = (0.4395064455, 0.617598629942, 0.652231566745)  # seal_utils.py:686-688 (trimesh's magic direction)
 
@@ -198,7 +201,9 @@ class SealBBoxMapper(SealMapper):
         T = np.array(seal_config["transform"], np.float64)
         R = T[:3, :3]
         scale = np.array(seal_config["scale"], np.float64)
-        frm = _box_from_corners(np.array(seal_config["raw"], np.float64))
+        raw = np.array(seal_config["raw"], np.float64).reshape(-1, 3)
+        # get_trimesh_box (:595-596): the oriented bounding box of the raw points (8 box corners are taken as the box itself)
+        frm = _box_from_corners(raw) if raw.shape[0] == 8 else mb.oriented_box(raw)
         from_center = frm.mean(0)
         to = (frm - from_center) * scale + from_center
         to = to @ R.T + T[:3, 3]
@@ -212,11 +217,7 @@ class SealBBoxMapper(SealMapper):
             "pose_center": (from_center + to_center) / 2, "pose_radius": np.linalg.norm(from_center - to_center, 2) * 10,
             "transform": np.linalg.inv(T), "rotation": np.linalg.inv(R), "scale": 1 / scale, "center": from_center,
         }
-        if "hsv" in seal_config:
-            self.map_data["hsv"] = seal_config["hsv"]
-        if "rgb" in seal_config:
-            self.map_data["rgb"] = seal_config["rgb"]
-            self.map_data["rgb_light_offset"] = seal_config.get("rgbLightOffset", 0)
+        _color_entries(self.map_data, seal_config)
         if seal_config.get("mapSource"):
             self.map_data["empty_bound"] = np.stack([frm.min(0), frm.max(0)])
             self.map_data["map_source"] = seal_config["mapSource"]
@@ -238,8 +239,46 @@ class SealBrushMapper(SealMapper):
     TYPE_ID = 1
 
     def __init__(self, config_path, seal_config):
-        raise NotImplementedError("building a brush mapper from a GUI config needs trimesh / scikit-spatial (mapper construction is outside "
-                                  "the hot path, SURVEY.md §8f); use SealBrushMapper.from_tensors(map_data, map_triangles, map_test_dir)")
+        # seal_utils.py:304-413.  raw: [N,3] stroke points or a list of strokes; normal: which side of the stroke plane is "up";
+        # brushType 'line' | 'curve' (per stroke or one for all); brushPressure / brushDepth / attenuationDistance / attenuationMode.
+        super().__init__(seal_config)
+        strokes = seal_config["raw"]
+        if np.asarray(strokes[0]).ndim == 1:
+            strokes = [strokes]
+        kinds = seal_config["brushType"]
+        if isinstance(kinds, str):
+            kinds = [kinds] * len(strokes)
+        tris, bounds, border = [], [], []
+        for pts, kind in zip(strokes, kinds):
+            pts = np.asarray(pts, np.float64).reshape(-1, 3)
+            point, normal = mb.plane_best_fit(pts)
+            if "normal" in seal_config and normal @ np.asarray(seal_config["normal"], np.float64) < 0:
+                normal = -normal
+            normal_expand = normal * seal_config["brushPressure"]
+            projected = mb.project_points(normal, point, pts)
+            if kind == "line":   # box around the stroke pushed +2 and -brushDepth pressures along the normal
+                t = mb.box_triangles(mb.oriented_box(np.vstack([pts + 2 * normal_expand, pts - seal_config["brushDepth"] * normal_expand])))
+            else:                # smooth sheet through the projected stroke points
+                t = mb.fit_curve_mesh(projected, normal_expand, (-seal_config["brushDepth"], 2), seal_config.get("simplifyVoxel", 16))
+            tris.append(t)
+            v = t.reshape(-1, 3)
+            bounds.append(np.stack([v.min(0), v.max(0)]))
+            border.append(projected[mb.surface_points_mask(t.astype(np.float32).astype(np.float64), projected)])
+        self.map_triangles = torch.as_tensor(np.concatenate(tris, 0).astype(np.float32))
+        self.map_test_dir = torch.as_tensor(normal_expand[None].astype(np.float32))  # (from the last stroke, like the reference)
+        self.map_data = {
+            "force_fill_bound": np.stack(bounds), "map_bound": np.stack(bounds), "normal_expand": normal_expand, "center": point,
+            "border_points": np.concatenate(border, 0), "attenuation_distance": seal_config["attenuationDistance"],
+            "attenuation_mode": seal_config["attenuationMode"],
+        }
+        _color_entries(self.map_data, seal_config)
+        if "imageConfig" in seal_config:
+            ic = seal_config["imageConfig"]
+            self.map_data["rgb_light_offset"] = seal_config.get("rgbLightOffset", 0)
+            image, alpha = _read_image(ic["path"])
+            v_o, v_w, v_h = (np.asarray(ic[k], np.float64) for k in ("o", "w", "h"))
+            self.map_data.update(image=image, image_mask=alpha, v_image_norm=mb.plane_best_fit([v_o, v_w, v_h])[1], v_image_o=v_o,
+                                 v_image_w=v_w, v_image_h=v_h)
 
     def _fill_type(self, d, device, keep):
         md = self.map_data
@@ -261,8 +300,27 @@ class SealAnchorMapper(SealMapper):
     TYPE_ID = 2
 
     def __init__(self, config_path, seal_config):
-        raise NotImplementedError("building an anchor mapper from a GUI config needs trimesh / scikit-spatial; use "
-                                  "SealAnchorMapper.from_tensors(map_data, map_triangles)")
+        # seal_utils.py:475-520.  raw: [N,3] points of the anchor plane; translation [3]; radius; scale [3].
+        super().__init__(seal_config)
+        raw = np.asarray(seal_config["raw"], np.float64).reshape(-1, 3)
+        v_translation = np.asarray(seal_config["translation"], np.float64)
+        v_anchor = raw.mean(0)
+        radius = seal_config["radius"]
+        point, normal = mb.plane_best_fit(raw)
+        v_translated = v_anchor + v_translation
+        v_projected = mb.project_points(normal, point, v_translated[None])[0]
+        v_offset = v_projected - v_anchor
+        v_h = v_projected - v_translated
+        sphere = mb.uv_sphere_vertices(radius * 1.1) + v_anchor
+        box = mb.oriented_box(np.vstack([sphere, v_anchor + 1.1 * v_translation, sphere - 0.1 * v_translation]))
+        self.map_triangles = torch.as_tensor(mb.box_triangles(box).astype(np.float32))
+        bounds = np.stack([box.min(0), box.max(0)])
+        self.map_data = {
+            "force_fill_bound": bounds, "map_bound": bounds, "pose_center": box.mean(0), "pose_radius": np.linalg.norm(v_translation, 2) * 10,
+            "v_anchor": v_anchor, "v_offset": v_offset, "v_h": v_h, "len_h": np.linalg.norm(v_h, 2), "radius": radius,
+            "scale": seal_config["scale"], "map_source": True,  # (the reference's workaround: keeps every local pre-training point)
+        }
+        _color_entries(self.map_data, seal_config)
 
     def _fill_type(self, d, device, keep):
         md = self.map_data
@@ -286,17 +344,32 @@ def get_seal_mapper(config_path, config_dict=None, config_file="seal.json"):
     raise NotImplementedError()
 
 
+def _color_entries(map_data, seal_config):
+    if "hsv" in seal_config:
+        map_data["hsv"] = seal_config["hsv"]
+    if "rgb" in seal_config:
+        map_data["rgb"] = seal_config["rgb"]
+        map_data["rgb_light_offset"] = seal_config.get("rgbLightOffset", 0)
+
+
+def _read_image(path):
+    """RGB float image in [0,1] + alpha mask (the reference reads it with cv2, seal_utils.py:389-399)."""
+    from PIL import Image
+    im = Image.open(path)
+    has_alpha = im.mode in ("RGBA", "LA") or "transparency" in im.info
+    a = np.asarray(im.convert("RGBA"), np.float32) / 255
+    return a[:, :, :3].copy(), (a[:, :, 3].astype(np.float64) if has_alpha else np.ones(a.shape[:2]))
+
+
 # ---- box helpers ---------------------------------------------------------------------------------------------------------
-_BOX_FACES = np.array([[0, 1, 3], [0, 3, 2], [4, 7, 5], [4, 6, 7], [0, 5, 1], [0, 4, 5], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4],
-                       [1, 5, 7], [1, 7, 3]])
+_BOX_FACES = mb.BOX_FACES
 
 
 def _box_from_corners(raw):
     """Order the 8 corners of an (oriented) box as (-,-,-), (-,-,+), (-,+,-) ... (+,+,+) in its own frame."""
     raw = np.asarray(raw, np.float64).reshape(-1, 3)
     if raw.shape[0] != 8:
-        raise NotImplementedError("bbox mapper from %d raw points: only the 8 corners of a box are supported without trimesh "
-                                  "(the reference fits an oriented bounding box with trimesh, seal_utils.py:595-596)" % raw.shape[0])
+        return mb.oriented_box(raw)
     v = raw[1:] - raw[0]
     far = int(np.argmax((v ** 2).sum(1)))
     best = None

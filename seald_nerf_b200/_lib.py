@@ -62,6 +62,7 @@ _SIGS = {
     "seald_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp],
     "seald_select_frame": [_vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp],
     "seald_mse_loss_bg": [_vp, _vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_l1_pretrain_loss": [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp],
     "seald_cast_pad_f16": [_vp, _vp, _u32, _u32, _u32, _vp],
     "seald_cast_pad_f16_batch": [_vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "seald_dp_reduce_shard": [_vp, _vp, _i32, C.c_uint64, C.c_uint64, _vp, _vp],

@@ -43,6 +43,39 @@ __global__ void k_mse_loss_bg(const float* __restrict__ image, const float* __re
     }
 }
 
+// Seal local pre-training loss (SealNeRF/trainer.py:448-462): L1Loss(sigma, gt_sigma) + L1Loss(rgb, gt_rgb), both 'mean' reductions
+// (over M resp. 3M elements); loss_sum += the loss, grads of loss_scale * loss (sign(0) = 0 like torch's l1_loss backward).
+__global__ void k_l1_pretrain_loss(const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ gt_sigma,
+                                   const float* __restrict__ gt_rgb, const uint32_t M, const float* __restrict__ loss_scale,
+                                   float* __restrict__ loss_sum, float* __restrict__ grad_sigma, float* __restrict__ grad_rgb) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    const float inv_s = 1.0f / (float)M, inv_c = 1.0f / (3.0f * (float)M);
+    float local = 0.0f;
+    if (n < M) {
+        const float scale = loss_scale ? *loss_scale : 1.0f;
+        const float ds = sigma[n] - gt_sigma[n];
+        local += fabsf(ds) * inv_s;
+        grad_sigma[n] = (ds > 0.0f ? 1.0f : (ds < 0.0f ? -1.0f : 0.0f)) * inv_s * scale;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float dc = rgb[(size_t)n * 3 + c] - gt_rgb[(size_t)n * 3 + c];
+            local += fabsf(dc) * inv_c;
+            grad_rgb[(size_t)n * 3 + c] = (dc > 0.0f ? 1.0f : (dc < 0.0f ? -1.0f : 0.0f)) * inv_c * scale;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ float s_part[32];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+    }
+}
+
 __global__ void k_cast_pad_f16(const float* __restrict__ src, __half* __restrict__ dst, const uint32_t rows, const uint32_t cols,
                                const uint32_t ld) {
     const size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x;
@@ -245,6 +278,14 @@ extern "C" int seald_mse_loss_bg(const float* image, const float* weights_sum, c
     if (!image || !weights_sum || !gt || !loss_sum || !grad_image || !grad_ws) return SEALD_E_BADARG;
     k_mse_loss_bg<<<div_up(N, 256u), 256, 0, to_stream(stream)>>>(image, weights_sum, bg, gt, N, inv_count, loss_scale, pred, loss_sum, grad_image,
                                                                  grad_ws);
+    return launch_status();
+}
+
+extern "C" int seald_l1_pretrain_loss(const float* sigma, const float* rgb, const float* gt_sigma, const float* gt_rgb, uint32_t M,
+                                      const float* loss_scale, float* loss_sum, float* grad_sigma, float* grad_rgb, seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!sigma || !rgb || !gt_sigma || !gt_rgb || !loss_sum || !grad_sigma || !grad_rgb) return SEALD_E_BADARG;
+    k_l1_pretrain_loss<<<div_up(M, 256u), 256, 0, to_stream(stream)>>>(sigma, rgb, gt_sigma, gt_rgb, M, loss_scale, loss_sum, grad_sigma, grad_rgb);
     return launch_status();
 }
 

@@ -670,6 +670,64 @@ class FusedTrainer:
                   self.growth_interval, ptr(self.step_dev), ptr(self.pending), st)
         return n
 
+    def pretrain_step(self, points, dirs, gt_sigma, gt_color, time, lr=0.07, optimize=True):
+        """One step of Seal's local pre-training (SealNeRF/trainer.py:396-462 pretrain_part / pretrain_step; data from
+        SealDNeRF/utils.py:386-562): the student field is evaluated at `points` [B,3] / `dirs` [B,3] of time stamp `time` and pulled
+        towards the teacher's (gt_sigma [B], gt_color [B,3]) with L1Loss(sigma) + L1Loss(colour); every MLP is frozen (freeze_mlp,
+        SealDNeRF/utils.py:365-376; the student's deformation net is frozen for the whole SealD run), so the only gradient is the hash
+        table's.  GradScaler.scale(loss).backward() -> scaler.step(optimizer) with every group's lr = `lr` (set_lr, :564-577) ->
+        scaler.update(), as device kernels on the trainer's own Adam state: deformation forward (tcgen05, nothing saved) -> grid
+        forward -> heads forward -> L1 loss + seeds -> heads backward (input gradient only) -> table scatter -> Adam on the table.
+        Returns nothing; `self.loss` holds the loss.  optimize=False stops after the backward pass (gradients stay in self.grad_table,
+        tests).  (One step counter serves all groups here: frozen weights keep torch's per-parameter `step`, which only matters
+        for Adam's bias correction during the first few hundred steps of a run.)"""
+        if self.world_size > 1:
+            raise NotImplementedError("Seal pre-training runs the same batch on every replica in the reference; use one GPU")
+        m, cfg, ws, hw = self.model, self.cfg, self.ws, self.hw
+        B = int(points.shape[0])
+        if B == 0:
+            return
+        if B > self.M:
+            raise ValueError("pre-training batch of %d points exceeds the trainer's sample capacity %d" % (B, self.M))
+        _lib.require_cuda(points, dirs, gt_sigma, gt_color)
+        self.flush()  # a pending table pass of the last training step comes first
+        pts, drs = points.detach().float().contiguous(), dirs.detach().float().contiguous()
+        gs, gc = gt_sigma.detach().float().contiguous().view(-1), gt_color.detach().float().contiguous().view(-1, 3)
+        if torch.is_tensor(time):
+            self.time.copy_(time.reshape(-1)[:1])
+        else:
+            self.time.fill_(float(time))
+        st = _lib.stream()
+        offsets = m.encoder.offsets
+        F16, F32 = _lib.F16, _lib.F32
+        F.deform_forward(cfg, hw, pts, self.time, B, None, 1, ws.deform, ws.x01, None, None)
+        _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(self.table16), ptr(offsets), ptr(ws.feat), None, B, 3, cfg.grid_dim,
+                  cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, None, st)
+        _lib.call("seald_field_heads_forward", ptr(ws.feat), ptr(drs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, B, None,
+                  cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs), ptr(ws.cin), ptr(ws.fwd_s), ptr(ws.fwd_c), st)
+        self.loss.zero_()
+        _lib.call("seald_l1_pretrain_loss", ptr(ws.sigma), ptr(ws.rgb), ptr(gs), ptr(gc), B, ptr(self.loss_scale), ptr(self.loss),
+                  ptr(self.grad_sigma), ptr(self.grad_rgb), st)
+        _lib.call("seald_field_heads_backward", ptr(self.grad_sigma), ptr(self.grad_rgb), ptr(ws.rgb), ptr(ws.hs), hw.p_sigma, cfg.n_sigma,
+                  hw.p_color, cfg.n_color, B, None, cfg.density_scale, ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.bwd_s), ptr(ws.bwd_c),
+                  ptr(ws.gout_s), ptr(ws.gout_c), ptr(ws.dfeat), st)
+        _lib.call("seald_grid_encode_backward_table", ptr(ws.dfeat), ptr(ws.x01), ptr(offsets), ptr(self.grad_table), B, 3, cfg.grid_dim,
+                  cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, F32, None,
+                  ptr(self.found_inf), st)
+        if optimize:
+            self._pretrain_optimize(lr)
+
+    def _pretrain_optimize(self, lr):
+        """scaler.step(optimizer) + scaler.update() of a pre-training step: Adam on the hash table only (the MLP groups are frozen)."""
+        st = _lib.stream()
+        b1, b2 = self.betas
+        _lib.call("seald_adam_step_lr", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n_table_pad,
+                  float(lr), None, b1, b2, self.eps, 1, ptr(self.step_dev), ptr(self.loss_scale), ptr(self.found_inf), ptr(self.table16_pad),
+                  1, 0, st)
+        _lib.call("seald_loss_scale_update", ptr(self.loss_scale), ptr(self.found_inf), ptr(self.growth_tracker), 2.0, 0.5,
+                  self.growth_interval, ptr(self.step_dev), st)
+        self.global_step += 1
+
     def flush(self):
         """Apply the deferred hash-table update of the last step now (parameters are about to be read: evaluation, checkpoint)."""
         if self.defer_table_update:

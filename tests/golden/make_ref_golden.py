@@ -4,7 +4,7 @@ B200, print how far apart they are per case, and write the reference's outputs a
     python tests/golden/make_ref_golden.py [out_dir=gpurun_out/golden_ref] [case ...]      (on the GPU box)
 
 then copy the *.npz into tests/golden/.  tests/test_gpu_ref_parity.py holds the tolerances; this script is where they were
-calibrated (it prints max-abs / relative-L2 / 99.9th-percentile differences).  Cases: field train frame occupancy ffmlp teacher.
+calibrated (it prints max-abs / relative-L2 / 99.9th-percentile differences).  Cases: field train pretrain frame occupancy ffmlp teacher.
 """
 import json
 import os
@@ -60,7 +60,7 @@ def small(res, case):
 
 def main():
     out_dir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden_ref")
-    which = sys.argv[2:] or ["field", "train", "frame", "occupancy", "teacher", "ffmlp"]
+    which = sys.argv[2:] or ["field", "train", "pretrain", "frame", "occupancy", "teacher", "ffmlp"]
     os.makedirs(out_dir, exist_ok=True)
     dev = torch.device("cuda:0")
 
@@ -87,6 +87,16 @@ def main():
         report("train", o, r)
         print(json.dumps({"train_loss": [float(o["loss"]), float(r["loss"])], "samples": [int(o["samples"]), int(r["samples"])]}), flush=True)
         np.savez_compressed(os.path.join(out_dir, "ref_train.npz"), **r)
+    if "pretrain" in which:
+        so = rc.ours_model(dev, seald=True)
+        sr = rc.ref_model(so, seald=True)
+        r, o = rc.ref_pretrain(sr, dev), rc.ours_pretrain(so, dev)
+        report("pretrain", o, r)
+        solid = np.abs(r["grad_table_head"]) > 1e-2 * np.abs(r["grad_table_head"]).max()
+        same = np.abs(o["table_after_head"] - r["table_after_head"])[solid] < 1e-3 * rc.PRETRAIN_LR
+        print(json.dumps({"pretrain_loss": [float(o["loss"]), float(r["loss"])], "solid_entries": int(solid.sum()), "same_update_frac": float(same.mean())}), flush=True)
+        np.savez_compressed(os.path.join(out_dir, "ref_pretrain.npz"), **r)
+        del so, sr
     if "frame" in which:
         for tag, T in (("", None),):
             r, o = rc.ref_frame(ref, dev, T_thresh=T), rc.ours_frame(ours, dev, T_thresh=T)

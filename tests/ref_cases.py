@@ -139,6 +139,73 @@ def ours_train(ours, dev):
     return res
 
 
+# ---- f4: one step of Seal's local pre-training (SealNeRF/trainer.py:396-462) on the D-NeRF student --------------------------------
+PRETRAIN_LR = 0.07  # init_pretraining default (SealDNeRF/utils.py:386)
+
+
+def pretrain_batch(dev, n=4096, seed=13):
+    """Lattice-free stand-in for a slice of pretraining_data: points inside an edited box, unit view directions, teacher labels."""
+    g = torch.Generator().manual_seed(seed)
+    pts = (torch.rand(n, 3, generator=g) * 0.6 - 0.3).to(dev)
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(dev)
+    gt_sigma = (torch.rand(n, generator=g) * 40.0).to(dev)
+    gt_color = torch.rand(n, 3, generator=g).to(dev)
+    return pts, dirs, gt_sigma, gt_color, 0.37
+
+
+def _pretrain_result(loss, gtable, offsets, table_after):
+    head, lv = _grad_summary(gtable, offsets)
+    return {"loss": np.float64(loss), "grad_table_head": head, "grad_table_levels": lv, "table_after_head": np_(table_after[:TABLE_ROWS_KEPT])}
+
+
+def ref_pretrain(ref, dev):
+    """pretrain_step's arithmetic on the reference network: L1Loss(sigma) + L1Loss(colour) under autocast, scaled backward, MLPs
+    frozen (freeze_mlp; the SealD student's deformation net is frozen too), torch.optim.Adam on the table at the pre-training lr."""
+    pts, dirs, gs, gc, t = pretrain_batch(dev)
+    ref.train()
+    ref.zero_grad(set_to_none=True)
+    saved = ref.encoder.embeddings.detach().clone()
+    for n_, p in ref.named_parameters():
+        p.requires_grad_(n_ == "encoder.embeddings")
+    tt = torch.tensor([[t]], dtype=torch.float32, device=dev)
+    l1 = torch.nn.L1Loss()
+    with torch.autocast(**AUTOCAST):
+        out = ref(pts, dirs, tt)
+        loss = l1(out[1], gc) * 1 + l1(out[0], gs)
+    (loss * LOSS_SCALE).backward()
+    g = ref.encoder.embeddings.grad / LOSS_SCALE       # scaler.unscale_
+    opt = torch.optim.Adam([ref.encoder.embeddings], lr=PRETRAIN_LR, betas=(0.9, 0.99), eps=1e-15)
+    ref.encoder.embeddings.grad = g.to(ref.encoder.embeddings.dtype)
+    opt.step()
+    res = _pretrain_result(loss.item(), g, ref.encoder.offsets, ref.encoder.embeddings)
+    with torch.no_grad():
+        ref.encoder.embeddings.copy_(saved)
+    for p in ref.parameters():
+        p.requires_grad_(True)
+    ref.zero_grad(set_to_none=True)
+    return res
+
+
+def ours_pretrain(ours, dev):
+    from seald_nerf_b200.trainer import FusedTrainer
+    pts, dirs, gs, gc, t = pretrain_batch(dev)
+    ours.train()
+    saved = ours.encoder.embeddings.detach().clone()
+    tr = FusedTrainer(ours, num_rays=1024, max_samples=pts.shape[0], use_graph=False, perturb=False, init_loss_scale=LOSS_SCALE, train_deform=False)
+    tr.grads.zero_()
+    tr.pretrain_step(pts, dirs, gs, gc, t, lr=PRETRAIN_LR, optimize=False)
+    torch.cuda.synchronize()
+    g = (tr.grad_table / LOSS_SCALE).clone()
+    loss = float(tr.loss.item())
+    tr._pretrain_optimize(PRETRAIN_LR)
+    torch.cuda.synchronize()
+    res = _pretrain_result(loss, g, ours.encoder.offsets, tr.params[:tr.n_table].view_as(ours.encoder.embeddings))
+    res["table16_is_half_of_master"] = np.bool_(bool((tr.table16.reshape(-1)[:tr.n_table].float() == tr.params[:tr.n_table].half().float()).all()))
+    with torch.no_grad():
+        ours.encoder.embeddings.copy_(saved)
+    return res
+
+
 # ---- a17 eval branch: a whole 800x800 frame through the round loop --------------------------------------------------------------
 FRAME_STRIDE = 16  # fixture keeps every 16th ray
 

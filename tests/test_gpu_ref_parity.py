@@ -147,6 +147,27 @@ def test_seald_teacher_render_vs_reference(cuda_dev, kind):
         np.testing.assert_allclose(o["depth"], r["depth"], rtol=0, atol=1e-4)   # measured <= 8.3e-6 (SealD: depth not normalised)
 
 
+def test_seal_pretrain_step_vs_reference(cuda_dev):
+    """f4: one step of Seal's local pre-training — L1Loss(sigma) + L1Loss(colour) of the student field at labelled points, scaled
+    backward with every MLP frozen, Adam on the table at the pre-training lr (SealNeRF/trainer.py:396-462) — on the reference's
+    network / autograd wrappers / torch.optim.Adam vs FusedTrainer.pretrain_step."""
+    import ref_cases as rc
+    ours, ref = _models(cuda_dev, seald=True)
+    r, _ = _reference("pretrain", lambda: rc.ref_pretrain(ref, cuda_dev))
+    o = rc.ours_pretrain(ours, cuda_dev)
+    assert abs(float(o["loss"]) - float(r["loss"])) <= 1e-3 * float(r["loss"])
+    assert rel_l2(o["grad_table_levels"][:, 1], r["grad_table_levels"][:, 1]) <= 2e-2   # per-level L2 norms of the table gradient
+    assert rel_l2(o["grad_table_head"], r["grad_table_head"]) <= 8e-2                   # rows of the dense levels (fp16 atomics in the reference)
+    # Adam's first step is lr * g / (|g| + 1e-15): wherever the gradient is well above the fp16-atomic noise both sides move the
+    # entry by the same +-lr; entries nobody touched stay put
+    solid = np.abs(r["grad_table_head"]) > 1e-2 * np.abs(r["grad_table_head"]).max()
+    same = np.abs(o["table_after_head"] - r["table_after_head"])[solid] < 1e-3 * rc.PRETRAIN_LR
+    assert int(solid.sum()) > 1000 and float(same.mean()) >= 0.999
+    idle = (r["grad_table_head"] == 0) & (o["grad_table_head"] == 0)
+    assert np.array_equal(o["table_after_head"][idle], r["table_after_head"][idle])
+    assert bool(o["table16_is_half_of_master"])
+
+
 def _ffmlp_reference_live(out_dir):
     """The reference's ffmlp extension (Sm70-tagged CUTLASS GEMMs recompiled for sm_100a) in its own process."""
     p = subprocess.run([sys.executable, os.path.join(GOLDEN, "make_ref_golden.py"), out_dir, "ffmlp_ref_child"], capture_output=True, text=True,

@@ -163,3 +163,73 @@ def test_teacher_render_with_mapper(cuda_dev, kind):
     with torch.no_grad():
         plain = net.render(ro[None], rd[None], time, perturb=False, force_all_rays=True)
     assert float((plain["image"] - out["image"]).abs().max()) > 1e-3
+
+
+def test_seal_pretrainer_builds_point_sets_and_fits_the_table(cuda_dev):
+    """f4 (SealDNeRF/utils.py:386-562 + SealNeRF/trainer.py:363-462): the three pre-training sets of a bbox edit — local points are
+    exactly the lattice points the mapping moves (labels = teacher at the mapped point, colours through map_color), surrounding /
+    global points are the ones it leaves alone — and a few epochs of the fused pre-training step pull the student's field towards
+    the labels with every MLP untouched."""
+    sys.path.insert(0, HERE)
+    import ref_cases as rc
+    from seald_nerf_b200.SealDNeRF.pretrain import SealPretrainer
+    from seald_nerf_b200.trainer import FusedTrainer
+    teacher = rc.ours_model(cuda_dev, seald=True)
+    mapper = seal_mapper_from_dict(rc.seal_mapper_dict("bbox"))
+    teacher.init_mapper(mapper=mapper)
+    student = rc.ours_model(cuda_dev, seald=True)
+    student.init_mapper(mapper=mapper)
+    tr = FusedTrainer(student, num_rays=1024, max_samples=8192, use_graph=False, train_deform=False, init_loss_scale=1024.0)
+    w_before = [w.detach().clone() for w in student.mlp_weights()]
+    pt = SealPretrainer(tr, teacher)
+    t_edit = 0.3
+    pt.init_pretraining(t_edit, epochs=4, batch_size=4096, lr=0.02, local_point_step=0.02, surrounding_point_step=0.05, global_point_step=0.25)
+    data = pt.pretraining_data
+    assert set(data) == {"local", "surrounding", "global"}
+    for k, d in data.items():
+        n = d["points"].shape[0]
+        assert n > 0 and d["dirs"].shape == (n, 3) and d["sigma"].shape == (n,) and d["color"].shape == (n, 3)
+        assert d["steps"][0] == 0 and d["steps"][-1] == n and all(b - a <= 4096 for a, b in zip(d["steps"], d["steps"][1:]))
+        assert bool(torch.isfinite(d["sigma"]).all()) and bool(torch.isfinite(d["color"]).all())
+        moved = mapper.map_mask(d["points"])
+        assert bool(moved.all()) if k == "local" else not bool(moved.any())
+    # local labels: the teacher evaluated at the mapped points
+    p, dirs = data["local"]["points"][:512], data["local"]["dirs"][:512]
+    mp, md, _ = mapper.map_to_origin(p, torch.zeros_like(p) + torch.tensor([1.0, 0.0, 0.0], device=cuda_dev))
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        s_t, c_t, _ = teacher(mp, md, torch.tensor([[t_edit]], device=cuda_dev))
+    torch.testing.assert_close(data["local"]["sigma"][:512], s_t.float().reshape(-1), rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(data["local"]["color"][:512], mapper.map_color(mp, md, c_t.float()), rtol=0, atol=2e-3)
+    losses = [pt.pretrain_one_epoch()["local"] for _ in range(4)]
+    torch.cuda.synchronize()
+    assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0], losses
+    for a, b in zip(w_before, student.mlp_weights()):
+        assert torch.equal(a, b.detach()), "pre-training must not touch the MLPs (freeze_mlp)"
+    assert 0 < int(tr.step_dev) <= 4 * pt.local_step  # one optimiser step per slice, minus the ones GradScaler skipped
+
+
+def _oracle_dict(mapper, kind):
+    """A constructed seal_utils mapper as the dict oracle/seal.py evaluates."""
+    d = {"type": kind, "map_triangles": mapper.map_triangles.numpy(), "map_test_dir": None if mapper.map_test_dir is None else mapper.map_test_dir.numpy()}
+    for k, v in mapper.map_data.items():
+        d[k] = np.asarray(v, np.float32) if not isinstance(v, (str, bool)) else v
+    return d
+
+
+@pytest.mark.parametrize("mode", ["dry", "linear"])
+def test_brush_mapper_built_from_config_runs_like_the_oracle(cuda_dev, mode):
+    """f4 mapper construction -> a18 runtime: a brush mapper built from a GUI-style config (get_seal_mapper) through the CUDA mapping
+    vs oracle/seal.py evaluating the same tensors (oracle pinned to the reference's seal_utils.py by test_oracle_seal.py)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+    from oracle import seal as S
+    m = bench.seald_mappers()["brush_" + mode]
+    od = _oracle_dict(m, "brush")
+    rng = np.random.default_rng(7)
+    pts = (np.array([0.13, 0.08, 0.05]) + (rng.random((20000, 3)) * 2 - 1) * [0.05, 0.4, 0.12]).astype(np.float32)
+    dirs = rng.normal(size=(20000, 3)).astype(np.float32)
+    p, d, mask = m.map_to_origin(torch.from_numpy(pts).to(cuda_dev), torch.from_numpy(dirs).to(cuda_dev))
+    po, do_, mo = S.map_to_origin(od, pts, dirs)
+    assert 0.05 < mo.mean() < 0.9
+    assert np.array_equal(mask.cpu().numpy(), mo)
+    np.testing.assert_allclose(p.cpu().numpy(), po, rtol=1e-5, atol=2e-5)
