@@ -445,8 +445,10 @@ int seald_dp_adam_shard_broadcast(void* const* peer_table16, void* mc_table16, i
 /* ------------------------------------------------------------------------------------------------
  * Occupancy-grid refresh on the device (NeRFRenderer.update_extra_state, dnerf/renderer.py:453-555).
  *   seald_occ_cell_points  sample point of cell j: (2 c / (H-1) - 1) * span + (rand * 2 - 1) * half_cell in the reference's fp32
- *                          operation order; c = coords[j] or, when coords == NULL, the j-th cell of custom_meshgrid(X, Y, Z)
- *                          (:477-497); indices[j] = Morton code of c (optional).
+ *                          operation order; c = coords[j] or, when coords == NULL (n = H^3, the full sweep), every cell of
+ *                          custom_meshgrid(X, Y, Z) (:477-497) with ITS row of rand3 (row (x H + y) H + z), emitted x-fastest
+ *                          (point j = cell (j % H, (j / H) % H, j / H^2)) so that a warp of the encoder that follows works on one
+ *                          x-line; indices[j] = Morton code of c (optional).
  *   seald_occ_partial_points  the 2n sample points of the partial pass (:504-518): points [0, n) from the drawn cells rand_coords
  *                          (torch.randint, int64 [n,3]); points [n, 2n) from the rand_mask[j]-th OCCUPIED cell
  *                          (== nonzero(grid > 0)[rand_mask], :509-511), found by binary search in csum = inclusive prefix sum of

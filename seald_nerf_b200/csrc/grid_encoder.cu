@@ -22,39 +22,58 @@ struct LevelParams {
     uint32_t resolution;
     uint32_t hashmap_size;
     uint32_t offset;  // in rows
+    // how grid_row addresses this level (functions of the level only, hoisted out of the per-corner arithmetic):
+    uint32_t stride1;   // resolution (+1 without align_corners): row stride of dimension 1 of the dense index
+    uint32_t n_dense;   // dimensions the dense index consumes before its stride passes hashmap_size (gridencoder.cu:57-60)
+    uint32_t use_hash;  // hashed level: gridtype 0 and the dense index does not fit
+    uint32_t mask;      // hashmap_size - 1 when hashmap_size is a power of two (x % size == x & mask), else 0
 };
 
 constexpr int kMaxLevels = 32;
 
 // gridencoder.cu:137-139 — evaluated on device in fp32 with the same expression shape.
-__device__ __forceinline__ LevelParams make_level(const int* __restrict__ offsets, uint32_t level, float S, uint32_t H) {
+__device__ __forceinline__ LevelParams make_level(const int* __restrict__ offsets, uint32_t level, float S, uint32_t H, const uint32_t D,
+                                                  const uint32_t gridtype, const bool align_corners) {
     LevelParams p;
     p.offset = (uint32_t)offsets[level];
     p.hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
     p.scale = exp2f(level * S) * H - 1.0f;
     p.resolution = (uint32_t)ceil(p.scale) + 1;
+    p.stride1 = align_corners ? p.resolution : p.resolution + 1;
+    uint32_t stride = 1, nd = 0;
+    for (uint32_t d = 0; d < D && stride <= p.hashmap_size; d++) {  // the loop of gridencoder.cu:57-60 on the strides alone
+        stride *= p.stride1;
+        nd++;
+    }
+    p.n_dense = nd;
+    p.use_hash = (gridtype == 0 && stride > p.hashmap_size) ? 1u : 0u;
+    p.mask = (p.hashmap_size & (p.hashmap_size - 1)) == 0 ? p.hashmap_size - 1 : 0u;
     return p;
 }
 
-// gridencoder.cu:50-84
+// gridencoder.cu:50-84 (get_grid_index): same index, with everything that depends on the level alone taken from LevelParams — the
+// reference's `index % hashmap_size` (an integer division per corner: half of this file's instructions when written naively)
+// becomes a mask on the power-of-two hashed levels and a never-taken compare on the dense ones.
 template <uint32_t D>
-__device__ __forceinline__ uint32_t grid_row(const uint32_t gridtype, const bool align_corners, const uint32_t hashmap_size,
-                                             const uint32_t resolution, const uint32_t pos_grid[D]) {
-    uint32_t stride = 1;
-    uint32_t index = 0;
-#pragma unroll
-    for (uint32_t d = 0; d < D && stride <= hashmap_size; d++) {
-        index += pos_grid[d] * stride;
-        stride *= align_corners ? resolution : (resolution + 1);
-    }
-    if (gridtype == 0 && stride > hashmap_size) {
+__device__ __forceinline__ uint32_t grid_row(const LevelParams& lp, const uint32_t pos_grid[D]) {
+    uint32_t index;
+    if (lp.use_hash) {
         constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
-        uint32_t result = 0;
+        index = 0;
 #pragma unroll
-        for (uint32_t i = 0; i < D; ++i) result ^= pos_grid[i] * primes[i];
-        index = result;
+        for (uint32_t i = 0; i < D; ++i) index ^= pos_grid[i] * primes[i];
+        if (lp.mask) return index & lp.mask;
+    } else {
+        uint32_t stride = 1;
+        index = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            if (d < lp.n_dense) index += pos_grid[d] * stride;
+            stride *= lp.stride1;
+        }
+        if (index < lp.hashmap_size) return index;
     }
-    return index % hashmap_size;
+    return index % lp.hashmap_size;
 }
 
 // ---- row-vector load/store of C channels --------------------------------------------------------
@@ -144,7 +163,7 @@ __global__ void __launch_bounds__(256) k_grid_forward(const float* __restrict__ 
                                                       const float S, const uint32_t H, const uint32_t gridtype,
                                                       const bool align_corners, const uint32_t interp, const int* __restrict__ b_dev) {
     __shared__ LevelParams s_lp[kMaxLevels];
-    if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H);
+    if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H, D, gridtype, align_corners);
     __syncthreads();
     const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;  // live rows
 
@@ -181,7 +200,7 @@ __global__ void __launch_bounds__(256) k_grid_forward(const float* __restrict__ 
                         uint32_t pg[D];
 #pragma unroll
                         for (uint32_t d = 0; d < D; d++) pg[d] = pos_grid[d] + ((idx >> d) & 1u);
-                        const uint32_t row = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+                        const uint32_t row = grid_row<D>(lp, pg);
                         Row<T, C>::load(tl + (size_t)row * C, val[g][idx]);
                     }
                 }
@@ -287,6 +306,72 @@ struct RowPack {
     }
 };
 
+// Rows (relative to the level) of the 2^(D-1) corner pairs of a cell: pair j = corners (x, y + j0, z + j1, ..) and (x + 1, ..).
+// Two straight-line fast paths chosen per LEVEL (uniform over the warp): hashed levels with a power-of-two table (row = (x ^ K) &
+// mask, K = xor of the other dimensions' products, shared by the pair) and dense levels whose largest corner index stays inside
+// the level (no wrap: row = base + strides, pair = r, r + 1).  Anything else (tiled grids, non-power-of-two hashed levels,
+// align_corners wrap at x = 1) takes the reference's index arithmetic per corner (grid_row).
+template <uint32_t D>
+__device__ __forceinline__ void pair_rows(const LevelParams& lp, const uint32_t (&pos_grid)[D], uint32_t (&r0)[1u << (D - 1)],
+                                          uint32_t (&r1)[1u << (D - 1)]) {
+    constexpr uint32_t NP = 1u << (D - 1);
+    bool fast = false;
+    if (lp.use_hash) {
+        if (lp.mask) {
+            constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+            uint32_t lo[D], hi[D];
+#pragma unroll
+            for (uint32_t d = 1; d < D; d++) {
+                lo[d] = pos_grid[d] * primes[d];
+                hi[d] = lo[d] + primes[d];
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < NP; j++) {
+                uint32_t k = 0;
+#pragma unroll
+                for (uint32_t d = 1; d < D; d++) k ^= ((j >> (d - 1)) & 1u) ? hi[d] : lo[d];
+                r0[j] = (pos_grid[0] ^ k) & lp.mask;
+                r1[j] = ((pos_grid[0] + 1) ^ k) & lp.mask;
+            }
+            fast = true;
+        }
+    } else if (lp.n_dense == D) {
+        uint32_t st[D];
+        st[0] = 1;
+#pragma unroll
+        for (uint32_t d = 1; d < D; d++) st[d] = st[d - 1] * lp.stride1;
+        uint32_t base = 0, top = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            base += pos_grid[d] * st[d];
+            top += st[d];
+        }
+        if (base + top < lp.hashmap_size) {
+#pragma unroll
+            for (uint32_t j = 0; j < NP; j++) {
+                uint32_t r = base;
+#pragma unroll
+                for (uint32_t d = 1; d < D; d++) r += ((j >> (d - 1)) & 1u) ? st[d] : 0u;
+                r0[j] = r;
+                r1[j] = r + 1;
+            }
+            fast = true;
+        }
+    }
+    if (!fast) {
+#pragma unroll
+        for (uint32_t j = 0; j < NP; j++) {
+            uint32_t pg[D];
+            pg[0] = pos_grid[0];
+#pragma unroll
+            for (uint32_t d = 1; d < D; d++) pg[d] = pos_grid[d] + ((j >> (d - 1)) & 1u);
+            r0[j] = grid_row<D>(lp, pg);
+            pg[0] = pos_grid[0] + 1;
+            r1[j] = grid_row<D>(lp, pg);
+        }
+    }
+}
+
 // Gathers the 2^D corner rows of one cell with paired loads.  issue(): all loads in flight; resolve(): rows as floats.
 template <typename T, uint32_t D, uint32_t C>
 struct CellGather {
@@ -302,20 +387,17 @@ struct CellGather {
                                           const uint32_t (&pos_grid)[D]) {
         code = 0;
         straddle = 0;
+        // absolute rows: 16-byte groups are aligned relative to the table base (level offsets need not be)
+        uint32_t r0[NP], r1[NP];
+        pair_rows<D>(lp, pos_grid, r0, r1);
+#pragma unroll
+        for (uint32_t j = 0; j < NP; j++) { r0[j] += lp.offset; r1[j] += lp.offset; }
 #pragma unroll
         for (uint32_t j = 0; j < NP; j++) {
-            uint32_t pg[D];
-            pg[0] = pos_grid[0];
-#pragma unroll
-            for (uint32_t d = 1; d < D; d++) pg[d] = pos_grid[d] + ((j >> (d - 1)) & 1u);
-            // absolute rows: 16-byte groups are aligned relative to the table base (level offsets need not be)
-            const uint32_t r0 = lp.offset + grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
-            pg[0] = pos_grid[0] + 1;
-            const uint32_t r1 = lp.offset + grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
-            u[j] = __ldg(reinterpret_cast<const uint4*>(tl + (size_t)(r0 & ~(RP::R16 - 1)) * C));
-            const bool far = (r0 ^ r1) >= RP::R16;
-            if (far) RP::load_row(tl + (size_t)r1 * C, w1[j]);
-            code |= ((r0 & (RP::R16 - 1)) | ((r1 & (RP::R16 - 1)) << 2)) << (4 * j);
+            u[j] = __ldg(reinterpret_cast<const uint4*>(tl + (size_t)(r0[j] & ~(RP::R16 - 1)) * C));
+            const bool far = (r0[j] ^ r1[j]) >= RP::R16;
+            if (far) RP::load_row(tl + (size_t)r1[j] * C, w1[j]);
+            code |= ((r0[j] & (RP::R16 - 1)) | ((r1[j] & (RP::R16 - 1)) << 2)) << (4 * j);
             straddle |= (far ? 1u : 0u) << j;
         }
     }
@@ -343,7 +425,7 @@ __global__ void __launch_bounds__(256) k_grid_forward_pair(const float* __restri
                                                            const float S, const uint32_t H, const uint32_t gridtype,
                                                            const bool align_corners, const uint32_t interp, const int* __restrict__ b_dev) {
     __shared__ LevelParams s_lp[kMaxLevels];
-    if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H);
+    if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H, D, gridtype, align_corners);
     __syncthreads();
     const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;  // live rows
     constexpr uint32_t NC = 1u << D;
@@ -504,7 +586,7 @@ __global__ void __launch_bounds__(256) k_grid_scatter(const T* __restrict__ grad
     const uint32_t b_begin = chunk * points_per_cta;
     const uint32_t b_end = min(Bn, b_begin + points_per_cta);
     if (b_begin >= b_end) return;
-    const LevelParams lp = make_level(offsets, level, S, H);
+    const LevelParams lp = make_level(offsets, level, S, H, D, gridtype, align_corners);
     const bool agg = level < agg_levels;
     constexpr uint32_t NP = 1u << (D - 1);
     const uint32_t lane = threadIdx.x & 31u;
@@ -532,15 +614,11 @@ __global__ void __launch_bounds__(256) k_grid_scatter(const T* __restrict__ grad
         float pos[D], deriv[D];
         uint32_t pos_grid[D];
         locate<D>(x, lp, align_corners, interp, pos, deriv, pos_grid);
+        uint32_t rows0[NP], rows1[NP];
+        pair_rows<D>(lp, pos_grid, rows0, rows1);
 #pragma unroll
         for (uint32_t j = 0; j < NP; j++) {
-            uint32_t pg[D];
-            pg[0] = pos_grid[0];
-#pragma unroll
-            for (uint32_t d = 1; d < D; d++) pg[d] = pos_grid[d] + ((j >> (d - 1)) & 1u);
-            const uint32_t r0 = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
-            pg[0] = pos_grid[0] + 1;
-            const uint32_t r1 = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+            const uint32_t r0 = rows0[j], r1 = rows1[j];
             // same product order as the reference (w = 1 * w_0 * w_1 * ...)
             float w0 = 1 - pos[0], w1 = pos[0];
 #pragma unroll
@@ -586,7 +664,7 @@ __global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* 
                                                                        const bool align_corners, const uint32_t interp,
                                                                        const int* __restrict__ b_dev) {
     __shared__ LevelParams s_lp[kMaxLevels];
-    if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H);
+    if (threadIdx.x < L) s_lp[threadIdx.x] = make_level(offsets, threadIdx.x, S, H, D, gridtype, align_corners);
     __syncthreads();
     const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;
     constexpr uint32_t NC = 1u << D;
@@ -620,7 +698,7 @@ __global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* 
                         uint32_t pg[D];
 #pragma unroll
                         for (uint32_t d = 0; d < D; d++) pg[d] = pos_grid[d] + ((idx >> d) & 1u);
-                        const uint32_t row = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+                        const uint32_t row = grid_row<D>(lp, pg);
                         Row<T, C>::load(tl + (size_t)row * C, val[idx]);
                     }
                 }
@@ -674,13 +752,13 @@ __global__ void k_grid_debug_indices(const float* __restrict__ inputs, const int
     constexpr uint32_t NC = 1u << D;
     const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
     if (t < L) {
-        const LevelParams lp = make_level(offsets, t, S, H);
+        const LevelParams lp = make_level(offsets, t, S, H, D, gridtype, align_corners);
         scales[t] = lp.scale;
         resolutions[t] = lp.resolution;
     }
     if (t >= B * L) return;
     const uint32_t b = t / L, l = t - b * L;
-    const LevelParams lp = make_level(offsets, l, S, H);
+    const LevelParams lp = make_level(offsets, l, S, H, D, gridtype, align_corners);
     float x[D], pos[D], deriv[D];
     uint32_t pos_grid[D];
 #pragma unroll
@@ -691,7 +769,7 @@ __global__ void k_grid_debug_indices(const float* __restrict__ inputs, const int
         uint32_t pg[D];
 #pragma unroll
         for (uint32_t d = 0; d < D; d++) pg[d] = pos_grid[d] + ((idx >> d) & 1u);
-        indices[(size_t)t * NC + idx] = grid_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, pg);
+        indices[(size_t)t * NC + idx] = grid_row<D>(lp, pg);
     }
 }
 

@@ -28,17 +28,24 @@ __device__ __forceinline__ uint32_t occ_compact_bits(uint32_t x) {  // inverse o
     return x;
 }
 
-// coords == nullptr: point j is cell (x, y, z) = (j / H^2, (j / H) % H, j % H), the order of custom_meshgrid(X, Y, Z)
-// (dnerf/renderer.py:481-483); else coords[j] (the random / re-sampled cells of the partial pass, :507-518).
+// coords == nullptr: the full sweep.  The reference enumerates the cells as j = (x * H + y) * H + z, the order of
+// custom_meshgrid(X, Y, Z) (dnerf/renderer.py:481-483), and its rand_like() jitter row j belongs to that cell.  The points are
+// PRODUCED x-fastest instead (thread i -> cell x = i % H, y = (i / H) % H, z = i / H^2, jitter still read from row j): the results go
+// to the grid through their Morton index, so the order of the batch is free — and 32 consecutive points of a warp then lie on one
+// x-line, where the hash grid's rows are contiguous (dense levels: row = x + ..., hashed levels: x ^ const), so the encoder that
+// follows shares sectors inside a warp: 25 instead of 72 sector requests per point, the quantity that bounds it
+// (profiles/r2_occupancy.md).  coords != nullptr: coords[j] (the random / re-sampled cells of the partial pass, :507-518).
 __global__ void k_occ_cell_points(const int* __restrict__ coords, const float* __restrict__ rand3, const uint32_t n, const uint32_t H,
                                   const float span, const float half_cell, float* __restrict__ xyzs, int* __restrict__ indices) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t c[3];
+    uint32_t jr = j;  // row of the reference's random numbers that belongs to this point
     if (coords) {
         c[0] = (uint32_t)coords[j * 3]; c[1] = (uint32_t)coords[j * 3 + 1]; c[2] = (uint32_t)coords[j * 3 + 2];
     } else {
-        c[2] = j % H; c[1] = (j / H) % H; c[0] = j / (H * H);
+        c[0] = j % H; c[1] = (j / H) % H; c[2] = j / (H * H);
+        jr = (c[0] * H + c[1]) * H + c[2];
     }
     if (indices) indices[j] = (int)(occ_expand_bits(c[0]) | (occ_expand_bits(c[1]) << 1) | (occ_expand_bits(c[2]) << 2));
     // torch divides a CUDA tensor by a host scalar as a * (1 / b) with the reciprocal rounded to fp32 (BinaryDivTrueKernel.cu)
@@ -47,8 +54,8 @@ __global__ void k_occ_cell_points(const int* __restrict__ coords, const float* _
     for (int d = 0; d < 3; d++) {
         // xyzs = 2 * coords.float() / (H - 1) - 1;  cas_xyzs = xyzs * (bound - half);  cas_xyzs += (rand * 2 - 1) * half
         const float x = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, (float)c[d]), inv_hm1), 1.0f);
-        const float jit = __fmul_rn(__fsub_rn(__fmul_rn(rand3[j * 3 + d], 2.0f), 1.0f), half_cell);
-        xyzs[j * 3 + d] = __fadd_rn(__fmul_rn(x, span), jit);
+        const float jit = __fmul_rn(__fsub_rn(__fmul_rn(__ldg(rand3 + (size_t)jr * 3 + d), 2.0f), 1.0f), half_cell);
+        xyzs[(size_t)j * 3 + d] = __fadd_rn(__fmul_rn(x, span), jit);
     }
 }
 
