@@ -1711,7 +1711,8 @@ static int march_train_impl(const float* rays_o, const float* rays_d, const uint
     // small batches (training: 4096 rays) are latency bound: one warp per ray.  Large batches (whole images) have enough
     // rays to fill the machine with one thread per ray, which does less total work.
     static const bool no_chain = getenv("SEALD_MARCH_CHAIN") && atoi(getenv("SEALD_MARCH_CHAIN")) == 0;  // measurement switch
-    if (N <= 65536u && max_steps <= kMaxStepsSmem && dt_gamma == 0.0f && !no_chain) {
+    static const uint32_t chain_max = getenv("SEALD_MARCH_CHAIN_MAX") ? (uint32_t)atoll(getenv("SEALD_MARCH_CHAIN_MAX")) : 65536u;
+    if (N <= chain_max && max_steps <= kMaxStepsSmem && dt_gamma == 0.0f && !no_chain) {
         // constant step: closed-form chain, every element probed in parallel + pointer chase
         auto k = mapper ? k_march_rays_train_chain<true> : k_march_rays_train_chain<false>;
         k<<<div_up(N, kMarchWarps), kMarchWarps * 32, 0, st>>>(rays_o, rays_d, bitfield, bound, max_steps, N, C, H, M, nears, fars, aabb6, min_near,
