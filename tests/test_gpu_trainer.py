@@ -267,3 +267,29 @@ def test_ema_matches_torch_ema_rule(cuda_dev):
     assert torch.equal(tr.params, tr.ema_shadow) and torch.equal(tr.table16, model.encoder.embeddings.data.half())
     tr.ema_restore()
     assert torch.equal(tr.params, raw)
+
+
+def test_pipelined_host_steps_equal_synchronous_ones(cuda_dev):
+    """train_step_host_pipelined (H2D of the next batch under the running step, loss read one step late) runs exactly the steps
+    train_step_host runs: same loss sequence (shifted by one call), same parameters afterwards."""
+    from seald_nerf_b200.trainer import FusedTrainer
+    import bench
+    ro, rd, ts, gt = bench.make_batches(4, cuda_dev, 0)
+    ro, rd, gt = ro[:, :1024].contiguous().cpu(), rd[:, :1024].contiguous().cpu(), gt[:, :1024].contiguous().cpu()
+    res = []
+    for pipelined in (False, True):
+        model = bench.build_scene(cuda_dev, seed=0)
+        tr = FusedTrainer(model, num_rays=1024, max_samples=1024 * 48, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=1024.0)
+        losses = []
+        for i in range(6):
+            fn = tr.train_step_host_pipelined if pipelined else tr.train_step_host
+            losses.append(fn(ro[i % 4], rd[i % 4], float(ts[i % 4]), gt[i % 4]))
+        if pipelined:
+            assert losses[0] is None
+            losses = losses[1:] + [tr.drain_host_pipeline()]
+        tr.flush()
+        torch.cuda.synchronize()
+        res.append((losses, tr.params.clone()))
+    (la, pa), (lb, pb) = res
+    assert all(abs(a - b) <= 2e-3 * abs(a) + 1e-7 for a, b in zip(la, lb)), (la, lb)   # (atomic-order noise between two runs)
+    assert float((pa - pb).abs().mean()) <= 0.05 * float(pa.abs().mean())
