@@ -7,6 +7,15 @@ from seald_nerf_b200._lib import ptr
 dev = torch.device("cuda:0")
 model = bench.build_scene(dev)
 cfg = model._field_cfg
+train_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+if train_steps:
+    from seald_nerf_b200.trainer import FusedTrainer
+    tr = FusedTrainer(model, num_rays=4096, max_samples=42368, lr=1e-2, lr_net=1e-3)
+    ro, rd, ts, gt = bench.make_batches(4, dev, 0)
+    for i in range(train_steps):
+        tr.train_step(ro[i % 4], rd[i % 4], ts[i % 4], gt[i % 4])
+    tr.flush(); torch.cuda.synchronize()
+    print("trained", train_steps, "steps", flush=True)
 hw = model._half_weights(); hw.refresh([w.detach() for w in model.mlp_weights()])
 table16 = model.encoder.embeddings.detach().half()
 H = 128; n = H ** 3
@@ -30,4 +39,5 @@ for name, p in orders.items():
     g = lambda: _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(off), ptr(ws.feat), None, n, 3, cfg.grid_dim, cfg.grid_levels,
                           cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, _lib.F16, None, _lib.stream())
     s = lambda: _lib.call("seald_field_sigma_forward", ptr(ws.feat), hw.p_sigma, cfg.n_sigma, n, 1.0, ptr(ws.sigma), None, _lib.stream())
-    print(name, "ms: deform", timeit(d), "grid", timeit(g), "sigma", timeit(s), flush=True)
+    print(name, "ms: deform", timeit(d), "grid", timeit(g), "sigma", timeit(s), "| oob frac", float(((ws.x01 < 0) | (ws.x01 > 1)).any(-1).float().mean()),
+          "mean |dx|", float(ws.deform.abs().mean()), flush=True)

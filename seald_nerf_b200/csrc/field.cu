@@ -10,6 +10,9 @@
 // weight-gradient GEMMs), hidden activations stay in registers (mlp.cuh), trunc_exp / sigmoid are epilogues.
 // Numerics follow the reference under autocast: fp16 operands and layer outputs, fp32 accumulation (cuBLAS),
 // exp in fp32 on the fp16-rounded pre-activation (activation.py:5-17), sigmoid on the fp16 output.
+#include <cstdlib>
+#include <string>
+
 #include "encoders.cuh"
 #include "mlp.cuh"
 
@@ -197,6 +200,211 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward(const __half* 
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same heads with the weights RESIDENT in shared memory and one WARP per 16-row slab, no block-wide barrier after the
+// weights are in: the tile kernel above re-stages 20 KiB of weights for every 128-row tile (8 KiB of input) behind ~10
+// __syncthreads and runs its per-row epilogues on half the CTA while the other half waits.  Here a warp loads its 16 feature rows,
+// runs sigma net -> epilogue (exp, SH of the view direction, colour input) -> colour net -> sigmoid on its own, synchronising with
+// __syncwarp only, so the 16 warps of an SM overlap each other's loads, MMAs and epilogues.  Same MMA order per output element as
+// mlp_forward_tile: results are bit-identical to the tile kernel (tests/test_gpu_field.py).  SIGMA_ONLY = NeRFNetwork.density.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kHrK0Stride = kHeadK0 + kPad;                       // 40 halves: rows of a K = 32 weight / input tile
+constexpr int kHrWStride = kHeadW + kPad;                         // 72 halves: rows of a K = 64 weight
+constexpr int kHrWarpBytes = 16 * kHrK0Stride * 2 + 16 * kOutStride * 4;  // per-warp input tile + output scratch
+
+__host__ __device__ inline int head_weight_halves(const int n_layers) {  // layer 0 [64][40], hidden [64][72] x (n - 2), last [16][72]
+    return kHeadW * kHrK0Stride + (n_layers - 2) * kHeadW * kHrWStride + 16 * kHrWStride;
+}
+__device__ __forceinline__ const __half* head_layer_ptr(const __half* base, const int l) {
+    return l == 0 ? base : base + kHeadW * kHrK0Stride + (l - 1) * kHeadW * kHrWStride;
+}
+
+// One warp, 16 rows: input tile s_in [16][40] halves -> s_out [16][17] floats (last layer pre-activation); sw = this net's weights.
+template <bool SAVE>
+__device__ __forceinline__ void warp_head_mlp(const __half* sw, const int n_layers, const __half* s_in, float* s_out,
+                                              __half* __restrict__ fwd_buf, const int M, const int m_used, const int row0) {
+    constexpr int NT = kHeadW / 8, KT = kHeadW / 16;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t areg[KT][4];
+    float acc[NT][4];
+    for (int l = 0; l < n_layers - 1; l++) {
+        const __half* wcur = head_layer_ptr(sw, l);
+#pragma unroll
+        for (int n = 0; n < NT; n++) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f; }
+        if (l == 0) {
+#pragma unroll
+            for (int kk = 0; kk < kHeadK0 / 16; kk++) {
+                uint32_t a[4];
+                ldmatrix_x4(a, s_in + ((lane & 7) + 8 * ((lane >> 3) & 1)) * kHrK0Stride + kk * 16 + 8 * (lane >> 4));
+#pragma unroll
+                for (int nn = 0; nn < NT; nn += 2) {
+                    uint32_t b[4];
+                    ldmatrix_x4(b, wcur + (8 * nn + (lane & 7) + 8 * (lane >> 4)) * kHrK0Stride + kk * 16 + 8 * ((lane >> 3) & 1));
+                    mma_16816(acc[nn], a, b[0], b[1]);
+                    mma_16816(acc[nn + 1], a, b[2], b[3]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < KT; kk++) {
+#pragma unroll
+                for (int nn = 0; nn < NT; nn += 2) {
+                    uint32_t b[4];
+                    ldmatrix_x4(b, wcur + (8 * nn + (lane & 7) + 8 * (lane >> 4)) * kHrWStride + kk * 16 + 8 * ((lane >> 3) & 1));
+                    mma_16816(acc[nn], areg[kk], b[0], b[1]);
+                    mma_16816(acc[nn + 1], areg[kk], b[2], b[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < KT; kk++) {
+            areg[kk][0] = pack_half2(fmaxf(acc[2 * kk][0], 0.f), fmaxf(acc[2 * kk][1], 0.f));
+            areg[kk][1] = pack_half2(fmaxf(acc[2 * kk][2], 0.f), fmaxf(acc[2 * kk][3], 0.f));
+            areg[kk][2] = pack_half2(fmaxf(acc[2 * kk + 1][0], 0.f), fmaxf(acc[2 * kk + 1][1], 0.f));
+            areg[kk][3] = pack_half2(fmaxf(acc[2 * kk + 1][2], 0.f), fmaxf(acc[2 * kk + 1][3], 0.f));
+        }
+        if (SAVE) {
+            __half* base = fwd_buf + (size_t)l * M * kHeadW;
+            const int r0 = row0 + g, r1 = r0 + 8;
+#pragma unroll
+            for (int kk = 0; kk < KT; kk++) {
+                if (r0 < m_used) {
+                    *reinterpret_cast<uint32_t*>(base + (size_t)r0 * kHeadW + kk * 16 + 2 * t) = areg[kk][0];
+                    *reinterpret_cast<uint32_t*>(base + (size_t)r0 * kHeadW + kk * 16 + 8 + 2 * t) = areg[kk][2];
+                }
+                if (r1 < m_used) {
+                    *reinterpret_cast<uint32_t*>(base + (size_t)r1 * kHeadW + kk * 16 + 2 * t) = areg[kk][1];
+                    *reinterpret_cast<uint32_t*>(base + (size_t)r1 * kHeadW + kk * 16 + 8 + 2 * t) = areg[kk][3];
+                }
+            }
+        }
+    }
+    const __half* wlast = head_layer_ptr(sw, n_layers - 1);
+    float o[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f; }
+#pragma unroll
+    for (int kk = 0; kk < KT; kk++) {
+        uint32_t b[4];
+        ldmatrix_x4(b, wlast + ((lane & 7) + 8 * (lane >> 4)) * kHrWStride + kk * 16 + 8 * ((lane >> 3) & 1));
+        mma_16816(o[0], areg[kk], b[0], b[1]);
+        mma_16816(o[1], areg[kk], b[2], b[3]);
+    }
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+        s_out[g * kOutStride + 8 * n + 2 * t] = o[n][0];
+        s_out[g * kOutStride + 8 * n + 2 * t + 1] = o[n][1];
+        s_out[(g + 8) * kOutStride + 8 * n + 2 * t] = o[n][2];
+        s_out[(g + 8) * kOutStride + 8 * n + 2 * t + 1] = o[n][3];
+    }
+}
+
+template <bool SAVE, bool SIGMA_ONLY>
+__global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __half* __restrict__ feat, const float* __restrict__ dirs,
+                                                                       const MlpWeights mw_s, const MlpWeights mw_c, const int M,
+                                                                       const int* __restrict__ m_dev, const float density_scale,
+                                                                       float* __restrict__ sigma, float* __restrict__ rgb,
+                                                                       __half* __restrict__ hs, __half* __restrict__ cin,
+                                                                       __half* __restrict__ fwd_s, __half* __restrict__ fwd_c,
+                                                                       __half* __restrict__ geo) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* sw_s = reinterpret_cast<__half*>(smem_raw);
+    __half* sw_c = sw_s + head_weight_halves(mw_s.n_layers);
+    unsigned char* warp_base = reinterpret_cast<unsigned char*>(sw_c + (SIGMA_ONLY ? 0 : head_weight_halves(mw_c.n_layers)));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __half* s_in = reinterpret_cast<__half*>(warp_base + (size_t)warp * kHrWarpBytes);
+    float* s_out = reinterpret_cast<float*>(s_in + 16 * kHrK0Stride);
+    const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
+
+    // ---- the weights, once per CTA
+#pragma unroll 1
+    for (int net = 0; net < (SIGMA_ONLY ? 1 : 2); net++) {
+        const MlpWeights& mw = net ? mw_c : mw_s;
+        __half* base = net ? sw_c : sw_s;
+        for (int l = 0; l < mw.n_layers; l++) {
+            __half* dst = const_cast<__half*>(head_layer_ptr(base, l));
+            if (l == 0) stage_weights(dst, kHrK0Stride, mw.w[0], kHeadW, kHeadW, mw.k0, mw.k0_ld);
+            else if (l < mw.n_layers - 1) stage_weights(dst, kHrWStride, mw.w[l], kHeadW, kHeadW, kHeadW, kHeadW);
+            else stage_weights(dst, kHrWStride, mw.w[l], 16, mw.n_out, kHeadW, kHeadW);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int n_slabs = (m_used + 15) / 16;
+    for (int slab = blockIdx.x * (kMlpThreads / 32) + warp; slab < n_slabs; slab += gridDim.x * (kMlpThreads / 32)) {
+        const int row0 = slab * 16;
+        // ---- 16 feature rows x 64 bytes: two 16-byte chunks per lane
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int idx = lane * 2 + c, r = idx >> 2, ch = idx & 3;
+            const int row = row0 + r;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (row < m_used) v = __ldg(reinterpret_cast<const uint4*>(feat + (size_t)row * 32 + ch * 8));
+            *reinterpret_cast<uint4*>(s_in + r * kHrK0Stride + ch * 8) = v;
+        }
+        __syncwarp();
+        warp_head_mlp<SAVE>(sw_s, mw_s.n_layers, s_in, s_out, fwd_s, M, m_used, row0);
+        __syncwarp();
+        // ---- sigma epilogue + colour input (lanes 0-15: one row each)
+        if (lane < 16) {
+            const int r = lane, row = row0 + r;
+            const float* z = s_out + r * kOutStride;
+            __half* ci = s_in + r * kHrK0Stride;
+            if (row < m_used) {
+                __align__(16) __half hrow[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) hrow[c] = __float2half_rn(z[c]);
+                sigma[row] = density_scale * expf(__half2float(hrow[0]));
+                if constexpr (SIGMA_ONLY) {
+                    if (geo) {
+#pragma unroll
+                        for (int c = 1; c < 16; c++) geo[(size_t)row * 15 + c - 1] = hrow[c];
+                    }
+                } else {
+                    float sh[16];
+                    const float* d = dirs + (size_t)row * 3;
+                    sh_eval<4>(d[0], d[1], d[2], sh);
+#pragma unroll
+                    for (int c = 0; c < 16; c++) ci[c] = __float2half_rn(sh[c]);
+#pragma unroll
+                    for (int c = 1; c < 16; c++) ci[15 + c] = hrow[c];
+                    ci[31] = __float2half_rn(0.0f);
+                    if (SAVE) {
+                        *reinterpret_cast<uint4*>(hs + (size_t)row * 16) = *reinterpret_cast<const uint4*>(hrow);
+                        *reinterpret_cast<uint4*>(hs + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(hrow + 8);
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            *reinterpret_cast<uint4*>(cin + (size_t)row * 32 + 8 * c) = *reinterpret_cast<const uint4*>(ci + 8 * c);
+                    }
+                }
+            } else if constexpr (!SIGMA_ONLY) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(ci + 8 * c) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        __syncwarp();
+        if constexpr (!SIGMA_ONLY) {
+            warp_head_mlp<SAVE>(sw_c, mw_c.n_layers, s_in, s_out, fwd_c, M, m_used, row0);
+            __syncwarp();
+            if (lane < 16) {
+                const int row = row0 + lane;
+                if (row < m_used) {
+                    const float* z = s_out + lane * kOutStride;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float zh = half_round(z[c]);
+                        rgb[(size_t)row * 3 + c] = half_round(1.0f / (1.0f + expf(-zh)));
+                    }
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -537,8 +745,28 @@ extern "C" int seald_field_heads_forward(const void* feat, const float* dirs, co
     int rc = make_weights(ms, w_sigma, n_sigma, kHeadK0, kHeadK0, 16);
     if (rc) return rc;
     if ((rc = make_weights(mc, w_color, n_color, kHeadK0, kHeadK0, 3))) return rc;
-    const size_t smem = HeadSmem::BYTES;
     cudaStream_t st = to_stream(stream);
+    // weights resident + one warp per 16-row slab (default); SEALD_HEADS_IMPL=tile: the 128-row tile kernel (measurement switch, and
+    // the fallback when the nets are too deep for their weights to stay in shared memory)
+    static const bool tile_impl = getenv("SEALD_HEADS_IMPL") && std::string(getenv("SEALD_HEADS_IMPL")) == "tile";
+    const size_t smem_res = (size_t)(head_weight_halves(n_sigma) + head_weight_halves(n_color)) * 2 + (kMlpThreads / 32) * kHrWarpBytes;
+    if (!tile_impl && smem_res <= 96 * 1024) {
+        const uint32_t slabs = div_up(M, 16u);
+        uint32_t blocks = div_up(slabs, (uint32_t)(kMlpThreads / 32));
+        if (blocks > 2u * SEALD_NUM_SMS) blocks = 2u * SEALD_NUM_SMS;
+        if (save) {
+            if ((rc = set_smem(k_heads_forward_warp<true, false>, smem_res))) return rc;
+            k_heads_forward_warp<true, false><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev, density_scale,
+                                                                                    sigma, rgb, (__half*)hs, (__half*)cin, (__half*)fwd_s,
+                                                                                    (__half*)fwd_c, nullptr);
+        } else {
+            if ((rc = set_smem(k_heads_forward_warp<false, false>, smem_res))) return rc;
+            k_heads_forward_warp<false, false><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev, density_scale,
+                                                                                     sigma, rgb, nullptr, nullptr, nullptr, nullptr, nullptr);
+        }
+        return launch_status();
+    }
+    const size_t smem = HeadSmem::BYTES;
     if (save) {
         if ((rc = set_smem(k_heads_forward<true>, smem))) return rc;
         k_heads_forward<true><<<tiles_grid(M, 2), kMlpThreads, smem, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev, density_scale, sigma, rgb,
@@ -558,6 +786,18 @@ extern "C" int seald_field_sigma_forward(const void* feat, const void* const* w_
     MlpWeights ms;
     int rc = make_weights(ms, w_sigma, n_sigma, kHeadK0, kHeadK0, 16);
     if (rc) return rc;
+    static const bool tile_impl = getenv("SEALD_HEADS_IMPL") && std::string(getenv("SEALD_HEADS_IMPL")) == "tile";
+    const size_t smem_res = (size_t)head_weight_halves(n_sigma) * 2 + (kMlpThreads / 32) * kHrWarpBytes;
+    if (!tile_impl && smem_res <= 96 * 1024) {
+        const uint32_t slabs = div_up(M, 16u);
+        uint32_t blocks = div_up(slabs, (uint32_t)(kMlpThreads / 32));
+        if (blocks > 2u * SEALD_NUM_SMS) blocks = 2u * SEALD_NUM_SMS;
+        if ((rc = set_smem(k_heads_forward_warp<false, true>, smem_res))) return rc;
+        k_heads_forward_warp<false, true><<<blocks, kMlpThreads, smem_res, to_stream(stream)>>>((const __half*)feat, nullptr, ms, ms, (int)M, nullptr,
+                                                                                               density_scale, sigma, nullptr, nullptr, nullptr,
+                                                                                               nullptr, nullptr, (__half*)geo);
+        return launch_status();
+    }
     const size_t smem = HeadSmem::BYTES;
     if ((rc = set_smem(k_sigma_forward, smem))) return rc;
     k_sigma_forward<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>((const __half*)feat, ms, (int)M, density_scale, sigma, (__half*)geo);
