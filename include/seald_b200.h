@@ -308,6 +308,18 @@ int seald_field_heads_backward(const float* grad_sigma, const float* grad_rgb, c
                                const void* fwd_s, const void* fwd_c, void* bwd_s, void* bwd_c, void* gout_s /*[M,16]*/, void* gout_c /*[M,16]*/,
                                void* dfeat /*[M,32] f16*/, seald_stream_t stream);
 
+/* The same two kernels with every tensor the weight-gradient GEMMs read saved as 128-row TILE IMAGES ([tile][width/8][128][8] fp16,
+ * ceil128(M) rows per layer, dead rows of a live tile zero; see seald_mlp_wgrad_umma): fwd_s, fwd_c, cin and feat_img (a tile-image
+ * copy of the input features, [ceil128(M), 32]) in the forward; fwd_s / fwd_c read and bwd_s, bwd_c, gout_s, gout_c written in the
+ * backward.  hs and dfeat stay row-major. */
+int seald_field_heads_forward_tiled(const void* feat, const float* dirs, const void* const* w_sigma, int n_sigma, const void* const* w_color,
+                                    int n_color, uint32_t M, const int32_t* m_dev, float density_scale, float* sigma, float* rgb, void* hs,
+                                    void* cin, void* fwd_s, void* fwd_c, void* feat_img, seald_stream_t stream);
+int seald_field_heads_backward_tiled(const float* grad_sigma, const float* grad_rgb, const float* rgb, const void* hs,
+                                     const void* const* w_sigma, int n_sigma, const void* const* w_color, int n_color, uint32_t M,
+                                     const int32_t* m_dev, float density_scale, const void* fwd_s, const void* fwd_c, void* bwd_s, void* bwd_c,
+                                     void* gout_s, void* gout_c, void* dfeat, seald_stream_t stream);
+
 /* Weight gradients dW[N][K] += G[M][N]^T A[M][K] (fp16 in, fp32 atomics out); replaces the CUTLASS split-K GEMMs of
  * ffmlp_backward (ffmlp/src/ffmlp.cu:801-877).  Up to 16 jobs per launch. */
 typedef struct {

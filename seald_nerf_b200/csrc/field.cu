@@ -223,7 +223,7 @@ __device__ __forceinline__ const __half* head_layer_ptr(const __half* base, cons
 }
 
 // One warp, 16 rows: input tile s_in [16][40] halves -> s_out [16][17] floats (last layer pre-activation); sw = this net's weights.
-template <bool SAVE>
+template <bool SAVE, bool TILED>
 __device__ __forceinline__ void warp_head_mlp(const __half* sw, const int n_layers, const __half* s_in, float* s_out,
                                               __half* __restrict__ fwd_buf, const int M, const int m_used, const int row0) {
     constexpr int NT = kHeadW / 8, KT = kHeadW / 16;
@@ -267,7 +267,17 @@ __device__ __forceinline__ void warp_head_mlp(const __half* sw, const int n_laye
             areg[kk][2] = pack_half2(fmaxf(acc[2 * kk + 1][0], 0.f), fmaxf(acc[2 * kk + 1][1], 0.f));
             areg[kk][3] = pack_half2(fmaxf(acc[2 * kk + 1][2], 0.f), fmaxf(acc[2 * kk + 1][3], 0.f));
         }
-        if (SAVE) {
+        if (SAVE && TILED) {  // tile images, every row of a live tile (M = rows rounded up to 128; dead rows are zeros here)
+            __half* base = fwd_buf + (size_t)l * M * kHeadW;
+            const int r0 = row0 + g, r1 = r0 + 8;
+#pragma unroll
+            for (int kk = 0; kk < KT; kk++) {
+                *reinterpret_cast<uint32_t*>(base + tile_img_off<kHeadW>(r0, kk * 16 + 2 * t)) = areg[kk][0];
+                *reinterpret_cast<uint32_t*>(base + tile_img_off<kHeadW>(r0, kk * 16 + 8 + 2 * t)) = areg[kk][2];
+                *reinterpret_cast<uint32_t*>(base + tile_img_off<kHeadW>(r1, kk * 16 + 2 * t)) = areg[kk][1];
+                *reinterpret_cast<uint32_t*>(base + tile_img_off<kHeadW>(r1, kk * 16 + 8 + 2 * t)) = areg[kk][3];
+            }
+        } else if (SAVE) {
             __half* base = fwd_buf + (size_t)l * M * kHeadW;
             const int r0 = row0 + g, r1 = r0 + 8;
 #pragma unroll
@@ -303,14 +313,16 @@ __device__ __forceinline__ void warp_head_mlp(const __half* sw, const int n_laye
     }
 }
 
-template <bool SAVE, bool SIGMA_ONLY>
+// TILED (training, tcgen05 weight gradients): fwd_s / fwd_c / cin and a copy of the input features (feat_img) are saved as 128-row
+// tile images with M_ld = M rounded up to 128 rows per layer; every row of a live tile is written (dead rows: zeros).
+template <bool SAVE, bool SIGMA_ONLY, bool TILED>
 __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __half* __restrict__ feat, const float* __restrict__ dirs,
                                                                        const MlpWeights mw_s, const MlpWeights mw_c, const int M,
                                                                        const int* __restrict__ m_dev, const float density_scale,
                                                                        float* __restrict__ sigma, float* __restrict__ rgb,
                                                                        __half* __restrict__ hs, __half* __restrict__ cin,
                                                                        __half* __restrict__ fwd_s, __half* __restrict__ fwd_c,
-                                                                       __half* __restrict__ geo) {
+                                                                       __half* __restrict__ geo, __half* __restrict__ feat_img) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* sw_s = reinterpret_cast<__half*>(smem_raw);
     __half* sw_c = sw_s + head_weight_halves(mw_s.n_layers);
@@ -336,7 +348,8 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __h
     cp_async_wait<0>();
     __syncthreads();
 
-    const int n_slabs = (m_used + 15) / 16;
+    const int M_ld = TILED ? (M + 127) / 128 * 128 : M;                                  // rows per saved layer
+    const int n_slabs = (SAVE && TILED) ? (m_used + 127) / 128 * 8 : (m_used + 15) / 16;   // tile images: whole live tiles
     for (int slab = blockIdx.x * (kMlpThreads / 32) + warp; slab < n_slabs; slab += gridDim.x * (kMlpThreads / 32)) {
         const int row0 = slab * 16;
         // ---- 16 feature rows x 64 bytes: two 16-byte chunks per lane
@@ -347,9 +360,10 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __h
             uint4 v = make_uint4(0, 0, 0, 0);
             if (row < m_used) v = __ldg(reinterpret_cast<const uint4*>(feat + (size_t)row * 32 + ch * 8));
             *reinterpret_cast<uint4*>(s_in + r * kHrK0Stride + ch * 8) = v;
+            if (SAVE && TILED) *reinterpret_cast<uint4*>(feat_img + tile_img_off<kHeadK0>(row, ch * 8)) = v;
         }
         __syncwarp();
-        warp_head_mlp<SAVE>(sw_s, mw_s.n_layers, s_in, s_out, fwd_s, M, m_used, row0);
+        warp_head_mlp<SAVE, TILED>(sw_s, mw_s.n_layers, s_in, s_out, fwd_s, M_ld, m_used, row0);
         __syncwarp();
         // ---- sigma epilogue + colour input (lanes 0-15: one row each)
         if (lane < 16) {
@@ -378,19 +392,26 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __h
                     if (SAVE) {
                         *reinterpret_cast<uint4*>(hs + (size_t)row * 16) = *reinterpret_cast<const uint4*>(hrow);
                         *reinterpret_cast<uint4*>(hs + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(hrow + 8);
+                        if constexpr (!TILED) {
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            *reinterpret_cast<uint4*>(cin + (size_t)row * 32 + 8 * c) = *reinterpret_cast<const uint4*>(ci + 8 * c);
+                            for (int c = 0; c < 4; c++)
+                                *reinterpret_cast<uint4*>(cin + (size_t)row * 32 + 8 * c) = *reinterpret_cast<const uint4*>(ci + 8 * c);
+                        }
                     }
                 }
             } else if constexpr (!SIGMA_ONLY) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(ci + 8 * c) = make_uint4(0, 0, 0, 0);
             }
+            if constexpr (SAVE && TILED && !SIGMA_ONLY) {  // colour input as a tile image, dead rows of a live tile included (zeros)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    *reinterpret_cast<uint4*>(cin + tile_img_off<kHeadK0>(row, 8 * c)) = *reinterpret_cast<const uint4*>(ci + 8 * c);
+            }
         }
         __syncwarp();
         if constexpr (!SIGMA_ONLY) {
-            warp_head_mlp<SAVE>(sw_c, mw_c.n_layers, s_in, s_out, fwd_c, M, m_used, row0);
+            warp_head_mlp<SAVE, TILED>(sw_c, mw_c.n_layers, s_in, s_out, fwd_c, M_ld, m_used, row0);
             __syncwarp();
             if (lane < 16) {
                 const int row = row0 + lane;
@@ -448,6 +469,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_sigma_forward(const __half* 
 //   grad_sigma [M] fp32, grad_rgb [M,3] fp32 (already multiplied by the loss scale)
 //   outputs: dfeat [M,32] fp16, and for the weight-gradient GEMMs: gout_c [M,16], gout_s [M,16], bwd_c [2][M][64], bwd_s [1][M][64]
 // ---------------------------------------------------------------------------------------------------
+template <bool TILED>
 __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_backward(const float* __restrict__ grad_sigma, const float* __restrict__ grad_rgb,
                                                                    const float* __restrict__ rgb, const __half* __restrict__ hs,
                                                                    const MlpWeights mw_s, const MlpWeights mw_c, const int M,
@@ -477,14 +499,20 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_backward(const float* 
                     const float y = rgb[(size_t)row * 3 + c];
                     g16[c] = __float2half_rn(grad_rgb[(size_t)row * 3 + c] * y * (1.0f - y));
                 }
-                *reinterpret_cast<uint4*>(gout_c + (size_t)row * 16) = *reinterpret_cast<const uint4*>(g16);
-                *reinterpret_cast<uint4*>(gout_c + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
+                if constexpr (!TILED) {
+                    *reinterpret_cast<uint4*>(gout_c + (size_t)row * 16) = *reinterpret_cast<const uint4*>(g16);
+                    *reinterpret_cast<uint4*>(gout_c + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
+                }
+            }
+            if constexpr (TILED) {  // tile image [tile][2][128][8], dead rows of the live tile as zeros
+                *reinterpret_cast<uint4*>(gout_c + tile_img_off<16>(row, 0)) = *reinterpret_cast<const uint4*>(g16);
+                *reinterpret_cast<uint4*>(gout_c + tile_img_off<16>(row, 8)) = *reinterpret_cast<const uint4*>(g16 + 8);
             }
             *reinterpret_cast<uint4*>(s_g + r * kGStride) = *reinterpret_cast<const uint4*>(g16);
             *reinterpret_cast<uint4*>(s_g + r * kGStride + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
         }
         // colour backward; dL/d(colour input) lands in the s_in tile
-        mlp_backward_tile<kHeadW, kHeadK0>(mw_c, s_g, s_w, fwd_c, bwd_c, s_in, HeadSmem::IN_STRIDE, 0, M, m_used, row0);
+        mlp_backward_tile<kHeadW, kHeadK0, TILED>(mw_c, s_g, s_w, fwd_c, bwd_c, s_in, HeadSmem::IN_STRIDE, 0, TILED ? (M + 127) / 128 * 128 : M, m_used, row0);
         // ---- sigma g_out: trunc_exp backward on column 0, d geo on columns 1..15
         if (threadIdx.x < kTileRows) {
             const int r = threadIdx.x, row = row0 + r;
@@ -496,13 +524,19 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_backward(const float* 
                 g16[0] = __float2half_rn(grad_sigma[row] * density_scale * expf(fminf(fmaxf(h0, -15.0f), 15.0f)));
 #pragma unroll
                 for (int c = 1; c < 16; c++) g16[c] = s_in[r * HeadSmem::IN_STRIDE + 15 + c];
-                *reinterpret_cast<uint4*>(gout_s + (size_t)row * 16) = *reinterpret_cast<const uint4*>(g16);
-                *reinterpret_cast<uint4*>(gout_s + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
+                if constexpr (!TILED) {
+                    *reinterpret_cast<uint4*>(gout_s + (size_t)row * 16) = *reinterpret_cast<const uint4*>(g16);
+                    *reinterpret_cast<uint4*>(gout_s + (size_t)row * 16 + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
+                }
+            }
+            if constexpr (TILED) {
+                *reinterpret_cast<uint4*>(gout_s + tile_img_off<16>(row, 0)) = *reinterpret_cast<const uint4*>(g16);
+                *reinterpret_cast<uint4*>(gout_s + tile_img_off<16>(row, 8)) = *reinterpret_cast<const uint4*>(g16 + 8);
             }
             *reinterpret_cast<uint4*>(s_g + r * kGStride) = *reinterpret_cast<const uint4*>(g16);
             *reinterpret_cast<uint4*>(s_g + r * kGStride + 8) = *reinterpret_cast<const uint4*>(g16 + 8);
         }
-        mlp_backward_tile<kHeadW, kHeadK0>(mw_s, s_g, s_w, fwd_s, bwd_s, dfeat, 32, row0, M, m_used, row0);
+        mlp_backward_tile<kHeadW, kHeadK0, TILED>(mw_s, s_g, s_w, fwd_s, bwd_s, dfeat, 32, row0, TILED ? (M + 127) / 128 * 128 : M, m_used, row0);
     }
 }
 
@@ -734,13 +768,15 @@ extern "C" int seald_field_deform_backward(const float* grad_x01, const float* t
     return launch_status();
 }
 
-extern "C" int seald_field_heads_forward(const void* feat, const float* dirs, const void* const* w_sigma, int n_sigma, const void* const* w_color,
-                                         int n_color, uint32_t M, const int32_t* m_dev, float density_scale, float* sigma, float* rgb, void* hs,
-                                         void* cin, void* fwd_s, void* fwd_c, seald_stream_t stream) {
+static int heads_forward_impl(const void* feat, const float* dirs, const void* const* w_sigma, int n_sigma, const void* const* w_color,
+                              int n_color, uint32_t M, const int32_t* m_dev, float density_scale, float* sigma, float* rgb, void* hs,
+                              void* cin, void* fwd_s, void* fwd_c, void* feat_img, seald_stream_t stream) {
     if (M == 0) return 0;
     if (!feat || !dirs || !sigma || !rgb) return SEALD_E_BADARG;
     const bool save = hs != nullptr;
+    const bool tiled = feat_img != nullptr;
     if (save && (!cin || !fwd_s || !fwd_c)) return SEALD_E_BADARG;
+    if (tiled && !save) return SEALD_E_BADARG;
     MlpWeights ms, mc;
     int rc = make_weights(ms, w_sigma, n_sigma, kHeadK0, kHeadK0, 16);
     if (rc) return rc;
@@ -750,19 +786,26 @@ extern "C" int seald_field_heads_forward(const void* feat, const float* dirs, co
     // the fallback when the nets are too deep for their weights to stay in shared memory)
     static const bool tile_impl = getenv("SEALD_HEADS_IMPL") && std::string(getenv("SEALD_HEADS_IMPL")) == "tile";
     const size_t smem_res = (size_t)(head_weight_halves(n_sigma) + head_weight_halves(n_color)) * 2 + (kMlpThreads / 32) * kHrWarpBytes;
+    if (tiled && (tile_impl || smem_res > 96 * 1024)) return SEALD_E_UNSUPPORTED;  // tile images are written by the warp kernel only
     if (!tile_impl && smem_res <= 96 * 1024) {
-        const uint32_t slabs = div_up(M, 16u);
+        const uint32_t slabs = tiled ? div_up(M, 128u) * 8u : div_up(M, 16u);
         uint32_t blocks = div_up(slabs, (uint32_t)(kMlpThreads / 32));
         if (blocks > 2u * SEALD_NUM_SMS) blocks = 2u * SEALD_NUM_SMS;
-        if (save) {
-            if ((rc = set_smem(k_heads_forward_warp<true, false>, smem_res))) return rc;
-            k_heads_forward_warp<true, false><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev, density_scale,
-                                                                                    sigma, rgb, (__half*)hs, (__half*)cin, (__half*)fwd_s,
-                                                                                    (__half*)fwd_c, nullptr);
+        if (save && tiled) {
+            if ((rc = set_smem(k_heads_forward_warp<true, false, true>, smem_res))) return rc;
+            k_heads_forward_warp<true, false, true><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev,
+                                                                                          density_scale, sigma, rgb, (__half*)hs, (__half*)cin,
+                                                                                          (__half*)fwd_s, (__half*)fwd_c, nullptr, (__half*)feat_img);
+        } else if (save) {
+            if ((rc = set_smem(k_heads_forward_warp<true, false, false>, smem_res))) return rc;
+            k_heads_forward_warp<true, false, false><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev,
+                                                                                           density_scale, sigma, rgb, (__half*)hs, (__half*)cin,
+                                                                                           (__half*)fwd_s, (__half*)fwd_c, nullptr, nullptr);
         } else {
-            if ((rc = set_smem(k_heads_forward_warp<false, false>, smem_res))) return rc;
-            k_heads_forward_warp<false, false><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev, density_scale,
-                                                                                     sigma, rgb, nullptr, nullptr, nullptr, nullptr, nullptr);
+            if ((rc = set_smem(k_heads_forward_warp<false, false, false>, smem_res))) return rc;
+            k_heads_forward_warp<false, false, false><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev,
+                                                                                            density_scale, sigma, rgb, nullptr, nullptr, nullptr,
+                                                                                            nullptr, nullptr, nullptr);
         }
         return launch_status();
     }
@@ -779,6 +822,22 @@ extern "C" int seald_field_heads_forward(const void* feat, const float* dirs, co
     return launch_status();
 }
 
+extern "C" int seald_field_heads_forward(const void* feat, const float* dirs, const void* const* w_sigma, int n_sigma, const void* const* w_color,
+                                         int n_color, uint32_t M, const int32_t* m_dev, float density_scale, float* sigma, float* rgb, void* hs,
+                                         void* cin, void* fwd_s, void* fwd_c, seald_stream_t stream) {
+    return heads_forward_impl(feat, dirs, w_sigma, n_sigma, w_color, n_color, M, m_dev, density_scale, sigma, rgb, hs, cin, fwd_s, fwd_c, nullptr,
+                              stream);
+}
+
+extern "C" int seald_field_heads_forward_tiled(const void* feat, const float* dirs, const void* const* w_sigma, int n_sigma,
+                                               const void* const* w_color, int n_color, uint32_t M, const int32_t* m_dev, float density_scale,
+                                               float* sigma, float* rgb, void* hs, void* cin, void* fwd_s, void* fwd_c, void* feat_img,
+                                               seald_stream_t stream) {
+    if (!feat_img) return SEALD_E_BADARG;
+    return heads_forward_impl(feat, dirs, w_sigma, n_sigma, w_color, n_color, M, m_dev, density_scale, sigma, rgb, hs, cin, fwd_s, fwd_c, feat_img,
+                              stream);
+}
+
 extern "C" int seald_field_sigma_forward(const void* feat, const void* const* w_sigma, int n_sigma, uint32_t M, float density_scale, float* sigma,
                                          void* geo, seald_stream_t stream) {
     if (M == 0) return 0;
@@ -792,10 +851,10 @@ extern "C" int seald_field_sigma_forward(const void* feat, const void* const* w_
         const uint32_t slabs = div_up(M, 16u);
         uint32_t blocks = div_up(slabs, (uint32_t)(kMlpThreads / 32));
         if (blocks > 2u * SEALD_NUM_SMS) blocks = 2u * SEALD_NUM_SMS;
-        if ((rc = set_smem(k_heads_forward_warp<false, true>, smem_res))) return rc;
-        k_heads_forward_warp<false, true><<<blocks, kMlpThreads, smem_res, to_stream(stream)>>>((const __half*)feat, nullptr, ms, ms, (int)M, nullptr,
-                                                                                               density_scale, sigma, nullptr, nullptr, nullptr,
-                                                                                               nullptr, nullptr, (__half*)geo);
+        if ((rc = set_smem(k_heads_forward_warp<false, true, false>, smem_res))) return rc;
+        k_heads_forward_warp<false, true, false><<<blocks, kMlpThreads, smem_res, to_stream(stream)>>>((const __half*)feat, nullptr, ms, ms, (int)M,
+                                                                                                      nullptr, density_scale, sigma, nullptr, nullptr,
+                                                                                                      nullptr, nullptr, nullptr, (__half*)geo, nullptr);
         return launch_status();
     }
     const size_t smem = HeadSmem::BYTES;
@@ -804,10 +863,10 @@ extern "C" int seald_field_sigma_forward(const void* feat, const void* const* w_
     return launch_status();
 }
 
-extern "C" int seald_field_heads_backward(const float* grad_sigma, const float* grad_rgb, const float* rgb, const void* hs,
-                                          const void* const* w_sigma, int n_sigma, const void* const* w_color, int n_color, uint32_t M,
-                                          const int32_t* m_dev, float density_scale, const void* fwd_s, const void* fwd_c, void* bwd_s, void* bwd_c,
-                                          void* gout_s, void* gout_c, void* dfeat, seald_stream_t stream) {
+static int heads_backward_impl(const float* grad_sigma, const float* grad_rgb, const float* rgb, const void* hs,
+                               const void* const* w_sigma, int n_sigma, const void* const* w_color, int n_color, uint32_t M,
+                               const int32_t* m_dev, float density_scale, const void* fwd_s, const void* fwd_c, void* bwd_s, void* bwd_c,
+                               void* gout_s, void* gout_c, void* dfeat, bool tiled, seald_stream_t stream) {
     if (M == 0) return 0;
     if (!grad_sigma || !grad_rgb || !rgb || !hs || !fwd_s || !fwd_c || !bwd_s || !bwd_c || !gout_s || !gout_c || !dfeat) return SEALD_E_BADARG;
     MlpWeights ms, mc;
@@ -815,12 +874,28 @@ extern "C" int seald_field_heads_backward(const float* grad_sigma, const float* 
     if (rc) return rc;
     if ((rc = make_weights(mc, w_color, n_color, kHeadK0, kHeadK0, 3))) return rc;
     const size_t smem = HeadSmem::BYTES;
-    if ((rc = set_smem(k_heads_backward, smem))) return rc;
-    k_heads_backward<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>(grad_sigma, grad_rgb, rgb, (const __half*)hs, ms, mc, (int)M, m_dev,
-                                                                                density_scale, (const __half*)fwd_s, (const __half*)fwd_c,
-                                                                                (__half*)bwd_s, (__half*)bwd_c, (__half*)gout_s, (__half*)gout_c,
-                                                                                (__half*)dfeat);
+    auto k = tiled ? k_heads_backward<true> : k_heads_backward<false>;
+    if ((rc = set_smem(k, smem))) return rc;
+    k<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>(grad_sigma, grad_rgb, rgb, (const __half*)hs, ms, mc, (int)M, m_dev, density_scale,
+                                                                 (const __half*)fwd_s, (const __half*)fwd_c, (__half*)bwd_s, (__half*)bwd_c,
+                                                                 (__half*)gout_s, (__half*)gout_c, (__half*)dfeat);
     return launch_status();
+}
+
+extern "C" int seald_field_heads_backward(const float* grad_sigma, const float* grad_rgb, const float* rgb, const void* hs,
+                                          const void* const* w_sigma, int n_sigma, const void* const* w_color, int n_color, uint32_t M,
+                                          const int32_t* m_dev, float density_scale, const void* fwd_s, const void* fwd_c, void* bwd_s, void* bwd_c,
+                                          void* gout_s, void* gout_c, void* dfeat, seald_stream_t stream) {
+    return heads_backward_impl(grad_sigma, grad_rgb, rgb, hs, w_sigma, n_sigma, w_color, n_color, M, m_dev, density_scale, fwd_s, fwd_c, bwd_s, bwd_c,
+                               gout_s, gout_c, dfeat, false, stream);
+}
+
+extern "C" int seald_field_heads_backward_tiled(const float* grad_sigma, const float* grad_rgb, const float* rgb, const void* hs,
+                                                const void* const* w_sigma, int n_sigma, const void* const* w_color, int n_color, uint32_t M,
+                                                const int32_t* m_dev, float density_scale, const void* fwd_s, const void* fwd_c, void* bwd_s,
+                                                void* bwd_c, void* gout_s, void* gout_c, void* dfeat, seald_stream_t stream) {
+    return heads_backward_impl(grad_sigma, grad_rgb, rgb, hs, w_sigma, n_sigma, w_color, n_color, M, m_dev, density_scale, fwd_s, fwd_c, bwd_s, bwd_c,
+                               gout_s, gout_c, dfeat, true, stream);
 }
 
 extern "C" int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream) {

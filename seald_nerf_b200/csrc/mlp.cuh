@@ -215,7 +215,16 @@ __device__ __forceinline__ void mlp_forward_tile(const MlpWeights& mw, const __h
 // ===================================================================================================
 constexpr int kGStride = 16 + kPad;
 
-template <int WIDTH, int K0MAX>
+// Element (row r, column c) of a saved [rows][W] fp16 tensor in the 128-row TILE-IMAGE layout (umma.cuh / wgrad_umma.cu):
+// [tile][W / 8][128 rows][8 halves] — what the tcgen05 weight-gradient kernel fetches with one bulk copy per tile.
+template <int W>
+__device__ __forceinline__ size_t tile_img_off(const int r, const int c) {
+    return (((size_t)(r >> 7) * (W / 8) + (c >> 3)) * 128 + (r & 127)) * 8 + (c & 7);
+}
+
+// TILED: fwd_buf / bwd_buf are tile images (M_ld = rows rounded up to 128); every row of a live tile is written (dead rows carry
+// zeros: their g_out and saved activations are zero), so the weight-gradient kernel needs no row mask.
+template <int WIDTH, int K0MAX, bool TILED = false>
 __device__ __forceinline__ void mlp_backward_tile(const MlpWeights& mw, const __half* s_g, __half* s_w, const __half* __restrict__ fwd_buf,
                                                   __half* __restrict__ bwd_buf, __half* dinput, const int din_ld, const int din_row0,
                                                   const int M_ld, const int M, const int row0) {
@@ -285,16 +294,26 @@ __device__ __forceinline__ void mlp_backward_tile(const MlpWeights& mw, const __
             for (int h = 0; h < 2; h++) {  // the two n8 tiles of this k16 group
                 const int col = kk * 16 + 8 * h + 2 * t;
                 uint32_t m0 = 0, m1 = 0;
-                if (r0 < M) m0 = *reinterpret_cast<const uint32_t*>(hsave + (size_t)r0 * WIDTH + col);
-                if (r1 < M) m1 = *reinterpret_cast<const uint32_t*>(hsave + (size_t)r1 * WIDTH + col);
+                if constexpr (TILED) {
+                    m0 = *reinterpret_cast<const uint32_t*>(hsave + tile_img_off<WIDTH>(r0, col));
+                    m1 = *reinterpret_cast<const uint32_t*>(hsave + tile_img_off<WIDTH>(r1, col));
+                } else {
+                    if (r0 < M) m0 = *reinterpret_cast<const uint32_t*>(hsave + (size_t)r0 * WIDTH + col);
+                    if (r1 < M) m1 = *reinterpret_cast<const uint32_t*>(hsave + (size_t)r1 * WIDTH + col);
+                }
                 const __half2 h0 = *reinterpret_cast<const __half2*>(&m0), h1 = *reinterpret_cast<const __half2*>(&m1);
                 const float* c = acc[2 * kk + h];
                 const uint32_t p0 = pack_half2(__low2float(h0) > 0.f ? c[0] : 0.f, __high2float(h0) > 0.f ? c[1] : 0.f);
                 const uint32_t p1 = pack_half2(__low2float(h1) > 0.f ? c[2] : 0.f, __high2float(h1) > 0.f ? c[3] : 0.f);
                 greg[kk][2 * h] = p0;
                 greg[kk][2 * h + 1] = p1;
-                if (r0 < M) *reinterpret_cast<uint32_t*>(gsave + (size_t)r0 * WIDTH + col) = p0;
-                if (r1 < M) *reinterpret_cast<uint32_t*>(gsave + (size_t)r1 * WIDTH + col) = p1;
+                if constexpr (TILED) {
+                    *reinterpret_cast<uint32_t*>(gsave + tile_img_off<WIDTH>(r0, col)) = p0;
+                    *reinterpret_cast<uint32_t*>(gsave + tile_img_off<WIDTH>(r1, col)) = p1;
+                } else {
+                    if (r0 < M) *reinterpret_cast<uint32_t*>(gsave + (size_t)r0 * WIDTH + col) = p0;
+                    if (r1 < M) *reinterpret_cast<uint32_t*>(gsave + (size_t)r1 * WIDTH + col) = p1;
+                }
             }
         }
     }

@@ -45,16 +45,17 @@ struct UWgradJobs {
 
 constexpr int kUWChunk = 64;     // rows per stage
 constexpr int kUWStages = 3;
-constexpr int kUWMaxStages = 6;  // row-major path inside the 192 KiB ring
+constexpr int kUWMaxStages = 6;      // row-major path inside the 192 KiB ring
+constexpr int kUWMaxTileStages = 8;  // tile-image path: stages of (G tile + A tile) bytes
 constexpr int kUWThreads = 128;  // 4 warps: all stage, thread 0 issues the MMAs, all flush (thread t = output row t)
 constexpr uint32_t kUWOperandBytes = (kUWChunk / 8) * 16 * 128;  // 16 KiB: [k/8][mn/8 = 16][k%8][mn%8] for a 128-wide operand
 constexpr uint32_t kUWStageBytes = 2 * kUWOperandBytes;
-constexpr size_t kUWSmem = kUWStages * kUWStageBytes + 128;
+constexpr size_t kUWSmem = kUWStages * kUWStageBytes + 256;
 // tile-image path: a stage holds one 128-row tile of G (<= 32 KiB) and of A (<= 32 KiB)
 constexpr int kUWTileRows = 128;
 constexpr uint32_t kUWTileOperandBytes = 128 * kUWTileRows * 2;
 constexpr uint32_t kUWTileStageBytes = 2 * kUWTileOperandBytes;
-constexpr size_t kUWSmemTile = kUWStages * kUWTileStageBytes + 128;
+constexpr size_t kUWSmemTile = kUWStages * kUWTileStageBytes + 256;
 
 // instruction descriptor: fp16 x fp16 -> fp32, A and B MN-major (bits 15 / 16), M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_mn_major(const uint32_t n) {
@@ -64,10 +65,10 @@ __host__ __device__ constexpr uint32_t idesc_mn_major(const uint32_t n) {
 __global__ void __launch_bounds__(kUWThreads) k_wgrad_umma(const __grid_constant__ UWgradJobs jobs, const int M, const int* __restrict__ m_dev,
                                                            const uint32_t ring_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bar_empty = reinterpret_cast<uint64_t*>(smem + ring_bytes);  // [<= 6] the MMAs reading a stage have completed
-    uint64_t* bar_done = bar_empty + kUWMaxStages;                         // all MMAs of this CTA have completed
-    uint64_t* bar_full = bar_done + 1;                                     // [3] tile path: the bulk copies of a stage have landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + kUWStages);
+    uint64_t* bar_empty = reinterpret_cast<uint64_t*>(smem + ring_bytes);  // [<= 8] the MMAs reading a stage have completed
+    uint64_t* bar_done = bar_empty + kUWMaxTileStages;                     // all MMAs of this CTA have completed
+    uint64_t* bar_full = bar_done + 1;                                     // [<= 8] tile path: the bulk copies of a stage have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + kUWMaxTileStages);
     // row-major path: as many 64-row stages as the ring holds (3 in the 96 KiB ring, 6 beside tile-image jobs)
     const int row_stages = (int)(ring_bytes / kUWStageBytes);
 
@@ -87,19 +88,15 @@ __global__ void __launch_bounds__(kUWThreads) k_wgrad_umma(const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < kUWMaxStages; i++) umma::mbar_init(bar_empty + i, 1);
-        for (int i = 0; i < kUWStages; i++) umma::mbar_init(bar_full + i, 1);
+        for (int i = 0; i < kUWMaxTileStages; i++) { umma::mbar_init(bar_empty + i, 1); umma::mbar_init(bar_full + i, 1); }
         umma::mbar_init(bar_done, 1);
         umma::mbar_fence_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, 128);
-    // zero the G part of the ring once: output rows of G beyond n_out (M is always 128 for the MMA) are never written again
-    if (tile_image) {
-        const uint32_t g_used = (uint32_t)jb.n_out * kUWTileRows * 2;
-        for (int st = 0; st < kUWStages; st++)
-            for (uint32_t i = g_used / 16 + tid; i < kUWTileOperandBytes / 16; i += kUWThreads)
-                reinterpret_cast<uint4*>(smem + (size_t)st * kUWTileStageBytes)[i] = make_uint4(0, 0, 0, 0);
-    } else {
+    // row-major path: zero the ring once (columns of G beyond n_out are never written again).  Tile path: nothing to zero — the
+    // M = 128 MMA reads 128 - n_out rows of whatever follows a narrow G tile, but those only reach output rows >= n_out, which are
+    // never flushed (rows of D are independent).
+    if (!tile_image) {
         for (uint32_t i = tid; i < row_stages * kUWStageBytes / 16; i += kUWThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     }
     umma::fence_proxy_async();
@@ -112,25 +109,29 @@ __global__ void __launch_bounds__(kUWThreads) k_wgrad_umma(const __grid_constant
 
     if (tile_image) {
         // ---- tile-image operands: producer thread (bulk copies) and issuer thread (MMAs) talk through mbarriers only
+        // a stage = the tile's G image followed by its A image; as many stages as the ring holds (<= 8: narrow head layers get a
+        // deeper pipeline, 3 x 64 KiB for the 128-wide layers), leaving room for the M = 128 over-read behind the last G tile
         const int n = m_end - m_begin;
         const uint32_t g_bytes = (uint32_t)jb.n_out * kUWTileRows * 2, a_bytes = (uint32_t)jb.n_in * kUWTileRows * 2;
+        const uint32_t stage_bytes = g_bytes + a_bytes;
+        const int n_st = min(kUWMaxTileStages, (int)((ring_bytes - (kUWTileOperandBytes - g_bytes)) / stage_bytes));
         if (tid == 32) {
             const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(jb.G) + (size_t)m_begin * g_bytes;
             const unsigned char* asrc = reinterpret_cast<const unsigned char*>(jb.A) + (size_t)m_begin * a_bytes;
             for (int i = 0; i < n; i++) {
-                const int st = i % kUWStages;
-                if (i >= kUWStages) umma::mbar_wait(bar_empty + st, ((i / kUWStages) - 1) & 1);  // the MMAs of tile i - 3 are done
-                unsigned char* sg = smem + (size_t)st * kUWTileStageBytes;
-                umma::mbar_arrive_expect_tx(bar_full + st, g_bytes + a_bytes);
+                const int st = i % n_st;
+                if (i >= n_st) umma::mbar_wait(bar_empty + st, ((i / n_st) - 1) & 1);  // the MMAs of tile i - n_st are done
+                unsigned char* sg = smem + (size_t)st * stage_bytes;
+                umma::mbar_arrive_expect_tx(bar_full + st, stage_bytes);
                 umma::bulk_load(sg, gsrc + (size_t)i * g_bytes, g_bytes, bar_full + st);
-                umma::bulk_load(sg + kUWTileOperandBytes, asrc + (size_t)i * a_bytes, a_bytes, bar_full + st);
+                umma::bulk_load(sg + g_bytes, asrc + (size_t)i * a_bytes, a_bytes, bar_full + st);
             }
         } else if (tid == 0) {
             for (int i = 0; i < n; i++) {
-                const int st = i % kUWStages;
-                umma::mbar_wait(bar_full + st, (i / kUWStages) & 1);
+                const int st = i % n_st;
+                umma::mbar_wait(bar_full + st, (i / n_st) & 1);
                 umma::fence_after_sync();
-                const uint32_t g0 = smem_base + st * kUWTileStageBytes, a0 = g0 + kUWTileOperandBytes;
+                const uint32_t g0 = smem_base + st * stage_bytes, a0 = g0 + g_bytes;
 #pragma unroll
                 for (int k = 0; k < kUWTileRows / 16; k++) {
                     // K = 16 sample rows = two k-groups 128 B apart (LBO); next 8 columns 2048 B further (SBO)
@@ -291,6 +292,6 @@ extern "C" int seald_mlp_wgrad_umma(const seald_wgrad_job* jobs, int n_jobs, uin
     const size_t smem = any_tile ? kUWSmemTile : kUWSmem;
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUWSmemTile);
     if (e != cudaSuccess) return (int)e;
-    k_wgrad_umma<<<total, kUWThreads, smem, to_stream(stream)>>>(js, (int)M, m_dev, (uint32_t)(smem - 128));
+    k_wgrad_umma<<<total, kUWThreads, smem, to_stream(stream)>>>(js, (int)M, m_dev, (uint32_t)(smem - 256));
     return launch_status();
 }

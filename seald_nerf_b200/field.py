@@ -91,6 +91,12 @@ DEFORM_IMPL = os.environ.get("SEALD_DEFORM_IMPL", "umma")  # "umma": tcgen05 ker
 TILE_ROWS = 128
 
 
+def heads_tiled():
+    """The heads save what the weight-gradient GEMMs read as 128-row tile images when the tcgen05 weight-gradient kernel consumes it
+    (every job of that kernel then takes the bulk-copy path); the mma.sync kernel reads row-major tensors."""
+    return WGRAD_IMPL == "umma"
+
+
 def tile_image(x):
     """[M, w] row-major fp16 -> the 128-row TILE-IMAGE layout the tcgen05 deformation kernels save their activations in
     (csrc/field_umma.cu, csrc/wgrad_umma.cu): [tile][w / 8][128 rows][8 halves], returned as [ceil128(M), w] (rows beyond M zero)."""
@@ -128,13 +134,17 @@ class FieldWorkspace:
             self.bwd_d = torch.empty(cfg.n_deform - 1, Mp, DEFORM_W, **f16)
             self.gout_d = torch.empty(Mp, 16, **f16)
             self.hs = torch.empty(M, 16, **f16)
-            self.cin = torch.empty(M, HEAD_K0, **f16)
-            self.fwd_s = torch.empty(cfg.n_sigma - 1, M, HEAD_W, **f16)
-            self.fwd_c = torch.empty(cfg.n_color - 1, M, HEAD_W, **f16)
-            self.bwd_s = torch.empty(cfg.n_sigma - 1, M, HEAD_W, **f16)
-            self.bwd_c = torch.empty(cfg.n_color - 1, M, HEAD_W, **f16)
-            self.gout_s = torch.empty(M, 16, **f16)
-            self.gout_c = torch.empty(M, 16, **f16)
+            # heads: tile images (whole 128-row tiles) with the tcgen05 weight-gradient kernel, row-major otherwise
+            self.heads_tiled = heads_tiled()
+            Mh = (M + TILE_ROWS - 1) // TILE_ROWS * TILE_ROWS if self.heads_tiled else M
+            self.cin = torch.empty(Mh, HEAD_K0, **f16)
+            self.feat_img = torch.empty(Mh, HEAD_K0, **f16) if self.heads_tiled else None  # tile-image copy of `feat` (sigma layer 0's A operand)
+            self.fwd_s = torch.empty(cfg.n_sigma - 1, Mh, HEAD_W, **f16)
+            self.fwd_c = torch.empty(cfg.n_color - 1, Mh, HEAD_W, **f16)
+            self.bwd_s = torch.empty(cfg.n_sigma - 1, Mh, HEAD_W, **f16)
+            self.bwd_c = torch.empty(cfg.n_color - 1, Mh, HEAD_W, **f16)
+            self.gout_s = torch.empty(Mh, 16, **f16)
+            self.gout_c = torch.empty(Mh, 16, **f16)
             self.dfeat = torch.empty(M, HEAD_K0, **f16)
             self.grad_x01 = torch.empty(M, 3, **f32)
 
@@ -159,6 +169,26 @@ def deform_backward(cfg, hw, grad_x01, time_dev, M, m_dev, fwd_d, bwd_d, gout_d)
                   ptr(bwd_d), ptr(gout_d), st)
 
 
+def heads_forward(cfg, hw, ws, dirs, M, m_dev, save):
+    """Sigma + colour heads on ws.feat -> ws.sigma, ws.rgb (+ the tensors the backward / weight gradients need when `save`)."""
+    st = _lib.stream()
+    if save and ws.heads_tiled:
+        _lib.call("seald_field_heads_forward_tiled", ptr(ws.feat), ptr(dirs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, M, ptr(m_dev),
+                  cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs), ptr(ws.cin), ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.feat_img), st)
+    else:
+        _lib.call("seald_field_heads_forward", ptr(ws.feat), ptr(dirs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, M, ptr(m_dev),
+                  cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs) if save else None, ptr(ws.cin) if save else None,
+                  ptr(ws.fwd_s) if save else None, ptr(ws.fwd_c) if save else None, st)
+
+
+def heads_backward(cfg, hw, ws, grad_sigma, grad_rgb, M, m_dev):
+    """dL/d(sigma, rgb) -> ws.dfeat (+ bwd_s, bwd_c, gout_s, gout_c for the weight gradients)."""
+    name = "seald_field_heads_backward_tiled" if ws.heads_tiled else "seald_field_heads_backward"
+    _lib.call(name, ptr(grad_sigma), ptr(grad_rgb), ptr(ws.rgb), ptr(ws.hs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, M, ptr(m_dev),
+              cfg.density_scale, ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.bwd_s), ptr(ws.bwd_c), ptr(ws.gout_s), ptr(ws.gout_c), ptr(ws.dfeat),
+              _lib.stream())
+
+
 def mlp_wgrad(jobs, n_jobs, M, m_dev):
     name = "seald_mlp_wgrad_umma" if WGRAD_IMPL == "umma" else "seald_mlp_wgrad"
     _lib.call(name, C.cast(jobs, C.c_void_p), n_jobs, M, ptr(m_dev), _lib.stream())
@@ -173,9 +203,7 @@ def field_forward(cfg, hw, ws, xyzs, dirs, time_dev, table16, offsets, m_dev=Non
     # rows >= *m_dev keep stale x01: the grid kernel clamps nothing, so feed it only well-defined rows
     _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
               cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, ptr(m_dev), st)
-    _lib.call("seald_field_heads_forward", ptr(ws.feat), ptr(dirs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, M, ptr(m_dev),
-              cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs) if save else None, ptr(ws.cin) if save else None,
-              ptr(ws.fwd_s) if save else None, ptr(ws.fwd_c) if save else None, st)
+    heads_forward(cfg, hw, ws, dirs, M, m_dev, save)
 
 
 def _job(G, A, dW, N, K, ldg, lda, ldw, n_real, k_real):
@@ -200,18 +228,19 @@ def wgrad_jobs(cfg, ws, grads32, deform=True):
             jobs.append(_job(G, A, gd[l], 16 if last else DEFORM_W, DEFORM_K0 if l == 0 else DEFORM_W, 0 if tiled else (16 if last else DEFORM_W),
                              0 if tiled else (DEFORM_K0 if l == 0 else DEFORM_W), gd[l].shape[1], 3 if last else DEFORM_W,
                              DEFORM_IN if l == 0 else DEFORM_W))
+    ht = ws.heads_tiled  # tile images: leading dimensions 0, sigma layer 0 reads the tile-image copy of the features
     for l in range(ns):
         last = l == ns - 1
         G = ws.gout_s if last else ws.bwd_s[l]
-        A = ws.feat if l == 0 else ws.fwd_s[l - 1]
-        jobs.append(_job(G, A, gs[l], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W, 16 if last else HEAD_W,
-                         HEAD_K0 if l == 0 else HEAD_W, gs[l].shape[1], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W))
+        A = (ws.feat_img if ht else ws.feat) if l == 0 else ws.fwd_s[l - 1]
+        jobs.append(_job(G, A, gs[l], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W, 0 if ht else (16 if last else HEAD_W),
+                         0 if ht else (HEAD_K0 if l == 0 else HEAD_W), gs[l].shape[1], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W))
     for l in range(nc):
         last = l == nc - 1
         G = ws.gout_c if last else ws.bwd_c[l]
         A = ws.cin if l == 0 else ws.fwd_c[l - 1]
-        jobs.append(_job(G, A, gc[l], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W, 16 if last else HEAD_W,
-                         HEAD_K0 if l == 0 else HEAD_W, gc[l].shape[1], 3 if last else HEAD_W, 31 if l == 0 else HEAD_W))
+        jobs.append(_job(G, A, gc[l], 16 if last else HEAD_W, HEAD_K0 if l == 0 else HEAD_W, 0 if ht else (16 if last else HEAD_W),
+                         0 if ht else (HEAD_K0 if l == 0 else HEAD_W), gc[l].shape[1], 3 if last else HEAD_W, 31 if l == 0 else HEAD_W))
     arr = (_lib.WgradJob * len(jobs))(*jobs)
     return arr, len(jobs)
 
@@ -224,9 +253,7 @@ def field_backward(cfg, hw, ws, grad_sigma, grad_rgb, time_is_zero, table16, off
     pass time_is_zero=False and time_dev: the kernel then zeroes the gradient itself if *time_dev == 0."""
     M = ws.M if M is None else int(M)
     st = _lib.stream()
-    _lib.call("seald_field_heads_backward", ptr(grad_sigma), ptr(grad_rgb), ptr(ws.rgb), ptr(ws.hs), hw.p_sigma, cfg.n_sigma, hw.p_color,
-              cfg.n_color, M, ptr(m_dev), cfg.density_scale, ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.bwd_s), ptr(ws.bwd_c), ptr(ws.gout_s),
-              ptr(ws.gout_c), ptr(ws.dfeat), st)
+    heads_backward(cfg, hw, ws, grad_sigma, grad_rgb, M, m_dev)
     want_dx = deform_grad and not time_is_zero
     _lib.call("seald_grid_encode_backward", ptr(ws.dfeat), ptr(ws.x01), ptr(table16), ptr(offsets), ptr(grad_table32), None,
               ptr(ws.grad_x01) if want_dx else None, M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype,

@@ -413,9 +413,7 @@ class FusedTrainer:
                       _lib.stream())
 
         def heads_fwd():
-            _lib.call("seald_field_heads_forward", ptr(ws.feat), ptr(self.dirs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, M,
-                      ptr(m_dev), cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs), ptr(ws.cin), ptr(ws.fwd_s), ptr(ws.fwd_c),
-                      _lib.stream())
+            F.heads_forward(cfg, hw, ws, self.dirs, M, m_dev, True)
 
         def composite_fwd():
             _lib.call("seald_composite_rays_train_forward", ptr(ws.sigma), ptr(ws.rgb), ptr(self.deltas), ptr(self.rays), M, N, self.T_thresh,
@@ -434,9 +432,7 @@ class FusedTrainer:
                       ptr(self.grad_rgb), _lib.stream())
 
         def heads_bwd():
-            _lib.call("seald_field_heads_backward", ptr(self.grad_sigma), ptr(self.grad_rgb), ptr(ws.rgb), ptr(ws.hs), hw.p_sigma, cfg.n_sigma,
-                      hw.p_color, cfg.n_color, M, ptr(m_dev), cfg.density_scale, ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.bwd_s), ptr(ws.bwd_c),
-                      ptr(ws.gout_s), ptr(ws.gout_c), ptr(ws.dfeat), _lib.stream())
+            F.heads_backward(cfg, hw, ws, self.grad_sigma, self.grad_rgb, M, m_dev)
 
         def grid_scatter():
             # table gradient; also raises the overflow flag when dfeat holds an inf/nan (== the table gradient would)
@@ -703,14 +699,11 @@ class FusedTrainer:
         F.deform_forward(cfg, hw, pts, self.time, B, None, 1, ws.deform, ws.x01, None, None)
         _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(self.table16), ptr(offsets), ptr(ws.feat), None, B, 3, cfg.grid_dim,
                   cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, None, st)
-        _lib.call("seald_field_heads_forward", ptr(ws.feat), ptr(drs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color, B, None,
-                  cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs), ptr(ws.cin), ptr(ws.fwd_s), ptr(ws.fwd_c), st)
+        F.heads_forward(cfg, hw, ws, drs, B, None, True)
         self.loss.zero_()
         _lib.call("seald_l1_pretrain_loss", ptr(ws.sigma), ptr(ws.rgb), ptr(gs), ptr(gc), B, ptr(self.loss_scale), ptr(self.loss),
                   ptr(self.grad_sigma), ptr(self.grad_rgb), st)
-        _lib.call("seald_field_heads_backward", ptr(self.grad_sigma), ptr(self.grad_rgb), ptr(ws.rgb), ptr(ws.hs), hw.p_sigma, cfg.n_sigma,
-                  hw.p_color, cfg.n_color, B, None, cfg.density_scale, ptr(ws.fwd_s), ptr(ws.fwd_c), ptr(ws.bwd_s), ptr(ws.bwd_c),
-                  ptr(ws.gout_s), ptr(ws.gout_c), ptr(ws.dfeat), st)
+        F.heads_backward(cfg, hw, ws, self.grad_sigma, self.grad_rgb, B, None)
         _lib.call("seald_grid_encode_backward_table", ptr(ws.dfeat), ptr(ws.x01), ptr(offsets), ptr(self.grad_table), B, 3, cfg.grid_dim,
                   cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, F32, None,
                   ptr(self.found_inf), st)

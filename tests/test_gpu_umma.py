@@ -97,24 +97,31 @@ def test_umma_wgrad_matches_mma_sync(cuda_dev, M, m_live):
     ws = F.FieldWorkspace(cfg, M, cuda_dev, training=True)
     g = torch.Generator(device=cuda_dev).manual_seed(1)
     n_live = M if m_live is None else m_live
-    deform_bufs = ("in_buf", "fwd_d", "bwd_d", "gout_d")
+    # row-major "truth" of every operand (rows beyond the live count zero, as the kernels leave them in the saved tile images)
+    tiled_bufs = ("in_buf", "fwd_d", "bwd_d", "gout_d", "cin", "fwd_s", "fwd_c", "bwd_s", "bwd_c", "gout_s", "gout_c")
     rowmajor = {}
-    for name in deform_bufs + ("hs", "cin", "fwd_s", "fwd_c", "bwd_s", "bwd_c", "gout_s", "gout_c", "feat"):
+    for name in tiled_bufs + ("feat",):
         t = getattr(ws, name)
         t.copy_(torch.randn(t.shape, device=cuda_dev, generator=g).to(t.dtype))
-        if name in deform_bufs:  # rows beyond the live count are zero in the saved tile images
-            t[..., n_live:, :] = 0
-            rowmajor[name] = t.clone()
+        t[..., n_live:, :] = 0
+        rowmajor[name] = t.clone()
+
+    def to_img(x):
+        return F.tile_image(x) if x.dim() == 2 else torch.stack([F.tile_image(y) for y in x])
+
     m_dev = None if m_live is None else torch.tensor([m_live], dtype=torch.int32, device=cuda_dev)
     outs = []
     for impl in ("mma", "umma"):
-        # mma.sync kernel: row-major operands; tcgen05 kernel: the deformation net's operands as tile images (bulk-copy path)
-        for name in deform_bufs:
-            t, src = getattr(ws, name), rowmajor[name]
-            if impl == "umma":
-                t.copy_(F.tile_image(src) if src.dim() == 2 else torch.stack([F.tile_image(x) for x in src]))
-            else:
-                t.copy_(src)
+        # mma.sync kernel: row-major operands; tcgen05 kernel: every operand as tile images (bulk-copy path), the sigma net's first
+        # layer reading the tile-image copy of the features
+        for name in tiled_bufs:
+            getattr(ws, name).copy_(to_img(rowmajor[name]) if impl == "umma" else rowmajor[name])
+        ws.heads_tiled = impl == "umma"
+        if impl == "umma":
+            Mp = ws.cin.shape[0]
+            feat_p = torch.zeros(Mp, 32, dtype=torch.float16, device=cuda_dev)
+            feat_p[:M] = rowmajor["feat"]
+            ws.feat_img.copy_(F.tile_image(feat_p))
         grads = [torch.zeros_like(w, dtype=torch.float32) for w in net.mlp_weights()]
         old = F.WGRAD_IMPL, F.DEFORM_IMPL
         F.WGRAD_IMPL = F.DEFORM_IMPL = impl
