@@ -445,6 +445,7 @@ def main():
             "grid_fwd": ("hbm", 588.0 * m_live),
             "grid_scatter": ("hbm", 1100.0 * m_live),      # §8(d): 12 + 64 + 2 * 8 * 16 * 2 * 2 (fp16 table); the fp32 table we keep moves 2124
             "grid_input_bwd": ("hbm", (588.0 + 12.0) * m_live),
+            "grid_bwd_both": ("hbm", (1100.0 + 588.0 + 12.0) * m_live),   # scatter + input gradient in one launch
             "march": ("hbm", 48.0 * N_RAYS + 32.0 * m_live + 262144.0),
             "composite_fwd": ("hbm", 24.0 * m_live + 32.0 * N_RAYS),
             "composite_bwd": ("hbm", 40.0 * m_live + 48.0 * N_RAYS),

@@ -67,6 +67,13 @@ int seald_grid_encode_backward(const void* grad_out, const float* x01, const voi
                                uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
                                int grad_table_dtype, const int32_t* b_dev, seald_stream_t stream);
 
+/* Table gradient AND input gradient (recomputed from the table, no dy_dx) of one backward pass in ONE launch where the fast paths
+ * apply (fp32 gradient table, C = 2, D 2..4, 16-byte aligned tables: CTA roles inside k_grid_backward_both; otherwise two launches),
+ * + the GradScaler overflow flag of seald_grid_encode_backward_table. */
+int seald_grid_encode_backward_both(const void* grad_out, const float* x01, const void* table, const int32_t* offsets, void* grad_table,
+                                    float* grad_x, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                    int align_corners, uint32_t interp, int dtype, int grad_table_dtype, const int32_t* b_dev,
+                                    int32_t* found_inf, seald_stream_t stream);
 /* The two halves of seald_grid_encode_backward as separate launches (they are independent: the fused trainer runs the table
  * scatter beside the deformation-net backward on a second stream).  found_inf (optional, device int32): set to a non-zero
  * word (the bits of 1.0f) when a consumed grad_out element is inf/nan; the table gradient is non-finite exactly then, so
@@ -357,6 +364,13 @@ int seald_ffmlp_backward(const void* grad, const void* inputs, const void* weigh
  * [T, frame_bytes] (and row t_idx of occ_all [T,6], optional) into the step's static buffers and zeroes counter[2] (optional). */
 int seald_select_frame(const float* time_dev, uint32_t T, const uint8_t* bitfield_all, uint32_t frame_bytes, uint8_t* bitfield_out,
                        const float* occ_all, float* occ_out, int32_t* counter, seald_stream_t stream);
+/* Start of a fused training step in one launch: seald_select_frame + *loss_sum = 0 (optional) + the step's perturbation noise
+ * (optional: noises [n_noise] uniform in [0,1), what the reference draws with torch.rand per march, raymarching.py:179-181; a
+ * counter-based hash of (noise_ctr2[0], index) so that CUDA-graph replays draw fresh numbers; noise_ctr2 = two zero-initialised
+ * uint64, [0] advances by one per launch). */
+int seald_step_begin(const float* time_dev, uint32_t T, const uint8_t* bitfield_all, uint32_t frame_bytes, uint8_t* bitfield_out,
+                     const float* occ_all, float* occ_out, int32_t* counter, float* loss_sum, float* noises, uint32_t n_noise,
+                     uint64_t* noise_ctr2, seald_stream_t stream);
 /* pred = image + (1 - ws) * bg (bg NULL = white); loss_sum += mean squared error (inv_count = 1/(3N) or 1/(3N*world));
  * grad_image / grad_ws = d(loss_scale * mse)/d(image, ws). */
 int seald_mse_loss_bg(const float* image, const float* weights_sum, const float* bg, const float* gt, uint32_t N, float inv_count,

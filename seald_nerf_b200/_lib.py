@@ -19,6 +19,7 @@ _vp, _u32, _i32, _f32 = C.c_void_p, C.c_uint32, C.c_int, C.c_float
 _SIGS = {
     "seald_grid_encode_forward": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp, _vp],
     "seald_grid_encode_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32, _vp, _vp],
+    "seald_grid_encode_backward_both": [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32, _vp, _vp, _vp],
     "seald_grid_encode_backward_table": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32, _vp, _vp, _vp],
     "seald_grid_encode_backward_input": [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp, _vp],
     "seald_grid_debug_indices": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _vp],
@@ -63,6 +64,7 @@ _SIGS = {
     "seald_ffmlp_forward": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "seald_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp],
     "seald_select_frame": [_vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp],
+    "seald_step_begin": [_vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp],
     "seald_mse_loss_bg": [_vp, _vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_l1_pretrain_loss": [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp],
     "seald_cast_pad_f16": [_vp, _vp, _u32, _u32, _u32, _vp],

@@ -574,14 +574,14 @@ __device__ __forceinline__ bool warp_aggregate(const uint32_t key, float (&v)[C]
 // gradient is non-finite exactly when one of them is (weights are in [0,1], the sums are fp32), so the optimiser's overflow
 // check does not have to re-read the whole table gradient.
 template <typename T, typename TG, uint32_t D, uint32_t C, bool V4>
-__global__ void __launch_bounds__(256) k_grid_scatter(const T* __restrict__ grad, const float* __restrict__ inputs,
+__device__ __forceinline__ void grid_scatter_body(const uint32_t bid, const T* __restrict__ grad, const float* __restrict__ inputs,
                                                       const int* __restrict__ offsets, TG* __restrict__ grad_table,
                                                       const uint32_t B, const uint32_t L, const float S, const uint32_t H,
                                                       const uint32_t gridtype, const bool align_corners, const uint32_t interp,
                                                       const uint32_t points_per_cta, const uint32_t agg_levels,
                                                       const int* __restrict__ b_dev, int* __restrict__ found_inf) {
-    const uint32_t level = blockIdx.x % L;
-    const uint32_t chunk = blockIdx.x / L;
+    const uint32_t level = bid % L;
+    const uint32_t chunk = bid / L;
     const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;  // live rows
     const uint32_t b_begin = chunk * points_per_cta;
     const uint32_t b_end = min(Bn, b_begin + points_per_cta);
@@ -655,9 +655,19 @@ __global__ void __launch_bounds__(256) k_grid_scatter(const T* __restrict__ grad
     if (found_inf && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(found_inf, 0x3f800000);
 }
 
+template <typename T, typename TG, uint32_t D, uint32_t C, bool V4>
+__global__ void __launch_bounds__(256) k_grid_scatter(const T* __restrict__ grad, const float* __restrict__ inputs,
+                                                      const int* __restrict__ offsets, TG* __restrict__ grad_table,
+                                                      const uint32_t B, const uint32_t L, const float S, const uint32_t H,
+                                                      const uint32_t gridtype, const bool align_corners, const uint32_t interp,
+                                                      const uint32_t points_per_cta, const uint32_t agg_levels,
+                                                      const int* __restrict__ b_dev, int* __restrict__ found_inf) {
+    grid_scatter_body<T, TG, D, C, V4>(blockIdx.x, grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align_corners, interp, points_per_cta, agg_levels, b_dev, found_inf);
+}
+
 // grad_x[b, d] = sum_{l,c} grad[b,l,c] * d out[b,l,c] / d x[b,d]; recomputed from the table (fp32 accumulate)
 template <typename T, uint32_t D, uint32_t C, bool PAIR>
-__global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* __restrict__ grad, const float* __restrict__ inputs,
+__device__ __forceinline__ void grid_input_backward_body(const uint32_t bid, const uint32_t nblocks, const T* __restrict__ grad, const float* __restrict__ inputs,
                                                                        const T* __restrict__ table, const int* __restrict__ offsets,
                                                                        float* __restrict__ grad_x, const uint32_t B, const uint32_t L,
                                                                        const float S, const uint32_t H, const uint32_t gridtype,
@@ -668,7 +678,7 @@ __global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* 
     __syncthreads();
     const uint32_t Bn = b_dev ? min(B, (uint32_t)max(*b_dev, 0)) : B;
     constexpr uint32_t NC = 1u << D;
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < Bn; b += gridDim.x * blockDim.x) {
+    for (uint32_t b = bid * blockDim.x + threadIdx.x; b < Bn; b += nblocks * blockDim.x) {
         float x[D];
         bool oob = false;
 #pragma unroll
@@ -727,6 +737,35 @@ __global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* 
 }
 
 // gridencoder.cu:344-369 with fp32 accumulation and the [B, L*C] grad layout.
+template <typename T, uint32_t D, uint32_t C, bool PAIR>
+__global__ void __launch_bounds__(256) k_grid_input_backward_recompute(const T* __restrict__ grad, const float* __restrict__ inputs,
+                                                                       const T* __restrict__ table, const int* __restrict__ offsets,
+                                                                       float* __restrict__ grad_x, const uint32_t B, const uint32_t L,
+                                                                       const float S, const uint32_t H, const uint32_t gridtype,
+                                                                       const bool align_corners, const uint32_t interp,
+                                                                       const int* __restrict__ b_dev) {
+    grid_input_backward_body<T, D, C, PAIR>(blockIdx.x, gridDim.x, grad, inputs, table, offsets, grad_x, B, L, S, H, gridtype, align_corners, interp, b_dev);
+}
+
+// Table scatter and input gradient of one backward pass in ONE launch ("horizontal" fusion): CTAs [0, n_input) run the per-point input
+// gradient (all levels of a point, paired gathers), the others the per-(chunk, level) scatter.  The two are independent, both latency
+// bound at training-batch size, and a kernel boundary costs ~5 us inside the step graph.
+template <typename T, typename TG, uint32_t D, uint32_t C, bool V4, bool PAIR>
+__global__ void __launch_bounds__(256) k_grid_backward_both(const uint32_t n_input, const T* __restrict__ table, float* __restrict__ grad_x,
+                                                            const T* __restrict__ grad, const float* __restrict__ inputs,
+                                                      const int* __restrict__ offsets, TG* __restrict__ grad_table,
+                                                      const uint32_t B, const uint32_t L, const float S, const uint32_t H,
+                                                      const uint32_t gridtype, const bool align_corners, const uint32_t interp,
+                                                      const uint32_t points_per_cta, const uint32_t agg_levels,
+                                                      const int* __restrict__ b_dev, int* __restrict__ found_inf) {
+    if (blockIdx.x < n_input) {
+        grid_input_backward_body<T, D, C, PAIR>(blockIdx.x, n_input, grad, inputs, table, offsets, grad_x, B, L, S, H, gridtype, align_corners, interp,
+                                                b_dev);
+    } else {
+        grid_scatter_body<T, TG, D, C, V4>(blockIdx.x - n_input, grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align_corners, interp, points_per_cta, agg_levels, b_dev, found_inf);
+    }
+}
+
 template <typename T, uint32_t D, uint32_t C>
 __global__ void k_grid_input_backward_dydx(const T* __restrict__ grad, const T* __restrict__ dy_dx, float* __restrict__ grad_x,
                                            const uint32_t B, const uint32_t L, const int* __restrict__ b_dev) {
@@ -889,6 +928,19 @@ int launch_backward(const void* grad, const float* x, const void* table, const i
                     float* grad_x, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align, uint32_t interp,
                     const int* b_dev, int* found_inf, cudaStream_t st) {
     int rc = 0;
+    // both halves, fp32 C = 2 gradient table, paired gathers: ONE launch (k_grid_backward_both); SEALD_GRID_BWD_SPLIT=1 keeps two
+    if constexpr (std::is_same<TG, float>::value && C == 2 && RowPack<T, C>::ok && D >= 2 && D <= 4) {
+        static const bool split = getenv("SEALD_GRID_BWD_SPLIT") && atoi(getenv("SEALD_GRID_BWD_SPLIT")) != 0;
+        if (!split && grad_table && grad_x && !dy_dx && table && (uintptr_t)grad_table % 16 == 0 && (uintptr_t)table % 16 == 0) {
+            const uint32_t ppc = B < (1u << 18) ? 256u : 1024u;
+            const uint32_t n_scatter = div_up(B, ppc) * L, n_input = div_up(B, 256u);
+            const uint32_t agg = default_agg_levels(B, L, S, H);
+            k_grid_backward_both<T, TG, D, C, true, true><<<n_input + n_scatter, 256, 0, st>>>(
+                n_input, (const T*)table, grad_x, (const T*)grad, x, offsets, (TG*)grad_table, B, L, S, H, gridtype, align, interp, ppc, agg, b_dev,
+                found_inf);
+            return launch_status();
+        }
+    }
     if (grad_table) rc = launch_scatter<T, TG, D, C>(grad, x, offsets, grad_table, B, L, S, H, gridtype, align, interp, b_dev, found_inf, st);
     if (rc) return rc;
     if (grad_x) rc = launch_input_backward<T, D, C>(grad, x, table, offsets, dy_dx, grad_x, B, L, S, H, gridtype, align, interp, b_dev, st);
@@ -963,6 +1015,15 @@ extern "C" int seald_grid_encode_backward(const void* grad_out, const float* x01
     if (!grad_table) return SEALD_E_BADARG;
     return grid_backward_any(grad_out, x01, table, offsets, grad_table, dy_dx, grad_x, B, D, C, L, S, H, gridtype, align_corners, interp, dtype,
                              grad_table_dtype, b_dev, nullptr, stream);
+}
+
+extern "C" int seald_grid_encode_backward_both(const void* grad_out, const float* x01, const void* table, const int32_t* offsets,
+                                               void* grad_table, float* grad_x, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                               uint32_t gridtype, int align_corners, uint32_t interp, int dtype, int grad_table_dtype,
+                                               const int32_t* b_dev, int32_t* found_inf, seald_stream_t stream) {
+    if (!grad_table || !grad_x || !table) return SEALD_E_BADARG;
+    return grid_backward_any(grad_out, x01, table, offsets, grad_table, nullptr, grad_x, B, D, C, L, S, H, gridtype, align_corners, interp, dtype,
+                             grad_table_dtype, b_dev, found_inf, stream);
 }
 
 extern "C" int seald_grid_encode_backward_table(const void* grad_out, const float* x01, const int32_t* offsets, void* grad_table, uint32_t B,

@@ -256,9 +256,61 @@ __global__ void k_select_frame(const float* __restrict__ time, const uint32_t T,
     }
 }
 
+// Start of a fused training step in ONE launch: select_frame + the zero of the loss accumulator + the step's perturbation noise
+// (noises [n_noise] uniform in [0, 1): the reference draws torch.rand(N) per march, raymarching.py:179-181).  The noise is a
+// counter-based hash of (ctr[0], ray) — two rounds of a 64-bit mix (splitmix64 finaliser), the top 24 bits as the mantissa — so a
+// CUDA-graph replay produces a fresh stream without host RNG state; ctr[0] is advanced by the LAST CTA to finish (ticket in ctr[1]),
+// after every CTA has read it.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_step_begin(const float* __restrict__ time, const uint32_t T, const uint4* __restrict__ bitfield_all, const uint32_t frame_vec16,
+                             uint4* __restrict__ bitfield_out, const float* __restrict__ occ_all, float* __restrict__ occ_out,
+                             int* __restrict__ counter, float* __restrict__ loss_sum, float* __restrict__ noises, const uint32_t n_noise,
+                             unsigned long long* __restrict__ ctr) {
+    int t_idx = (int)floorf(*time * (float)T);
+    t_idx = min(max(t_idx, 0), (int)T - 1);
+    const uint4* src = bitfield_all + (size_t)t_idx * frame_vec16;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < frame_vec16; i += gridDim.x * blockDim.x) bitfield_out[i] = src[i];
+    if (noises) {
+        const uint64_t base = mix64(ctr[0] * 0x9E3779B97F4A7C15ull + 0x1234567ull);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_noise; i += gridDim.x * blockDim.x)
+            noises[i] = (float)(mix64(base + (uint64_t)i * 0x9E3779B97F4A7C15ull) >> 40) * (1.0f / 16777216.0f);
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 6 && occ_all && occ_out) occ_out[threadIdx.x] = occ_all[(size_t)t_idx * 6 + threadIdx.x];
+        if (threadIdx.x < 2 && counter) counter[threadIdx.x] = 0;
+        if (threadIdx.x == 0 && loss_sum) *loss_sum = 0.0f;
+    }
+    if (noises) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned long long done = atomicAdd(ctr + 1, 1ull) + 1ull;
+            if (done == gridDim.x) { ctr[1] = 0ull; ctr[0] += 1ull; }
+        }
+    }
+}
+
 }  // namespace seald
 
 using namespace seald;
+
+extern "C" int seald_step_begin(const float* time_dev, uint32_t T, const uint8_t* bitfield_all, uint32_t frame_bytes, uint8_t* bitfield_out,
+                                const float* occ_all, float* occ_out, int32_t* counter, float* loss_sum, float* noises, uint32_t n_noise,
+                                uint64_t* noise_ctr2, seald_stream_t stream) {
+    if (!time_dev || !bitfield_all || !bitfield_out || T == 0 || frame_bytes == 0) return SEALD_E_BADARG;
+    if (noises && !noise_ctr2) return SEALD_E_BADARG;
+    if (frame_bytes % 16 || ((uintptr_t)bitfield_all & 15) || ((uintptr_t)bitfield_out & 15)) return SEALD_E_ALIGN;
+    const uint32_t n16 = frame_bytes / 16;
+    const uint32_t blocks = div_up(n16, 256u) < (uint32_t)SEALD_NUM_SMS ? div_up(n16, 256u) : (uint32_t)SEALD_NUM_SMS;
+    k_step_begin<<<blocks, 256, 0, to_stream(stream)>>>(time_dev, T, reinterpret_cast<const uint4*>(bitfield_all), n16,
+                                                       reinterpret_cast<uint4*>(bitfield_out), occ_all, occ_out, counter, loss_sum, noises, n_noise,
+                                                       reinterpret_cast<unsigned long long*>(noise_ctr2));
+    return launch_status();
+}
 
 extern "C" int seald_select_frame(const float* time_dev, uint32_t T, const uint8_t* bitfield_all, uint32_t frame_bytes, uint8_t* bitfield_out,
                                   const float* occ_all, float* occ_out, int32_t* counter, seald_stream_t stream) {

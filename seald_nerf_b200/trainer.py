@@ -178,6 +178,7 @@ class FusedTrainer:
         self.bg = torch.ones(N, 3, **f32)
         self.time = self.inputs[9 * N:9 * N + 1]
         self.noises = torch.zeros(N, **f32)
+        self.noise_ctr = torch.zeros(2, dtype=torch.int64, device=dev)  # seald_step_begin: {draw counter, CTA ticket}
         self.nears = torch.empty(N, **f32)
         self.fars = torch.empty(N, **f32)
         self.bitfield_frame = torch.zeros(model.density_bitfield.shape[1], dtype=torch.uint8, device=dev)
@@ -392,11 +393,11 @@ class FusedTrainer:
         F16, F32 = _lib.F16, _lib.F32
 
         def select_frame():
-            # occupancy frame of this time stamp (dnerf/renderer.py:285) + its occupied-cell box, selected on the device; counter reset
-            _lib.call("seald_select_frame", ptr(self.time), int(m.time_size), ptr(m.density_bitfield), int(m.density_bitfield.shape[1]),
-                      ptr(self.bitfield_frame), ptr(self.occ_all), ptr(self.occ_frame), ptr(self.counter), _lib.stream())
-            if self.perturb:
-                self.noises.uniform_(0, 1)
+            # occupancy frame of this time stamp (dnerf/renderer.py:285) + its occupied-cell box, selected on the device; sample counter
+            # and loss accumulator reset; this step's perturbation noise (a counter-based hash: graph replays draw fresh numbers)
+            _lib.call("seald_step_begin", ptr(self.time), int(m.time_size), ptr(m.density_bitfield), int(m.density_bitfield.shape[1]),
+                      ptr(self.bitfield_frame), ptr(self.occ_all), ptr(self.occ_frame), ptr(self.counter), ptr(self.loss),
+                      ptr(self.noises) if self.perturb else None, N, ptr(self.noise_ctr), _lib.stream())
 
         def march():
             _lib.call("seald_march_rays_train", ptr(self.rays_o), ptr(self.rays_d), ptr(self.bitfield_frame), float(m.bound), self.dt_gamma,
@@ -440,6 +441,12 @@ class FusedTrainer:
                       cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, F32, ptr(m_dev),
                       ptr(self.found_inf), _lib.stream())
 
+        def grid_bwd_both():
+            # table scatter + input gradient in one launch (CTA roles): both only need dfeat and x01 and are latency bound at this size
+            _lib.call("seald_grid_encode_backward_both", ptr(ws.dfeat), ptr(ws.x01), ptr(self.table16), ptr(offsets), ptr(self.grad_table),
+                      ptr(ws.grad_x01), M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners),
+                      cfg.interp, F16, F32, ptr(m_dev), ptr(self.found_inf), _lib.stream())
+
         def grid_input_bwd():
             _lib.call("seald_grid_encode_backward_input", ptr(ws.dfeat), ptr(ws.x01), ptr(self.table16), ptr(offsets), None, ptr(ws.grad_x01),
                       M, 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16,
@@ -452,20 +459,26 @@ class FusedTrainer:
             F.mlp_wgrad(self.jobs, self.n_jobs, M, m_dev)
 
         def composite_loss_fused():
-            # composite forward + loss + composite backward in one kernel (bg/gt are indexed by ray)
-            self.loss.zero_()
+            # composite forward + loss + composite backward in one kernel (bg/gt are indexed by ray); the loss accumulator was zeroed by
+            # the step's first kernel
             _lib.call("seald_composite_train_loss_fused", ptr(ws.sigma), ptr(ws.rgb), ptr(self.deltas), ptr(self.rays), M, N, self.T_thresh,
                       ptr(self.bg), ptr(self.gt), inv_count, ptr(self.loss_scale), ptr(self.weights_sum), ptr(self.depth), ptr(self.image),
                       ptr(self.pred), ptr(self.loss), ptr(self.grad_sigma), ptr(self.grad_rgb), _lib.stream())
 
         if self.fuse_composite:
-            tail = [("composite_loss_fused", composite_loss_fused, 2)]
+            tail = [("composite_loss_fused", composite_loss_fused, 1)]
         else:
             tail = [("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3)]
-        stages = [("select_frame", select_frame, 2), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
-                  ("heads_fwd", heads_fwd, 1)] + tail + [("heads_bwd", heads_bwd, 1), ("grid_scatter", grid_scatter, 1)]
-        if self.train_deform:
-            stages += [("grid_input_bwd", grid_input_bwd, 1), ("deform_bwd", deform_bwd, 1)]
+        stages = [("select_frame", select_frame, 1), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
+                  ("heads_fwd", heads_fwd, 1)] + tail + [("heads_bwd", heads_bwd, 1)]
+        # one GPU: scatter and input gradient share a launch; data parallel: the scatter runs on the side stream ahead of the exchange
+        both = self.train_deform and self.dp_mode == "single" and not self.fork_scatter and os.environ.get("SEALD_GRID_BWD_SPLIT", "0") == "0"
+        if both:
+            stages += [("grid_bwd_both", grid_bwd_both, 1), ("deform_bwd", deform_bwd, 1)]
+        else:
+            stages.append(("grid_scatter", grid_scatter, 1))
+            if self.train_deform:
+                stages += [("grid_input_bwd", grid_input_bwd, 1), ("deform_bwd", deform_bwd, 1)]
         stages.append(("wgrad", wgrad, 1))
         return stages
 
@@ -528,6 +541,7 @@ class FusedTrainer:
         run("deform_fwd")
         main.wait_stream(side)
         run("grid_fwd", "heads_fwd", "composite_fwd", "loss", "composite_bwd", "composite_loss_fused", "heads_bwd")
+        run("grid_bwd_both")  # (one GPU: scatter + input gradient in one launch; then "grid_scatter" / "grid_input_bwd" below are absent)
         # ---- the table scatter (atomics) beside the tensor-core backward of the deformation net
         fork = self.fork_scatter or mode in ("fused", "sharded", "allreduce")
         if fork:

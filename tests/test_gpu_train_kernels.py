@@ -110,3 +110,45 @@ def test_overflow_skips_update_and_backs_off_like_gradscaler(cuda_dev):
         _lib.call("seald_loss_scale_update", ptr(scale), ptr(found), ptr(tracker), 2.0, 0.5, 3, ptr(step_dev), _lib.stream())
         assert int(step_dev) == k + 1
     assert float(scale) == 65536.0 and int(tracker) == 0
+
+
+def test_step_begin_selects_the_frame_and_draws_fresh_uniform_noise(cuda_dev):
+    """seald_step_begin: frame selection like seald_select_frame + loss reset + counter-based uniform noise in [0, 1) that changes with
+    every launch (graph replays included) and is reproducible from the counter."""
+    from seald_nerf_b200 import _lib
+    from seald_nerf_b200._lib import ptr
+    T, fb, N = 8, 4096, 4096
+    bits = torch.randint(0, 255, (T, fb), dtype=torch.uint8, device=cuda_dev)
+    occ = torch.rand(T, 6, device=cuda_dev)
+    out = torch.zeros(fb, dtype=torch.uint8, device=cuda_dev); occ_out = torch.zeros(6, device=cuda_dev)
+    counter = torch.full((2,), 9, dtype=torch.int32, device=cuda_dev); loss = torch.full((1,), 3.0, device=cuda_dev)
+    noises = torch.zeros(N, device=cuda_dev); ctr = torch.zeros(2, dtype=torch.int64, device=cuda_dev)
+    time = torch.tensor([0.63], device=cuda_dev)
+
+    def call():
+        _lib.call("seald_step_begin", ptr(time), T, ptr(bits), fb, ptr(out), ptr(occ), ptr(occ_out), ptr(counter), ptr(loss), ptr(noises), N,
+                  ptr(ctr), _lib.stream())
+    call()
+    torch.cuda.synchronize()
+    t_idx = int(0.63 * T)
+    assert torch.equal(out, bits[t_idx]) and torch.equal(occ_out, occ[t_idx]) and int(counter.sum()) == 0 and float(loss) == 0.0
+    a = noises.clone()
+    assert float(a.min()) >= 0.0 and float(a.max()) < 1.0 and abs(float(a.mean()) - 0.5) < 0.02 and abs(float(a.std()) - 0.2887) < 0.01
+    assert ctr.tolist() == [1, 0]
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        call()
+        with torch.cuda.graph(g):
+            call()
+    torch.cuda.current_stream().wait_stream(s)
+    draws = [noises.clone()]
+    for _ in range(3):
+        g.replay(); torch.cuda.synchronize()
+        draws.append(noises.clone())
+    assert int(ctr[0]) == 5 and all(not torch.equal(x, y) for x, y in zip(draws, draws[1:])) and not torch.equal(draws[0], a)
+    # lag-1 correlation between consecutive draws and between neighbouring rays ~ 0
+    c1 = float(torch.corrcoef(torch.stack([draws[1], draws[2]]))[0, 1]); c2 = float(torch.corrcoef(torch.stack([a[:-1], a[1:]]))[0, 1])
+    assert abs(c1) < 0.06 and abs(c2) < 0.06
+    ctr.zero_(); call(); torch.cuda.synchronize()
+    assert torch.equal(noises, a)  # same counter -> same numbers
