@@ -443,6 +443,7 @@ def main():
             "heads_fwd": ("tensor", 2.0 * mac_heads * m_live),
             "heads_bwd": ("tensor", 2.0 * mac_heads * m_live),
             "grid_fwd": ("hbm", 588.0 * m_live),
+            "grid_heads_fwd": ("hbm", 588.0 * m_live),   # encoder + heads in one launch, reported on the encoder's bytes
             "grid_scatter": ("hbm", 1100.0 * m_live),      # §8(d): 12 + 64 + 2 * 8 * 16 * 2 * 2 (fp16 table); the fp32 table we keep moves 2124
             "grid_input_bwd": ("hbm", (588.0 + 12.0) * m_live),
             "grid_bwd_both": ("hbm", (1100.0 + 588.0 + 12.0) * m_live),   # scatter + input gradient in one launch

@@ -327,6 +327,19 @@ int seald_field_heads_backward_tiled(const float* grad_sigma, const float* grad_
                                      const int32_t* m_dev, float density_scale, const void* fwd_s, const void* fwd_c, void* bwd_s, void* bwd_c,
                                      void* gout_s, void* gout_c, void* dfeat, seald_stream_t stream);
 
+/* Hash-grid encoder FUSED into the heads / the density head (one launch instead of seald_grid_encode_forward + seald_field_heads_forward
+ * resp. seald_field_sigma_forward; the 32 features never reach HBM): D = 3, C = 2, L = 16, fp16 table (16-byte aligned), same gathers
+ * and interpolation order as seald_grid_encode_forward — bit-identical features.  Training (hs != NULL) saves tile images like
+ * seald_field_heads_forward_tiled (feat_img required); hs == NULL: inference.  Other grid shapes: SEALD_E_UNSUPPORTED (use the two calls). */
+int seald_field_grid_heads_forward(const float* x01, const void* table, const int32_t* offsets, uint32_t D, uint32_t C, uint32_t L, float S,
+                                   uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp, const float* dirs,
+                                   const void* const* w_sigma, int n_sigma, const void* const* w_color, int n_color, uint32_t M,
+                                   const int32_t* m_dev, float density_scale, float* sigma, float* rgb, void* hs, void* cin, void* fwd_s,
+                                   void* fwd_c, void* feat_img, seald_stream_t stream);
+int seald_field_grid_sigma_forward(const float* x01, const void* table, const int32_t* offsets, uint32_t D, uint32_t C, uint32_t L, float S,
+                                   uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp, const void* const* w_sigma, int n_sigma,
+                                   uint32_t M, float density_scale, float* sigma, void* geo, seald_stream_t stream);
+
 /* Weight gradients dW[N][K] += G[M][N]^T A[M][K] (fp16 in, fp32 atomics out); replaces the CUTLASS split-K GEMMs of
  * ffmlp_backward (ffmlp/src/ffmlp.cu:801-877).  Up to 16 jobs per launch. */
 typedef struct {

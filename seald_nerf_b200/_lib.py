@@ -56,6 +56,9 @@ _SIGS = {
     "seald_field_deform_backward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
     "seald_field_heads_forward": [_vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_field_sigma_forward": [_vp, _vp, _i32, _u32, _f32, _vp, _vp, _vp],
+    "seald_field_grid_heads_forward": [_vp, _vp, _vp, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "seald_field_grid_sigma_forward": [_vp, _vp, _vp, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _vp, _i32, _u32, _f32, _vp, _vp, _vp],
     "seald_field_heads_forward_tiled": [_vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_field_heads_backward_tiled": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_field_heads_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -14,6 +14,7 @@
 #include <string>
 
 #include "encoders.cuh"
+#include "grid_device.cuh"
 #include "mlp.cuh"
 
 namespace seald {
@@ -315,8 +316,22 @@ __device__ __forceinline__ void warp_head_mlp(const __half* sw, const int n_laye
 
 // TILED (training, tcgen05 weight gradients): fwd_s / fwd_c / cin and a copy of the input features (feat_img) are saved as 128-row
 // tile images with M_ld = M rounded up to 128 rows per layer; every row of a live tile is written (dead rows: zeros).
-template <bool SAVE, bool SIGMA_ONLY, bool TILED>
-__global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __half* __restrict__ feat, const float* __restrict__ dirs,
+// GRID: the 32 input features are not read from HBM but ENCODED here — the hash-grid forward (grid_encoder.cu's k_grid_forward_pair,
+// same gathers, same interpolation order: bit-identical features) for 16 levels x 2 features, fp16 table: lane = (row, half of the
+// levels), 8 levels each in two passes of 4 with all gathers in flight, the 16 halves written straight into the warp's input tile.
+// One launch and one HBM round trip of the features (64 B / sample each way) less per field evaluation.
+struct GridArgs {
+    const float* x01;     // [M,3] positions in [0,1]
+    const __half* table;  // fp16 table (16-byte aligned)
+    const int* offsets;   // [L+1]
+    float S;
+    uint32_t H, gridtype, interp;
+    bool align_corners;
+};
+
+template <bool SAVE, bool SIGMA_ONLY, bool TILED, bool GRID>
+__global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __half* __restrict__ feat, const GridArgs ga,
+                                                                       const float* __restrict__ dirs,
                                                                        const MlpWeights mw_s, const MlpWeights mw_c, const int M,
                                                                        const int* __restrict__ m_dev, const float density_scale,
                                                                        float* __restrict__ sigma, float* __restrict__ rgb,
@@ -331,6 +346,10 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __h
     __half* s_in = reinterpret_cast<__half*>(warp_base + (size_t)warp * kHrWarpBytes);
     float* s_out = reinterpret_cast<float*>(s_in + 16 * kHrK0Stride);
     const int m_used = m_dev ? min(M, max(*m_dev, 0)) : M;
+    __shared__ LevelParams s_lp[16];
+    if constexpr (GRID) {
+        if (threadIdx.x < 16) s_lp[threadIdx.x] = make_level(ga.offsets, threadIdx.x, ga.S, ga.H, 3, ga.gridtype, ga.align_corners);
+    }
 
     // ---- the weights, once per CTA
 #pragma unroll 1
@@ -352,15 +371,70 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_heads_forward_warp(const __h
     const int n_slabs = (SAVE && TILED) ? (m_used + 127) / 128 * 8 : (m_used + 15) / 16;   // tile images: whole live tiles
     for (int slab = blockIdx.x * (kMlpThreads / 32) + warp; slab < n_slabs; slab += gridDim.x * (kMlpThreads / 32)) {
         const int row0 = slab * 16;
-        // ---- 16 feature rows x 64 bytes: two 16-byte chunks per lane
+        if constexpr (GRID) {
+            // ---- encode: lane = (row r, levels [8 h, 8 h + 8))
+            const int r = lane >> 1, h = lane & 1, row = row0 + r;
+            float x[3] = {0.f, 0.f, 0.f};
+            bool live = row < m_used;
+            if (live) {
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const int idx = lane * 2 + c, r = idx >> 2, ch = idx & 3;
-            const int row = row0 + r;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (row < m_used) v = __ldg(reinterpret_cast<const uint4*>(feat + (size_t)row * 32 + ch * 8));
-            *reinterpret_cast<uint4*>(s_in + r * kHrK0Stride + ch * 8) = v;
-            if (SAVE && TILED) *reinterpret_cast<uint4*>(feat_img + tile_img_off<kHeadK0>(row, ch * 8)) = v;
+                for (int d = 0; d < 3; d++) {
+                    x[d] = ga.x01[(size_t)row * 3 + d];
+                    if (x[d] < 0 || x[d] > 1) live = false;  // outside [0,1]: zero features (gridencoder.cu:117-131)
+                }
+            }
+            constexpr int GL = 2;  // levels in flight per pass (4 would need > 128 registers next to the MLP fragments: spills)
+            uint32_t w[8];
+#pragma unroll
+            for (int pass = 0; pass < 8 / GL; pass++) {
+                CellGather<__half, 3, 2> cg[GL];
+                float pos[GL][3], deriv[GL][3];
+                if (live) {
+#pragma unroll
+                    for (int g = 0; g < GL; g++) {
+                        const LevelParams lp = s_lp[h * 8 + pass * GL + g];
+                        uint32_t pos_grid[3];
+                        locate<3>(x, lp, ga.align_corners, ga.interp, pos[g], deriv[g], pos_grid);
+                        cg[g].issue(ga.table, ga.gridtype, ga.align_corners, lp, pos_grid);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < GL; g++) {
+                    float res[2] = {0.f, 0.f};
+                    if (live) {
+                        float val[8][2];
+                        cg[g].resolve(val);
+#pragma unroll
+                        for (uint32_t idx = 0; idx < 8; idx++) {
+                            float wt = 1;
+#pragma unroll
+                            for (uint32_t d = 0; d < 3; d++) wt *= ((idx >> d) & 1u) ? pos[g][d] : 1 - pos[g][d];
+                            res[0] += wt * val[idx][0];
+                            res[1] += wt * val[idx][1];
+                        }
+                    }
+                    __half hh[2];
+                    Row<__half, 2>::store(hh, res);
+                    w[pass * GL + g] = *reinterpret_cast<const uint32_t*>(hh);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint4 v = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                *reinterpret_cast<uint4*>(s_in + r * kHrK0Stride + h * 16 + q * 8) = v;
+                if (SAVE && TILED) *reinterpret_cast<uint4*>(feat_img + tile_img_off<kHeadK0>(row, h * 16 + q * 8)) = v;
+            }
+        } else {
+            // ---- 16 feature rows x 64 bytes: two 16-byte chunks per lane
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int idx = lane * 2 + c, r = idx >> 2, ch = idx & 3;
+                const int row = row0 + r;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (row < m_used) v = __ldg(reinterpret_cast<const uint4*>(feat + (size_t)row * 32 + ch * 8));
+                *reinterpret_cast<uint4*>(s_in + r * kHrK0Stride + ch * 8) = v;
+                if (SAVE && TILED) *reinterpret_cast<uint4*>(feat_img + tile_img_off<kHeadK0>(row, ch * 8)) = v;
+            }
         }
         __syncwarp();
         warp_head_mlp<SAVE, TILED>(sw_s, mw_s.n_layers, s_in, s_out, fwd_s, M_ld, m_used, row0);
@@ -770,9 +844,10 @@ extern "C" int seald_field_deform_backward(const float* grad_x01, const float* t
 
 static int heads_forward_impl(const void* feat, const float* dirs, const void* const* w_sigma, int n_sigma, const void* const* w_color,
                               int n_color, uint32_t M, const int32_t* m_dev, float density_scale, float* sigma, float* rgb, void* hs,
-                              void* cin, void* fwd_s, void* fwd_c, void* feat_img, seald_stream_t stream) {
+                              void* cin, void* fwd_s, void* fwd_c, void* feat_img, seald_stream_t stream, const GridArgs* grid = nullptr) {
     if (M == 0) return 0;
-    if (!feat || !dirs || !sigma || !rgb) return SEALD_E_BADARG;
+    if ((!feat && !grid) || !dirs || !sigma || !rgb) return SEALD_E_BADARG;
+    const GridArgs ga = grid ? *grid : GridArgs{};
     const bool save = hs != nullptr;
     const bool tiled = feat_img != nullptr;
     if (save && (!cin || !fwd_s || !fwd_c)) return SEALD_E_BADARG;
@@ -786,27 +861,29 @@ static int heads_forward_impl(const void* feat, const float* dirs, const void* c
     // the fallback when the nets are too deep for their weights to stay in shared memory)
     static const bool tile_impl = getenv("SEALD_HEADS_IMPL") && std::string(getenv("SEALD_HEADS_IMPL")) == "tile";
     const size_t smem_res = (size_t)(head_weight_halves(n_sigma) + head_weight_halves(n_color)) * 2 + (kMlpThreads / 32) * kHrWarpBytes;
-    if (tiled && (tile_impl || smem_res > 96 * 1024)) return SEALD_E_UNSUPPORTED;  // tile images are written by the warp kernel only
+    if ((tiled || grid) && (tile_impl || smem_res > 96 * 1024)) return SEALD_E_UNSUPPORTED;  // tile images / fused encoder: warp kernel only
+    if (grid && save && !tiled) return SEALD_E_UNSUPPORTED;
     if (!tile_impl && smem_res <= 96 * 1024) {
         const uint32_t slabs = tiled ? div_up(M, 128u) * 8u : div_up(M, 16u);
         uint32_t blocks = div_up(slabs, (uint32_t)(kMlpThreads / 32));
         if (blocks > 2u * SEALD_NUM_SMS) blocks = 2u * SEALD_NUM_SMS;
+#define SEALD_LAUNCH_HEADS(SAVE_, TILED_, GRID_, HS, CIN, FS, FC, FIMG)                                                                  \
+    do {                                                                                                                             \
+        auto k = k_heads_forward_warp<SAVE_, false, TILED_, GRID_>;                                                                  \
+        if ((rc = set_smem(k, smem_res))) return rc;                                                                                 \
+        k<<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, ga, dirs, ms, mc, (int)M, m_dev, density_scale, sigma, rgb,    \
+                                                 (__half*)(HS), (__half*)(CIN), (__half*)(FS), (__half*)(FC), nullptr, (__half*)(FIMG)); \
+    } while (0)
         if (save && tiled) {
-            if ((rc = set_smem(k_heads_forward_warp<true, false, true>, smem_res))) return rc;
-            k_heads_forward_warp<true, false, true><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev,
-                                                                                          density_scale, sigma, rgb, (__half*)hs, (__half*)cin,
-                                                                                          (__half*)fwd_s, (__half*)fwd_c, nullptr, (__half*)feat_img);
+            if (grid) SEALD_LAUNCH_HEADS(true, true, true, hs, cin, fwd_s, fwd_c, feat_img);
+            else SEALD_LAUNCH_HEADS(true, true, false, hs, cin, fwd_s, fwd_c, feat_img);
         } else if (save) {
-            if ((rc = set_smem(k_heads_forward_warp<true, false, false>, smem_res))) return rc;
-            k_heads_forward_warp<true, false, false><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev,
-                                                                                           density_scale, sigma, rgb, (__half*)hs, (__half*)cin,
-                                                                                           (__half*)fwd_s, (__half*)fwd_c, nullptr, nullptr);
+            SEALD_LAUNCH_HEADS(true, false, false, hs, cin, fwd_s, fwd_c, nullptr);
         } else {
-            if ((rc = set_smem(k_heads_forward_warp<false, false, false>, smem_res))) return rc;
-            k_heads_forward_warp<false, false, false><<<blocks, kMlpThreads, smem_res, st>>>((const __half*)feat, dirs, ms, mc, (int)M, m_dev,
-                                                                                            density_scale, sigma, rgb, nullptr, nullptr, nullptr,
-                                                                                            nullptr, nullptr, nullptr);
+            if (grid) SEALD_LAUNCH_HEADS(false, false, true, nullptr, nullptr, nullptr, nullptr, nullptr);
+            else SEALD_LAUNCH_HEADS(false, false, false, nullptr, nullptr, nullptr, nullptr, nullptr);
         }
+#undef SEALD_LAUNCH_HEADS
         return launch_status();
     }
     const size_t smem = HeadSmem::BYTES;
@@ -838,10 +915,11 @@ extern "C" int seald_field_heads_forward_tiled(const void* feat, const float* di
                               stream);
 }
 
-extern "C" int seald_field_sigma_forward(const void* feat, const void* const* w_sigma, int n_sigma, uint32_t M, float density_scale, float* sigma,
-                                         void* geo, seald_stream_t stream) {
+static int sigma_forward_impl(const void* feat, const void* const* w_sigma, int n_sigma, uint32_t M, float density_scale, float* sigma,
+                              void* geo, seald_stream_t stream, const GridArgs* grid) {
     if (M == 0) return 0;
-    if (!feat || !sigma) return SEALD_E_BADARG;
+    if ((!feat && !grid) || !sigma) return SEALD_E_BADARG;
+    const GridArgs ga = grid ? *grid : GridArgs{};
     MlpWeights ms;
     int rc = make_weights(ms, w_sigma, n_sigma, kHeadK0, kHeadK0, 16);
     if (rc) return rc;
@@ -851,16 +929,54 @@ extern "C" int seald_field_sigma_forward(const void* feat, const void* const* w_
         const uint32_t slabs = div_up(M, 16u);
         uint32_t blocks = div_up(slabs, (uint32_t)(kMlpThreads / 32));
         if (blocks > 2u * SEALD_NUM_SMS) blocks = 2u * SEALD_NUM_SMS;
-        if ((rc = set_smem(k_heads_forward_warp<false, true, false>, smem_res))) return rc;
-        k_heads_forward_warp<false, true, false><<<blocks, kMlpThreads, smem_res, to_stream(stream)>>>((const __half*)feat, nullptr, ms, ms, (int)M,
-                                                                                                      nullptr, density_scale, sigma, nullptr, nullptr,
-                                                                                                      nullptr, nullptr, nullptr, (__half*)geo, nullptr);
+        auto k = grid ? k_heads_forward_warp<false, true, false, true> : k_heads_forward_warp<false, true, false, false>;
+        if ((rc = set_smem(k, smem_res))) return rc;
+        k<<<blocks, kMlpThreads, smem_res, to_stream(stream)>>>((const __half*)feat, ga, nullptr, ms, ms, (int)M, nullptr, density_scale, sigma,
+                                                                nullptr, nullptr, nullptr, nullptr, nullptr, (__half*)geo, nullptr);
         return launch_status();
     }
+    if (grid) return SEALD_E_UNSUPPORTED;
     const size_t smem = HeadSmem::BYTES;
     if ((rc = set_smem(k_sigma_forward, smem))) return rc;
     k_sigma_forward<<<tiles_grid(M, 2), kMlpThreads, smem, to_stream(stream)>>>((const __half*)feat, ms, (int)M, density_scale, sigma, (__half*)geo);
     return launch_status();
+}
+
+extern "C" int seald_field_sigma_forward(const void* feat, const void* const* w_sigma, int n_sigma, uint32_t M, float density_scale, float* sigma,
+                                         void* geo, seald_stream_t stream) {
+    return sigma_forward_impl(feat, w_sigma, n_sigma, M, density_scale, sigma, geo, stream, nullptr);
+}
+
+// hash-grid encoder (16 levels x 2 features, 3-D, fp16 table) fused into the heads / the density head
+static int make_grid_args(GridArgs& ga, const float* x01, const void* table, const int32_t* offsets, uint32_t D, uint32_t C, uint32_t L, float S,
+                          uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp) {
+    if (!x01 || !table || !offsets) return SEALD_E_BADARG;
+    if (D != 3 || C != 2 || L != 16 || gridtype > 1 || interp > 1) return SEALD_E_UNSUPPORTED;
+    if ((uintptr_t)table % 16) return SEALD_E_ALIGN;
+    ga = GridArgs{x01, (const __half*)table, offsets, S, H, gridtype, interp, align_corners != 0};
+    return 0;
+}
+
+extern "C" int seald_field_grid_heads_forward(const float* x01, const void* table, const int32_t* offsets, uint32_t D, uint32_t C, uint32_t L,
+                                              float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp, const float* dirs,
+                                              const void* const* w_sigma, int n_sigma, const void* const* w_color, int n_color, uint32_t M,
+                                              const int32_t* m_dev, float density_scale, float* sigma, float* rgb, void* hs, void* cin,
+                                              void* fwd_s, void* fwd_c, void* feat_img, seald_stream_t stream) {
+    GridArgs ga;
+    int rc = make_grid_args(ga, x01, table, offsets, D, C, L, S, H, gridtype, align_corners, interp);
+    if (rc) return rc;
+    return heads_forward_impl(nullptr, dirs, w_sigma, n_sigma, w_color, n_color, M, m_dev, density_scale, sigma, rgb, hs, cin, fwd_s, fwd_c, feat_img,
+                              stream, &ga);
+}
+
+extern "C" int seald_field_grid_sigma_forward(const float* x01, const void* table, const int32_t* offsets, uint32_t D, uint32_t C, uint32_t L,
+                                              float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp,
+                                              const void* const* w_sigma, int n_sigma, uint32_t M, float density_scale, float* sigma, void* geo,
+                                              seald_stream_t stream) {
+    GridArgs ga;
+    int rc = make_grid_args(ga, x01, table, offsets, D, C, L, S, H, gridtype, align_corners, interp);
+    if (rc) return rc;
+    return sigma_forward_impl(nullptr, w_sigma, n_sigma, M, density_scale, sigma, geo, stream, &ga);
 }
 
 static int heads_backward_impl(const float* grad_sigma, const float* grad_rgb, const float* rgb, const void* hs,

@@ -181,6 +181,33 @@ def heads_forward(cfg, hw, ws, dirs, M, m_dev, save):
                   ptr(ws.fwd_s) if save else None, ptr(ws.fwd_c) if save else None, st)
 
 
+FUSE_GRID_HEADS = os.environ.get("SEALD_FUSE_GRID_HEADS", "1") != "0"  # measurement switch
+
+
+def grid_heads_fusable(cfg, ws, save):
+    """The encoder runs inside the heads kernel for the field's own grid shape (3-D, 16 levels x 2 features, fp16 table) in TRAINING
+    (tile-image saves, tcgen05 weight gradients): at training-batch size the step is bound by kernel boundaries and the fused kernel
+    saves one (0.0201 -> 0.0177 ms + the boundary).  Inference keeps the two kernels: on millions of samples the fused kernel's
+    two-levels-in-flight gather (its register budget is shared with the MLP fragments) is slower (800x800 frame 4.13 vs 4.58 ms)."""
+    return FUSE_GRID_HEADS and save and cfg.grid_dim == 2 and cfg.grid_levels == 16 and ws.heads_tiled
+
+
+def grid_heads_forward(cfg, hw, ws, dirs, table16, offsets, M, m_dev, save):
+    """ws.x01 -> hash-grid features -> sigma / colour heads -> ws.sigma, ws.rgb: ONE launch when grid_heads_fusable (the features stay
+    in shared memory; ws.feat is not written), else encoder + heads."""
+    st = _lib.stream()
+    if grid_heads_fusable(cfg, ws, save):
+        _lib.call("seald_field_grid_heads_forward", ptr(ws.x01), ptr(table16), ptr(offsets), 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S,
+                  cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, ptr(dirs), hw.p_sigma, cfg.n_sigma, hw.p_color, cfg.n_color,
+                  M, ptr(m_dev), cfg.density_scale, ptr(ws.sigma), ptr(ws.rgb), ptr(ws.hs) if save else None, ptr(ws.cin) if save else None,
+                  ptr(ws.fwd_s) if save else None, ptr(ws.fwd_c) if save else None, ptr(ws.feat_img) if save else None, st)
+        return 1
+    _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
+              cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, ptr(m_dev), st)
+    heads_forward(cfg, hw, ws, dirs, M, m_dev, save)
+    return 2
+
+
 def heads_backward(cfg, hw, ws, grad_sigma, grad_rgb, M, m_dev):
     """dL/d(sigma, rgb) -> ws.dfeat (+ bwd_s, bwd_c, gout_s, gout_c for the weight gradients)."""
     name = "seald_field_heads_backward_tiled" if ws.heads_tiled else "seald_field_heads_backward"
@@ -201,9 +228,7 @@ def field_forward(cfg, hw, ws, xyzs, dirs, time_dev, table16, offsets, m_dev=Non
     save = ws.training
     deform_forward(cfg, hw, xyzs, time_dev, M, m_dev, t0_mode, ws.deform, ws.x01, ws.in_buf if save else None, ws.fwd_d if save else None)
     # rows >= *m_dev keep stale x01: the grid kernel clamps nothing, so feed it only well-defined rows
-    _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
-              cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, ptr(m_dev), st)
-    heads_forward(cfg, hw, ws, dirs, M, m_dev, save)
+    grid_heads_forward(cfg, hw, ws, dirs, table16, offsets, M, m_dev, save)
 
 
 def _job(G, A, dW, N, K, ldg, lda, ldw, n_real, k_real):
@@ -268,6 +293,12 @@ def field_density(cfg, hw, ws, xyzs, time_dev, table16, offsets, M=None):
     M = ws.M if M is None else int(M)
     st = _lib.stream()
     deform_forward(cfg, hw, xyzs, time_dev, M, None, 2, ws.deform, ws.x01, None, None)
+    # encoder inside the density head: one launch, no feature round trip (occupancy refresh: partial pass 61.8 -> 53.5 ms, full sweep equal)
+    if FUSE_GRID_HEADS and cfg.grid_dim == 2 and cfg.grid_levels == 16:
+        _lib.call("seald_field_grid_sigma_forward", ptr(ws.x01), ptr(table16), ptr(offsets), 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S,
+                  cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, hw.p_sigma, cfg.n_sigma, M, cfg.density_scale, ptr(ws.sigma),
+                  None, st)
+        return
     _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
               cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, None, st)
     _lib.call("seald_field_sigma_forward", ptr(ws.feat), hw.p_sigma, cfg.n_sigma, M, cfg.density_scale, ptr(ws.sigma), None, st)

@@ -416,6 +416,10 @@ class FusedTrainer:
         def heads_fwd():
             F.heads_forward(cfg, hw, ws, self.dirs, M, m_dev, True)
 
+        def grid_heads_fwd():
+            # hash-grid encoder inside the heads kernel: one launch, the features never reach HBM
+            F.grid_heads_forward(cfg, hw, ws, self.dirs, self.table16, offsets, M, m_dev, True)
+
         def composite_fwd():
             _lib.call("seald_composite_rays_train_forward", ptr(ws.sigma), ptr(ws.rgb), ptr(self.deltas), ptr(self.rays), M, N, self.T_thresh,
                       ptr(self.weights_sum), ptr(self.depth), ptr(self.image), _lib.stream())
@@ -469,8 +473,8 @@ class FusedTrainer:
             tail = [("composite_loss_fused", composite_loss_fused, 1)]
         else:
             tail = [("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3)]
-        stages = [("select_frame", select_frame, 1), ("march", march, 1), ("deform_fwd", deform_fwd, 1), ("grid_fwd", grid_fwd, 1),
-                  ("heads_fwd", heads_fwd, 1)] + tail + [("heads_bwd", heads_bwd, 1)]
+        field = [("grid_heads_fwd", grid_heads_fwd, 1)] if F.grid_heads_fusable(cfg, ws, True) else [("grid_fwd", grid_fwd, 1), ("heads_fwd", heads_fwd, 1)]
+        stages = [("select_frame", select_frame, 1), ("march", march, 1), ("deform_fwd", deform_fwd, 1)] + field + tail + [("heads_bwd", heads_bwd, 1)]
         # one GPU: scatter and input gradient share a launch; data parallel: the scatter runs on the side stream ahead of the exchange
         both = self.train_deform and self.dp_mode == "single" and not self.fork_scatter and os.environ.get("SEALD_GRID_BWD_SPLIT", "0") == "0"
         if both:
@@ -540,7 +544,7 @@ class FusedTrainer:
                 n[0] += self._optimizer_table_deferred()
         run("deform_fwd")
         main.wait_stream(side)
-        run("grid_fwd", "heads_fwd", "composite_fwd", "loss", "composite_bwd", "composite_loss_fused", "heads_bwd")
+        run("grid_fwd", "heads_fwd", "grid_heads_fwd", "composite_fwd", "loss", "composite_bwd", "composite_loss_fused", "heads_bwd")
         run("grid_bwd_both")  # (one GPU: scatter + input gradient in one launch; then "grid_scatter" / "grid_input_bwd" below are absent)
         # ---- the table scatter (atomics) beside the tensor-core backward of the deformation net
         fork = self.fork_scatter or mode in ("fused", "sharded", "allreduce")
@@ -711,9 +715,7 @@ class FusedTrainer:
         offsets = m.encoder.offsets
         F16, F32 = _lib.F16, _lib.F32
         F.deform_forward(cfg, hw, pts, self.time, B, None, 1, ws.deform, ws.x01, None, None)
-        _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(self.table16), ptr(offsets), ptr(ws.feat), None, B, 3, cfg.grid_dim,
-                  cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, None, st)
-        F.heads_forward(cfg, hw, ws, drs, B, None, True)
+        F.grid_heads_forward(cfg, hw, ws, drs, self.table16, offsets, B, None, True)
         self.loss.zero_()
         _lib.call("seald_l1_pretrain_loss", ptr(ws.sigma), ptr(ws.rgb), ptr(gs), ptr(gc), B, ptr(self.loss_scale), ptr(self.loss),
                   ptr(self.grad_sigma), ptr(self.grad_rgb), st)

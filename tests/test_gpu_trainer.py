@@ -76,7 +76,7 @@ def test_training_reduces_loss(cuda_dev, use_graph):
     # host-input API returns the same kind of number
     l = tr.train_step_host(o.cpu(), d.cpu(), t, gt.cpu())
     assert np.isfinite(l)
-    assert tr.launches_per_step >= 12  # (the step is ~20 launches after the fusions)
+    assert 8 <= tr.launches_per_step <= 13  # (11 launches on one GPU after the fusions)
 
 
 def test_fused_composite_loss_kernel_equals_three_kernels(cuda_dev):
