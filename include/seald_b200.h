@@ -444,6 +444,16 @@ int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg*
                    float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters, int32_t* sync2,
                    seald_stream_t stream);
 
+/* seald_mlp_tail + the hash-table pass of the same optimiser step (seald_adam_step_lr over table_p / g / m / v [table_n], lr table_lr,
+ * fp16 copy table_p16, gradient cleared) in ONE launch: every CTA takes part in the overflow check, then runs its share of Adam over the
+ * table next to the MLP weights; GradScaler.update / lr_scheduler.step by the last CTA.  The whole
+ * scaler.step(optimizer); scaler.update(); lr_scheduler.step() of nerf/utils.py:884-889. */
+int seald_optimizer_step(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2,
+                         float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth,
+                         float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters, int32_t* sync2,
+                         float* table_p, float* table_g, float* table_m, float* table_v, uint64_t table_n, float table_lr, void* table_p16,
+                         seald_stream_t stream);
+
 /* torch_ema.ExponentialMovingAverage.update: shadow -= (1 - decay) * (shadow - param) (ema_decay = 0.95, main_dnerf.py:136;
  * once per epoch, nerf/utils.py:909-910). */
 int seald_ema_update(float* shadow, const float* param, uint64_t n, float decay, seald_stream_t stream);

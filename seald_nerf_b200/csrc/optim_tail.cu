@@ -18,6 +18,7 @@
 //             learning-rate factor, stashes {found_inf, step, loss scale} for the hash-table pass that follows, resets the flags
 //
 // The hash-table Adam pass (k_adam, train.cu) runs after it (or beside the next step's march) with the stashed values.
+#include "adam.cuh"
 #include "common.cuh"
 
 namespace seald {
@@ -55,10 +56,21 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) k_mlp_tail(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+// The hash-table pass of the same optimiser step (optional: p == nullptr): with it the kernel is the WHOLE scaler.step(optimizer) /
+// scaler.update() / lr_scheduler.step() of a training step in one launch — every CTA first takes part in the overflow check, then
+// runs its grid-stride share of torch.optim.Adam over the table (adam.cuh, same arithmetic as k_adam) next to the MLP weights.
+struct TableAdam {
+    float *p, *g, *m, *v;
+    size_t n;
+    float lr;
+    __half* p16;
+};
+
+template <bool TABLE>
+__global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                   const __grid_constant__ TailSegs segs, const TailState st, const float lr,
                                                   const float beta1, const float beta2, const float eps, const float growth, const float backoff,
-                                                  const int interval, const int sched_iters) {
+                                                  const int interval, const int sched_iters, const TableAdam tb) {
     const uint32_t n = segs.total;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,6 +113,15 @@ __global__ void __launch_bounds__(256) k_mlp_tail(float* __restrict__ p, float* 
         }
     } else {
         for (uint32_t i = i0; i < n; i += stride) g[i] = 0.0f;
+    }
+    if constexpr (TABLE) {
+        // the table: step number / loss scale / lr factor of THIS step (phase 2 changes them only after every CTA is done)
+        const double stp = (double)(*st.step_dev + 1);
+        const float bc1 = (float)(1.0 - pow((double)beta1, stp));
+        const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, stp));
+        const float lr_eff = st.lr_scale ? tb.lr * *st.lr_scale : tb.lr;
+        adam_slab_body(blockIdx.x, gridDim.x, tb.p, tb.g, tb.m, tb.v, tb.n, beta1, beta2, eps, bc2_sqrt, 1.0f / *st.loss_scale, lr_eff / bc1, skip,
+                       tb.p16, 1);
     }
 
     // ---- phase 2: the last CTA closes the step ---------------------------------------------------------------------------------------
@@ -149,10 +170,10 @@ __global__ void k_ema_update(float* __restrict__ shadow, const float* __restrict
 
 using namespace seald;
 
-extern "C" int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2,
-                              float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth,
-                              float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters,
-                              int32_t* sync2, seald_stream_t stream) {
+static int tail_launch(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2,
+                       float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth,
+                       float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters,
+                       int32_t* sync2, const TableAdam& tb, seald_stream_t stream) {
     if (!p || !g || !m || !v || !segs || n_segs <= 0 || n_segs > kTailMaxSegs) return SEALD_E_BADARG;
     if (!step_dev || !loss_scale || !found_inf || !growth_tracker || !stash || !sync2) return SEALD_E_BADARG;
     TailSegs ts;
@@ -167,12 +188,40 @@ extern "C" int seald_mlp_tail(float* p, float* g, float* m, float* v, const seal
     ts.n = n_segs;
     ts.total = total;
     TailState st{step_dev, loss_scale, found_inf, growth_tracker, stash, lr_scale, sched_step, sync2};
+    if (tb.p) {
+        // with the table pass: 4 CTAs per SM (launch bounds: <= 64 registers), all resident for the grid barrier — the kernel follows the
+        // weight-gradient kernel in stream order, so it finds the SMs empty
+        if (!tb.g || !tb.m || !tb.v) return SEALD_E_BADARG;
+        if ((((uintptr_t)tb.p | (uintptr_t)tb.g | (uintptr_t)tb.m | (uintptr_t)tb.v) & 15) || ((uintptr_t)tb.p16 & 7)) return SEALD_E_ALIGN;
+        k_mlp_tail<true><<<4u * SEALD_NUM_SMS, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff, interval,
+                                                                          sched_iters, tb);
+        return launch_status();
+    }
     // at most one CTA per SM: the grid barrier needs every CTA resident
     uint32_t blocks = div_up(total, 256u * 4u);
     if (blocks > (uint32_t)SEALD_NUM_SMS) blocks = SEALD_NUM_SMS;
     if (blocks == 0) blocks = 1;
-    k_mlp_tail<<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff, interval, sched_iters);
+    k_mlp_tail<false><<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff, interval, sched_iters, tb);
     return launch_status();
+}
+
+extern "C" int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2,
+                              float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth,
+                              float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters,
+                              int32_t* sync2, seald_stream_t stream) {
+    return tail_launch(p, g, m, v, segs, n_segs, lr, beta1, beta2, eps, step_dev, loss_scale, found_inf, growth_tracker, growth, backoff, interval,
+                       stash, lr_scale, sched_step, sched_iters, sync2, TableAdam{}, stream);
+}
+
+extern "C" int seald_optimizer_step(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1,
+                                    float beta2, float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker,
+                                    float growth, float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step,
+                                    int sched_iters, int32_t* sync2, float* table_p, float* table_g, float* table_m, float* table_v,
+                                    uint64_t table_n, float table_lr, void* table_p16, seald_stream_t stream) {
+    if (!table_p || table_n == 0) return SEALD_E_BADARG;
+    return tail_launch(p, g, m, v, segs, n_segs, lr, beta1, beta2, eps, step_dev, loss_scale, found_inf, growth_tracker, growth, backoff, interval,
+                       stash, lr_scale, sched_step, sched_iters, sync2,
+                       TableAdam{table_p, table_g, table_m, table_v, (size_t)table_n, table_lr, (__half*)table_p16}, stream);
 }
 
 extern "C" int seald_ema_update(float* shadow, const float* param, uint64_t n, float decay, seald_stream_t stream) {

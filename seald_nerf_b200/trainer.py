@@ -152,6 +152,7 @@ class FusedTrainer:
         self.defer_point = defer
         self.pending = torch.tensor([1, 0, 0, 0], dtype=torch.int32, device=dev)
         self.adam_blocks = int(os.environ.get("SEALD_ADAM_BLOCKS", "296"))
+        self.one_launch_optimizer = os.environ.get("SEALD_OPT_ONE_LAUNCH", "1") != "0"  # measurement switch (seald_optimizer_step)
         # one GPU: the scatter beside the deformation backward measured SLOWER than in line (0.414 vs 0.400-0.408 ms: its 2656 short CTAs
         # delay the persistent tensor-core kernel's CTAs); the second stream is for the data-parallel exchange
         self.fork_scatter = os.environ.get("SEALD_FORK", "0") != "0"
@@ -659,10 +660,16 @@ class FusedTrainer:
             # ONE launch: overflow check of the MLP gradients, Adam on the weights, fp16 copies + tcgen05 tiles, GradScaler.update,
             # lr_scheduler.step; it stashes {found_inf, step, loss scale, lr factor} of this step for the table pass
             o = 4 * ntp
-            _lib.call("seald_mlp_tail", self.params.data_ptr() + o, self.grads.data_ptr() + o, self.exp_avg.data_ptr() + o,
-                      self.exp_avg_sq.data_ptr() + o, C.cast(self._tail_segs, C.c_void_p), len(self._tail_segs), self.lr_net, b1, b2, self.eps,
-                      ptr(self.step_dev), ptr(self.loss_scale), ptr(found), ptr(self.growth_tracker), 2.0, 0.5, self.growth_interval,
-                      ptr(self.pending), ptr(self.lr_scale), ptr(self.sched_step), self.lr_decay_iters, ptr(self._tail_sync), st)
+            tail_args = (self.params.data_ptr() + o, self.grads.data_ptr() + o, self.exp_avg.data_ptr() + o, self.exp_avg_sq.data_ptr() + o,
+                         C.cast(self._tail_segs, C.c_void_p), len(self._tail_segs), self.lr_net, b1, b2, self.eps, ptr(self.step_dev),
+                         ptr(self.loss_scale), ptr(found), ptr(self.growth_tracker), 2.0, 0.5, self.growth_interval, ptr(self.pending),
+                         ptr(self.lr_scale), ptr(self.sched_step), self.lr_decay_iters, ptr(self._tail_sync))
+            if not self.defer_table_update and self.dp_mode == "single" and self.one_launch_optimizer:
+                # one GPU, table pass in place: the whole scaler.step / scaler.update / lr_scheduler.step in ONE launch
+                _lib.call("seald_optimizer_step", *tail_args, ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                          self.n_table_pad, self.lr, ptr(self.table16_pad), st)
+                return 1
+            _lib.call("seald_mlp_tail", *tail_args, st)
             n = 1
             if not self.defer_table_update:
                 n += self._optimizer_table_deferred()
