@@ -444,6 +444,15 @@ int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg*
                    float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters, int32_t* sync2,
                    seald_stream_t stream);
 
+/* seald_mlp_tail for the data-parallel trainer: the gradient of element i is the sum over the ranks' peer-mapped gradient buffers
+ * (peer_grads[r] + w_off + i, summed in rank order), the step overflows when some rank's flag (peer_grads[r][flag_off], a float) is
+ * set or a summed gradient is not finite; the decision is kept in the rank-local word *found_local (zero-initialised, reset here).
+ * Local gradients and flags are not cleared (peers may still read them).  p / m / v: this rank's MLP region. */
+int seald_mlp_tail_dp(const void* const* peer_grads, int world, uint64_t w_off, uint64_t flag_off, int32_t* found_local, float* p, float* m,
+                      float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2, float eps, int32_t* step_dev,
+                      float* loss_scale, int32_t* growth_tracker, float growth, float backoff, int interval, int32_t* stash, float* lr_scale,
+                      int32_t* sched_step, int sched_iters, int32_t* sync2, seald_stream_t stream);
+
 /* seald_mlp_tail + the hash-table pass of the same optimiser step (seald_adam_step_lr over table_p / g / m / v [table_n], lr table_lr,
  * fp16 copy table_p16, gradient cleared) in ONE launch: every CTA takes part in the overflow check, then runs its share of Adam over the
  * table next to the MLP weights; GradScaler.update / lr_scheduler.step by the last CTA.  The whole
@@ -489,7 +498,7 @@ int seald_dp_adam_weights(const void* const* peer_grads, const void* mc_grads, i
 int seald_dp_adam_shard_broadcast(void* const* peer_table16, void* mc_table16, int world, float* p, float* m, float* v,
                                   const float* grad_shard, uint64_t shard_off, uint64_t shard_len, float lr, float beta1,
                                   float beta2, float eps, const int32_t* step_dev, const float* loss_scale,
-                                  const int32_t* found_inf, seald_stream_t stream);
+                                  const int32_t* found_inf, const float* lr_scale_dev /* NULL: lr as given */, seald_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Occupancy-grid refresh on the device (NeRFRenderer.update_extra_state, dnerf/renderer.py:453-555).

@@ -102,10 +102,12 @@ grad_ok = grad_ok and fused_ok
 # +-lr with a noise-chosen sign: the max over 12M entries is meaningless; compare the mean absolute difference and the loss. -----------
 results = {}
 for name, kw in (("fused", dict(dp_mode="fused")), ("fused_no_multicast", dict(dp_mode="fused")), ("fused_switch_reduce", dict(dp_mode="fused")),
+                 ("fused_dp_tail", dict(dp_mode="fused")),  # single-launch optimiser tail with the peer sums inside (seald_mlp_tail_dp)
                  ("eager_fused", dict(dp_mode="fused", use_graph=False)),
                  ("sharded", dict(dp_mode="sharded")), ("allreduce", dict(dp_mode="allreduce")),
                  ("eager_sharded", dict(dp_mode="sharded", use_graph=False)), ("eager_allreduce", dict(dp_mode="allreduce", use_graph=False))):
     os.environ["SEALD_DP_MULTICAST"] = "0" if name == "fused_no_multicast" else "1"
+    os.environ["SEALD_DP_TAIL"] = "1" if name == "fused_dp_tail" else "0"
     os.environ["SEALD_DP_MULTICAST_REDUCE"] = "1" if name == "fused_switch_reduce" else "auto"  # multimem.ld_reduce for the shard sum
     tr = run(world, **kw)
     results[name] = (tr.table16.float().clone(), [w.clone() for w in tr.weight_views], float(tr.loss), int(tr.step_dev),

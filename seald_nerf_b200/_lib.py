@@ -74,7 +74,7 @@ _SIGS = {
     "seald_cast_pad_f16_batch": [_vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "seald_dp_reduce_shard": [_vp, _vp, _i32, C.c_uint64, C.c_uint64, _vp, _vp],
     "seald_dp_adam_weights": [_vp, _vp, _i32, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],
-    "seald_dp_adam_shard_broadcast": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],
+    "seald_dp_adam_shard_broadcast": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
     "seald_loss_scale_update_stash": [_vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp],
     "seald_occ_cell_points": [_vp, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _vp],
     "seald_occ_partial_points": [_vp, _vp, _vp, _u32, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _vp],
@@ -88,6 +88,8 @@ _SIGS = {
     "seald_adam_step": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _vp],
     "seald_adam_step_ex": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _u32, _vp],
     "seald_adam_step_lr": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _vp, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _u32, _vp],
+    "seald_mlp_tail_dp": [_vp, _i32, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _f32, _f32,
+                          _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "seald_optimizer_step": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _vp,
                              _vp, _vp, _vp, _vp, C.c_uint64, _f32, _vp, _vp],
     "seald_mlp_tail": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],

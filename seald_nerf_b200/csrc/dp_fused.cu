@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_dp_adam_shard_broadcast(const DpPeers p
                                                                  const float* __restrict__ grad_shard, const size_t shard_off,
                                                                  const size_t shard_len, const float lr, const float beta1,
                                                                  const float beta2, const float eps, const int* __restrict__ step_dev,
-                                                                 const float* __restrict__ loss_scale, const int* __restrict__ found_inf) {
+                                                                 const float* __restrict__ loss_scale, const int* __restrict__ found_inf, const float* __restrict__ lr_scale) {
     if (*found_inf != 0) return;
     __shared__ float s_bc[2];
     if (threadIdx.x == 0) {
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) k_dp_adam_shard_broadcast(const DpPeers p
     const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
     const float inv_scale = 1.0f / *loss_scale;
     const size_t tid = threadIdx.x + (size_t)blockIdx.x * blockDim.x, nth = (size_t)gridDim.x * blockDim.x;
-    const float step_size = lr / bc1;
+    const float step_size = (lr_scale ? lr * *lr_scale : lr) / bc1;  // LambdaLR factor of the step this (deferred) pass belongs to
     const size_t n8 = shard_len / 8;
     for (size_t j = tid; j < n8; j += nth) {
         const size_t i = shard_off + j * 8;
@@ -257,7 +257,7 @@ extern "C" int seald_dp_adam_weights(const void* const* peer_grads, const void* 
 extern "C" int seald_dp_adam_shard_broadcast(void* const* peer_table16, void* mc_table16, int world, float* p, float* m, float* v,
                                              const float* grad_shard, uint64_t shard_off, uint64_t shard_len, float lr, float beta1,
                                              float beta2, float eps, const int32_t* step_dev, const float* loss_scale,
-                                             const int32_t* found_inf, seald_stream_t stream) {
+                                             const int32_t* found_inf, const float* lr_scale_dev, seald_stream_t stream) {
     if (!peer_table16 || !p || !m || !v || !grad_shard || !step_dev || !loss_scale || !found_inf) return SEALD_E_BADARG;
     if ((shard_off | shard_len) % 8 || world < 1 || world > kMaxRanks) return SEALD_E_BADARG;
     DpPeers peers;
@@ -270,9 +270,9 @@ extern "C" int seald_dp_adam_shard_broadcast(void* const* peer_table16, void* mc
     const uint32_t blocks = 4u * SEALD_NUM_SMS;
     if (mc_table16)
         k_dp_adam_shard_broadcast<true><<<blocks, 256, 0, st>>>(peers, (__half*)mc_table16, world, p, m, v, grad_shard, shard_off, shard_len, lr,
-                                                                beta1, beta2, eps, step_dev, loss_scale, found_inf);
+                                                                beta1, beta2, eps, step_dev, loss_scale, found_inf, lr_scale_dev);
     else
         k_dp_adam_shard_broadcast<false><<<blocks, 256, 0, st>>>(peers, nullptr, world, p, m, v, grad_shard, shard_off, shard_len, lr, beta1, beta2,
-                                                                 eps, step_dev, loss_scale, found_inf);
+                                                                 eps, step_dev, loss_scale, found_inf, lr_scale_dev);
     return launch_status();
 }

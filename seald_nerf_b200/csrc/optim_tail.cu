@@ -66,21 +66,52 @@ struct TableAdam {
     __half* p16;
 };
 
-template <bool TABLE>
+// Data parallel (PEERS): the gradient of element i is the sum over the ranks' gradient buffers (peer-mapped, read in rank order on
+// every rank: identical sums), the overflow decision is "some rank raised its flag (table scatter) or the summed MLP gradient is not
+// finite".  The local gradient / flag are NOT cleared here — peers may still be reading them; the trainer clears the buffer behind
+// the next step's cross-rank barrier — and the decision lives in a rank-local word (found_local).
+constexpr int kTailMaxRanks = 16;
+struct TailPeers {
+    const float* g[kTailMaxRanks];  // each rank's flat gradient buffer
+    int world;
+    size_t w_off, flag_off;         // MLP region / overflow flag (a float) inside it
+    int* found_local;
+};
+
+template <bool PEERS>
+__device__ __forceinline__ float tail_grad(const float* __restrict__ g, const TailPeers& pr, const uint32_t i) {
+    if constexpr (PEERS) {
+        float s = 0.0f;
+        for (int r = 0; r < pr.world; r++) s += pr.g[r][pr.w_off + i];
+        return s;
+    } else {
+        return g[i];
+    }
+}
+
+template <bool TABLE, bool PEERS>
 __global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                   const __grid_constant__ TailSegs segs, const TailState st, const float lr,
                                                   const float beta1, const float beta2, const float eps, const float growth, const float backoff,
-                                                  const int interval, const int sched_iters, const TableAdam tb) {
+                                                  const int interval, const int sched_iters, const TableAdam tb, const __grid_constant__ TailPeers pr) {
+    int* const found = PEERS ? pr.found_local : st.found_inf;
     const uint32_t n = segs.total;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
 
     // ---- phase 0: overflow check over this thread's gradients -----------------------------------------------------------------
     bool bad = false;
-    for (uint32_t i = i0; i < n; i += stride) bad |= !isfinite(g[i]);
+    for (uint32_t i = i0; i < n; i += stride) bad |= !isfinite(tail_grad<PEERS>(g, pr, i));
+    if constexpr (PEERS) {
+        if (i0 == 0) {  // the ranks' overflow flags (raised by their table scatters)
+            float f = 0.0f;
+            for (int r = 0; r < pr.world; r++) f += pr.g[r][pr.flag_off];
+            bad |= !(f == 0.0f);
+        }
+    }
     const int any_bad = __syncthreads_or(bad ? 1 : 0);
     if (threadIdx.x == 0) {
-        if (any_bad) atomicOr(st.found_inf, 0x3f800000);
+        if (any_bad) atomicOr(found, 0x3f800000);
         __threadfence();
         atomicAdd(st.sync, 1);
         while (ld_acquire(st.sync) < (int)gridDim.x) __nanosleep(32);
@@ -88,7 +119,7 @@ __global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restri
     __syncthreads();
 
     // ---- phase 1: Adam + fp16 copies ----------------------------------------------------------------------------------------------
-    const bool skip = ld_acquire(st.found_inf) != 0;
+    const bool skip = ld_acquire(found) != 0;
     if (!skip) {
         const double stp = (double)(*st.step_dev + 1);
         const float bc1 = (float)(1.0 - pow((double)beta1, stp));
@@ -99,11 +130,12 @@ __global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restri
         for (uint32_t i = i0; i < n; i += stride) {
             while (k + 1 < segs.n && i >= segs.s[k + 1].first) k++;
             const TailSeg& sg = segs.s[k];
-            const float gi = g[i] * inv_scale;
+            const float gi = tail_grad<PEERS>(g, pr, i) * inv_scale;
             const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
             const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
             const float pi = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-            m[i] = mi; v[i] = vi; p[i] = pi; g[i] = 0.0f;
+            m[i] = mi; v[i] = vi; p[i] = pi;
+            if constexpr (!PEERS) g[i] = 0.0f;
             const uint32_t j = i - sg.first;
             const uint32_t r = j / sg.cols, c = j - r * sg.cols;
             const __half h = __float2half_rn(pi);
@@ -111,7 +143,7 @@ __global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restri
             if (sg.packed) sg.packed[((size_t)(c >> 3) * sg.n_pad + r) * 8 + (c & 7)] = h;
             if (sg.packedT) sg.packedT[((size_t)(r >> 3) * 128 + c) * 8 + (r & 7)] = h;
         }
-    } else {
+    } else if constexpr (!PEERS) {
         for (uint32_t i = i0; i < n; i += stride) g[i] = 0.0f;
     }
     if constexpr (TABLE) {
@@ -130,12 +162,12 @@ __global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restri
         __threadfence();
         const int done = atomicAdd(st.sync + 1, 1) + 1;
         if (done == (int)gridDim.x) {
-            const int found = *st.found_inf;
-            st.stash[0] = found;
+            const int found_v = *found;
+            st.stash[0] = found_v;
             st.stash[1] = *st.step_dev;
             st.stash[2] = __float_as_int(*st.loss_scale);
             st.stash[3] = __float_as_int(st.lr_scale ? *st.lr_scale : 1.0f);
-            if (found) {
+            if (found_v) {
                 *st.loss_scale *= backoff;
                 *st.growth_tracker = 0;
             } else {
@@ -149,7 +181,7 @@ __global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restri
                 *st.sched_step = e;
                 if (st.lr_scale && sched_iters > 0) *st.lr_scale = (float)pow(0.1, fmin((double)e / (double)sched_iters, 1.0));
             }
-            *st.found_inf = 0;
+            *found = 0;
             st.sync[0] = 0;
             st.sync[1] = 0;
             __threadfence();
@@ -173,7 +205,7 @@ using namespace seald;
 static int tail_launch(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2,
                        float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth,
                        float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters,
-                       int32_t* sync2, const TableAdam& tb, seald_stream_t stream) {
+                       int32_t* sync2, const TableAdam& tb, seald_stream_t stream, const TailPeers* peers = nullptr) {
     if (!p || !g || !m || !v || !segs || n_segs <= 0 || n_segs > kTailMaxSegs) return SEALD_E_BADARG;
     if (!step_dev || !loss_scale || !found_inf || !growth_tracker || !stash || !sync2) return SEALD_E_BADARG;
     TailSegs ts;
@@ -193,16 +225,38 @@ static int tail_launch(float* p, float* g, float* m, float* v, const seald_tail_
         // weight-gradient kernel in stream order, so it finds the SMs empty
         if (!tb.g || !tb.m || !tb.v) return SEALD_E_BADARG;
         if ((((uintptr_t)tb.p | (uintptr_t)tb.g | (uintptr_t)tb.m | (uintptr_t)tb.v) & 15) || ((uintptr_t)tb.p16 & 7)) return SEALD_E_ALIGN;
-        k_mlp_tail<true><<<4u * SEALD_NUM_SMS, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff, interval,
-                                                                          sched_iters, tb);
+        if (peers) return SEALD_E_UNSUPPORTED;
+        k_mlp_tail<true, false><<<4u * SEALD_NUM_SMS, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff,
+                                                                                 interval, sched_iters, tb, TailPeers{});
         return launch_status();
     }
     // at most one CTA per SM: the grid barrier needs every CTA resident
     uint32_t blocks = div_up(total, 256u * 4u);
     if (blocks > (uint32_t)SEALD_NUM_SMS) blocks = SEALD_NUM_SMS;
     if (blocks == 0) blocks = 1;
-    k_mlp_tail<false><<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff, interval, sched_iters, tb);
+    if (peers)
+        k_mlp_tail<false, true><<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff, interval,
+                                                                     sched_iters, tb, *peers);
+    else
+        k_mlp_tail<false, false><<<blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, ts, st, lr, beta1, beta2, eps, growth, backoff, interval,
+                                                                      sched_iters, tb, TailPeers{});
     return launch_status();
+}
+
+extern "C" int seald_mlp_tail_dp(const void* const* peer_grads, int world, uint64_t w_off, uint64_t flag_off, int32_t* found_local, float* p,
+                                 float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2, float eps,
+                                 int32_t* step_dev, float* loss_scale, int32_t* growth_tracker, float growth, float backoff, int interval,
+                                 int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters, int32_t* sync2, seald_stream_t stream) {
+    if (!peer_grads || world <= 0 || world > kTailMaxRanks || !found_local) return SEALD_E_BADARG;
+    TailPeers pr;
+    for (int r = 0; r < world; r++) {
+        if (!peer_grads[r]) return SEALD_E_BADARG;
+        pr.g[r] = (const float*)peer_grads[r];
+    }
+    pr.world = world; pr.w_off = (size_t)w_off; pr.flag_off = (size_t)flag_off; pr.found_local = found_local;
+    // (g: unused in this mode, the sums are read from the peers; found_inf: the local word doubles as the required argument)
+    return tail_launch(p, p, m, v, segs, n_segs, lr, beta1, beta2, eps, step_dev, loss_scale, found_local, growth_tracker, growth, backoff, interval,
+                       stash, lr_scale, sched_step, sched_iters, sync2, TableAdam{}, stream, &pr);
 }
 
 extern "C" int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2,

@@ -164,6 +164,10 @@ class FusedTrainer:
         self._tail_segs = self._build_tail_segs(sizes)
         # the fused MLP tail (csrc/optim_tail.cu): single GPU; the data-parallel modes keep their exchange-fused optimiser kernels
         self.fused_tail = self.dp_mode == "single" and os.environ.get("SEALD_FUSED_TAIL", "1") != "0"
+        # data parallel with the fused exchange: the same single-launch tail with the gradients summed over the peers inside it
+        # (seald_mlp_tail_dp).  Measured SLOWER than the four small kernels on 2 GPUs (0.3276 vs 0.3135 ms per step: two rounds of peer
+        # loads around a grid barrier), so it is used only where it is needed — it is what advances the device-side LR schedule
+        self.dp_tail = self.dp_mode == "fused" and (os.environ.get("SEALD_DP_TAIL", "0") != "0" or bool(self.lr_decay_iters))
         # torch_ema.ExponentialMovingAverage over every parameter (ema_decay = 0.95 in main_dnerf.py:136): a shadow of the flat buffer
         self.ema_shadow = self.params.clone() if self.ema_decay else None
         self.ema_num_updates = 0
@@ -476,7 +480,8 @@ class FusedTrainer:
             tail = [("composite_fwd", composite_fwd, 1), ("loss", loss, 2), ("composite_bwd", composite_bwd, 3)]
         field = [("grid_heads_fwd", grid_heads_fwd, 1)] if F.grid_heads_fusable(cfg, ws, True) else [("grid_fwd", grid_fwd, 1), ("heads_fwd", heads_fwd, 1)]
         stages = [("select_frame", select_frame, 1), ("march", march, 1), ("deform_fwd", deform_fwd, 1)] + field + tail + [("heads_bwd", heads_bwd, 1)]
-        # one GPU: scatter and input gradient share a launch; data parallel: the scatter runs on the side stream ahead of the exchange
+        # one GPU: scatter and input gradient share a launch.  Data parallel: the scatter runs on the side stream ahead of the exchange
+        # beside the input gradient (measured on 2 GPUs: 0.3088 ms split vs 0.3135 ms merged)
         both = self.train_deform and self.dp_mode == "single" and not self.fork_scatter and os.environ.get("SEALD_GRID_BWD_SPLIT", "0") == "0"
         if both:
             stages += [("grid_bwd_both", grid_bwd_both, 1), ("deform_bwd", deform_bwd, 1)]
@@ -566,7 +571,7 @@ class FusedTrainer:
                           self.rank * self.shard_len, self.shard_len, ptr(self.grad_shard), _lib.stream())
                 n[0] += 2
         run("grid_input_bwd", "deform_bwd", "wgrad")
-        if not self.fused_tail:
+        if not self.fused_tail and not self.dp_tail:
             _lib.call("seald_grad_finite_check", self.grads.data_ptr() + 4 * ntp, self.n_weights, ptr(self.found_inf), _lib.stream())
             n[0] += 1
         main.wait_stream(side)  # (also orders the overflow flag written by the scatter before it is exchanged)
@@ -629,7 +634,8 @@ class FusedTrainer:
         if self.dp_mode == "fused":  # own shard (gradient already summed over the ranks) + fp16 rows to every rank's table
             _lib.call("seald_dp_adam_shard_broadcast", C.cast(self._peer_table16, C.c_void_p), self._mc_table16, self.world_size,
                       ptr(self.params), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.grad_shard), self.rank * self.shard_len,
-                      self.shard_len, self.lr, b1, b2, self.eps, step_dev, loss_scale, found_inf, st)
+                      self.shard_len, self.lr, b1, b2, self.eps, step_dev, loss_scale, found_inf,
+                      lr_scale if self.dp_tail else None, st)
         elif self.dp_mode == "sharded":
             off = self.rank * self.shard_len
             _lib.call("seald_adam_step", self.params.data_ptr() + 4 * off, ptr(self.grad_shard), self.exp_avg.data_ptr() + 4 * off,
@@ -646,7 +652,7 @@ class FusedTrainer:
         """The hash-table pass of the previous step's optimiser, with the overflow decision / step number / loss scale that step
         stashed (the first call finds found_inf = 1: nothing pending)."""
         p = self.pending.data_ptr()
-        return self._adam_table(p + 4, p + 8, p, _lib.stream(), p + 12 if self.fused_tail else None)
+        return self._adam_table(p + 4, p + 8, p, _lib.stream(), p + 12 if (self.fused_tail or self.dp_tail) else None)
 
     def _optimizer(self):
         """GradScaler.step + optimizer.step + GradScaler.update as device kernels (nerf/utils.py:884-886): the whole update is
@@ -670,6 +676,19 @@ class FusedTrainer:
                           self.n_table_pad, self.lr, ptr(self.table16_pad), st)
                 return 1
             _lib.call("seald_mlp_tail", *tail_args, st)
+            n = 1
+            if not self.defer_table_update:
+                n += self._optimizer_table_deferred()
+            return n
+        if self.dp_tail:
+            # ONE launch: flags + MLP gradients summed over the peers, Adam on the replicated weights, fp16 copies / tcgen05 tiles,
+            # GradScaler.update, LambdaLR; the stash carries {found_inf, step, loss scale, lr factor} to the deferred shard pass
+            o = 4 * ntp
+            _lib.call("seald_mlp_tail_dp", C.cast(self._peer_grads, C.c_void_p), self.world_size, ntp, self.n_flag, ptr(self.found_inf_global),
+                      self.params.data_ptr() + o, self.exp_avg.data_ptr() + o, self.exp_avg_sq.data_ptr() + o,
+                      C.cast(self._tail_segs, C.c_void_p), len(self._tail_segs), self.lr_net, b1, b2, self.eps, ptr(self.step_dev),
+                      ptr(self.loss_scale), ptr(self.growth_tracker), 2.0, 0.5, self.growth_interval, ptr(self.pending), ptr(self.lr_scale),
+                      ptr(self.sched_step), self.lr_decay_iters, ptr(self._tail_sync), st)
             n = 1
             if not self.defer_table_update:
                 n += self._optimizer_table_deferred()
