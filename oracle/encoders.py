@@ -2,7 +2,8 @@
 
 freq_encode   : freqencoder/src/freqencoder.cu:30-58 (channel order, scalbnf, sin(x + pi/2) for cos)
 freq_backward : freqencoder/src/freqencoder.cu:63-94
-sh_encode     : shencoder/src/shencoder.cu:49-70 (degree <= 4), same polynomials as testing/test_shencoder.py:51-92
+sh_encode     : shencoder/src/shencoder.cu:49-70 (degree <= 4), same polynomials as testing/test_shencoder.py:51-92; bands 4..7
+                (degrees 5..8, :71-135) from scipy's spherical harmonics, for unit vectors
 trunc_exp     : activation.py:5-17
 """
 import numpy as np
@@ -65,8 +66,36 @@ def sh_encode(dirs, degree=4):
         out[:, 14] = 1.4453057213202769 * z * (x2 - y2)
         out[:, 15] = 0.59004358992664352 * x * (-x2 + 3.0 * y2)
     if degree > 4:
-        raise NotImplementedError("oracle SH restated up to degree 4 (the D-NeRF setting)")
+        # bands 4..7 (shencoder.cu:71-135): not restated polynomial by polynomial — evaluated from scipy's complex spherical
+        # harmonics (valid for UNIT vectors; pinned by the check that the same construction reproduces bands 0..3 above and, on the
+        # GPU box, by the reference extension itself)
+        out[:, 16:] = sh_bands_scipy(d, range(4, degree))
     return out
+
+
+def sh_bands_scipy(dirs, bands):
+    """Real spherical harmonics of UNIT vectors for the given bands, ordered l*l + l + m within a band, in the reference's
+    convention: Y_l^{+m} = sqrt(2) Re(Y_l^m), Y_l^{-m} = sqrt(2) Im(Y_l^m) with scipy's Condon-Shortley-phased complex Y_l^m."""
+    from scipy import special
+    d = np.asarray(dirs, np.float64)
+    d = d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-300)
+    theta = np.arccos(np.clip(d[:, 2], -1.0, 1.0))   # polar
+    phi = np.arctan2(d[:, 1], d[:, 0])               # azimuth
+    cols = []
+    for l in bands:
+        blk = np.empty((d.shape[0], 2 * l + 1))
+        for m in range(0, l + 1):
+            if hasattr(special, "sph_harm_y"):
+                Y = special.sph_harm_y(l, m, theta, phi)
+            else:
+                Y = special.sph_harm(m, l, phi, theta)
+            if m == 0:
+                blk[:, l] = Y.real
+            else:
+                blk[:, l + m] = np.sqrt(2.0) * Y.real
+                blk[:, l - m] = np.sqrt(2.0) * Y.imag
+        cols.append(blk)
+    return np.concatenate(cols, axis=1)
 
 
 def sh_jacobian_fd(dirs, degree=4, eps=1e-6):

@@ -40,15 +40,22 @@ __global__ void k_sh_fwd(const float* __restrict__ inputs, float* __restrict__ o
     const uint32_t b = threadIdx.x + blockIdx.x * blockDim.x;
     if (b >= B) return;
     constexpr int C2 = DEG * DEG;
+    constexpr int LOW = DEG < 4 ? DEG : 4;  // bands 0..3: the hard-coded forms; 4..7: sh_high_bands
     const float x = inputs[(size_t)b * 3], y = inputs[(size_t)b * 3 + 1], z = inputs[(size_t)b * 3 + 2];
     float o[C2];
-    sh_eval<DEG>(x, y, z, o);
     float* out = outputs + (size_t)b * C2;
+    if (!dy_dx) {
+        sh_eval<LOW>(x, y, z, o);
+        if constexpr (DEG > 4) sh_high_bands<DEG, false>(x, y, z, o, nullptr, nullptr, nullptr);
 #pragma unroll
-    for (int i = 0; i < C2; i++) out[i] = o[i];
-    if (dy_dx) {
+        for (int i = 0; i < C2; i++) out[i] = o[i];
+    } else {
         float gx[C2], gy[C2], gz[C2];
-        sh_grad<DEG>(x, y, z, gx, gy, gz);
+        sh_eval<LOW>(x, y, z, o);
+        sh_grad<LOW>(x, y, z, gx, gy, gz);
+        if constexpr (DEG > 4) sh_high_bands<DEG, true>(x, y, z, o, gx, gy, gz);
+#pragma unroll
+        for (int i = 0; i < C2; i++) out[i] = o[i];
         float* g = dy_dx + (size_t)b * 3 * C2;  // [B, D, C2] (shencoder.cu:139-141)
 #pragma unroll
         for (int i = 0; i < C2; i++) { g[i] = gx[i]; g[C2 + i] = gy[i]; g[2 * C2 + i] = gz[i]; }
@@ -105,6 +112,10 @@ extern "C" int seald_sh_encode_forward(const float* inputs, float* outputs, uint
         case 2: k_sh_fwd<2><<<blocks, 256, 0, st>>>(inputs, outputs, B, dy_dx); break;
         case 3: k_sh_fwd<3><<<blocks, 256, 0, st>>>(inputs, outputs, B, dy_dx); break;
         case 4: k_sh_fwd<4><<<blocks, 256, 0, st>>>(inputs, outputs, B, dy_dx); break;
+        case 5: k_sh_fwd<5><<<blocks, 256, 0, st>>>(inputs, outputs, B, dy_dx); break;
+        case 6: k_sh_fwd<6><<<blocks, 256, 0, st>>>(inputs, outputs, B, dy_dx); break;
+        case 7: k_sh_fwd<7><<<blocks, 256, 0, st>>>(inputs, outputs, B, dy_dx); break;
+        case 8: k_sh_fwd<8><<<blocks, 256, 0, st>>>(inputs, outputs, B, dy_dx); break;
         default: return SEALD_E_UNSUPPORTED;
     }
     return launch_status();
@@ -114,7 +125,7 @@ extern "C" int seald_sh_encode_backward(const float* grad, const float* inputs, 
                                         float* grad_inputs, seald_stream_t stream) {
     if (B == 0) return 0;
     if (!grad || !dy_dx || !grad_inputs) return SEALD_E_BADARG;
-    if (D != 3 || degree < 1 || degree > 4) return SEALD_E_UNSUPPORTED;
+    if (D != 3 || degree < 1 || degree > 8) return SEALD_E_UNSUPPORTED;
     (void)inputs;
     k_sh_bwd<<<div_up(B * D, 256u), 256, 0, to_stream(stream)>>>(grad, B, D, degree * degree, dy_dx, grad_inputs);
     return launch_status();

@@ -2,6 +2,7 @@
 // kernels (encoders.cu) and the fused field kernels (field.cu).
 #pragma once
 #include "common.cuh"
+#include "sh_tables.cuh"
 
 namespace seald {
 
@@ -83,6 +84,47 @@ __device__ __forceinline__ void sh_grad(const float x, const float y, const floa
         dz[13] = -4.5704579946446566f * xz;
         dz[14] = 1.4453057213202769f * x2 - 1.4453057213202769f * y2;
         dz[15] = 0.0f;
+    }
+}
+
+// Bands l = 4 .. DEG - 1 (degrees 5 .. 8 of the reference, shencoder.cu:71-135) from the generated z-polynomials: Y_l^{+-m} =
+// Q_lm(z) * Re / Im((x + i y)^m).  out / dx / dy / dz are indexed like the reference: l * l + l + m.  The reference hard-codes the
+// same polynomials expanded; here they are evaluated as a product of a polynomial in z and one in (x, y), so values agree to fp32
+// round-off and the partial derivatives (x, y, z treated as independent, like the reference's dy_dx) are those of the same form.
+template <int DEG, bool GRAD>
+__device__ __forceinline__ void sh_high_bands(const float x, const float y, const float z, float* out, float* dx, float* dy, float* dz) {
+    float c[8], s[8], zp[8];
+    c[0] = 1.0f; s[0] = 0.0f; zp[0] = 1.0f;
+#pragma unroll
+    for (int m = 1; m < DEG; m++) {
+        c[m] = x * c[m - 1] - y * s[m - 1];
+        s[m] = x * s[m - 1] + y * c[m - 1];
+        zp[m] = zp[m - 1] * z;
+    }
+#pragma unroll
+    for (int l = 4; l < DEG; l++) {
+#pragma unroll
+        for (int m = 0; m <= l; m++) {
+            float q = 0.0f, dq = 0.0f;
+#pragma unroll
+            for (int k = l - m; k >= 0; k -= 2) {  // Q_lm has the parity of l - m
+                q += kShQ[l][m][k] * zp[k];
+                if (GRAD && k >= 1) dq += (float)k * kShQ[l][m][k] * zp[k - 1];
+            }
+            const int ip = l * l + l + m, im = l * l + l - m;
+            if (m == 0) {
+                out[ip] = q;
+                if (GRAD) { dx[ip] = 0.0f; dy[ip] = 0.0f; dz[ip] = dq; }
+            } else {
+                out[ip] = q * c[m];
+                out[im] = q * s[m];
+                if (GRAD) {
+                    const float fm = (float)m;
+                    dx[ip] = q * fm * c[m - 1]; dy[ip] = -q * fm * s[m - 1]; dz[ip] = dq * c[m];
+                    dx[im] = q * fm * s[m - 1]; dy[im] = q * fm * c[m - 1]; dz[im] = dq * s[m];
+                }
+            }
+        }
     }
 }
 

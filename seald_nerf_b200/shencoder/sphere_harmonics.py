@@ -1,5 +1,5 @@
 """Drop-in `shencoder` package (reference: shencoder/sphere_harmonics.py:14-86) on libseald_b200.so.
-Degrees 1..4 (D-NeRF uses 4); higher degrees are outside the hot-path scope and raise."""
+Degrees 1..8 like the reference (D-NeRF uses 4; bands 4..7 come from generated z-polynomials, csrc/sh_tables.cuh)."""
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -48,8 +48,6 @@ class SHEncoder(nn.Module):
         self.output_dim = degree ** 2
         assert self.input_dim == 3, "SH encoder only support input dim == 3"
         assert self.degree > 0 and self.degree <= 8, "SH encoder only supports degree in [1, 8]"
-        if self.degree > 4:
-            raise NotImplementedError("seald_b200 SHEncoder implements degree <= 4 (the D-NeRF/SealD setting)")
 
     def __repr__(self):
         return f"SHEncoder: input_dim={self.input_dim} degree={self.degree}"

@@ -34,7 +34,7 @@ def test_freq_forward_backward(cuda_dev, D, deg):
         torch.testing.assert_close(gi_r, x.grad, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("deg", [1, 2, 3, 4])
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_sh_forward_backward(cuda_dev, deg):
     from seald_nerf_b200.shencoder import SHEncoder
     from oracle import encoders as oe
@@ -45,21 +45,24 @@ def test_sh_forward_backward(cuda_dev, deg):
     d = d.requires_grad_(True)
     y = enc(d)
     y_o = oe.sh_encode(d.detach().cpu().numpy(), deg)
-    np.testing.assert_allclose(y.detach().cpu().numpy(), y_o, rtol=1e-5, atol=2e-6)
+    lo = 1 if deg > 4 else 0  # (the scipy-based oracle of bands 4..7 is defined for unit vectors: skip the zero row there)
+    np.testing.assert_allclose(y.detach().cpu().numpy()[lo:], y_o[lo:], rtol=1e-5, atol=2e-5 if deg > 4 else 2e-6)
     g = torch.randn_like(y)
     (y * g).sum().backward()
     J = oe.sh_jacobian_fd(d.detach().cpu().numpy().astype(np.float64), deg)
     gi_o = np.einsum("bc,bdc->bd", g.cpu().numpy().astype(np.float64), J)
-    np.testing.assert_allclose(d.grad.cpu().numpy(), gi_o, rtol=1e-4, atol=1e-4)
+    if deg <= 4:  # (finite differences of the oracle leave the unit sphere: only meaningful for the polynomial restatement)
+        np.testing.assert_allclose(d.grad.cpu().numpy(), gi_o, rtol=1e-4, atol=1e-4)
     ref = load_ref("shencoder")
     if ref is not None:
         out_r = torch.empty_like(y)
         dy_r = torch.empty(d.shape[0], 3 * deg * deg, device=cuda_dev)
         ref.sh_encode_forward(d.detach(), out_r, d.shape[0], 3, deg, dy_r)
-        torch.testing.assert_close(out_r, y.detach(), rtol=1e-6, atol=1e-7)
+        # bands 0..3: the same expressions; bands 4..7: z-polynomial x (x, y)-polynomial vs the reference's expanded forms (fp32 round-off)
+        torch.testing.assert_close(out_r, y.detach(), rtol=1e-6 if deg <= 4 else 1e-5, atol=1e-7 if deg <= 4 else 2e-5)  # (measured 5e-6 on band-7 values of magnitude ~3)
         gi_r = torch.zeros_like(d)
         ref.sh_encode_backward(g, d.detach(), d.shape[0], 3, deg, dy_r, gi_r)
-        torch.testing.assert_close(gi_r, d.grad, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(gi_r, d.grad, rtol=1e-5 if deg <= 4 else 1e-4, atol=1e-5 if deg <= 4 else 2e-4)
 
 
 def test_trunc_exp(cuda_dev):
