@@ -356,6 +356,10 @@ int seald_mlp_wgrad(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const i
  * operands as the tcgen05 deformation kernels save them: [tile][width/8][128 rows][8 halves] per 128-row tile (dead rows of a live
  * tile zero); such a tile is fetched with one cp.async.bulk per operand. */
 int seald_mlp_wgrad_umma(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream);
+/* The same + GradScaler's overflow flag: *found_inf |= bits of 1.0f when a partial sum added to a weight gradient is not finite (then the
+ * accumulated gradient is not finite either): replaces a separate seald_grad_finite_check pass over the weight gradients. */
+int seald_mlp_wgrad_umma_flag(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, int32_t* found_inf,
+                              seald_stream_t stream);
 
 /* FFMLP-compatible fused MLP.  Replace ffmlp_forward / ffmlp_inference / ffmlp_backward (ffmlp/src/ffmlp.h:8-11).
  * inputs [B,input_dim] f16 (input_dim % 16 == 0, <= 128), weights: flat f16 buffer (ffmlp.cu:632 layout),
@@ -447,8 +451,10 @@ int seald_mlp_tail(float* p, float* g, float* m, float* v, const seald_tail_seg*
 /* seald_mlp_tail for the data-parallel trainer: the gradient of element i is the sum over the ranks' peer-mapped gradient buffers
  * (peer_grads[r] + w_off + i, summed in rank order), the step overflows when some rank's flag (peer_grads[r][flag_off], a float) is
  * set or a summed gradient is not finite; the decision is kept in the rank-local word *found_local (zero-initialised, reset here).
- * Local gradients and flags are not cleared (peers may still read them).  p / m / v: this rank's MLP region. */
-int seald_mlp_tail_dp(const void* const* peer_grads, int world, uint64_t w_off, uint64_t flag_off, int32_t* found_local, float* p, float* m,
+ * Local gradients and flags are not cleared (peers may still read them).  p / m / v: this rank's MLP region.  flags_only != 0: every rank
+ * has already flagged its own gradients (table scatter + seald_mlp_wgrad_umma_flag), the decision is the sum of the flags alone and the kernel
+ * runs without its check pass and grid barrier. */
+int seald_mlp_tail_dp(const void* const* peer_grads, int world, uint64_t w_off, uint64_t flag_off, int flags_only, int32_t* found_local, float* p, float* m,
                       float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2, float eps, int32_t* step_dev,
                       float* loss_scale, int32_t* growth_tracker, float growth, float backoff, int interval, int32_t* stash, float* lr_scale,
                       int32_t* sched_step, int sched_iters, int32_t* sync2, seald_stream_t stream);

@@ -64,6 +64,7 @@ _SIGS = {
     "seald_field_heads_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_mlp_wgrad": [_vp, _i32, _u32, _vp, _vp],
     "seald_mlp_wgrad_umma": [_vp, _i32, _u32, _vp, _vp],
+    "seald_mlp_wgrad_umma_flag": [_vp, _i32, _u32, _vp, _vp, _vp],
     "seald_ffmlp_forward": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "seald_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp],
     "seald_select_frame": [_vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp],
@@ -88,7 +89,7 @@ _SIGS = {
     "seald_adam_step": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _vp],
     "seald_adam_step_ex": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _u32, _vp],
     "seald_adam_step_lr": [_vp, _vp, _vp, _vp, C.c_uint64, _f32, _vp, _f32, _f32, _f32, _u32, _vp, _vp, _vp, _vp, _i32, _u32, _vp],
-    "seald_mlp_tail_dp": [_vp, _i32, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _f32, _f32,
+    "seald_mlp_tail_dp": [_vp, _i32, C.c_uint64, C.c_uint64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _f32, _f32,
                           _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "seald_optimizer_step": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _vp,
                              _vp, _vp, _vp, _vp, C.c_uint64, _f32, _vp, _vp],

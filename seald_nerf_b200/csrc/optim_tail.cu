@@ -76,6 +76,8 @@ struct TailPeers {
     int world;
     size_t w_off, flag_off;         // MLP region / overflow flag (a float) inside it
     int* found_local;
+    int flags_only;                 // 1: every rank has already raised its flag for its own gradients (table scatter + weight-gradient
+                                    // flush): the decision is the sum of the flags alone — no check pass, no grid barrier
 };
 
 template <bool PEERS>
@@ -99,27 +101,41 @@ __global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restri
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
 
-    // ---- phase 0: overflow check over this thread's gradients -----------------------------------------------------------------
-    bool bad = false;
-    for (uint32_t i = i0; i < n; i += stride) bad |= !isfinite(tail_grad<PEERS>(g, pr, i));
-    if constexpr (PEERS) {
-        if (i0 == 0) {  // the ranks' overflow flags (raised by their table scatters)
+    bool skip;
+    if (PEERS && pr.flags_only) {
+        // decision = "some rank raised its flag" (each rank flags its own gradients: table scatter + weight-gradient flush); every CTA
+        // reads the W flags itself — the same answer everywhere, no check pass, no grid barrier
+        __shared__ int s_found;
+        if (threadIdx.x == 0) {
             float f = 0.0f;
             for (int r = 0; r < pr.world; r++) f += pr.g[r][pr.flag_off];
-            bad |= !(f == 0.0f);
+            s_found = (f == 0.0f) ? 0 : 0x3f800000;
         }
+        __syncthreads();
+        skip = s_found != 0;
+        if (i0 == 0) *found = s_found;  // (read again in phase 2 only, behind the ticket)
+    } else {
+        // ---- phase 0: overflow check over this thread's gradients -------------------------------------------------------------
+        bool bad = false;
+        for (uint32_t i = i0; i < n; i += stride) bad |= !isfinite(tail_grad<PEERS>(g, pr, i));
+        if constexpr (PEERS) {
+            if (i0 == 0) {  // the ranks' overflow flags (raised by their table scatters)
+                float f = 0.0f;
+                for (int r = 0; r < pr.world; r++) f += pr.g[r][pr.flag_off];
+                bad |= !(f == 0.0f);
+            }
+        }
+        const int any_bad = __syncthreads_or(bad ? 1 : 0);
+        if (threadIdx.x == 0) {
+            if (any_bad) atomicOr(found, 0x3f800000);
+            __threadfence();
+            atomicAdd(st.sync, 1);
+            while (ld_acquire(st.sync) < (int)gridDim.x) __nanosleep(32);
+        }
+        __syncthreads();
+        skip = ld_acquire(found) != 0;
     }
-    const int any_bad = __syncthreads_or(bad ? 1 : 0);
-    if (threadIdx.x == 0) {
-        if (any_bad) atomicOr(found, 0x3f800000);
-        __threadfence();
-        atomicAdd(st.sync, 1);
-        while (ld_acquire(st.sync) < (int)gridDim.x) __nanosleep(32);
-    }
-    __syncthreads();
-
     // ---- phase 1: Adam + fp16 copies ----------------------------------------------------------------------------------------------
-    const bool skip = ld_acquire(found) != 0;
     if (!skip) {
         const double stp = (double)(*st.step_dev + 1);
         const float bc1 = (float)(1.0 - pow((double)beta1, stp));
@@ -243,7 +259,7 @@ static int tail_launch(float* p, float* g, float* m, float* v, const seald_tail_
     return launch_status();
 }
 
-extern "C" int seald_mlp_tail_dp(const void* const* peer_grads, int world, uint64_t w_off, uint64_t flag_off, int32_t* found_local, float* p,
+extern "C" int seald_mlp_tail_dp(const void* const* peer_grads, int world, uint64_t w_off, uint64_t flag_off, int flags_only, int32_t* found_local, float* p,
                                  float* m, float* v, const seald_tail_seg* segs, int n_segs, float lr, float beta1, float beta2, float eps,
                                  int32_t* step_dev, float* loss_scale, int32_t* growth_tracker, float growth, float backoff, int interval,
                                  int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters, int32_t* sync2, seald_stream_t stream) {
@@ -253,7 +269,7 @@ extern "C" int seald_mlp_tail_dp(const void* const* peer_grads, int world, uint6
         if (!peer_grads[r]) return SEALD_E_BADARG;
         pr.g[r] = (const float*)peer_grads[r];
     }
-    pr.world = world; pr.w_off = (size_t)w_off; pr.flag_off = (size_t)flag_off; pr.found_local = found_local;
+    pr.world = world; pr.w_off = (size_t)w_off; pr.flag_off = (size_t)flag_off; pr.found_local = found_local; pr.flags_only = flags_only ? 1 : 0;
     // (g: unused in this mode, the sums are read from the peers; found_inf: the local word doubles as the required argument)
     return tail_launch(p, p, m, v, segs, n_segs, lr, beta1, beta2, eps, step_dev, loss_scale, found_local, growth_tracker, growth, backoff, interval,
                        stash, lr_scale, sched_step, sched_iters, sync2, TableAdam{}, stream, &pr);

@@ -63,7 +63,7 @@ __host__ __device__ constexpr uint32_t idesc_mn_major(const uint32_t n) {
 }
 
 __global__ void __launch_bounds__(kUWThreads) k_wgrad_umma(const __grid_constant__ UWgradJobs jobs, const int M, const int* __restrict__ m_dev,
-                                                           const uint32_t ring_bytes) {
+                                                           const uint32_t ring_bytes, int* __restrict__ found_inf) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar_empty = reinterpret_cast<uint64_t*>(smem + ring_bytes);  // [<= 8] the MMAs reading a stage have completed
     uint64_t* bar_done = bar_empty + kUWMaxTileStages;                     // all MMAs of this CTA have completed
@@ -221,11 +221,17 @@ __global__ void __launch_bounds__(kUWThreads) k_wgrad_umma(const __grid_constant
     const bool row_ok = tid < jb.n_real;
     float* out_row = jb.dW + (size_t)tid * jb.ldw;
     const bool vec_ok = (jb.ldw % 4 == 0) && (((uintptr_t)jb.dW & 15) == 0);
+    bool bad = false;  // a non-finite partial sum makes the accumulated gradient non-finite: GradScaler's found_inf (optional)
     for (int q = 0; q < jb.n_in; q += 16) {
         uint32_t v[16];
         umma::tmem_ld16(t_lane + q, v);
         umma::wait_ld();
         if (row_ok) {
+            if (found_inf) {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (q + i < jb.k_real) bad |= !isfinite(__uint_as_float(v[i]));
+            }
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const int col = q + i;
@@ -240,6 +246,7 @@ __global__ void __launch_bounds__(kUWThreads) k_wgrad_umma(const __grid_constant
             }
         }
     }
+    if (found_inf && __any_sync(0xffffffffu, bad) && (tid & 31) == 0) atomicOr(found_inf, 0x3f800000);
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) {
@@ -253,7 +260,19 @@ __global__ void __launch_bounds__(kUWThreads) k_wgrad_umma(const __grid_constant
 using namespace seald;
 
 // Same job table as seald_mlp_wgrad (include/seald_b200.h); N = out columns of G (16 / 64 / 128), K = in columns of A.
+static int wgrad_umma_launch(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, int32_t* found_inf, seald_stream_t stream);
+
 extern "C" int seald_mlp_wgrad_umma(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, seald_stream_t stream) {
+    return wgrad_umma_launch(jobs, n_jobs, M, m_dev, nullptr, stream);
+}
+
+// + GradScaler's overflow flag: *found_inf |= 0x3f800000 when a partial sum added to a weight gradient is not finite
+extern "C" int seald_mlp_wgrad_umma_flag(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, int32_t* found_inf,
+                                         seald_stream_t stream) {
+    return wgrad_umma_launch(jobs, n_jobs, M, m_dev, found_inf, stream);
+}
+
+static int wgrad_umma_launch(const seald_wgrad_job* jobs, int n_jobs, uint32_t M, const int32_t* m_dev, int32_t* found_inf, seald_stream_t stream) {
     if (M == 0 || n_jobs == 0) return 0;
     if (!jobs || n_jobs < 0 || n_jobs > kUWMaxJobs) return SEALD_E_BADARG;
     UWgradJobs js;
@@ -292,6 +311,6 @@ extern "C" int seald_mlp_wgrad_umma(const seald_wgrad_job* jobs, int n_jobs, uin
     const size_t smem = any_tile ? kUWSmemTile : kUWSmem;
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUWSmemTile);
     if (e != cudaSuccess) return (int)e;
-    k_wgrad_umma<<<total, kUWThreads, smem, to_stream(stream)>>>(js, (int)M, m_dev, (uint32_t)(smem - 256));
+    k_wgrad_umma<<<total, kUWThreads, smem, to_stream(stream)>>>(js, (int)M, m_dev, (uint32_t)(smem - 256), found_inf);
     return launch_status();
 }

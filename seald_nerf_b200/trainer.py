@@ -165,9 +165,11 @@ class FusedTrainer:
         # the fused MLP tail (csrc/optim_tail.cu): single GPU; the data-parallel modes keep their exchange-fused optimiser kernels
         self.fused_tail = self.dp_mode == "single" and os.environ.get("SEALD_FUSED_TAIL", "1") != "0"
         # data parallel with the fused exchange: the same single-launch tail with the gradients summed over the peers inside it
-        # (seald_mlp_tail_dp).  Measured SLOWER than the four small kernels on 2 GPUs (0.3276 vs 0.3135 ms per step: two rounds of peer
-        # loads around a grid barrier), so it is used only where it is needed — it is what advances the device-side LR schedule
-        self.dp_tail = self.dp_mode == "fused" and (os.environ.get("SEALD_DP_TAIL", "0") != "0" or bool(self.lr_decay_iters))
+        # (seald_mlp_tail_dp), in its flags-only form — every rank flags its own gradients (table scatter + weight-gradient flush), the
+        # tail sums the flags: no check pass, no grid barrier.  Measured on 2 GPUs: 0.3145 ms (17 launches) vs 0.3172 ms (20) with the
+        # four small kernels; the variant WITH the check pass + grid barrier was slower (0.3276).  It also advances the LR schedule
+        self.dp_tail = (self.dp_mode == "fused" and F.WGRAD_IMPL == "umma"
+                        and (os.environ.get("SEALD_DP_TAIL", "1") != "0" or bool(self.lr_decay_iters)))
         # torch_ema.ExponentialMovingAverage over every parameter (ema_decay = 0.95 in main_dnerf.py:136): a shadow of the flat buffer
         self.ema_shadow = self.params.clone() if self.ema_decay else None
         self.ema_num_updates = 0
@@ -465,7 +467,11 @@ class FusedTrainer:
             F.deform_backward(cfg, hw, ws.grad_x01, self.time, M, m_dev, ws.fwd_d, ws.bwd_d, ws.gout_d)
 
         def wgrad():
-            F.mlp_wgrad(self.jobs, self.n_jobs, M, m_dev)
+            if self.dp_tail and F.WGRAD_IMPL == "umma":
+                # + this rank's overflow flag for its weight gradients (no separate finite-check pass; the tail sums the ranks' flags)
+                _lib.call("seald_mlp_wgrad_umma_flag", C.cast(self.jobs, C.c_void_p), self.n_jobs, M, ptr(m_dev), ptr(self.found_inf), _lib.stream())
+            else:
+                F.mlp_wgrad(self.jobs, self.n_jobs, M, m_dev)
 
         def composite_loss_fused():
             # composite forward + loss + composite backward in one kernel (bg/gt are indexed by ray); the loss accumulator was zeroed by
@@ -684,7 +690,7 @@ class FusedTrainer:
             # ONE launch: flags + MLP gradients summed over the peers, Adam on the replicated weights, fp16 copies / tcgen05 tiles,
             # GradScaler.update, LambdaLR; the stash carries {found_inf, step, loss scale, lr factor} to the deferred shard pass
             o = 4 * ntp
-            _lib.call("seald_mlp_tail_dp", C.cast(self._peer_grads, C.c_void_p), self.world_size, ntp, self.n_flag, ptr(self.found_inf_global),
+            _lib.call("seald_mlp_tail_dp", C.cast(self._peer_grads, C.c_void_p), self.world_size, ntp, self.n_flag, 1, ptr(self.found_inf_global),
                       self.params.data_ptr() + o, self.exp_avg.data_ptr() + o, self.exp_avg_sq.data_ptr() + o,
                       C.cast(self._tail_segs, C.c_void_p), len(self._tail_segs), self.lr_net, b1, b2, self.eps, ptr(self.step_dev),
                       ptr(self.loss_scale), ptr(self.growth_tracker), 2.0, 0.5, self.growth_interval, ptr(self.pending), ptr(self.lr_scale),

@@ -185,3 +185,43 @@ def test_umma_deform_backward_matches_mma_sync(cuda_dev, M, m_live, tval):
         assert torch.equal(a[l] == 0, b[l] == 0) or float(((a[l] == 0) != (b[l] == 0)).float().mean()) < 1e-3  # same ReLU mask
     if m_live is not None:
         assert float(outs[1][0][:, n:].abs().max()) == 0.0
+
+
+def test_umma_wgrad_raises_the_overflow_flag(cuda_dev):
+    """seald_mlp_wgrad_umma_flag: GradScaler's found_inf from the weight-gradient flush itself — clean operands leave the flag alone,
+    one inf in an activation gradient (tile-image layout) raises it; the gradients equal those of the unflagged entry point."""
+    import ctypes as C
+    from seald_nerf_b200 import _lib, field as F
+    from seald_nerf_b200._lib import ptr
+    from seald_nerf_b200.dnerf.network import NeRFNetwork
+    torch.manual_seed(0)
+    net = NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True).to(cuda_dev)
+    cfg = net._field_cfg
+    M = 1000
+    ws = F.FieldWorkspace(cfg, M, cuda_dev, training=True)
+    g = torch.Generator(device=cuda_dev).manual_seed(1)
+    for name in ("in_buf", "fwd_d", "bwd_d", "gout_d", "cin", "feat_img", "fwd_s", "fwd_c", "bwd_s", "bwd_c", "gout_s", "gout_c"):
+        t = getattr(ws, name)
+        t.copy_((torch.randn(t.shape, device=cuda_dev, generator=g) * 0.1).to(t.dtype))
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+    res = []
+    for poison in (False, True):
+        if poison:
+            ws.bwd_d[3].view(-1)[12345] = float("inf")
+        grads = [torch.zeros_like(w, dtype=torch.float32) for w in net.mlp_weights()]
+        jobs, n_jobs = F.wgrad_jobs(cfg, ws, grads, deform=True)
+        flag.zero_()
+        _lib.call("seald_mlp_wgrad_umma_flag", C.cast(jobs, C.c_void_p), n_jobs, M, None, ptr(flag), _lib.stream())
+        torch.cuda.synchronize()
+        res.append((int(flag), grads))
+    assert res[0][0] == 0 and res[1][0] == 0x3f800000
+    plain = [torch.zeros_like(w, dtype=torch.float32) for w in net.mlp_weights()]
+    ws.bwd_d[3].view(-1)[12345] = 0.0
+    jobs, n_jobs = F.wgrad_jobs(cfg, ws, plain, deform=True)
+    F.mlp_wgrad(jobs, n_jobs, M, None)
+    torch.cuda.synchronize()
+    for a, b in zip(res[0][1], plain):
+        scale = float(b.abs().max())
+        if scale > 0:  # (the poisoned element was random before: only that layer's gradient differs slightly)
+            assert float((a - b).abs().max()) <= 5e-2 * scale
+    assert not all(bool(torch.isfinite(x).all()) for x in res[1][1])
