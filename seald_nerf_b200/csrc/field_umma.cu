@@ -9,7 +9,9 @@
 //                                 the group's mbarrier (and to the weight stage's "free" barrier).
 //   loader warp (one thread)    : streams the layer weights global -> shared with cp.async.bulk (3 stages of 32 KiB, pre-packed in
 //                                 the canonical K-major layout of umma.cuh), refilling a stage once every group's MMAs on it are done.
-//   4 warps per group           : thread t owns sample row t of its tile = TMEM lane t.  Layer 0 input: frequency
+//   4 warps per group (8 for G = 2: two warpgroups, each half of the output columns — the small-batch layer step is epilogue bound:
+//                                 backward 34.7 -> 25.8 us at 31.7k samples)
+//                               : thread t owns sample row t of its tile = TMEM lane t.  Layer 0 input: frequency
 //                                 encoding of xyz (63) and t (13) written straight into the A-operand tile.  After each
 //                                 layer: tcgen05.ld the fp32 row, ReLU, pack to fp16, store as the next layer's A tile
 //                                 (and, when training, into fwd_buf for the backward pass).  Last layer: dx, x' = x + dx,
@@ -40,7 +42,11 @@ constexpr uint32_t kTileBytes = kUW * kUW * 2;  // 32 KiB: one A tile / one weig
 
 template <int G>
 struct UmmaSmem {
-    static constexpr int THREADS = G * 128 + (G + 1) * 32;  // G groups x 4 epilogue warps + G issuer warps + 1 loader warp
+    // G == 2 (training-size batches: one or two tiles per SM, the step of a layer is dominated by its epilogue): TWO warpgroups per
+    // tile, each taking half of the 128 output columns (warps w and w + 4 of a group share a tensor-memory lane quadrant)
+    static constexpr int EW = (G == 2) ? 2 : 1;
+    static constexpr int EPI = 128 * EW;                    // epilogue threads per group
+    static constexpr int THREADS = G * EPI + (G + 1) * 32;  // G groups x 4 EW epilogue warps + G issuer warps + 1 loader warp
     static constexpr uint32_t TMEM_COLS = G * kUW;
     static constexpr size_t A_OFF = 0;
     static constexpr size_t W_OFF = G * kTileBytes;
@@ -86,8 +92,8 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                                                                       __half* __restrict__ in_buf, __half* __restrict__ fwd_buf) {
     extern __shared__ __align__(128) unsigned char smem[];
     using SM = UmmaSmem<G>;
-    constexpr int ISSUE0 = G * 4;      // warps ISSUE0 .. ISSUE0 + G - 1 issue the MMAs of group 0 .. G - 1
-    constexpr int LOADER = G * 4 + G;  // streams the weights
+    constexpr int ISSUE0 = G * 4 * SM::EW;  // warps ISSUE0 .. ISSUE0 + G - 1 issue the MMAs of group 0 .. G - 1
+    constexpr int LOADER = ISSUE0 + G;      // streams the weights
     unsigned char* s_a = smem + SM::A_OFF;
     unsigned char* s_w = smem + SM::W_OFF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
 
     if (tid == 0) {
         for (int i = 0; i < 3; i++) { umma::mbar_init(bar_full + i, 1); umma::mbar_init(bar_wfree + i, G); }
-        for (int i = 0; i < G; i++) { umma::mbar_init(bar_aready + i, 128); umma::mbar_init(bar_mma + i, 1); }
+        for (int i = 0; i < G; i++) { umma::mbar_init(bar_aready + i, SM::EPI); umma::mbar_init(bar_mma + i, 1); }
         umma::mbar_fence_init();
     }
     if (warp == LOADER) umma::tmem_alloc(tmem_slot, SM::TMEM_COLS);
@@ -155,7 +161,8 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
         }
     } else {
         // =============================== epilogue groups: one thread per sample row ===============================
-        const int g = tid >> 7, r = tid & 127;
+        const int g = tid / SM::EPI, te = tid - g * SM::EPI, r = te & 127, half = te >> 7;  // half: which share of the columns (EW == 2)
+        constexpr int QN = 4 / SM::EW, C8N = (kUK0 / 8) / SM::EW;
         unsigned char* a_tile = s_a + (size_t)g * kTileBytes;
         const uint32_t t_lane = tmem_base + ((uint32_t)(r & ~31) << 16) + g * kUW;  // this warp's 32-lane quadrant, group's columns
         const float tval = *time;
@@ -174,8 +181,9 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                 const bool live = row < m_used;
                 if (live) { px = xyz[(size_t)row * 3]; py = xyz[(size_t)row * 3 + 1]; pz = xyz[(size_t)row * 3 + 2]; }
                 const float xv[3] = {px, py, pz};
-#pragma unroll
-                for (int c8 = 0; c8 < kUK0 / 8; c8++) {
+                // 8 columns of the encoded input -> one 16-byte chunk of the A tile (c8 is a compile-time constant after unrolling: the
+                // channel -> (frequency, phase, dimension) decode of freq_channel folds away)
+                auto encode_chunk = [&](const int c8) {
                     uint32_t w[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
@@ -198,6 +206,13 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                     // saved in the tile-image layout (umma.cuh): the shared-memory tile as it is, 512 contiguous bytes per warp store;
                     // dead rows of a live tile are zeros (their values never reach a weight gradient)
                     if (save_tile) *reinterpret_cast<uint4*>(in_buf + (((size_t)tile * (kUK0 / 8) + c8) * kUW + r) * 8) = u;
+                };
+                if (SM::EW == 1 || half == 0) {
+#pragma unroll
+                    for (int c8 = 0; c8 < C8N; c8++) encode_chunk(c8);
+                } else {
+#pragma unroll
+                    for (int c8 = C8N; c8 < 2 * C8N; c8++) encode_chunk(c8);
                 }
                 umma::fence_proxy_async();
                 umma::mbar_arrive(bar_aready + g);
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
             umma::fence_after_sync();
             if (l < n_layers - 1) {
 #pragma unroll 1
-                for (int q = 0; q < 4; q++) {
+                for (int q = half * QN; q < (half + 1) * QN; q++) {
                     uint32_t v[32];
                     umma::tmem_ld32(t_lane + q * 32, v);
                     umma::wait_ld();
@@ -230,7 +245,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                 umma::fence_before_sync();
                 umma::fence_proxy_async();
                 umma::mbar_arrive(bar_aready + g);
-            } else {
+            } else if (half == 0) {
                 uint32_t v[16];
                 umma::tmem_ld16(t_lane, v);
                 umma::wait_ld();
@@ -311,7 +326,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
                                                                                   __half* __restrict__ gout_buf) {
     extern __shared__ __align__(128) unsigned char smem[];
     using SM = UmmaSmem<G>;
-    constexpr int ISSUE0 = G * 4, LOADER = G * 4 + G;  // same warp roles as the forward kernel
+    constexpr int ISSUE0 = G * 4 * SM::EW, LOADER = ISSUE0 + G;  // same warp roles as the forward kernel
     unsigned char* s_a = smem + SM::A_OFF;
     unsigned char* s_w = smem + SM::W_OFF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
@@ -331,7 +346,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
 
     if (tid == 0) {
         for (int i = 0; i < 3; i++) { umma::mbar_init(bar_full + i, 1); umma::mbar_init(bar_wfree + i, G); }
-        for (int i = 0; i < G; i++) { umma::mbar_init(bar_aready + i, 128); umma::mbar_init(bar_mma + i, 1); }
+        for (int i = 0; i < G; i++) { umma::mbar_init(bar_aready + i, SM::EPI); umma::mbar_init(bar_mma + i, 1); }
         umma::mbar_fence_init();
     }
     if (warp == LOADER) umma::tmem_alloc(tmem_slot, SM::TMEM_COLS);
@@ -374,7 +389,8 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
             }
         }
     } else {
-        const int g = tid >> 7, r = tid & 127;
+        const int g = tid / SM::EPI, te = tid - g * SM::EPI, r = te & 127, half = te >> 7;  // half: which share of the columns (EW == 2)
+        constexpr int QN = 4 / SM::EW;
         unsigned char* a_tile = s_a + (size_t)g * kTileBytes;
         const uint32_t t_lane = tmem_base + ((uint32_t)(r & ~31) << 16) + g * kUW;
         // at t == 0 the deformation is replaced by zeros (network.py:140-141): no gradient reaches the net
@@ -396,11 +412,13 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
                 const __half2 h01 = __floats2half2_rn(gv[0], gv[1]), h2 = __floats2half2_rn(gv[2], 0.0f);
                 const uint4 u0 = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h2), 0u, 0u);
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(a_tile + ((size_t)0 * kUW + r) * 16) = u0;
-                *reinterpret_cast<uint4*>(a_tile + ((size_t)1 * kUW + r) * 16) = z;
-                if (live_tile) {  // tile-image layout, dead rows zero (u0 is zero for them)
-                    *reinterpret_cast<uint4*>(gout_buf + (((size_t)tile * 2 + 0) * kUW + r) * 8) = u0;
-                    *reinterpret_cast<uint4*>(gout_buf + (((size_t)tile * 2 + 1) * kUW + r) * 8) = z;
+                if (half == 0) {
+                    *reinterpret_cast<uint4*>(a_tile + ((size_t)0 * kUW + r) * 16) = u0;
+                    *reinterpret_cast<uint4*>(a_tile + ((size_t)1 * kUW + r) * 16) = z;
+                    if (live_tile) {  // tile-image layout, dead rows zero (u0 is zero for them)
+                        *reinterpret_cast<uint4*>(gout_buf + (((size_t)tile * 2 + 0) * kUW + r) * 8) = u0;
+                        *reinterpret_cast<uint4*>(gout_buf + (((size_t)tile * 2 + 1) * kUW + r) * 8) = z;
+                    }
                 }
                 umma::fence_proxy_async();
                 umma::mbar_arrive(bar_aready + g);
@@ -415,12 +433,12 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
                 for (int c4 = 0; c4 < 4; c4++)
                     hm[c4] = live ? __ldg(reinterpret_cast<const uint4*>(hsave + (size_t)(q * 4 + c4) * kUW * 8)) : make_uint4(0u, 0u, 0u, 0u);
             };
-            load_mask(0);  // in flight while the MMAs finish
+            load_mask(half * QN);  // in flight while the MMAs finish
             umma::mbar_wait(bar_mma + g, i & 1);
             umma::fence_after_sync();
             const bool feeds_next = (s + 1 < n_steps);
 #pragma unroll 1
-            for (int q = 0; q < 4; q++) {
+            for (int q = half * QN; q < (half + 1) * QN; q++) {
                 uint32_t v[32];
                 umma::tmem_ld32(t_lane + q * 32, v);
                 umma::wait_ld();
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_backward_umm
                     }
                     out[c4] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-                if (q + 1 < 4) load_mask(q + 1);
+                if (q + 1 < (half + 1) * QN) load_mask(q + 1);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++) {
                     if (feeds_next) *reinterpret_cast<uint4*>(a_tile + ((size_t)(q * 4 + c4) * kUW + r) * 16) = out[c4];
