@@ -467,6 +467,7 @@ int seald_optimizer_step(float* p, float* g, float* m, float* v, const seald_tai
                          float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker, float growth,
                          float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step, int sched_iters, int32_t* sync2,
                          float* table_p, float* table_g, float* table_m, float* table_v, uint64_t table_n, float table_lr, void* table_p16,
+                         int flags_final /* 1: *found_inf is final already (scatter + seald_mlp_wgrad_umma_flag): no check pass / barrier */,
                          seald_stream_t stream);
 
 /* torch_ema.ExponentialMovingAverage.update: shadow -= (1 - decay) * (shadow - param) (ema_decay = 0.95, main_dnerf.py:136;

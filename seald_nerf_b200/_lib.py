@@ -92,7 +92,7 @@ _SIGS = {
     "seald_mlp_tail_dp": [_vp, _i32, C.c_uint64, C.c_uint64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _f32, _f32,
                           _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "seald_optimizer_step": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _vp,
-                             _vp, _vp, _vp, _vp, C.c_uint64, _f32, _vp, _vp],
+                             _vp, _vp, _vp, _vp, C.c_uint64, _f32, _vp, _i32, _vp],
     "seald_mlp_tail": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "seald_ema_update": [_vp, _vp, C.c_uint64, _f32, _vp],
     "seald_umma_probe": [_i32, _i32, _i32, _i32, _vp, _vp],

@@ -64,6 +64,7 @@ struct TableAdam {
     size_t n;
     float lr;
     __half* p16;
+    int flags_final;  // 1: *found_inf is already final (table scatter + weight-gradient flush raised it): no check pass, no grid barrier
 };
 
 // Data parallel (PEERS): the gradient of element i is the sum over the ranks' gradient buffers (peer-mapped, read in rank order on
@@ -114,6 +115,10 @@ __global__ void __launch_bounds__(256, TABLE ? 4 : 1) k_mlp_tail(float* __restri
         __syncthreads();
         skip = s_found != 0;
         if (i0 == 0) *found = s_found;  // (read again in phase 2 only, behind the ticket)
+    } else if (TABLE && tb.flags_final) {
+        // the overflow flag was raised by the kernels that produced the gradients (seald_grid_encode_backward_* for the table,
+        // seald_mlp_wgrad_umma_flag for the weights): nothing to check, nothing to wait for
+        skip = ld_acquire(found) != 0;
     } else {
         // ---- phase 0: overflow check over this thread's gradients -------------------------------------------------------------
         bool bad = false;
@@ -287,11 +292,11 @@ extern "C" int seald_optimizer_step(float* p, float* g, float* m, float* v, cons
                                     float beta2, float eps, int32_t* step_dev, float* loss_scale, int32_t* found_inf, int32_t* growth_tracker,
                                     float growth, float backoff, int interval, int32_t* stash, float* lr_scale, int32_t* sched_step,
                                     int sched_iters, int32_t* sync2, float* table_p, float* table_g, float* table_m, float* table_v,
-                                    uint64_t table_n, float table_lr, void* table_p16, seald_stream_t stream) {
+                                    uint64_t table_n, float table_lr, void* table_p16, int flags_final, seald_stream_t stream) {
     if (!table_p || table_n == 0) return SEALD_E_BADARG;
     return tail_launch(p, g, m, v, segs, n_segs, lr, beta1, beta2, eps, step_dev, loss_scale, found_inf, growth_tracker, growth, backoff, interval,
                        stash, lr_scale, sched_step, sched_iters, sync2,
-                       TableAdam{table_p, table_g, table_m, table_v, (size_t)table_n, table_lr, (__half*)table_p16}, stream);
+                       TableAdam{table_p, table_g, table_m, table_v, (size_t)table_n, table_lr, (__half*)table_p16, flags_final ? 1 : 0}, stream);
 }
 
 extern "C" int seald_ema_update(float* shadow, const float* param, uint64_t n, float decay, seald_stream_t stream) {

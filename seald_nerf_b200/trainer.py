@@ -467,7 +467,7 @@ class FusedTrainer:
             F.deform_backward(cfg, hw, ws.grad_x01, self.time, M, m_dev, ws.fwd_d, ws.bwd_d, ws.gout_d)
 
         def wgrad():
-            if self.dp_tail and F.WGRAD_IMPL == "umma":
+            if self._wgrad_flags():
                 # + this rank's overflow flag for its weight gradients (no separate finite-check pass; the tail sums the ranks' flags)
                 _lib.call("seald_mlp_wgrad_umma_flag", C.cast(self.jobs, C.c_void_p), self.n_jobs, M, ptr(m_dev), ptr(self.found_inf), _lib.stream())
             else:
@@ -654,6 +654,14 @@ class FusedTrainer:
                       self.lr, lr_scale, b1, b2, self.eps, 1, step_dev, loss_scale, found_inf, ptr(self.table16_pad), 1, cap, st)
         return 1
 
+    def _wgrad_flags(self):
+        """The weight-gradient kernel raises GradScaler's overflow flag itself (seald_mlp_wgrad_umma_flag): the single-launch optimiser
+        (one GPU, table pass in place) and the data-parallel tail then need no check pass and no grid barrier."""
+        if F.WGRAD_IMPL != "umma":
+            return False
+        return self.dp_tail or (self.fused_tail and not self.defer_table_update and self.dp_mode == "single" and self.one_launch_optimizer
+                                and os.environ.get("SEALD_FLAGS_FINAL", "1") != "0")
+
     def _optimizer_table_deferred(self):
         """The hash-table pass of the previous step's optimiser, with the overflow decision / step number / loss scale that step
         stashed (the first call finds found_inf = 1: nothing pending)."""
@@ -679,7 +687,7 @@ class FusedTrainer:
             if not self.defer_table_update and self.dp_mode == "single" and self.one_launch_optimizer:
                 # one GPU, table pass in place: the whole scaler.step / scaler.update / lr_scheduler.step in ONE launch
                 _lib.call("seald_optimizer_step", *tail_args, ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                          self.n_table_pad, self.lr, ptr(self.table16_pad), st)
+                          self.n_table_pad, self.lr, ptr(self.table16_pad), 1 if self._wgrad_flags() else 0, st)
                 return 1
             _lib.call("seald_mlp_tail", *tail_args, st)
             n = 1

@@ -175,6 +175,27 @@ def test_data_parallel_modes_two_gpus():
     assert "MISMATCH" not in p.stdout and p.stdout.count(" OK") >= 9
 
 
+def test_overflowing_loss_scale_skips_the_step_and_halves_the_scale(cuda_dev):
+    """GradScaler semantics through the WHOLE step with the overflow flag raised by the kernels that produce the gradients (table
+    scatter + seald_mlp_wgrad_umma_flag; the one-launch optimiser has no check pass of its own on one GPU): an absurd loss scale makes
+    the fp16 gradients overflow -> nothing moves, the scale halves, the step counter stays; once the scale is sane the step is taken."""
+    from seald_nerf_b200.trainer import FusedTrainer
+    o, d, t, gt = _batch(cuda_dev, n=2048, seed=5)
+    model = _scene(cuda_dev, seed=2)
+    tr = FusedTrainer(model, num_rays=2048, max_samples=2048 * 48, lr=1e-2, lr_net=1e-3, perturb=False, init_loss_scale=2.0 ** 40,
+                      growth_interval=1000, defer_table_update=False)
+    p0 = tr.params.clone()
+    tr.train_step(o, d, t, gt)
+    torch.cuda.synchronize()
+    assert int(tr.step_dev) == 0 and float(tr.loss_scale) == 2.0 ** 39 and torch.equal(tr.params, p0)
+    assert float(tr.grads.abs().max()) == 0.0  # cleared for the next step either way
+    for _ in range(40):
+        tr.train_step(o, d, t, gt)
+    torch.cuda.synchronize()
+    assert int(tr.step_dev) >= 1 and float(tr.loss_scale) < 2.0 ** 30 and not torch.equal(tr.params, p0)
+    assert bool(torch.isfinite(tr.params).all())
+
+
 def test_fused_optimizer_tail_equals_five_kernel_tail_and_follows_lambda_lr(cuda_dev, monkeypatch):
     """The one-launch MLP tail (csrc/optim_tail.cu: overflow check -> Adam -> fp16 copies + tcgen05 tiles -> GradScaler.update ->
     lr_scheduler.step) against the round-1 sequence of five kernels on the SAME gradients and optimiser state: parameters, moments,
@@ -206,7 +227,7 @@ def test_fused_optimizer_tail_equals_five_kernel_tail_and_follows_lambda_lr(cuda
                 dst.copy_(src)
             tr.hw.refresh(tr.weight_views)
             tr.fused_tail = fused
-            if not fused:
+            if not fused or tr._wgrad_flags():  # (one GPU: the weight-gradient kernel raises the flag, the tail trusts it)
                 L.call("seald_grad_finite_check", tr.grads.data_ptr() + 4 * ntp, nw, L.ptr(tr.found_inf), L.stream())
             tr._optimizer()
             torch.cuda.synchronize()
