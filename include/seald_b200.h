@@ -291,6 +291,21 @@ int seald_field_umma_pack_deform(const void* const* weights, int n_layers, void*
 int seald_field_deform_forward_umma(const float* xyz, const float* time_dev, const void* packed, int n_layers, uint32_t M,
                                     const int32_t* m_dev, float bound, int t0_mode, float* deform, float* x01, void* in_buf,
                                     void* fwd_buf, seald_stream_t stream);
+/* NeRFNetwork.density (dnerf/network.py:171-208: deformation net -> hash grid -> sigma head) in ONE launch on tcgen05: the
+ * deformation kernel's tile pipeline continues past its last layer — the epilogue threads turn the deformed position into the
+ * 16 x 2 hash-grid features (gridencoder.cu:100-216) written straight into the A-operand tile, and the sigma head's layers are
+ * further tile-layers of the same chain; only xyz (12 B) in and sigma (4 B) out per sample touch HBM.  `packed_sigma`: the
+ * sigma weights as operand tiles (seald_field_umma_pack_sigma, seald_field_umma_sigma_bytes(n_sigma) bytes).  D = 3, C = 2,
+ * L = 16 only (SEALD_E_UNSUPPORTED otherwise).  sigma = density_scale * exp(h[0]); optional scatter for the occupancy refresh
+ * (dnerf/renderer.py:497-499): tmp[indices[i]] = sigma[i] * store_scale.  `sigma` or `tmp` may be NULL, not both. */
+uint64_t seald_field_umma_sigma_bytes(int n_sigma);
+int seald_field_umma_pack_sigma(const void* const* weights, int n_sigma, void* packed_sigma, seald_stream_t stream);
+int seald_field_density_umma(const float* xyz, const float* time_dev, const void* packed, int n_layers, const void* packed_sigma,
+                             int n_sigma, const void* table, const int32_t* offsets, uint32_t D, uint32_t C, uint32_t L, float S,
+                             uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp, uint32_t M, const int32_t* m_dev,
+                             float bound, int t0_mode, float density_scale, float* sigma, const int32_t* indices, float store_scale,
+                             float* tmp, seald_stream_t stream);
+
 /* Backward (dgrad chain) on tcgen05: the buffers of seald_field_deform_backward as tile images (fwd_buf as written by
  * seald_field_deform_forward_umma; bwd_buf [n_layers-1] x ceil128(M) x 128, gout_buf ceil128(M) x 16 halves); packedT = the transposed
  * weight tiles W_l^T of layers 1..n-1 (seald_field_umma_pack_deform_T, seald_field_umma_deform_bytes_T(n_layers) bytes). */

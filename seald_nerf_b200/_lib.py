@@ -50,6 +50,9 @@ _SIGS = {
     "seald_field_deform_forward": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "seald_field_umma_pack_deform": [_vp, _i32, _vp, _vp],
     "seald_field_deform_forward_umma": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "seald_field_umma_pack_sigma": [_vp, _i32, _vp, _vp],
+    "seald_field_density_umma": [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _u32, _vp, _f32, _i32,
+                                 _f32, _vp, _vp, _f32, _vp, _vp],
     "seald_field_umma_pack_deform_T": [_vp, _i32, _vp, _vp],
     "seald_field_umma_pack_deform_both": [_vp, _i32, _vp, _vp, _vp],
     "seald_field_deform_backward_umma": [_vp, _vp, _vp, _i32, _u32, _vp, _f32, _vp, _vp, _vp, _vp],
@@ -124,7 +127,8 @@ _lib = None
 
 def exported_symbols():
     """Every entry point include/seald_b200.h declares (used by the CPU-side ABI test)."""
-    return ["seald_version", "seald_sm_arch", "seald_strerror", "seald_field_umma_deform_bytes", "seald_field_umma_deform_bytes_T"] + list(_SIGS)
+    return ["seald_version", "seald_sm_arch", "seald_strerror", "seald_field_umma_deform_bytes", "seald_field_umma_deform_bytes_T",
+            "seald_field_umma_sigma_bytes"] + list(_SIGS)
 
 
 def load():
@@ -142,6 +146,8 @@ def load():
     lib.seald_strerror.argtypes = [C.c_int]
     lib.seald_field_umma_deform_bytes.restype = C.c_uint64
     lib.seald_field_umma_deform_bytes.argtypes = [C.c_int]
+    lib.seald_field_umma_sigma_bytes.restype = C.c_uint64
+    lib.seald_field_umma_sigma_bytes.argtypes = [C.c_int]
     lib.seald_field_umma_deform_bytes_T.restype = C.c_uint64
     lib.seald_field_umma_deform_bytes_T.argtypes = [C.c_int]
     for name, sig in _SIGS.items():

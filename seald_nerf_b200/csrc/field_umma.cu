@@ -30,6 +30,7 @@
 #include <cstdlib>
 
 #include "encoders.cuh"
+#include "grid_device.cuh"
 #include "umma.cuh"
 
 namespace seald {
@@ -52,7 +53,47 @@ struct UmmaSmem {
     static constexpr size_t W_OFF = G * kTileBytes;
     static constexpr size_t BAR_OFF = W_OFF + kUStages * kTileBytes;
     static constexpr size_t BYTES = BAR_OFF + 128;
+    static constexpr size_t LP_OFF = BYTES;                                    // density kernel: the 16 hash-grid level records
+    static constexpr size_t BYTES_DENS = LP_OFF + 16 * sizeof(LevelParams);
 };
+
+// ---- density query (k_deform_forward_umma<.., DENS = true>): the sigma head rides the same pipeline as extra tile-layers ----
+constexpr int kSK0 = 32;  // sigma head input: 16 levels x 2 features
+constexpr int kSW = 64;   // sigma head hidden width
+constexpr int kSNLast = 16;
+struct DensityArgs {
+    const __half* packed_sigma;  // sigma head weights as operand tiles (seald_field_umma_pack_sigma)
+    int n_sigma;
+    const __half* table;         // fp16 hash table (16-byte aligned)
+    const int* offsets;          // [17]
+    float S;
+    uint32_t H, gridtype, interp;
+    bool align_corners;
+    float density_scale;
+    float* sigma;                // [M] or null
+    const int* indices;          // optional scatter: tmp[indices[row]] = sigma * store_scale (occupancy refresh)
+    float store_scale;
+    float* tmp;
+};
+__host__ __device__ __forceinline__ uint32_t sigma_layer_bytes(const int s, const int n_sigma) {
+    return (uint32_t)((s == 0 ? kSK0 : kSW) * (s == n_sigma - 1 ? kSNLast : kSW) * 2);
+}
+__host__ __device__ __forceinline__ size_t sigma_layer_offset(const int s, const int n_sigma) {
+    size_t o = 0;
+    for (int i = 0; i < s; i++) o += sigma_layer_bytes(i, n_sigma);
+    return o;
+}
+// shape of tile-layer l of the chain deformation net (n_layers) -> sigma head (n_sigma)
+__device__ __forceinline__ void chain_shape(const int l, const int n_layers, const int n_sigma, int& K, int& N) {
+    if (l < n_layers) {
+        K = (l == 0) ? kUK0 : kUW;
+        N = (l == n_layers - 1) ? kUNLast : kUW;
+    } else {
+        const int sl = l - n_layers;
+        K = (sl == 0) ? kSK0 : kSW;
+        N = (sl == n_sigma - 1) ? kSNLast : kSW;
+    }
+}
 
 __host__ __device__ __forceinline__ uint32_t umma_layer_bytes(const int l, const int n_layers) {
     if (l == 0) return kUK0 * kUW * 2;
@@ -84,12 +125,25 @@ __device__ __forceinline__ void pack_umma_body(const PackJobs& jobs, __half* __r
 }
 __global__ void k_pack_umma(const PackJobs jobs, __half* __restrict__ packed) { pack_umma_body(jobs, packed, blockIdx.y); }
 
-template <bool SAVE, int G>
+// sigma head: layer s [N][K] row-major (ld = K) -> [K/8][N][8]
+__global__ void k_pack_umma_sigma(const PackJobs jobs, __half* __restrict__ packed) {
+    const int s_l = blockIdx.y, n_sigma = jobs.n_layers;
+    const int K = (s_l == 0) ? kSK0 : kSW, N = (s_l == n_sigma - 1) ? kSNLast : kSW;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K / 8 * N) return;
+    const int c = i / N, n = i - c * N;
+    const uint4 v = *reinterpret_cast<const uint4*>(jobs.src[s_l] + (size_t)n * K + c * 8);
+    __half* dst = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(packed) + sigma_layer_offset(s_l, n_sigma));
+    *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = v;
+}
+
+template <bool SAVE, int G, bool DENS>
 __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma(const float* __restrict__ xyz, const float* __restrict__ time,
                                                                       const __half* __restrict__ packed, const int n_layers, const int M,
                                                                       const int* __restrict__ m_dev, const float bound, const int t0_mode,
                                                                       float* __restrict__ deform, float* __restrict__ x01,
-                                                                      __half* __restrict__ in_buf, __half* __restrict__ fwd_buf) {
+                                                                      __half* __restrict__ in_buf, __half* __restrict__ fwd_buf,
+                                                                      const DensityArgs da) {
     extern __shared__ __align__(128) unsigned char smem[];
     using SM = UmmaSmem<G>;
     constexpr int ISSUE0 = G * 4 * SM::EW;  // warps ISSUE0 .. ISSUE0 + G - 1 issue the MMAs of group 0 .. G - 1
@@ -108,7 +162,16 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
     const int n_tiles = (m_used + kUW - 1) / kUW;
     const int n_pairs = (n_tiles + G - 1) / G;  // work units of G tiles
     const int my_pairs = (n_pairs > (int)blockIdx.x) ? (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int n_items = my_pairs * n_layers;
+    // DENS: the chain continues through the hash grid (gathered by the epilogue threads into the A tile) and the sigma head
+    const int n_chain = DENS ? n_layers + da.n_sigma : n_layers;
+    const int n_items = my_pairs * n_chain;
+    LevelParams* s_lp = reinterpret_cast<LevelParams*>(smem + SM::LP_OFF);
+    // (The groups of a CTA share the weight ring and therefore stay within two tile-layers of each other: they reach the gather
+    // together and the tensor pipe idles meanwhile — why this variant loses to the two-kernel query on big batches,
+    // profiles/r2_occupancy.md.  Staggering their start would dead-lock on the ring.)
+    if constexpr (DENS) {
+        if (tid < 16) s_lp[tid] = make_level(da.offsets, tid, da.S, da.H, 3, da.gridtype, da.align_corners);
+    }
 
     if (tid == 0) {
         for (int i = 0; i < 3; i++) { umma::mbar_init(bar_full + i, 1); umma::mbar_init(bar_wfree + i, G); }
@@ -125,12 +188,19 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
         // =============================== loader: weights of item i into stage i % 3, two items ahead of the MMAs ===============================
         if (lane == 0) {
             for (int i = 0; i < n_items; i++) {
-                const int l = i % n_layers, s = i % kUStages;
+                const int l = i % n_chain, s = i % kUStages;
                 if (i >= kUStages) umma::mbar_wait(bar_wfree + s, ((i / kUStages) - 1) & 1);  // every group is done with item i - 3
-                const uint32_t bytes = umma_layer_bytes(l, n_layers);
+                uint32_t bytes;
+                const unsigned char* src;
+                if (!DENS || l < n_layers) {
+                    bytes = umma_layer_bytes(l, n_layers);
+                    src = reinterpret_cast<const unsigned char*>(packed) + umma_layer_offset(l, n_layers);
+                } else {
+                    bytes = sigma_layer_bytes(l - n_layers, da.n_sigma);
+                    src = reinterpret_cast<const unsigned char*>(da.packed_sigma) + sigma_layer_offset(l - n_layers, da.n_sigma);
+                }
                 umma::mbar_arrive_expect_tx(bar_full + s, bytes);
-                umma::bulk_load(s_w + (size_t)s * kTileBytes, reinterpret_cast<const unsigned char*>(packed) + umma_layer_offset(l, n_layers), bytes,
-                                bar_full + s);
+                umma::bulk_load(s_w + (size_t)s * kTileBytes, src, bytes, bar_full + s);
             }
         }
     } else if (warp >= ISSUE0) {
@@ -140,10 +210,11 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
             const uint32_t a0 = umma::smem_addr(s_a) + g * kTileBytes, w_addr = umma::smem_addr(s_w);
             const uint32_t d = tmem_base + g * kUW;
             for (int i = 0; i < n_items; i++) {
-                const int l = i % n_layers, s = i % kUStages;
-                const bool last = (l == n_layers - 1);
-                const int ksteps = (l == 0 ? kUK0 : kUW) / 16;
-                const uint32_t n_rows = last ? kUNLast : kUW;
+                const int l = i % n_chain, s = i % kUStages;
+                int K_l, N_l;
+                chain_shape(l, n_layers, DENS ? da.n_sigma : 0, K_l, N_l);
+                const int ksteps = K_l / 16;
+                const uint32_t n_rows = (uint32_t)N_l;
                 const uint32_t idesc = umma::instr_desc_f16(128, n_rows);
                 const uint32_t w_lbo = n_rows * 16;
                 umma::mbar_wait(bar_full + s, (i / kUStages) & 1);
@@ -172,9 +243,9 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
         const size_t tiles_cap = (size_t)(M + kUW - 1) / kUW;  // tiles the saved-activation buffers hold per layer
         float px = 0.f, py = 0.f, pz = 0.f;
         for (int i = 0; i < n_items; i++) {
-            const int l = i % n_layers;
+            const int l = i % n_chain;
             if (l == 0) {
-                const int pair = (int)blockIdx.x + (i / n_layers) * (int)gridDim.x;
+                const int pair = (int)blockIdx.x + (i / n_chain) * (int)gridDim.x;
                 tile = G * pair + g;
                 row = tile * kUW + r;
                 save_tile = SAVE && tile < n_tiles;
@@ -243,6 +314,102 @@ __global__ void __launch_bounds__(UmmaSmem<G>::THREADS, 1) k_deform_forward_umma
                     }
                 }
                 umma::fence_before_sync();
+                umma::fence_proxy_async();
+                umma::mbar_arrive(bar_aready + g);
+            } else if (DENS && l >= n_layers) {
+                // ---- sigma head (NeRFNetwork.density, dnerf/network.py:196-208): hidden layers of 64, then [sigma, geo_feat]
+                if (l < n_chain - 1) {
+#pragma unroll 1
+                    for (int q = half * (2 / SM::EW); q < (half + 1) * (2 / SM::EW); q++) {
+                        uint32_t v[32];
+                        umma::tmem_ld32(t_lane + q * 32, v);
+                        umma::wait_ld();
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const float a = fmaxf(__uint_as_float(v[c4 * 8 + j * 2]), 0.0f);
+                                const float b = fmaxf(__uint_as_float(v[c4 * 8 + j * 2 + 1]), 0.0f);
+                                const __half2 h = __floats2half2_rn(a, b);
+                                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            *reinterpret_cast<uint4*>(a_tile + ((size_t)(q * 4 + c4) * kUW + r) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                    umma::fence_before_sync();
+                    umma::fence_proxy_async();
+                    umma::mbar_arrive(bar_aready + g);
+                } else if (half == 0) {
+                    uint32_t v[16];
+                    umma::tmem_ld16(t_lane, v);
+                    umma::wait_ld();
+                    umma::fence_before_sync();
+                    if (row < m_used) {
+                        const float sg = da.density_scale * expf(__half2float(__float2half_rn(__uint_as_float(v[0]))));
+                        if (da.sigma) da.sigma[row] = sg;
+                        if (da.tmp) da.tmp[da.indices[row]] = sg * da.store_scale;
+                    }
+                }
+            } else if (DENS) {
+                // ---- last deformation layer -> x01 -> hash-grid features (16 levels x 2, fp16) as the sigma head's A tile: this
+                // thread's row, levels [half * 16 / EW, (half + 1) * 16 / EW), two levels in flight (gridencoder.cu:100-216)
+                uint32_t v[16];
+                umma::tmem_ld16(t_lane, v);
+                umma::wait_ld();
+                umma::fence_before_sync();
+                float x[3];
+                bool live = row < m_used;
+                {
+                    const float xin[3] = {px, py, pz};
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const float dx = __half2float(__float2half_rn(__uint_as_float(v[d])));
+                        const float xp = t_is_zero ? xin[d] : xin[d] + dx;
+                        x[d] = (xp + bound) / (2 * bound);
+                        if (x[d] < 0 || x[d] > 1) live = false;  // outside [0,1]: zero features (gridencoder.cu:117-131)
+                    }
+                }
+                constexpr int LV = 16 / SM::EW;  // levels per thread
+                constexpr int GL = 2;
+#pragma unroll 1
+                for (int c8 = 0; c8 < LV / 4; c8++) {  // 4 levels = 8 halves = one 16-byte chunk of the A tile
+                    uint32_t w[4];
+#pragma unroll
+                    for (int pass = 0; pass < 4 / GL; pass++) {
+                        CellGather<__half, 3, 2> cg[GL];
+                        float pos[GL][3], deriv[GL][3];
+                        if (live) {
+#pragma unroll
+                            for (int gl = 0; gl < GL; gl++) {
+                                const LevelParams lp = s_lp[half * LV + c8 * 4 + pass * GL + gl];
+                                uint32_t pos_grid[3];
+                                locate<3>(x, lp, da.align_corners, da.interp, pos[gl], deriv[gl], pos_grid);
+                                cg[gl].issue(da.table, da.gridtype, da.align_corners, lp, pos_grid);
+                            }
+                        }
+#pragma unroll
+                        for (int gl = 0; gl < GL; gl++) {
+                            float res[2] = {0.f, 0.f};
+                            if (live) {
+                                float val[8][2];
+                                cg[gl].resolve(val);
+#pragma unroll
+                                for (uint32_t idx = 0; idx < 8; idx++) {
+                                    float wt = 1;
+#pragma unroll
+                                    for (uint32_t d = 0; d < 3; d++) wt *= ((idx >> d) & 1u) ? pos[gl][d] : 1 - pos[gl][d];
+                                    res[0] += wt * val[idx][0];
+                                    res[1] += wt * val[idx][1];
+                                }
+                            }
+                            __half hh[2];
+                            Row<__half, 2>::store(hh, res);
+                            w[pass * GL + gl] = *reinterpret_cast<const uint32_t*>(hh);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(a_tile + ((size_t)(half * (LV / 4) + c8) * kUW + r) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
                 umma::fence_proxy_async();
                 umma::mbar_arrive(bar_aready + g);
             } else if (half == 0) {
@@ -576,7 +743,7 @@ extern "C" int seald_field_deform_forward_umma(const float* xyz, const float* ti
         const uint32_t units = div_up(n_tiles, (uint32_t)G);
         const uint32_t grid = units < (uint32_t)SEALD_NUM_SMS ? units : (uint32_t)SEALD_NUM_SMS;
         kernel<<<grid, threads, smem, st>>>(xyz, time_dev, (const __half*)packed, n_layers, (int)M, m_dev, bound, t0_mode, deform, x01,
-                                            (__half*)in_buf, (__half*)fwd_buf);
+                                            (__half*)in_buf, (__half*)fwd_buf, DensityArgs{});
         return 0;
     };
     // enough tiles to give every SM four at a time: G = 4 (tensor pipe saturated); otherwise spread over more SMs with G = 2
@@ -584,12 +751,65 @@ extern "C" int seald_field_deform_forward_umma(const float* xyz, const float* ti
     const bool big = forced_g ? forced_g == 4 : n_tiles >= 4u * SEALD_NUM_SMS;
     int rc;
     if (fwd_buf) {
-        rc = big ? launch(k_deform_forward_umma<true, 4>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
-                 : launch(k_deform_forward_umma<true, 2>, 2, UmmaSmem<2>::BYTES, UmmaSmem<2>::THREADS);
+        rc = big ? launch(k_deform_forward_umma<true, 4, false>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
+                 : launch(k_deform_forward_umma<true, 2, false>, 2, UmmaSmem<2>::BYTES, UmmaSmem<2>::THREADS);
     } else {
-        rc = big ? launch(k_deform_forward_umma<false, 4>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
-                 : launch(k_deform_forward_umma<false, 2>, 2, UmmaSmem<2>::BYTES, UmmaSmem<2>::THREADS);
+        rc = big ? launch(k_deform_forward_umma<false, 4, false>, 4, UmmaSmem<4>::BYTES, UmmaSmem<4>::THREADS)
+                 : launch(k_deform_forward_umma<false, 2, false>, 2, UmmaSmem<2>::BYTES, UmmaSmem<2>::THREADS);
     }
+    if (rc) return rc;
+    return launch_status();
+}
+
+// ---- density query in ONE launch: deformation net -> hash grid -> sigma head, nothing but xyz in and sigma out touches HBM ----
+extern "C" uint64_t seald_field_umma_sigma_bytes(int n_sigma) {
+    if (n_sigma < 2) return 0;
+    return (uint64_t)sigma_layer_offset(n_sigma, n_sigma);
+}
+
+// weights: HOST array of device pointers to the fp16 staging copies of the sigma head (layer 0 [64][32], hidden [64][64], last [16][64])
+extern "C" int seald_field_umma_pack_sigma(const void* const* weights, int n_sigma, void* packed, seald_stream_t stream) {
+    if (!weights || !packed || n_sigma < 2 || n_sigma > 12) return SEALD_E_BADARG;
+    PackJobs jobs;
+    jobs.n_layers = n_sigma;
+    for (int l = 0; l < n_sigma; l++) {
+        if (!weights[l]) return SEALD_E_BADARG;
+        if ((uintptr_t)weights[l] & 15) return SEALD_E_ALIGN;
+        jobs.src[l] = reinterpret_cast<const __half*>(weights[l]);
+    }
+    k_pack_umma_sigma<<<dim3(div_up(kSW / 8 * kSW, 256), n_sigma), 256, 0, to_stream(stream)>>>(jobs, reinterpret_cast<__half*>(packed));
+    return launch_status();
+}
+
+extern "C" int seald_field_density_umma(const float* xyz, const float* time_dev, const void* packed, int n_layers, const void* packed_sigma,
+                                        int n_sigma, const void* table, const int32_t* offsets, uint32_t D, uint32_t C, uint32_t L, float S,
+                                        uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp, uint32_t M, const int32_t* m_dev,
+                                        float bound, int t0_mode, float density_scale, float* sigma, const int32_t* indices, float store_scale,
+                                        float* tmp, seald_stream_t stream) {
+    if (M == 0) return 0;
+    if (!xyz || !time_dev || !packed || !packed_sigma || !table || !offsets || n_layers < 2 || n_layers > 12 || n_sigma < 2 || n_sigma > 12)
+        return SEALD_E_BADARG;
+    if (!sigma && !tmp) return SEALD_E_BADARG;
+    if (tmp && !indices) return SEALD_E_BADARG;
+    if (D != 3 || C != 2 || L != 16 || gridtype > 1 || interp > 1) return SEALD_E_UNSUPPORTED;
+    if (((uintptr_t)packed & 15) || ((uintptr_t)packed_sigma & 15) || ((uintptr_t)table & 15)) return SEALD_E_ALIGN;
+    const uint32_t n_tiles = div_up(M, (uint32_t)kUW);
+    cudaStream_t st = to_stream(stream);
+    const DensityArgs da{(const __half*)packed_sigma, n_sigma, (const __half*)table, offsets, S, H, gridtype, interp, align_corners != 0,
+                         density_scale, sigma, indices, store_scale, tmp};
+    auto launch = [&](auto kernel, const int G, const size_t smem, const int threads) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        const uint32_t units = div_up(n_tiles, (uint32_t)G);
+        const uint32_t grid = units < (uint32_t)SEALD_NUM_SMS ? units : (uint32_t)SEALD_NUM_SMS;
+        kernel<<<grid, threads, smem, st>>>(xyz, time_dev, (const __half*)packed, n_layers, (int)M, m_dev, bound, t0_mode, nullptr, nullptr, nullptr,
+                                            nullptr, da);
+        return 0;
+    };
+    static const int forced_g = getenv("SEALD_UMMA_G") ? atoi(getenv("SEALD_UMMA_G")) : 0;  // measurement switch
+    const bool big = forced_g ? forced_g == 4 : n_tiles >= 4u * SEALD_NUM_SMS;
+    const int rc = big ? launch(k_deform_forward_umma<false, 4, true>, 4, UmmaSmem<4>::BYTES_DENS, UmmaSmem<4>::THREADS)
+                       : launch(k_deform_forward_umma<false, 2, true>, 2, UmmaSmem<2>::BYTES_DENS, UmmaSmem<2>::THREADS);
     if (rc) return rc;
     return launch_status();
 }

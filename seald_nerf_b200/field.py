@@ -64,6 +64,8 @@ class HalfWeights:
         self.packed_deform = torch.zeros(int(_lib.load().seald_field_umma_deform_bytes(cfg.n_deform)) // 2, dtype=torch.float16, device=device)
         self.packed_deform_T = torch.zeros(int(_lib.load().seald_field_umma_deform_bytes_T(cfg.n_deform)) // 2, dtype=torch.float16, device=device)
         self.pack_transposed = True  # the transposed tiles are only needed for training (deformation backward)
+        # the sigma head as operand tiles for the one-launch density query (seald_field_density_umma); packed on demand (pack_sigma)
+        self.packed_sigma = torch.zeros(max(int(_lib.load().seald_field_umma_sigma_bytes(cfg.n_sigma)) // 2, 8), dtype=torch.float16, device=device)
 
         n = len(self.views)
         self._dst = _lib.ptr_array(self.views)
@@ -84,6 +86,12 @@ class HalfWeights:
                       _lib.stream())
         else:
             _lib.call("seald_field_umma_pack_deform", self.p_deform, self.cfg.n_deform, ptr(self.packed_deform), _lib.stream())
+
+
+    def pack_sigma(self):
+        """Operand tiles of the sigma head from the current fp16 staging copies (one tiny launch; the optimiser tail keeps the staging
+        copies and the deformation tiles fresh, the sigma tiles are only needed by density queries)."""
+        _lib.call("seald_field_umma_pack_sigma", self.p_sigma, self.cfg.n_sigma, ptr(self.packed_sigma), _lib.stream())
 
 
 WGRAD_IMPL = os.environ.get("SEALD_WGRAD_IMPL", "umma")  # "umma": tcgen05 kernel (csrc/wgrad_umma.cu); "mma": mma.sync kernel (field.cu)
@@ -288,17 +296,48 @@ def field_backward(cfg, hw, ws, grad_sigma, grad_rgb, time_is_zero, table16, off
     mlp_wgrad(jobs, n_jobs, M, m_dev)
 
 
-def field_density(cfg, hw, ws, xyzs, time_dev, table16, offsets, M=None):
-    """Density-only query (NeRFNetwork.density, dnerf/network.py:171-208): deform -> grid -> sigma net."""
+# "split" (default): tcgen05 deformation kernel + encoder/sigma-head kernel.  "umma": sigma-only queries in ONE tcgen05 launch
+# (seald_field_density_umma) — measured SLOWER above ~64k points (profiles/r2_occupancy.md: the tile groups of a CTA share the weight
+# ring, so they run in lock step and all gather at the same time with the tensor pipe idle; 2^21 points 1.20-1.36 ms vs 0.97 ms),
+# faster below (32k points: 0.027 vs 0.033 ms); kept as an opt-in with its parity test.
+DENSITY_IMPL = os.environ.get("SEALD_DENSITY_IMPL", "split")
+
+
+def density_fused_ok(cfg):
+    return (DENSITY_IMPL == "umma" and DEFORM_IMPL == "umma" and cfg.grid_dim == 2 and cfg.grid_levels == 16 and cfg.n_sigma >= 2
+            and cfg.n_deform >= 2)
+
+
+def field_density(cfg, hw, ws, xyzs, time_dev, table16, offsets, M=None, sigma_packed=False, scatter=None, sigma_only=False):
+    """Density-only query (NeRFNetwork.density, dnerf/network.py:171-208): deform -> grid -> sigma net.  scatter = (indices int32 [M],
+    scale, tmp): also tmp[indices] = sigma * scale (occupancy refresh, dnerf/renderer.py:497-499).  sigma_only: the caller reads
+    nothing but ws.sigma / the scatter (no ws.deform, ws.x01): the one-launch kernel may serve it.  sigma_packed: hw.pack_sigma() was
+    called since the weights last changed."""
     M = ws.M if M is None else int(M)
     st = _lib.stream()
+    if sigma_only and density_fused_ok(cfg):
+        # ONE launch: the sigma head and the hash-grid gather ride the deformation kernel's tile pipeline (csrc/field_umma.cu, DENS)
+        if not sigma_packed:
+            hw.pack_sigma()
+        idx, scale, tmp = scatter if scatter is not None else (None, 1.0, None)
+        _lib.call("seald_field_density_umma", ptr(xyzs), ptr(time_dev), ptr(hw.packed_deform), cfg.n_deform, ptr(hw.packed_sigma), cfg.n_sigma,
+                  ptr(table16), ptr(offsets), 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners),
+                  cfg.interp, M, None, cfg.bound, 2, cfg.density_scale, ptr(ws.sigma), ptr(idx) if idx is not None else None, float(scale),
+                  ptr(tmp) if tmp is not None else None, st)
+        return
     deform_forward(cfg, hw, xyzs, time_dev, M, None, 2, ws.deform, ws.x01, None, None)
     # encoder inside the density head: one launch, no feature round trip (occupancy refresh: partial pass 61.8 -> 53.5 ms, full sweep equal)
     if FUSE_GRID_HEADS and cfg.grid_dim == 2 and cfg.grid_levels == 16:
         _lib.call("seald_field_grid_sigma_forward", ptr(ws.x01), ptr(table16), ptr(offsets), 3, cfg.grid_dim, cfg.grid_levels, cfg.grid_S,
                   cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, hw.p_sigma, cfg.n_sigma, M, cfg.density_scale, ptr(ws.sigma),
                   None, st)
+        if scatter is not None:
+            idx, scale, tmp = scatter
+            _lib.call("seald_occ_store", ptr(ws.sigma), ptr(idx), M, float(scale), ptr(tmp), st)
         return
     _lib.call("seald_grid_encode_forward", ptr(ws.x01), ptr(table16), ptr(offsets), ptr(ws.feat), None, M, 3, cfg.grid_dim, cfg.grid_levels,
               cfg.grid_S, cfg.grid_base, cfg.gridtype, int(cfg.align_corners), cfg.interp, F16, None, st)
     _lib.call("seald_field_sigma_forward", ptr(ws.feat), hw.p_sigma, cfg.n_sigma, M, cfg.density_scale, ptr(ws.sigma), None, st)
+    if scatter is not None:
+        idx, scale, tmp = scatter
+        _lib.call("seald_occ_store", ptr(ws.sigma), ptr(idx), M, float(scale), ptr(tmp), st)

@@ -4,7 +4,8 @@ Same schedule as the reference (full sweep of every cell of every time frame for
 H^3/4 re-sampled occupied cells per frame), same random-number consumption for the full sweep (so it is bit-identical to the
 torch-composed `NeRFRenderer.update_extra_state` of this package under the same seed), but per time frame it is
     1 kernel   jittered sample points + Morton indices          (csrc/occupancy.cu; the reference: ~10 torch kernels)
-    3 kernels  density query: tcgen05 deformation net -> hash grid -> sigma head, on buffers allocated ONCE for H^3 points
+    2 kernels  density query: tcgen05 deformation net -> hash grid + sigma head in one launch, on buffers allocated ONCE for H^3
+               points (the all-in-one tcgen05 launch seald_field_density_umma is slower at this size: field.DENSITY_IMPL)
     2 kernels  store into a per-frame temporary, decayed maximum (no 512 MiB temporaries, no boolean-mask passes)
 followed by ONE packbits launch over all time frames.  The partial pass draws the reference's random numbers in the reference's
 order (cells, ranks among the occupied cells, jitter), so it consumes the same generator stream and samples the SAME points; the
@@ -57,11 +58,11 @@ class FusedOccupancy:
         m, cfg = self.model, self.cfg
         saved, cfg.density_scale = cfg.density_scale, 1.0  # like NeRFNetwork.density: the renderer applies density_scale itself
         try:
-            F.field_density(cfg, hw, pp["ws"], pp["xyzs"], pp["time_dev"], table16, m.encoder.offsets, M=n)
+            F.field_density(cfg, hw, pp["ws"], pp["xyzs"], pp["time_dev"], table16, m.encoder.offsets, M=n, sigma_packed=True,
+                            scatter=(pp["indices"], float(m.density_scale), pp["tmp"]), sigma_only=True)
         finally:
             cfg.density_scale = saved
         st = _lib.stream()
-        _lib.call("seald_occ_store", ptr(pp["ws"].sigma), ptr(pp["indices"]), n, float(m.density_scale), ptr(pp["tmp"]), st)
         _lib.call("seald_occ_ema_max", ptr(m.density_grid[t, cas]), ptr(pp["tmp"]), self.n_full, self._decay, st)
 
     @torch.no_grad()
@@ -84,6 +85,8 @@ class FusedOccupancy:
                 # occupied-cell count of every frame in ONE host read (the reference synchronises per frame for `nonzero`, :509)
                 occ_counts = (m.density_grid > 0).sum(-1).cpu()
             per = m.time_size // self.world_size
+            if F.density_fused_ok(self.cfg):
+                hw.pack_sigma()  # operand tiles of the sigma head for the one-launch density query
             main = torch.cuda.current_stream()
             for pp in self.pipes:
                 pp["stream"].wait_stream(main)

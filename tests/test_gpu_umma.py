@@ -225,3 +225,42 @@ def test_umma_wgrad_raises_the_overflow_flag(cuda_dev):
         if scale > 0:  # (the poisoned element was random before: only that layer's gradient differs slightly)
             assert float((a - b).abs().max()) <= 5e-2 * scale
     assert not all(bool(torch.isfinite(x).all()) for x in res[1][1])
+
+
+@pytest.mark.parametrize("M,tval", [(1000, 0.37), (128 * 3 + 5, 0.0), (76000, 0.81), (200000, 0.37), (700001, 0.5)])
+def test_one_launch_density_matches_three_kernel_density(cuda_dev, M, tval):
+    """seald_field_density_umma (deformation net -> hash-grid gather -> sigma head inside ONE tcgen05 tile pipeline) against the
+    deformation kernel + fused grid/sigma kernel on the same inputs: same fp16 operands, fp32 accumulation in a different ORDER in the
+    sigma head (tcgen05 vs mma.sync), so log-densities agree to fp16 rounding flips of the hidden activations; the occupancy scatter
+    writes exactly sigma * scale.  Both tile-group configurations (G = 2 below 592 tiles, G = 4 above), points outside the grid,
+    t == 0 (no deformation)."""
+    from seald_nerf_b200 import _lib
+    F, cfg, hw, xyz = _setup(cuda_dev, M, seed=5)
+    from seald_nerf_b200.dnerf.network import NeRFNetwork
+    torch.manual_seed(5)
+    net = NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True).to(cuda_dev)
+    table16 = (net.encoder.embeddings.detach() * 3e4).to(torch.float16)  # features of order 1: densities that vary over the batch
+    xyz = xyz * 1.25  # some points leave [-bound, bound]: zero features
+    ws = F.FieldWorkspace(cfg, M, cuda_dev, training=False)
+    td = torch.tensor([tval], device=cuda_dev)
+    old = F.DENSITY_IMPL
+    res = {}
+    try:
+        for impl in ("split", "umma"):
+            F.DENSITY_IMPL = impl
+            ws.sigma.fill_(-7.0)
+            idx = torch.randperm(M, device=cuda_dev).to(torch.int32)
+            tmp = torch.full((M,), -1.0, device=cuda_dev)
+            F.field_density(cfg, hw, ws, xyz, td, table16, net.encoder.offsets, scatter=(idx, 0.5, tmp), sigma_only=True)
+            torch.cuda.synchronize()
+            assert torch.equal(tmp[idx.long()], ws.sigma * 0.5)
+            res[impl] = ws.sigma.clone()
+    finally:
+        F.DENSITY_IMPL = old
+    a, b = res["split"], res["umma"]
+    assert bool(torch.isfinite(b).all()) and float(b.min()) > 0
+    la, lb = a.log(), b.log()
+    assert float(la.std()) > 0.05, "the test field must vary"
+    d = (la - lb).abs()
+    assert float(d.max()) <= 0.03 and float(d.mean()) <= 1e-3, (float(d.max()), float(d.mean()))
+    assert float((d <= 2e-3).float().mean()) > 0.98
