@@ -109,7 +109,7 @@ def test_fused_composite_loss_kernel_equals_three_kernels(cuda_dev):
     for a, b in zip(res[0][4:6], res[1][4:6]):  # gradients: same zero pattern (early stops), values to fp32 round-off (FMA contraction)
         assert torch.equal(a == 0, b == 0)
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-9)
-    assert abs(res[0][6] - res[1][6]) <= 1e-6 * abs(res[0][6]) + 1e-9
+    assert abs(res[0][6] - res[1][6]) <= 5e-6 * abs(res[0][6]) + 1e-9  # (fp32 atomic sum over the rays: order-dependent round-off)
     assert float((res[0][4] == 0).float().mean()) > 0.2  # many samples lie behind an early stop
     scale = float(res[0][7].abs().max())
     assert float((res[0][7] - res[1][7]).abs().max()) <= 1e-4 * scale  # (atomic order in the scatter)
