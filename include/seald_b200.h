@@ -243,6 +243,24 @@ int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays
                           float* xyzs, float* dirs, float* deltas, const float* noises, const int32_t* n_alive_dev,
                           const int32_t* n_step_dev, const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6,
                           seald_stream_t stream);
+
+/* SAMPLE-PACKED inference round (csrc/raymarch.cu k_march_round_pack / k_composite_round_pack; same per-ray numbers as
+ * march_rays / composite_rays, raymarching.cu:701-914, different buffer contract).  A round's samples are stored back to back instead of
+ * n_step rows per ray (22% of an 800x800 frame's rows are empty terminator slots otherwise): ray_rows[n] = {first row, count} of alive
+ * entry n (count -1: the round's buffers were full, the ray was not marched and survives), state[6] = rows written this round = the live
+ * count for the field kernels (must be 0 on entry; seald_composite_rays_pack clears it; it exceeds cap_rows in a round that deferred rays:
+ * the field kernels clamp to their buffer).  state[0..5] as seald_composite_rays_compact.
+ * n_alive / n_step are launch bounds (cap_rows >= 128 * n_step).  mapper: optional fused Seal proxy mapping (mask [cap]). */
+int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                          const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                          const uint8_t* bitfield, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                          int32_t* state, uint32_t cap_rows, int32_t* ray_rows /* [n_alive, 2] */,
+                          float* stage /* scratch, 3 floats per (alive entry, step): >= 3 * max over rounds of n_alive * n_step */,
+                          const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6, seald_stream_t stream);
+int seald_composite_rays_pack(uint32_t n_alive, float T_thresh, const int32_t* rays_alive, float* rays_t, const float* sigmas,
+                              const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
+                              int32_t* next_alive, int32_t* state, int32_t* counters2, const int32_t* ray_rows, uint32_t budget,
+                              uint32_t max_steps, uint32_t max_n_step, uint32_t cap_rows, seald_stream_t stream);
 int seald_march_rays_train_seal(const float* rays_o, const float* rays_d, const uint8_t* bitfield, float bound,
                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                 const float* nears, const float* fars, const float* aabb6, float min_near,

@@ -209,10 +209,17 @@ struct Probe {
     int nx, ny, nz;
 };
 
+// the sample position at parameter t (raymarching.cu:360-362); ONE definition so that every kernel rounds it the same way
+__device__ __forceinline__ void ray_point(const float ox, const float oy, const float oz, const float dx, const float dy, const float dz,
+                                          const float bound, const float t, float& x, float& y, float& z) {
+    x = clampf(ox + t * dx, -bound, bound);
+    y = clampf(oy + t * dy, -bound, bound);
+    z = clampf(oz + t * dz, -bound, bound);
+}
+
 __device__ __forceinline__ bool probe_grid(const Ray& r, const MarchConst& mc, const uint8_t* __restrict__ grid, const float t, Probe& p) {
-    const float x = clampf(r.ox + t * r.dx, -mc.bound, mc.bound);
-    const float y = clampf(r.oy + t * r.dy, -mc.bound, mc.bound);
-    const float z = clampf(r.oz + t * r.dz, -mc.bound, mc.bound);
+    float x, y, z;
+    ray_point(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, mc.bound, t, x, y, z);
 
     const float dt = clampf(t * mc.dt_gamma, mc.dt_min, mc.dt_max);
 
@@ -1568,6 +1575,201 @@ __global__ void __launch_bounds__(kRoundThreads) k_composite_round(
 }
 
 // ------------------------------------------------------------------------------------------------
+// SAMPLE-PACKED round (FusedRenderer's loop; the drop-in ops above keep the reference's n_step-rows-per-ray contract).
+//
+// With n_step rows reserved per live ray, 22% of the rows a frame hands to the field are empty (round 0: 640 000 rows for 98 774
+// samples; rays that leave the occupied region mid-round).  Here a round's samples are stored back to back:
+//
+//   k_march_round_pack      thread per ray walks the bitfield and parks (t, dt, dt_ray) of its samples in a global scratch slot (12 B
+//                           per sample, L2 resident; shared memory for 128 x 32 slots would cut the march to 16 warps per SM: measured
+//                           +1.3 ms per frame); the CTA's sample count is scanned, ONE compare-and-swap reserves that many rows of the round's
+//                           buffers (state[6] = rows so far = the live count the field kernels read), and the rows are written by a
+//                           thread-per-row loop: coalesced stores, positions recomputed from t with the march's own expression
+//                           (ray_point), the Seal proxy mapping applied there.  ray_rows[n] = (first row, count) of alive entry n.
+//                           A CTA that no longer fits the buffers writes nothing and marks its rays deferred (count -1): they
+//                           survive the round untouched - so n_step may be chosen optimistically (round 0).
+//   k_composite_round_pack  the front-to-back recurrence over the ray's rows; survivors (n_step samples, still transparent, or
+//                           deferred) appended to the next alive list; the last CTA derives the next round's schedule and clears
+//                           the row counter.
+// Every number a ray produces is the reference's: how its samples are cut into rounds and where they sit does not enter.
+// ------------------------------------------------------------------------------------------------
+template <bool SEAL>
+__global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
+    uint32_t n_alive, const uint32_t n_step_bound, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps,
+    const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ fars, float* __restrict__ xyzs,
+    float* __restrict__ dirs, float* __restrict__ deltas, const float* __restrict__ noises, const int* __restrict__ n_alive_dev,
+    const int* __restrict__ n_step_dev, const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask,
+    const float* __restrict__ occ, int* __restrict__ row_counter, const uint32_t cap, int2* __restrict__ ray_rows,
+    float* __restrict__ stage) {
+    // stage: [n_alive * n_step][3] = t of the sample, dt, t_after - t_of_previous (slot (n, s) of alive entry n)
+    __shared__ uint32_t s_off[kRoundThreads + 1];
+    __shared__ uint32_t s_wsum[kRoundThreads / 32];
+    __shared__ int s_base;
+    n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
+    const uint32_t n_step = min((uint32_t)max(*n_step_dev, 0), n_step_bound);
+    const uint32_t first = blockIdx.x * blockDim.x;
+    if (first >= n_alive || n_step == 0) return;
+    const uint32_t n_rays = min((uint32_t)blockDim.x, n_alive - first);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t count = 0;
+    if (tid < n_rays) {
+        const uint32_t n = first + tid;
+        const int index = rays_alive[n];
+        const float noise = noises ? noises[n] : 0.0f;
+        Ray r;
+        const float* o = rays_o + (size_t)index * 3;
+        const float* d = rays_d + (size_t)index * 3;
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+        r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+        const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+        float t = rays_t[index];
+        float far = fars[index];
+        t += clampf(t * dt_gamma, mc.dt_min, mc.dt_max) * noise;
+        float last_t = t;
+        if (occ && !clip_to_occupied(r, occ, t, far)) far = t;
+        float* slot = stage + (size_t)n * n_step * 3;
+        Probe p;
+        while (t < far && count < n_step) {
+            if (probe_grid(r, mc, grid, t, p)) {
+                slot[count * 3] = t;
+                t += p.dt;
+                slot[count * 3 + 1] = p.dt;
+                slot[count * 3 + 2] = t - last_t;
+                last_t = t;
+                count++;
+            } else {
+                t = skip_voxel(r, mc, p, t);
+            }
+        }
+    }
+    // ---- exclusive scan of the counts over the CTA, one reservation
+    const uint32_t incl = warp_inclusive_scan(count, lane);
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kRoundThreads / 32; w++) before += (w < warp) ? s_wsum[w] : 0u;
+    s_off[tid] = before + incl - count;
+    if (tid == kRoundThreads - 1) {
+        const uint32_t total = before + incl;
+        s_off[kRoundThreads] = total;
+        // ONE atomicAdd (a compare-and-swap loop convoys: every success makes all other CTAs retry, ~0.4 us per CTA, serialised).
+        // A reservation that passes `cap` is not rolled back: every later one starts beyond cap and fails too, so the written rows
+        // stay contiguous from 0; the counter then overshoots (the field clamps its live count to the buffer, seald_composite_rays_pack
+        // clears it) and the rows between the last success and cap hold stale samples nobody composites.
+        int base = 0;
+        if (total) {
+            base = atomicAdd(row_counter, (int)total);
+            if ((uint32_t)base + total > cap) base = -1;
+        }
+        s_base = base;
+    }
+    __syncthreads();
+    const int base = s_base;
+    if (tid < n_rays) ray_rows[first + tid] = (base < 0) ? make_int2(0, -1) : make_int2(base + (int)s_off[tid], (int)count);
+    if (base < 0) return;
+    // ---- the CTA's rows, one thread per row (consecutive threads -> consecutive rows)
+    const uint32_t total = s_off[kRoundThreads];
+    for (uint32_t i = tid; i < total; i += blockDim.x) {
+        uint32_t lo = 0, hi = kRoundThreads;  // last ray whose first row is <= i (rays without samples share their successor's offset)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= i) lo = mid; else hi = mid;
+        }
+        const uint32_t sidx = i - s_off[lo];
+        const float* slot = stage + ((size_t)(first + lo) * n_step + sidx) * 3;
+        const int index = rays_alive[first + lo];
+        const float* o = rays_o + (size_t)index * 3;
+        const float* d = rays_d + (size_t)index * 3;
+        float sdx = d[0], sdy = d[1], sdz = d[2], sx, sy, sz;
+        ray_point(o[0], o[1], o[2], sdx, sdy, sdz, bound, slot[0], sx, sy, sz);
+        const size_t row = (size_t)base + i;
+        if (SEAL) seal_mask[row] = seal_map_sample(mp, sx, sy, sz, sdx, sdy, sdz) ? 1 : 0;
+        xyzs[row * 3] = sx; xyzs[row * 3 + 1] = sy; xyzs[row * 3 + 2] = sz;
+        dirs[row * 3] = sdx; dirs[row * 3 + 1] = sdy; dirs[row * 3 + 2] = sdz;
+        *reinterpret_cast<float2*>(deltas + row * 2) = make_float2(slot[1], slot[2]);
+    }
+}
+
+__global__ void __launch_bounds__(kRoundThreads) k_composite_round_pack(
+    uint32_t n_alive, const float T_thresh, const int* __restrict__ rays_alive, float* __restrict__ rays_t, const float* __restrict__ sigmas,
+    const float* __restrict__ rgbs, const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ depth,
+    float* __restrict__ image, int* __restrict__ next_alive, int* __restrict__ state, int* __restrict__ counters,
+    const int2* __restrict__ ray_rows, const uint32_t budget, const uint32_t max_steps, const uint32_t max_n_step, const uint32_t cap) {
+    n_alive = min(n_alive, (uint32_t)max(state[0], 0));
+    const int n_step = max(state[1], 0);
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    bool survive = false;
+    int index = -1;
+    if (n < n_alive && n_step > 0) {
+        index = rays_alive[n];
+        const int2 rr = ray_rows[n];
+        if (rr.y < 0) {
+            survive = true;  // deferred: the round's buffers were full, nothing marched
+        } else {
+            const float* sg = sigmas + rr.x;
+            const float* cl = rgbs + (size_t)rr.x * 3;
+            const float* dl = deltas + (size_t)rr.x * 2;
+            float t = rays_t[index];
+            float ws = weights_sum[index], d = depth[index];
+            float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
+            int step = 0;
+            for (; step < rr.y; step++) {
+                const float2 dd = *reinterpret_cast<const float2*>(dl + step * 2);
+                const float alpha = 1.0f - __expf(-sg[step] * dd.x);
+                const float T = 1 - ws;
+                const float weight = alpha * T;
+                ws += weight;
+                t += dd.y;
+                d += weight * t;
+                r += weight * cl[step * 3];
+                g += weight * cl[step * 3 + 1];
+                b += weight * cl[step * 3 + 2];
+                if (T < T_thresh) break;  // (tested on the transmittance BEFORE this sample, raymarching.cu:880-886)
+            }
+            survive = (step == n_step);   // a full round of samples and still transparent; fewer samples = the ray ended
+            if (survive) rays_t[index] = t;
+            weights_sum[index] = ws;
+            depth[index] = d;
+            image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+        }
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, survive);
+    if (bal) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(bal) - 1)) base = (uint32_t)atomicAdd(counters, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        if (survive) next_alive[base + __popc(bal & ((1u << lane) - 1u))] = index;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(counters + 1, 1) + 1;
+        if (done == (int)gridDim.x) {
+            __threadfence();
+            int n_new = atomicAdd(counters, 0);
+            const int step = state[3] + state[1];
+            state[4] += min(state[6], (int)cap);        // rows the field evaluated this round
+            state[5] += (state[0] > 0) ? 1 : 0;
+            if ((uint32_t)step >= max_steps) n_new = 0;
+            int ns = 1;
+            if (n_new > 0) ns = max(min((int)(budget / (uint32_t)n_new), (int)max_n_step), 1);
+            state[0] = n_new;
+            state[1] = ns;
+            state[2] = n_new * ns;
+            state[3] = step;
+            state[6] = 0;
+            counters[0] = 0;
+            counters[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // order-preserving compaction of the alive list: three tiny kernels (count per tile, scan of tile totals,
 // scatter).  Tiles of 1024 entries.
 // ------------------------------------------------------------------------------------------------
@@ -1885,6 +2087,45 @@ extern "C" int seald_composite_rays_compact(uint32_t n_alive, uint32_t n_step, f
     k_composite_round<true><<<div_up(n_alive, kRoundThreads), kRoundThreads, smem, to_stream(stream)>>>(
         n_alive, n_step, T_thresh, const_cast<int32_t*>(rays_alive), rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, state, state + 1,
         next_alive, state, counters2, budget, max_steps, max_n_step, smem_rows);
+    return launch_status();
+}
+
+// sample-packed round (k_march_round_pack / k_composite_round_pack).  state: int32[8] device = {n_alive, n_step, n_alive * n_step,
+// steps marched, rows evaluated so far, non-empty rounds, ROWS OF THIS ROUND (the field kernels' live count; zero on entry), -};
+// n_alive / n_step arguments are launch bounds.  mapper may be NULL (then mask is ignored).
+extern "C" int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                                     const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                                     const uint8_t* bitfield, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                                     int32_t* state, uint32_t cap_rows, int32_t* ray_rows, float* stage, const seald_seal_mapper* mapper,
+                                     uint8_t* mask, const float* occ_aabb6, seald_stream_t stream) {
+    if (n_alive == 0 || n_step == 0) return 0;
+    if (!rays_alive || !rays_t || !rays_o || !rays_d || !bitfield || !fars || !xyzs || !dirs || !deltas || !state || !ray_rows || !stage)
+        return SEALD_E_BADARG;
+    if (C == 0 || H == 0 || max_steps == 0 || cap_rows < kRoundThreads * n_step) return SEALD_E_BADARG;
+    if (mapper) {
+        if (int rc = check_fusable_mapper(mapper, mask)) return rc;
+    }
+    static const seald_seal_mapper no_mapper = {};
+    const seald_seal_mapper& mp = mapper ? *mapper : no_mapper;
+    auto k = mapper ? k_march_round_pack<true> : k_march_round_pack<false>;
+    k<<<div_up(n_alive, kRoundThreads), kRoundThreads, 0, to_stream(stream)>>>(
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, bitfield, fars, xyzs, dirs, deltas, noises, state,
+        state + 1, mp, mask, occ_aabb6, state + 6, cap_rows, reinterpret_cast<int2*>(ray_rows), stage);
+    return launch_status();
+}
+
+extern "C" int seald_composite_rays_pack(uint32_t n_alive, float T_thresh, const int32_t* rays_alive, float* rays_t, const float* sigmas,
+                                         const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
+                                         int32_t* next_alive, int32_t* state, int32_t* counters2, const int32_t* ray_rows, uint32_t budget,
+                                         uint32_t max_steps, uint32_t max_n_step, uint32_t cap_rows, seald_stream_t stream) {
+    if (n_alive == 0) return 0;
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image || !next_alive || !state || !counters2 ||
+        !ray_rows)
+        return SEALD_E_BADARG;
+    if (budget == 0 || max_n_step == 0 || rays_alive == next_alive) return SEALD_E_BADARG;
+    k_composite_round_pack<<<div_up(n_alive, kRoundThreads), kRoundThreads, 0, to_stream(stream)>>>(
+        n_alive, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, next_alive, state, counters2,
+        reinterpret_cast<const int2*>(ray_rows), budget, max_steps, max_n_step, cap_rows);
     return launch_status();
 }
 

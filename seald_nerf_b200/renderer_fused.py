@@ -54,6 +54,12 @@ class FusedRenderer:
             if os.environ.get("SEALD_RENDER_MAX_NSTEP"):
                 max_n_step = int(os.environ["SEALD_RENDER_MAX_NSTEP"])
         self.max_n_step = int(max_n_step)
+        # Sample-packed rounds (csrc/raymarch.cu k_march_round_pack): a round's samples are stored back to back, so the field never
+        # sees the empty terminator rows of the n_step-rows-per-ray layout (22% of a frame's rows) and round 0 may march several
+        # samples per ray although only `slots` rows exist (a CTA that does not fit defers its rays to the next round).
+        # SEALD_RENDER_PACK=0: the reference's layout (measurement switch).
+        self.pack = os.environ.get("SEALD_RENDER_PACK", "1") != "0"
+        self.n_step0 = max(1, min(int(os.environ.get("SEALD_RENDER_NSTEP0", "4")), self.max_n_step))
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
@@ -68,8 +74,11 @@ class FusedRenderer:
         self.rays_t = torch.empty(N, **f32)
         self.noises = torch.zeros(N, **f32)
         self.alive = [torch.empty(N, **i32), torch.empty(N, **i32)]
+        self.ray_rows = torch.zeros(N, 2, **i32)  # packed rounds: {first row, count} of every alive-list entry
+        # packed rounds: (t, dt, dt_ray) of every marched sample before its row is known; n_alive * n_step <= slots, round 0: N * n_step0
+        self.stage = torch.empty(3 * max(self.slots, N * self.n_step0) + 16, **f32) if self.pack else None
         # device-side loop state {n_alive, n_step, n_alive * n_step, steps done} and the compaction's output count
-        self.state = torch.zeros(8, **i32)  # + [4] live samples evaluated so far, [5] non-empty rounds so far
+        self.state = torch.zeros(8, **i32)  # + [4] live samples evaluated so far, [5] non-empty rounds so far, [6] rows of this round (packed)
         self.counters = torch.zeros(2, **i32)  # survivors appended so far / CTAs finished (seald_composite_rays_compact; left zero)
         self.n_new = torch.zeros(1, **i32)
         self.scratch = torch.empty((N + 1023) // 1024 + 1, **i32)
@@ -111,6 +120,26 @@ class FusedRenderer:
         n_bound = N  # launch bound; kernels stop at *n_alive_dev
         noises = self.noises if (first and opts["perturb"]) else None
         launches = 0
+        if self.pack:
+            m_dev = self.state[6:7]  # rows the march really wrote
+            fused_map = mapper is not None and mapper.fusable
+            _lib.call("seald_march_rays_pack", n_bound, self.max_n_step, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d),
+                      float(m.bound), opts["dt_gamma"], opts["max_steps"], int(m.cascade), int(m.grid_size), ptr(self.bitfield), ptr(self.fars),
+                      ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(noises), ptr(self.state), self.cap, ptr(self.ray_rows),
+                      ptr(self.stage), C.byref(desc) if fused_map else None, ptr(self.mask) if fused_map else None, ptr(self.occ), st)
+            if mapper is not None and not fused_map:  # anchor mapper: batch-wide early exit, separate op
+                _lib.call("seald_seal_map_to_origin", C.byref(desc), ptr(self.xyzs), ptr(self.dirs), self.cap, ptr(m_dev), ptr(self.xyzs),
+                          ptr(self.dirs), ptr(self.mask), ptr(mapper._dev_cache["scratch_i"]), st)
+                launches += 3
+            F.field_forward(cfg, self.hw, self.ws, self.xyzs, self.dirs, self.time, self.table16, m.encoder.offsets, m_dev, 1, M=self.cap)
+            if mapper is not None and mapper.has_color_map:
+                _lib.call("seald_seal_map_color", C.byref(mapper._dev_cache["color"]), ptr(self.xyzs), ptr(self.mask), ptr(self.ws.rgb), self.cap,
+                          ptr(m_dev), ptr(mapper._dev_cache["scratch_f"]), st)
+                launches += 4
+            _lib.call("seald_composite_rays_pack", n_bound, opts["T_thresh"], ptr(alive), ptr(self.rays_t), ptr(self.ws.sigma), ptr(self.ws.rgb),
+                      ptr(self.deltas), ptr(self.weights_sum), ptr(self.depth), ptr(self.image), ptr(nxt), ptr(self.state), ptr(self.counters),
+                      ptr(self.ray_rows), max(N, self.slots), opts["max_steps"], self.max_n_step, self.cap, st)
+            return launches + 5
         if mapper is not None and mapper.fusable:
             _lib.call("seald_march_rays_seal", n_bound, self.max_n_step, ptr(alive), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d), float(m.bound),
                       opts["dt_gamma"], opts["max_steps"], int(m.cascade), int(m.grid_size), ptr(self.bitfield), ptr(self.nears),
@@ -204,6 +233,8 @@ class FusedRenderer:
             self.noises[:N].uniform_(0, 1)
         budget = max(N, self.slots)
         n_step0 = max(min(budget // N, self.max_n_step), 1)
+        if self.pack:
+            n_step0 = max(n_step0, self.n_step0)  # optimistic: most rays of a frame miss the occupied region and write nothing
         self.h_state.zero_()
         self.h_state[0] = N; self.h_state[1] = n_step0; self.h_state[2] = N * n_step0
         self.state.copy_(self.h_state, non_blocking=True)

@@ -103,3 +103,33 @@ def test_one_pass_small_batch_render_matches_round_loop(cuda_dev, kind):
     ref_fb = small.render(ro, rd, time, T_thresh=1e-4)
     assert small.iterations > 1
     torch.testing.assert_close(out_fb["image"], ref_fb["image"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["plain", "bbox"])
+def test_sample_packed_rounds_equal_fixed_stride_rounds(cuda_dev, kind, monkeypatch):
+    """The sample-packed round (samples of a round stored back to back, k_march_round_pack / k_composite_round_pack) against the
+    reference's n_step-rows-per-ray layout: every ray composites the SAME sample sequence, so image / depth / weights are
+    bit-identical whatever the first round's n_step — including n_step0 = 32 on a buffer of `rays` rows, where most CTAs of round 0 do
+    not fit and their rays are deferred — while the field evaluates fewer rows."""
+    from seald_nerf_b200.renderer_fused import FusedRenderer
+    net = _model(cuda_dev, seald=(kind != "plain"))
+    if kind != "plain":
+        from oracle import seal as S
+        net.init_mapper(mapper=seal_mapper_from_dict(S.make_bbox_mapper(center=(0.0, 0.1, 0.0), half=(0.2, 0.25, 0.2), translate=(0.08, 0.0, 0.03),
+                                                                         rot_deg=30.0, hsv=(0.1, 0.0, 0.0))))
+    ro, rd = camera_rays(70000, seed=5, center_crop=400)
+    ro, rd = torch.from_numpy(ro).to(cuda_dev), torch.from_numpy(rd).to(cuda_dev)
+    monkeypatch.setenv("SEALD_RENDER_PACK", "0")
+    fr0 = FusedRenderer(net, max_rays=70000)
+    ref = fr0.render(ro, rd, 0.4)
+    assert not fr0.pack and fr0.samples > 70000
+    monkeypatch.setenv("SEALD_RENDER_PACK", "1")
+    for n0 in (1, 4, 32):
+        monkeypatch.setenv("SEALD_RENDER_NSTEP0", str(n0))
+        fr = FusedRenderer(net, max_rays=70000)
+        assert fr.pack and fr.n_step0 == n0
+        for rep in range(2):  # second call: the captured double-round graph is reused
+            out = fr.render(ro, rd, 0.4)
+            for k in ("image", "depth", "weights_sum"):
+                assert torch.equal(out[k], ref[k]), (kind, n0, k, float((out[k] - ref[k]).abs().max()))
+        assert fr.samples < fr0.samples, (fr.samples, fr0.samples)
