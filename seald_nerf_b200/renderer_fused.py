@@ -42,7 +42,16 @@ class FusedRenderer:
         # cut into rounds.
         # (measurement switches: SEALD_RENDER_SLOTS_MULT scales the slot budget of full frames, SEALD_RENDER_MAX_NSTEP caps n_step)
         import os
-        mult = float(os.environ.get("SEALD_RENDER_SLOTS_MULT", "1"))
+        # Sample-packed rounds (csrc/raymarch.cu k_march_round_pack): a round's samples are stored back to back, so the field never
+        # sees the empty terminator rows of the n_step-rows-per-ray layout (22% of a frame's rows) and round 0 may march several
+        # samples per ray although only `slots` rows exist (a CTA that does not fit defers its rays to the next round).
+        # SEALD_RENDER_PACK=0: the reference's layout (measurement switch).
+        self.pack = os.environ.get("SEALD_RENDER_PACK", "1") != "0"
+        # Row budget of a round.  Fixed-stride layout: N (larger budgets cost more in empty rows than they save in rounds, measured).
+        # Packed: 2 N — rows are real samples, so a larger budget only costs the samples a ray evaluates past its termination inside
+        # its last round (none in the synthetic benchmark scene, where 1x / 1.5x / 2x / 3x give 3.55 / 3.49 / 3.37 / 3.33 ms per
+        # frame in 10 / 8 / 6 / 5 rounds; a trained scene with opaque surfaces pays up to n_step - 1 samples per terminated ray).
+        mult = float(os.environ.get("SEALD_RENDER_SLOTS_MULT", "2" if self.pack else "1"))
         self.slots = max(int(self.N * mult), int(min_samples))
         self.cap = self.slots + 128  # rounded up to the MLP tile
         self.use_graph = bool(use_graph)
@@ -54,11 +63,6 @@ class FusedRenderer:
             if os.environ.get("SEALD_RENDER_MAX_NSTEP"):
                 max_n_step = int(os.environ["SEALD_RENDER_MAX_NSTEP"])
         self.max_n_step = int(max_n_step)
-        # Sample-packed rounds (csrc/raymarch.cu k_march_round_pack): a round's samples are stored back to back, so the field never
-        # sees the empty terminator rows of the n_step-rows-per-ray layout (22% of a frame's rows) and round 0 may march several
-        # samples per ray although only `slots` rows exist (a CTA that does not fit defers its rays to the next round).
-        # SEALD_RENDER_PACK=0: the reference's layout (measurement switch).
-        self.pack = os.environ.get("SEALD_RENDER_PACK", "1") != "0"
         self.n_step0 = max(1, min(int(os.environ.get("SEALD_RENDER_NSTEP0", "4")), self.max_n_step))
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
