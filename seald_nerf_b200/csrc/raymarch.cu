@@ -1371,6 +1371,8 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_train_loss_fused(
 
 // ------------------------------------------------------------------------------------------------
 // inference round (run_cuda eval branch, dnerf/renderer.py:349-376): march n_step samples per live ray, [field], composite.
+// (These two kernels keep the reference's buffer contract for the drop-in ops; FusedRenderer's loop runs the SAMPLE-PACKED pair
+// further down, k_march_round_pack / k_composite_round_pack.)
 //
 // The contract of the sample buffers is the reference's (row n * n_step + s belongs to the n-th entry of the alive list; unused
 // slots are zero, delta == 0 being the "ray ended" marker, raymarching.cu:850), and so is every number a ray produces; the kernels
