@@ -249,7 +249,7 @@ int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays
  * n_step rows per ray (22% of an 800x800 frame's rows are empty terminator slots otherwise): ray_rows[n] = {first row, count} of alive
  * entry n (count -1: the round's buffers were full, the ray was not marched and survives), state[6] = rows written this round = the live
  * count for the field kernels (must be 0 on entry; seald_composite_rays_pack clears it; it exceeds cap_rows in a round that deferred rays:
- * the field kernels clamp to their buffer).  state[0..5] as seald_composite_rays_compact.
+ * the field kernels clamp to their buffer); state[7] = rays deferred this round (0 on entry), state[2] = rays deferred so far.  state[0..5] as seald_composite_rays_compact.
  * n_alive / n_step are launch bounds (cap_rows >= 128 * n_step).  mapper: optional fused Seal proxy mapping (mask [cap]). */
 int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                           const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,

@@ -1664,7 +1664,10 @@ __global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
         int base = 0;
         if (total) {
             base = atomicAdd(row_counter, (int)total);
-            if ((uint32_t)base + total > cap) base = -1;
+            if ((uint32_t)base + total > cap) {
+                base = -1;
+                atomicAdd(row_counter + 1, (int)n_rays);  // state[7]: rays deferred this round
+            }
         }
         s_base = base;
     }
@@ -1753,7 +1756,9 @@ __global__ void __launch_bounds__(kRoundThreads) k_composite_round_pack(
         if (done == (int)gridDim.x) {
             __threadfence();
             int n_new = atomicAdd(counters, 0);
-            const int step = state[3] + state[1];
+            // (a round that deferred rays does not count towards max_steps: those rays did not move)
+            const int deferred = state[7];
+            const int step = state[3] + (deferred ? 0 : state[1]);
             state[4] += min(state[6], (int)cap);        // rows the field evaluated this round
             state[5] += (state[0] > 0) ? 1 : 0;
             if ((uint32_t)step >= max_steps) n_new = 0;
@@ -1761,9 +1766,10 @@ __global__ void __launch_bounds__(kRoundThreads) k_composite_round_pack(
             if (n_new > 0) ns = max(min((int)(budget / (uint32_t)n_new), (int)max_n_step), 1);
             state[0] = n_new;
             state[1] = ns;
-            state[2] = n_new * ns;
+            state[2] += deferred;                       // rays deferred so far (statistics)
             state[3] = step;
             state[6] = 0;
+            state[7] = 0;
             counters[0] = 0;
             counters[1] = 0;
             __threadfence();
@@ -2092,8 +2098,9 @@ extern "C" int seald_composite_rays_compact(uint32_t n_alive, uint32_t n_step, f
     return launch_status();
 }
 
-// sample-packed round (k_march_round_pack / k_composite_round_pack).  state: int32[8] device = {n_alive, n_step, n_alive * n_step,
-// steps marched, rows evaluated so far, non-empty rounds, ROWS OF THIS ROUND (the field kernels' live count; zero on entry), -};
+// sample-packed round (k_march_round_pack / k_composite_round_pack).  state: int32[8] device = {n_alive, n_step, rays deferred so
+// far, steps marched, rows evaluated so far, non-empty rounds, ROWS OF THIS ROUND (the field kernels' live count; zero on entry),
+// rays deferred this round (zero on entry)};
 // n_alive / n_step arguments are launch bounds.  mapper may be NULL (then mask is ignored).
 extern "C" int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                                      const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,

@@ -105,6 +105,7 @@ class FusedRenderer:
         self.iterations = 0
         self.samples = 0
         self.launches = 0
+        self.deferred = 0
 
     def refresh_weights(self):
         """Re-stage the fp16 copies of the model's parameters (call after the model was trained / loaded)."""
@@ -240,7 +241,7 @@ class FusedRenderer:
         if self.pack:
             n_step0 = max(n_step0, self.n_step0)  # optimistic: most rays of a frame miss the occupied region and write nothing
         self.h_state.zero_()
-        self.h_state[0] = N; self.h_state[1] = n_step0; self.h_state[2] = N * n_step0
+        self.h_state[0] = N; self.h_state[1] = n_step0; self.h_state[2] = 0 if self.pack else N * n_step0
         self.state.copy_(self.h_state, non_blocking=True)
         desc = mapper.descriptor(self.device) if mapper is not None else None
 
@@ -269,6 +270,7 @@ class FusedRenderer:
         self.h_state.copy_(self.state, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self.iterations, self.samples, self.launches = int(self.h_state[5]), int(self.h_state[4]), launches
+        self.deferred = int(self.h_state[2]) if self.pack else 0  # rays a packed round could not fit and marched one round later
         image = image + (1 - ws_out).unsqueeze(-1) * bg_color
         depth_out = torch.clamp(depth - nears, min=0) / (fars - nears) if normalize_depth else depth.clone()
         return {"image": image.view(*prefix, 3), "depth": depth_out.view(*prefix), "weights_sum": ws_out.clone()}

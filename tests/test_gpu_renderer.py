@@ -133,3 +133,11 @@ def test_sample_packed_rounds_equal_fixed_stride_rounds(cuda_dev, kind, monkeypa
             for k in ("image", "depth", "weights_sum"):
                 assert torch.equal(out[k], ref[k]), (kind, n0, k, float((out[k] - ref[k]).abs().max()))
         assert fr.samples < fr0.samples, (fr.samples, fr0.samples)
+    # a row budget far below what round 0 asks for: most CTAs of the first rounds are deferred, the image does not change
+    monkeypatch.setenv("SEALD_RENDER_NSTEP0", "32")
+    monkeypatch.setenv("SEALD_RENDER_SLOTS_MULT", "0.25")
+    fr = FusedRenderer(net, max_rays=70000, min_samples=1 << 12)
+    out = fr.render(ro, rd, 0.4)
+    assert fr.deferred > 0, "the budget was meant to overflow"
+    for k in ("image", "depth", "weights_sum"):
+        assert torch.equal(out[k], ref[k]), (kind, "deferred", k)
