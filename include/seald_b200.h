@@ -257,6 +257,13 @@ int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const int32_t* rays
                           int32_t* state, uint32_t cap_rows, int32_t* ray_rows /* [n_alive, 2] */,
                           float* stage /* scratch, 3 floats per (alive entry, step): >= 3 * max over rounds of n_alive * n_step */,
                           const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6, seald_stream_t stream);
+/* frame prologue of the packed loop in one launch: near_far_from_aabb (raymarching.cu:108-144) for all N rays, rays_t = near, zeroed
+ * weights_sum / depth / image, `alive` = the rays whose [near, far] meets the occupied region (any order; the others keep weights_sum 0
+ * = background, as if marched), state[0..7] = {n_alive, n_step = clamp(budget / n_alive, n_step_min, max_n_step), 0, ...}. */
+int seald_render_init_pack(const float* rays_o, const float* rays_d, const float* aabb6, const float* occ_aabb6, uint32_t N,
+                           float min_near, float* nears, float* fars, float* rays_t, float* weights_sum, float* depth, float* image,
+                           int32_t* alive, int32_t* state, int32_t* counters2, uint32_t budget, uint32_t n_step_min,
+                           uint32_t max_n_step, seald_stream_t stream);
 int seald_composite_rays_pack(uint32_t n_alive, float T_thresh, const int32_t* rays_alive, float* rays_t, const float* sigmas,
                               const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
                               int32_t* next_alive, int32_t* state, int32_t* counters2, const int32_t* ray_rows, uint32_t budget,

@@ -37,6 +37,7 @@ _SIGS = {
     "seald_composite_rays": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "seald_march_rays_pack": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp,
                               _vp, _vp, _vp, _vp],
+    "seald_render_init_pack": [_vp, _vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
     "seald_composite_rays_pack": [_u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _vp],
     "seald_composite_rays_compact": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
     "seald_render_schedule": [_vp, _vp, _u32, _u32, _u32, _vp],

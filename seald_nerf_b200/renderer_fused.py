@@ -229,23 +229,27 @@ class FusedRenderer:
                   ptr(self.occ), st)
         aabb = m.aabb_train if m.training else m.aabb_infer
         nears, fars = self.nears[:N], self.fars[:N]
-        _lib.call("seald_near_far_from_aabb", ptr(self.rays_o), ptr(self.rays_d), ptr(aabb), N, float(m.min_near), ptr(nears), ptr(fars), st)
-        self.rays_t[:N].copy_(nears)
         ws_out, depth, image = self.weights_sum[:N], self.depth[:N], self.image[:N]
-        ws_out.zero_(); depth.zero_(); image.zero_()
-        torch.arange(N, dtype=torch.int32, device=self.device, out=self.alive[0][:N])
         if perturb:
             self.noises[:N].uniform_(0, 1)
         budget = max(N, self.slots)
-        n_step0 = max(min(budget // N, self.max_n_step), 1)
         if self.pack:
-            n_step0 = max(n_step0, self.n_step0)  # optimistic: most rays of a frame miss the occupied region and write nothing
-        self.h_state.zero_()
-        self.h_state[0] = N; self.h_state[1] = n_step0; self.h_state[2] = 0 if self.pack else N * n_step0
-        self.state.copy_(self.h_state, non_blocking=True)
+            # one launch: near / far, rays_t, zeroed outputs, alive list of the rays that can meet an occupied cell, round-0 schedule
+            _lib.call("seald_render_init_pack", ptr(self.rays_o), ptr(self.rays_d), ptr(aabb), ptr(self.occ), N, float(m.min_near), ptr(nears),
+                      ptr(fars), ptr(self.rays_t), ptr(ws_out), ptr(depth), ptr(image), ptr(self.alive[0]), ptr(self.state), ptr(self.counters),
+                      budget, self.n_step0, self.max_n_step, st)
+        else:
+            _lib.call("seald_near_far_from_aabb", ptr(self.rays_o), ptr(self.rays_d), ptr(aabb), N, float(m.min_near), ptr(nears), ptr(fars), st)
+            self.rays_t[:N].copy_(nears)
+            ws_out.zero_(); depth.zero_(); image.zero_()
+            torch.arange(N, dtype=torch.int32, device=self.device, out=self.alive[0][:N])
+            n_step0 = max(min(budget // N, self.max_n_step), 1)
+            self.h_state.zero_()
+            self.h_state[0] = N; self.h_state[1] = n_step0; self.h_state[2] = N * n_step0
+            self.state.copy_(self.h_state, non_blocking=True)
         desc = mapper.descriptor(self.device) if mapper is not None else None
 
-        launches = 12 + self._round(N, 0, True, opts, mapper, desc)  # round 0 (perturbed start, alive 0 -> 1)
+        launches = (7 if self.pack else 12) + self._round(N, 0, True, opts, mapper, desc)  # round 0 (perturbed start, alive 0 -> 1)
         rounds = 1
         graph = self._double_round_graph(N, opts, mapper, desc) if self.use_graph else None
         k = 0
