@@ -256,7 +256,11 @@ int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const int32_t* rays
                           const uint8_t* bitfield, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
                           int32_t* state, uint32_t cap_rows, int32_t* ray_rows /* [n_alive, 2] */,
                           float* stage /* scratch, 3 floats per (alive entry, step): >= 3 * max over rounds of n_alive * n_step */,
-                          const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6, seald_stream_t stream);
+                          const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6,
+                          const uint32_t* coarse_bits /* optional (C == 1, H <= 128): seald_occupancy_coarse_bits — empty 8^3 blocks are
+                                                         left in one step; the samples are the same chain elements */,
+                          seald_stream_t stream);
+int seald_occupancy_coarse_bits(const uint8_t* bitfield, uint32_t H, uint32_t* coarse_bits /* (H/8)^3 / 32 words */, seald_stream_t stream);
 /* frame prologue of the packed loop in one launch: near_far_from_aabb (raymarching.cu:108-144) for all N rays, rays_t = near, zeroed
  * weights_sum / depth / image, `alive` = the rays whose [near, far] meets the occupied region (any order; the others keep weights_sum 0
  * = background, as if marched), state[0..7] = {n_alive, n_step = clamp(budget / n_alive, n_step_min, max_n_step), 0, ...}. */

@@ -1595,6 +1595,22 @@ __global__ void __launch_bounds__(kRoundThreads) k_composite_round(
 //                           the row counter.
 // Every number a ray produces is the reference's: how its samples are cut into rounds and where they sit does not enter.
 // ------------------------------------------------------------------------------------------------
+// one bit per 8^3 block of cells: the Morton order makes a block 512 consecutive cells = 64 consecutive bytes of the bitfield
+__global__ void k_coarse_bits(const uint8_t* __restrict__ bitfield, const uint32_t n_blocks, uint32_t* __restrict__ coarse) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool any = false;
+    if (j < n_blocks) {
+        const uint4* p = reinterpret_cast<const uint4*>(bitfield + (size_t)j * 64);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 v = p[i];
+            any = any || (v.x | v.y | v.z | v.w) != 0u;
+        }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31u) == 0 && j < n_blocks) coarse[j >> 5] = bal;
+}
+
 template <bool SEAL>
 __global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
     uint32_t n_alive, const uint32_t n_step_bound, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
@@ -1603,9 +1619,13 @@ __global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
     float* __restrict__ dirs, float* __restrict__ deltas, const float* __restrict__ noises, const int* __restrict__ n_alive_dev,
     const int* __restrict__ n_step_dev, const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask,
     const float* __restrict__ occ, int* __restrict__ row_counter, const uint32_t cap, int2* __restrict__ ray_rows,
-    float* __restrict__ stage) {
+    float* __restrict__ stage, const uint32_t* __restrict__ coarse) {
     // stage: [n_alive * n_step][3] = t of the sample, dt, t_after - t_of_previous (slot (n, s) of alive entry n)
+    // coarse (optional, C == 1, H <= 128): one bit per 8^3 cells of the bitfield (k_coarse_bits).  The samples of a ray are the chain
+    // elements t_k whose cell is occupied, however the walk gets from one to the next — so an empty 8^3 block may be left in one
+    // step (same adds, 1/8 of the probes) exactly like the reference leaves an empty cell.
     __shared__ uint32_t s_off[kRoundThreads + 1];
+    __shared__ uint32_t s_coarse[128];
     __shared__ uint32_t s_wsum[kRoundThreads / 32];
     __shared__ int s_base;
     n_alive = min(n_alive, (uint32_t)max(*n_alive_dev, 0));
@@ -1614,6 +1634,11 @@ __global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
     if (first >= n_alive || n_step == 0) return;
     const uint32_t n_rays = min((uint32_t)blockDim.x, n_alive - first);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (coarse) {
+        const uint32_t n_words = (H / 8) * (H / 8) * (H / 8) / 32;
+        for (uint32_t i = tid; i < n_words; i += blockDim.x) s_coarse[i] = coarse[i];
+        __syncthreads();
+    }
     uint32_t count = 0;
     if (tid < n_rays) {
         const uint32_t n = first + tid;
@@ -1634,6 +1659,27 @@ __global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
         float* slot = stage + (size_t)n * n_step * 3;
         Probe p;
         while (t < far && count < n_step) {
+            if (coarse) {
+                // the cell of probe_grid (cascade level 0: C == 1), then its 8^3 block
+                float x, y, z;
+                ray_point(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, mc.bound, t, x, y, z);
+                const float mip_bound = fminf(1.0f, mc.bound), mip_rbound = 1 / mip_bound;
+                const int nx = clampf(0.5 * (x * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+                const int ny = clampf(0.5 * (y * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+                const int nz = clampf(0.5 * (z * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+                const uint32_t ci = morton3D_enc(nx >> 3, ny >> 3, nz >> 3);
+                if (!((s_coarse[ci >> 5] >> (ci & 31u)) & 1u)) {
+                    const float rHc = 8.0f * mc.rH;
+                    const float tx = ((((nx >> 3) + 0.5f + 0.5f * signf(r.dx)) * rHc * 2 - 1) * mip_bound - x) * r.rdx;
+                    const float ty = ((((ny >> 3) + 0.5f + 0.5f * signf(r.dy)) * rHc * 2 - 1) * mip_bound - y) * r.rdy;
+                    const float tz = ((((nz >> 3) + 0.5f + 0.5f * signf(r.dz)) * rHc * 2 - 1) * mip_bound - z) * r.rdz;
+                    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+                    do {
+                        t += clampf(t * mc.dt_gamma, mc.dt_min, mc.dt_max);
+                    } while (t < tt);
+                    continue;
+                }
+            }
             if (probe_grid(r, mc, grid, t, p)) {
                 slot[count * 3] = t;
                 t += p.dt;
@@ -2165,11 +2211,12 @@ extern "C" int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const in
                                      const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                                      const uint8_t* bitfield, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
                                      int32_t* state, uint32_t cap_rows, int32_t* ray_rows, float* stage, const seald_seal_mapper* mapper,
-                                     uint8_t* mask, const float* occ_aabb6, seald_stream_t stream) {
+                                     uint8_t* mask, const float* occ_aabb6, const uint32_t* coarse_bits, seald_stream_t stream) {
     if (n_alive == 0 || n_step == 0) return 0;
     if (!rays_alive || !rays_t || !rays_o || !rays_d || !bitfield || !fars || !xyzs || !dirs || !deltas || !state || !ray_rows || !stage)
         return SEALD_E_BADARG;
     if (C == 0 || H == 0 || max_steps == 0 || cap_rows < kRoundThreads * n_step) return SEALD_E_BADARG;
+    if (coarse_bits && (C != 1 || H % 32 != 0 || H > 128)) return SEALD_E_UNSUPPORTED;
     if (mapper) {
         if (int rc = check_fusable_mapper(mapper, mask)) return rc;
     }
@@ -2178,7 +2225,7 @@ extern "C" int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const in
     auto k = mapper ? k_march_round_pack<true> : k_march_round_pack<false>;
     k<<<div_up(n_alive, kRoundThreads), kRoundThreads, 0, to_stream(stream)>>>(
         n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, bitfield, fars, xyzs, dirs, deltas, noises, state,
-        state + 1, mp, mask, occ_aabb6, state + 6, cap_rows, reinterpret_cast<int2*>(ray_rows), stage);
+        state + 1, mp, mask, occ_aabb6, state + 6, cap_rows, reinterpret_cast<int2*>(ray_rows), stage, coarse_bits);
     return launch_status();
 }
 
@@ -2195,6 +2242,16 @@ extern "C" int seald_render_init_pack(const float* rays_o, const float* rays_d, 
     if (budget == 0 || n_step_min == 0 || max_n_step < n_step_min) return SEALD_E_BADARG;
     k_render_init<<<div_up(N, 256u), 256, 0, to_stream(stream)>>>(rays_o, rays_d, aabb6, occ_aabb6, N, min_near, nears, fars, rays_t, weights_sum,
                                                                   depth, image, alive, state, counters2, budget, n_step_min, max_n_step);
+    return launch_status();
+}
+
+// coarse occupancy of one cascade level for seald_march_rays_pack: bit j of coarse_bits = any cell of the j-th 8^3 block (Morton order)
+// occupied.  H % 32 == 0; bitfield 16-byte aligned; coarse_bits: (H / 8)^3 / 32 words.
+extern "C" int seald_occupancy_coarse_bits(const uint8_t* bitfield, uint32_t H, uint32_t* coarse_bits, seald_stream_t stream) {
+    if (!bitfield || !coarse_bits || H == 0 || H % 32 != 0) return SEALD_E_BADARG;
+    if ((uintptr_t)bitfield % 16) return SEALD_E_ALIGN;
+    const uint32_t n_blocks = (H / 8) * (H / 8) * (H / 8);
+    k_coarse_bits<<<div_up(n_blocks, 256u), 256, 0, to_stream(stream)>>>(bitfield, n_blocks, coarse_bits);
     return launch_status();
 }
 

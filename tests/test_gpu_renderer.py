@@ -133,6 +133,15 @@ def test_sample_packed_rounds_equal_fixed_stride_rounds(cuda_dev, kind, monkeypa
             for k in ("image", "depth", "weights_sum"):
                 assert torch.equal(out[k], ref[k]), (kind, n0, k, float((out[k] - ref[k]).abs().max()))
         assert fr.samples < fr0.samples, (fr.samples, fr0.samples)
+    # opt-in coarse skipping (one bit per 8^3 block of cells): the same chain elements are sampled
+    monkeypatch.setenv("SEALD_RENDER_COARSE", "1")
+    monkeypatch.setenv("SEALD_RENDER_NSTEP0", "4")
+    fr = FusedRenderer(net, max_rays=70000)
+    assert fr.coarse is not None
+    out = fr.render(ro, rd, 0.4)
+    for k in ("image", "depth", "weights_sum"):
+        assert torch.equal(out[k], ref[k]), (kind, "coarse", k)
+    monkeypatch.setenv("SEALD_RENDER_COARSE", "0")
     # a row budget far below what round 0 asks for: most CTAs of the first rounds are deferred, the image does not change
     monkeypatch.setenv("SEALD_RENDER_NSTEP0", "32")
     monkeypatch.setenv("SEALD_RENDER_SLOTS_MULT", "0.25")
