@@ -253,7 +253,8 @@ int seald_march_rays_seal(uint32_t n_alive, uint32_t n_step, const int32_t* rays
  * n_alive / n_step are launch bounds (cap_rows >= 128 * n_step).  mapper: optional fused Seal proxy mapping (mask [cap]). */
 int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                           const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
-                          const uint8_t* bitfield, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                          const uint8_t* bitfield, const float* fars, float* xyzs, float* dirs, float* deltas,
+                          float* noises /* optional, per RAY: applied at a ray's first real march, then cleared — pass it every round */,
                           int32_t* state, uint32_t cap_rows, int32_t* ray_rows /* [n_alive, 2] */,
                           float* stage /* scratch, 3 floats per (alive entry, step): >= 3 * max over rounds of n_alive * n_step */,
                           const seald_seal_mapper* mapper, uint8_t* mask, const float* occ_aabb6,

@@ -1616,7 +1616,7 @@ __global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
     uint32_t n_alive, const uint32_t n_step_bound, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps,
     const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ fars, float* __restrict__ xyzs,
-    float* __restrict__ dirs, float* __restrict__ deltas, const float* __restrict__ noises, const int* __restrict__ n_alive_dev,
+    float* __restrict__ dirs, float* __restrict__ deltas, float* __restrict__ noises, const int* __restrict__ n_alive_dev,
     const int* __restrict__ n_step_dev, const __grid_constant__ seald_seal_mapper mp, uint8_t* __restrict__ seal_mask,
     const float* __restrict__ occ, int* __restrict__ row_counter, const uint32_t cap, int2* __restrict__ ray_rows,
     float* __restrict__ stage, const uint32_t* __restrict__ coarse) {
@@ -1640,10 +1640,14 @@ __global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
         __syncthreads();
     }
     uint32_t count = 0;
+    int my_index = -1;
     if (tid < n_rays) {
         const uint32_t n = first + tid;
         const int index = rays_alive[n];
-        const float noise = noises ? noises[index] : 0.0f;  // (per RAY: the first alive list need not be the identity, k_render_init)
+        my_index = index;
+        // perturbed start (raymarching.cu:741): per RAY (the first alive list is not the identity, k_render_init) and applied the first
+        // time the ray is really marched — the entry is cleared below unless this CTA is deferred, later rounds add an exact 0
+        const float noise = noises ? noises[index] : 0.0f;
         Ray r;
         const float* o = rays_o + (size_t)index * 3;
         const float* d = rays_d + (size_t)index * 3;
@@ -1721,6 +1725,7 @@ __global__ void __launch_bounds__(kRoundThreads) k_march_round_pack(
     const int base = s_base;
     if (tid < n_rays) ray_rows[first + tid] = (base < 0) ? make_int2(0, -1) : make_int2(base + (int)s_off[tid], (int)count);
     if (base < 0) return;
+    if (noises && my_index >= 0) noises[my_index] = 0.0f;
     // ---- the CTA's rows, one thread per row (consecutive threads -> consecutive rows)
     const uint32_t total = s_off[kRoundThreads];
     for (uint32_t i = tid; i < total; i += blockDim.x) {
@@ -2209,7 +2214,7 @@ extern "C" int seald_composite_rays_compact(uint32_t n_alive, uint32_t n_step, f
 // n_alive / n_step arguments are launch bounds.  mapper may be NULL (then mask is ignored).
 extern "C" int seald_march_rays_pack(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                                      const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
-                                     const uint8_t* bitfield, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                                     const uint8_t* bitfield, const float* fars, float* xyzs, float* dirs, float* deltas, float* noises,
                                      int32_t* state, uint32_t cap_rows, int32_t* ray_rows, float* stage, const seald_seal_mapper* mapper,
                                      uint8_t* mask, const float* occ_aabb6, const uint32_t* coarse_bits, seald_stream_t stream) {
     if (n_alive == 0 || n_step == 0) return 0;

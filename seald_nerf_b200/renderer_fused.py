@@ -129,7 +129,8 @@ class FusedRenderer:
         alive, nxt = self.alive[cur], self.alive[1 - cur]
         n_alive_dev, n_step_dev, m_dev = self.state[0:1], self.state[1:2], self.state[2:3]
         n_bound = N  # launch bound; kernels stop at *n_alive_dev
-        noises = self.noises if (first and opts["perturb"]) else None
+        # fixed stride: round 0 perturbs; packed: every round gets the buffer (a deferred ray is perturbed when it is first marched)
+        noises = self.noises if (opts["perturb"] and (first or self.pack)) else None
         launches = 0
         if self.pack:
             m_dev = self.state[6:7]  # rows the march really wrote

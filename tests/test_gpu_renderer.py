@@ -133,6 +133,19 @@ def test_sample_packed_rounds_equal_fixed_stride_rounds(cuda_dev, kind, monkeypa
             for k in ("image", "depth", "weights_sum"):
                 assert torch.equal(out[k], ref[k]), (kind, n0, k, float((out[k] - ref[k]).abs().max()))
         assert fr.samples < fr0.samples, (fr.samples, fr0.samples)
+    # perturbed start (noise per RAY, same generator state).  A perturbed eval render depends on how a ray's samples are cut into rounds
+    # in the reference too (composite_rays advances rays_t by the deltas from the UNPERTURBED start, so every round restarts the
+    # perturbation offset earlier, raymarching.cu:741,868): the two schedules agree to that offset's effect, not bit for bit
+    monkeypatch.setenv("SEALD_RENDER_NSTEP0", "4")
+    torch.manual_seed(77)
+    ref_p = fr0.render(ro, rd, 0.4, perturb=True)
+    fr = FusedRenderer(net, max_rays=70000)
+    torch.manual_seed(77)
+    out_p = fr.render(ro, rd, 0.4, perturb=True)
+    assert not torch.equal(ref_p["image"], ref["image"])
+    assert int((fr.noises[:70000] != 0).sum()) < 70000  # consumed (cleared) for every ray that was marched
+    torch.testing.assert_close(out_p["image"], ref_p["image"], rtol=0, atol=2e-2)
+    torch.testing.assert_close(out_p["weights_sum"], ref_p["weights_sum"], rtol=0, atol=4e-2)
     # opt-in coarse skipping (one bit per 8^3 block of cells): the same chain elements are sampled
     monkeypatch.setenv("SEALD_RENDER_COARSE", "1")
     monkeypatch.setenv("SEALD_RENDER_NSTEP0", "4")
