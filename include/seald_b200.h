@@ -269,6 +269,12 @@ int seald_render_init_pack(const float* rays_o, const float* rays_d, const float
                            float min_near, float* nears, float* fars, float* rays_t, float* weights_sum, float* depth, float* image,
                            int32_t* alive, int32_t* state, int32_t* counters2, uint32_t budget, uint32_t n_step_min,
                            uint32_t max_n_step, seald_stream_t stream);
+/* frame epilogue of run_cuda (dnerf/renderer.py:378-384) in one launch: image = acc + (1 - weights_sum) * bg (scalar background),
+ * depth = clamp(depth - near, 0) / (far - near) when normalize_depth (else raw, SealDNeRF/renderer.py:284), weights_sum copied; any of
+ * the outputs may be NULL; out_packed5: rows {r, g, b, depth, weights_sum} (all-gather input of the tile-sharded frame). */
+int seald_render_finish(const float* image, const float* weights_sum, const float* depth, const float* nears, const float* fars,
+                        uint32_t N, float bg, int normalize_depth, float* out_image, float* out_depth, float* out_ws,
+                        float* out_packed5, seald_stream_t stream);
 int seald_composite_rays_pack(uint32_t n_alive, float T_thresh, const int32_t* rays_alive, float* rays_t, const float* sigmas,
                               const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
                               int32_t* next_alive, int32_t* state, int32_t* counters2, const int32_t* ray_rows, uint32_t budget,

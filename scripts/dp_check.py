@@ -129,6 +129,20 @@ for name, (t16, ws, loss, steps, master) in results.items():
     if rank == 0:
         print("%-18s table16 mean rel diff %.2e  fp32 master %.2e  weights %.2e  loss %.5f (single %.5f)  steps %d/%d  fp16==half(master) %s  %s"
               % (name, dt, dm, dw, loss, ref_loss, steps, ref_steps, consistent, "OK" if good else "MISMATCH"), flush=True)
+# ---- 4. tile-sharded 800x800 frame == the frame one GPU renders alone (rays are independent: bit for bit), on every rank --------------
+from seald_nerf_b200 import microbench  # noqa: E402
+from seald_nerf_b200.renderer_fused import FusedRenderer  # noqa: E402
+model = microbench.build_scene(dev)
+model.eval()
+fro, frd = microbench.frame_rays(dev)
+alone = FusedRenderer(model, max_rays=fro.shape[0]).render(fro, frd, 0.5, T_thresh=1e-2)
+from seald_nerf_b200 import parallel  # noqa: E402
+fr = FusedRenderer(model, max_rays=parallel.shard_tiles(fro.shape[0], world, rank).shape[0])
+for rep in range(2):  # (second call: cached shard index / gather buffers)
+    sh = fr.render_sharded(fro, frd, 0.5, rank, world, T_thresh=1e-2)
+frame_ok = all(torch.equal(sh[k].reshape(-1), alone[k].reshape(-1)) for k in ("image", "depth", "weights_sum"))
+ok &= frame_ok
+print("rank %d sharded frame == single-GPU frame: %s (coverage %.4f)" % (rank, "OK" if frame_ok else "MISMATCH", float(sh["weights_sum"].mean())), flush=True)
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 dist.destroy_process_group()

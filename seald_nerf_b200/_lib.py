@@ -39,6 +39,7 @@ _SIGS = {
                               _vp, _vp, _vp, _vp, _vp],
     "seald_occupancy_coarse_bits": [_vp, _u32, _vp, _vp],
     "seald_render_init_pack": [_vp, _vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
+    "seald_render_finish": [_vp, _vp, _vp, _vp, _vp, _u32, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "seald_composite_rays_pack": [_u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _vp],
     "seald_composite_rays_compact": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
     "seald_render_schedule": [_vp, _vp, _u32, _u32, _u32, _vp],

@@ -2260,6 +2260,41 @@ extern "C" int seald_occupancy_coarse_bits(const uint8_t* bitfield, uint32_t H, 
     return launch_status();
 }
 
+// Frame epilogue in one launch (the reference: seven torch ops, dnerf/renderer.py:378-384): image = acc + (1 - weights_sum) * bg,
+// depth = clamp(depth - near, 0) / (far - near) (or raw), weights_sum copied out; written to separate tensors and / or as packed rows
+// {r, g, b, depth, weights_sum} (the all-gather input of the tile-sharded multi-GPU frame).  Same roundings as the torch expressions
+// (no contraction).
+__global__ void k_render_finish(const float* __restrict__ image, const float* __restrict__ weights_sum, const float* __restrict__ depth,
+                                const float* __restrict__ nears, const float* __restrict__ fars, const uint32_t N, const float bg,
+                                const int normalize, float* __restrict__ out_image, float* __restrict__ out_depth,
+                                float* __restrict__ out_ws, float* __restrict__ out_packed) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ws = weights_sum[n];
+    const float a = __fmul_rn(__fsub_rn(1.0f, ws), bg);
+    const float r = __fadd_rn(image[(size_t)n * 3], a), g = __fadd_rn(image[(size_t)n * 3 + 1], a), b = __fadd_rn(image[(size_t)n * 3 + 2], a);
+    float d = depth[n];
+    if (normalize) d = __fdiv_rn(fmaxf(__fsub_rn(d, nears[n]), 0.0f), __fsub_rn(fars[n], nears[n]));
+    if (out_image) { out_image[(size_t)n * 3] = r; out_image[(size_t)n * 3 + 1] = g; out_image[(size_t)n * 3 + 2] = b; }
+    if (out_depth) out_depth[n] = d;
+    if (out_ws) out_ws[n] = ws;
+    if (out_packed) {
+        float* o = out_packed + (size_t)n * 5;
+        o[0] = r; o[1] = g; o[2] = b; o[3] = d; o[4] = ws;
+    }
+}
+
+extern "C" int seald_render_finish(const float* image, const float* weights_sum, const float* depth, const float* nears, const float* fars,
+                                   uint32_t N, float bg, int normalize_depth, float* out_image, float* out_depth, float* out_ws,
+                                   float* out_packed5, seald_stream_t stream) {
+    if (N == 0) return 0;
+    if (!image || !weights_sum || !depth || (normalize_depth && (!nears || !fars))) return SEALD_E_BADARG;
+    if (!out_image && !out_depth && !out_ws && !out_packed5) return SEALD_E_BADARG;
+    k_render_finish<<<div_up(N, 256u), 256, 0, to_stream(stream)>>>(image, weights_sum, depth, nears, fars, N, bg, normalize_depth, out_image,
+                                                                    out_depth, out_ws, out_packed5);
+    return launch_status();
+}
+
 extern "C" int seald_composite_rays_pack(uint32_t n_alive, float T_thresh, const int32_t* rays_alive, float* rays_t, const float* sigmas,
                                          const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
                                          int32_t* next_alive, int32_t* state, int32_t* counters2, const int32_t* ray_rows, uint32_t budget,

@@ -203,7 +203,7 @@ class FusedRenderer:
 
     @torch.no_grad()
     def render(self, rays_o, rays_d, time, bg_color=None, perturb=False, dt_gamma=0, max_steps=1024, T_thresh=None, normalize_depth=None,
-               **kwargs):
+               _packed_out=None, **kwargs):
         """rays_o, rays_d [..., 3] (<= max_rays rays); time [1,1] or float -> dict(image [...,3], depth [...], weights_sum [N]).
 
         The loop runs without host synchronisation: round sizes (n_alive, n_step = clamp(N // n_alive, 1, 8)) live on the
@@ -224,8 +224,9 @@ class FusedRenderer:
             bg_color = 1
         opts = {"perturb": bool(perturb), "dt_gamma": float(dt_gamma), "max_steps": int(max_steps), "T_thresh": float(T_thresh)}
         st = _lib.stream()
-        self.rays_o[:N].copy_(rays_o.reshape(-1, 3), non_blocking=True)
-        self.rays_d[:N].copy_(rays_d.reshape(-1, 3), non_blocking=True)
+        if rays_o.data_ptr() != self.rays_o.data_ptr():  # (render_sharded gathers its tiles straight into the staging buffers)
+            self.rays_o[:N].copy_(rays_o.reshape(-1, 3), non_blocking=True)
+            self.rays_d[:N].copy_(rays_d.reshape(-1, 3), non_blocking=True)
         if torch.is_tensor(time):
             self.time.copy_(time.reshape(-1)[:1])
             t_idx = m._frame_index(self.time.view(1, 1))  # (device scalar -> index: the same host sync as the reference, renderer.py:285)
@@ -285,9 +286,23 @@ class FusedRenderer:
         torch.cuda.current_stream().synchronize()
         self.iterations, self.samples, self.launches = int(self.h_state[5]), int(self.h_state[4]), launches
         self.deferred = int(self.h_state[2]) if self.pack else 0  # rays a packed round could not fit and marched one round later
+        if isinstance(bg_color, (int, float)):
+            # epilogue in one launch (background blend, depth normalisation, copies out of the persistent accumulators)
+            if _packed_out is not None:  # tile-sharded frame: rows {r, g, b, depth, weights_sum} straight into the all-gather input
+                _lib.call("seald_render_finish", ptr(image), ptr(ws_out), ptr(depth), ptr(nears), ptr(fars), N, float(bg_color),
+                          int(bool(normalize_depth)), None, None, None, ptr(_packed_out), st)
+                return {"packed": _packed_out}
+            o_img, o_dep, o_ws = torch.empty_like(image), torch.empty_like(depth), torch.empty_like(ws_out)
+            _lib.call("seald_render_finish", ptr(image), ptr(ws_out), ptr(depth), ptr(nears), ptr(fars), N, float(bg_color),
+                      int(bool(normalize_depth)), ptr(o_img), ptr(o_dep), ptr(o_ws), None, st)
+            return {"image": o_img.view(*prefix, 3), "depth": o_dep.view(*prefix), "weights_sum": o_ws}
         image = image + (1 - ws_out).unsqueeze(-1) * bg_color
         depth_out = torch.clamp(depth - nears, min=0) / (fars - nears) if normalize_depth else depth.clone()
-        return {"image": image.view(*prefix, 3), "depth": depth_out.view(*prefix), "weights_sum": ws_out.clone()}
+        out = {"image": image.view(*prefix, 3), "depth": depth_out.view(*prefix), "weights_sum": ws_out.clone()}
+        if _packed_out is not None:
+            _packed_out[:N] = torch.cat([out["image"].view(-1, 3), out["depth"].view(-1, 1), out["weights_sum"].view(-1, 1)], dim=1)
+            return {"packed": _packed_out}
+        return out
 
     @torch.no_grad()
     def render_one_pass(self, rays_o, rays_d, time, bg_color=None, dt_gamma=0, max_steps=1024, T_thresh=None, normalize_depth=None, **kwargs):
@@ -379,8 +394,16 @@ class FusedRenderer:
         if getattr(self, "_shard_key", None) != key:  # cached: building the index on the host costs more than the render
             self._shard_idx = parallel.shard_tiles(N, world_size, rank, tile).to(rays_o.device)
             self._shard_key = key
+            cap = parallel.shard_capacity(N, world_size, tile)
+            self._gather_in = torch.zeros(cap, 5, dtype=torch.float32, device=rays_o.device)   # rows past this rank's share stay zero
+            self._gather_out = torch.empty(world_size * cap, 5, dtype=torch.float32, device=rays_o.device)
         idx = self._shard_idx
-        out = self.render(rays_o.index_select(0, idx), rays_d.index_select(0, idx), time, **kwargs)
-        local = torch.cat([out["image"].view(-1, 3), out["depth"].view(-1, 1), out["weights_sum"].view(-1, 1)], dim=1)
-        full = parallel.gather_frame(local, N, rank, world_size, group, tile)
-        return {"image": full[:, :3].contiguous(), "depth": full[:, 3].contiguous(), "weights_sum": full[:, 4].contiguous()}
+        n = idx.shape[0]
+        # this rank's tiles gathered straight into the staging buffers; the render's epilogue writes {r, g, b, depth, weights_sum} rows
+        # into the all-gather input; one index pass puts the gathered rows back into ray order (the outputs are VIEWS of that tensor)
+        torch.index_select(rays_o, 0, idx, out=self.rays_o[:n])
+        torch.index_select(rays_d, 0, idx, out=self.rays_d[:n])
+        self.render(self.rays_o[:n], self.rays_d[:n], time, _packed_out=self._gather_in, **kwargs)
+        torch.distributed.all_gather_into_tensor(self._gather_out, self._gather_in, group=group)
+        full = self._gather_out.index_select(0, parallel.unshard_index(N, world_size, tile, rays_o.device))
+        return {"image": full[:, :3], "depth": full[:, 3], "weights_sum": full[:, 4]}
